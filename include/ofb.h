@@ -1,0 +1,185 @@
+/* ofb.h — C ABI of libofb.so, the B200 (sm_100a) dense/sparse optical-flow engine.
+ *
+ * Drop-in boundary for the per-frame-pair flow call of the ROS 2 image-subscriber
+ * nodes of Hagestregen/OpticalFlowContainer.  The reference has no FFI for this
+ * path: the boundary is the expression at the node's flow call,
+ *   ros2_ws/src/liteflownet3/liteflownet3/lfn3_sub_node.py:194   flow = self.net(t1,t2)
+ *   ros2_ws/src/optical_flow/optical_flow/opticalflow_node.py:87
+ *   ros2_ws/src/pwc_net/pwc_net/pwc_sub_node.py:183
+ *   ros2_ws/src/liteflownet3/liteflownet3/lfn3_node.py:184
+ * which a Farneback/LK node fills with cv2.calcOpticalFlowFarneback /
+ * cv2.goodFeaturesToTrack / cv2.calcOpticalFlowPyrLK (OpenCV: un-vendored
+ * dependency, ros2_ws/src/nueflow/setup.py:29).  Each entry point below names the
+ * cv2 call (and the reference line it sits behind) that it replaces.  The
+ * reference's only native-binding precedent is the pybind module
+ * ros2_ws/src/liteflownet3/correlation_package/correlation_cuda.cc:169-172
+ * (free functions, caller-allocated outputs, int status) — the same conventions
+ * are kept here, minus the torch types.
+ *
+ * Conventions
+ *   - plain C, no C++ exceptions cross the ABI, never aborts; every function
+ *     returns an ofb_status (0 = OK) and records a message readable through
+ *     ofb_last_error().
+ *   - the caller owns every host/device array it passes; the library owns the
+ *     device work buffers and pinned staging buffers inside the handle.
+ *   - a handle is bound to one CUDA device and one stream; it is NOT re-entrant
+ *     (one call at a time per handle, from any thread); different handles are
+ *     independent (one per GPU / per camera stream).
+ *   - there is no CPU fallback: if no CUDA device is usable ofb_create fails.
+ */
+#ifndef OFB_H_
+#define OFB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* libofb.so is built with -fvisibility=hidden */
+#endif
+
+#define OFB_VERSION 100 /* 0.1.0 */
+
+typedef enum ofb_status {
+  OFB_OK = 0,
+  OFB_ERR_INVALID_ARG = 1, /* cv2 would raise cv::Exception (bad size/type/flags) */
+  OFB_ERR_CUDA = 2,        /* a CUDA runtime call or kernel launch failed */
+  OFB_ERR_NO_DEVICE = 3,   /* no usable CUDA device: there is no CPU fallback */
+  OFB_ERR_CAPACITY = 4,    /* frame or batch larger than the handle was created for */
+  OFB_ERR_ALLOC = 5
+} ofb_status;
+
+/* cv2 flag values (cv2.OPTFLOW_*), identical numbers */
+#define OFB_OPTFLOW_USE_INITIAL_FLOW 4
+#define OFB_OPTFLOW_LK_GET_MIN_EIGENVALS 8
+#define OFB_OPTFLOW_FARNEBACK_GAUSSIAN 256
+
+typedef struct ofb_handle ofb_handle;
+
+/* cv2.calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize,
+ *                              iterations, poly_n, poly_sigma, flags) — same meaning, same order. */
+typedef struct ofb_farneback_params {
+  double pyr_scale; /* < 1 */
+  int levels;       /* cv2 semantics: levels+1 scales, clamped so the coarsest is >= 32 px */
+  int winsize;
+  int iterations;
+  int poly_n;
+  double poly_sigma;
+  int flags; /* 0 | OFB_OPTFLOW_USE_INITIAL_FLOW | OFB_OPTFLOW_FARNEBACK_GAUSSIAN */
+} ofb_farneback_params;
+
+/* cv2.calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status, err,
+ *                          winSize, maxLevel, criteria, flags, minEigThreshold) */
+typedef struct ofb_lk_params {
+  int win_w, win_h;      /* winSize, default 21x21 */
+  int max_level;         /* default 3 */
+  int max_count;         /* criteria.maxCount, clamped to [0,100] as cv2 does */
+  double epsilon;        /* criteria.epsilon, clamped to [0,10], squared internally */
+  int flags;             /* 0 | OFB_OPTFLOW_USE_INITIAL_FLOW | OFB_OPTFLOW_LK_GET_MIN_EIGENVALS */
+  double min_eig_threshold; /* default 1e-4 */
+} ofb_lk_params;
+
+/* cv2.goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask,
+ *                         blockSize, useHarrisDetector=False, k) — Shi-Tomasi only. */
+typedef struct ofb_gftt_params {
+  int max_corners;
+  double quality_level;
+  double min_distance;
+  int block_size; /* 3 */
+} ofb_gftt_params;
+
+/* ---- lifetime ---------------------------------------------------------------- */
+int ofb_version(void);
+const char* ofb_status_string(int status);
+
+/* Creates an engine on CUDA device `device` able to process up to `max_batch`
+ * frame pairs of up to max_width x max_height per call.  Allocates all device
+ * work buffers and pinned staging buffers up front (nothing is allocated on the
+ * hot path). */
+int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_handle** out);
+int ofb_destroy(ofb_handle* h);
+/* Last error message of this handle (or of the failed ofb_create when h == NULL). */
+const char* ofb_last_error(const ofb_handle* h);
+/* The handle's CUDA stream (a cudaStream_t) so callers can order their own work. */
+void* ofb_stream(ofb_handle* h);
+int ofb_synchronize(ofb_handle* h);
+
+/* ---- Farneback: replaces cv2.calcOpticalFlowFarneback at lfn3_sub_node.py:194 -- */
+
+/* Host-buffer call, synchronous: uploads prev/next (uint8, `stride_bytes` per row)
+ * through pinned staging on the handle's stream, runs all levels, downloads
+ * flow (float32 [height][width][2] = (dx,dy), `flow_stride_bytes` per row, 0 =
+ * packed).  With OFB_OPTFLOW_USE_INITIAL_FLOW `flow` is read as the initial
+ * estimate first (as cv2 does with its in/out `flow` argument). */
+int ofb_farneback(ofb_handle* h, const uint8_t* prev, const uint8_t* next, int width, int height,
+                  size_t stride_bytes, float* flow, size_t flow_stride_bytes,
+                  const ofb_farneback_params* params);
+
+/* Batched host-buffer call: n independent pairs (n <= max_batch); prev[i], next[i],
+ * flow[i] as above.  One upload, one batched launch sequence, one download. */
+int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next,
+                        int width, int height, size_t stride_bytes, float* const* flow,
+                        size_t flow_stride_bytes, const ofb_farneback_params* params);
+
+/* Device-resident call, asynchronous on the handle's stream: d_prev/d_next are n
+ * uint8 images (row pitch `pitch_bytes`, image i at + i*image_stride_bytes);
+ * d_flow is n packed float32 [height][width][2] fields.  Returns after enqueueing. */
+int ofb_farneback_device(ofb_handle* h, int n, const uint8_t* d_prev, const uint8_t* d_next, int width,
+                         int height, size_t pitch_bytes, size_t image_stride_bytes, float* d_flow,
+                         const ofb_farneback_params* params);
+
+/* Camera-stream call (consecutive frames of ONE stream: pair i = (frame i, frame i+1)):
+ * d_frames holds n+1 frames; the polynomial expansion of each frame is computed
+ * once and shared by the two pairs it belongs to.  Results are identical to n
+ * independent ofb_farneback_device pairs. */
+int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_frames, int width,
+                                  int height, size_t pitch_bytes, size_t image_stride_bytes,
+                                  float* d_flow, const ofb_farneback_params* params);
+
+/* Number of kernel launches this handle has enqueued since creation (bench evidence). */
+uint64_t ofb_launch_count(const ofb_handle* h);
+
+/* ---- on-device reduction of the flow field (the node contract) ----------------
+ * Every reference node collapses the field to one scalar right after the flow
+ * call (lfn3_sub_node.py:205-212: np.median(flow_np[0]); opticalflow_node.py:98:
+ * np.mean(flow_np[0]); masked: sub_n_pub_lfn3_node.py:195-210).  These reduce the
+ * most recent flow field(s) held on the device, so the 8N-byte D2H is avoided.
+ * mask: optional uint8 [height][width] host array (non-zero = use), NULL = all.
+ * out_mean / out_median: n values (u component); either may be NULL. */
+int ofb_flow_u_stats(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median);
+
+/* ---- sparse path: replaces cv2.goodFeaturesToTrack + cv2.calcOpticalFlowPyrLK -- */
+
+/* Shi-Tomasi corners of a uint8 image (host buffer).  corners_xy: capacity
+ * max_corners*2 floats, receives (x,y) pairs in cv2's order; *n_out their count. */
+int ofb_good_features(ofb_handle* h, const uint8_t* image, int width, int height, size_t stride_bytes,
+                      const ofb_gftt_params* params, float* corners_xy, int* n_out);
+
+/* cv2.cornerMinEigenVal(image, blockSize=3, ksize=3) — exposed for bit-exact parity tests. */
+int ofb_corner_min_eigenval(ofb_handle* h, const uint8_t* image, int width, int height,
+                            size_t stride_bytes, int block_size, float* eig_out);
+
+/* cv2.buildOpticalFlowPyramid levels as a cv2.pyrDown chain (uint8, bit-exact) and
+ * the Scharr derivative images (int16 [h][w][2] = (dx,dy), bit-exact).
+ * level_out[l] (may be NULL) receives packed uint8 [h_l][w_l]; deriv_out[l] (may be
+ * NULL) packed int16 [h_l][w_l][2]; *n_levels_out the number of levels built. */
+int ofb_lk_pyramid(ofb_handle* h, const uint8_t* image, int width, int height, size_t stride_bytes,
+                   int win_w, int win_h, int max_level, uint8_t* const* level_out,
+                   int16_t* const* deriv_out, int* n_levels_out);
+
+/* Pyramidal Lucas-Kanade.  prev_pts/next_pts: n_points (x,y) float pairs; next_pts is
+ * read as the initial guess when OFB_OPTFLOW_USE_INITIAL_FLOW is set; status: n bytes;
+ * err: n floats (may be NULL). */
+int ofb_pyrlk(ofb_handle* h, const uint8_t* prev, const uint8_t* next, int width, int height,
+              size_t stride_bytes, const float* prev_pts, int n_points, float* next_pts,
+              uint8_t* status, float* err, const ofb_lk_params* params);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFB_H_ */

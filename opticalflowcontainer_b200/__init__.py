@@ -1,0 +1,89 @@
+"""opticalflowcontainer_b200 — B200-native drop-in for the per-frame-pair OpenCV flow call.
+
+Same Python signatures as cv2 (``calcOpticalFlowFarneback``, ``calcOpticalFlowPyrLK``,
+``goodFeaturesToTrack``) so a node shaped like
+``ros2_ws/src/liteflownet3/liteflownet3/lfn3_sub_node.py`` swaps ``import cv2`` for
+``import opticalflowcontainer_b200 as ofb`` at the flow call (line 194) and nothing else.
+All arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of ``libofb.so``
+(``include/ofb.h``).  There is no CPU fallback: without the built library or a CUDA device
+every call raises.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from ._lib import OfbError, LIB_PATH, EXPORTED_SYMBOLS  # noqa: F401
+from .engine import (FlowEngine, OPTFLOW_FARNEBACK_GAUSSIAN, OPTFLOW_LK_GET_MIN_EIGENVALS,  # noqa: F401
+                     OPTFLOW_USE_INITIAL_FLOW)
+
+__all__ = ["FlowEngine", "OfbError", "calcOpticalFlowFarneback", "calcOpticalFlowPyrLK", "goodFeaturesToTrack",
+           "buildOpticalFlowPyramid", "cornerMinEigenVal", "OPTFLOW_USE_INITIAL_FLOW", "OPTFLOW_FARNEBACK_GAUSSIAN",
+           "OPTFLOW_LK_GET_MIN_EIGENVALS", "set_device"]
+
+_engines = {}
+_engines_lock = threading.Lock()
+_device = 0
+
+
+def set_device(device: int):
+    """Device used by the module-level cv2-style functions (one engine per (device, size))."""
+    global _device
+    _device = int(device)
+
+
+def _engine_for(h: int, w: int) -> FlowEngine:
+    key = (_device, h, w)
+    with _engines_lock:
+        e = _engines.get(key)
+        if e is None:
+            e = FlowEngine(w, h, max_batch=1, device=_device)
+            _engines[key] = e
+        return e
+
+
+def calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags):
+    """Drop-in for ``cv2.calcOpticalFlowFarneback`` → float32 [H,W,2]."""
+    prev = np.asarray(prev)
+    return _engine_for(prev.shape[0], prev.shape[1]).farneback(prev, next, flow, pyr_scale, levels, winsize,
+                                                               iterations, poly_n, poly_sigma, flags)
+
+
+def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None, blockSize=3,
+                        useHarrisDetector=False, k=0.04):
+    """Drop-in for ``cv2.goodFeaturesToTrack`` (Shi-Tomasi; no mask / Harris)."""
+    if mask is not None or useHarrisDetector:
+        raise OfbError(1, "goodFeaturesToTrack: mask and useHarrisDetector are not supported")
+    image = np.asarray(image)
+    r = _engine_for(image.shape[0], image.shape[1]).good_features(image, maxCorners, qualityLevel, minDistance,
+                                                                  blockSize)
+    return r if len(r) else None
+
+
+def cornerMinEigenVal(src, blockSize, ksize=3):
+    if ksize != 3:
+        raise OfbError(1, "cornerMinEigenVal: only ksize=3 is supported")
+    src = np.asarray(src)
+    return _engine_for(src.shape[0], src.shape[1]).corner_min_eigenval(src, blockSize)
+
+
+def buildOpticalFlowPyramid(img, winSize, maxLevel, withDerivatives=True):
+    """Returns (maxLevel_built, [level0, deriv0, level1, deriv1, ...]) like cv2 (without the
+    winSize border cv2 pads its pyramid Mats with)."""
+    img = np.asarray(img)
+    lv, dv = _engine_for(img.shape[0], img.shape[1]).lk_pyramid(img, winSize, maxLevel, withDerivatives)
+    out = []
+    for i, l in enumerate(lv):
+        out.append(l)
+        if withDerivatives:
+            out.append(dv[i])
+    return len(lv) - 1, out
+
+
+def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=None, winSize=(21, 21), maxLevel=3,
+                         criteria=(3, 30, 0.01), flags=0, minEigThreshold=1e-4):
+    """Drop-in for ``cv2.calcOpticalFlowPyrLK`` → (nextPts [N,1,2], status [N,1], err [N,1])."""
+    prevImg = np.asarray(prevImg)
+    return _engine_for(prevImg.shape[0], prevImg.shape[1]).pyrlk(prevImg, nextImg, prevPts, nextPts, winSize, maxLevel,
+                                                                criteria, flags, minEigThreshold)

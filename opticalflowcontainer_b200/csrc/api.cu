@@ -1,0 +1,256 @@
+// api.cu — the C ABI of libofb.so (include/ofb.h): handle lifetime, argument validation with
+// cv2's error behaviour, pinned-host staging and the host/device entry points of the dense path.
+#include <stdarg.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace ofb {
+
+thread_local std::string g_create_error;
+
+int set_error(ofb_handle* h, int status, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return status;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// cv2 argument checks of calcOpticalFlowFarneback (optflowgf.cpp: CV_Assert lines) — INVALID_ARG
+// where cv2 raises cv::error.
+static int validate_farneback(ofb_handle* h, int n, int width, int height, const ofb_farneback_params* p) {
+  if (!p) return set_error(h, OFB_ERR_INVALID_ARG, "params is NULL");
+  if (n < 1) return set_error(h, OFB_ERR_INVALID_ARG, "need at least one frame pair");
+  if (width < 1 || height < 1) return set_error(h, OFB_ERR_INVALID_ARG, "empty image");
+  if (n > h->max_batch || width > h->max_w || height > h->max_h || (size_t)width * height > (size_t)h->max_w * h->max_h)
+    return set_error(h, OFB_ERR_CAPACITY, "request %d x %dx%d exceeds handle capacity %d x %dx%d", n, width, height,
+                     h->max_batch, h->max_w, h->max_h);
+  if (!(p->pyr_scale > 0.0 && p->pyr_scale < 1.0))
+    return set_error(h, OFB_ERR_INVALID_ARG, "pyr_scale must be in (0,1)");
+  if (p->levels < 0) return set_error(h, OFB_ERR_INVALID_ARG, "levels must be >= 0");
+  if (p->iterations < 0) return set_error(h, OFB_ERR_INVALID_ARG, "iterations must be >= 0");
+  if (p->winsize < 1 || p->winsize / 2 > kMaxBlurRadius)
+    return set_error(h, OFB_ERR_INVALID_ARG, "winsize must be in [1,%d]", 2 * kMaxBlurRadius + 1);
+  if (p->poly_n < 1 || p->poly_n > kMaxPolyN)
+    return set_error(h, OFB_ERR_INVALID_ARG, "poly_n must be in [1,%d]", kMaxPolyN);
+  if (p->flags & ~(OFB_OPTFLOW_USE_INITIAL_FLOW | OFB_OPTFLOW_FARNEBACK_GAUSSIAN))
+    return set_error(h, OFB_ERR_INVALID_ARG, "unsupported flags 0x%x", p->flags);
+  return OFB_OK;
+}
+
+}  // namespace ofb
+
+using namespace ofb;
+
+extern "C" {
+
+int ofb_version(void) { return OFB_VERSION; }
+
+const char* ofb_status_string(int s) {
+  switch (s) {
+    case OFB_OK: return "OK";
+    case OFB_ERR_INVALID_ARG: return "invalid argument";
+    case OFB_ERR_CUDA: return "CUDA error";
+    case OFB_ERR_NO_DEVICE: return "no usable CUDA device (libofb has no CPU fallback)";
+    case OFB_ERR_CAPACITY: return "request exceeds handle capacity";
+    case OFB_ERR_ALLOC: return "allocation failed";
+    default: return "unknown status";
+  }
+}
+
+const char* ofb_last_error(const ofb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void* ofb_stream(ofb_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+uint64_t ofb_launch_count(const ofb_handle* h) { return h ? h->launches : 0; }
+
+int ofb_synchronize(ofb_handle* h) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+int ofb_destroy(ofb_handle* h) {
+  if (!h) return OFB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  sparse_destroy(h);
+  cudaFree(h->d_src); cudaFree(h->d_img); cudaFree(h->d_RA); cudaFree(h->d_RB);
+  cudaFree(h->d_MA); cudaFree(h->d_MB); cudaFree(h->d_VA); cudaFree(h->d_VB);
+  for (int i = 0; i < 3; i++) cudaFree(h->d_flow[i]);
+  cudaFree(h->d_flow_out); cudaFree(h->d_init_flow); cudaFree(h->d_stats); cudaFree(h->d_mask);
+  cudaFree(h->d_scratch);
+  if (h->h_src) cudaFreeHost(h->h_src);
+  if (h->h_flow) cudaFreeHost(h->h_flow);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return OFB_OK;
+}
+
+int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_handle** out) {
+  if (!out) return set_error(nullptr, OFB_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (max_width < 1 || max_height < 1 || max_batch < 1)
+    return set_error(nullptr, OFB_ERR_INVALID_ARG, "max_width, max_height, max_batch must be >= 1");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return set_error(nullptr, OFB_ERR_NO_DEVICE, "no CUDA device: %s (libofb has no CPU fallback)",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= count)
+    return set_error(nullptr, OFB_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
+  ofb_handle* h = new (std::nothrow) ofb_handle();
+  if (!h) return set_error(nullptr, OFB_ERR_ALLOC, "out of host memory");
+  h->device = device;
+  h->max_w = max_width;
+  h->max_h = max_height;
+  h->max_batch = max_batch;
+#define CREATE_CUDA(call)                                                                      \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      int st__ = set_error(nullptr, e__ == cudaErrorMemoryAllocation ? OFB_ERR_ALLOC : OFB_ERR_CUDA, \
+                           "%s failed: %s", #call, cudaGetErrorString(e__));                   \
+      ofb_destroy(h);                                                                          \
+      return st__;                                                                             \
+    }                                                                                          \
+  } while (0)
+  CREATE_CUDA(cudaSetDevice(device));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const size_t N = (size_t)max_width * max_height;
+  const size_t frames = 2 * (size_t)max_batch;
+  h->src_pitch = align_up((size_t)max_width, 256);
+  h->src_image_stride = h->src_pitch * max_height;
+  CREATE_CUDA(cudaMalloc(&h->d_src, h->src_image_stride * frames));
+  CREATE_CUDA(cudaMalloc(&h->d_img, frames * N * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_RA, frames * N * sizeof(float4)));
+  CREATE_CUDA(cudaMalloc(&h->d_RB, frames * N * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_MA, max_batch * N * sizeof(float4)));
+  CREATE_CUDA(cudaMalloc(&h->d_MB, max_batch * N * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_VA, max_batch * N * sizeof(float4)));
+  CREATE_CUDA(cudaMalloc(&h->d_VB, max_batch * N * sizeof(float)));
+  for (int i = 0; i < 2; i++) CREATE_CUDA(cudaMalloc(&h->d_flow[i], max_batch * N * sizeof(float2)));
+  CREATE_CUDA(cudaMalloc(&h->d_flow_out, max_batch * N * sizeof(float2)));
+  CREATE_CUDA(cudaMalloc(&h->d_init_flow, max_batch * N * sizeof(float2)));
+  CREATE_CUDA(cudaMalloc(&h->d_stats, 64 * sizeof(double) * (size_t)max_batch));
+  CREATE_CUDA(cudaMalloc(&h->d_mask, N));
+  h->h_src_bytes = h->src_image_stride * frames;
+  h->h_flow_bytes = max_batch * N * sizeof(float2);
+  CREATE_CUDA(cudaHostAlloc(&h->h_src, h->h_src_bytes, cudaHostAllocDefault));
+  CREATE_CUDA(cudaHostAlloc(&h->h_flow, h->h_flow_bytes, cudaHostAllocDefault));
+#undef CREATE_CUDA
+  *out = h;
+  return OFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense path entry points
+// ------------------------------------------------------------------------------------------
+int ofb_farneback_device(ofb_handle* h, int n, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
+                         size_t pitch_bytes, size_t image_stride_bytes, float* d_flow,
+                         const ofb_farneback_params* params) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!d_prev || !d_next || !d_flow) return set_error(h, OFB_ERR_INVALID_ARG, "NULL device pointer");
+  int st = validate_farneback(h, n, width, height, params);
+  if (st) return st;
+  if (pitch_bytes < (size_t)width) return set_error(h, OFB_ERR_INVALID_ARG, "pitch smaller than width");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  const float* init = nullptr;
+  if (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
+    // cv2 semantics: `flow` is in/out.  Copy the initial estimate aside (d_flow is overwritten last).
+    OFB_CUDA(h, cudaMemcpyAsync(h->d_init_flow, d_flow, (size_t)n * width * height * sizeof(float2),
+                                cudaMemcpyDeviceToDevice, h->stream));
+    init = h->d_init_flow;
+  }
+  return farneback_run(h, n, false, d_prev, d_next, width, height, pitch_bytes, image_stride_bytes, d_flow, init,
+                       params);
+}
+
+int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_frames, int width, int height,
+                                  size_t pitch_bytes, size_t image_stride_bytes, float* d_flow,
+                                  const ofb_farneback_params* params) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!d_frames || !d_flow) return set_error(h, OFB_ERR_INVALID_ARG, "NULL device pointer");
+  int st = validate_farneback(h, n_pairs, width, height, params);
+  if (st) return st;
+  if (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
+    return set_error(h, OFB_ERR_INVALID_ARG, "USE_INITIAL_FLOW is not supported by the sequence call");
+  if (pitch_bytes < (size_t)width) return set_error(h, OFB_ERR_INVALID_ARG, "pitch smaller than width");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  return farneback_run(h, n_pairs, true, d_frames, d_frames, width, height, pitch_bytes, image_stride_bytes, d_flow,
+                       nullptr, params);
+}
+
+int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next, int width,
+                        int height, size_t stride_bytes, float* const* flow, size_t flow_stride_bytes,
+                        const ofb_farneback_params* params) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!prev || !next || !flow) return set_error(h, OFB_ERR_INVALID_ARG, "NULL array pointer");
+  int st = validate_farneback(h, n, width, height, params);
+  if (st) return st;
+  if (stride_bytes == 0) stride_bytes = (size_t)width;
+  if (stride_bytes < (size_t)width) return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than width");
+  const size_t row_flow = (size_t)width * 2 * sizeof(float);
+  if (flow_stride_bytes == 0) flow_stride_bytes = row_flow;
+  if (flow_stride_bytes < row_flow) return set_error(h, OFB_ERR_INVALID_ARG, "flow stride smaller than a row");
+  for (int i = 0; i < n; i++)
+    if (!prev[i] || !next[i] || !flow[i]) return set_error(h, OFB_ERR_INVALID_ARG, "NULL image/flow pointer");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  // stage into pinned memory (packed rows of `pitch`), one async upload
+  const size_t pitch = align_up((size_t)width, 16);
+  const size_t istride = pitch * height;
+  for (int i = 0; i < n; i++)
+    for (int img = 0; img < 2; img++) {
+      const uint8_t* s = img ? next[i] : prev[i];
+      uint8_t* d = h->h_src + (size_t)(img * n + i) * istride;
+      if (stride_bytes == pitch) memcpy(d, s, istride);
+      else for (int y = 0; y < height; y++) memcpy(d + (size_t)y * pitch, s + (size_t)y * stride_bytes, width);
+    }
+  OFB_CUDA(h, cudaMemcpyAsync(h->d_src, h->h_src, istride * 2 * n, cudaMemcpyHostToDevice, h->stream));
+  const float* init = nullptr;
+  const size_t fl_img = (size_t)width * height * 2;
+  if (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
+    for (int i = 0; i < n; i++)
+      for (int y = 0; y < height; y++)
+        memcpy(h->h_flow + i * fl_img + (size_t)y * width * 2, (const char*)flow[i] + (size_t)y * flow_stride_bytes,
+               row_flow);
+    OFB_CUDA(h, cudaMemcpyAsync(h->d_init_flow, h->h_flow, n * fl_img * sizeof(float), cudaMemcpyHostToDevice,
+                                h->stream));
+    init = h->d_init_flow;
+  }
+  st = farneback_run(h, n, false, h->d_src, h->d_src + (size_t)n * istride, width, height, pitch, istride,
+                     h->d_flow_out, init, params);
+  if (st) return st;
+  OFB_CUDA(h, cudaMemcpyAsync(h->h_flow, h->d_flow_out, n * fl_img * sizeof(float), cudaMemcpyDeviceToHost,
+                              h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; i++) {
+    if (flow_stride_bytes == row_flow) memcpy(flow[i], h->h_flow + i * fl_img, fl_img * sizeof(float));
+    else
+      for (int y = 0; y < height; y++)
+        memcpy((char*)flow[i] + (size_t)y * flow_stride_bytes, h->h_flow + i * fl_img + (size_t)y * width * 2, row_flow);
+  }
+  return OFB_OK;
+}
+
+int ofb_farneback(ofb_handle* h, const uint8_t* prev, const uint8_t* next, int width, int height, size_t stride_bytes,
+                  float* flow, size_t flow_stride_bytes, const ofb_farneback_params* params) {
+  const uint8_t* pp[1] = {prev};
+  const uint8_t* nn[1] = {next};
+  float* ff[1] = {flow};
+  return ofb_farneback_batch(h, 1, pp, nn, width, height, stride_bytes, ff, flow_stride_bytes, params);
+}
+
+int ofb_flow_u_stats(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  return flow_u_stats(h, n, mask, out_mean, out_median);
+}
+
+}  // extern "C"

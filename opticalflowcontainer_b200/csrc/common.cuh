@@ -1,0 +1,124 @@
+// common.cuh — shared declarations of libofb (B200 / sm_100a optical-flow engine).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ofb.h"
+
+namespace ofb {
+
+constexpr int kMaxLevels = 16;     // scales per call (cv2 clamps by the 32-px rule long before)
+constexpr int kMaxPolyN = 10;      // poly_n <= 10 (cv2 users: 5 or 7)
+constexpr int kMaxBlurRadius = 64; // winsize <= 129
+
+// One pyramid scale of the Farneback schedule (FarnebackOpticalFlowImpl::calc).
+struct Level {
+  int k;
+  double scale;
+  double sigma;
+  int ksize;
+  int width, height;
+};
+
+// Polynomial-expansion constants (FarnebackPrepareGaussian).
+struct PolyCoef {
+  int n;
+  float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
+  float ig11, ig03, ig33, ig55;
+};
+
+struct BlurCoef {
+  int m;               // radius = winsize / 2
+  float scale;         // box: 1 / winsize^2 ; gaussian: 1
+  int gaussian;
+  float k[kMaxBlurRadius + 1];  // box: all ones
+};
+
+inline int cv_round(double v) { return (int)__builtin_nearbyint(v); }  // round-half-even like cvRound
+
+}  // namespace ofb
+
+struct ofb_handle {
+  int device = 0;
+  int max_w = 0, max_h = 0, max_batch = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+
+  // device buffers (allocated once in ofb_create)
+  uint8_t* d_src = nullptr;       // staging for host API: [2*max_batch (+1)] images, pitch src_pitch
+  size_t src_pitch = 0, src_image_stride = 0;
+  float* d_img = nullptr;         // level images I: [frames][h][w] f32
+  float4* d_RA = nullptr;         // polynomial coefficients ch0..3: [frames][h][w] float4
+  float* d_RB = nullptr;          // polynomial coefficient ch4:     [frames][h][w] float
+  float4* d_MA = nullptr;         // generic path: matrix field ch0..3 / blurred
+  float* d_MB = nullptr;
+  float4* d_VA = nullptr;         // generic path: vertical-pass intermediate
+  float* d_VB = nullptr;
+  float2* d_flow[3] = {nullptr, nullptr, nullptr};  // ping/pong/previous-level, [batch][h][w] float2
+  float* d_flow_out = nullptr;    // staging for host API output [batch][H][W][2]
+  float* d_init_flow = nullptr;   // USE_INITIAL_FLOW input [batch][H][W][2]
+  // last result bookkeeping for ofb_flow_u_stats
+  const float* last_flow = nullptr;
+  int last_n = 0, last_w = 0, last_h = 0;
+  double* d_stats = nullptr;
+  uint8_t* d_mask = nullptr;
+  float* d_scratch = nullptr;  // median selection scratch
+  size_t scratch_bytes = 0;
+
+  // pinned host staging
+  uint8_t* h_src = nullptr;
+  float* h_flow = nullptr;
+  size_t h_src_bytes = 0, h_flow_bytes = 0;
+
+  // sparse path buffers are owned by lk.cu / features.cu state
+  void* sparse = nullptr;
+};
+
+namespace ofb {
+
+extern thread_local std::string g_create_error;
+
+int set_error(ofb_handle* h, int status, const char* fmt, ...);
+
+#define OFB_CUDA(h, call)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return ofb::set_error((h), OFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,              \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                   \
+  } while (0)
+
+#define OFB_LAUNCH_CHECK(h)                                                                 \
+  do {                                                                                      \
+    (h)->launches++;                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return ofb::set_error((h), OFB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",          \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                   \
+  } while (0)
+
+// ---- farneback.cu --------------------------------------------------------------------
+int build_schedule(int width, int height, double pyr_scale, int levels, Level* out, int* n_out);
+void prepare_poly(int n, double sigma, PolyCoef* pc);
+void prepare_blur(int winsize, bool gaussian, BlurCoef* bc);
+
+// Runs the whole multi-level schedule for n_pairs pairs on the handle's stream.
+//   sequence == false: frames are [prev_0..prev_{n-1}] at d_prev and [next_0..] at d_next
+//   sequence == true : d_prev holds n_pairs+1 consecutive frames (d_next ignored)
+int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
+                  int width, int height, size_t pitch, size_t image_stride, float* d_flow_out,
+                  const float* d_init_flow, const ofb_farneback_params* p);
+
+int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mean, float* out_median);
+
+// ---- sparse ---------------------------------------------------------------------------
+void sparse_destroy(ofb_handle* h);
+
+}  // namespace ofb

@@ -1,0 +1,234 @@
+"""Host-side engine object over the C ABI: one handle = one GPU + one CUDA stream.
+
+``FlowEngine`` owns an ``ofb_handle``; its methods take/return NumPy arrays (host path, what a
+ROS node calls) or raw device pointers / torch CUDA tensors (device path, used by ``bench.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import FarnebackParams, GfttParams, LKParams, OfbError
+
+OPTFLOW_USE_INITIAL_FLOW = 4
+OPTFLOW_LK_GET_MIN_EIGENVALS = 8
+OPTFLOW_FARNEBACK_GAUSSIAN = 256
+
+
+def _u8_image(a, name):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise OfbError(1, "%s must be a single-channel uint8 image [H,W] (got %s %s)" % (name, a.dtype, a.shape))
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class FlowEngine:
+    """A libofb handle.  Not re-entrant: calls are serialised with a lock (nodes call from one
+    thread at a time, possibly a non-main thread — ``lfn3_node.py:84-89``)."""
+
+    def __init__(self, max_width: int, max_height: int, max_batch: int = 1, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        st = self._lib.ofb_create(int(device), int(max_width), int(max_height), int(max_batch), C.byref(h))
+        _lib.check(st, None)
+        self._h = h
+        self.max_width, self.max_height, self.max_batch, self.device = max_width, max_height, max_batch, device
+        self._lock = threading.Lock()
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ofb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.ofb_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ofb_launch_count(self._h))
+
+    def synchronize(self):
+        _lib.check(self._lib.ofb_synchronize(self._h), self._h)
+
+    # -- dense
+    @staticmethod
+    def _fb_params(pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags) -> FarnebackParams:
+        return FarnebackParams(float(pyr_scale), int(levels), int(winsize), int(iterations), int(poly_n),
+                               float(poly_sigma), int(flags))
+
+    def farneback(self, prev, nxt, flow=None, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5,
+                  poly_sigma=1.2, flags=0) -> np.ndarray:
+        """cv2.calcOpticalFlowFarneback with host arrays → float32 [H,W,2]."""
+        prev = _u8_image(prev, "prev")
+        nxt = _u8_image(nxt, "next")
+        if prev.shape != nxt.shape:
+            raise OfbError(1, "prev and next must have the same size")
+        hgt, wid = prev.shape
+        if flags & OPTFLOW_USE_INITIAL_FLOW:
+            if flow is None or np.asarray(flow).shape != (hgt, wid, 2) or np.asarray(flow).dtype != np.float32:
+                raise OfbError(1, "OPTFLOW_USE_INITIAL_FLOW needs a float32 [H,W,2] flow")
+            out = np.ascontiguousarray(flow)
+        else:
+            if (isinstance(flow, np.ndarray) and flow.shape == (hgt, wid, 2) and flow.dtype == np.float32
+                    and flow.flags.c_contiguous):
+                out = flow
+            else:
+                out = np.empty((hgt, wid, 2), np.float32)
+        p = self._fb_params(pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags)
+        if prev.strides[0] != nxt.strides[0]:
+            prev, nxt = np.ascontiguousarray(prev), np.ascontiguousarray(nxt)
+        with self._lock:
+            st = self._lib.ofb_farneback(self._h, prev.ctypes.data, nxt.ctypes.data, wid, hgt, prev.strides[0],
+                                         out.ctypes.data, 0, C.byref(p))
+            _lib.check(st, self._h)
+        return out
+
+    def farneback_batch(self, prevs: Sequence[np.ndarray], nexts: Sequence[np.ndarray], **kw) -> np.ndarray:
+        """n independent pairs in one batched launch sequence → float32 [n,H,W,2]."""
+        n = len(prevs)
+        if n != len(nexts) or n == 0:
+            raise OfbError(1, "prevs and nexts must be equally long and non-empty")
+        prevs = [np.ascontiguousarray(_u8_image(a, "prev")) for a in prevs]
+        nexts = [np.ascontiguousarray(_u8_image(a, "next")) for a in nexts]
+        hgt, wid = prevs[0].shape
+        for a in prevs + nexts:
+            if a.shape != (hgt, wid):
+                raise OfbError(1, "all images of a batch must have the same size")
+        flags = int(kw.get("flags", 0))
+        out = np.empty((n, hgt, wid, 2), np.float32)
+        if flags & OPTFLOW_USE_INITIAL_FLOW:
+            out[...] = np.asarray(kw["flow"], np.float32)
+        p = self._fb_params(kw.get("pyr_scale", 0.5), kw.get("levels", 3), kw.get("winsize", 15),
+                            kw.get("iterations", 3), kw.get("poly_n", 5), kw.get("poly_sigma", 1.2), flags)
+        pp = (C.c_void_p * n)(*[a.ctypes.data for a in prevs])
+        nn = (C.c_void_p * n)(*[a.ctypes.data for a in nexts])
+        ff = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        with self._lock:
+            st = self._lib.ofb_farneback_batch(self._h, n, pp, nn, wid, hgt, wid, ff, 0, C.byref(p))
+            _lib.check(st, self._h)
+        return out
+
+    def farneback_device(self, n: int, d_prev: int, d_next: int, width: int, height: int, pitch: int,
+                         image_stride: int, d_flow: int, sequence: bool = False, **kw):
+        """Asynchronous device-pointer call on the handle's stream (see ofb_farneback_device /
+        ofb_farneback_sequence_device)."""
+        p = self._fb_params(kw.get("pyr_scale", 0.5), kw.get("levels", 3), kw.get("winsize", 15),
+                            kw.get("iterations", 3), kw.get("poly_n", 5), kw.get("poly_sigma", 1.2),
+                            kw.get("flags", 0))
+        with self._lock:
+            if sequence:
+                st = self._lib.ofb_farneback_sequence_device(self._h, n, d_prev, width, height, pitch, image_stride,
+                                                             d_flow, C.byref(p))
+            else:
+                st = self._lib.ofb_farneback_device(self._h, n, d_prev, d_next, width, height, pitch, image_stride,
+                                                    d_flow, C.byref(p))
+            _lib.check(st, self._h)
+
+    def flow_u_stats(self, n: int = 1, mask: Optional[np.ndarray] = None, mean=True, median=True):
+        """Mean / median of the u component of the most recent flow field(s), reduced on the
+        device (the node contract, lfn3_sub_node.py:205-212)."""
+        om = (C.c_double * n)() if mean else None
+        od = (C.c_float * n)() if median else None
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
+            mp = mask.ctypes.data
+        with self._lock:
+            st = self._lib.ofb_flow_u_stats(self._h, n, mp, om, od)
+            _lib.check(st, self._h)
+        return (list(om) if mean else None), (list(od) if median else None)
+
+    # -- sparse
+    def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3) -> np.ndarray:
+        image = _u8_image(image, "image")
+        hgt, wid = image.shape
+        cap = int(maxCorners) if maxCorners > 0 else hgt * wid
+        out = np.empty((max(cap, 1), 2), np.float32)
+        n = C.c_int(0)
+        p = GfttParams(int(maxCorners), float(qualityLevel), float(minDistance), int(blockSize))
+        with self._lock:
+            st = self._lib.ofb_good_features(self._h, image.ctypes.data, wid, hgt, image.strides[0], C.byref(p),
+                                             out.ctypes.data, C.byref(n))
+            _lib.check(st, self._h)
+        return out[:n.value].reshape(-1, 1, 2).copy()
+
+    def corner_min_eigenval(self, image, blockSize=3) -> np.ndarray:
+        image = _u8_image(image, "image")
+        hgt, wid = image.shape
+        out = np.empty((hgt, wid), np.float32)
+        with self._lock:
+            st = self._lib.ofb_corner_min_eigenval(self._h, image.ctypes.data, wid, hgt, image.strides[0],
+                                                   int(blockSize), out.ctypes.data)
+            _lib.check(st, self._h)
+        return out
+
+    def lk_pyramid(self, image, winSize=(21, 21), maxLevel=3, with_derivatives=True):
+        """(levels, derivs): uint8 pyrDown chain and int16 Scharr (dx,dy) per level."""
+        image = _u8_image(image, "image")
+        hgt, wid = image.shape
+        sizes = [(hgt, wid)]
+        for _ in range(maxLevel):
+            sizes.append(((sizes[-1][0] + 1) // 2, (sizes[-1][1] + 1) // 2))
+        lv = [np.empty(s, np.uint8) for s in sizes]
+        dv = [np.empty(s + (2,), np.int16) for s in sizes] if with_derivatives else None
+        lp = (C.c_void_p * len(lv))(*[a.ctypes.data for a in lv])
+        dp = (C.c_void_p * len(lv))(*[a.ctypes.data for a in dv]) if dv else None
+        n = C.c_int(0)
+        with self._lock:
+            st = self._lib.ofb_lk_pyramid(self._h, image.ctypes.data, wid, hgt, image.strides[0], int(winSize[0]),
+                                          int(winSize[1]), int(maxLevel), lp, dp, C.byref(n))
+            _lib.check(st, self._h)
+        return lv[:n.value], (dv[:n.value] if dv else None)
+
+    def pyrlk(self, prev, nxt, prevPts, nextPts=None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01), flags=0,
+              minEigThreshold=1e-4):
+        prev = _u8_image(prev, "prevImg")
+        nxt = _u8_image(nxt, "nextImg")
+        if prev.shape != nxt.shape:
+            raise OfbError(1, "prevImg and nextImg must have the same size")
+        if prev.strides[0] != nxt.strides[0]:
+            prev, nxt = np.ascontiguousarray(prev), np.ascontiguousarray(nxt)
+        pts = np.ascontiguousarray(np.asarray(prevPts, np.float32).reshape(-1, 2))
+        n = pts.shape[0]
+        if flags & OPTFLOW_USE_INITIAL_FLOW:
+            nxp = np.ascontiguousarray(np.asarray(nextPts, np.float32).reshape(-1, 2)).copy()
+            if nxp.shape != pts.shape:
+                raise OfbError(1, "nextPts must match prevPts with OPTFLOW_USE_INITIAL_FLOW")
+        else:
+            nxp = np.empty_like(pts)
+        status = np.zeros((n,), np.uint8)
+        err = np.zeros((n,), np.float32)
+        ctype, max_count, eps = criteria
+        if not (ctype & 1):
+            max_count = 30
+        if not (ctype & 2):
+            eps = 0.01 if not (ctype & 1) else 0.0
+        p = LKParams(int(winSize[0]), int(winSize[1]), int(maxLevel), int(max_count), float(eps), int(flags),
+                     float(minEigThreshold))
+        hgt, wid = prev.shape
+        with self._lock:
+            st = self._lib.ofb_pyrlk(self._h, prev.ctypes.data, nxt.ctypes.data, wid, hgt, prev.strides[0],
+                                     pts.ctypes.data, n, nxp.ctypes.data, status.ctypes.data, err.ctypes.data,
+                                     C.byref(p))
+            _lib.check(st, self._h)
+        return nxp.reshape(-1, 1, 2), status.reshape(-1, 1), err.reshape(-1, 1)

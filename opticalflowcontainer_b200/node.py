@@ -1,0 +1,115 @@
+"""Host-side mirror of the reference nodes' frame → velocity contract, without rclpy.
+
+Every reference node does the same thing around its flow call:
+``ros2_ws/src/liteflownet3/liteflownet3/lfn3_sub_node.py:141-222`` (median),
+``ros2_ws/src/optical_flow/optical_flow/opticalflow_node.py:41-128`` (mean),
+``ros2_ws/src/liteflownet3/liteflownet3/sub_n_pub_lfn3_node.py:195-210`` (masked median):
+first frame primes the state; then ``dt = stamp - prev_stamp`` (``<= 0 → 1e-3``), flow,
+``u_avg = median|mean(flow[0]) / dt``, ``vx = u_avg * pixel_to_meter``, a ``deque(maxlen=5)``
+mean for the smooth topic, and a ``Vector3Stamped{stamp = image stamp, frame_id 'camera_link',
+vector = (vx, 0, 0)}``.  ``FarnebackVelocityNode`` is that logic with the flow call swapped for
+the B200 engine; messages are plain dataclasses so the class runs (and is tested) without ROS.
+``examples/farneback_sub_node.py`` shows the same class wired to rclpy.
+"""
+from __future__ import annotations
+
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from .engine import FlowEngine
+
+
+@dataclass
+class Vector3Stamped:
+    """geometry_msgs/Vector3Stamped look-alike."""
+    stamp: float
+    frame_id: str = "camera_link"
+    vector: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+
+
+def to_gray_u8(image: np.ndarray, encoding: str = "bgr8") -> np.ndarray:
+    """sensor_msgs/Image payload → gray uint8 with cv2's fixed-point BGR2GRAY
+    ``(B*3735 + G*19235 + R*9798 + 16384) >> 15`` (probe-verified)."""
+    image = np.asarray(image)
+    if image.ndim == 2:
+        return np.ascontiguousarray(image.astype(np.uint8, copy=False))
+    if encoding == "bgr8":
+        b, g, r = image[..., 0], image[..., 1], image[..., 2]
+    elif encoding == "rgb8":
+        r, g, b = image[..., 0], image[..., 1], image[..., 2]
+    else:
+        raise ValueError("Unsupported image encoding: %s" % encoding)
+    y = (b.astype(np.uint32) * 3735 + g.astype(np.uint32) * 19235 + r.astype(np.uint32) * 9798 + 16384) >> 15
+    return np.ascontiguousarray(y.astype(np.uint8))
+
+
+@dataclass
+class FarnebackVelocityNode:
+    width: int = 640
+    height: int = 480
+    pixel_to_meter: float = 0.0011
+    reduce: str = "median"        # 'median' (lfn3_sub_node.py:207) or 'mean' (opticalflow_node.py:98)
+    device: int = 0
+    pyr_scale: float = 0.5
+    levels: int = 3
+    winsize: int = 15
+    iterations: int = 3
+    poly_n: int = 5
+    poly_sigma: float = 1.2
+    flags: int = 0
+    on_device_reduce: bool = False
+    engine: Optional[FlowEngine] = None
+    prev_gray: Optional[np.ndarray] = field(default=None, repr=False)
+    prev_time: Optional[float] = None
+    velocity_buffer: deque = field(default_factory=lambda: deque(maxlen=5), repr=False)
+    last_flow: Optional[np.ndarray] = field(default=None, repr=False)
+
+    def __post_init__(self):
+        if self.engine is None:
+            self.engine = FlowEngine(self.width, self.height, 1, self.device)
+
+    def image_callback(self, image: np.ndarray, stamp: float, encoding: str = "bgr8",
+                       mask: Optional[np.ndarray] = None) -> Optional[Tuple[Vector3Stamped, Vector3Stamped]]:
+        """One camera frame in → (raw, smooth) velocity messages out (None on the priming frame)."""
+        gray = to_gray_u8(image, encoding)
+        if gray.shape != (self.height, self.width):
+            raise ValueError("frame is %s, node is configured for %s" % (gray.shape, (self.height, self.width)))
+        if self.prev_gray is None:
+            self.prev_gray, self.prev_time = gray, stamp
+            return None
+        dt = stamp - self.prev_time
+        if dt <= 0:
+            dt = 1e-3
+        self.prev_time = stamp
+        flow = self.engine.farneback(self.prev_gray, gray, None, self.pyr_scale, self.levels, self.winsize,
+                                     self.iterations, self.poly_n, self.poly_sigma, self.flags)
+        self.last_flow = flow
+        flow_np = np.transpose(flow, (2, 0, 1))      # [2,H,W] as the reference nodes consume it
+        if self.on_device_reduce:
+            mean, med = self.engine.flow_u_stats(1, mask, mean=self.reduce == "mean", median=self.reduce == "median")
+            u = (mean if self.reduce == "mean" else med)[0]
+        else:
+            u_field = flow_np[0] if mask is None else flow_np[0][np.asarray(mask, bool)]
+            if u_field.size == 0:
+                self.prev_gray = gray
+                return None
+            u = float(np.mean(u_field)) if self.reduce == "mean" else float(np.median(u_field))
+        vx = float(u / dt * self.pixel_to_meter)
+        self.velocity_buffer.append(vx)
+        vx_smooth = float(np.mean(self.velocity_buffer))
+        self.prev_gray = gray
+        return (Vector3Stamped(stamp, "camera_link", (vx, 0.0, 0.0)),
+                Vector3Stamped(stamp, "camera_link", (vx_smooth, 0.0, 0.0)))
+
+
+def junction_mask(points: Sequence[Sequence[float]], height: int, width: int, radius: int = 5) -> np.ndarray:
+    """±radius squares around junction points (sub_n_pub_lfn3_node.py:195-204)."""
+    mask = np.zeros((height, width), dtype=bool)
+    for p in points:
+        x, y = int(p[0]), int(p[1])
+        if 0 <= x < width and 0 <= y < height:
+            mask[max(0, y - radius):min(height, y + radius + 1), max(0, x - radius):min(width, x + radius + 1)] = True
+    return mask

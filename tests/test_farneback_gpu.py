@@ -1,0 +1,150 @@
+"""GPU parity of the dense path, called through the C ABI (ctypes → libofb.so), against
+(i) the reference implementation of the path (cv2 wheel), (ii) the NumPy restatement and
+(iii) the committed golden fixtures.
+
+Tolerance (BASELINE.json north_star): mean endpoint error <= 0.01 px and max <= 0.1 px vs cv2 on
+identical inputs.  The tests use a 10x tighter gate (1e-3 / 1e-2) on well-conditioned inputs.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cv2_oracle as C
+from oracle import farneback_np as F
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+MEAN_GATE, MAX_GATE = 0.01, 0.1          # the contract
+TIGHT_MEAN, TIGHT_MAX = 1e-3, 1e-2       # what we hold ourselves to
+
+
+def _check(ref, got, mean_gate=TIGHT_MEAN, max_gate=TIGHT_MAX):
+    assert got.shape == ref.shape and got.dtype == np.float32
+    assert np.isfinite(got).all()
+    mean, mx = C.epe(ref, got)
+    assert mean <= mean_gate and mx <= max_gate, (mean, mx)
+    return mean, mx
+
+
+CASES = [
+    ("vga_small_shift", (480, 640), 0, (1.7, -0.9), {}),
+    ("vga_large_shift", (480, 640), 1, (14.3, -9.6), {}),
+    ("odd_size", (481, 637), 2, (3.1, 2.2), {}),
+    ("odd_size2", (539, 959), 2, (-4.1, 1.2), {}),
+    ("gaussian", (240, 320), 3, (3, 2), dict(flags=256)),
+    ("gaussian31", (240, 320), 3, (3, 2), dict(flags=256, winsize=31)),
+    ("winsize16", (240, 320), 4, (3, 2), dict(winsize=16)),
+    ("winsize5", (240, 320), 4, (2, 1), dict(winsize=5)),
+    ("winsize31", (240, 320), 4, (2, 1), dict(winsize=31)),
+    ("poly7", (240, 320), 5, (3, 2), dict(poly_n=7, poly_sigma=1.5)),
+    ("pyr08", (240, 320), 6, (3, 2), dict(pyr_scale=0.8, levels=5)),
+    ("levels0", (200, 300), 7, (2, 1), dict(levels=0)),
+    ("levels1", (200, 300), 7, (2, 1), dict(levels=1)),
+    ("levels8_clamped", (200, 300), 7, (2, 1), dict(levels=8)),
+    ("iter1", (240, 320), 8, (2, 1), dict(iterations=1)),
+    ("tiny_33x35", (33, 35), 9, (0.5, 0.25), {}),
+]
+
+
+@pytest.mark.parametrize("name,shape,seed,shift,kw", CASES, ids=[c[0] for c in CASES])
+def test_farneback_matches_cv2(engine_factory, name, shape, seed, shift, kw):
+    a, b = synth.synth_pair(shape[0], shape[1], seed, shift)
+    eng = engine_factory(shape[1], shape[0])
+    got = eng.farneback(a, b, None, **kw)
+    _check(C.farneback(a, b, **kw), got)
+
+
+def test_module_level_cv2_signature(built_lib):
+    import opticalflowcontainer_b200 as ofb
+    a, b = synth.synth_pair(120, 160, 21, (1.0, 0.5))
+    got = ofb.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    _check(C.farneback(a, b), got)
+
+
+def test_rotation_zoom_and_low_texture(engine_factory):
+    eng = engine_factory(640, 480)
+    a, b = synth.synth_warp_pair(480, 640, 31)
+    _check(C.farneback(a, b), eng.farneback(a, b))
+    a, b = synth.low_texture_pair(480, 640, 3)
+    # low-texture frames are ill-conditioned (the 1e-3 regulariser dominates): contract gate
+    _check(C.farneback(a, b), eng.farneback(a, b), MEAN_GATE, MAX_GATE)
+
+
+def test_initial_flow(engine_factory):
+    a, b = synth.synth_pair(240, 320, 2, (5, 3))
+    f0 = np.full((240, 320, 2), (4.5, 2.5), np.float32)
+    eng = engine_factory(320, 240)
+    got = eng.farneback(a, b, f0.copy(), flags=4)
+    _check(C.farneback(a, b, flow=f0.copy(), flags=4), got)
+    # odd size: INTER_AREA with fractional cells
+    a, b = synth.synth_pair(203, 317, 2, (5, 3))
+    rng = np.random.default_rng(0)
+    f0 = (np.array([4.5, 2.5], np.float32) + rng.standard_normal((203, 317, 2)).astype(np.float32) * 0.2)
+    eng = engine_factory(317, 203)
+    _check(C.farneback(a, b, flow=f0.copy(), flags=4), eng.farneback(a, b, f0.copy(), flags=4))
+
+
+def test_against_numpy_restatement(engine_factory):
+    a, b = synth.synth_pair(200, 264, 41, (2.2, -1.1))
+    eng = engine_factory(264, 200)
+    _check(F.farneback(a, b), eng.farneback(a, b))
+
+
+def test_golden_fixtures(engine_factory):
+    files = sorted(glob.glob(os.path.join(GOLDEN, "farneback_*.npz")))
+    assert files
+    for f in files:
+        z = np.load(f)
+        kw = {k[3:]: z[k].item() for k in z.files if k.startswith("kw_")}
+        hgt, wid = z["prev"].shape
+        eng = engine_factory(wid, hgt)
+        gate = (MEAN_GATE, MAX_GATE) if "lowtex" in f else (TIGHT_MEAN, TIGHT_MAX)
+        _check(z["flow"], eng.farneback(z["prev"], z["next"], None, **kw), *gate)
+
+
+def test_batch_equals_single(engine_factory):
+    eng = engine_factory(320, 240, 4)
+    pairs = [synth.synth_pair(240, 320, 50 + i, (1.0 + i, -0.5 * i)) for i in range(4)]
+    out = eng.farneback_batch([p[0] for p in pairs], [p[1] for p in pairs])
+    for i, (a, b) in enumerate(pairs):
+        single = eng.farneback(a, b)
+        assert np.array_equal(single, out[i])          # batching must not change a bit
+        _check(C.farneback(a, b), out[i])
+
+
+def test_strided_input_and_capacity(engine_factory):
+    import opticalflowcontainer_b200 as ofb
+    a, b = synth.synth_pair(120, 200, 60, (1.5, 0.5))
+    big_a = np.zeros((120, 256), np.uint8); big_a[:, :200] = a
+    big_b = np.zeros((120, 256), np.uint8); big_b[:, :200] = b
+    eng = engine_factory(200, 120)
+    got = eng.farneback(big_a[:, :200], big_b[:, :200])       # row stride 256
+    assert np.array_equal(got, eng.farneback(a, b))
+    with pytest.raises(ofb.OfbError) as ei:
+        eng.farneback(np.zeros((300, 300), np.uint8), np.zeros((300, 300), np.uint8))
+    assert ei.value.status == 4
+    with pytest.raises(ofb.OfbError):
+        eng.farneback(a, b, pyr_scale=1.5)
+    with pytest.raises(ofb.OfbError):
+        eng.farneback(a, b[:100])
+    with pytest.raises(ofb.OfbError):
+        eng.farneback(a.astype(np.float32), b)
+
+
+def test_full_size_1080p_properties(engine_factory):
+    """BASELINE config[1] size.  cv2 at 1080p takes ~0.8 s — affordable once; plus size-independent
+    properties: a pure translation is recovered in the interior, and swapping the frames negates it."""
+    a, b = synth.synth_pair(1080, 1920, 1, (6.2, 3.4))
+    eng = engine_factory(1920, 1080)
+    got = eng.farneback(a, b)
+    _check(C.farneback(a, b), got)
+    inner = got[100:-100, 100:-100]
+    assert abs(float(np.median(inner[..., 0])) - 6.2) < 0.1 and abs(float(np.median(inner[..., 1])) - 3.4) < 0.1
+    back = eng.farneback(b, a)[100:-100, 100:-100]
+    assert abs(float(np.median(back[..., 0])) + 6.2) < 0.1 and abs(float(np.median(back[..., 1])) + 3.4) < 0.1
+    # determinism: same input twice -> identical bits
+    assert np.array_equal(got, eng.farneback(a, b))
