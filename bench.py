@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — Farneback 1080p frame-pairs/s on N B200s (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the cv2 CPU path on the box's host cores
+
+A step = one pass of the hot path (all pyramid levels, all iterations) over one batch of
+`--batch` synthetic 1920x1080 frame pairs per GPU.  `value` = pairs/s with inputs resident in
+HBM; `e2e` = the same through the host-buffer C-ABI call (H2D of both frames from pinned memory
+and D2H of the full flow field inside the timed region).  Frame pairs are independent, so ranks
+shard them with no data-path collective (weak scaling); torch.distributed is used only for the
+barrier and the max-over-ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "farneback_1080p_frame_pairs_per_s"
+UNIT = "frame-pairs/s"
+W_, H_ = 1920, 1080
+PARAMS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+L2_BYTES = 126 * 1024 * 1024
+
+
+def level_pixels(w, h, pyr_scale=0.5, levels=3):
+    out, scale = [], 1.0
+    k = 0
+    while k < levels:
+        scale *= pyr_scale
+        if w * scale < 32 or h * scale < 32:
+            break
+        k += 1
+    for kk in range(k, -1, -1):
+        s = pyr_scale ** kk
+        out.append(int(np.rint(w * s)) * int(np.rint(h * s)))
+    return out
+
+
+def algorithmic_bytes_per_pair(w, h, iters=3):
+    """SURVEY.md §8d fused-stage model: B = L*2N + (40 + 56*iters) * sum(n_l)."""
+    nl = level_pixels(w, h)
+    return len(nl) * 2 * w * h + (40 + 56 * iters) * sum(nl)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "note": "no NVML samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """cv2.calcOpticalFlowFarneback (the reference implementation of the path) on the host cores,
+    process-parallel (the wheel's Farneback is single-threaded).  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    import multiprocessing as mp
+    workers = os.cpu_count() or 1
+    pairs_per_worker = max(1, args.ref_pairs)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        for _ in range(max(args.warmup, 1) if args.warmup else 0):
+            cpu_bench.farneback_cpu_step(H_, W_, 1, workers, pool)
+        t_total = 0.0
+        for s in range(args.steps):
+            t_total += cpu_bench.farneback_cpu_step(H_, W_, pairs_per_worker, workers, pool, seed=100 * s)
+    pairs = workers * pairs_per_worker * args.steps
+    value = pairs / t_total
+    import cv2
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "farneback_1920x1080_single_stream", "params": PARAMS,
+                   "pairs_per_step": workers * pairs_per_worker},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference",
+                         "sample": "%d worker processes x %d pairs x %d steps of cv2 %s calcOpticalFlowFarneback "
+                                   "(cv2.setNumThreads(1) per worker; the algorithm is single-threaded)"
+                                   % (workers, pairs_per_worker, args.steps, cv2.__version__)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from opticalflowcontainer_b200 import build as ofb_build
+    if rank == 0:
+        ofb_build.build()
+    if world > 1:
+        dist.barrier()
+    import opticalflowcontainer_b200 as ofb
+    from oracle import synth  # input generator only (test infrastructure), never on the timed path
+
+    B = args.batch
+    seq = args.mode == "sequence"
+    eng = ofb.FlowEngine(W_, H_, B, local_rank)
+    pitch = W_
+    istride = pitch * H_
+    frames_per_set = (B + 1) if seq else 2 * B
+    n_sets = max(2, int(np.ceil(2.0 * L2_BYTES / (frames_per_set * istride))) + 1)
+    # synthetic frames: a few distinct textures, shifted copies as "next"
+    base = [synth.cheap_texture(H_, W_, 1000 * rank + i) for i in range(4)]
+    rng = np.random.default_rng(rank)
+    host_sets = []
+    for s in range(n_sets):
+        fr = np.empty((frames_per_set, H_, W_), np.uint8)
+        if seq:
+            t = base[s % 4]
+            ox = oy = 0
+            for i in range(frames_per_set):
+                fr[i] = np.roll(t, (oy, ox), axis=(0, 1))
+                ox += int(rng.integers(-8, 9)); oy += int(rng.integers(-8, 9))
+        else:
+            for i in range(B):
+                t = base[(s + i) % 4]
+                fr[i] = np.roll(t, (i * 7 % 13, i * 5 % 11), axis=(0, 1))
+                fr[B + i] = np.roll(fr[i], (int(rng.integers(-8, 9)), int(rng.integers(-8, 9))), axis=(0, 1))
+        host_sets.append(fr)
+    dev_sets = [torch.from_numpy(fr).cuda() for fr in host_sets]
+    d_flow = torch.empty((B, H_, W_, 2), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+
+    def step(i):
+        d = dev_sets[i % n_sets]
+        p0 = d.data_ptr()
+        eng.farneback_device(B, p0, p0 + B * istride, W_, H_, pitch, istride, d_flow.data_ptr(), sequence=seq, **PARAMS)
+
+    stream = torch.cuda.ExternalStream(eng.stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    # ---- timed region: exactly K steps, CUDA events on the engine's stream
+    sampler = ClockSampler(local_rank)
+    l0 = eng.launch_count
+    eng.timing_enable(True)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record(stream)
+    eng.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    stage = eng.timing_read()
+    eng.timing_enable(False)
+    launches = eng.launch_count - l0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+
+    # the stage timers add event records between kernels; re-time the K steps without them for `value`
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + args.steps + i)
+    ev1.record(stream)
+    eng.synchronize()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    plain_ms_max = float(t.item())
+    pairs = B * args.steps * world
+    value = pairs / (plain_ms_max * 1e-3)
+
+    # ---- e2e: host-buffer C-ABI call, pinned host memory, H2D + D2H inside the timed region
+    pin_prev = [torch.from_numpy(host_sets[s][:B].copy()).pin_memory() for s in range(min(n_sets, 3))]
+    pin_next = [torch.from_numpy((host_sets[s][1:B + 1] if seq else host_sets[s][B:2 * B]).copy()).pin_memory()
+                for s in range(min(n_sets, 3))]
+    pin_flow = torch.empty((B, H_, W_, 2), dtype=torch.float32).pin_memory()
+    e2e_steps = args.steps if args.e2e_steps <= 0 else args.e2e_steps
+
+    def e2e_step(i):
+        s = i % len(pin_prev)
+        eng.farneback_batch_into(pin_prev[s].numpy(), pin_next[s].numpy(), pin_flow.numpy(), **PARAMS)
+
+    for i in range(min(2, args.warmup)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    eng.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * e2e_steps * world / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    nl = level_pixels(W_, H_)
+    it_ms, it_cnt = stage["iteration"]
+    iters = PARAMS["iterations"]
+    alg_iter_bytes = 56.0 * sum(nl) * iters * B * args.steps       # all iteration-stage launches of the timed region
+    it_gbs = alg_iter_bytes / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0
+    pipe_gbs = algorithmic_bytes_per_pair(W_, H_) * (value / world) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": plain_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "farneback_1920x1080_single_stream", "params": PARAMS, "pairs_per_step_per_gpu": B,
+                   "mode": args.mode, "parallelism": "frame-pair sharding x%d, no collective" % world,
+                   "l2": "inputs rotate over %d frame sets (%.0f MB > 2x L2); per-step working set %.0f MB >> L2"
+                         % (n_sets, n_sets * frames_per_set * istride / 1e6, B * 232.0)},
+        "roofline": {"bound": "hbm", "kernel": "iteration stage (UpdateMatrices + blur + 2x2 solve)",
+                     "achieved": it_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": it_gbs / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch_group": "56 B x n_l x %d pairs" % B,
+                     "share_of_step": it_ms / dev_ms if dev_ms > 0 else None,
+                     "pipeline_achieved": pipe_gbs, "pipeline_frac": pipe_gbs / peaks["hbm_gbs"],
+                     "pipeline_bytes_per_pair": algorithmic_bytes_per_pair(W_, H_),
+                     "stage_ms": {k: v[0] for k, v in stage.items()}, "stage_launch_groups": {k: v[1] for k, v in stage.items()},
+                     "timed_region_ms_with_stage_events": dev_ms_max},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * W_ * H_,
+                "d2h_bytes_per_step": 8 * B * W_ * H_, "steps": e2e_steps,
+                "api": "ofb_farneback_batch (host buffers, pinned; full float32 [H,W,2] flow returned)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_bench
+        cb = cpu_bench.farneback_cpu_throughput(H_, W_, target_seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "reference",
+                                "sample": "cv2 %s calcOpticalFlowFarneback, %d processes x %d pairs of 1920x1080 "
+                                          "(single-threaded algorithm; 1 pair = %.0f ms on one core)"
+                                          % (cb["cv2_version"], cb["cores"], cb["pairs_per_worker"], cb["single_pair_ms"])}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frame pairs per step per GPU")
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence"])
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--ref-pairs", type=int, default=2, help="--impl reference: pairs per worker per step")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

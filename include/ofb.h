@@ -141,6 +141,22 @@ int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_f
 /* Number of kernel launches this handle has enqueued since creation (bench evidence). */
 uint64_t ofb_launch_count(const ofb_handle* h);
 
+/* Per-stage device timing with CUDA events recorded on the handle's stream around every
+ * kernel launch of a stage (what bench.py's roofline block reads).  Stages: */
+enum {
+  OFB_STAGE_PYRAMID = 0,   /* convert + GaussianBlur + resize (a2) */
+  OFB_STAGE_POLYEXP = 1,   /* FarnebackPolyExp (a4) */
+  OFB_STAGE_ITERATION = 2, /* UpdateMatrices + blur + solve (a5-a7): the dominant kernel */
+  OFB_STAGE_FLOW_INIT = 3, /* zero / initial-flow / inter-level upsample (a8, a9) */
+  OFB_STAGE_OTHER = 4,
+  OFB_NUM_STAGES = 5
+};
+/* enable != 0 starts a fresh recording (drops earlier samples); 0 stops recording. */
+int ofb_timing_enable(ofb_handle* h, int enable);
+/* Synchronises the stream and returns, per stage, the summed event time in milliseconds and the
+ * number of launches recorded since ofb_timing_enable(h, 1).  Arrays of OFB_NUM_STAGES. */
+int ofb_timing_read(ofb_handle* h, double* ms_out, uint64_t* launches_out);
+
 /* ---- on-device reduction of the flow field (the node contract) ----------------
  * Every reference node collapses the field to one scalar right after the flow
  * call (lfn3_sub_node.py:205-212: np.median(flow_np[0]); opticalflow_node.py:98:

@@ -20,6 +20,37 @@ int set_error(ofb_handle* h, int status, const char* fmt, ...) {
   return status;
 }
 
+int timing_begin(ofb_handle* h, int stage) {
+  if (!h->timing) return OFB_OK;
+  if (h->ev_used * 2 + 2 > h->ev_pool.size()) {
+    for (int i = 0; i < 2; i++) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "cudaEventCreate failed");
+      h->ev_pool.push_back(e);
+    }
+    h->ev_stage.push_back(stage);
+  }
+  h->ev_stage[h->ev_used] = stage;
+  OFB_CUDA(h, cudaEventRecord(h->ev_pool[h->ev_used * 2], h->stream));
+  return OFB_OK;
+}
+
+int timing_end(ofb_handle* h) {
+  if (!h->timing) return OFB_OK;
+  OFB_CUDA(h, cudaEventRecord(h->ev_pool[h->ev_used * 2 + 1], h->stream));
+  h->ev_used++;
+  return OFB_OK;
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // cv2 argument checks of calcOpticalFlowFarneback (optflowgf.cpp: CV_Assert lines) — INVALID_ARG
@@ -70,6 +101,29 @@ void* ofb_stream(ofb_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 uint64_t ofb_launch_count(const ofb_handle* h) { return h ? h->launches : 0; }
 
+int ofb_timing_enable(ofb_handle* h, int enable) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->timing = enable != 0;
+  h->ev_used = 0;
+  return OFB_OK;
+}
+
+int ofb_timing_read(ofb_handle* h, double* ms_out, uint64_t* launches_out) {
+  if (!h || !ms_out || !launches_out) return OFB_ERR_INVALID_ARG;
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < OFB_NUM_STAGES; i++) { ms_out[i] = 0; launches_out[i] = 0; }
+  for (size_t i = 0; i < h->ev_used; i++) {
+    float ms = 0.f;
+    OFB_CUDA(h, cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+    ms_out[h->ev_stage[i]] += ms;
+    launches_out[h->ev_stage[i]]++;
+  }
+  return OFB_OK;
+}
+
 int ofb_synchronize(ofb_handle* h) {
   if (!h) return OFB_ERR_INVALID_ARG;
   OFB_CUDA(h, cudaSetDevice(h->device));
@@ -89,6 +143,7 @@ int ofb_destroy(ofb_handle* h) {
   cudaFree(h->d_scratch);
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OFB_OK;
@@ -203,31 +258,56 @@ int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const 
   for (int i = 0; i < n; i++)
     if (!prev[i] || !next[i] || !flow[i]) return set_error(h, OFB_ERR_INVALID_ARG, "NULL image/flow pointer");
   OFB_CUDA(h, cudaSetDevice(h->device));
-  // stage into pinned memory (packed rows of `pitch`), one async upload
+  // Pinned (page-locked / registered) caller buffers are DMA'd directly; pageable ones are staged
+  // through the handle's pinned buffers (one memcpy each way, as cudaMemcpy would do internally).
+  bool pinned = true;
+  for (int i = 0; i < n && pinned; i++) pinned = is_pinned(prev[i]) && is_pinned(next[i]) && is_pinned(flow[i]);
   const size_t pitch = align_up((size_t)width, 16);
   const size_t istride = pitch * height;
-  for (int i = 0; i < n; i++)
-    for (int img = 0; img < 2; img++) {
-      const uint8_t* s = img ? next[i] : prev[i];
-      uint8_t* d = h->h_src + (size_t)(img * n + i) * istride;
-      if (stride_bytes == pitch) memcpy(d, s, istride);
-      else for (int y = 0; y < height; y++) memcpy(d + (size_t)y * pitch, s + (size_t)y * stride_bytes, width);
-    }
-  OFB_CUDA(h, cudaMemcpyAsync(h->d_src, h->h_src, istride * 2 * n, cudaMemcpyHostToDevice, h->stream));
-  const float* init = nullptr;
   const size_t fl_img = (size_t)width * height * 2;
-  if (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
+  const float* init = nullptr;
+  if (pinned) {
+    for (int i = 0; i < n; i++) {
+      OFB_CUDA(h, cudaMemcpy2DAsync(h->d_src + (size_t)i * istride, pitch, prev[i], stride_bytes, width, height,
+                                    cudaMemcpyHostToDevice, h->stream));
+      OFB_CUDA(h, cudaMemcpy2DAsync(h->d_src + (size_t)(n + i) * istride, pitch, next[i], stride_bytes, width, height,
+                                    cudaMemcpyHostToDevice, h->stream));
+    }
+    if (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
+      for (int i = 0; i < n; i++)
+        OFB_CUDA(h, cudaMemcpy2DAsync(h->d_init_flow + i * fl_img, row_flow, flow[i], flow_stride_bytes, row_flow,
+                                      height, cudaMemcpyHostToDevice, h->stream));
+      init = h->d_init_flow;
+    }
+  } else {
     for (int i = 0; i < n; i++)
-      for (int y = 0; y < height; y++)
-        memcpy(h->h_flow + i * fl_img + (size_t)y * width * 2, (const char*)flow[i] + (size_t)y * flow_stride_bytes,
-               row_flow);
-    OFB_CUDA(h, cudaMemcpyAsync(h->d_init_flow, h->h_flow, n * fl_img * sizeof(float), cudaMemcpyHostToDevice,
-                                h->stream));
-    init = h->d_init_flow;
+      for (int img = 0; img < 2; img++) {
+        const uint8_t* s = img ? next[i] : prev[i];
+        uint8_t* d = h->h_src + (size_t)(img * n + i) * istride;
+        if (stride_bytes == pitch) memcpy(d, s, istride);
+        else for (int y = 0; y < height; y++) memcpy(d + (size_t)y * pitch, s + (size_t)y * stride_bytes, width);
+      }
+    OFB_CUDA(h, cudaMemcpyAsync(h->d_src, h->h_src, istride * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    if (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
+      for (int i = 0; i < n; i++)
+        for (int y = 0; y < height; y++)
+          memcpy(h->h_flow + i * fl_img + (size_t)y * width * 2, (const char*)flow[i] + (size_t)y * flow_stride_bytes,
+                 row_flow);
+      OFB_CUDA(h, cudaMemcpyAsync(h->d_init_flow, h->h_flow, n * fl_img * sizeof(float), cudaMemcpyHostToDevice,
+                                  h->stream));
+      init = h->d_init_flow;
+    }
   }
   st = farneback_run(h, n, false, h->d_src, h->d_src + (size_t)n * istride, width, height, pitch, istride,
                      h->d_flow_out, init, params);
   if (st) return st;
+  if (pinned) {
+    for (int i = 0; i < n; i++)
+      OFB_CUDA(h, cudaMemcpy2DAsync(flow[i], flow_stride_bytes, h->d_flow_out + i * fl_img, row_flow, row_flow, height,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return OFB_OK;
+  }
   OFB_CUDA(h, cudaMemcpyAsync(h->h_flow, h->d_flow_out, n * fl_img * sizeof(float), cudaMemcpyDeviceToHost,
                               h->stream));
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -79,6 +79,12 @@ struct ofb_handle {
 
   // sparse path buffers are owned by lk.cu / features.cu state
   void* sparse = nullptr;
+
+  // per-stage event timing (ofb_timing_enable / ofb_timing_read)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;     // pairs (start, stop)
+  std::vector<int> ev_stage;            // stage of pair i
+  size_t ev_used = 0;                   // pairs in use
 };
 
 namespace ofb {
@@ -103,6 +109,10 @@ int set_error(ofb_handle* h, int status, const char* fmt, ...);
       return ofb::set_error((h), OFB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",          \
                             cudaGetErrorString(e__), __FILE__, __LINE__);                   \
   } while (0)
+
+// RAII-free stage timer: call begin before the launch(es) of a stage and end after.
+int timing_begin(ofb_handle* h, int stage);
+int timing_end(ofb_handle* h);
 
 // ---- farneback.cu --------------------------------------------------------------------
 int build_schedule(int width, int height, double pyr_scale, int levels, Level* out, int* n_out);

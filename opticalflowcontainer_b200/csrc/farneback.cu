@@ -569,7 +569,10 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
     // level's result (read by the upsample); alt may alias it (first written after the upsample).
     float2* cur = prev_flow == h->d_flow[0] ? h->d_flow[1] : h->d_flow[0];
     float2* alt = cur == h->d_flow[0] ? h->d_flow[1] : h->d_flow[0];
+#define TB(stage) do { int s__ = timing_begin(h, stage); if (s__) return s__; } while (0)
+#define TE() do { int s__ = timing_end(h); if (s__) return s__; } while (0)
     // --- initial flow of the level
+    TB(OFB_STAGE_FLOW_INIT);
     if (prev_flow == nullptr) {
       if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
         k_init_flow_area<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>((const float2*)d_init_flow, width, height, cur, w,
@@ -585,13 +588,17 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
                                                                    (float)(1.0 / p->pyr_scale));
       OFB_LAUNCH_CHECK(h);
     }
+    TE();
     // --- pyramid level + polynomial expansion of every frame
     PyrCoef pyc;
     if (prepare_pyr(lv.ksize, lv.sigma, &pyc) != OFB_OK)
       return set_error(h, OFB_ERR_INVALID_ARG, "pyramid smoothing kernel too large (ksize=%d)", lv.ksize);
+    TB(OFB_STAGE_PYRAMID);
     k_pyr_level<<<grid2d(w, hh, frames, blk), blk, 0, st>>>(src, width, height, h->d_img, w, hh,
                                                             1.0 / ((double)w / width), 1.0 / ((double)hh / height), pyc);
     OFB_LAUNCH_CHECK(h);
+    TE();
+    TB(OFB_STAGE_POLYEXP);
     {
       dim3 g((w + PE_T - 1) / PE_T, (hh + PE_T - 1) / PE_T, frames);
       if (pc.n == 5) k_polyexp<5><<<g, blk, 0, st>>>(h->d_img, h->d_RA, h->d_RB, w, hh, pc);
@@ -599,11 +606,13 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       else k_polyexp<0><<<g, blk, 0, st>>>(h->d_img, h->d_RA, h->d_RB, w, hh, pc);
       OFB_LAUNCH_CHECK(h);
     }
+    TE();
     // --- iterations
     float2* fin = cur;
     for (int it = 0; it < p->iterations; it++) {
       const bool last_it = it == p->iterations - 1;
       float2* fout = (last_level && last_it) ? (float2*)d_flow_out : (fin == cur ? alt : cur);
+      TB(OFB_STAGE_ITERATION);
       k_update_matrices<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_RA, h->d_RB, fin, h->d_MA, h->d_MB, w, hh,
                                                                      f1_offset);
       OFB_LAUNCH_CHECK(h);
@@ -611,6 +620,7 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       OFB_LAUNCH_CHECK(h);
       k_blur_h_solve<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_VA, h->d_VB, fout, w, hh, bc);
       OFB_LAUNCH_CHECK(h);
+      TE();
       fin = fout;
     }
     if (p->iterations == 0 && last_level) {

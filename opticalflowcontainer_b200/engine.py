@@ -67,6 +67,18 @@ class FlowEngine:
     def launch_count(self) -> int:
         return int(self._lib.ofb_launch_count(self._h))
 
+    STAGES = ("pyramid", "polyexp", "iteration", "flow_init", "other")
+
+    def timing_enable(self, on: bool = True):
+        _lib.check(self._lib.ofb_timing_enable(self._h, 1 if on else 0), self._h)
+
+    def timing_read(self):
+        """{stage: (ms_total, launches)} of the CUDA-event stage timers since timing_enable()."""
+        ms = (C.c_double * len(self.STAGES))()
+        cnt = (C.c_uint64 * len(self.STAGES))()
+        _lib.check(self._lib.ofb_timing_read(self._h, ms, cnt), self._h)
+        return {s: (ms[i], int(cnt[i])) for i, s in enumerate(self.STAGES)}
+
     def synchronize(self):
         _lib.check(self._lib.ofb_synchronize(self._h), self._h)
 
@@ -123,6 +135,26 @@ class FlowEngine:
         pp = (C.c_void_p * n)(*[a.ctypes.data for a in prevs])
         nn = (C.c_void_p * n)(*[a.ctypes.data for a in nexts])
         ff = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        with self._lock:
+            st = self._lib.ofb_farneback_batch(self._h, n, pp, nn, wid, hgt, wid, ff, 0, C.byref(p))
+            _lib.check(st, self._h)
+        return out
+
+    def farneback_batch_into(self, prevs: np.ndarray, nexts: np.ndarray, out: np.ndarray, **kw) -> np.ndarray:
+        """Zero-copy variant of farneback_batch: prevs/nexts uint8 [n,H,W], out float32 [n,H,W,2], all
+        C-contiguous (pinned memory is DMA'd directly, pageable memory is staged by the library)."""
+        n, hgt, wid = prevs.shape
+        if (nexts.shape != prevs.shape or out.shape != (n, hgt, wid, 2) or prevs.dtype != np.uint8
+                or nexts.dtype != np.uint8 or out.dtype != np.float32
+                or not (prevs.flags.c_contiguous and nexts.flags.c_contiguous and out.flags.c_contiguous)):
+            raise OfbError(1, "farneback_batch_into: need contiguous uint8 [n,H,W] x2 and float32 [n,H,W,2]")
+        p = self._fb_params(kw.get("pyr_scale", 0.5), kw.get("levels", 3), kw.get("winsize", 15),
+                            kw.get("iterations", 3), kw.get("poly_n", 5), kw.get("poly_sigma", 1.2),
+                            kw.get("flags", 0))
+        ist, fst = hgt * wid, hgt * wid * 8
+        pp = (C.c_void_p * n)(*[prevs.ctypes.data + i * ist for i in range(n)])
+        nn = (C.c_void_p * n)(*[nexts.ctypes.data + i * ist for i in range(n)])
+        ff = (C.c_void_p * n)(*[out.ctypes.data + i * fst for i in range(n)])
         with self._lock:
             st = self._lib.ofb_farneback_batch(self._h, n, pp, nn, wid, hgt, wid, ff, 0, C.byref(p))
             _lib.check(st, self._h)

@@ -1,0 +1,65 @@
+"""CPU baseline: the reference implementation of the path (cv2 wheel) timed on host cores.
+
+TEST INFRASTRUCTURE / BASELINE ONLY — used by ``bench.py`` (``cpu_baseline`` block and
+``--impl reference``).  Farneback in this wheel is single-threaded, so the fair
+multi-core figure is process-parallel: one frame pair per worker, ``workers`` processes.
+"""
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+
+
+def _texture_pair(h, w, seed):
+    from oracle import synth
+    a = synth.cheap_texture(h, w, seed)
+    b = np.roll(a, (2, 3), axis=(0, 1))
+    return a, b
+
+
+def _worker(args):
+    h, w, seed, n_pairs, params = args
+    import cv2
+    cv2.setNumThreads(1)
+    a, b = _texture_pair(h, w, seed)
+    cv2.calcOpticalFlowFarneback(a, b, None, *params)  # warm-up (page-in, allocator)
+    t0 = time.perf_counter()
+    for _ in range(n_pairs):
+        cv2.calcOpticalFlowFarneback(a, b, None, *params)
+    return time.perf_counter() - t0
+
+
+PARAMS = (0.5, 3, 15, 3, 5, 1.2, 0)
+
+
+def farneback_cpu_throughput(h, w, target_seconds=12.0, workers=None, params=PARAMS):
+    """Returns dict(value=pairs/s aggregate, cores, pairs_per_worker, seconds, single_pair_ms,
+    cv2_version, cv2_threads)."""
+    import cv2
+    workers = workers or os.cpu_count() or 1
+    a, b = _texture_pair(h, w, 0)
+    cv2.calcOpticalFlowFarneback(a, b, None, *params)
+    t0 = time.perf_counter()
+    cv2.calcOpticalFlowFarneback(a, b, None, *params)
+    t1 = time.perf_counter() - t0
+    n_pairs = int(max(1, min(32, round(target_seconds / max(t1, 1e-3)))))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        t0 = time.perf_counter()
+        pool.map(_worker, [(h, w, 1000 + i, n_pairs, params) for i in range(workers)])
+        wall = time.perf_counter() - t0
+    # wall includes interpreter start + warm-up of each worker; use the slowest worker's own timer
+    with ctx.Pool(workers) as pool:
+        times = pool.map(_worker, [(h, w, 2000 + i, n_pairs, params) for i in range(workers)])
+    busy = max(times)
+    return dict(value=workers * n_pairs / busy, cores=workers, pairs_per_worker=n_pairs, seconds=busy,
+                single_pair_ms=t1 * 1e3, cv2_version=cv2.__version__, cv2_threads=1, wall_first_pool=wall)
+
+
+def farneback_cpu_step(h, w, pairs_per_worker, workers, pool, params=PARAMS, seed=0):
+    """One bounded 'step' for --impl reference: every worker runs `pairs_per_worker` pairs."""
+    times = pool.map(_worker, [(h, w, seed + i, pairs_per_worker, params) for i in range(workers)])
+    return max(times)
