@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libofb.so (include/ofb.h): handle lifetime, argument validation with
 // cv2's error behaviour, pinned-host staging and the host/device entry points of the dense path.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -179,6 +180,11 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
   } while (0)
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+  {
+    const char* fg = getenv("OFB_FORCE_GENERIC");
+    h->force_generic = fg && fg[0] == '1';
+  }
   const size_t N = (size_t)max_width * max_height;
   const size_t frames = 2 * (size_t)max_batch;
   h->src_pitch = align_up((size_t)max_width, 256);

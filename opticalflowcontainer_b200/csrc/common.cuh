@@ -48,6 +48,8 @@ struct ofb_handle {
   int device = 0;
   int max_w = 0, max_h = 0, max_batch = 0;
   cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  bool force_generic = false;  // OFB_FORCE_GENERIC=1: always take the generic (unfused) kernels
   uint64_t launches = 0;
   std::string err;
 

@@ -459,6 +459,155 @@ __global__ void __launch_bounds__(256) k_blur_h_solve(const float4* __restrict__
 }
 
 // =====================================================================================
+// Fused iteration kernel (box window): UpdateMatrices + (2m+1)^2 box blur + 2x2 solve in ONE pass.
+// HBM traffic per pixel-iteration = R0 (20 B) + R1 gather (20 B) + flow in (8 B) + flow out (8 B).
+//
+// A CTA (8 warps) owns a strip of FI_COLS = 256 matrix columns (2m of them halo) and a segment of
+// `seg_rows` output rows, and marches down it FI_CH = 4 matrix rows at a time:
+//   A1  every warp computes M for one half-row (4 px per lane, 32 px apart: coalesced R0/flow loads
+//       and L1-friendly gathers) into a shared staging row;
+//   A2  horizontal window sums H: each lane owns 4 adjacent columns, reads the 2m+4 staged values
+//       it needs as float4s and writes H into a ring of 2m+1 rows in shared memory;
+//   B   one thread per column keeps the vertical window sum as a running sum in DOUBLE (add the
+//       new H row, subtract the row leaving the window — exactly cv2's vsum scheme, so there is no
+//       float cancellation drift), scales, solves the 2x2 system and writes flow.
+// =====================================================================================
+constexpr int FI_COLS = 256;
+constexpr int FI_CH = 4;
+constexpr int FI_THREADS = 256;
+
+template <int MT>
+__global__ void __launch_bounds__(FI_THREADS, 2)
+    k_iter_box(const float4* __restrict__ RA, const float* __restrict__ RB, const float2* __restrict__ flow_in,
+               float2* __restrict__ flow_out, int w, int h, int f1_offset, int m_rt, float scale, int seg_rows,
+               int strips) {
+  const int m = MT > 0 ? MT : m_rt;
+  const int R = 2 * m + 1;
+  const int tw = FI_COLS - 2 * m;
+  extern __shared__ float smem[];
+  float* stage = smem;                          // [FI_CH][5][FI_COLS]
+  float* ring = smem + FI_CH * 5 * FI_COLS;     // [R][5][FI_COLS]
+
+  const int strip = blockIdx.x % strips;
+  const int seg = blockIdx.x / strips;
+  const int pair = blockIdx.y;
+  const int x_base = strip * tw - m;            // image x of strip column 0
+  const int y0 = seg * seg_rows;
+  const int y1 = min(y0 + seg_rows, h);         // exclusive
+  const int t_first = y0 - m, t_last = y1 - 1 + m;
+
+  const size_t n = (size_t)w * h;
+  const float4* RA0 = RA + (size_t)pair * n;
+  const float* RB0 = RB + (size_t)pair * n;
+  const float4* RA1 = RA + (size_t)(pair + f1_offset) * n;
+  const float* RB1 = RB + (size_t)(pair + f1_offset) * n;
+  const float2* fin = flow_in + (size_t)pair * n;
+  float2* fout = flow_out + (size_t)pair * n;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int a_row = warp >> 1, a_half = warp & 1;
+  const int col = tid;                          // phase-B column
+  const int out_x = x_base + col;
+  const bool col_valid = col >= m && col < FI_COLS - m && out_x < w;
+
+  double vs0 = 0, vs1 = 0, vs2 = 0, vs3 = 0, vs4 = 0;
+
+  for (int tc = t_first; tc <= t_last; tc += FI_CH) {
+    // ---------------- A1: matrices of row tc + a_row -> staging
+    const int t = tc + a_row;
+    if (t <= t_last) {
+      const int y = clampi(t, 0, h - 1);
+      float* srow = stage + a_row * 5 * FI_COLS;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = a_half * 128 + lane + 32 * j;
+        const int x = clampi(x_base + c, 0, w - 1);
+        const float2 fl = __ldg(fin + (size_t)y * w + x);
+        const M5 mm = update_matrix_px(RA0, RB0, RA1, RB1, fl, x, y, w, h);
+        srow[0 * FI_COLS + c] = mm.g11;
+        srow[1 * FI_COLS + c] = mm.g12;
+        srow[2 * FI_COLS + c] = mm.g22;
+        srow[3 * FI_COLS + c] = mm.h1;
+        srow[4 * FI_COLS + c] = mm.h2;
+      }
+    }
+    // rows leaving the window: their ring slots are overwritten in A2, so fetch them now
+    float old[FI_CH][5];
+#pragma unroll
+    for (int rr = 0; rr < FI_CH; rr++) {
+      const int tt = tc + rr;
+      const bool have = (tt - t_first >= R) && tt <= t_last;
+      const int slot = (tt - t_first) % R;
+#pragma unroll
+      for (int ch = 0; ch < 5; ch++) old[rr][ch] = have ? ring[(slot * 5 + ch) * FI_COLS + col] : 0.f;
+    }
+    __syncthreads();
+    // ---------------- A2: horizontal window sums of the staged rows -> ring
+    if (t <= t_last) {
+      const float* srow = stage + a_row * 5 * FI_COLS;
+      float* rrow = ring + ((t - t_first) % R) * 5 * FI_COLS;
+      const int q0 = a_half * 128 + 4 * lane;   // first of this lane's 4 columns
+      const int kq = (m + 3) >> 2;              // quads to each side
+#pragma unroll
+      for (int ch = 0; ch < 5; ch++) {
+        const float* s = srow + ch * FI_COLS;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (MT > 0) {
+#pragma unroll
+          for (int k = -((MT + 3) / 4); k <= (MT + 3) / 4; k++) {
+            const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
+            const float4 v = *reinterpret_cast<const float4*>(s + cq);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int d = 4 * k + i;  // offset from q0
+              if (d >= 0 - MT && d <= 0 + MT) s0 += e[i];
+              if (d >= 1 - MT && d <= 1 + MT) s1 += e[i];
+              if (d >= 2 - MT && d <= 2 + MT) s2 += e[i];
+              if (d >= 3 - MT && d <= 3 + MT) s3 += e[i];
+            }
+          }
+        } else {
+          for (int k = -kq; k <= kq; k++) {
+            const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
+            const float4 v = *reinterpret_cast<const float4*>(s + cq);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int d = 4 * k + i;
+              if (d >= 0 - m && d <= 0 + m) s0 += e[i];
+              if (d >= 1 - m && d <= 1 + m) s1 += e[i];
+              if (d >= 2 - m && d <= 2 + m) s2 += e[i];
+              if (d >= 3 - m && d <= 3 + m) s3 += e[i];
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(rrow + ch * FI_COLS + q0) = make_float4(s0, s1, s2, s3);
+      }
+    }
+    __syncthreads();
+    // ---------------- B: vertical running sums (double) + solve
+#pragma unroll
+    for (int rr = 0; rr < FI_CH; rr++) {
+      const int tt = tc + rr;
+      if (tt > t_last) break;
+      const float* rrow = ring + ((tt - t_first) % R) * 5 * FI_COLS + col;
+      vs0 += (double)rrow[0 * FI_COLS] - (double)old[rr][0];
+      vs1 += (double)rrow[1 * FI_COLS] - (double)old[rr][1];
+      vs2 += (double)rrow[2 * FI_COLS] - (double)old[rr][2];
+      vs3 += (double)rrow[3 * FI_COLS] - (double)old[rr][3];
+      vs4 += (double)rrow[4 * FI_COLS] - (double)old[rr][4];
+      const int y = tt - m;
+      if (y >= y0 && col_valid) {
+        fout[(size_t)y * w + out_x] = solve2x2((float)vs0 * scale, (float)vs1 * scale, (float)vs2 * scale,
+                                               (float)vs3 * scale, (float)vs4 * scale);
+      }
+    }
+  }
+}
+
+// =====================================================================================
 // Stage a8: inter-level flow upsample = resize(prevFlow, INTER_LINEAR) * (1/pyr_scale)
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_upsample_flow(const float2* __restrict__ prev, int pw, int ph,
@@ -558,6 +707,16 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   src.image_stride = image_stride;
   cudaStream_t st = h->stream;
   const dim3 blk(32, 8);
+  // fused box-window iteration kernel: radius 2..19 (shared-memory ring of 2m+1 rows); the generic
+  // three-kernel path covers the Gaussian window and every other radius.
+  const bool use_fused = !bc.gaussian && bc.m >= 2 && bc.m <= 19 && !h->force_generic;
+  if (use_fused) {
+    const int smem = (FI_CH + 2 * bc.m + 1) * 5 * FI_COLS * (int)sizeof(float);
+    if (bc.m == 7)
+      OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else
+      OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
 
   float2* prev_flow = nullptr;
   int prev_w = 0, prev_h = 0;
@@ -613,13 +772,32 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       const bool last_it = it == p->iterations - 1;
       float2* fout = (last_level && last_it) ? (float2*)d_flow_out : (fin == cur ? alt : cur);
       TB(OFB_STAGE_ITERATION);
-      k_update_matrices<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_RA, h->d_RB, fin, h->d_MA, h->d_MB, w, hh,
-                                                                     f1_offset);
-      OFB_LAUNCH_CHECK(h);
-      k_blur_v<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_MA, h->d_MB, h->d_VA, h->d_VB, w, hh, bc);
-      OFB_LAUNCH_CHECK(h);
-      k_blur_h_solve<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_VA, h->d_VB, fout, w, hh, bc);
-      OFB_LAUNCH_CHECK(h);
+      if (use_fused) {
+        const int tw = FI_COLS - 2 * bc.m;
+        const int strips = (w + tw - 1) / tw;
+        const int slots = 2 * h->num_sms;
+        const int per = strips * n_pairs;
+        int segs = per >= slots ? 1 : slots / per;
+        int seg_rows = std::max(16, (hh + segs - 1) / segs);
+        segs = (hh + seg_rows - 1) / seg_rows;
+        const size_t smem = (size_t)(FI_CH + 2 * bc.m + 1) * 5 * FI_COLS * sizeof(float);
+        dim3 g(strips * segs, n_pairs);
+        if (bc.m == 7)
+          k_iter_box<7><<<g, FI_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
+                                                     seg_rows, strips);
+        else
+          k_iter_box<0><<<g, FI_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
+                                                     seg_rows, strips);
+        OFB_LAUNCH_CHECK(h);
+      } else {
+        k_update_matrices<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_RA, h->d_RB, fin, h->d_MA, h->d_MB, w, hh,
+                                                                       f1_offset);
+        OFB_LAUNCH_CHECK(h);
+        k_blur_v<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_MA, h->d_MB, h->d_VA, h->d_VB, w, hh, bc);
+        OFB_LAUNCH_CHECK(h);
+        k_blur_h_solve<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_VA, h->d_VB, fout, w, hh, bc);
+        OFB_LAUNCH_CHECK(h);
+      }
       TE();
       fin = fout;
     }
