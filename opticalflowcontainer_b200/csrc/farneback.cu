@@ -17,6 +17,9 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "fb_device.cuh"
+#include "fb_iter.cuh"
+#include "fb_pyramid.cuh"
 
 namespace ofb {
 
@@ -141,13 +144,6 @@ void prepare_blur(int winsize, bool gaussian, BlurCoef* bc) {
   bc->scale = 1.f;
 }
 
-// cv::getGaussianKernel(ksize, sigma, CV_32F) — half kernel k[0..r].
-constexpr int kMaxPyrRadius = 159;
-struct PyrCoef {
-  int r;
-  float k[kMaxPyrRadius + 1];
-};
-
 static int prepare_pyr(int ksize, double sigma, PyrCoef* pc) {
   int r = ksize / 2;
   if (r > kMaxPyrRadius) return OFB_ERR_INVALID_ARG;
@@ -166,81 +162,6 @@ static int prepare_pyr(int ksize, double sigma, PyrCoef* pc) {
   }
   for (int i = 0; i <= r; i++) pc->k[i] = (float)(t[r + i] / sum);
   return OFB_OK;
-}
-
-// =====================================================================================
-// Device helpers
-// =====================================================================================
-__device__ __forceinline__ int reflect101(int i, int n) {
-  if (n == 1) return 0;
-  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
-  return i;
-}
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-// cv::resize INTER_LINEAR source coordinate (resize.cpp): fx=(dx+0.5)*scale-0.5, clamp at both ends.
-__device__ __forceinline__ void linear_coord(int d, double scale, int src_n, int* s0, float* w1) {
-  float f = (float)((d + 0.5) * scale - 0.5);
-  int s = (int)floorf(f);
-  f -= (float)s;
-  if (s < 0) { f = 0.f; s = 0; }
-  if (s >= src_n - 1) { f = 0.f; s = src_n - 1; }
-  *s0 = s;
-  *w1 = f;
-}
-
-struct FrameSrc {
-  const uint8_t* a;  // frames [0, na)
-  const uint8_t* b;  // frames [na, ...)
-  int na;
-  size_t pitch, image_stride;
-  __device__ __forceinline__ const uint8_t* frame(int f) const {
-    return f < na ? a + (size_t)f * image_stride : b + (size_t)(f - na) * image_stride;
-  }
-};
-
-// =====================================================================================
-// Stage a2: pyramid level = convertTo(f32) + GaussianBlur(REFLECT_101) + resize(INTER_LINEAR)
-// One thread per level pixel; the blur is evaluated only at the (up to) 2x2 source samples the
-// bilinear resize reads.  Horizontal pass first, then vertical, as cv2's separable filter does.
-// =====================================================================================
-__global__ void __launch_bounds__(256) k_pyr_level(FrameSrc src, int W, int H, float* __restrict__ out, int w,
-                                                   int h, double sx_scale, double sy_scale, PyrCoef pc) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= w || y >= h) return;
-  const uint8_t* img = src.frame(blockIdx.z);
-  const int r = pc.r;
-  int sx0, sy0;
-  float fx, fy;
-  if (w == W) { sx0 = x; fx = 0.f; } else linear_coord(x, sx_scale, W, &sx0, &fx);
-  if (h == H) { sy0 = y; fy = 0.f; } else linear_coord(y, sy_scale, H, &sy0, &fy);
-  const bool need_c1 = fx != 0.f, need_r1 = fy != 0.f;
-  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;  // blurred(sy0, sx0), (sy0, sx0+1), (sy0+1, sx0), (sy0+1, sx0+1)
-  const int t_hi = need_r1 ? r + 1 : r;
-  const int i_hi = need_c1 ? r + 1 : r;
-  for (int t = -r; t <= t_hi; t++) {
-    const uint8_t* row = img + (size_t)reflect101(sy0 + t, H) * src.pitch;
-    float h0 = 0.f, h1 = 0.f;
-    for (int i = -r; i <= i_hi; i++) {
-      float v = (float)__ldg(row + reflect101(sx0 + i, W));
-      if (i <= r) h0 = fmaf(pc.k[abs(i)], v, h0);
-      if (i >= -r + 1) h1 = fmaf(pc.k[abs(i - 1)], v, h1);
-    }
-    if (t <= r) {
-      float kt = pc.k[abs(t)];
-      a00 = fmaf(kt, h0, a00);
-      a01 = fmaf(kt, h1, a01);
-    }
-    if (t >= -r + 1) {
-      float kt = pc.k[abs(t - 1)];
-      a10 = fmaf(kt, h0, a10);
-      a11 = fmaf(kt, h1, a11);
-    }
-  }
-  float top = a00 * (1.f - fx) + a01 * fx;
-  float bot = a10 * (1.f - fx) + a11 * fx;
-  out[((size_t)blockIdx.z * h + y) * w + x] = top * (1.f - fy) + bot * fy;
 }
 
 // =====================================================================================
@@ -316,71 +237,6 @@ __global__ void __launch_bounds__(256) k_polyexp(const float* __restrict__ I, fl
   }
 }
 
-// =====================================================================================
-// Stage a5: FarnebackUpdateMatrices (per pixel; bilinear gather of R1 at x + flow).
-// =====================================================================================
-__device__ __forceinline__ float border_w(int i, int n) {
-  // {0.14, 0.14, 0.4472, 0.4472, 0.4472} from each side, multiplicative
-  float s = 1.f;
-  if (i < 5) s *= (i < 2 ? 0.14f : 0.4472f);
-  if (i >= n - 5) s *= (n - 1 - i < 2 ? 0.14f : 0.4472f);
-  return s;
-}
-
-struct M5 {
-  float g11, g12, g22, h1, h2;
-};
-
-__device__ __forceinline__ M5 update_matrix_px(const float4* __restrict__ RA0, const float* __restrict__ RB0,
-                                               const float4* __restrict__ RA1, const float* __restrict__ RB1,
-                                               float2 fl, int x, int y, int w, int h) {
-  const size_t o = (size_t)y * w + x;
-  const float4 a0 = __ldg(RA0 + o);
-  const float b0 = __ldg(RB0 + o);
-  const float dx = fl.x, dy = fl.y;
-  float fx = (float)x + dx, fy = (float)y + dy;
-  const float flx = floorf(fx), fly = floorf(fy);
-  fx -= flx;
-  fy -= fly;
-  float r2, r3, r4, r5, r6;
-  // (unsigned)x1 < (unsigned)(w-1): compare in float first so huge/NaN flows stay outside
-  if (flx >= 0.f && flx < (float)(w - 1) && fly >= 0.f && fly < (float)(h - 1)) {
-    const int x1 = (int)flx, y1 = (int)fly;
-    const size_t p = (size_t)y1 * w + x1;
-    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-    const float4 q00 = __ldg(RA1 + p), q01 = __ldg(RA1 + p + 1), q10 = __ldg(RA1 + p + w), q11 = __ldg(RA1 + p + w + 1);
-    const float s00 = __ldg(RB1 + p), s01 = __ldg(RB1 + p + 1), s10 = __ldg(RB1 + p + w), s11 = __ldg(RB1 + p + w + 1);
-    r2 = a00 * q00.x + a01 * q01.x + a10 * q10.x + a11 * q11.x;
-    r3 = a00 * q00.y + a01 * q01.y + a10 * q10.y + a11 * q11.y;
-    r4 = a00 * q00.z + a01 * q01.z + a10 * q10.z + a11 * q11.z;
-    r5 = a00 * q00.w + a01 * q01.w + a10 * q10.w + a11 * q11.w;
-    r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
-    r4 = (a0.z + r4) * 0.5f;
-    r5 = (a0.w + r5) * 0.5f;
-    r6 = (b0 + r6) * 0.25f;
-  } else {
-    r2 = r3 = 0.f;
-    r4 = a0.z;
-    r5 = a0.w;
-    r6 = b0 * 0.5f;
-  }
-  r2 = (a0.x - r2) * 0.5f;
-  r3 = (a0.y - r3) * 0.5f;
-  r2 += r4 * dy + r6 * dx;
-  r3 += r6 * dy + r5 * dx;
-  if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-    const float s = border_w(x, w) * border_w(y, h);
-    r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
-  }
-  M5 m;
-  m.g11 = r4 * r4 + r6 * r6;
-  m.g12 = (r4 + r5) * r6;
-  m.g22 = r5 * r5 + r6 * r6;
-  m.h1 = r4 * r2 + r6 * r3;
-  m.h2 = r6 * r2 + r5 * r3;
-  return m;
-}
-
 __global__ void __launch_bounds__(256) k_update_matrices(const float4* __restrict__ RA, const float* __restrict__ RB,
                                                          const float2* __restrict__ flow, float4* __restrict__ MA,
                                                          float* __restrict__ MB, int w, int h, int f1_offset) {
@@ -427,11 +283,6 @@ __global__ void __launch_bounds__(256) k_blur_v(const float4* __restrict__ MA, c
   VB[base + (size_t)y * w + x] = sb;
 }
 
-__device__ __forceinline__ float2 solve2x2(float g11, float g12, float g22, float h1, float h2) {
-  float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
-  return make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
-}
-
 __global__ void __launch_bounds__(256) k_blur_h_solve(const float4* __restrict__ VA, const float* __restrict__ VB,
                                                       float2* __restrict__ flow, int w, int h, BlurCoef bc) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,155 +307,6 @@ __global__ void __launch_bounds__(256) k_blur_h_solve(const float4* __restrict__
   }
   const float sc = bc.scale;
   flow[base + (size_t)y * w + x] = solve2x2(s.x * sc, s.y * sc, s.z * sc, s.w * sc, sb * sc);
-}
-
-// =====================================================================================
-// Fused iteration kernel (box window): UpdateMatrices + (2m+1)^2 box blur + 2x2 solve in ONE pass.
-// HBM traffic per pixel-iteration = R0 (20 B) + R1 gather (20 B) + flow in (8 B) + flow out (8 B).
-//
-// A CTA (8 warps) owns a strip of FI_COLS = 256 matrix columns (2m of them halo) and a segment of
-// `seg_rows` output rows, and marches down it FI_CH = 4 matrix rows at a time:
-//   A1  every warp computes M for one half-row (4 px per lane, 32 px apart: coalesced R0/flow loads
-//       and L1-friendly gathers) into a shared staging row;
-//   A2  horizontal window sums H: each lane owns 4 adjacent columns, reads the 2m+4 staged values
-//       it needs as float4s and writes H into a ring of 2m+1 rows in shared memory;
-//   B   one thread per column keeps the vertical window sum as a running sum in DOUBLE (add the
-//       new H row, subtract the row leaving the window — exactly cv2's vsum scheme, so there is no
-//       float cancellation drift), scales, solves the 2x2 system and writes flow.
-// =====================================================================================
-constexpr int FI_COLS = 256;
-constexpr int FI_CH = 4;
-constexpr int FI_THREADS = 256;
-
-template <int MT>
-__global__ void __launch_bounds__(FI_THREADS, 2)
-    k_iter_box(const float4* __restrict__ RA, const float* __restrict__ RB, const float2* __restrict__ flow_in,
-               float2* __restrict__ flow_out, int w, int h, int f1_offset, int m_rt, float scale, int seg_rows,
-               int strips) {
-  const int m = MT > 0 ? MT : m_rt;
-  const int R = 2 * m + 1;
-  const int tw = FI_COLS - 2 * m;
-  extern __shared__ float smem[];
-  float* stage = smem;                          // [FI_CH][5][FI_COLS]
-  float* ring = smem + FI_CH * 5 * FI_COLS;     // [R][5][FI_COLS]
-
-  const int strip = blockIdx.x % strips;
-  const int seg = blockIdx.x / strips;
-  const int pair = blockIdx.y;
-  const int x_base = strip * tw - m;            // image x of strip column 0
-  const int y0 = seg * seg_rows;
-  const int y1 = min(y0 + seg_rows, h);         // exclusive
-  const int t_first = y0 - m, t_last = y1 - 1 + m;
-
-  const size_t n = (size_t)w * h;
-  const float4* RA0 = RA + (size_t)pair * n;
-  const float* RB0 = RB + (size_t)pair * n;
-  const float4* RA1 = RA + (size_t)(pair + f1_offset) * n;
-  const float* RB1 = RB + (size_t)(pair + f1_offset) * n;
-  const float2* fin = flow_in + (size_t)pair * n;
-  float2* fout = flow_out + (size_t)pair * n;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int a_row = warp >> 1, a_half = warp & 1;
-  const int col = tid;                          // phase-B column
-  const int out_x = x_base + col;
-  const bool col_valid = col >= m && col < FI_COLS - m && out_x < w;
-
-  double vs0 = 0, vs1 = 0, vs2 = 0, vs3 = 0, vs4 = 0;
-
-  for (int tc = t_first; tc <= t_last; tc += FI_CH) {
-    // ---------------- A1: matrices of row tc + a_row -> staging
-    const int t = tc + a_row;
-    if (t <= t_last) {
-      const int y = clampi(t, 0, h - 1);
-      float* srow = stage + a_row * 5 * FI_COLS;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int c = a_half * 128 + lane + 32 * j;
-        const int x = clampi(x_base + c, 0, w - 1);
-        const float2 fl = __ldg(fin + (size_t)y * w + x);
-        const M5 mm = update_matrix_px(RA0, RB0, RA1, RB1, fl, x, y, w, h);
-        srow[0 * FI_COLS + c] = mm.g11;
-        srow[1 * FI_COLS + c] = mm.g12;
-        srow[2 * FI_COLS + c] = mm.g22;
-        srow[3 * FI_COLS + c] = mm.h1;
-        srow[4 * FI_COLS + c] = mm.h2;
-      }
-    }
-    // rows leaving the window: their ring slots are overwritten in A2, so fetch them now
-    float old[FI_CH][5];
-#pragma unroll
-    for (int rr = 0; rr < FI_CH; rr++) {
-      const int tt = tc + rr;
-      const bool have = (tt - t_first >= R) && tt <= t_last;
-      const int slot = (tt - t_first) % R;
-#pragma unroll
-      for (int ch = 0; ch < 5; ch++) old[rr][ch] = have ? ring[(slot * 5 + ch) * FI_COLS + col] : 0.f;
-    }
-    __syncthreads();
-    // ---------------- A2: horizontal window sums of the staged rows -> ring
-    if (t <= t_last) {
-      const float* srow = stage + a_row * 5 * FI_COLS;
-      float* rrow = ring + ((t - t_first) % R) * 5 * FI_COLS;
-      const int q0 = a_half * 128 + 4 * lane;   // first of this lane's 4 columns
-      const int kq = (m + 3) >> 2;              // quads to each side
-#pragma unroll
-      for (int ch = 0; ch < 5; ch++) {
-        const float* s = srow + ch * FI_COLS;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        if (MT > 0) {
-#pragma unroll
-          for (int k = -((MT + 3) / 4); k <= (MT + 3) / 4; k++) {
-            const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
-            const float4 v = *reinterpret_cast<const float4*>(s + cq);
-            const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const int d = 4 * k + i;  // offset from q0
-              if (d >= 0 - MT && d <= 0 + MT) s0 += e[i];
-              if (d >= 1 - MT && d <= 1 + MT) s1 += e[i];
-              if (d >= 2 - MT && d <= 2 + MT) s2 += e[i];
-              if (d >= 3 - MT && d <= 3 + MT) s3 += e[i];
-            }
-          }
-        } else {
-          for (int k = -kq; k <= kq; k++) {
-            const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
-            const float4 v = *reinterpret_cast<const float4*>(s + cq);
-            const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const int d = 4 * k + i;
-              if (d >= 0 - m && d <= 0 + m) s0 += e[i];
-              if (d >= 1 - m && d <= 1 + m) s1 += e[i];
-              if (d >= 2 - m && d <= 2 + m) s2 += e[i];
-              if (d >= 3 - m && d <= 3 + m) s3 += e[i];
-            }
-          }
-        }
-        *reinterpret_cast<float4*>(rrow + ch * FI_COLS + q0) = make_float4(s0, s1, s2, s3);
-      }
-    }
-    __syncthreads();
-    // ---------------- B: vertical running sums (double) + solve
-#pragma unroll
-    for (int rr = 0; rr < FI_CH; rr++) {
-      const int tt = tc + rr;
-      if (tt > t_last) break;
-      const float* rrow = ring + ((tt - t_first) % R) * 5 * FI_COLS + col;
-      vs0 += (double)rrow[0 * FI_COLS] - (double)old[rr][0];
-      vs1 += (double)rrow[1 * FI_COLS] - (double)old[rr][1];
-      vs2 += (double)rrow[2 * FI_COLS] - (double)old[rr][2];
-      vs3 += (double)rrow[3 * FI_COLS] - (double)old[rr][3];
-      vs4 += (double)rrow[4 * FI_COLS] - (double)old[rr][4];
-      const int y = tt - m;
-      if (y >= y0 && col_valid) {
-        fout[(size_t)y * w + out_x] = solve2x2((float)vs0 * scale, (float)vs1 * scale, (float)vs2 * scale,
-                                               (float)vs3 * scale, (float)vs4 * scale);
-      }
-    }
-  }
 }
 
 // =====================================================================================
@@ -753,9 +455,17 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
     if (prepare_pyr(lv.ksize, lv.sigma, &pyc) != OFB_OK)
       return set_error(h, OFB_ERR_INVALID_ARG, "pyramid smoothing kernel too large (ksize=%d)", lv.ksize);
     TB(OFB_STAGE_PYRAMID);
-    k_pyr_level<<<grid2d(w, hh, frames, blk), blk, 0, st>>>(src, width, height, h->d_img, w, hh,
-                                                            1.0 / ((double)w / width), 1.0 / ((double)hh / height), pyc);
-    OFB_LAUNCH_CHECK(h);
+    {
+      // pass H writes hb[frames][H][w] into d_MA (free here: the generic iteration path only uses it
+      // after the pyramid stage of the level), pass V writes the level image.
+      float* hb = reinterpret_cast<float*>(h->d_MA);
+      dim3 gh((w + 127) / 128, height, frames);
+      k_pyr_h<<<gh, 128, 0, st>>>(src, width, height, hb, w, 1.0 / ((double)w / width), pyc);
+      OFB_LAUNCH_CHECK(h);
+      dim3 bv(128, 2), gv((w + 127) / 128, (hh + 1) / 2, frames);
+      k_pyr_v<<<gv, bv, 0, st>>>(hb, height, h->d_img, w, hh, 1.0 / ((double)hh / height), pyc);
+      OFB_LAUNCH_CHECK(h);
+    }
     TE();
     TB(OFB_STAGE_POLYEXP);
     {

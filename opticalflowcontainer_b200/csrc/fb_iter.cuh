@@ -1,0 +1,179 @@
+// fb_iter.cuh — fused Farneback iteration kernel (box window):
+// FarnebackUpdateMatrices + FarnebackUpdateFlow_Blur in ONE pass over the level.
+#pragma once
+#include "fb_device.cuh"
+
+namespace ofb {
+
+// HBM traffic per pixel-iteration = R0 (20 B) + R1 gather (20 B) + flow in (8 B) + flow out (8 B).
+//
+// A CTA (8 warps) owns a strip of FI_COLS = 256 matrix columns (2m of them halo) and a segment of
+// `seg_rows` output rows, and marches down it FI_CH = 4 matrix rows at a time:
+//   A1  every warp computes M for one half-row (4 px per lane, 32 px apart: coalesced R0/flow loads
+//       and L1-friendly gathers; all 40 loads of the 4 px are issued before the first use, and the
+//       flow of the next chunk is prefetched) into a shared staging row;
+//   A2  horizontal window sums H: each lane owns 4 adjacent columns, reads the 2m+4 staged values
+//       it needs as float4s and writes H into a ring of 2m+1 rows in shared memory;
+//   B   one thread per column keeps the vertical window sum as a running sum in DOUBLE (add the
+//       new H row, subtract the row leaving the window — exactly cv2's vsum scheme, so there is no
+//       float cancellation drift), scales, solves the 2x2 system and writes flow.
+constexpr int FI_COLS = 256;
+constexpr int FI_CH = 4;
+constexpr int FI_THREADS = 256;
+
+template <int MT>
+__global__ void __launch_bounds__(FI_THREADS, 2)
+    k_iter_box(const float4* __restrict__ RA, const float* __restrict__ RB, const float2* __restrict__ flow_in,
+               float2* __restrict__ flow_out, int w, int h, int f1_offset, int m_rt, float scale, int seg_rows,
+               int strips) {
+  const int m = MT > 0 ? MT : m_rt;
+  const int R = 2 * m + 1;
+  const int tw = FI_COLS - 2 * m;
+  extern __shared__ float smem[];
+  float* stage = smem;                          // [FI_CH][5][FI_COLS]
+  float* ring = smem + FI_CH * 5 * FI_COLS;     // [R][5][FI_COLS]
+
+  const int strip = blockIdx.x % strips;
+  const int seg = blockIdx.x / strips;
+  const int pair = blockIdx.y;
+  const int x_base = strip * tw - m;            // image x of strip column 0
+  const int y0 = seg * seg_rows;
+  const int y1 = min(y0 + seg_rows, h);         // exclusive
+  const int t_first = y0 - m, t_last = y1 - 1 + m;
+
+  const size_t n = (size_t)w * h;
+  const float4* RA0 = RA + (size_t)pair * n;
+  const float* RB0 = RB + (size_t)pair * n;
+  const float4* RA1 = RA + (size_t)(pair + f1_offset) * n;
+  const float* RB1 = RB + (size_t)(pair + f1_offset) * n;
+  const float2* fin = flow_in + (size_t)pair * n;
+  float2* fout = flow_out + (size_t)pair * n;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int a_row = warp >> 1, a_half = warp & 1;
+  const int col = tid;                          // phase-B column
+  const int out_x = x_base + col;
+  const bool col_valid = col >= m && col < FI_COLS - m && out_x < w;
+
+  double vs0 = 0, vs1 = 0, vs2 = 0, vs3 = 0, vs4 = 0;
+
+  // flow of the 4 pixels this lane handles in A1, prefetched one chunk ahead so that the
+  // flow -> gather dependency never costs two memory latencies back to back
+  float2 fl[4];
+  int xs[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) xs[j] = clampi(x_base + a_half * 128 + lane + 32 * j, 0, w - 1);
+  {
+    const int y = clampi(t_first + a_row, 0, h - 1);
+#pragma unroll
+    for (int j = 0; j < 4; j++) fl[j] = __ldg(fin + y * w + xs[j]);
+  }
+
+  for (int tc = t_first; tc <= t_last; tc += FI_CH) {
+    // ---------------- A1: matrices of row tc + a_row -> staging
+    const int t = tc + a_row;
+    if (t <= t_last) {
+      const int y = clampi(t, 0, h - 1);
+      float* srow = stage + a_row * 5 * FI_COLS + a_half * 128 + lane;
+      UmLoads L[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) um_issue(L[j], RA0, RB0, RA1, RB1, fl[j], xs[j], y, w, h);
+      {  // next chunk's flow (clamped row: always a valid address)
+        const int yn = clampi(t + FI_CH, 0, h - 1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) fl[j] = __ldg(fin + yn * w + xs[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const M5 mm = um_finish(L[j], xs[j], y, w, h);
+        srow[0 * FI_COLS + 32 * j] = mm.g11;
+        srow[1 * FI_COLS + 32 * j] = mm.g12;
+        srow[2 * FI_COLS + 32 * j] = mm.g22;
+        srow[3 * FI_COLS + 32 * j] = mm.h1;
+        srow[4 * FI_COLS + 32 * j] = mm.h2;
+      }
+    }
+    // rows leaving the window: their ring slots are overwritten in A2, so fetch them now
+    float old[FI_CH][5];
+#pragma unroll
+    for (int rr = 0; rr < FI_CH; rr++) {
+      const int tt = tc + rr;
+      const bool have = (tt - t_first >= R) && tt <= t_last;
+      const int slot = (tt - t_first) % R;
+#pragma unroll
+      for (int ch = 0; ch < 5; ch++) old[rr][ch] = have ? ring[(slot * 5 + ch) * FI_COLS + col] : 0.f;
+    }
+    __syncthreads();
+    // ---------------- A2: horizontal window sums of the staged rows -> ring
+    if (t <= t_last) {
+      const float* srow = stage + a_row * 5 * FI_COLS;
+      float* rrow = ring + ((t - t_first) % R) * 5 * FI_COLS;
+      const int q0 = a_half * 128 + 4 * lane;   // first of this lane's 4 columns
+#pragma unroll
+      for (int ch = 0; ch < 5; ch++) {
+        const float* s = srow + ch * FI_COLS;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (MT > 0) {
+          // offsets d in [3-MT, MT] from q0 lie inside all four windows: sum them once
+          float core = 0.f;
+#pragma unroll
+          for (int k = -((MT + 3) / 4); k <= (MT + 3) / 4; k++) {
+            const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
+            const float4 v = *reinterpret_cast<const float4*>(s + cq);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int d = 4 * k + i;
+              if (d >= 3 - MT && d <= MT) {
+                core += e[i];
+              } else {
+                if (d >= 0 - MT && d <= 0 + MT) s0 += e[i];
+                if (d >= 1 - MT && d <= 1 + MT) s1 += e[i];
+                if (d >= 2 - MT && d <= 2 + MT) s2 += e[i];
+                if (d >= 3 - MT && d <= 3 + MT) s3 += e[i];
+              }
+            }
+          }
+          s0 += core; s1 += core; s2 += core; s3 += core;
+        } else {
+          const int kq = (m + 3) >> 2;          // quads to each side
+          for (int k = -kq; k <= kq; k++) {
+            const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
+            const float4 v = *reinterpret_cast<const float4*>(s + cq);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int d = 4 * k + i;
+              if (d >= 0 - m && d <= 0 + m) s0 += e[i];
+              if (d >= 1 - m && d <= 1 + m) s1 += e[i];
+              if (d >= 2 - m && d <= 2 + m) s2 += e[i];
+              if (d >= 3 - m && d <= 3 + m) s3 += e[i];
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(rrow + ch * FI_COLS + q0) = make_float4(s0, s1, s2, s3);
+      }
+    }
+    __syncthreads();
+    // ---------------- B: vertical running sums (double) + solve
+#pragma unroll
+    for (int rr = 0; rr < FI_CH; rr++) {
+      const int tt = tc + rr;
+      if (tt > t_last) break;
+      const float* rrow = ring + ((tt - t_first) % R) * 5 * FI_COLS + col;
+      vs0 += (double)rrow[0 * FI_COLS] - (double)old[rr][0];
+      vs1 += (double)rrow[1 * FI_COLS] - (double)old[rr][1];
+      vs2 += (double)rrow[2 * FI_COLS] - (double)old[rr][2];
+      vs3 += (double)rrow[3 * FI_COLS] - (double)old[rr][3];
+      vs4 += (double)rrow[4 * FI_COLS] - (double)old[rr][4];
+      const int y = tt - m;
+      if (y >= y0 && col_valid) {
+        fout[(size_t)y * w + out_x] = solve2x2((float)vs0 * scale, (float)vs1 * scale, (float)vs2 * scale,
+                                               (float)vs3 * scale, (float)vs4 * scale);
+      }
+    }
+  }
+}
+
+}  // namespace ofb

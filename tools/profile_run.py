@@ -27,3 +27,12 @@ for _ in range(calls):
     eng.farneback_device(B, d.data_ptr(), d.data_ptr() + B * W * H, W, H, W, W * H, flow.data_ptr())
 eng.synchronize()
 print("ok", float(flow[0, H // 2, W // 2, 0]), eng.launch_count)
+if os.environ.get("OFB_STAGES", "1") == "1":
+    eng.timing_enable(True)
+    K = 5
+    for _ in range(K):
+        eng.farneback_device(B, d.data_ptr(), d.data_ptr() + B * W * H, W, H, W, W * H, flow.data_ptr())
+    st = eng.timing_read()
+    eng.timing_enable(False)
+    tot = sum(v[0] for v in st.values())
+    print("per-call ms (batch %d): " % B + ", ".join("%s %.3f" % (k, v[0] / K) for k, v in st.items()) + " | total %.3f -> %.0f pairs/s" % (tot / K, B * K / tot * 1e3))
