@@ -59,7 +59,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int validate_farneback(ofb_handle* h, int n, int width, int height, const ofb_farneback_params* p) {
   if (!p) return set_error(h, OFB_ERR_INVALID_ARG, "params is NULL");
   if (n < 1) return set_error(h, OFB_ERR_INVALID_ARG, "need at least one frame pair");
-  if (width < 1 || height < 1) return set_error(h, OFB_ERR_INVALID_ARG, "empty image");
+  if (width < 2 || height < 2) return set_error(h, OFB_ERR_INVALID_ARG, "image must be at least 2x2");
   if (n > h->max_batch || width > h->max_w || height > h->max_h || (size_t)width * height > (size_t)h->max_w * h->max_h)
     return set_error(h, OFB_ERR_CAPACITY, "request %d x %dx%d exceeds handle capacity %d x %dx%d", n, width, height,
                      h->max_batch, h->max_w, h->max_h);
@@ -141,7 +141,7 @@ int ofb_destroy(ofb_handle* h) {
   cudaFree(h->d_MA); cudaFree(h->d_MB); cudaFree(h->d_VA); cudaFree(h->d_VB);
   for (int i = 0; i < 3; i++) cudaFree(h->d_flow[i]);
   cudaFree(h->d_flow_out); cudaFree(h->d_init_flow); cudaFree(h->d_stats); cudaFree(h->d_mask);
-  cudaFree(h->d_scratch);
+  cudaFree(h->d_scratch); cudaFree(h->d_sel);
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -202,6 +202,7 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
   CREATE_CUDA(cudaMalloc(&h->d_init_flow, max_batch * N * sizeof(float2)));
   CREATE_CUDA(cudaMalloc(&h->d_stats, 64 * sizeof(double) * (size_t)max_batch));
   CREATE_CUDA(cudaMalloc(&h->d_mask, N));
+  CREATE_CUDA(cudaMalloc(&h->d_sel, (size_t)max_batch * 4104 * sizeof(uint32_t)));
   h->h_src_bytes = h->src_image_stride * frames;
   h->h_flow_bytes = max_batch * N * sizeof(float2);
   CREATE_CUDA(cudaHostAlloc(&h->h_src, h->h_src_bytes, cudaHostAllocDefault));

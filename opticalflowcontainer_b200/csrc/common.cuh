@@ -70,6 +70,7 @@ struct ofb_handle {
   const float* last_flow = nullptr;
   int last_n = 0, last_w = 0, last_h = 0;
   double* d_stats = nullptr;
+  uint32_t* d_sel = nullptr;   // radix-select state of ofb_flow_u_stats (reduce.cu)
   uint8_t* d_mask = nullptr;
   float* d_scratch = nullptr;  // median selection scratch
   size_t scratch_bytes = 0;

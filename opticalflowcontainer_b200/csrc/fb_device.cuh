@@ -74,16 +74,17 @@ __device__ __forceinline__ void um_issue(UmLoads& L, const float4* __restrict__ 
   // huge / NaN flows stay outside.  Outside pixels gather from (0,0) (in bounds, result discarded).
   L.inside = flx >= 0.f && flx < (float)(w - 1) && fly >= 0.f && fly < (float)(h - 1);
   const int x1 = L.inside ? (int)flx : 0, y1 = L.inside ? (int)fly : 0;
-  const int p = y1 * w + x1;
-  const int p2 = p + (h > 1 ? w : 0), dxo = w > 1 ? 1 : 0;
-  L.q00 = __ldg(RA1 + p);
-  L.q01 = __ldg(RA1 + p + dxo);
-  L.q10 = __ldg(RA1 + p2);
-  L.q11 = __ldg(RA1 + p2 + dxo);
-  L.s00 = __ldg(RB1 + p);
-  L.s01 = __ldg(RB1 + p + dxo);
-  L.s10 = __ldg(RB1 + p2);
-  L.s11 = __ldg(RB1 + p2 + dxo);
+  // w >= 2 and h >= 2 is validated at the API (constant +1 / +w offsets keep the address math short)
+  const float4* pa = RA1 + (y1 * w + x1);
+  const float* pb = RB1 + (y1 * w + x1);
+  L.q00 = __ldg(pa);
+  L.q01 = __ldg(pa + 1);
+  L.q10 = __ldg(pa + w);
+  L.q11 = __ldg(pa + w + 1);
+  L.s00 = __ldg(pb);
+  L.s01 = __ldg(pb + 1);
+  L.s10 = __ldg(pb + w);
+  L.s11 = __ldg(pb + w + 1);
 }
 
 __device__ __forceinline__ M5 um_finish(const UmLoads& L, int x, int y, int w, int h) {

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
     for (int j = 0; j < 4; j++) fl[j] = __ldg(fin + y * w + xs[j]);
   }
 
+  int slot0 = 0;  // ring slot of row tc
   for (int tc = t_first; tc <= t_last; tc += FI_CH) {
     // ---------------- A1: matrices of row tc + a_row -> staging
     const int t = tc + a_row;
@@ -94,49 +95,64 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
         srow[4 * FI_COLS + 32 * j] = mm.h2;
       }
     }
-    // rows leaving the window: their ring slots are overwritten in A2, so fetch them now
-    float old[FI_CH][5];
+    // ring slots of the chunk's rows (slot = (row - t_first) mod R, kept incrementally)
+    int slot[FI_CH];
 #pragma unroll
     for (int rr = 0; rr < FI_CH; rr++) {
-      const int tt = tc + rr;
-      const bool have = (tt - t_first >= R) && tt <= t_last;
-      const int slot = (tt - t_first) % R;
+      int sl = slot0 + rr;
+      slot[rr] = sl >= R ? sl - R : sl;
+    }
+    // rows leaving the window: their ring slots are overwritten in A2, so fetch them now
+    float old[FI_CH][5];
+    const int n_done = tc - t_first;            // rows already in the ring
 #pragma unroll
-      for (int ch = 0; ch < 5; ch++) old[rr][ch] = have ? ring[(slot * 5 + ch) * FI_COLS + col] : 0.f;
+    for (int rr = 0; rr < FI_CH; rr++) {
+      const bool have_old = n_done + rr >= R;   // row tc+rr-R exists (its slot is slot[rr]; R > FI_CH)
+#pragma unroll
+      for (int ch = 0; ch < 5; ch++) old[rr][ch] = have_old ? ring[(slot[rr] * 5 + ch) * FI_COLS + col] : 0.f;
     }
     __syncthreads();
     // ---------------- A2: horizontal window sums of the staged rows -> ring
     if (t <= t_last) {
       const float* srow = stage + a_row * 5 * FI_COLS;
-      float* rrow = ring + ((t - t_first) % R) * 5 * FI_COLS;
+      float* rrow = ring + slot[0] * 5 * FI_COLS;
+      if (a_row == 1) rrow = ring + slot[1] * 5 * FI_COLS;
+      if (a_row == 2) rrow = ring + slot[2] * 5 * FI_COLS;
+      if (a_row == 3) rrow = ring + slot[3] * 5 * FI_COLS;
       const int q0 = a_half * 128 + 4 * lane;   // first of this lane's 4 columns
 #pragma unroll
       for (int ch = 0; ch < 5; ch++) {
         const float* s = srow + ch * FI_COLS;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        float s0, s1, s2, s3;
         if (MT > 0) {
-          // offsets d in [3-MT, MT] from q0 lie inside all four windows: sum them once
-          float core = 0.f;
+          constexpr int KQ = (MT + 3) / 4;
+          float e[(2 * KQ + 1) * 4];            // e[d + 4*KQ] = staged value at column q0 + d
 #pragma unroll
-          for (int k = -((MT + 3) / 4); k <= (MT + 3) / 4; k++) {
+          for (int k = -KQ; k <= KQ; k++) {
             const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
             const float4 v = *reinterpret_cast<const float4*>(s + cq);
-            const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const int d = 4 * k + i;
-              if (d >= 3 - MT && d <= MT) {
-                core += e[i];
-              } else {
-                if (d >= 0 - MT && d <= 0 + MT) s0 += e[i];
-                if (d >= 1 - MT && d <= 1 + MT) s1 += e[i];
-                if (d >= 2 - MT && d <= 2 + MT) s2 += e[i];
-                if (d >= 3 - MT && d <= 3 + MT) s3 += e[i];
-              }
-            }
+            e[(k + KQ) * 4 + 0] = v.x; e[(k + KQ) * 4 + 1] = v.y; e[(k + KQ) * 4 + 2] = v.z; e[(k + KQ) * 4 + 3] = v.w;
           }
-          s0 += core; s1 += core; s2 += core; s3 += core;
+          constexpr int O = 4 * KQ;
+          // d in [3-MT, MT] lies inside all four windows: sum once; then suffix sums on the left
+          // (d = 2-MT .. -MT) and prefix sums on the right (d = MT+1 .. MT+3)
+          float core = e[O + 3 - MT];
+#pragma unroll
+          for (int d = 4 - MT; d <= MT; d++) core += e[O + d];
+          float l = e[O + 2 - MT];
+          s2 = core + l;
+          l += e[O + 1 - MT];
+          s1 = core + l;
+          l += e[O - MT];
+          s0 = core + l;
+          float r = e[O + MT + 1];
+          s1 += r;
+          r += e[O + MT + 2];
+          s2 += r;
+          r += e[O + MT + 3];
+          s3 = core + r;
         } else {
+          s0 = s1 = s2 = s3 = 0.f;
           const int kq = (m + 3) >> 2;          // quads to each side
           for (int k = -kq; k <= kq; k++) {
             const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
@@ -157,22 +173,25 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
     }
     __syncthreads();
     // ---------------- B: vertical running sums (double) + solve
+    const int nrows = min(FI_CH, t_last - tc + 1);
 #pragma unroll
     for (int rr = 0; rr < FI_CH; rr++) {
-      const int tt = tc + rr;
-      if (tt > t_last) break;
-      const float* rrow = ring + ((tt - t_first) % R) * 5 * FI_COLS + col;
-      vs0 += (double)rrow[0 * FI_COLS] - (double)old[rr][0];
-      vs1 += (double)rrow[1 * FI_COLS] - (double)old[rr][1];
-      vs2 += (double)rrow[2 * FI_COLS] - (double)old[rr][2];
-      vs3 += (double)rrow[3 * FI_COLS] - (double)old[rr][3];
-      vs4 += (double)rrow[4 * FI_COLS] - (double)old[rr][4];
-      const int y = tt - m;
-      if (y >= y0 && col_valid) {
-        fout[(size_t)y * w + out_x] = solve2x2((float)vs0 * scale, (float)vs1 * scale, (float)vs2 * scale,
-                                               (float)vs3 * scale, (float)vs4 * scale);
+      if (rr < nrows) {
+        const float* rrow = ring + slot[rr] * 5 * FI_COLS + col;
+        vs0 += (double)rrow[0 * FI_COLS] - (double)old[rr][0];
+        vs1 += (double)rrow[1 * FI_COLS] - (double)old[rr][1];
+        vs2 += (double)rrow[2 * FI_COLS] - (double)old[rr][2];
+        vs3 += (double)rrow[3 * FI_COLS] - (double)old[rr][3];
+        vs4 += (double)rrow[4 * FI_COLS] - (double)old[rr][4];
+        const int y = tc + rr - m;
+        if (y >= y0 && col_valid) {
+          fout[y * w + out_x] = solve2x2((float)vs0 * scale, (float)vs1 * scale, (float)vs2 * scale,
+                                         (float)vs3 * scale, (float)vs4 * scale);
+        }
       }
     }
+    slot0 += FI_CH;
+    if (slot0 >= R) slot0 -= R;
   }
 }
 

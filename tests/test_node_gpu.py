@@ -1,0 +1,96 @@
+"""Node-level contract (frame in -> Vector3Stamped out) and the on-device flow reduction,
+against the same arithmetic done with NumPy on the cv2 flow (what the reference nodes do:
+lfn3_sub_node.py:205-222, opticalflow_node.py:97-109, sub_n_pub_lfn3_node.py:195-210)."""
+from collections import deque
+
+import numpy as np
+import pytest
+
+from oracle import cv2_oracle as C
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_flow_u_stats_matches_numpy(engine_factory):
+    a, b = synth.synth_warp_pair(240, 320, 5)
+    eng = engine_factory(320, 240, 2)
+    flow = eng.farneback(a, b)
+    mean, med = eng.flow_u_stats(1)
+    assert abs(mean[0] - float(np.mean(flow[..., 0].astype(np.float64)))) < 1e-6
+    assert med[0] == np.float32(np.median(flow[..., 0]))          # exact selection
+    # odd count + mask
+    mask = np.zeros((240, 320), np.uint8)
+    mask[10:51, 20:61] = 1                                          # 41*41 = 1681 (odd)
+    mean, med = eng.flow_u_stats(1, mask=mask)
+    sel = flow[..., 0][mask.astype(bool)]
+    assert abs(mean[0] - float(sel.astype(np.float64).mean())) < 1e-6
+    assert med[0] == np.float32(np.median(sel))
+    # batch of 2
+    pairs = [synth.synth_pair(240, 320, 70 + i, (2.0 + i, -1.0)) for i in range(2)]
+    out = eng.farneback_batch([p[0] for p in pairs], [p[1] for p in pairs])
+    mean, med = eng.flow_u_stats(2)
+    for i in range(2):
+        assert abs(mean[i] - float(out[i, ..., 0].astype(np.float64).mean())) < 1e-6
+        assert med[i] == np.float32(np.median(out[i, ..., 0]))
+
+
+def test_flow_u_stats_negative_and_empty_mask(engine_factory):
+    a, b = synth.synth_pair(120, 160, 9, (-3.5, 1.0))
+    eng = engine_factory(160, 120)
+    flow = eng.farneback(a, b)
+    _, med = eng.flow_u_stats(1)
+    assert med[0] == np.float32(np.median(flow[..., 0])) and med[0] < 0
+    mean, med = eng.flow_u_stats(1, mask=np.zeros((120, 160), np.uint8))
+    assert np.isnan(mean[0]) and np.isnan(med[0])
+
+
+@pytest.mark.parametrize("reduce,on_device", [("median", False), ("mean", False), ("median", True), ("mean", True)])
+def test_node_velocity_contract(built_lib, reduce, on_device):
+    from opticalflowcontainer_b200.node import FarnebackVelocityNode
+    frames = synth.panning_sequence(120, 160, 5, seed=3, max_shift=3.0)
+    node = FarnebackVelocityNode(width=160, height=120, pixel_to_meter=0.0011, reduce=reduce,
+                                 on_device_reduce=on_device)
+    stamps = [0.0, 0.033, 0.066, 0.066, 0.1]            # a repeated stamp -> dt <= 0 -> 1e-3
+    buf = deque(maxlen=5)
+    prev, prev_t = None, None
+    for f, t in zip(frames, stamps):
+        bgr = np.repeat(f[..., None], 3, axis=2)
+        out = node.image_callback(bgr, t, "bgr8")
+        if prev is None:
+            assert out is None                           # first frame only primes the state
+            prev, prev_t = f, t
+            continue
+        dt = t - prev_t
+        if dt <= 0:
+            dt = 1e-3
+        flow = C.farneback(prev, f)
+        u = np.mean(flow[..., 0]) if reduce == "mean" else np.median(flow[..., 0])
+        vx = float(u / dt * 0.0011)
+        buf.append(vx)
+        raw, smooth = out
+        assert raw.frame_id == "camera_link" and raw.stamp == t and raw.vector[1:] == (0.0, 0.0)
+        assert abs(raw.vector[0] - vx) <= 1e-3 * max(1.0, abs(vx)) + 1e-6, (raw.vector[0], vx)
+        assert abs(smooth.vector[0] - float(np.mean(buf))) <= 1e-3 * max(1.0, abs(vx)) + 1e-6
+        prev, prev_t = f, t
+
+
+def test_gray_conversion_is_cv2_exact():
+    cv2 = pytest.importorskip("cv2")
+    from opticalflowcontainer_b200.node import to_gray_u8
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(97, 131, 3), dtype=np.uint8)
+    assert np.array_equal(to_gray_u8(img, "bgr8"), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    assert np.array_equal(to_gray_u8(img, "rgb8"), cv2.cvtColor(img, cv2.COLOR_RGB2GRAY))
+
+
+def test_junction_mask_matches_reference_logic():
+    from opticalflowcontainer_b200.node import junction_mask
+    pts = [(5.2, 7.9), (159, 119), (-3, 4), (80, 60)]
+    m = junction_mask(pts, 120, 160)
+    ref = np.zeros((120, 160), bool)
+    for p in pts:
+        x, y = int(p[0]), int(p[1])
+        if 0 <= x < 160 and 0 <= y < 120:
+            ref[max(0, y - 5):min(120, y + 6), max(0, x - 5):min(160, x + 6)] = True
+    assert np.array_equal(m, ref)
