@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include <new>
 
 #include "common.cuh"
@@ -145,6 +147,9 @@ int ofb_destroy(ofb_handle* h) {
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OFB_OK;
@@ -180,10 +185,14 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
   } while (0)
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
   CREATE_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   {
     const char* fg = getenv("OFB_FORCE_GENERIC");
     h->force_generic = fg && fg[0] == '1';
+    const char* np = getenv("OFB_NO_PIPELINE");
+    h->no_pipeline = np && np[0] == '1';
   }
   const size_t N = (size_t)max_width * max_height;
   const size_t frames = 2 * (size_t)max_batch;
@@ -273,6 +282,47 @@ int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const 
   const size_t istride = pitch * height;
   const size_t fl_img = (size_t)width * height * 2;
   const float* init = nullptr;
+  if (pinned && n > 1 && !h->no_pipeline) {
+    // Pipelined path: chunks of `c` pairs; H2D of chunk i+1 (copy-in stream) and D2H of chunk i-1
+    // (copy-out stream) overlap the kernels of chunk i (handle stream).  PCIe is full duplex, so the
+    // steady state is bounded by max(compute, D2H of the 8N-byte field).
+    const int c = n >= 8 ? 2 : 1;
+    const int chunks = (n + c - 1) / c;
+    while ((int)h->pipe_ev.size() < 2 * chunks) {
+      cudaEvent_t e;
+      OFB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->pipe_ev.push_back(e);
+    }
+    const bool use_init = (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) != 0;
+    for (int ci = 0; ci < chunks; ci++) {
+      const int i0 = ci * c, cn = std::min(c, n - i0);
+      uint8_t* base = h->d_src + (size_t)2 * i0 * istride;   // [prev x cn][next x cn]
+      for (int i = 0; i < cn; i++) {
+        OFB_CUDA(h, cudaMemcpy2DAsync(base + (size_t)i * istride, pitch, prev[i0 + i], stride_bytes, width, height,
+                                      cudaMemcpyHostToDevice, h->s_in));
+        OFB_CUDA(h, cudaMemcpy2DAsync(base + (size_t)(cn + i) * istride, pitch, next[i0 + i], stride_bytes, width,
+                                      height, cudaMemcpyHostToDevice, h->s_in));
+        if (use_init)
+          OFB_CUDA(h, cudaMemcpy2DAsync(h->d_init_flow + (i0 + i) * fl_img, row_flow, flow[i0 + i], flow_stride_bytes,
+                                        row_flow, height, cudaMemcpyHostToDevice, h->s_in));
+      }
+      OFB_CUDA(h, cudaEventRecord(h->pipe_ev[2 * ci], h->s_in));
+      OFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->pipe_ev[2 * ci], 0));
+      st = farneback_run(h, cn, false, base, base + (size_t)cn * istride, width, height, pitch, istride,
+                         h->d_flow_out + i0 * fl_img, use_init ? h->d_init_flow + i0 * fl_img : nullptr, params);
+      if (st) return st;
+      OFB_CUDA(h, cudaEventRecord(h->pipe_ev[2 * ci + 1], h->stream));
+      OFB_CUDA(h, cudaStreamWaitEvent(h->s_out, h->pipe_ev[2 * ci + 1], 0));
+      for (int i = 0; i < cn; i++)
+        OFB_CUDA(h, cudaMemcpy2DAsync(flow[i0 + i], flow_stride_bytes, h->d_flow_out + (i0 + i) * fl_img, row_flow,
+                                      row_flow, height, cudaMemcpyDeviceToHost, h->s_out));
+    }
+    OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
+    OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->last_flow = h->d_flow_out;
+    h->last_n = n;
+    return OFB_OK;
+  }
   if (pinned) {
     for (int i = 0; i < n; i++) {
       OFB_CUDA(h, cudaMemcpy2DAsync(h->d_src + (size_t)i * istride, pitch, prev[i], stride_bytes, width, height,

@@ -50,6 +50,10 @@ struct ofb_handle {
   cudaStream_t stream = nullptr;
   int num_sms = 148;
   bool force_generic = false;  // OFB_FORCE_GENERIC=1: always take the generic (unfused) kernels
+  // host-buffer pipeline: copy-in / copy-out streams and their events (api.cu)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> pipe_ev;
+  bool no_pipeline = false;    // OFB_NO_PIPELINE=1: serial upload -> compute -> download
   uint64_t launches = 0;
   std::string err;
 

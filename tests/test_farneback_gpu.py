@@ -148,3 +148,23 @@ def test_full_size_1080p_properties(engine_factory):
     assert abs(float(np.median(back[..., 0])) + 6.2) < 0.1 and abs(float(np.median(back[..., 1])) + 3.4) < 0.1
     # determinism: same input twice -> identical bits
     assert np.array_equal(got, eng.farneback(a, b))
+
+
+@pytest.mark.parametrize("n", [3, 8])
+def test_pinned_pipelined_batch_equals_single(engine_factory, n):
+    """Pinned host buffers take the chunked copy/compute/copy pipeline; results must be bit-identical
+    to one-pair calls."""
+    import torch
+    eng = engine_factory(320, 240, 8)
+    pairs = [synth.synth_pair(240, 320, 80 + i, (1.0 + 0.5 * i, -0.25 * i)) for i in range(n)]
+    prevs = torch.from_numpy(np.stack([p[0] for p in pairs])).pin_memory()
+    nexts = torch.from_numpy(np.stack([p[1] for p in pairs])).pin_memory()
+    out = torch.empty((n, 240, 320, 2), dtype=torch.float32).pin_memory()
+    eng.farneback_batch_into(prevs.numpy(), nexts.numpy(), out.numpy())
+    for i, (a, b) in enumerate(pairs):
+        assert np.array_equal(eng.farneback(a, b), out[i].numpy())
+    # the on-device reduction sees all n fields of the pipelined call
+    eng.farneback_batch_into(prevs.numpy(), nexts.numpy(), out.numpy())
+    _, med = eng.flow_u_stats(n)
+    for i in range(n):
+        assert med[i] == np.float32(np.median(out[i].numpy()[..., 0]))
