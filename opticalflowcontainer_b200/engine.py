@@ -254,7 +254,7 @@ class FlowEngine:
         if not (ctype & 1):
             max_count = 30
         if not (ctype & 2):
-            eps = 0.01 if not (ctype & 1) else 0.0
+            eps = 0.01
         p = LKParams(int(winSize[0]), int(winSize[1]), int(maxLevel), int(max_count), float(eps), int(flags),
                      float(minEigThreshold))
         hgt, wid = prev.shape

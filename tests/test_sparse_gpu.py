@@ -1,0 +1,140 @@
+"""GPU parity of the sparse path through the C ABI: uint8 pyrDown pyramid, Scharr derivatives and
+the Shi-Tomasi corner list are BIT-EXACT against the cv2 wheel (BASELINE.json north_star);
+pyramidal-LK status flags are equal and positions within the flow tolerance (mean EPE <= 0.01 px,
+max <= 0.1 px) — in practice ~1e-4 px."""
+import numpy as np
+import pytest
+
+from oracle import features_np as FT
+from oracle import lk_np as LK
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (135, 241), (97, 131), (1080, 1920)])
+def test_pyramid_and_scharr_bit_exact(engine_factory, shape):
+    a, _ = synth.synth_pair(shape[0], shape[1], 3)
+    eng = engine_factory(shape[1], shape[0])
+    levels, derivs = eng.lk_pyramid(a, (21, 21), 3, True)
+    ref = a
+    n_ref, _ = cv2.buildOpticalFlowPyramid(a, (21, 21), 3, withDerivatives=False)
+    assert len(levels) == n_ref + 1
+    for l, (lv, dv) in enumerate(zip(levels, derivs)):
+        if l > 0:
+            ref = cv2.pyrDown(ref)
+        assert np.array_equal(lv, ref), "pyramid level %d differs" % l
+        assert np.array_equal(dv[..., 0], cv2.Scharr(ref, cv2.CV_16S, 1, 0))
+        assert np.array_equal(dv[..., 1], cv2.Scharr(ref, cv2.CV_16S, 0, 1))
+
+
+def test_pyramid_random_bytes_and_depth_clamp(engine_factory):
+    rng = np.random.default_rng(5)
+    r = rng.integers(0, 256, size=(60, 80), dtype=np.uint8)
+    eng = engine_factory(80, 60)
+    levels, derivs = eng.lk_pyramid(r, (21, 21), 3, True)
+    assert len(levels) == 2                      # 20x15 <= winSize is refused
+    assert np.array_equal(levels[1], cv2.pyrDown(r))
+    assert np.array_equal(levels[1], LK.pyr_down(r))
+    assert np.array_equal(derivs[0], LK.scharr_deriv(r))
+
+
+@pytest.mark.parametrize("shape,seed", [((480, 640), 0), ((270, 480), 1), ((135, 241), 2), ((100, 247), 3)])
+def test_min_eigenval_bit_exact(engine_factory, shape, seed):
+    a, _ = synth.synth_pair(shape[0], shape[1], seed)
+    eng = engine_factory(shape[1], shape[0])
+    got = eng.corner_min_eigenval(a, 3)
+    assert np.array_equal(got, FT.corner_min_eigenval(a, 3))          # oracle restatement: every size
+    if shape[1] % 32 == 0:                                              # live cv2: SIMD-tail-free widths
+        assert np.array_equal(got, cv2.cornerMinEigenVal(a, 3, ksize=3))
+
+
+@pytest.mark.parametrize("shape,seed,maxc,q,md", [((480, 640), 0, 2000, 0.01, 7), ((480, 640), 1, 100, 0.05, 3.5),
+                                                    ((270, 480), 2, 0, 0.1, 10), ((240, 320), 3, 100, 0.01, 0),
+                                                    ((240, 320), 4, 500, 0.001, 1)])
+def test_good_features_exact_list(engine_factory, shape, seed, maxc, q, md):
+    a, _ = synth.synth_pair(shape[0], shape[1], seed)
+    eng = engine_factory(shape[1], shape[0])
+    got = eng.good_features(a, maxc, q, md, 3)
+    ref = cv2.goodFeaturesToTrack(a, maxc, q, md, blockSize=3)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_good_features_1080p_2000_corners(engine_factory):
+    """BASELINE config[3] front end: 2000 Shi-Tomasi corners at 1080p, exact list and order."""
+    a, _ = synth.synth_pair(1080, 1920, 300)
+    eng = engine_factory(1920, 1080)
+    got = eng.good_features(a, 2000, 0.01, 7, 3)
+    ref = cv2.goodFeaturesToTrack(a, 2000, 0.01, 7, blockSize=3)
+    assert got.shape == (2000, 1, 2) and np.array_equal(got, ref)
+
+
+def test_good_features_ties_and_flat_image(engine_factory):
+    import opticalflowcontainer_b200 as ofb
+    t = np.zeros((64, 64), np.uint8)
+    for y in range(8, 64, 16):
+        for x in range(8, 64, 16):
+            t[y:y + 4, x:x + 4] = 200
+    eng = engine_factory(64, 64)
+    for md in (0, 5):
+        assert np.array_equal(eng.good_features(t, 50, 0.01, md, 3), cv2.goodFeaturesToTrack(t, 50, 0.01, md, blockSize=3))
+    flat = np.full((64, 64), 77, np.uint8)
+    assert len(eng.good_features(flat, 10, 0.01, 3, 3)) == 0
+    assert ofb.goodFeaturesToTrack(flat, 10, 0.01, 3) is None        # cv2 returns None
+
+
+def _lk_check(ref, got, pos_tol=1e-2):
+    rn, rs, re = ref
+    gn, gs, ge = got
+    assert np.array_equal(rs, gs)
+    ok = rs.ravel() == 1
+    d = np.sqrt(((rn - gn).reshape(-1, 2)[ok] ** 2).sum(-1))
+    assert d.size == 0 or (d.mean() <= 1e-3 and d.max() <= pos_tol), (d.mean(), d.max())
+    return ok
+
+
+def test_pyrlk_matches_cv2(engine_factory):
+    a, b = synth.synth_pair(480, 640, 4, (3.2, -1.7))
+    eng = engine_factory(640, 480)
+    pts = cv2.goodFeaturesToTrack(a, 400, 0.01, 7, blockSize=3)
+    extra = np.array([[[1.5, 2.0]], [[638.2, 477.9]], [[0.0, 240.0]], [[320.0, 0.3]], [[-5.0, 10.0]], [[700.0, 100.0]]],
+                     np.float32)
+    pts = np.concatenate([pts, extra])
+    ref = cv2.calcOpticalFlowPyrLK(a, b, pts, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    got = eng.pyrlk(a, b, pts, None, (21, 21), 3, (3, 30, 0.01))
+    ok = _lk_check(ref, got)
+    assert np.abs(ref[2] - got[2])[ok].max() < 1e-2
+    # true motion recovered
+    mv = (got[0] - pts).reshape(-1, 2)[ok]
+    assert abs(np.median(mv[:, 0]) - 3.2) < 0.1 and abs(np.median(mv[:, 1]) + 1.7) < 0.1
+
+
+@pytest.mark.parametrize("win,lvl,crit,flags,thr", [((15, 11), 2, (3, 10, 0.03), 8, 1e-3), ((31, 31), 4, (1, 5, 0.0), 0, 1e-4),
+                                                      ((9, 9), 0, (2, 0, 0.05), 0, 1e-4), ((21, 21), 3, (3, 30, 0.01), 4, 1e-4)])
+def test_pyrlk_variants(engine_factory, win, lvl, crit, flags, thr):
+    a, b = synth.synth_warp_pair(270, 480, 6, angle_deg=0.8, zoom=1.01)
+    eng = engine_factory(480, 270)
+    pts = cv2.goodFeaturesToTrack(a, 150, 0.01, 5, blockSize=3)
+    init = (pts + np.float32([0.5, -0.5])).astype(np.float32) if flags & 4 else None
+    ref = cv2.calcOpticalFlowPyrLK(a, b, pts, None if init is None else init.copy(), winSize=win, maxLevel=lvl,
+                                   criteria=crit, flags=flags, minEigThreshold=thr)
+    got = eng.pyrlk(a, b, pts, init, win, lvl, crit, flags, thr)
+    ok = _lk_check(ref, got)
+    if flags & 8:
+        assert np.allclose(ref[2], got[2], rtol=1e-3, atol=1e-6)
+    else:
+        assert np.abs(ref[2] - got[2])[ok].max() < 2e-2
+
+
+def test_pyrlk_1080p_2000_points_and_module_api(built_lib):
+    """BASELINE config[3]: 2000 Shi-Tomasi corners tracked at 1080p through the cv2-signature functions."""
+    import opticalflowcontainer_b200 as ofb
+    a, b = synth.synth_pair(1080, 1920, 301, (5.5, 2.25))
+    pts = ofb.goodFeaturesToTrack(a, 2000, 0.01, 7, blockSize=3)
+    assert np.array_equal(pts, cv2.goodFeaturesToTrack(a, 2000, 0.01, 7, blockSize=3))
+    got = ofb.calcOpticalFlowPyrLK(a, b, pts, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    ref = cv2.calcOpticalFlowPyrLK(a, b, pts, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    _lk_check(ref, got)
+    n, pyr = ofb.buildOpticalFlowPyramid(a, (21, 21), 3, True)
+    assert n == 3 and np.array_equal(pyr[2], cv2.pyrDown(a))
