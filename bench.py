@@ -159,6 +159,9 @@ def run_ours(args, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    # keep stdout clean for the ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -320,7 +323,8 @@ def run_ours(args, rank, local_rank, world):
                                 "sample": "cv2 %s calcOpticalFlowFarneback, %d processes x %d pairs of 1920x1080 "
                                           "(single-threaded algorithm; 1 pair = %.0f ms on one core)"
                                           % (cb["cv2_version"], cb["cores"], cb["pairs_per_worker"], cb["single_pair_ms"])}
-    print(json.dumps(line), flush=True)
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
