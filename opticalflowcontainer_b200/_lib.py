@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libofb.so")
+LIB_PATH = os.environ.get("OFB_LIB") or os.path.join(_HERE, "libofb.so")   # OFB_LIB: experiment builds only
 
 
 class OfbError(RuntimeError):

@@ -20,6 +20,7 @@ BUILD = os.path.join(HERE, "csrc", "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math=false"]
+CFLAGS += os.environ.get("OFB_NVCC_FLAGS", "").split()   # experiments only (e.g. -DOFB_DBG=1)
 
 
 def _sources():

@@ -191,6 +191,12 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
   {
     const char* fg = getenv("OFB_FORCE_GENERIC");
     h->force_generic = fg && fg[0] == '1';
+    const char* ic = getenv("OFB_ITER_COLS");
+    if (ic) h->iter_cols = atoi(ic) == 128 ? 128 : 256;
+    const char* ws = getenv("OFB_ITER_WS");
+    if (ws) h->iter_ws = ws[0] != '0';
+    const char* iw = getenv("OFB_ITER_WAVES");
+    if (iw) h->iter_waves = std::max(1, atoi(iw));
     const char* np = getenv("OFB_NO_PIPELINE");
     h->no_pipeline = np && np[0] == '1';
   }

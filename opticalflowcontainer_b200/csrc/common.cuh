@@ -50,6 +50,9 @@ struct ofb_handle {
   cudaStream_t stream = nullptr;
   int num_sms = 148;
   bool force_generic = false;  // OFB_FORCE_GENERIC=1: always take the generic (unfused) kernels
+  int iter_cols = 256;         // OFB_ITER_COLS: strip width / CTA size of the fused iteration kernel (128|256)
+  bool iter_ws = true;         // OFB_ITER_WS=0: barrier-phased k_iter_box instead of warp-specialised k_iter_ws
+  int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
   // host-buffer pipeline: copy-in / copy-out streams and their events (api.cu)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> pipe_ev;

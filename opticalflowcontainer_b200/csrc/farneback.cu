@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "fb_device.cuh"
 #include "fb_iter.cuh"
+#include "fb_iter_ws.cuh"
 #include "fb_pyramid.cuh"
 
 namespace ofb {
@@ -412,12 +413,17 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   // fused box-window iteration kernel: radius 2..19 (shared-memory ring of 2m+1 rows); the generic
   // three-kernel path covers the Gaussian window and every other radius.
   const bool use_fused = !bc.gaussian && bc.m >= 2 && bc.m <= 19 && !h->force_generic;
+  const int FI_COLS = (h->iter_cols == 128 && !h->iter_ws) ? 128 : 256;   // strip width of the fused kernel
   if (use_fused) {
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float)));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float)));
     const int smem = (FI_CH + 2 * bc.m + 1) * 5 * FI_COLS * (int)sizeof(float);
-    if (bc.m == 7)
-      OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else
-      OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<7, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
 
   float2* prev_flow = nullptr;
@@ -485,19 +491,29 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       if (use_fused) {
         const int tw = FI_COLS - 2 * bc.m;
         const int strips = (w + tw - 1) / tw;
-        const int slots = 2 * h->num_sms;
+        const int slots = (512 / FI_COLS) * h->num_sms * h->iter_waves;   // resident CTAs (x waves)
         const int per = strips * n_pairs;
         int segs = per >= slots ? 1 : slots / per;
         int seg_rows = std::max(16, (hh + segs - 1) / segs);
         segs = (hh + seg_rows - 1) / seg_rows;
         const size_t smem = (size_t)(FI_CH + 2 * bc.m + 1) * 5 * FI_COLS * sizeof(float);
         dim3 g(strips * segs, n_pairs);
-        if (bc.m == 7)
-          k_iter_box<7><<<g, FI_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
-                                                     seg_rows, strips);
-        else
-          k_iter_box<0><<<g, FI_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
-                                                     seg_rows, strips);
+#define OFB_ITER_LAUNCH(MT, CW)                                                                                  \
+  k_iter_box<MT, CW><<<g, CW, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale, seg_rows, \
+                                          strips)
+        if (h->iter_ws) {
+          if (bc.m == 7)
+            k_iter_ws<7><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
+                                                      seg_rows, strips);
+          else
+            k_iter_ws<0><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
+                                                      seg_rows, strips);
+        } else if (FI_COLS == 256) {
+          if (bc.m == 7) OFB_ITER_LAUNCH(7, 256); else OFB_ITER_LAUNCH(0, 256);
+        } else {
+          if (bc.m == 7) OFB_ITER_LAUNCH(7, 128); else OFB_ITER_LAUNCH(0, 128);
+        }
+#undef OFB_ITER_LAUNCH
         OFB_LAUNCH_CHECK(h);
       } else {
         k_update_matrices<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_RA, h->d_RB, fin, h->d_MA, h->d_MB, w, hh,

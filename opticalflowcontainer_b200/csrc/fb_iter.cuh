@@ -7,7 +7,7 @@ namespace ofb {
 
 // HBM traffic per pixel-iteration = R0 (20 B) + R1 gather (20 B) + flow in (8 B) + flow out (8 B).
 //
-// A CTA (8 warps) owns a strip of FI_COLS = 256 matrix columns (2m of them halo) and a segment of
+// A CTA (8 warps) owns a strip of COLS = 256 matrix columns (2m of them halo) and a segment of
 // `seg_rows` output rows, and marches down it FI_CH = 4 matrix rows at a time:
 //   A1  every warp computes M for one half-row (4 px per lane, 32 px apart: coalesced R0/flow loads
 //       and L1-friendly gathers; all 40 loads of the 4 px are issued before the first use, and the
@@ -17,21 +17,20 @@ namespace ofb {
 //   B   one thread per column keeps the vertical window sum as a running sum in DOUBLE (add the
 //       new H row, subtract the row leaving the window — exactly cv2's vsum scheme, so there is no
 //       float cancellation drift), scales, solves the 2x2 system and writes flow.
-constexpr int FI_COLS = 256;
 constexpr int FI_CH = 4;
-constexpr int FI_THREADS = 256;
 
-template <int MT>
-__global__ void __launch_bounds__(FI_THREADS, 2)
+// COLS = strip width = threads per CTA (128 or 256); 512 threads per SM either way.
+template <int MT, int COLS>
+__global__ void __launch_bounds__(COLS, 512 / COLS)
     k_iter_box(const float4* __restrict__ RA, const float* __restrict__ RB, const float2* __restrict__ flow_in,
                float2* __restrict__ flow_out, int w, int h, int f1_offset, int m_rt, float scale, int seg_rows,
                int strips) {
   const int m = MT > 0 ? MT : m_rt;
   const int R = 2 * m + 1;
-  const int tw = FI_COLS - 2 * m;
+  const int tw = COLS - 2 * m;
   extern __shared__ float smem[];
-  float* stage = smem;                          // [FI_CH][5][FI_COLS]
-  float* ring = smem + FI_CH * 5 * FI_COLS;     // [R][5][FI_COLS]
+  float* stage = smem;                          // [FI_CH][5][COLS]
+  float* ring = smem + FI_CH * 5 * COLS;     // [R][5][COLS]
 
   const int strip = blockIdx.x % strips;
   const int seg = blockIdx.x / strips;
@@ -51,10 +50,11 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int a_row = warp >> 1, a_half = warp & 1;
+  constexpr int HALVES = COLS / 128;            // warps per matrix row
+  const int a_row = warp / HALVES, a_half = warp % HALVES;
   const int col = tid;                          // phase-B column
   const int out_x = x_base + col;
-  const bool col_valid = col >= m && col < FI_COLS - m && out_x < w;
+  const bool col_valid = col >= m && col < COLS - m && out_x < w;
 
   double vs0 = 0, vs1 = 0, vs2 = 0, vs3 = 0, vs4 = 0;
 
@@ -76,8 +76,12 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
     const int t = tc + a_row;
     if (t <= t_last) {
       const int y = clampi(t, 0, h - 1);
-      float* srow = stage + a_row * 5 * FI_COLS + a_half * 128 + lane;
+      float* srow = stage + a_row * 5 * COLS + a_half * 128 + lane;
       UmLoads L[4];
+#if defined(OFB_DBG) && (OFB_DBG & 2)   // experiment: zero displacement (perfectly coalesced gathers)
+#pragma unroll
+      for (int j = 0; j < 4; j++) fl[j] = make_float2(0.f, 0.f);
+#endif
 #pragma unroll
       for (int j = 0; j < 4; j++) um_issue(L[j], RA0, RB0, RA1, RB1, fl[j], xs[j], y, w, h);
       {  // next chunk's flow (clamped row: always a valid address)
@@ -87,12 +91,17 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
       }
 #pragma unroll
       for (int j = 0; j < 4; j++) {
+#if defined(OFB_DBG) && (OFB_DBG & 8)   // experiment: no R loads / UpdateMatrices arithmetic
+        M5 mm;
+        mm.g11 = fl[j].x; mm.g12 = fl[j].y; mm.g22 = 1.f; mm.h1 = fl[j].x; mm.h2 = fl[j].y;
+#else
         const M5 mm = um_finish(L[j], xs[j], y, w, h);
-        srow[0 * FI_COLS + 32 * j] = mm.g11;
-        srow[1 * FI_COLS + 32 * j] = mm.g12;
-        srow[2 * FI_COLS + 32 * j] = mm.g22;
-        srow[3 * FI_COLS + 32 * j] = mm.h1;
-        srow[4 * FI_COLS + 32 * j] = mm.h2;
+#endif
+        srow[0 * COLS + 32 * j] = mm.g11;
+        srow[1 * COLS + 32 * j] = mm.g12;
+        srow[2 * COLS + 32 * j] = mm.g22;
+        srow[3 * COLS + 32 * j] = mm.h1;
+        srow[4 * COLS + 32 * j] = mm.h2;
       }
     }
     // ring slots of the chunk's rows (slot = (row - t_first) mod R, kept incrementally)
@@ -109,27 +118,27 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
     for (int rr = 0; rr < FI_CH; rr++) {
       const bool have_old = n_done + rr >= R;   // row tc+rr-R exists (its slot is slot[rr]; R > FI_CH)
 #pragma unroll
-      for (int ch = 0; ch < 5; ch++) old[rr][ch] = have_old ? ring[(slot[rr] * 5 + ch) * FI_COLS + col] : 0.f;
+      for (int ch = 0; ch < 5; ch++) old[rr][ch] = have_old ? ring[(slot[rr] * 5 + ch) * COLS + col] : 0.f;
     }
     __syncthreads();
     // ---------------- A2: horizontal window sums of the staged rows -> ring
     if (t <= t_last) {
-      const float* srow = stage + a_row * 5 * FI_COLS;
-      float* rrow = ring + slot[0] * 5 * FI_COLS;
-      if (a_row == 1) rrow = ring + slot[1] * 5 * FI_COLS;
-      if (a_row == 2) rrow = ring + slot[2] * 5 * FI_COLS;
-      if (a_row == 3) rrow = ring + slot[3] * 5 * FI_COLS;
+      const float* srow = stage + a_row * 5 * COLS;
+      float* rrow = ring + slot[0] * 5 * COLS;
+      if (a_row == 1) rrow = ring + slot[1] * 5 * COLS;
+      if (a_row == 2) rrow = ring + slot[2] * 5 * COLS;
+      if (a_row == 3) rrow = ring + slot[3] * 5 * COLS;
       const int q0 = a_half * 128 + 4 * lane;   // first of this lane's 4 columns
 #pragma unroll
       for (int ch = 0; ch < 5; ch++) {
-        const float* s = srow + ch * FI_COLS;
+        const float* s = srow + ch * COLS;
         float s0, s1, s2, s3;
         if (MT > 0) {
           constexpr int KQ = (MT + 3) / 4;
           float e[(2 * KQ + 1) * 4];            // e[d + 4*KQ] = staged value at column q0 + d
 #pragma unroll
           for (int k = -KQ; k <= KQ; k++) {
-            const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
+            const int cq = min(max(q0 + 4 * k, 0), COLS - 4);
             const float4 v = *reinterpret_cast<const float4*>(s + cq);
             e[(k + KQ) * 4 + 0] = v.x; e[(k + KQ) * 4 + 1] = v.y; e[(k + KQ) * 4 + 2] = v.z; e[(k + KQ) * 4 + 3] = v.w;
           }
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
           s0 = s1 = s2 = s3 = 0.f;
           const int kq = (m + 3) >> 2;          // quads to each side
           for (int k = -kq; k <= kq; k++) {
-            const int cq = min(max(q0 + 4 * k, 0), FI_COLS - 4);
+            const int cq = min(max(q0 + 4 * k, 0), COLS - 4);
             const float4 v = *reinterpret_cast<const float4*>(s + cq);
             const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -168,7 +177,13 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
             }
           }
         }
-        *reinterpret_cast<float4*>(rrow + ch * FI_COLS + q0) = make_float4(s0, s1, s2, s3);
+#if defined(OFB_DBG) && (OFB_DBG & 1)   // experiment: no horizontal sums (dead-code-eliminates the above)
+        {
+          const float4 v = *reinterpret_cast<const float4*>(s + q0);
+          s0 = v.x; s1 = v.y; s2 = v.z; s3 = v.w;
+        }
+#endif
+        *reinterpret_cast<float4*>(rrow + ch * COLS + q0) = make_float4(s0, s1, s2, s3);
       }
     }
     __syncthreads();
@@ -177,12 +192,16 @@ __global__ void __launch_bounds__(FI_THREADS, 2)
 #pragma unroll
     for (int rr = 0; rr < FI_CH; rr++) {
       if (rr < nrows) {
-        const float* rrow = ring + slot[rr] * 5 * FI_COLS + col;
-        vs0 += (double)rrow[0 * FI_COLS] - (double)old[rr][0];
-        vs1 += (double)rrow[1 * FI_COLS] - (double)old[rr][1];
-        vs2 += (double)rrow[2 * FI_COLS] - (double)old[rr][2];
-        vs3 += (double)rrow[3 * FI_COLS] - (double)old[rr][3];
-        vs4 += (double)rrow[4 * FI_COLS] - (double)old[rr][4];
+        const float* rrow = ring + slot[rr] * 5 * COLS + col;
+#if defined(OFB_DBG) && (OFB_DBG & 4)   // experiment: no double running sums / solve
+        if (tc + rr - m >= y0 && col_valid) fout[(tc + rr - m) * w + out_x] = make_float2(rrow[0], rrow[3 * COLS] + old[rr][1]);
+        continue;
+#endif
+        vs0 += (double)rrow[0 * COLS] - (double)old[rr][0];
+        vs1 += (double)rrow[1 * COLS] - (double)old[rr][1];
+        vs2 += (double)rrow[2 * COLS] - (double)old[rr][2];
+        vs3 += (double)rrow[3 * COLS] - (double)old[rr][3];
+        vs4 += (double)rrow[4 * COLS] - (double)old[rr][4];
         const int y = tc + rr - m;
         if (y >= y0 && col_valid) {
           fout[y * w + out_x] = solve2x2((float)vs0 * scale, (float)vs1 * scale, (float)vs2 * scale,
