@@ -194,9 +194,21 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     const char* ic = getenv("OFB_ITER_COLS");
     if (ic) h->iter_cols = atoi(ic) == 128 ? 128 : 256;
     const char* ws = getenv("OFB_ITER_WS");
-    if (ws) h->iter_ws = ws[0] != '0';
+    if (ws) h->iter_ws = std::min(4, std::max(0, atoi(ws)));
+    const char* ich = getenv("OFB_ITER_CH");
+    if (ich) h->iter_ch = atoi(ich);
+    const char* ip = getenv("OFB_ITER_PREFETCH");
+    if (ip) h->iter_prefetch = ip[0] != '0';
+    const char* ipd = getenv("OFB_ITER_PFD");
+    if (ipd) h->iter_pfd = atoi(ipd) == 2 ? 2 : 3;
     const char* iw = getenv("OFB_ITER_WAVES");
     if (iw) h->iter_waves = std::max(1, atoi(iw));
+    const char* pt = getenv("OFB_POLYEXP_TILE");
+    h->polyexp_tile = pt && pt[0] == '1';
+    const char* nf = getenv("OFB_NO_FUSED_SRC");
+    h->no_fused_src = nf && nf[0] == '1';
+    const char* pw = getenv("OFB_PX_WAVES");
+    if (pw) h->px_waves = std::max(1, atoi(pw));
     const char* np = getenv("OFB_NO_PIPELINE");
     h->no_pipeline = np && np[0] == '1';
   }
@@ -206,8 +218,8 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
   h->src_image_stride = h->src_pitch * max_height;
   CREATE_CUDA(cudaMalloc(&h->d_src, h->src_image_stride * frames));
   CREATE_CUDA(cudaMalloc(&h->d_img, frames * N * sizeof(float)));
-  CREATE_CUDA(cudaMalloc(&h->d_RA, frames * N * sizeof(float4)));
-  CREATE_CUDA(cudaMalloc(&h->d_RB, frames * N * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_RA, (frames * N + (size_t)kRowPad * max_width) * sizeof(float4)));
+  CREATE_CUDA(cudaMalloc(&h->d_RB, (frames * N + (size_t)kRowPad * max_width) * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_MA, max_batch * N * sizeof(float4)));
   CREATE_CUDA(cudaMalloc(&h->d_MB, max_batch * N * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_VA, max_batch * N * sizeof(float4)));

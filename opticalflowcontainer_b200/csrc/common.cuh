@@ -16,6 +16,7 @@ namespace ofb {
 constexpr int kMaxLevels = 16;     // scales per call (cv2 clamps by the 32-px rule long before)
 constexpr int kMaxPolyN = 10;      // poly_n <= 10 (cv2 users: 5 or 7)
 constexpr int kMaxBlurRadius = 64; // winsize <= 129
+constexpr int kRowPad = 4;         // spare rows at the end of the R buffers (k_iter_ws2 prefetches up to 3 rows past a pixel)
 
 // One pyramid scale of the Farneback schedule (FarnebackOpticalFlowImpl::calc).
 struct Level {
@@ -51,8 +52,14 @@ struct ofb_handle {
   int num_sms = 148;
   bool force_generic = false;  // OFB_FORCE_GENERIC=1: always take the generic (unfused) kernels
   int iter_cols = 256;         // OFB_ITER_COLS: strip width / CTA size of the fused iteration kernel (128|256)
-  bool iter_ws = true;         // OFB_ITER_WS=0: barrier-phased k_iter_box instead of warp-specialised k_iter_ws
+  int iter_ws = 4;             // OFB_ITER_WS: 4 = vertical-first float k_iter_v, 3 = high-occupancy k_iter_z, 2 = k_iter_ws2, 1 = k_iter_ws, 0 = barrier-phased k_iter_box
+  int iter_ch = 2;             // OFB_ITER_CH: rows per chunk of k_iter_z (experiments)
+  int iter_pfd = 3;            // OFB_ITER_PFD: L2 prefetch distance (rows) of k_iter_v (2 or 3)
+  bool iter_prefetch = true;   // OFB_ITER_PREFETCH=0: no L2 prefetch of the next chunk in k_iter_ws2
   int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
+  bool polyexp_tile = false;   // OFB_POLYEXP_TILE=1: 32x32-tile PolyExp kernel instead of the marching one
+  bool no_fused_src = false;   // OFB_NO_FUSED_SRC=1: level-0 pyramid stage as separate kernels
+  int px_waves = 4;            // OFB_PX_WAVES: target CTA waves of the marching PolyExp kernel
   // host-buffer pipeline: copy-in / copy-out streams and their events (api.cu)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> pipe_ev;

@@ -20,6 +20,10 @@
 #include "fb_device.cuh"
 #include "fb_iter.cuh"
 #include "fb_iter_ws.cuh"
+#include "fb_iter_ws2.cuh"
+#include "fb_iter_z.cuh"
+#include "fb_iter_v.cuh"
+#include "fb_polyexp.cuh"
 #include "fb_pyramid.cuh"
 
 namespace ofb {
@@ -386,6 +390,54 @@ __global__ void __launch_bounds__(256) k_init_flow_area(const float2* __restrict
 // =====================================================================================
 // Driver: the multi-level schedule on the handle's stream (no host sync inside).
 // =====================================================================================
+// k_iter_z launcher: picks the instantiation for (m, strip width, rows per chunk).
+template <int MT, int COLS, int CH, int MINB>
+static cudaError_t launch_iter_z(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
+                                 int f1_offset, int m, float reg, cudaStream_t st) {
+  const int smem = iter_z_smem_floats<COLS, CH>(m) * (int)sizeof(float);
+  static int configured = -1;   // largest dynamic smem configured for this instantiation
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_iter_z<MT, COLS, CH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int tw = COLS - 2 * m;
+  const int strips = (w + tw - 1) / tw;
+  const int slots = MINB * h->num_sms * h->iter_waves;
+  const int per = strips * n_pairs;
+  int segs = per >= slots ? 1 : slots / per;
+  int seg_rows = std::max(16, (hh + segs - 1) / segs);
+  segs = (hh + seg_rows - 1) / seg_rows;
+  dim3 g(strips * segs, n_pairs);
+  k_iter_z<MT, COLS, CH, MINB><<<g, 2 * COLS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m, reg,
+                                                         seg_rows, strips);
+  return cudaGetLastError();
+}
+
+// k_iter_v launcher.
+template <int MT, int COLS, int CH, int MINB, int PFD>
+static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
+                                 int f1_offset, int m, float reg, cudaStream_t st) {
+  const int smem = iter_v_smem_floats<COLS, CH>(m) * (int)sizeof(float);
+  static int configured = -1;   // largest dynamic smem configured for this instantiation
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int tw = COLS - 2 * m;
+  const int strips = (w + tw - 1) / tw;
+  const int slots = MINB * h->num_sms * h->iter_waves;
+  const int per = strips * n_pairs;
+  int segs = per >= slots ? 1 : slots / per;
+  int seg_rows = std::max(16, (hh + segs - 1) / segs);
+  segs = (hh + seg_rows - 1) / seg_rows;
+  dim3 g(strips * segs, n_pairs);
+  k_iter_v<MT, COLS, CH, MINB, PFD><<<g, COLS + CH * COLS / 4, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m,
+                                                                     reg, seg_rows, strips);
+  return cudaGetLastError();
+}
+
 static inline dim3 grid2d(int w, int h, int z, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y, z); }
 
 int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
@@ -419,6 +471,11 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
                                      (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float)));
     OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float)));
+    const int ws_smem = (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float);
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws2<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws2<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
     const int smem = (FI_CH + 2 * bc.m + 1) * 5 * FI_COLS * (int)sizeof(float);
     OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -460,8 +517,12 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
     PyrCoef pyc;
     if (prepare_pyr(lv.ksize, lv.sigma, &pyc) != OFB_OK)
       return set_error(h, OFB_ERR_INVALID_ARG, "pyramid smoothing kernel too large (ksize=%d)", lv.ksize);
-    TB(OFB_STAGE_PYRAMID);
-    {
+    // Marching PolyExp kernel (poly_n <= 8).  When the level has the source size (k = 0: 3-tap blur,
+    // identity resize) the pyramid stage is fused into it and the level image never exists in HBM.
+    const bool march = pc.n <= PX_MAXN && !h->polyexp_tile;
+    const bool fused_src = march && w == width && hh == height && pyc.r == 1 && !h->no_fused_src;
+    if (!fused_src) {
+      TB(OFB_STAGE_PYRAMID);
       // pass H writes hb[frames][H][w] into d_MA (free here: the generic iteration path only uses it
       // after the pyramid stage of the level), pass V writes the level image.
       float* hb = reinterpret_cast<float*>(h->d_MA);
@@ -471,10 +532,30 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       dim3 bv(128, 2), gv((w + 127) / 128, (hh + 1) / 2, frames);
       k_pyr_v<<<gv, bv, 0, st>>>(hb, height, h->d_img, w, hh, 1.0 / ((double)hh / height), pyc);
       OFB_LAUNCH_CHECK(h);
+      TE();
     }
-    TE();
     TB(OFB_STAGE_POLYEXP);
-    {
+    if (march) {
+      const int strips = (w + PX_TW - 1) / PX_TW;
+      const int per = strips * frames;
+      const int slots = 3 * h->num_sms * h->px_waves;
+      int segs = std::max(1, slots / per);
+      int seg_rows = std::max(16, ((hh + segs - 1) / segs + PX_ROWS - 1) / PX_ROWS * PX_ROWS);
+      segs = (hh + seg_rows - 1) / seg_rows;
+      dim3 g(strips * segs, frames);
+#define OFB_PX_LAUNCH(NT)                                                                                           \
+  do {                                                                                                              \
+    if (fused_src)                                                                                                  \
+      k_polyexp_march<NT, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], h->d_RA, h->d_RB, w, hh,      \
+                                                    seg_rows, strips, pc);                                          \
+    else                                                                                                            \
+      k_polyexp_march<NT, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, h->d_RA, h->d_RB, w, hh, seg_rows,     \
+                                                    strips, pc);                                                    \
+  } while (0)
+      if (pc.n == 5) OFB_PX_LAUNCH(5); else if (pc.n == 7) OFB_PX_LAUNCH(7); else OFB_PX_LAUNCH(0);
+#undef OFB_PX_LAUNCH
+      OFB_LAUNCH_CHECK(h);
+    } else {
       dim3 g((w + PE_T - 1) / PE_T, (hh + PE_T - 1) / PE_T, frames);
       if (pc.n == 5) k_polyexp<5><<<g, blk, 0, st>>>(h->d_img, h->d_RA, h->d_RB, w, hh, pc);
       else if (pc.n == 7) k_polyexp<7><<<g, blk, 0, st>>>(h->d_img, h->d_RA, h->d_RB, w, hh, pc);
@@ -501,7 +582,54 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
 #define OFB_ITER_LAUNCH(MT, CW)                                                                                  \
   k_iter_box<MT, CW><<<g, CW, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale, seg_rows, \
                                           strips)
-        if (h->iter_ws) {
+        if (h->iter_ws == 4) {
+          const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
+          cudaError_t e;
+#define OFB_V_ARGS h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st
+          const int pfd = h->iter_prefetch ? h->iter_pfd : 0;
+          if (bc.m == 7) {
+            if (h->iter_cols == 128) {
+              if (h->iter_ch == 4) e = launch_iter_v<7, 128, 4, 3, 0>(OFB_V_ARGS);
+              else if (pfd == 0) e = launch_iter_v<7, 128, 2, 4, 0>(OFB_V_ARGS);
+              else if (pfd == 2) e = launch_iter_v<7, 128, 2, 4, 2>(OFB_V_ARGS);
+              else e = launch_iter_v<7, 128, 2, 4, 3>(OFB_V_ARGS);
+            } else {
+              if (h->iter_ch == 3) e = launch_iter_v<7, 256, 3, 2, 0>(OFB_V_ARGS);
+              else if (pfd == 0) e = launch_iter_v<7, 256, 2, 2, 0>(OFB_V_ARGS);
+              else if (pfd == 2) e = launch_iter_v<7, 256, 2, 2, 2>(OFB_V_ARGS);
+              else e = launch_iter_v<7, 256, 2, 2, 3>(OFB_V_ARGS);
+            }
+          } else {
+            e = launch_iter_v<0, 128, 4, 1, 0>(OFB_V_ARGS);
+          }
+#undef OFB_V_ARGS
+          if (e != cudaSuccess)
+            return set_error(h, OFB_ERR_CUDA, "k_iter_v launch failed: %s", cudaGetErrorString(e));
+        } else if (h->iter_ws == 3) {
+          const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
+          cudaError_t e;
+          if (bc.m == 7) {
+            if (h->iter_cols == 128 && h->iter_ch == 2) e = launch_iter_z<7, 128, 2, 4>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
+            else if (h->iter_cols == 128) e = launch_iter_z<7, 128, 4, 3>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
+            else if (h->iter_ch == 2) e = launch_iter_z<7, 256, 2, 2>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
+            else e = launch_iter_z<7, 256, 3, 2>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
+          } else {
+            e = launch_iter_z<0, 128, 4, 1>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
+          }
+          if (e != cudaSuccess)
+            return set_error(h, OFB_ERR_CUDA, "k_iter_z launch failed: %s", cudaGetErrorString(e));
+        } else if (h->iter_ws == 2) {
+          const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
+#define OFB_WS2_LAUNCH(MT, PF)                                                                                    \
+  k_iter_ws2<MT, PF><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, reg, seg_rows, \
+                                                  strips)
+          if (h->iter_prefetch) {
+            if (bc.m == 7) OFB_WS2_LAUNCH(7, true); else OFB_WS2_LAUNCH(0, true);
+          } else {
+            if (bc.m == 7) OFB_WS2_LAUNCH(7, false); else OFB_WS2_LAUNCH(0, false);
+          }
+#undef OFB_WS2_LAUNCH
+        } else if (h->iter_ws) {
           if (bc.m == 7)
             k_iter_ws<7><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
                                                       seg_rows, strips);

@@ -93,3 +93,31 @@ def cheap_texture(h: int, w: int, seed: int) -> np.ndarray:
     big = big[:h, :w]
     big = (big - big.min()) / max(float(big.max() - big.min()), 1e-6) * 255.0
     return np.ascontiguousarray(np.round(big).astype(np.uint8))
+
+
+def subpixel_shift(frame: np.ndarray, sx: float, sy: float) -> np.ndarray:
+    """``frame`` translated by a real-valued (sx, sy) with bilinear weights and wrap-around
+    (NumPy only; for throughput inputs where the content moves by a non-integer amount, as the
+    panning corpus C2 of SURVEY.md §8d does)."""
+    ix, iy = int(np.floor(sx)), int(np.floor(sy))
+    ax, ay = float(sx - ix), float(sy - iy)
+    f = frame.astype(np.float32)
+    r00 = np.roll(f, (iy, ix), axis=(0, 1))
+    r01 = np.roll(f, (iy, ix + 1), axis=(0, 1))
+    r10 = np.roll(f, (iy + 1, ix), axis=(0, 1))
+    r11 = np.roll(f, (iy + 1, ix + 1), axis=(0, 1))
+    out = (1 - ay) * ((1 - ax) * r00 + ax * r01) + ay * ((1 - ax) * r10 + ax * r11)
+    return np.ascontiguousarray(np.clip(np.round(out), 0, 255).astype(np.uint8))
+
+
+def high_contrast_pair(h: int, w: int, seed: int, roll=(2, -3)):
+    """Dark frame with random bright/dark rectangles + U{0,1,2} noise, rolled by (dy, dx): strong
+    edges next to flat areas — the stress case for the accumulation precision of the box blur."""
+    rng = np.random.default_rng(seed)
+    a = np.full((h, w), 20, np.uint8)
+    for _ in range(40):
+        y, x = int(rng.integers(0, h - 40)), int(rng.integers(0, w - 40))
+        a[y:y + int(rng.integers(8, 40)), x:x + int(rng.integers(8, 40))] = int(rng.integers(0, 2)) * 235 + 10
+    a = (a + rng.integers(0, 3, size=a.shape)).astype(np.uint8)
+    b = np.roll(a, roll, axis=(0, 1))
+    return np.ascontiguousarray(a), np.ascontiguousarray(b)

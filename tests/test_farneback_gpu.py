@@ -74,6 +74,15 @@ def test_rotation_zoom_and_low_texture(engine_factory):
     _check(C.farneback(a, b), eng.farneback(a, b), MEAN_GATE, MAX_GATE)
 
 
+def test_high_contrast_edges(engine_factory):
+    """Strong edges beside flat areas: the float (van Herk / Gil-Werman) vertical sums of the fused
+    iteration kernel replace cv2's double running sums here — contract gate."""
+    eng = engine_factory(640, 480)
+    for seed in (5, 6):
+        a, b = synth.high_contrast_pair(480, 640, seed)
+        _check(C.farneback(a, b), eng.farneback(a, b), MEAN_GATE, MAX_GATE)
+
+
 def test_initial_flow(engine_factory):
     a, b = synth.synth_pair(240, 320, 2, (5, 3))
     f0 = np.full((240, 320, 2), (4.5, 2.5), np.float32)

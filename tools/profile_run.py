@@ -20,7 +20,10 @@ t = synth.cheap_texture(H, W, 1)
 fr = np.empty((2 * B, H, W), np.uint8)
 for i in range(B):
     fr[i] = np.roll(t, (3 * i, 5 * i), axis=(0, 1))
-    fr[B + i] = np.roll(fr[i], (2 + i, -3 + i), axis=(0, 1))
+    if os.environ.get("OFB_SHIFT", "frac") == "int":
+        fr[B + i] = np.roll(fr[i], (2 + i, -3 + i), axis=(0, 1))
+    else:   # sub-pixel pan, like corpus C2
+        fr[B + i] = synth.subpixel_shift(fr[i], -3.3 + 1.37 * i, 2.6 + 0.71 * i)
 d = torch.from_numpy(fr).cuda()
 flow = torch.empty((B, H, W, 2), dtype=torch.float32, device="cuda")
 for _ in range(calls):
