@@ -143,7 +143,8 @@ int ofb_destroy(ofb_handle* h) {
   cudaFree(h->d_MA); cudaFree(h->d_MB); cudaFree(h->d_VA); cudaFree(h->d_VB);
   for (int i = 0; i < 3; i++) cudaFree(h->d_flow[i]);
   cudaFree(h->d_flow_out); cudaFree(h->d_init_flow); cudaFree(h->d_stats); cudaFree(h->d_mask);
-  cudaFree(h->d_scratch); cudaFree(h->d_sel);
+  cudaFree(h->d_scratch); cudaFree(h->d_sel); cudaFree(h->d_lintab);
+  if (h->h_lintab) cudaFreeHost(h->h_lintab);
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -195,8 +196,6 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     if (ic) h->iter_cols = atoi(ic) == 128 ? 128 : 256;
     const char* ws = getenv("OFB_ITER_WS");
     if (ws) h->iter_ws = std::min(4, std::max(0, atoi(ws)));
-    const char* ich = getenv("OFB_ITER_CH");
-    if (ich) h->iter_ch = atoi(ich);
     const char* ip = getenv("OFB_ITER_PREFETCH");
     if (ip) h->iter_prefetch = ip[0] != '0';
     const char* ipd = getenv("OFB_ITER_PFD");
@@ -230,6 +229,9 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
   CREATE_CUDA(cudaMalloc(&h->d_stats, 64 * sizeof(double) * (size_t)max_batch));
   CREATE_CUDA(cudaMalloc(&h->d_mask, N));
   CREATE_CUDA(cudaMalloc(&h->d_sel, (size_t)max_batch * 4104 * sizeof(uint32_t)));
+  h->lintab_cap = (size_t)kMaxLevels * ((size_t)max_width + max_height);
+  CREATE_CUDA(cudaMalloc(&h->d_lintab, h->lintab_cap * sizeof(LinTab)));
+  CREATE_CUDA(cudaHostAlloc(&h->h_lintab, h->lintab_cap * sizeof(LinTab), cudaHostAllocDefault));
   h->h_src_bytes = h->src_image_stride * frames;
   h->h_flow_bytes = max_batch * N * sizeof(float2);
   CREATE_CUDA(cudaHostAlloc(&h->h_src, h->h_src_bytes, cudaHostAllocDefault));

@@ -16,7 +16,7 @@ namespace ofb {
 constexpr int kMaxLevels = 16;     // scales per call (cv2 clamps by the 32-px rule long before)
 constexpr int kMaxPolyN = 10;      // poly_n <= 10 (cv2 users: 5 or 7)
 constexpr int kMaxBlurRadius = 64; // winsize <= 129
-constexpr int kRowPad = 4;         // spare rows at the end of the R buffers (k_iter_ws2 prefetches up to 3 rows past a pixel)
+constexpr int kRowPad = 6;         // spare rows at the end of the R buffers (k_iter_ws2 prefetches up to 3 rows past a pixel)
 
 // One pyramid scale of the Farneback schedule (FarnebackOpticalFlowImpl::calc).
 struct Level {
@@ -41,6 +41,12 @@ struct BlurCoef {
   float k[kMaxBlurRadius + 1];  // box: all ones
 };
 
+// One entry of a cv::resize INTER_LINEAR coordinate table: source index and weight of source index + 1.
+struct LinTab {
+  int i0;
+  float f;
+};
+
 inline int cv_round(double v) { return (int)__builtin_nearbyint(v); }  // round-half-even like cvRound
 
 }  // namespace ofb
@@ -52,8 +58,7 @@ struct ofb_handle {
   int num_sms = 148;
   bool force_generic = false;  // OFB_FORCE_GENERIC=1: always take the generic (unfused) kernels
   int iter_cols = 256;         // OFB_ITER_COLS: strip width / CTA size of the fused iteration kernel (128|256)
-  int iter_ws = 4;             // OFB_ITER_WS: 4 = vertical-first float k_iter_v, 3 = high-occupancy k_iter_z, 2 = k_iter_ws2, 1 = k_iter_ws, 0 = barrier-phased k_iter_box
-  int iter_ch = 2;             // OFB_ITER_CH: rows per chunk of k_iter_z (experiments)
+  int iter_ws = 4;             // OFB_ITER_WS=1: k_iter_ws (double vertical sums, cv2's scheme) instead of k_iter_v
   int iter_pfd = 3;            // OFB_ITER_PFD: L2 prefetch distance (rows) of k_iter_v (2 or 3)
   bool iter_prefetch = true;   // OFB_ITER_PREFETCH=0: no L2 prefetch of the next chunk in k_iter_ws2
   int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
@@ -80,6 +85,14 @@ struct ofb_handle {
   float2* d_flow[3] = {nullptr, nullptr, nullptr};  // ping/pong/previous-level, [batch][h][w] float2
   float* d_flow_out = nullptr;    // staging for host API output [batch][H][W][2]
   float* d_init_flow = nullptr;   // USE_INITIAL_FLOW input [batch][H][W][2]
+  // INTER_LINEAR coordinate tables of the inter-level flow upsample, one (x, y) pair per level; built
+  // on the host (double arithmetic, as cv::resize does) and cached for the current schedule
+  ofb::LinTab* d_lintab = nullptr;
+  ofb::LinTab* h_lintab = nullptr;   // pinned
+  size_t lintab_cap = 0;             // entries
+  int tab_w = 0, tab_h = 0, tab_levels = -1;
+  double tab_scale = 0;
+  size_t tab_x_off[ofb::kMaxLevels] = {0}, tab_y_off[ofb::kMaxLevels] = {0};
   // last result bookkeeping for ofb_flow_u_stats
   const float* last_flow = nullptr;
   int last_n = 0, last_w = 0, last_h = 0;

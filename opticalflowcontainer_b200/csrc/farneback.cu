@@ -18,10 +18,7 @@
 
 #include "common.cuh"
 #include "fb_device.cuh"
-#include "fb_iter.cuh"
 #include "fb_iter_ws.cuh"
-#include "fb_iter_ws2.cuh"
-#include "fb_iter_z.cuh"
 #include "fb_iter_v.cuh"
 #include "fb_polyexp.cuh"
 #include "fb_pyramid.cuh"
@@ -317,24 +314,81 @@ __global__ void __launch_bounds__(256) k_blur_h_solve(const float4* __restrict__
 // =====================================================================================
 // Stage a8: inter-level flow upsample = resize(prevFlow, INTER_LINEAR) * (1/pyr_scale)
 // =====================================================================================
+// One column, UPS_ROWS consecutive rows per thread: sixteen independent gathers in flight per thread
+// (the one-pixel version was latency-bound) while a warp still reads and writes contiguous row
+// segments (a four-columns-per-thread variant was LSU-bound: 3x the L1 wavefronts).  Source
+// coordinates come from per-level tables (LinTab) built once on the host in double, as cv::resize
+// computes them.
+constexpr int UPS_ROWS = 4;
 __global__ void __launch_bounds__(256) k_upsample_flow(const float2* __restrict__ prev, int pw, int ph,
-                                                       float2* __restrict__ out, int w, int h, double sx, double sy,
-                                                       float mul) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= w || y >= h) return;
+                                                       float2* __restrict__ out, int w, int h,
+                                                       const LinTab* __restrict__ tabx,
+                                                       const LinTab* __restrict__ taby, float mul) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yb = (blockIdx.y * blockDim.y + threadIdx.y) * UPS_ROWS;
+  if (x >= w || yb >= h) return;
   const float2* p = prev + (size_t)blockIdx.z * pw * ph;
-  int x0, y0;
-  float fx, fy;
-  linear_coord(x, sx, pw, &x0, &fx);
-  linear_coord(y, sy, ph, &y0, &fy);
-  int x1 = min(x0 + 1, pw - 1), y1 = min(y0 + 1, ph - 1);
-  float2 q00 = __ldg(p + (size_t)y0 * pw + x0), q01 = __ldg(p + (size_t)y0 * pw + x1);
-  float2 q10 = __ldg(p + (size_t)y1 * pw + x0), q11 = __ldg(p + (size_t)y1 * pw + x1);
-  float ax0 = 1.f - fx, ay0 = 1.f - fy;
-  float tx = q00.x * ax0 + q01.x * fx, ty = q00.y * ax0 + q01.y * fx;
-  float bx = q10.x * ax0 + q11.x * fx, by = q10.y * ax0 + q11.y * fx;
-  out[(size_t)blockIdx.z * w * h + (size_t)y * w + x] = make_float2((tx * ay0 + bx * fy) * mul, (ty * ay0 + by * fy) * mul);
+  const LinTab tx = tabx[x];
+  const int x0 = tx.i0, x1 = min(x0 + 1, pw - 1);
+  const float fx = tx.f, ax0 = 1.f - fx;
+  float2 q00[UPS_ROWS], q01[UPS_ROWS], q10[UPS_ROWS], q11[UPS_ROWS];
+  float fy[UPS_ROWS];
+#pragma unroll
+  for (int j = 0; j < UPS_ROWS; j++) {
+    const LinTab ty = taby[min(yb + j, h - 1)];
+    const float2* r0 = p + (size_t)ty.i0 * pw;
+    const float2* r1 = p + (size_t)min(ty.i0 + 1, ph - 1) * pw;
+    fy[j] = ty.f;
+    q00[j] = __ldg(r0 + x0);
+    q01[j] = __ldg(r0 + x1);
+    q10[j] = __ldg(r1 + x0);
+    q11[j] = __ldg(r1 + x1);
+  }
+  float2* o = out + (size_t)blockIdx.z * w * h + (size_t)yb * w + x;
+#pragma unroll
+  for (int j = 0; j < UPS_ROWS; j++) {
+    const float ay0 = 1.f - fy[j];
+    const float tx2 = q00[j].x * ax0 + q01[j].x * fx, ty2 = q00[j].y * ax0 + q01[j].y * fx;
+    const float bx = q10[j].x * ax0 + q11[j].x * fx, by = q10[j].y * ax0 + q11[j].y * fx;
+    if (yb + j < h) o[(size_t)j * w] = make_float2((tx2 * ay0 + bx * fy[j]) * mul, (ty2 * ay0 + by * fy[j]) * mul);
+  }
+}
+
+// cv::resize INTER_LINEAR source coordinate of destination index d (host twin of linear_coord).
+static inline LinTab lin_entry(int d, double scale, int src_n) {
+  float f = (float)((d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (s < 0) { f = 0.f; s = 0; }
+  if (s >= src_n - 1) { f = 0.f; s = src_n - 1; }
+  LinTab t;
+  t.i0 = s;
+  t.f = f;
+  return t;
+}
+
+// (Re)builds the upsample tables when the schedule changed; the upload is ordered on the handle's stream.
+static int ensure_lintabs(ofb_handle* h, const Level* sched, int n_levels, int width, int height, double pyr_scale) {
+  if (h->tab_w == width && h->tab_h == height && h->tab_levels == n_levels && h->tab_scale == pyr_scale) return OFB_OK;
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));   // the pinned table may still be in flight from the last rebuild
+  size_t off = 0;
+  for (int li = 1; li < n_levels; li++) {
+    const int w = sched[li].width, hh = sched[li].height, pw = sched[li - 1].width, ph = sched[li - 1].height;
+    if (off + (size_t)w + hh > h->lintab_cap) return set_error(h, OFB_ERR_CAPACITY, "resize table capacity exceeded");
+    const double sx = 1.0 / ((double)w / pw), sy = 1.0 / ((double)hh / ph);
+    h->tab_x_off[li] = off;
+    for (int x = 0; x < w; x++) h->h_lintab[off + x] = lin_entry(x, sx, pw);
+    off += w;
+    h->tab_y_off[li] = off;
+    for (int y = 0; y < hh; y++) h->h_lintab[off + y] = lin_entry(y, sy, ph);
+    off += hh;
+  }
+  if (off) OFB_CUDA(h, cudaMemcpyAsync(h->d_lintab, h->h_lintab, off * sizeof(LinTab), cudaMemcpyHostToDevice, h->stream));
+  h->tab_w = width;
+  h->tab_h = height;
+  h->tab_levels = n_levels;
+  h->tab_scale = pyr_scale;
+  return OFB_OK;
 }
 
 // OPTFLOW_USE_INITIAL_FLOW: resize(flow0, INTER_AREA) * scale  (computeResizeAreaTab weights).
@@ -390,38 +444,14 @@ __global__ void __launch_bounds__(256) k_init_flow_area(const float2* __restrict
 // =====================================================================================
 // Driver: the multi-level schedule on the handle's stream (no host sync inside).
 // =====================================================================================
-// k_iter_z launcher: picks the instantiation for (m, strip width, rows per chunk).
-template <int MT, int COLS, int CH, int MINB>
-static cudaError_t launch_iter_z(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                 int f1_offset, int m, float reg, cudaStream_t st) {
-  const int smem = iter_z_smem_floats<COLS, CH>(m) * (int)sizeof(float);
-  static int configured = -1;   // largest dynamic smem configured for this instantiation
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_iter_z<MT, COLS, CH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  const int tw = COLS - 2 * m;
-  const int strips = (w + tw - 1) / tw;
-  const int slots = MINB * h->num_sms * h->iter_waves;
-  const int per = strips * n_pairs;
-  int segs = per >= slots ? 1 : slots / per;
-  int seg_rows = std::max(16, (hh + segs - 1) / segs);
-  segs = (hh + seg_rows - 1) / seg_rows;
-  dim3 g(strips * segs, n_pairs);
-  k_iter_z<MT, COLS, CH, MINB><<<g, 2 * COLS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m, reg,
-                                                         seg_rows, strips);
-  return cudaGetLastError();
-}
-
 // k_iter_v launcher.
-template <int MT, int COLS, int CH, int MINB, int PFD>
+template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1>
 static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
                                  int f1_offset, int m, float reg, cudaStream_t st) {
   const int smem = iter_v_smem_floats<COLS, CH>(m) * (int)sizeof(float);
   static int configured = -1;   // largest dynamic smem configured for this instantiation
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
@@ -433,7 +463,7 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   int seg_rows = std::max(16, (hh + segs - 1) / segs);
   segs = (hh + seg_rows - 1) / seg_rows;
   dim3 g(strips * segs, n_pairs);
-  k_iter_v<MT, COLS, CH, MINB, PFD><<<g, COLS + CH * COLS / 4, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m,
+  k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP><<<g, COLS + (CH / CLOOP) * COLS / PXT, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m,
                                                                      reg, seg_rows, strips);
   return cudaGetLastError();
 }
@@ -447,6 +477,10 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   int n_levels = 0;
   if (build_schedule(width, height, p->pyr_scale, p->levels, sched, &n_levels) != OFB_OK)
     return set_error(h, OFB_ERR_INVALID_ARG, "too many pyramid levels");
+  {
+    int s__ = ensure_lintabs(h, sched, n_levels, width, height, p->pyr_scale);
+    if (s__) return s__;
+  }
   PolyCoef pc;
   prepare_poly(p->poly_n, p->poly_sigma, &pc);
   BlurCoef bc;
@@ -465,22 +499,10 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   // fused box-window iteration kernel: radius 2..19 (shared-memory ring of 2m+1 rows); the generic
   // three-kernel path covers the Gaussian window and every other radius.
   const bool use_fused = !bc.gaussian && bc.m >= 2 && bc.m <= 19 && !h->force_generic;
-  const int FI_COLS = (h->iter_cols == 128 && !h->iter_ws) ? 128 : 256;   // strip width of the fused kernel
-  if (use_fused) {
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float)));
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float)));
+  if (use_fused && h->iter_ws == 1) {
     const int ws_smem = (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float);
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws2<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws2<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
-    const int smem = (FI_CH + 2 * bc.m + 1) * 5 * FI_COLS * (int)sizeof(float);
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<7, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_box<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
+    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
   }
 
   float2* prev_flow = nullptr;
@@ -507,9 +529,9 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
         OFB_CUDA(h, cudaMemsetAsync(cur, 0, (size_t)n_pairs * w * hh * sizeof(float2), st));
       }
     } else {
-      k_upsample_flow<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(prev_flow, prev_w, prev_h, cur, w, hh,
-                                                                   1.0 / ((double)w / prev_w), 1.0 / ((double)hh / prev_h),
-                                                                   (float)(1.0 / p->pyr_scale));
+      k_upsample_flow<<<grid2d(w, (hh + UPS_ROWS - 1) / UPS_ROWS, n_pairs, blk), blk, 0, st>>>(
+          prev_flow, prev_w, prev_h, cur, w, hh, h->d_lintab + h->tab_x_off[li], h->d_lintab + h->tab_y_off[li],
+          (float)(1.0 / p->pyr_scale));
       OFB_LAUNCH_CHECK(h);
     }
     TE();
@@ -526,12 +548,20 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       // pass H writes hb[frames][H][w] into d_MA (free here: the generic iteration path only uses it
       // after the pyramid stage of the level), pass V writes the level image.
       float* hb = reinterpret_cast<float*>(h->d_MA);
-      dim3 gh((w + 127) / 128, height, frames);
-      k_pyr_h<<<gh, 128, 0, st>>>(src, width, height, hb, w, 1.0 / ((double)w / width), pyc);
-      OFB_LAUNCH_CHECK(h);
+      dim3 gh((w + 127) / 128, (height + PYR_RPT - 1) / PYR_RPT, frames);
       dim3 bv(128, 2), gv((w + 127) / 128, (hh + 1) / 2, frames);
-      k_pyr_v<<<gv, bv, 0, st>>>(hb, height, h->d_img, w, hh, 1.0 / ((double)hh / height), pyc);
-      OFB_LAUNCH_CHECK(h);
+#define OFB_PYR_LAUNCH(RT)                                                                             \
+  do {                                                                                                 \
+    k_pyr_h<RT><<<gh, 128, 0, st>>>(src, width, height, hb, w, 1.0 / ((double)w / width), pyc);        \
+    OFB_LAUNCH_CHECK(h);                                                                               \
+    k_pyr_v<RT><<<gv, bv, 0, st>>>(hb, height, h->d_img, w, hh, 1.0 / ((double)hh / height), pyc);    \
+    OFB_LAUNCH_CHECK(h);                                                                               \
+  } while (0)
+      if (pyc.r == 1) OFB_PYR_LAUNCH(1);
+      else if (pyc.r == 4) OFB_PYR_LAUNCH(4);
+      else if (pyc.r == 9) OFB_PYR_LAUNCH(9);
+      else OFB_PYR_LAUNCH(0);
+#undef OFB_PYR_LAUNCH
       TE();
     }
     TB(OFB_STAGE_POLYEXP);
@@ -570,78 +600,46 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       float2* fout = (last_level && last_it) ? (float2*)d_flow_out : (fin == cur ? alt : cur);
       TB(OFB_STAGE_ITERATION);
       if (use_fused) {
-        const int tw = FI_COLS - 2 * bc.m;
-        const int strips = (w + tw - 1) / tw;
-        const int slots = (512 / FI_COLS) * h->num_sms * h->iter_waves;   // resident CTAs (x waves)
-        const int per = strips * n_pairs;
-        int segs = per >= slots ? 1 : slots / per;
-        int seg_rows = std::max(16, (hh + segs - 1) / segs);
-        segs = (hh + seg_rows - 1) / seg_rows;
-        const size_t smem = (size_t)(FI_CH + 2 * bc.m + 1) * 5 * FI_COLS * sizeof(float);
-        dim3 g(strips * segs, n_pairs);
-#define OFB_ITER_LAUNCH(MT, CW)                                                                                  \
-  k_iter_box<MT, CW><<<g, CW, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale, seg_rows, \
-                                          strips)
-        if (h->iter_ws == 4) {
+        if (h->iter_ws != 1) {
+          // k_iter_v: float van Herk / Gil-Werman vertical sums, no FP64 (default)
           const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
           cudaError_t e;
 #define OFB_V_ARGS h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st
           const int pfd = h->iter_prefetch ? h->iter_pfd : 0;
           if (bc.m == 7) {
             if (h->iter_cols == 128) {
-              if (h->iter_ch == 4) e = launch_iter_v<7, 128, 4, 3, 0>(OFB_V_ARGS);
-              else if (pfd == 0) e = launch_iter_v<7, 128, 2, 4, 0>(OFB_V_ARGS);
-              else if (pfd == 2) e = launch_iter_v<7, 128, 2, 4, 2>(OFB_V_ARGS);
-              else e = launch_iter_v<7, 128, 2, 4, 3>(OFB_V_ARGS);
+              if (pfd == 0) e = launch_iter_v<7, 128, 2, 4, 0, 4>(OFB_V_ARGS);
+              else e = launch_iter_v<7, 128, 2, 4, 3, 4>(OFB_V_ARGS);
             } else {
-              if (h->iter_ch == 3) e = launch_iter_v<7, 256, 3, 2, 0>(OFB_V_ARGS);
-              else if (pfd == 0) e = launch_iter_v<7, 256, 2, 2, 0>(OFB_V_ARGS);
-              else if (pfd == 2) e = launch_iter_v<7, 256, 2, 2, 2>(OFB_V_ARGS);
-              else e = launch_iter_v<7, 256, 2, 2, 3>(OFB_V_ARGS);
+              if (pfd == 0) e = launch_iter_v<7, 256, 2, 2, 0, 4>(OFB_V_ARGS);
+              else if (pfd == 2) e = launch_iter_v<7, 256, 2, 2, 2, 4>(OFB_V_ARGS);
+              else e = launch_iter_v<7, 256, 2, 2, 3, 4>(OFB_V_ARGS);
             }
           } else {
-            e = launch_iter_v<0, 128, 4, 1, 0>(OFB_V_ARGS);
+            e = launch_iter_v<0, 128, 4, 1, 0, 4>(OFB_V_ARGS);
           }
 #undef OFB_V_ARGS
           if (e != cudaSuccess)
             return set_error(h, OFB_ERR_CUDA, "k_iter_v launch failed: %s", cudaGetErrorString(e));
-        } else if (h->iter_ws == 3) {
-          const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
-          cudaError_t e;
-          if (bc.m == 7) {
-            if (h->iter_cols == 128 && h->iter_ch == 2) e = launch_iter_z<7, 128, 2, 4>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
-            else if (h->iter_cols == 128) e = launch_iter_z<7, 128, 4, 3>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
-            else if (h->iter_ch == 2) e = launch_iter_z<7, 256, 2, 2>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
-            else e = launch_iter_z<7, 256, 3, 2>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
-          } else {
-            e = launch_iter_z<0, 128, 4, 1>(h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st);
-          }
-          if (e != cudaSuccess)
-            return set_error(h, OFB_ERR_CUDA, "k_iter_z launch failed: %s", cudaGetErrorString(e));
-        } else if (h->iter_ws == 2) {
-          const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
-#define OFB_WS2_LAUNCH(MT, PF)                                                                                    \
-  k_iter_ws2<MT, PF><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, reg, seg_rows, \
-                                                  strips)
-          if (h->iter_prefetch) {
-            if (bc.m == 7) OFB_WS2_LAUNCH(7, true); else OFB_WS2_LAUNCH(0, true);
-          } else {
-            if (bc.m == 7) OFB_WS2_LAUNCH(7, false); else OFB_WS2_LAUNCH(0, false);
-          }
-#undef OFB_WS2_LAUNCH
-        } else if (h->iter_ws) {
+        } else {
+          // k_iter_ws: cv2's double vertical running sums (OFB_ITER_WS=1; slower — XU-bound — kept as the
+          // precision reference for the float path)
+          const int tw = WS_COLS - 2 * bc.m;
+          const int strips = (w + tw - 1) / tw;
+          const int slots = 2 * h->num_sms * h->iter_waves;   // resident CTAs (x waves)
+          const int per = strips * n_pairs;
+          int segs = per >= slots ? 1 : slots / per;
+          int seg_rows = std::max(16, (hh + segs - 1) / segs);
+          segs = (hh + seg_rows - 1) / seg_rows;
+          const size_t smem = (size_t)(2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * sizeof(float);
+          dim3 g(strips * segs, n_pairs);
           if (bc.m == 7)
             k_iter_ws<7><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
                                                       seg_rows, strips);
           else
             k_iter_ws<0><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
                                                       seg_rows, strips);
-        } else if (FI_COLS == 256) {
-          if (bc.m == 7) OFB_ITER_LAUNCH(7, 256); else OFB_ITER_LAUNCH(0, 256);
-        } else {
-          if (bc.m == 7) OFB_ITER_LAUNCH(7, 128); else OFB_ITER_LAUNCH(0, 128);
         }
-#undef OFB_ITER_LAUNCH
         OFB_LAUNCH_CHECK(h);
       } else {
         k_update_matrices<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_RA, h->d_RB, fin, h->d_MA, h->d_MB, w, hh,

@@ -10,6 +10,10 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
   return i;
 }
+// uint8 -> float without the XU pipe: ptxas turns (float)uint8 into I2F.U16, which runs at a
+// fraction of the FP32 rate on B200 (the level-3 pyramid pass spent 80 us on it).  Exact for v < 2^23.
+__device__ __forceinline__ float u8f(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.f; }
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // cv::resize INTER_LINEAR source coordinate (resize.cpp): fx=(dx+0.5)*scale-0.5, clamp at both ends.

@@ -1,11 +1,10 @@
 // fb_iter_v.cuh — fused Farneback iteration kernel (box window), vertical-first, no FP64.
 //
 // UpdateMatrices + (2m+1)^2 box blur + 2x2 solve in one pass over the level, 56 B of HBM traffic
-// per pixel-iteration.  ncu on the earlier kernels (k_iter_ws / ws2 / z) found the common wall: the
-// XU pipe at 75 % "realtime" — they kept cv2's vertical running sums in double, and the
-// F2F.F64.F32 / F2F.F32.F64 conversions around them (15 per pixel) run at a fraction of the FP32
-// rate on B200.  Instruction diets, L2 prefetch and twice the resident warps all left the time
-// unchanged.  This kernel removes FP64 altogether:
+// per pixel-iteration.  ncu on the earlier kernels (k_iter_ws and two successors) showed
+// the XU pipe at 75 % "realtime": they kept cv2's vertical running sums in double, and the
+// F2F.F64.F32 / F2F.F32.F64 conversions around them (15 per pixel) run at a fraction of the FP32 rate
+// on B200.  This kernel removes FP64 altogether:
 //
 //   * the vertical window sum is done FIRST, on the matrices themselves, by the thread that owns
 //     the column, in float, WITHOUT cancellation drift: rows are grouped in blocks of R = 2m+1;
@@ -19,11 +18,12 @@
 //     horizontal window sums (4 adjacent pixels per thread from float4 reads), the solve and the
 //     coalesced flow store.  No consumer-side ring, no consumer-only barrier.
 //
-// CTA = COLS producer threads + CH*COLS/4 consumer threads; FULL/EMPTY named barriers hand the
+// CTA = COLS producer threads + CH*COLS/PXT consumer threads (PXT = 4 or 8 adjacent pixels each); FULL/EMPTY named barriers hand the
 // double-buffered staging rows (CH output rows per chunk) over.
 #pragma once
 #include "fb_device.cuh"
-#include "fb_iter_ws2.cuh"
+#include "fb_iter_ws.cuh"   // named_bar_sync / named_bar_arrive
+#include "fb_um.cuh"
 
 namespace ofb {
 
@@ -34,15 +34,23 @@ constexpr int iter_v_smem_floats(int m) { return (2 * CH + 2 * m + 1) * 5 * COLS
 // (R0, flow, and the new corner row of the R1 gather — the flow field is smooth, so "same
 // displacement, PFD rows down" predicts it).  A producer has only one row of loads in flight, so
 // without this each row pays a full HBM round trip (~1 us under load); with it the demand loads
-// hit in L2.  Prefetches write no register and use no scoreboard.  The R buffers carry kRowPad
-// spare rows so the predicted corner row stays inside the allocation (PFD + 1 <= kRowPad).
-template <int MT, int COLS, int CH, int MINB, int PFD>
-__global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
+// hit in L2.  Prefetches write no register and use no scoreboard (a register-level software
+// pipeline does not work: ptxas puts every LDG of the loop on one counting scoreboard).  Measured
+// -10 % kernel time; a cp.async.bulk.prefetch.L2 variant (5 requests per strip row) measured +2 %.
+// The R buffers carry kRowPad spare rows so the predicted corner row stays inside the allocation.
+// RIF = matrix rows a producer thread keeps in flight (1, or CH: the loads of all CH rows of a chunk are
+// issued before the first is consumed).  CLOOP = rows a consumer thread handles per chunk (1, or CH).
+template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1>
+__global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
     k_iter_v(const float4* __restrict__ RA, const float* __restrict__ RB, const float2* __restrict__ flow_in,
              float2* __restrict__ flow_out, int w, int h, int f1_offset, int m_rt, float reg, int seg_rows,
              int strips) {
-  constexpr int QUADS = COLS / 4;
-  constexpr int NCONS = CH * QUADS;
+  static_assert(PXT == 4 || PXT == 8, "4 or 8 adjacent pixels per consumer thread");
+  constexpr int GROUPS = COLS / PXT;
+  static_assert(RIF == 1 || RIF == CH, "rows in flight: 1 or the whole chunk");
+  static_assert(CLOOP == 1 || CLOOP == CH, "consumer rows per thread: 1 or the whole chunk");
+  constexpr int NCONS = (CH / CLOOP) * GROUPS;
+  static_assert(NCONS % 32 == 0, "whole consumer warps");
   constexpr int NT = COLS + NCONS;
   enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3 };
   const int m = MT > 0 ? MT : m_rt;
@@ -75,51 +83,49 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     const unsigned uw = (unsigned)w, uh = (unsigned)h;
     const int x = clampi(x_base + tid, 0, w - 1);
     const bool xborder = (unsigned)(x - 5) >= (unsigned)(w - 10);
-    float2 fl = __ldg(fin + ((unsigned)clampi(t_first, 0, h - 1) * uw + (unsigned)x));
     float* rcol = ring + tid;                        // ring[k][ch][tid]
     float P[5] = {0.f, 0.f, 0.f, 0.f, 0.f};          // prefix sums of the current block
     float Bp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};         // sum of the previous block
     int k = 0;                                       // offset of row t inside its block
     bool have_prev = false;
 
-    // one matrix row: M(t) -> P += M; V = (Bp - P_prev[k]) + P; ring[k] = P; block bookkeeping
-    auto row = [&](int t, float (&V)[5]) {
+    // start the loads of matrix row t (flow of the row in `f`), prefetch PFD rows ahead
+    auto issue = [&](UmLoads2& L, float2 f, int t) {
       const int y = clampi(t, 0, h - 1);
       const unsigned yw = (unsigned)y * uw;
 #if defined(OFB_DBG) && (OFB_DBG & 1)     // experiment: zero displacement (perfectly regular gathers)
-      fl = make_float2(0.f, 0.f);
+      f = make_float2(0.f, 0.f);
 #endif
-#if defined(OFB_DBG) && (OFB_DBG & 2)     // experiment: no loads, no UpdateMatrices
-      M5 mm; mm.g11 = 1.f; mm.g12 = 0.f; mm.g22 = 1.f; mm.h1 = 0.5f; mm.h2 = 0.25f;
-      float old[5];
-#pragma unroll
-      for (int ch = 0; ch < 5; ch++) old[ch] = have_prev ? rcol[(k * 5 + ch) * COLS] : 0.f;
-#else
-      UmLoads2 L;
 #if defined(OFB_DBG) && (OFB_DBG & 8)     // experiment: no R1 gather (R0 values stand in for the corners)
       {
         const unsigned o = yw + (unsigned)x;
         L.a0 = __ldg(RA0 + o); L.b0 = __ldg(RB0 + o);
         L.q00 = L.q01 = L.q10 = L.q11 = L.a0; L.s00 = L.s01 = L.s10 = L.s11 = L.b0;
-        L.dx = fl.x; L.dy = fl.y; L.fx = 0.25f; L.fy = 0.5f; L.inside = true;
+        L.dx = f.x; L.dy = f.y; L.fx = 0.25f; L.fy = 0.5f; L.inside = true;
       }
 #else
-      um_issue2<false>(L, RA0, RB0, RA1, RB1, fl, x, y, yw, uw, uh);
+      um_issue2(L, RA0, RB0, RA1, RB1, f, x, y, yw, uw, uh);
 #endif
       if (PFD > 0) {
         static_assert(PFD + 1 <= kRowPad, "prefetch distance exceeds the row padding of the R buffers");
         const unsigned op = (unsigned)clampi(t + PFD, 0, h - 1) * uw + (unsigned)x;
         prefetch_l2(RA0 + op);
         prefetch_l2(RB0 + op);
-        prefetch_l2(fin + ((unsigned)clampi(t + PFD + 1, 0, h - 1) * uw + (unsigned)x));
+        prefetch_l2(fin + ((unsigned)clampi(t + PFD + RIF, 0, h - 1) * uw + (unsigned)x));
         const unsigned g = L.inside ? (unsigned)__float2int_rd((float)y + L.dy) * uw + (unsigned)__float2int_rd((float)x + L.dx) : 0u;
         prefetch_l2(RA1 + (g + (PFD + 1) * uw));
         prefetch_l2(RB1 + (g + (PFD + 1) * uw));
       }
-      fl = __ldg(fin + ((unsigned)clampi(t + 1, 0, h - 1) * uw + (unsigned)x));   // next row's flow
+    };
+    // matrix row t from its loads: M(t) -> P += M; V = (Bp - P_prev[k]) + P; ring[k] = P; block bookkeeping
+    auto finish = [&](const UmLoads2& L, int t, float (&V)[5]) {
+      const int y = clampi(t, 0, h - 1);
       float old[5];
 #pragma unroll
       for (int ch = 0; ch < 5; ch++) old[ch] = have_prev ? rcol[(k * 5 + ch) * COLS] : 0.f;
+#if defined(OFB_DBG) && (OFB_DBG & 2)     // experiment: no UpdateMatrices (and, with the loads unused, no loads)
+      M5 mm; mm.g11 = 1.f; mm.g12 = 0.f; mm.g22 = 1.f; mm.h1 = 0.5f; mm.h2 = 0.25f;
+#else
       const M5 mm = um_finish2(L, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h);
 #endif
       P[0] += mm.g11; P[1] += mm.g12; P[2] += mm.g22; P[3] += mm.h1; P[4] += mm.h2;
@@ -135,117 +141,183 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         for (int ch = 0; ch < 5; ch++) { Bp[ch] = P[ch]; P[ch] = 0.f; }
       }
     };
+    auto flow_at = [&](int t) { return __ldg(fin + ((unsigned)clampi(t, 0, h - 1) * uw + (unsigned)x)); };
 
-    // warm-up: the R-1 rows above the first output row (no hand-over)
-    for (int t = t_first; t < t_first + R - 1; t++) {
-      float V[5];
-      row(t, V);
-    }
-    for (int c = 0; c < n_chunks; c++) {
-      const int buf = c & 1;
-      if (c >= 2) named_bar_sync(BAR_EMPTY0 + buf, NT);            // consumers released this buffer
-      float* srow = stage + buf * CH * 5 * COLS + tid;
+    if constexpr (RIF == 1) {
+      float2 fl = flow_at(t_first);
+      // warm-up: the R-1 rows above the first output row (no hand-over)
+      for (int t = t_first; t < t_first + R - 1; t++) {
+        UmLoads2 L;
+        float V[5];
+        issue(L, fl, t);
+        fl = flow_at(t + 1);
+        finish(L, t, V);
+      }
+      for (int c = 0; c < n_chunks; c++) {
+        const int buf = c & 1;
+        if (c >= 2) named_bar_sync(BAR_EMPTY0 + buf, NT);            // consumers released this buffer
+        float* srow = stage + buf * CH * 5 * COLS + tid;
 #pragma unroll
-      for (int rr = 0; rr < CH; rr++) {
-        const int yo = y0 + c * CH + rr;                           // output row; newest matrix row = yo + m
-        if (yo < y1) {
+        for (int rr = 0; rr < CH; rr++) {
+          const int yo = y0 + c * CH + rr;                           // output row; newest matrix row = yo + m
+          if (yo < y1) {
+            UmLoads2 L;
+            float V[5];
+            issue(L, fl, yo + m);
+            fl = flow_at(yo + m + 1);
+            finish(L, yo + m, V);
+#pragma unroll
+            for (int ch = 0; ch < 5; ch++) srow[(rr * 5 + ch) * COLS] = V[ch];
+          }
+        }
+        named_bar_arrive(BAR_FULL0 + buf, NT);                       // staged rows of chunk c are ready
+      }
+    } else {
+      // CH rows in flight: all loads of a chunk are issued before the first row is consumed
+      float2 fl[CH];
+#pragma unroll
+      for (int rr = 0; rr < CH; rr++) fl[rr] = flow_at(t_first + rr);
+      // warm-up rows t_first .. t_first+R-2 in groups of CH (rows past the warm-up are handled by chunk 0,
+      // so the warm-up only takes whole groups and chunk 0 starts where it stopped)
+      int t = t_first;
+      const int t_out = t_first + R - 1;                             // first matrix row that yields an output row
+      for (; t + CH <= t_out; t += CH) {
+        UmLoads2 L[CH];
+#pragma unroll
+        for (int rr = 0; rr < CH; rr++) issue(L[rr], fl[rr], t + rr);
+#pragma unroll
+        for (int rr = 0; rr < CH; rr++) fl[rr] = flow_at(t + CH + rr);
+#pragma unroll
+        for (int rr = 0; rr < CH; rr++) {
           float V[5];
-          row(yo + m, V);
+          finish(L[rr], t + rr, V);
+        }
+      }
+      for (; t < t_out; t++) {                                       // remainder of the warm-up, one row at a time
+        UmLoads2 L1;
+        float V[5];
+        issue(L1, fl[0], t);
+#pragma unroll
+        for (int rr = 0; rr + 1 < CH; rr++) fl[rr] = fl[rr + 1];
+        fl[CH - 1] = flow_at(t + CH);
+        finish(L1, t, V);
+      }
+      for (int c = 0; c < n_chunks; c++) {
+        const int buf = c & 1;
+        const int tc = y0 + c * CH + m;                              // newest matrix row of output row y0 + c*CH
+        UmLoads2 L[CH];
+#pragma unroll
+        for (int rr = 0; rr < CH; rr++) issue(L[rr], fl[rr], tc + rr);
+#pragma unroll
+        for (int rr = 0; rr < CH; rr++) fl[rr] = flow_at(tc + CH + rr);
+        if (c >= 2) named_bar_sync(BAR_EMPTY0 + buf, NT);            // consumers released this buffer
+        float* srow = stage + buf * CH * 5 * COLS + tid;
+#pragma unroll
+        for (int rr = 0; rr < CH; rr++) {
+          float V[5];
+          finish(L[rr], tc + rr, V);                                 // (rows past y1 keep the state consistent; never read)
 #pragma unroll
           for (int ch = 0; ch < 5; ch++) srow[(rr * 5 + ch) * COLS] = V[ch];
         }
+        named_bar_arrive(BAR_FULL0 + buf, NT);                       // staged rows of chunk c are ready
       }
-      named_bar_arrive(BAR_FULL0 + buf, NT);                       // staged rows of chunk c are ready
     }
     return;
   }
 
-  // -------------------------------------------------------------------- CONSUMERS (one quad of one row each)
+  // -------------------------------------------------------------------- CONSUMERS (PXT adjacent pixels of one row each)
   float2* fout = flow_out + (size_t)pair * n;
   const int ct = tid - COLS;                         // 0..NCONS-1
-  const int q_row = ct / QUADS;                      // staged row of this thread's quad
-  const int q0 = (ct % QUADS) * 4;                   // first of its 4 strip columns
+  const int q_row0 = (ct / GROUPS) * CLOOP;          // first staged row of this thread's pixel group
+  const int q0 = (ct % GROUPS) * PXT;                // first of its PXT strip columns
   const int ox = x_base + q0;                        // image x of that column
-  // columns of the quad that are real outputs of this strip
-  bool valid[4];
+  // columns of the group that are real outputs of this strip
+  unsigned vmask = 0;
 #pragma unroll
-  for (int j = 0; j < 4; j++) valid[j] = q0 + j >= m && q0 + j < COLS - m && ox + j < w;
-  const bool any_valid = valid[0] || valid[1] || valid[2] || valid[3];
-  const bool all_valid = valid[0] && valid[1] && valid[2] && valid[3];
+  for (int j = 0; j < PXT; j++)
+    if (q0 + j >= m && q0 + j < COLS - m && ox + j < w) vmask |= 1u << j;
+  constexpr unsigned ALL = (1u << PXT) - 1u;
 
   for (int c = 0; c < n_chunks; c++) {
     const int buf = c & 1;
-    const int yo = y0 + c * CH + q_row;
     named_bar_sync(BAR_FULL0 + buf, NT);             // producers finished staging chunk c
 #if defined(OFB_DBG) && (OFB_DBG & 4)     // experiment: consumers only hand the buffers back
-    if (c == n_chunks - 1 && any_valid) fout[(unsigned)(y0 * w + max(ox, 0))] = make_float2(stage[ct], 0.f);
+    if (c == n_chunks - 1 && vmask) fout[(unsigned)(y0 * w + max(ox, 0))] = make_float2(stage[ct], 0.f);
     if (c + 2 < n_chunks) named_bar_arrive(BAR_EMPTY0 + buf, NT);
     continue;
 #endif
-    if (yo < y1 && any_valid) {
+#pragma unroll
+    for (int cl = 0; cl < CLOOP; cl++) {
+      const int q_row = q_row0 + cl;
+      const int yo = y0 + c * CH + q_row;
+      if (!(yo < y1 && vmask)) continue;
       const float* srow = stage + (buf * CH + q_row) * 5 * COLS;
-      float sum[5][4];
+      float sum[5][PXT];
 #pragma unroll
       for (int ch = 0; ch < 5; ch++) {
         const float* s = srow + ch * COLS;
-        float s0, s1, s2, s3;
-        if (MT > 0) {
-          constexpr int KQ = (MT + 3) / 4;
-          float e[(2 * KQ + 1) * 4];                 // e[d + 4*KQ] = staged value at column q0 + d
+        if constexpr (MT > 0) {
+          // e[i] = staged value at strip column q0 - PAD + i; the window of pixel j is e[PAD+j-MT .. PAD+j+MT]
+          constexpr int PAD = (MT + 3) / 4 * 4;
+          constexpr int NE = PXT + 2 * PAD;
+          float e[NE];
 #pragma unroll
-          for (int kk = -KQ; kk <= KQ; kk++) {
-            const int cq = min(max(q0 + 4 * kk, 0), COLS - 4);
-            const float4 v = *reinterpret_cast<const float4*>(s + cq);
-            e[(kk + KQ) * 4 + 0] = v.x; e[(kk + KQ) * 4 + 1] = v.y; e[(kk + KQ) * 4 + 2] = v.z; e[(kk + KQ) * 4 + 3] = v.w;
+          for (int v = 0; v < NE / 4; v++) {
+            const int cq = min(max(q0 - PAD + 4 * v, 0), COLS - 4);
+            const float4 t4 = *reinterpret_cast<const float4*>(s + cq);
+            e[4 * v] = t4.x; e[4 * v + 1] = t4.y; e[4 * v + 2] = t4.z; e[4 * v + 3] = t4.w;
           }
-          constexpr int O = 4 * KQ;
-          float core = e[O + 3 - MT];                // d in [3-MT, MT] is inside all four windows
+          // columns common to all PXT windows: [PAD + PXT-1 - MT, PAD + MT]
+          constexpr int C0 = PAD + PXT - 1 - MT, C1 = PAD + MT;
+          static_assert(C0 <= C1, "window narrower than the pixel group");
+          float core = e[C0];
 #pragma unroll
-          for (int d = 4 - MT; d <= MT; d++) core += e[O + d];
-          float l = e[O + 2 - MT];
-          s2 = core + l;
-          l += e[O + 1 - MT];
-          s1 = core + l;
-          l += e[O - MT];
-          s0 = core + l;
-          float r = e[O + MT + 1];
-          s1 += r;
-          r += e[O + MT + 2];
-          s2 += r;
-          r += e[O + MT + 3];
-          s3 = core + r;
+          for (int i = C0 + 1; i <= C1; i++) core += e[i];
+          float l = 0.f;                             // suffix sums on the left of the core
+          sum[ch][PXT - 1] = core;
+#pragma unroll
+          for (int j = PXT - 2; j >= 0; j--) {
+            l += e[PAD + j - MT];                    // columns PAD+j-MT .. C0-1 belong to windows <= j
+            sum[ch][j] = core + l;
+          }
+          float r = 0.f;                             // prefix sums on the right of the core
+#pragma unroll
+          for (int j = 1; j < PXT; j++) {
+            r += e[PAD + j + MT];
+            sum[ch][j] += r;
+          }
         } else {
-          s0 = s1 = s2 = s3 = 0.f;
-          const int kq = (m + 3) >> 2;
-          for (int kk = -kq; kk <= kq; kk++) {
-            const int cq = min(max(q0 + 4 * kk, 0), COLS - 4);
-            const float4 v = *reinterpret_cast<const float4*>(s + cq);
-            const float e[4] = {v.x, v.y, v.z, v.w};
+          const int kq = (m + 3) >> 2;               // quads to each side
+#pragma unroll
+          for (int j = 0; j < PXT; j++) sum[ch][j] = 0.f;
+          for (int v = -kq; v < PXT / 4 + kq; v++) {
+            const int cq = min(max(q0 + 4 * v, 0), COLS - 4);
+            const float4 t4 = *reinterpret_cast<const float4*>(s + cq);
+            const float e[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-              const int d = 4 * kk + i;
-              if (d >= 0 - m && d <= 0 + m) s0 += e[i];
-              if (d >= 1 - m && d <= 1 + m) s1 += e[i];
-              if (d >= 2 - m && d <= 2 + m) s2 += e[i];
-              if (d >= 3 - m && d <= 3 + m) s3 += e[i];
+              const int d = 4 * v + i;               // column offset from q0
+#pragma unroll
+              for (int j = 0; j < PXT; j++)
+                if (d >= j - m && d <= j + m) sum[ch][j] += e[i];
             }
           }
         }
-        sum[ch][0] = s0; sum[ch][1] = s1; sum[ch][2] = s2; sum[ch][3] = s3;
       }
-      float2 f[4];
+      float2 f[PXT];
 #pragma unroll
-      for (int j = 0; j < 4; j++) f[j] = solve2x2_sums(sum[0][j], sum[1][j], sum[2][j], sum[3][j], sum[4][j], reg);
+      for (int j = 0; j < PXT; j++) f[j] = solve2x2_sums(sum[0][j], sum[1][j], sum[2][j], sum[3][j], sum[4][j], reg);
       const int oi = yo * w + ox;                    // (oi + j >= 0 for every valid column j)
       float2* o = fout + (unsigned)max(oi, 0);
-      if (all_valid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-        // 16-byte aligned: two 128-bit stores
-        *reinterpret_cast<float4*>(o) = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
-        *reinterpret_cast<float4*>(o + 2) = make_float4(f[2].x, f[2].y, f[3].x, f[3].y);
+      if (vmask == ALL && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        // 16-byte aligned: 128-bit stores
+#pragma unroll
+        for (int j = 0; j < PXT; j += 2)
+          *reinterpret_cast<float4*>(o + j) = make_float4(f[j].x, f[j].y, f[j + 1].x, f[j + 1].y);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (valid[j]) fout[(unsigned)(oi + j)] = f[j];
+        for (int j = 0; j < PXT; j++)
+          if ((vmask >> j) & 1u) fout[(unsigned)(oi + j)] = f[j];
       }
     }
     if (c + 2 < n_chunks) named_bar_arrive(BAR_EMPTY0 + buf, NT);   // staging buffer may be refilled

@@ -25,13 +25,17 @@ constexpr int PX_TW = PX_COLS - 2 * PX_HALO;
 constexpr int PX_ROWS = 4;     // rows per step
 constexpr int PX_MAXN = 8;     // largest poly_n served by this kernel
 
-// Level-image value feed of one thread (= one column xc, rows visited in increasing order).
+// Level-image value feed of one thread (= one column xc, rows visited in increasing order).  Loading
+// and consuming a row are separate steps so the kernel can issue the loads of the NEXT step right
+// after it has consumed the raw values of the current one: the loads then have a whole step of
+// arithmetic to land (ncu on the first version: long-scoreboard stalls on the u8 loads dominated).
 template <int SRC>
 struct LevelColumn;
 
 // SRC = 0: level image in HBM (levels k >= 1, written by k_pyr_h / k_pyr_v).
 template <>
 struct LevelColumn<0> {
+  typedef float Raw;
   const float* col;
   int w, h;
   __device__ __forceinline__ void init(const float* img, int xc, int w_, int h_) {
@@ -39,17 +43,21 @@ struct LevelColumn<0> {
     w = w_;
     h = h_;
   }
-  __device__ __forceinline__ float at(int t) const { return __ldg(col + (size_t)clampi(t, 0, h - 1) * w); }
+  __device__ __forceinline__ void start(int) {}
+  __device__ __forceinline__ Raw load(int t) const { return __ldg(col + (size_t)clampi(t, 0, h - 1) * w); }
+  __device__ __forceinline__ float consume(int, Raw r) { return r; }
 };
 
 // SRC = 1: uint8 source frame of the level's size; I = Gv * (Gh * float(src)), 3 taps, REFLECT_101.
-// Horizontally blurred rows tc-1, tc, tc+1 are kept while the row index advances.
+// Horizontally blurred rows tc-1, tc, tc+1 are kept while the row index advances by 0 or 1 per call;
+// the only new data a row needs is the source row below it.
 template <>
 struct LevelColumn<1> {
+  struct Raw { unsigned a, b, c; };
   const uint8_t* base;
   size_t pitch;
   int xl, xc, xr, h;
-  int tc;            // row the state is centred on (-1 = none yet)
+  int tc;            // row the state is centred on
   float k0, k1, hm, h0, hp, cur;
   __device__ __forceinline__ void init(const uint8_t* frame, size_t pitch_, int xc_, int w, int h_, float k0_,
                                        float k1_) {
@@ -61,23 +69,32 @@ struct LevelColumn<1> {
     h = h_;
     k0 = k0_;
     k1 = k1_;
-    tc = -1;
   }
-  __device__ __forceinline__ float hrow(int s) const {
+  __device__ __forceinline__ Raw raw_row(int s) const {
     const uint8_t* p = base + (size_t)s * pitch;
-    return fmaf(k1, (float)__ldg(p + xl) + (float)__ldg(p + xr), k0 * (float)__ldg(p + xc));
+    Raw r;
+    r.a = __ldg(p + xl);
+    r.b = __ldg(p + xc);
+    r.c = __ldg(p + xr);
+    return r;
   }
-  __device__ __forceinline__ float at(int t) {
+  __device__ __forceinline__ float hval(Raw r) const { return fmaf(k1, u8f(r.a) + u8f(r.c), k0 * u8f(r.b)); }
+  // centre the state on the first row to be consumed (direct loads, once per segment)
+  __device__ __forceinline__ void start(int t) {
     const int n = clampi(t, 0, h - 1);
-    if (n != tc) {   // uniform over the CTA (depends on t only)
-      if (tc >= 0 && n == tc + 1) {
-        hm = h0;
-        h0 = hp;
-      } else {
-        h0 = hrow(n);
-        hm = hrow(reflect101(n - 1, h));
-      }
-      hp = hrow(reflect101(n + 1, h));
+    h0 = hval(raw_row(n));
+    hm = hval(raw_row(reflect101(n - 1, h)));
+    hp = hval(raw_row(reflect101(n + 1, h)));
+    tc = n;
+    cur = fmaf(k1, hm + hp, k0 * h0);
+  }
+  __device__ __forceinline__ Raw load(int t) const { return raw_row(reflect101(clampi(t, 0, h - 1) + 1, h)); }
+  __device__ __forceinline__ float consume(int t, Raw r) {
+    const int n = clampi(t, 0, h - 1);
+    if (n != tc) {   // n == tc + 1; uniform over the CTA (depends on t only)
+      hm = h0;
+      h0 = hp;
+      hp = hval(r);
       tc = n;
       cur = fmaf(k1, hm + hp, k0 * h0);
     }
@@ -106,13 +123,21 @@ __global__ void __launch_bounds__(PX_COLS)
   if constexpr (SRC == 0) feed.init(I + fbase, xc, w, h);
   else feed.init(src.frame(frame), src.pitch, xc, w, h, k0, k1);
 
+  typedef typename LevelColumn<SRC>::Raw Raw;
   // window rows: win[i] = I(row ys - NMAX + i) for the step starting at output row ys
+  // (generic n < NMAX: the outer rows are loaded but never used)
   float win[WIN];
+  feed.start(y0 - NMAX);
+  {
+    Raw rw[2 * NMAX];
 #pragma unroll
-  for (int i = 0; i < 2 * NMAX; i++) {
-    const int t = y0 - NMAX + i;
-    win[i] = feed.at(t);   // (generic n < NMAX: the outer rows are loaded but never used)
+    for (int i = 0; i < 2 * NMAX; i++) rw[i] = feed.load(y0 - NMAX + i);
+#pragma unroll
+    for (int i = 0; i < 2 * NMAX; i++) win[i] = feed.consume(y0 - NMAX + i, rw[i]);
   }
+  Raw nx[PX_ROWS];   // raw values of the rows entering the window in the next step (loads in flight)
+#pragma unroll
+  for (int r = 0; r < PX_ROWS; r++) nx[r] = feed.load(y0 + NMAX + r);
 
   // H-phase role
   const int hr = tid >> 6;            // row within the step
@@ -124,7 +149,9 @@ __global__ void __launch_bounds__(PX_COLS)
   for (int ys = y0; ys < y1; ys += PX_ROWS) {
     // ---------------- V: 4 new rows, vertical moments of rows ys .. ys+3
 #pragma unroll
-    for (int r = 0; r < PX_ROWS; r++) win[2 * NMAX + r] = feed.at(ys + NMAX + r);
+    for (int r = 0; r < PX_ROWS; r++) win[2 * NMAX + r] = feed.consume(ys + NMAX + r, nx[r]);
+#pragma unroll
+    for (int r = 0; r < PX_ROWS; r++) nx[r] = feed.load(ys + PX_ROWS + NMAX + r);   // rows clamp: always valid
 #pragma unroll
     for (int r = 0; r < PX_ROWS; r++) {
       const float* c = win + NMAX + r;   // centre of row ys + r
