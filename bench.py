@@ -98,7 +98,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv:
@@ -182,6 +182,8 @@ def run_ours(args, rank, local_rank, world):
     frames_per_set = (B + 1) if seq else 2 * B
     n_sets = max(2, int(np.ceil(2.0 * L2_BYTES / (frames_per_set * istride))) + 1)
     # synthetic frames: a few distinct textures, shifted copies as "next"
+    # (corpus C2: a panning texture, per-frame shift ~U(-8, 8) px — real-valued, so the
+    # flow is sub-pixel as it is for a real camera)
     base = [synth.cheap_texture(H_, W_, 1000 * rank + i) for i in range(4)]
     rng = np.random.default_rng(rank)
     host_sets = []
@@ -189,15 +191,15 @@ def run_ours(args, rank, local_rank, world):
         fr = np.empty((frames_per_set, H_, W_), np.uint8)
         if seq:
             t = base[s % 4]
-            ox = oy = 0
+            ox = oy = 0.0
             for i in range(frames_per_set):
-                fr[i] = np.roll(t, (oy, ox), axis=(0, 1))
-                ox += int(rng.integers(-8, 9)); oy += int(rng.integers(-8, 9))
+                fr[i] = synth.subpixel_shift(t, ox, oy)
+                ox += float(rng.uniform(-8, 8)); oy += float(rng.uniform(-8, 8))
         else:
             for i in range(B):
                 t = base[(s + i) % 4]
                 fr[i] = np.roll(t, (i * 7 % 13, i * 5 % 11), axis=(0, 1))
-                fr[B + i] = np.roll(fr[i], (int(rng.integers(-8, 9)), int(rng.integers(-8, 9))), axis=(0, 1))
+                fr[B + i] = synth.subpixel_shift(fr[i], float(rng.uniform(-8, 8)), float(rng.uniform(-8, 8)))
         host_sets.append(fr)
     dev_sets = [torch.from_numpy(fr).cuda() for fr in host_sets]
     d_flow = torch.empty((B, H_, W_, 2), dtype=torch.float32, device="cuda")
@@ -235,6 +237,7 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop()
     dev_ms = ev0.elapsed_time(ev1)
     stage = eng.timing_read()
+    iter_samples = eng.timing_samples("iteration")
     eng.timing_enable(False)
     launches = eng.launch_count - l0
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -290,9 +293,23 @@ def run_ours(args, rank, local_rank, world):
     nl = level_pixels(W_, H_)
     it_ms, it_cnt = stage["iteration"]
     iters = PARAMS["iterations"]
-    alg_iter_bytes = 56.0 * sum(nl) * iters * B * args.steps       # all iteration-stage launches of the timed region
-    it_gbs = alg_iter_bytes / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0
+    # dominant kernel = the level-0 (1920x1080) launch of the fused iteration kernel k_iter_v: the last
+    # `iters` iteration launches of every call.  achieved = algorithmic bytes of one such launch
+    # (56 B x N x B pairs) / its average CUDA-event duration in the timed region.
+    per_call = len(nl) * iters
+    l0 = [t for i, t in enumerate(iter_samples) if i % per_call >= per_call - iters]
+    l0_ms = float(np.mean(l0)) if l0 else 0.0
+    alg_launch_bytes = 56.0 * nl[-1] * B
+    it_gbs = alg_launch_bytes / (l0_ms * 1e-3) / 1e9 if l0_ms > 0 else 0.0
+    stage_gbs = 56.0 * sum(nl) * iters * B * args.steps / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0
     pipe_gbs = algorithmic_bytes_per_pair(W_, H_) * (value / world) / 1e9
+    traffic = None                                                  # DRAM bytes per launch from the committed ncu capture
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_iter_v_ncu.json")))
+        if prof.get("pairs_per_launch"):
+            traffic = prof["dram_bytes_per_launch"] * B / prof["pairs_per_launch"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": plain_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -301,10 +318,14 @@ def run_ours(args, rank, local_rank, world):
                    "mode": args.mode, "parallelism": "frame-pair sharding x%d, no collective" % world,
                    "l2": "inputs rotate over %d frame sets (%.0f MB > 2x L2); per-step working set %.0f MB >> L2"
                          % (n_sets, n_sets * frames_per_set * istride / 1e6, B * 232.0)},
-        "roofline": {"bound": "hbm", "kernel": "iteration stage (UpdateMatrices + blur + 2x2 solve)",
+        "roofline": {"bound": "hbm", "kernel": "k_iter_v, level-0 launch (UpdateMatrices + box blur + 2x2 solve fused)",
                      "achieved": it_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": it_gbs / peaks["hbm_gbs"],
-                     "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch_group": "56 B x n_l x %d pairs" % B,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_launch_bytes,
+                     "algorithmic_bytes_model": "56 B x 2073600 px x %d pairs" % B,
+                     "launch_ms": l0_ms, "launches_timed": len(l0),
+                     "level0_launch_share_of_step": (sum(l0) / dev_ms) if dev_ms > 0 else None,
+                     "iteration_stage_all_levels_gbs": stage_gbs,
                      "share_of_step": it_ms / dev_ms if dev_ms > 0 else None,
                      "pipeline_achieved": pipe_gbs, "pipeline_frac": pipe_gbs / peaks["hbm_gbs"],
                      "pipeline_bytes_per_pair": algorithmic_bytes_per_pair(W_, H_),
@@ -335,7 +356,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="frame pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="frame pairs per step per GPU")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence"])
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--ref-pairs", type=int, default=2, help="--impl reference: pairs per worker per step")

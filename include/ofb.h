@@ -156,6 +156,9 @@ int ofb_timing_enable(ofb_handle* h, int enable);
 /* Synchronises the stream and returns, per stage, the summed event time in milliseconds and the
  * number of launches recorded since ofb_timing_enable(h, 1).  Arrays of OFB_NUM_STAGES. */
 int ofb_timing_read(ofb_handle* h, double* ms_out, uint64_t* launches_out);
+/* The individual samples of one stage, in launch order: ms_out receives up to `capacity` event
+ * times (milliseconds), *n_out the number of samples recorded for that stage. */
+int ofb_timing_read_samples(ofb_handle* h, int stage, double* ms_out, int capacity, int* n_out);
 
 /* ---- on-device reduction of the flow field (the node contract) ----------------
  * Every reference node collapses the field to one scalar right after the flow

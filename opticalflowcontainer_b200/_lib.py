@@ -58,6 +58,7 @@ _SIGNATURES = {
     "ofb_launch_count": (C.c_uint64, [C.c_void_p]),
     "ofb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ofb_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "ofb_timing_read_samples": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]),
     "ofb_flow_u_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "ofb_good_features": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.POINTER(GfttParams),
                                     C.c_void_p, C.POINTER(C.c_int)]),

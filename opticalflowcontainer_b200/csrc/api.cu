@@ -127,6 +127,24 @@ int ofb_timing_read(ofb_handle* h, double* ms_out, uint64_t* launches_out) {
   return OFB_OK;
 }
 
+int ofb_timing_read_samples(ofb_handle* h, int stage, double* ms_out, int capacity, int* n_out) {
+  if (!h || !ms_out || !n_out || stage < 0 || stage >= OFB_NUM_STAGES || capacity < 0) return OFB_ERR_INVALID_ARG;
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int n = 0;
+  for (size_t i = 0; i < h->ev_used; i++) {
+    if (h->ev_stage[i] != stage) continue;
+    if (n < capacity) {
+      float ms = 0.f;
+      OFB_CUDA(h, cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+      ms_out[n] = ms;
+    }
+    n++;
+  }
+  *n_out = n;
+  return OFB_OK;
+}
+
 int ofb_synchronize(ofb_handle* h) {
   if (!h) return OFB_ERR_INVALID_ARG;
   OFB_CUDA(h, cudaSetDevice(h->device));

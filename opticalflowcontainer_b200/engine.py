@@ -79,6 +79,15 @@ class FlowEngine:
         _lib.check(self._lib.ofb_timing_read(self._h, ms, cnt), self._h)
         return {s: (ms[i], int(cnt[i])) for i, s in enumerate(self.STAGES)}
 
+    def timing_samples(self, stage: str):
+        """Per-launch event times (ms, launch order) of one stage since timing_enable()."""
+        idx = self.STAGES.index(stage)
+        n = C.c_int(0)
+        cap = 1 << 16
+        buf = (C.c_double * cap)()
+        _lib.check(self._lib.ofb_timing_read_samples(self._h, idx, buf, cap, C.byref(n)), self._h)
+        return [buf[i] for i in range(min(n.value, cap))]
+
     def synchronize(self):
         _lib.check(self._lib.ofb_synchronize(self._h), self._h)
 
