@@ -138,6 +138,36 @@ int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_f
                                   int height, size_t pitch_bytes, size_t image_stride_bytes,
                                   float* d_flow, const ofb_farneback_params* params);
 
+/* ---- spatially tiled mode: ONE frame pair split into row strips over the GPUs of a node -------
+ * (BASELINE.json config 5: 7680x4320 over 8 B200.)  One handle per GPU ("rank"), all created with the
+ * same max_width/max_height.  Every rank holds the two source frames and computes the rows it owns at
+ * every pyramid level; rows owned by neighbours are read through NVLink peer pointers inside the
+ * kernels, and a flag barrier in peer memory orders the stages.  Set-up:
+ *   ofb_tiled_init(h, rank, world)                        on every rank
+ *   ofb_tiled_export(h, blob)  -> all-gather the blobs -> ofb_tiled_import(h, all_blobs)   (one process per GPU,
+ *       CUDA IPC), or ofb_tiled_import_local(h, handles) when all handles live in one process. */
+#define OFB_TILED_EXPORT_BYTES 320 /* 5 CUDA IPC memory handles */
+int ofb_tiled_init(ofb_handle* h, int rank, int world);
+int ofb_tiled_export(ofb_handle* h, void* blob /* OFB_TILED_EXPORT_BYTES */);
+int ofb_tiled_import(ofb_handle* h, const void* all_blobs /* world * OFB_TILED_EXPORT_BYTES, rank order */);
+int ofb_tiled_import_local(ofb_handle* h, ofb_handle* const* handles /* world handles, rank order */);
+/* Asynchronous on the handle's stream.  d_prev/d_next: the full uint8 frames on this rank's device;
+ * d_flow: a full-size float32 [height][width][2] buffer of which this rank writes rows
+ * [*row_begin, *row_end) only.  flags must be 0, winsize in [4, 39], poly_n <= 8, iterations >= 1.
+ * All ranks must make the same call; a rank that does not arrive makes the others time out (~2 s),
+ * reported by ofb_tiled_status. */
+int ofb_farneback_tiled_device(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
+                               size_t pitch_bytes, float* d_flow, const ofb_farneback_params* params,
+                               int* row_begin, int* row_end);
+/* Synchronises the stream; *timed_out = 1 if a cross-GPU barrier gave up waiting since the last call. */
+int ofb_tiled_status(ofb_handle* h, int* timed_out);
+/* Test path for fewer GPUs than ranks: all `world` handles live in this process on ONE device (set up
+ * with ofb_tiled_init + ofb_tiled_import_local); runs the stages of all ranks in order, synchronously,
+ * without the barrier kernel, and fills the whole of d_flow. */
+int ofb_farneback_tiled_emulated(ofb_handle* const* handles, int world, const uint8_t* d_prev, const uint8_t* d_next,
+                                 int width, int height, size_t pitch_bytes, float* d_flow,
+                                 const ofb_farneback_params* params);
+
 /* Number of kernel launches this handle has enqueued since creation (bench evidence). */
 uint64_t ofb_launch_count(const ofb_handle* h);
 

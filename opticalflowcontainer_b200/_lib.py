@@ -59,6 +59,16 @@ _SIGNATURES = {
     "ofb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ofb_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "ofb_timing_read_samples": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]),
+    "ofb_tiled_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ofb_tiled_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ofb_tiled_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ofb_tiled_import_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ofb_farneback_tiled_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
+                                             C.c_void_p, C.POINTER(FarnebackParams), C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int)]),
+    "ofb_tiled_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "ofb_farneback_tiled_emulated": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_size_t, C.c_void_p, C.POINTER(FarnebackParams)]),
     "ofb_flow_u_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "ofb_good_features": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.POINTER(GfttParams),
                                     C.c_void_p, C.POINTER(C.c_int)]),
@@ -68,6 +78,8 @@ _SIGNATURES = {
     "ofb_pyrlk": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                             C.c_void_p, C.c_void_p, C.POINTER(LKParams)]),
 }
+
+TILED_EXPORT_BYTES = 320   # OFB_TILED_EXPORT_BYTES
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

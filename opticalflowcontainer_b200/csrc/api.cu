@@ -166,6 +166,18 @@ int ofb_destroy(ofb_handle* h) {
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->tile.imported && !h->tile.same_process) {
+    for (int r = 0; r < h->tile.world; r++) {
+      if (r == h->tile.rank) continue;
+      cudaIpcCloseMemHandle(h->tile.peer_RA[r]);
+      cudaIpcCloseMemHandle(h->tile.peer_RB[r]);
+      cudaIpcCloseMemHandle(h->tile.peer_flow[0][r]);
+      cudaIpcCloseMemHandle(h->tile.peer_flow[1][r]);
+      cudaIpcCloseMemHandle(h->tile.peer_flags[r]);
+    }
+  }
+  cudaFree(h->tile.d_flags);
+  cudaFree(h->tile.d_err);
   for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -280,6 +292,144 @@ int ofb_farneback_device(ofb_handle* h, int n, const uint8_t* d_prev, const uint
   }
   return farneback_run(h, n, false, d_prev, d_next, width, height, pitch_bytes, image_stride_bytes, d_flow, init,
                        params);
+}
+
+// ------------------------------------------------------------------------------------------
+// Spatially tiled mode
+// ------------------------------------------------------------------------------------------
+int ofb_tiled_init(ofb_handle* h, int rank, int world) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (world < 1 || world > kMaxTileRanks || rank < 0 || rank >= world)
+    return set_error(h, OFB_ERR_INVALID_ARG, "tiled mode: need 0 <= rank < world <= %d", kMaxTileRanks);
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  if (!h->tile.d_flags) {
+    OFB_CUDA(h, cudaMalloc(&h->tile.d_flags, kMaxTileRanks * sizeof(unsigned)));
+    OFB_CUDA(h, cudaMalloc(&h->tile.d_err, sizeof(int)));
+  }
+  OFB_CUDA(h, cudaMemset(h->tile.d_flags, 0, kMaxTileRanks * sizeof(unsigned)));
+  OFB_CUDA(h, cudaMemset(h->tile.d_err, 0, sizeof(int)));
+  h->tile.rank = rank;
+  h->tile.world = world;
+  h->tile.epoch = 0;
+  h->tile.imported = false;
+  return OFB_OK;
+}
+
+int ofb_tiled_export(ofb_handle* h, void* blob) {
+  if (!h || !blob) return OFB_ERR_INVALID_ARG;
+  if (!h->tile.d_flags) return set_error(h, OFB_ERR_INVALID_ARG, "ofb_tiled_init first");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  static_assert(5 * sizeof(cudaIpcMemHandle_t) == OFB_TILED_EXPORT_BYTES, "export blob size");
+  cudaIpcMemHandle_t* out = reinterpret_cast<cudaIpcMemHandle_t*>(blob);
+  OFB_CUDA(h, cudaIpcGetMemHandle(&out[0], h->d_RA));
+  OFB_CUDA(h, cudaIpcGetMemHandle(&out[1], h->d_RB));
+  OFB_CUDA(h, cudaIpcGetMemHandle(&out[2], h->d_flow[0]));
+  OFB_CUDA(h, cudaIpcGetMemHandle(&out[3], h->d_flow[1]));
+  OFB_CUDA(h, cudaIpcGetMemHandle(&out[4], h->tile.d_flags));
+  return OFB_OK;
+}
+
+static void tiled_set_self(ofb_handle* h) {
+  const int r = h->tile.rank;
+  h->tile.peer_RA[r] = h->d_RA;
+  h->tile.peer_RB[r] = h->d_RB;
+  h->tile.peer_flow[0][r] = h->d_flow[0];
+  h->tile.peer_flow[1][r] = h->d_flow[1];
+  h->tile.peer_flags[r] = h->tile.d_flags;
+}
+
+int ofb_tiled_import(ofb_handle* h, const void* all_blobs) {
+  if (!h || !all_blobs) return OFB_ERR_INVALID_ARG;
+  if (!h->tile.d_flags) return set_error(h, OFB_ERR_INVALID_ARG, "ofb_tiled_init first");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  const cudaIpcMemHandle_t* in = reinterpret_cast<const cudaIpcMemHandle_t*>(all_blobs);
+  for (int r = 0; r < h->tile.world; r++) {
+    if (r == h->tile.rank) continue;
+    void* p[5];
+    for (int k = 0; k < 5; k++)
+      OFB_CUDA(h, cudaIpcOpenMemHandle(&p[k], in[r * 5 + k], cudaIpcMemLazyEnablePeerAccess));
+    h->tile.peer_RA[r] = p[0];
+    h->tile.peer_RB[r] = p[1];
+    h->tile.peer_flow[0][r] = p[2];
+    h->tile.peer_flow[1][r] = p[3];
+    h->tile.peer_flags[r] = reinterpret_cast<unsigned*>(p[4]);
+  }
+  tiled_set_self(h);
+  h->tile.imported = true;
+  h->tile.same_process = false;
+  return OFB_OK;
+}
+
+int ofb_tiled_import_local(ofb_handle* h, ofb_handle* const* handles) {
+  if (!h || !handles) return OFB_ERR_INVALID_ARG;
+  if (!h->tile.d_flags) return set_error(h, OFB_ERR_INVALID_ARG, "ofb_tiled_init first");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  for (int r = 0; r < h->tile.world; r++) {
+    ofb_handle* q = handles[r];
+    if (!q || !q->tile.d_flags) return set_error(h, OFB_ERR_INVALID_ARG, "peer %d is not initialised for tiled mode", r);
+    if (q->max_w != h->max_w || q->max_h != h->max_h)
+      return set_error(h, OFB_ERR_INVALID_ARG, "tiled mode needs handles of identical capacity");
+    if (q->device != h->device) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "no peer access %d -> %d: %s", h->device, q->device, cudaGetErrorString(e));
+    }
+    h->tile.peer_RA[r] = q->d_RA;
+    h->tile.peer_RB[r] = q->d_RB;
+    h->tile.peer_flow[0][r] = q->d_flow[0];
+    h->tile.peer_flow[1][r] = q->d_flow[1];
+    h->tile.peer_flags[r] = q->tile.d_flags;
+  }
+  h->tile.imported = true;
+  h->tile.same_process = true;
+  return OFB_OK;
+}
+
+static int validate_tiled(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
+                          size_t pitch_bytes, float* d_flow, const ofb_farneback_params* params) {
+  if (!d_prev || !d_next || !d_flow) return set_error(h, OFB_ERR_INVALID_ARG, "NULL device pointer");
+  int st = validate_farneback(h, 1, width, height, params);
+  if (st) return st;
+  if (pitch_bytes < (size_t)width) return set_error(h, OFB_ERR_INVALID_ARG, "pitch smaller than width");
+  if (!h->tile.imported) return set_error(h, OFB_ERR_INVALID_ARG, "tiled mode is not set up (init/export/import)");
+  return OFB_OK;
+}
+
+int ofb_farneback_tiled_device(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
+                               size_t pitch_bytes, float* d_flow, const ofb_farneback_params* params,
+                               int* row_begin, int* row_end) {
+  if (!h || !row_begin || !row_end) return OFB_ERR_INVALID_ARG;
+  int st = validate_tiled(h, d_prev, d_next, width, height, pitch_bytes, d_flow, params);
+  if (st) return st;
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  return farneback_run_tiled(h, d_prev, d_next, width, height, pitch_bytes, d_flow, params, row_begin, row_end);
+}
+
+int ofb_tiled_status(ofb_handle* h, int* timed_out) {
+  if (!h || !timed_out) return OFB_ERR_INVALID_ARG;
+  if (!h->tile.d_err) return set_error(h, OFB_ERR_INVALID_ARG, "ofb_tiled_init first");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int v = 0;
+  OFB_CUDA(h, cudaMemcpy(&v, h->tile.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (v) OFB_CUDA(h, cudaMemset(h->tile.d_err, 0, sizeof(int)));
+  *timed_out = v;
+  return OFB_OK;
+}
+
+int ofb_farneback_tiled_emulated(ofb_handle* const* handles, int world, const uint8_t* d_prev, const uint8_t* d_next,
+                                 int width, int height, size_t pitch_bytes, float* d_flow,
+                                 const ofb_farneback_params* params) {
+  if (!handles || world < 1 || world > kMaxTileRanks || !handles[0]) return OFB_ERR_INVALID_ARG;
+  for (int r = 0; r < world; r++) {
+    if (!handles[r]) return OFB_ERR_INVALID_ARG;
+    int st = validate_tiled(handles[r], d_prev, d_next, width, height, pitch_bytes, d_flow, params);
+    if (st) return st;
+    if (handles[r]->device != handles[0]->device || handles[r]->tile.world != world || handles[r]->tile.rank != r)
+      return set_error(handles[r], OFB_ERR_INVALID_ARG, "emulated tiled run needs ranks 0..world-1 on one device");
+  }
+  OFB_CUDA(handles[0], cudaSetDevice(handles[0]->device));
+  return farneback_run_tiled_emulated(handles, world, d_prev, d_next, width, height, pitch_bytes, d_flow, params);
 }
 
 int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_frames, int width, int height,

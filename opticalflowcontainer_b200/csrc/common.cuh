@@ -47,6 +47,19 @@ struct LinTab {
   float f;
 };
 
+// Spatially tiled mode (one frame pair split into row strips over the GPUs of a node): every rank
+// holds full-size level buffers but fills only the rows it owns; rows owned by another rank are read
+// from that rank's buffer (same offsets) through NVLink peer pointers.  Level rows are split evenly:
+// rank r owns [r * rpr, min((r+1) * rpr, h)), rpr = ceil(h / world).
+constexpr int kMaxTileRanks = 8;
+struct PeerTab {
+  const float4* RA[kMaxTileRanks];
+  const float* RB[kMaxTileRanks];
+  const float2* flow[kMaxTileRanks];   // the flow buffer the launch reads (ping or pong of every rank)
+  int rpr;                             // rows per rank at the level of the launch
+  int world;
+};
+
 inline int cv_round(double v) { return (int)__builtin_nearbyint(v); }  // round-half-even like cvRound
 
 }  // namespace ofb
@@ -93,6 +106,18 @@ struct ofb_handle {
   int tab_w = 0, tab_h = 0, tab_levels = -1;
   double tab_scale = 0;
   size_t tab_x_off[ofb::kMaxLevels] = {0}, tab_y_off[ofb::kMaxLevels] = {0};
+  // spatially tiled mode (tiled.cuh / ofb_tiled_*)
+  struct Tile {
+    int rank = 0, world = 0;
+    bool imported = false, same_process = false;
+    void* peer_RA[ofb::kMaxTileRanks] = {nullptr};
+    void* peer_RB[ofb::kMaxTileRanks] = {nullptr};
+    void* peer_flow[2][ofb::kMaxTileRanks] = {{nullptr}};
+    unsigned* peer_flags[ofb::kMaxTileRanks] = {nullptr};
+    unsigned* d_flags = nullptr;     // [world] written by the peers
+    int* d_err = nullptr;            // barrier timeout flag
+    unsigned epoch = 0;
+  } tile;
   // last result bookkeeping for ofb_flow_u_stats
   const float* last_flow = nullptr;
   int last_n = 0, last_w = 0, last_h = 0;
@@ -155,6 +180,13 @@ void prepare_blur(int winsize, bool gaussian, BlurCoef* bc);
 int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
                   int width, int height, size_t pitch, size_t image_stride, float* d_flow_out,
                   const float* d_init_flow, const ofb_farneback_params* p);
+
+// Spatially tiled mode (tiled.cuh)
+int farneback_run_tiled(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
+                        size_t pitch, float* d_flow_out, const ofb_farneback_params* p, int* row_begin, int* row_end);
+int farneback_run_tiled_emulated(ofb_handle* const* hs, int world, const uint8_t* d_prev, const uint8_t* d_next,
+                                 int width, int height, size_t pitch, float* d_flow_out,
+                                 const ofb_farneback_params* p);
 
 int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mean, float* out_median);
 

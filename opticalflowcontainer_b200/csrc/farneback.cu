@@ -445,13 +445,18 @@ __global__ void __launch_bounds__(256) k_init_flow_area(const float2* __restrict
 // Driver: the multi-level schedule on the handle's stream (no host sync inside).
 // =====================================================================================
 // k_iter_v launcher.
-template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1>
+template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false>
 static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                 int f1_offset, int m, float reg, cudaStream_t st) {
+                                 int f1_offset, int m, float reg, cudaStream_t st, int y_begin = 0, int y_end = -1,
+                                 const PeerTab* tab = nullptr, int my_rank = 0) {
+  if (y_end < 0) y_end = hh;
+  if (y_end <= y_begin) return cudaSuccess;
+  PeerTab t;
+  if (tab) t = *tab; else memset(&t, 0, sizeof(t));
   const int smem = iter_v_smem_floats<COLS, CH>(m) * (int)sizeof(float);
   static int configured = -1;   // largest dynamic smem configured for this instantiation
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
@@ -459,12 +464,13 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   const int strips = (w + tw - 1) / tw;
   const int slots = MINB * h->num_sms * h->iter_waves;
   const int per = strips * n_pairs;
+  const int rows = y_end - y_begin;
   int segs = per >= slots ? 1 : slots / per;
-  int seg_rows = std::max(16, (hh + segs - 1) / segs);
-  segs = (hh + seg_rows - 1) / seg_rows;
+  int seg_rows = std::max(16, (rows + segs - 1) / segs);
+  segs = (rows + seg_rows - 1) / seg_rows;
   dim3 g(strips * segs, n_pairs);
-  k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP><<<g, COLS + (CH / CLOOP) * COLS / PXT, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m,
-                                                                     reg, seg_rows, strips);
+  k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED><<<g, COLS + (CH / CLOOP) * COLS / PXT, smem, st>>>(
+      h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank);
   return cudaGetLastError();
 }
 
@@ -552,9 +558,9 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       dim3 bv(128, 2), gv((w + 127) / 128, (hh + 1) / 2, frames);
 #define OFB_PYR_LAUNCH(RT)                                                                             \
   do {                                                                                                 \
-    k_pyr_h<RT><<<gh, 128, 0, st>>>(src, width, height, hb, w, 1.0 / ((double)w / width), pyc);        \
+    k_pyr_h<RT><<<gh, 128, 0, st>>>(src, width, height, hb, w, 1.0 / ((double)w / width), pyc, 0, height); \
     OFB_LAUNCH_CHECK(h);                                                                               \
-    k_pyr_v<RT><<<gv, bv, 0, st>>>(hb, height, h->d_img, w, hh, 1.0 / ((double)hh / height), pyc);    \
+    k_pyr_v<RT><<<gv, bv, 0, st>>>(hb, height, h->d_img, w, hh, 1.0 / ((double)hh / height), pyc, 0, hh); \
     OFB_LAUNCH_CHECK(h);                                                                               \
   } while (0)
       if (pyc.r == 1) OFB_PYR_LAUNCH(1);
@@ -577,10 +583,10 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   do {                                                                                                              \
     if (fused_src)                                                                                                  \
       k_polyexp_march<NT, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], h->d_RA, h->d_RB, w, hh,      \
-                                                    seg_rows, strips, pc);                                          \
+                                                    seg_rows, strips, pc, 0, hh);                                   \
     else                                                                                                            \
       k_polyexp_march<NT, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, h->d_RA, h->d_RB, w, hh, seg_rows,     \
-                                                    strips, pc);                                                    \
+                                                    strips, pc, 0, hh);                                             \
   } while (0)
       if (pc.n == 5) OFB_PX_LAUNCH(5); else if (pc.n == 7) OFB_PX_LAUNCH(7); else OFB_PX_LAUNCH(0);
 #undef OFB_PX_LAUNCH
@@ -669,3 +675,5 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
 }
 
 }  // namespace ofb
+
+#include "tiled.cuh"

@@ -40,11 +40,15 @@ constexpr int iter_v_smem_floats(int m) { return (2 * CH + 2 * m + 1) * 5 * COLS
 // The R buffers carry kRowPad spare rows so the predicted corner row stays inside the allocation.
 // RIF = matrix rows a producer thread keeps in flight (1, or CH: the loads of all CH rows of a chunk are
 // issued before the first is consumed).  CLOOP = rows a consumer thread handles per chunk (1, or CH).
-template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1>
+// TILED (spatially tiled mode, one pair): the CTA grid covers only the level rows [y_begin, y_end) this
+// rank owns; R0 / R1 / flow rows owned by other ranks (the 2m halo rows of the blur and whatever the
+// displacement reaches) are read from those ranks' buffers through the NVLink peer pointers in `tab` —
+// the halo exchange is these loads, issued tile by tile inside the kernel that consumes them.
+template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false>
 __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
     k_iter_v(const float4* __restrict__ RA, const float* __restrict__ RB, const float2* __restrict__ flow_in,
              float2* __restrict__ flow_out, int w, int h, int f1_offset, int m_rt, float reg, int seg_rows,
-             int strips) {
+             int strips, int y_begin, int y_end, PeerTab tab, int my_rank) {
   static_assert(PXT == 4 || PXT == 8, "4 or 8 adjacent pixels per consumer thread");
   constexpr int GROUPS = COLS / PXT;
   static_assert(RIF == 1 || RIF == CH, "rows in flight: 1 or the whole chunk");
@@ -64,8 +68,8 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
   const int seg = blockIdx.x / strips;
   const int pair = blockIdx.y;
   const int x_base = strip * tw - m;                 // image x of strip column 0
-  const int y0 = seg * seg_rows;
-  const int y1 = min(y0 + seg_rows, h);              // exclusive
+  const int y0 = y_begin + seg * seg_rows;
+  const int y1 = min(y0 + seg_rows, y_end);          // exclusive
   const int t_first = y0 - m;                        // first matrix row the segment needs
   const int n_chunks = (y1 - y0 + CH - 1) / CH;
 
@@ -104,9 +108,14 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
         L.dx = f.x; L.dy = f.y; L.fx = 0.25f; L.fy = 0.5f; L.inside = true;
       }
 #else
-      um_issue2(L, RA0, RB0, RA1, RB1, f, x, y, yw, uw, uh);
+      if constexpr (TILED) {
+        const int ro = tile_owner(y, tab);           // uniform over the CTA
+        um_issue2_tiled(L, tab.RA[ro], tab.RB[ro], tab, n, my_rank, f, x, y, yw, uw, uh);
+      } else {
+        um_issue2(L, RA0, RB0, RA1, RB1, f, x, y, yw, uw, uh);
+      }
 #endif
-      if (PFD > 0) {
+      if (PFD > 0 && !TILED) {
         static_assert(PFD + 1 <= kRowPad, "prefetch distance exceeds the row padding of the R buffers");
         const unsigned op = (unsigned)clampi(t + PFD, 0, h - 1) * uw + (unsigned)x;
         prefetch_l2(RA0 + op);
@@ -141,7 +150,11 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
         for (int ch = 0; ch < 5; ch++) { Bp[ch] = P[ch]; P[ch] = 0.f; }
       }
     };
-    auto flow_at = [&](int t) { return __ldg(fin + ((unsigned)clampi(t, 0, h - 1) * uw + (unsigned)x)); };
+    auto flow_at = [&](int t) {
+      const int yc = clampi(t, 0, h - 1);
+      const float2* f = TILED ? tab.flow[tile_owner(yc, tab)] : fin;
+      return __ldg(f + ((unsigned)yc * uw + (unsigned)x));
+    };
 
     if constexpr (RIF == 1) {
       float2 fl = flow_at(t_first);

@@ -105,7 +105,8 @@ struct LevelColumn<1> {
 template <int NT, int SRC>
 __global__ void __launch_bounds__(PX_COLS)
     k_polyexp_march(const float* __restrict__ I, FrameSrc src, float k0, float k1, float4* __restrict__ RA,
-                    float* __restrict__ RB, int w, int h, int seg_rows, int strips, PolyCoef pc) {
+                    float* __restrict__ RB, int w, int h, int seg_rows, int strips, PolyCoef pc, int y_begin,
+                    int y_end) {
   constexpr int NMAX = NT > 0 ? NT : PX_MAXN;
   const int n = NT > 0 ? NT : pc.n;
   constexpr int WIN = 2 * NMAX + PX_ROWS;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(PX_COLS)
   const int strip = blockIdx.x % strips, seg = blockIdx.x / strips;
   const int frame = blockIdx.y;
   const int x_base = strip * PX_TW - PX_HALO;
-  const int y0 = seg * seg_rows, y1 = min(y0 + seg_rows, h);
+  const int y0 = y_begin + seg * seg_rows, y1 = min(y0 + seg_rows, y_end);   // rows [y_begin, y_end) of the level
   const int xc = clampi(x_base + tid, 0, w - 1);   // replicate border of PolyExp
   const size_t fbase = (size_t)frame * w * h;
 

@@ -28,10 +28,12 @@ constexpr int PYR_RPT = 16;
 // operands); RT = 0: runtime radius.  The node defaults use r = 1, 4, 9 (ksize 3, 9, 19).
 template <int RT>
 __global__ void __launch_bounds__(128) k_pyr_h(FrameSrc src, int W, int H, float* __restrict__ hb, int w,
-                                               double sx_scale, PyrCoef pc) {
+                                               double sx_scale, PyrCoef pc, int sy_begin, int sy_end) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= w) return;
-  const int y_begin = blockIdx.y * PYR_RPT, y_end = min(y_begin + PYR_RPT, H);
+  // source rows [sy_begin, sy_end) (the whole frame, or what one rank's level rows need)
+  const int y_begin = sy_begin + blockIdx.y * PYR_RPT, y_end = min(y_begin + PYR_RPT, sy_end);
+  if (y_begin >= y_end) return;
   const int r = RT > 0 ? RT : pc.r;
   int sx0;
   float fx;
@@ -99,10 +101,10 @@ __global__ void __launch_bounds__(128) k_pyr_h(FrameSrc src, int W, int H, float
 // four so that four loads are in flight per thread (the rolled loop was latency-bound).
 template <int RT>
 __global__ void __launch_bounds__(256) k_pyr_v(const float* __restrict__ hb, int H, float* __restrict__ out, int w,
-                                               int h, double sy_scale, PyrCoef pc) {
+                                               int h, double sy_scale, PyrCoef pc, int y_begin, int y_end) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= w || y >= h) return;
+  const int y = y_begin + blockIdx.y * blockDim.y + threadIdx.y;   // level rows [y_begin, y_end)
+  if (x >= w || y >= y_end) return;
   const float* col = hb + (size_t)blockIdx.z * H * w + x;
   const int r = RT > 0 ? RT : pc.r;
   int sy0;

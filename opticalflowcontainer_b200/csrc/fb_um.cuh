@@ -52,6 +52,43 @@ __device__ __forceinline__ void um_issue2(UmLoads2& L, const float4* __restrict_
   L.s11 = __ldg(pb + w + 1);
 }
 
+// Tiled variant: R0 and the two corner rows of the R1 gather may live on different ranks.  RA0/RB0 are
+// the (frame-0) bases of the rank that owns row y; the corner rows pick their owner per lane.
+__device__ __forceinline__ int tile_owner(int y, const PeerTab& t) { return min(y / t.rpr, t.world - 1); }
+
+__device__ __forceinline__ void um_issue2_tiled(UmLoads2& L, const float4* __restrict__ RA0, const float* __restrict__ RB0,
+                                                const PeerTab& t, size_t f1_elems, int my_rank, float2 fl, int x, int y,
+                                                unsigned yw, unsigned w, unsigned h) {
+  const unsigned o = yw + (unsigned)x;
+  L.a0 = __ldg(RA0 + o);
+  L.b0 = __ldg(RB0 + o);
+  L.dx = fl.x;
+  L.dy = fl.y;
+  const float fx = (float)x + fl.x, fy = (float)y + fl.y;
+  const int ix = __float2int_rd(fx), iy = __float2int_rd(fy);
+  L.fx = fx - (float)ix;
+  L.fy = fy - (float)iy;
+  L.inside = (unsigned)ix < w - 1u && (unsigned)iy < h - 1u;
+  const int ry = L.inside ? iy : 0;
+  const unsigned g = L.inside ? (unsigned)iy * w + (unsigned)ix : 0u;
+  // owners of the two corner rows: this rank in the common case, one division otherwise
+  const int lo = my_rank * t.rpr, hi = lo + t.rpr;
+  const int r_top = (ry >= lo && ry < hi) ? my_rank : tile_owner(ry, t);
+  const int r_bot = (ry + 1 >= lo && ry + 1 < hi) ? my_rank : tile_owner(ry + 1, t);
+  const float4* pa = t.RA[r_top] + f1_elems + g;
+  const float* pb = t.RB[r_top] + f1_elems + g;
+  const float4* qa = t.RA[r_bot] + f1_elems + g + w;
+  const float* qb = t.RB[r_bot] + f1_elems + g + w;
+  L.q00 = __ldg(pa);
+  L.q01 = __ldg(pa + 1);
+  L.q10 = __ldg(qa);
+  L.q11 = __ldg(qa + 1);
+  L.s00 = __ldg(pb);
+  L.s01 = __ldg(pb + 1);
+  L.s10 = __ldg(qb);
+  L.s11 = __ldg(qb + 1);
+}
+
 // border: this pixel lies within 5 px of the level border (attenuation table applies)
 __device__ __forceinline__ M5 um_finish2(const UmLoads2& L, bool border, int x, int y, int w, int h) {
   const float fx = L.fx, fy = L.fy;
