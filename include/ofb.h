@@ -159,6 +159,9 @@ int ofb_tiled_import_local(ofb_handle* h, ofb_handle* const* handles /* world ha
 int ofb_farneback_tiled_device(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
                                size_t pitch_bytes, float* d_flow, const ofb_farneback_params* params,
                                int* row_begin, int* row_end);
+/* Enqueues one cross-GPU flag barrier on the handle's stream (every rank must call it; real multi-GPU
+ * set-ups only — never with several ranks on one device). */
+int ofb_tiled_barrier(ofb_handle* h);
 /* Synchronises the stream; *timed_out = 1 if a cross-GPU barrier gave up waiting since the last call. */
 int ofb_tiled_status(ofb_handle* h, int* timed_out);
 /* Test path for fewer GPUs than ranks: all `world` handles live in this process on ONE device (set up

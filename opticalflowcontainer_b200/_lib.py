@@ -66,6 +66,7 @@ _SIGNATURES = {
     "ofb_farneback_tiled_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
                                              C.c_void_p, C.POINTER(FarnebackParams), C.POINTER(C.c_int),
                                              C.POINTER(C.c_int)]),
+    "ofb_tiled_barrier": (C.c_int, [C.c_void_p]),
     "ofb_tiled_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "ofb_farneback_tiled_emulated": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                C.c_size_t, C.c_void_p, C.POINTER(FarnebackParams)]),

@@ -405,6 +405,13 @@ int ofb_farneback_tiled_device(ofb_handle* h, const uint8_t* d_prev, const uint8
   return farneback_run_tiled(h, d_prev, d_next, width, height, pitch_bytes, d_flow, params, row_begin, row_end);
 }
 
+int ofb_tiled_barrier(ofb_handle* h) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!h->tile.imported) return set_error(h, OFB_ERR_INVALID_ARG, "tiled mode is not set up (init/export/import)");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  return tiled_barrier_public(h);
+}
+
 int ofb_tiled_status(ofb_handle* h, int* timed_out) {
   if (!h || !timed_out) return OFB_ERR_INVALID_ARG;
   if (!h->tile.d_err) return set_error(h, OFB_ERR_INVALID_ARG, "ofb_tiled_init first");

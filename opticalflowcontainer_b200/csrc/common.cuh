@@ -58,6 +58,9 @@ struct PeerTab {
   const float2* flow[kMaxTileRanks];   // the flow buffer the launch reads (ping or pong of every rank)
   int rpr;                             // rows per rank at the level of the launch
   int world;
+  // rows [r_lo, r_hi) of R and [f_lo, f_hi) of the flow are present in THIS rank's buffers (own rows
+  // plus the halo rows pulled from the neighbours before the launch); other rows are read remotely
+  int r_lo, r_hi, f_lo, f_hi;
 };
 
 inline int cv_round(double v) { return (int)__builtin_nearbyint(v); }  // round-half-even like cvRound
@@ -117,6 +120,7 @@ struct ofb_handle {
     unsigned* d_flags = nullptr;     // [world] written by the peers
     int* d_err = nullptr;            // barrier timeout flag
     unsigned epoch = 0;
+    int r_lo = 0, r_hi = 0;          // R rows present locally at the current level (own + pulled halo)
   } tile;
   // last result bookkeeping for ofb_flow_u_stats
   const float* last_flow = nullptr;
@@ -184,6 +188,7 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
 // Spatially tiled mode (tiled.cuh)
 int farneback_run_tiled(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
                         size_t pitch, float* d_flow_out, const ofb_farneback_params* p, int* row_begin, int* row_end);
+int tiled_barrier_public(ofb_handle* h);
 int farneback_run_tiled_emulated(ofb_handle* const* hs, int world, const uint8_t* d_prev, const uint8_t* d_next,
                                  int width, int height, size_t pitch, float* d_flow_out,
                                  const ofb_farneback_params* p);

@@ -454,11 +454,14 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   PeerTab t;
   if (tab) t = *tab; else memset(&t, 0, sizeof(t));
   const int smem = iter_v_smem_floats<COLS, CH>(m) * (int)sizeof(float);
-  static int configured = -1;   // largest dynamic smem configured for this instantiation
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  // largest dynamic smem configured for this instantiation, per device (function attributes are per device)
+  static int configured[64] = {0};
+  const int dev = h->device & 63;
+  if (smem > configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[dev] = smem;
   }
   const int tw = COLS - 2 * m;
   const int strips = (w + tw - 1) / tw;

@@ -109,13 +109,13 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
       }
 #else
       if constexpr (TILED) {
-        const int ro = tile_owner(y, tab);           // uniform over the CTA
+        const int ro = (y >= tab.r_lo && y < tab.r_hi) ? my_rank : tile_owner(y, tab);   // uniform over the CTA
         um_issue2_tiled(L, tab.RA[ro], tab.RB[ro], tab, n, my_rank, f, x, y, yw, uw, uh);
       } else {
         um_issue2(L, RA0, RB0, RA1, RB1, f, x, y, yw, uw, uh);
       }
 #endif
-      if (PFD > 0 && !TILED) {
+      if (PFD > 0) {   // (tiled mode: RA0.. are this rank's own buffers — rows of a neighbour are simply not prefetched usefully)
         static_assert(PFD + 1 <= kRowPad, "prefetch distance exceeds the row padding of the R buffers");
         const unsigned op = (unsigned)clampi(t + PFD, 0, h - 1) * uw + (unsigned)x;
         prefetch_l2(RA0 + op);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
     };
     auto flow_at = [&](int t) {
       const int yc = clampi(t, 0, h - 1);
-      const float2* f = TILED ? tab.flow[tile_owner(yc, tab)] : fin;
+      const float2* f = TILED ? tab.flow[(yc >= tab.f_lo && yc < tab.f_hi) ? my_rank : tile_owner(yc, tab)] : fin;
       return __ldg(f + ((unsigned)yc * uw + (unsigned)x));
     };
 

@@ -69,12 +69,15 @@ __device__ __forceinline__ void um_issue2_tiled(UmLoads2& L, const float4* __res
   L.fx = fx - (float)ix;
   L.fy = fy - (float)iy;
   L.inside = (unsigned)ix < w - 1u && (unsigned)iy < h - 1u;
-  const int ry = L.inside ? iy : 0;
-  const unsigned g = L.inside ? (unsigned)iy * w + (unsigned)ix : 0u;
-  // owners of the two corner rows: this rank in the common case, one division otherwise
-  const int lo = my_rank * t.rpr, hi = lo + t.rpr;
-  const int r_top = (ry >= lo && ry < hi) ? my_rank : tile_owner(ry, t);
-  const int r_bot = (ry + 1 >= lo && ry + 1 < hi) ? my_rank : tile_owner(ry + 1, t);
+  // outside pixels gather (and discard) from the start of their OWN row: always present locally —
+  // row 0, as in the untiled kernel, would be a remote NVLink load on every rank but the first, and the
+  // clamped columns of the last strip are all "outside": their CTAs set the kernel time (measured 1.6x)
+  const int ry = L.inside ? iy : y;
+  const unsigned g = L.inside ? (unsigned)iy * w + (unsigned)ix : yw;
+  // where the two corner rows live: in this rank's buffer (own rows + pulled halo) in the common case,
+  // one division and a remote NVLink load otherwise (displacement beyond the halo)
+  const int r_top = (ry >= t.r_lo && ry < t.r_hi) ? my_rank : tile_owner(ry, t);
+  const int r_bot = (ry + 1 >= t.r_lo && ry + 1 < t.r_hi) ? my_rank : tile_owner(ry + 1, t);
   const float4* pa = t.RA[r_top] + f1_elems + g;
   const float* pb = t.RB[r_top] + f1_elems + g;
   const float4* qa = t.RA[r_bot] + f1_elems + g + w;

@@ -23,6 +23,8 @@
 
 namespace ofb {
 
+constexpr int kTileGatherMargin = 24;   // rows of R1 pulled beyond the blur halo (larger displacements read remotely)
+
 struct PeerFlags {
   unsigned* p[kMaxTileRanks];
 };
@@ -44,6 +46,27 @@ __global__ void k_tile_barrier(volatile unsigned* my_flags, PeerFlags peers, int
     }
   }
   __threadfence_system();
+}
+
+// Halo pull: copies the level rows [lo, yb) and [ye, hi) of a row-major buffer from their owners into this
+// rank's buffer (same offsets), 16 bytes per thread, so that the compute kernel that follows finds the
+// blur halo (and a margin for the displacement) locally.  One bulk NVLink transfer per stage instead of
+// a remote round trip per halo row inside the marching producers (measured: the rank below a boundary
+// ran its iteration kernels 44 % slower without it).
+struct PullSrc {
+  const uint4* p[kMaxTileRanks];
+};
+__global__ void __launch_bounds__(256) k_tile_pull(uint4* __restrict__ dst, PullSrc src, int rpr, int world,
+                                                   int row_vec, int lo, int yb, int ye, int hi, size_t frame_vec) {
+  // grid.y enumerates halo rows: first the rows above [lo, yb), then the rows below [ye, hi)
+  int r = lo + blockIdx.y;
+  if (r >= yb) r = ye + (r - yb);
+  if (r >= hi) return;
+  const int owner = min(r / rpr, world - 1);
+  const size_t off = (size_t)blockIdx.z * frame_vec + (size_t)r * row_vec;
+  const uint4* s = src.p[owner] + off;
+  uint4* d = dst + off;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_vec; i += gridDim.x * blockDim.x) d[i] = s[i];
 }
 
 // Inter-level flow upsample of the own rows [y_begin, y_end); the coarse rows come from their owners.
@@ -94,6 +117,9 @@ static inline void tile_rows(int hh, int world, int rank, int* rpr, int* yb, int
   *ye = std::min(*yb + *rpr, hh);
 }
 
+static int tiled_pull(ofb_handle* h, void* dst, void* const* peers, int w, int hh, int elem_bytes, int frames,
+                      int halo, int* lo_out, int* hi_out);
+
 // One stage of one rank.  kind 0 = flow init / upsample + pyramid + PolyExp of level li; kind 1 = iteration `it`.
 static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int it) {
   const int world = h->tile.world, rank = h->tile.rank;
@@ -110,6 +136,7 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
 
   if (kind == 0) {
     // ---- initial flow of the level (own rows)
+    TB(OFB_STAGE_FLOW_INIT);
     if (ye > yb) {
       if (li == 0) {
         OFB_CUDA(h, cudaMemsetAsync(cur + (size_t)yb * w, 0, (size_t)(ye - yb) * w * sizeof(float2), st));
@@ -128,6 +155,7 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
         OFB_LAUNCH_CHECK(h);
       }
     }
+    TE();
     if (ye <= yb) return OFB_OK;
     // ---- pyramid + PolyExp of the own rows (local)
     PyrCoef pyc;
@@ -149,11 +177,22 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
       float* hb = reinterpret_cast<float*>(h->d_MA);
       dim3 gh((w + 127) / 128, (se - sb + PYR_RPT - 1) / PYR_RPT, frames);
       dim3 bv(128, 2), gv((w + 127) / 128, (le - lb + 1) / 2, frames);
-      k_pyr_h<0><<<gh, 128, 0, st>>>(src, pl.width, pl.height, hb, w, 1.0 / ((double)w / pl.width), pyc, sb, se);
-      OFB_LAUNCH_CHECK(h);
-      k_pyr_v<0><<<gv, bv, 0, st>>>(hb, pl.height, h->d_img, w, hh, sy, pyc, lb, le);
-      OFB_LAUNCH_CHECK(h);
+      TB(OFB_STAGE_PYRAMID);
+#define OFB_PYR_LAUNCH(RT)                                                                                        \
+  do {                                                                                                            \
+    k_pyr_h<RT><<<gh, 128, 0, st>>>(src, pl.width, pl.height, hb, w, 1.0 / ((double)w / pl.width), pyc, sb, se); \
+    OFB_LAUNCH_CHECK(h);                                                                                          \
+    k_pyr_v<RT><<<gv, bv, 0, st>>>(hb, pl.height, h->d_img, w, hh, sy, pyc, lb, le);                              \
+    OFB_LAUNCH_CHECK(h);                                                                                          \
+  } while (0)
+      if (pyc.r == 1) OFB_PYR_LAUNCH(1);
+      else if (pyc.r == 4) OFB_PYR_LAUNCH(4);
+      else if (pyc.r == 9) OFB_PYR_LAUNCH(9);
+      else OFB_PYR_LAUNCH(0);
+#undef OFB_PYR_LAUNCH
+      TE();
     }
+    TB(OFB_STAGE_POLYEXP);
     {
       const int strips = (w + PX_TW - 1) / PX_TW;
       const int per = strips * frames;
@@ -179,6 +218,7 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
       }
       OFB_LAUNCH_CHECK(h);
     }
+    TE();
     return OFB_OK;
   }
 
@@ -198,14 +238,63 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
   }
   t.rpr = rpr;
   t.world = world;
+  // halo pulls (the barrier before this stage guarantees the neighbours' rows are final)
+  TB(OFB_STAGE_OTHER);
+  {
+    int st2;
+    const int halo_f = pl.bc.m + 2;                 // blur halo + the row the producers prefetch
+    const int halo_r = pl.bc.m + kTileGatherMargin;  // blur halo + margin for the displacement of the gather
+    if ((st2 = tiled_pull(h, h->d_flow[fin_idx], h->tile.peer_flow[fin_idx], w, hh, 8, 1, halo_f, &t.f_lo, &t.f_hi))) return st2;
+    if (it == 0) {
+      int a, b;
+      if ((st2 = tiled_pull(h, h->d_RA, h->tile.peer_RA, w, hh, 16, 2, halo_r, &t.r_lo, &t.r_hi))) return st2;
+      if ((st2 = tiled_pull(h, h->d_RB, h->tile.peer_RB, w, hh, 4, 2, halo_r, &a, &b))) return st2;
+      t.r_lo = std::max(t.r_lo, a);                 // both R arrays must be local for a row to count as local
+      t.r_hi = std::min(t.r_hi, b);
+      h->tile.r_lo = t.r_lo;
+      h->tile.r_hi = t.r_hi;
+    } else {
+      t.r_lo = h->tile.r_lo;
+      t.r_hi = h->tile.r_hi;
+    }
+  }
+  TE();
   const float reg = (float)(1e-3 / ((double)pl.bc.scale * (double)pl.bc.scale));
   cudaError_t e;
+  TB(OFB_STAGE_ITERATION);
   if (pl.bc.m == 7)
-    e = launch_iter_v<7, 256, 2, 2, 0, 4, 1, 1, true>(h, fin, fout, w, hh, 1, 1, pl.bc.m, reg, st, yb, ye, &t, rank);
+    e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, true>(h, fin, fout, w, hh, 1, 1, pl.bc.m, reg, st, yb, ye, &t, rank);
   else
     e = launch_iter_v<0, 128, 4, 1, 0, 4, 1, 1, true>(h, fin, fout, w, hh, 1, 1, pl.bc.m, reg, st, yb, ye, &t, rank);
   if (e != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "tiled k_iter_v launch failed: %s", cudaGetErrorString(e));
   h->launches++;
+  TE();
+  return OFB_OK;
+}
+
+// Pull halo rows [yb - halo, yb) and [ye, ye + halo) of a buffer with `elem_bytes` per pixel and `frames`
+// frames of hh x w pixels.  Rows must be a multiple of 16 bytes (else the halo stays remote: returns 0 rows).
+static int tiled_pull(ofb_handle* h, void* dst, void* const* peers, int w, int hh, int elem_bytes, int frames,
+                      int halo, int* lo_out, int* hi_out) {
+  const int world = h->tile.world, rank = h->tile.rank;
+  int rpr, yb, ye;
+  tile_rows(hh, world, rank, &rpr, &yb, &ye);
+  *lo_out = yb;
+  *hi_out = ye;
+  const size_t row_bytes = (size_t)w * elem_bytes;
+  if (world == 1 || ye <= yb || (row_bytes & 15) || (((size_t)hh * row_bytes) & 15)) return OFB_OK;
+  const int lo = std::max(yb - halo, 0), hi = std::min(ye + halo, hh);
+  const int nrows = (yb - lo) + (hi - ye);
+  if (nrows <= 0) return OFB_OK;
+  PullSrc ps;
+  for (int r = 0; r < kMaxTileRanks; r++) ps.p[r] = r < world ? (const uint4*)peers[r] : nullptr;
+  const int row_vec = (int)(row_bytes / 16);
+  dim3 g(std::min((row_vec + 255) / 256, 8), nrows, frames);
+  k_tile_pull<<<g, 256, 0, h->stream>>>((uint4*)dst, ps, rpr, world, row_vec, lo, yb, ye, hi,
+                                        (size_t)hh * row_bytes / 16);
+  OFB_LAUNCH_CHECK(h);
+  *lo_out = lo;
+  *hi_out = hi;
   return OFB_OK;
 }
 
@@ -214,9 +303,11 @@ static int tiled_barrier(ofb_handle* h) {
   for (int r = 0; r < kMaxTileRanks; r++) pf.p[r] = r < h->tile.world ? h->tile.peer_flags[r] : nullptr;
   h->tile.epoch++;
   // ~2 s at 1.9 GHz: a rank that died must not hang the others (and the GPU) forever
+  TB(OFB_STAGE_OTHER);
   k_tile_barrier<<<1, 32, 0, h->stream>>>(h->tile.d_flags, pf, h->tile.rank, h->tile.world, h->tile.epoch,
                                           h->tile.d_err, 4000000000LL);
   OFB_LAUNCH_CHECK(h);
+  TE();
   return OFB_OK;
 }
 
@@ -246,6 +337,8 @@ static int tiled_make_plan(ofb_handle* h, TiledPlan* pl, const uint8_t* d_prev, 
   pl->p = p;
   return OFB_OK;
 }
+
+int tiled_barrier_public(ofb_handle* h) { return tiled_barrier(h); }
 
 // Real multi-GPU run of this rank: stages with the peer-memory flag barrier in between.
 int farneback_run_tiled(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
@@ -292,13 +385,17 @@ int farneback_run_tiled_emulated(ofb_handle* const* hs, int world, const uint8_t
   int st = sync_all();
   if (st) return st;
   for (int li = 0; li < pls[0].n_levels; li++) {
-    for (int r = 0; r < world; r++)
+    // (each rank's stage runs alone: the streams are synchronised after every rank, so per-rank stage
+    //  timers are clean and no two ranks' kernels share the device)
+    for (int r = 0; r < world; r++) {
       if ((st = tiled_stage(hs[r], pls[r], li, 0, 0))) return st;
-    if ((st = sync_all())) return st;
-    for (int it = 0; it < p->iterations; it++) {
-      for (int r = 0; r < world; r++)
-        if ((st = tiled_stage(hs[r], pls[r], li, 1, it))) return st;
       if ((st = sync_all())) return st;
+    }
+    for (int it = 0; it < p->iterations; it++) {
+      for (int r = 0; r < world; r++) {
+        if ((st = tiled_stage(hs[r], pls[r], li, 1, it))) return st;
+        if ((st = sync_all())) return st;
+      }
     }
   }
   return OFB_OK;

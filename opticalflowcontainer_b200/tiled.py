@@ -75,6 +75,12 @@ def farneback_tiled_device(engine: FlowEngine, d_prev: int, d_next: int, width: 
     return b.value, e.value
 
 
+def tiled_barrier(engine: FlowEngine) -> None:
+    """Enqueue one cross-GPU flag barrier on the engine's stream (all ranks must call it)."""
+    lib = _lib.load()
+    _lib.check(lib.ofb_tiled_barrier(engine._h), engine._h)
+
+
 def tiled_status(engine: FlowEngine) -> bool:
     """Synchronise; True if a cross-GPU barrier timed out since the last call."""
     lib = _lib.load()
