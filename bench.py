@@ -152,6 +152,86 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ sparse path (config 4)
+def run_lk(args, rank, local_rank, world):
+    """BASELINE.json config 4: Shi-Tomasi (2000 corners) + pyramidal LK on 1080p camera streams, 8 streams
+    sharded over the ranks.  A step = one frame of every stream of this rank through the host-buffer API
+    (upload, corners, track, download).  Extra line, not the headline metric."""
+    import torch
+    import torch.distributed as dist
+
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from opticalflowcontainer_b200 import build as ofb_build
+    if rank == 0:
+        ofb_build.build()
+    if world > 1:
+        dist.barrier()
+    import opticalflowcontainer_b200 as ofb
+    from opticalflowcontainer_b200 import sharding
+    from oracle import synth
+
+    streams = sharding.shard_indices(8, rank, world)
+    eng = ofb.FlowEngine(W_, H_, 1, local_rank)
+    pairs = [synth.synth_pair(H_, W_, 300 + s, (3.3 + 0.4 * s, -2.1 + 0.3 * s)) for s in streams]
+
+    def step():
+        n_pts = 0
+        for a, b in pairs:
+            pts = eng.good_features(a, 2000, 0.01, 7, 3)
+            if pts is None or len(pts) == 0:
+                continue
+            nxt, st, err = eng.pyrlk(a, b, pts, None, (21, 21), 3, (3, 30, 0.01))
+            n_pts += int(st.sum())
+        return n_pts
+
+    for _ in range(max(args.warmup, 1)):
+        tracked = step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    frames = torch.tensor([len(pairs) * args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(frames, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        import cv2
+        cv2.setNumThreads(0)
+        a, b = pairs[0]
+        t1 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            p = cv2.goodFeaturesToTrack(a, 2000, 0.01, 7, blockSize=3)
+            cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=3,
+                                     criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01))
+        cpu_ms = (time.perf_counter() - t1) / reps * 1e3
+        value = float(frames.item()) / float(tt.item())
+        line = {"metric": "shi_tomasi_pyrlk_1080p_2000pt_frames_per_s", "value": value, "unit": "frames/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(tt.item()) / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
+                "config": {"workload": "goodFeaturesToTrack(2000, 0.01, 7) + calcOpticalFlowPyrLK(21x21, maxLevel 3, (30, 0.01)) "
+                                       "on 1920x1080, 8 camera streams", "streams_this_rank": len(pairs),
+                           "tracked_points_last_step_rank0": tracked,
+                           "api": "host buffers in and out (ofb_good_features + ofb_pyrlk), synchronous"},
+                "cpu_baseline": {"value": 1e3 / cpu_ms, "unit": "frames/s", "cores": cv2.getNumThreads(), "kind": "reference",
+                                 "sample": "cv2 %s goodFeaturesToTrack + calcOpticalFlowPyrLK, %d frames of stream 0, "
+                                           "default cv2 threads (%.1f ms per frame)" % (cv2.__version__, reps, cpu_ms)},
+                "gpu_launches": int(eng.launch_count)}
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ tiled mode (config 5)
 def run_tiled(args, rank, local_rank, world):
     """One frame pair spatially tiled over the N ranks (BASELINE.json config 5: 7680x4320 over 8 B200).
@@ -493,7 +573,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frame pairs per step per GPU")
-    ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence", "tiled"])
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence", "tiled", "lk"])
     ap.add_argument("--tile-size", default="8k", choices=["8k", "4k", "1080p"], help="--mode tiled: frame size")
     ap.add_argument("--no-tiled-check", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
@@ -510,6 +590,8 @@ def main():
         run_reference(args, rank, world)
     elif args.mode == "tiled":
         run_tiled(args, rank, local_rank, world)
+    elif args.mode == "lk":
+        run_lk(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -202,6 +202,16 @@ int ofb_timing_read_samples(ofb_handle* h, int stage, double* ms_out, int capaci
  * out_mean / out_median: n values (u component); either may be NULL. */
 int ofb_flow_u_stats(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median);
 
+/* ---- frame ingest (the step in front of the flow call: lfn3_sub_node.py:148-159) --------------
+ * cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) / COLOR_RGB2GRAY on an interleaved 8-bit 3-channel frame
+ * (sensor_msgs/Image bgr8 / rgb8 with row `step`), bit-exact with cv2's 15-bit fixed-point formula.
+ * rgb_order: 0 = BGR (cv2 / bgr8), 1 = RGB (rgb8).  Host variant is synchronous; stride 0 = packed. */
+int ofb_cvt_gray(ofb_handle* h, const uint8_t* src, int width, int height, size_t stride_bytes, int rgb_order,
+                 uint8_t* dst, size_t dst_stride_bytes);
+/* Device-resident, asynchronous on the handle's stream. */
+int ofb_cvt_gray_device(ofb_handle* h, const uint8_t* d_src, int width, int height, size_t src_pitch_bytes,
+                        int rgb_order, uint8_t* d_dst, size_t dst_pitch_bytes);
+
 /* ---- sparse path: replaces cv2.goodFeaturesToTrack + cv2.calcOpticalFlowPyrLK -- */
 
 /* Shi-Tomasi corners of a uint8 image (host buffer).  corners_xy: capacity

@@ -71,6 +71,9 @@ _SIGNATURES = {
     "ofb_farneback_tiled_emulated": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                C.c_size_t, C.c_void_p, C.POINTER(FarnebackParams)]),
     "ofb_flow_u_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "ofb_cvt_gray": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),
+    "ofb_cvt_gray_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p,
+                                      C.c_size_t]),
     "ofb_good_features": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.POINTER(GfttParams),
                                     C.c_void_p, C.POINTER(C.c_int)]),
     "ofb_corner_min_eigenval": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p]),

@@ -200,6 +200,22 @@ class FlowEngine:
         return (list(om) if mean else None), (list(od) if median else None)
 
     # -- sparse
+    def cvt_gray(self, frame, rgb: bool = False) -> np.ndarray:
+        """cv2.cvtColor(frame, COLOR_BGR2GRAY) (or RGB2GRAY with ``rgb=True``) of a uint8 [H,W,3] frame on
+        the device, bit-exact with cv2 (the ingest step of the nodes: lfn3_sub_node.py:148-159)."""
+        frame = np.asarray(frame)
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+            raise OfbError(1, "cvt_gray needs a uint8 [H,W,3] frame")
+        if frame.strides[2] != 1 or frame.strides[1] != 3:
+            frame = np.ascontiguousarray(frame)
+        hgt, wid = frame.shape[:2]
+        out = np.empty((hgt, wid), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_cvt_gray(self._h, frame.ctypes.data, wid, hgt, frame.strides[0], 1 if rgb else 0,
+                                        out.ctypes.data, 0)
+            _lib.check(st, self._h)
+        return out
+
     def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3) -> np.ndarray:
         image = _u8_image(image, "image")
         hgt, wid = image.shape

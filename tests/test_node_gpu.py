@@ -94,3 +94,18 @@ def test_junction_mask_matches_reference_logic():
         if 0 <= x < 160 and 0 <= y < 120:
             ref[max(0, y - 5):min(120, y + 6), max(0, x - 5):min(160, x + 6)] = True
     assert np.array_equal(m, ref)
+
+
+def test_cvt_gray_bit_exact(engine_factory):
+    """Frame ingest: BGR/RGB -> gray on the device equals cv2.cvtColor bit for bit,
+    including odd widths and padded rows (sensor_msgs/Image `step`)."""
+    import cv2
+    rng = np.random.default_rng(5)
+    eng = engine_factory(641, 481)
+    for (h, w) in [(480, 640), (481, 641), (7, 5), (64, 3)]:
+        bgr = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        assert np.array_equal(eng.cvt_gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+        assert np.array_equal(eng.cvt_gray(bgr, rgb=True), cv2.cvtColor(bgr, cv2.COLOR_RGB2GRAY))
+    padded = rng.integers(0, 256, size=(100, 200, 3), dtype=np.uint8)
+    view = padded[:, :150]                      # row step 600 bytes, 450 used
+    assert np.array_equal(eng.cvt_gray(view), cv2.cvtColor(np.ascontiguousarray(view), cv2.COLOR_BGR2GRAY))
