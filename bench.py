@@ -480,25 +480,45 @@ def run_ours(args, rank, local_rank, world):
     pin_prev = [torch.from_numpy(host_sets[s][:B].copy()).pin_memory() for s in range(min(n_sets, 3))]
     pin_next = [torch.from_numpy((host_sets[s][1:B + 1] if seq else host_sets[s][B:2 * B]).copy()).pin_memory()
                 for s in range(min(n_sets, 3))]
-    pin_flow = torch.empty((B, H_, W_, 2), dtype=torch.float32).pin_memory()
+    # two result buffers: the asynchronous batch call pipelines across calls (upload + kernels of step
+    # i+1 overlap the download of step i); a step's result is complete before its buffer is reused
+    # (the library orders that) and everything is complete at eng.wait() inside the timed region
+    pin_flow = [torch.empty((B, H_, W_, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
     e2e_steps = args.steps if args.e2e_steps <= 0 else args.e2e_steps
 
     def e2e_step(i):
         s = i % len(pin_prev)
-        eng.farneback_batch_into(pin_prev[s].numpy(), pin_next[s].numpy(), pin_flow.numpy(), **PARAMS)
+        eng.farneback_batch_into(pin_prev[s].numpy(), pin_next[s].numpy(), pin_flow[i % 2].numpy(),
+                                 wait=args.e2e_sync, **PARAMS)
 
     for i in range(min(2, args.warmup)):
         e2e_step(i)
+    eng.wait()
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(i)
-    eng.synchronize()
+    eng.wait()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * e2e_steps * world / float(t.item())
+
+    # ---- e2e through the node contract: frames up, flow on the device, median/mean of u back (what every
+    # node of the reference does right after the flow call) — the field never crosses PCIe
+    for i in range(2):
+        eng.farneback_batch_stats(pin_prev[i % len(pin_prev)].numpy(), pin_next[i % len(pin_prev)].numpy(), **PARAMS)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        s_ = i % len(pin_prev)
+        eng.farneback_batch_stats(pin_prev[s_].numpy(), pin_next[s_].numpy(), **PARAMS)
+    node_s = time.perf_counter() - t0
+    t = torch.tensor([node_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    node_value = B * e2e_steps * world / float(t.item())
 
     if rank != 0:
         if world > 1:
@@ -549,7 +569,12 @@ def run_ours(args, rank, local_rank, world):
                      "timed_region_ms_with_stage_events": dev_ms_max},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * W_ * H_,
                 "d2h_bytes_per_step": 8 * B * W_ * H_, "steps": e2e_steps,
-                "api": "ofb_farneback_batch (host buffers, pinned; full float32 [H,W,2] flow returned)"},
+                "api": ("ofb_farneback_batch" if args.e2e_sync else "ofb_farneback_batch_async + ofb_wait") +
+                       " (host buffers, pinned; full float32 [H,W,2] flow of every pair returned to the host)"},
+        "e2e_node_contract": {"value": node_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * W_ * H_,
+                              "d2h_bytes_per_step": 12 * B, "steps": e2e_steps,
+                              "api": "ofb_farneback_batch_stats (host frames in, on-device mean + exact median of u out: "
+                                     "the reduction every node applies, lfn3_sub_node.py:205-212)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -577,6 +602,7 @@ def main():
     ap.add_argument("--tile-size", default="8k", choices=["8k", "4k", "1080p"], help="--mode tiled: frame size")
     ap.add_argument("--no-tiled-check", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--e2e-sync", action="store_true", help="e2e through the synchronous batch call (no cross-call overlap)")
     ap.add_argument("--ref-pairs", type=int, default=2, help="--impl reference: pairs per worker per step")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

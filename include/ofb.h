@@ -123,6 +123,23 @@ int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const 
                         int width, int height, size_t stride_bytes, float* const* flow,
                         size_t flow_stride_bytes, const ofb_farneback_params* params);
 
+/* Asynchronous variant for throughput: enqueues the uploads, kernels and downloads of the batch and
+ * returns.  Buffers must be page-locked (else it degrades to the synchronous path) and must stay
+ * untouched until ofb_wait.  Successive calls pipeline ACROSS calls: the uploads and kernels of call
+ * i+1 overlap the downloads of call i (use a second set of flow buffers for it). */
+int ofb_farneback_batch_async(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next,
+                              int width, int height, size_t stride_bytes, float* const* flow,
+                              size_t flow_stride_bytes, const ofb_farneback_params* params);
+/* The node contract in one call (lfn3_sub_node.py:194-212: flow -> np.median / np.mean of u): uploads
+ * the n pairs (pipelined with the kernels), computes the flow and reduces it on the device; only the
+ * n scalars come back — the 8N-byte field never crosses PCIe.  mask/out_mean/out_median as in
+ * ofb_flow_u_stats.  Synchronous. */
+int ofb_farneback_batch_stats(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next,
+                              int width, int height, size_t stride_bytes, const ofb_farneback_params* params,
+                              const uint8_t* mask, double* out_mean, float* out_median);
+/* Blocks until everything enqueued on the handle (all three streams) has finished. */
+int ofb_wait(ofb_handle* h);
+
 /* Device-resident call, asynchronous on the handle's stream: d_prev/d_next are n
  * uint8 images (row pitch `pitch_bytes`, image i at + i*image_stride_bytes);
  * d_flow is n packed float32 [height][width][2] fields.  Returns after enqueueing. */

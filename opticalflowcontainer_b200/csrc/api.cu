@@ -238,6 +238,8 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     h->no_fused_src = nf && nf[0] == '1';
     const char* pw = getenv("OFB_PX_WAVES");
     if (pw) h->px_waves = std::max(1, atoi(pw));
+    const char* pch = getenv("OFB_PIPE_CHUNK");
+    if (pch) h->pipe_chunk = std::max(0, atoi(pch));
     const char* np = getenv("OFB_NO_PIPELINE");
     h->no_pipeline = np && np[0] == '1';
   }
@@ -454,11 +456,14 @@ int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_f
                        nullptr, params);
 }
 
-int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next, int width,
-                        int height, size_t stride_bytes, float* const* flow, size_t flow_stride_bytes,
-                        const ofb_farneback_params* params) {
+static int farneback_batch_impl(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next,
+                                int width, int height, size_t stride_bytes, float* const* flow,
+                                size_t flow_stride_bytes, const ofb_farneback_params* params, bool wait) {
   if (!h) return OFB_ERR_INVALID_ARG;
-  if (!prev || !next || !flow) return set_error(h, OFB_ERR_INVALID_ARG, "NULL array pointer");
+  const bool download = flow != nullptr;   // nullptr: the field stays on the device (ofb_farneback_batch_stats)
+  if (!prev || !next) return set_error(h, OFB_ERR_INVALID_ARG, "NULL array pointer");
+  if (!download && (params && (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)))
+    return set_error(h, OFB_ERR_INVALID_ARG, "USE_INITIAL_FLOW needs the flow arrays");
   int st = validate_farneback(h, n, width, height, params);
   if (st) return st;
   if (stride_bytes == 0) stride_bytes = (size_t)width;
@@ -467,12 +472,13 @@ int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const 
   if (flow_stride_bytes == 0) flow_stride_bytes = row_flow;
   if (flow_stride_bytes < row_flow) return set_error(h, OFB_ERR_INVALID_ARG, "flow stride smaller than a row");
   for (int i = 0; i < n; i++)
-    if (!prev[i] || !next[i] || !flow[i]) return set_error(h, OFB_ERR_INVALID_ARG, "NULL image/flow pointer");
+    if (!prev[i] || !next[i] || (download && !flow[i])) return set_error(h, OFB_ERR_INVALID_ARG, "NULL image/flow pointer");
   OFB_CUDA(h, cudaSetDevice(h->device));
   // Pinned (page-locked / registered) caller buffers are DMA'd directly; pageable ones are staged
   // through the handle's pinned buffers (one memcpy each way, as cudaMemcpy would do internally).
   bool pinned = true;
-  for (int i = 0; i < n && pinned; i++) pinned = is_pinned(prev[i]) && is_pinned(next[i]) && is_pinned(flow[i]);
+  for (int i = 0; i < n && pinned; i++)
+    pinned = is_pinned(prev[i]) && is_pinned(next[i]) && (!download || is_pinned(flow[i]));
   const size_t pitch = align_up((size_t)width, 16);
   const size_t istride = pitch * height;
   const size_t fl_img = (size_t)width * height * 2;
@@ -481,17 +487,29 @@ int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const 
     // Pipelined path: chunks of `c` pairs; H2D of chunk i+1 (copy-in stream) and D2H of chunk i-1
     // (copy-out stream) overlap the kernels of chunk i (handle stream).  PCIe is full duplex, so the
     // steady state is bounded by max(compute, D2H of the 8N-byte field).
-    const int c = n >= 8 ? 2 : 1;
+    // With the asynchronous entry point the pipeline also runs ACROSS calls (the next call's uploads and
+    // kernels overlap this call's downloads): every chunk slot keeps three events (upload done, kernels
+    // done, download done) that the next call's work on the same staging regions waits for.
+    const int c = h->pipe_chunk > 0 ? std::min(h->pipe_chunk, n) : (n >= 16 ? 4 : (n >= 8 ? 2 : 1));
     const int chunks = (n + c - 1) / c;
-    while ((int)h->pipe_ev.size() < 2 * chunks) {
+    while ((int)h->pipe_ev.size() < 3 * chunks) {
       cudaEvent_t e;
       OFB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       h->pipe_ev.push_back(e);
+    }
+    if (h->pipe_n != n || h->pipe_c != c || h->pipe_w != width || h->pipe_h != height) {
+      // different staging layout than the call before: drain it first
+      OFB_CUDA(h, cudaStreamSynchronize(h->s_in));
+      OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+      OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
+      h->pipe_n = n; h->pipe_c = c; h->pipe_w = width; h->pipe_h = height;
     }
     const bool use_init = (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) != 0;
     for (int ci = 0; ci < chunks; ci++) {
       const int i0 = ci * c, cn = std::min(c, n - i0);
       uint8_t* base = h->d_src + (size_t)2 * i0 * istride;   // [prev x cn][next x cn]
+      cudaEvent_t ev_in = h->pipe_ev[3 * ci], ev_comp = h->pipe_ev[3 * ci + 1], ev_out = h->pipe_ev[3 * ci + 2];
+      OFB_CUDA(h, cudaStreamWaitEvent(h->s_in, ev_comp, 0));     // previous call's kernels have read this source slot
       for (int i = 0; i < cn; i++) {
         OFB_CUDA(h, cudaMemcpy2DAsync(base + (size_t)i * istride, pitch, prev[i0 + i], stride_bytes, width, height,
                                       cudaMemcpyHostToDevice, h->s_in));
@@ -501,23 +519,31 @@ int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const 
           OFB_CUDA(h, cudaMemcpy2DAsync(h->d_init_flow + (i0 + i) * fl_img, row_flow, flow[i0 + i], flow_stride_bytes,
                                         row_flow, height, cudaMemcpyHostToDevice, h->s_in));
       }
-      OFB_CUDA(h, cudaEventRecord(h->pipe_ev[2 * ci], h->s_in));
-      OFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->pipe_ev[2 * ci], 0));
+      OFB_CUDA(h, cudaEventRecord(ev_in, h->s_in));
+      OFB_CUDA(h, cudaStreamWaitEvent(h->stream, ev_in, 0));
+      OFB_CUDA(h, cudaStreamWaitEvent(h->stream, ev_out, 0));    // previous call's download of this result slot is done
       st = farneback_run(h, cn, false, base, base + (size_t)cn * istride, width, height, pitch, istride,
                          h->d_flow_out + i0 * fl_img, use_init ? h->d_init_flow + i0 * fl_img : nullptr, params);
       if (st) return st;
-      OFB_CUDA(h, cudaEventRecord(h->pipe_ev[2 * ci + 1], h->stream));
-      OFB_CUDA(h, cudaStreamWaitEvent(h->s_out, h->pipe_ev[2 * ci + 1], 0));
-      for (int i = 0; i < cn; i++)
+      OFB_CUDA(h, cudaEventRecord(ev_comp, h->stream));
+      OFB_CUDA(h, cudaStreamWaitEvent(h->s_out, ev_comp, 0));
+      for (int i = 0; i < cn && download; i++)
         OFB_CUDA(h, cudaMemcpy2DAsync(flow[i0 + i], flow_stride_bytes, h->d_flow_out + (i0 + i) * fl_img, row_flow,
                                       row_flow, height, cudaMemcpyDeviceToHost, h->s_out));
+      OFB_CUDA(h, cudaEventRecord(ev_out, h->s_out));
     }
-    OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
-    OFB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->last_flow = h->d_flow_out;
     h->last_n = n;
+    if (wait) {
+      OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
+      OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     return OFB_OK;
   }
+  // serial paths (single pair, pageable buffers, OFB_NO_PIPELINE): always synchronous
+  OFB_CUDA(h, cudaStreamSynchronize(h->s_in));
+  OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
+  h->pipe_n = 0;
   if (pinned) {
     for (int i = 0; i < n; i++) {
       OFB_CUDA(h, cudaMemcpy2DAsync(h->d_src + (size_t)i * istride, pitch, prev[i], stride_bytes, width, height,
@@ -553,6 +579,10 @@ int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const 
   st = farneback_run(h, n, false, h->d_src, h->d_src + (size_t)n * istride, width, height, pitch, istride,
                      h->d_flow_out, init, params);
   if (st) return st;
+  if (!download) {
+    OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return OFB_OK;
+  }
   if (pinned) {
     for (int i = 0; i < n; i++)
       OFB_CUDA(h, cudaMemcpy2DAsync(flow[i], flow_stride_bytes, h->d_flow_out + i * fl_img, row_flow, row_flow, height,
@@ -569,6 +599,35 @@ int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const 
       for (int y = 0; y < height; y++)
         memcpy((char*)flow[i] + (size_t)y * flow_stride_bytes, h->h_flow + i * fl_img + (size_t)y * width * 2, row_flow);
   }
+  return OFB_OK;
+}
+
+int ofb_farneback_batch(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next, int width,
+                        int height, size_t stride_bytes, float* const* flow, size_t flow_stride_bytes,
+                        const ofb_farneback_params* params) {
+  return farneback_batch_impl(h, n, prev, next, width, height, stride_bytes, flow, flow_stride_bytes, params, true);
+}
+
+int ofb_farneback_batch_async(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next, int width,
+                              int height, size_t stride_bytes, float* const* flow, size_t flow_stride_bytes,
+                              const ofb_farneback_params* params) {
+  return farneback_batch_impl(h, n, prev, next, width, height, stride_bytes, flow, flow_stride_bytes, params, false);
+}
+
+int ofb_farneback_batch_stats(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next, int width,
+                              int height, size_t stride_bytes, const ofb_farneback_params* params, const uint8_t* mask,
+                              double* out_mean, float* out_median) {
+  int st = farneback_batch_impl(h, n, prev, next, width, height, stride_bytes, nullptr, 0, params, false);
+  if (st) return st;
+  return flow_u_stats(h, n, mask, out_mean, out_median);   // synchronises the stream and copies n scalars back
+}
+
+int ofb_wait(ofb_handle* h) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  OFB_CUDA(h, cudaStreamSynchronize(h->s_in));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
   return OFB_OK;
 }
 

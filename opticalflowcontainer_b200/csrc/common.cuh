@@ -84,6 +84,8 @@ struct ofb_handle {
   // host-buffer pipeline: copy-in / copy-out streams and their events (api.cu)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> pipe_ev;
+  int pipe_chunk = 0;          // OFB_PIPE_CHUNK: pairs per pipeline chunk of the host-buffer batch call (0 = auto)
+  int pipe_n = 0, pipe_c = 0, pipe_w = 0, pipe_h = 0;   // staging layout of the previous pipelined call
   bool no_pipeline = false;    // OFB_NO_PIPELINE=1: serial upload -> compute -> download
   uint64_t launches = 0;
   std::string err;

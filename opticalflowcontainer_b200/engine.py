@@ -149,9 +149,16 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out
 
-    def farneback_batch_into(self, prevs: np.ndarray, nexts: np.ndarray, out: np.ndarray, **kw) -> np.ndarray:
+    def wait(self):
+        """Block until everything enqueued by the asynchronous calls has finished (ofb_wait)."""
+        _lib.check(self._lib.ofb_wait(self._h), self._h)
+
+    def farneback_batch_into(self, prevs: np.ndarray, nexts: np.ndarray, out: np.ndarray, wait: bool = True,
+                             **kw) -> np.ndarray:
         """Zero-copy variant of farneback_batch: prevs/nexts uint8 [n,H,W], out float32 [n,H,W,2], all
-        C-contiguous (pinned memory is DMA'd directly, pageable memory is staged by the library)."""
+        C-contiguous (pinned memory is DMA'd directly, pageable memory is staged by the library).
+        ``wait=False`` (page-locked buffers only) returns as soon as the work is enqueued: successive
+        calls then pipeline across calls — keep the buffers untouched until :meth:`wait`."""
         n, hgt, wid = prevs.shape
         if (nexts.shape != prevs.shape or out.shape != (n, hgt, wid, 2) or prevs.dtype != np.uint8
                 or nexts.dtype != np.uint8 or out.dtype != np.float32
@@ -164,10 +171,37 @@ class FlowEngine:
         pp = (C.c_void_p * n)(*[prevs.ctypes.data + i * ist for i in range(n)])
         nn = (C.c_void_p * n)(*[nexts.ctypes.data + i * ist for i in range(n)])
         ff = (C.c_void_p * n)(*[out.ctypes.data + i * fst for i in range(n)])
+        fn = self._lib.ofb_farneback_batch if wait else self._lib.ofb_farneback_batch_async
         with self._lock:
-            st = self._lib.ofb_farneback_batch(self._h, n, pp, nn, wid, hgt, wid, ff, 0, C.byref(p))
+            st = fn(self._h, n, pp, nn, wid, hgt, wid, ff, 0, C.byref(p))
             _lib.check(st, self._h)
         return out
+
+    def farneback_batch_stats(self, prevs: np.ndarray, nexts: np.ndarray, mask: Optional[np.ndarray] = None, **kw):
+        """The node contract in one call: flow of n pairs (uint8 [n,H,W] each) reduced on the device to
+        (mean_u [n] float64, median_u [n] float32); the field itself is not downloaded."""
+        n, hgt, wid = prevs.shape
+        if (nexts.shape != prevs.shape or prevs.dtype != np.uint8 or nexts.dtype != np.uint8
+                or not (prevs.flags.c_contiguous and nexts.flags.c_contiguous)):
+            raise OfbError(1, "farneback_batch_stats: need contiguous uint8 [n,H,W] x2")
+        p = self._fb_params(kw.get("pyr_scale", 0.5), kw.get("levels", 3), kw.get("winsize", 15),
+                            kw.get("iterations", 3), kw.get("poly_n", 5), kw.get("poly_sigma", 1.2),
+                            kw.get("flags", 0))
+        ist = hgt * wid
+        pp = (C.c_void_p * n)(*[prevs.ctypes.data + i * ist for i in range(n)])
+        nn = (C.c_void_p * n)(*[nexts.ctypes.data + i * ist for i in range(n)])
+        mean = (C.c_double * n)()
+        med = (C.c_float * n)()
+        mptr = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            if mask.shape != (hgt, wid):
+                raise OfbError(1, "mask must be uint8 [H,W]")
+            mptr = mask.ctypes.data
+        with self._lock:
+            st = self._lib.ofb_farneback_batch_stats(self._h, n, pp, nn, wid, hgt, wid, C.byref(p), mptr, mean, med)
+            _lib.check(st, self._h)
+        return np.array(mean[:], np.float64), np.array(med[:], np.float32)
 
     def farneback_device(self, n: int, d_prev: int, d_next: int, width: int, height: int, pitch: int,
                          image_stride: int, d_flow: int, sequence: bool = False, **kw):

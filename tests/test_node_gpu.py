@@ -109,3 +109,21 @@ def test_cvt_gray_bit_exact(engine_factory):
     padded = rng.integers(0, 256, size=(100, 200, 3), dtype=np.uint8)
     view = padded[:, :150]                      # row step 600 bytes, 450 used
     assert np.array_equal(eng.cvt_gray(view), cv2.cvtColor(np.ascontiguousarray(view), cv2.COLOR_BGR2GRAY))
+
+
+def test_batch_stats_matches_numpy(built_lib):
+    """ofb_farneback_batch_stats = flow + on-device mean/median of u without downloading the field."""
+    import opticalflowcontainer_b200 as ofb
+    n, h, w = 4, 240, 320
+    eng = ofb.FlowEngine(w, h, n, 0)
+    try:
+        prs = [synth.synth_pair(h, w, 60 + i, (1.5 + 0.7 * i, -0.5 * i)) for i in range(n)]
+        a = np.stack([p[0] for p in prs]); b = np.stack([p[1] for p in prs])
+        flows = eng.farneback_batch_into(a, b, np.empty((n, h, w, 2), np.float32))
+        mean, med = eng.farneback_batch_stats(a, b)
+        for i in range(n):
+            u = flows[i, :, :, 0]
+            assert abs(mean[i] - float(u.astype(np.float64).mean())) <= 1e-6
+            assert med[i] == np.float32(np.median(u))
+    finally:
+        eng.close()
