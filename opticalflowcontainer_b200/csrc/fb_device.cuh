@@ -14,6 +14,11 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // fraction of the FP32 rate on B200 (the level-3 pyramid pass spent 80 us on it).  Exact for v < 2^23.
 __device__ __forceinline__ float u8f(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.f; }
 
+// BORDER_REFLECT_101 for an index that overshoots by less than n (one reflection, branch-free)
+__device__ __forceinline__ int reflect101_once(int i, int n) {
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * (n - 1) - i : i;
+}
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // cv::resize INTER_LINEAR source coordinate (resize.cpp): fx=(dx+0.5)*scale-0.5, clamp at both ends.

@@ -46,6 +46,9 @@ struct LevelColumn<0> {
   __device__ __forceinline__ void start(int) {}
   __device__ __forceinline__ Raw load(int t) const { return __ldg(col + (size_t)clampi(t, 0, h - 1) * w); }
   __device__ __forceinline__ float consume(int, Raw r) { return r; }
+  __device__ __forceinline__ bool edge() const { return false; }
+  __device__ __forceinline__ Raw load_fast(int t) const { return __ldg(col + (size_t)t * w); }   // 0 <= t < h
+  __device__ __forceinline__ float consume_fast(int, Raw r) { return r; }
 };
 
 // SRC = 1: uint8 source frame of the level's size; I = Gv * (Gh * float(src)), 3 taps, REFLECT_101.
@@ -88,7 +91,26 @@ struct LevelColumn<1> {
     tc = n;
     cur = fmaf(k1, hm + hp, k0 * h0);
   }
-  __device__ __forceinline__ Raw load(int t) const { return raw_row(reflect101(clampi(t, 0, h - 1) + 1, h)); }
+  __device__ __forceinline__ Raw load(int t) const { return raw_row(reflect101_once(clampi(t, 0, h - 1) + 1, h)); }
+  // Fast path for interior rows (1 <= t, t + 1 <= h - 1) of interior columns: no clamp, no reflection,
+  // one address computation per row (the generic path spent ~60 instructions per pixel on them).
+  __device__ __forceinline__ bool edge() const { return xl != xc - 1 || xr != xc + 1; }
+  __device__ __forceinline__ Raw load_fast(int t) const {
+    const uint8_t* p = base + (size_t)(t + 1) * pitch + xc;
+    Raw r;
+    r.a = __ldg(p - 1);
+    r.b = __ldg(p);
+    r.c = __ldg(p + 1);
+    return r;
+  }
+  __device__ __forceinline__ float consume_fast(int t, Raw r) {   // t == tc + 1
+    hm = h0;
+    h0 = hp;
+    hp = hval(r);
+    tc = t;
+    cur = fmaf(k1, hm + hp, k0 * h0);
+    return cur;
+  }
   __device__ __forceinline__ float consume(int t, Raw r) {
     const int n = clampi(t, 0, h - 1);
     if (n != tc) {   // n == tc + 1; uniform over the CTA (depends on t only)
@@ -149,10 +171,22 @@ __global__ void __launch_bounds__(PX_COLS)
   int buf = 0;
   for (int ys = y0; ys < y1; ys += PX_ROWS) {
     // ---------------- V: 4 new rows, vertical moments of rows ys .. ys+3
+    // rows entering now: t0 .. t0+3; rows to load for the next step: t0+4 .. t0+7
+    const int t0 = ys + NMAX;
+    if (t0 >= 2 && t0 + PX_ROWS <= h - 1 && !feed.edge()) {       // (t0 - 1 was consumed un-clamped: tc == t0 - 1)
 #pragma unroll
-    for (int r = 0; r < PX_ROWS; r++) win[2 * NMAX + r] = feed.consume(ys + NMAX + r, nx[r]);
+      for (int r = 0; r < PX_ROWS; r++) win[2 * NMAX + r] = feed.consume_fast(t0 + r, nx[r]);
+    } else {
 #pragma unroll
-    for (int r = 0; r < PX_ROWS; r++) nx[r] = feed.load(ys + PX_ROWS + NMAX + r);   // rows clamp: always valid
+      for (int r = 0; r < PX_ROWS; r++) win[2 * NMAX + r] = feed.consume(t0 + r, nx[r]);
+    }
+    if (t0 + PX_ROWS >= 1 && t0 + 2 * PX_ROWS <= h - 1 && !feed.edge()) {
+#pragma unroll
+      for (int r = 0; r < PX_ROWS; r++) nx[r] = feed.load_fast(t0 + PX_ROWS + r);
+    } else {
+#pragma unroll
+      for (int r = 0; r < PX_ROWS; r++) nx[r] = feed.load(t0 + PX_ROWS + r);   // rows clamp: always valid
+    }
 #pragma unroll
     for (int r = 0; r < PX_ROWS; r++) {
       const float* c = win + NMAX + r;   // centre of row ys + r

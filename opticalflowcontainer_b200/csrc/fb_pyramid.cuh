@@ -83,6 +83,20 @@ __global__ void __launch_bounds__(128) k_pyr_h(FrameSrc src, int W, int H, float
       h1 = fmaf(pc.k[r], u8f(__ldg(p + r + 1)), h1);
       *out = h0 * gx + h1 * fx;
     }
+  } else if (RT > 0 && RT + 1 < W) {
+    // image border, compile-time radius: same unrolled sweep with one branch-free reflection per tap (the
+    // rolled generic loop below made the two border warps of every row the tail of the whole kernel)
+    for (int y = y_begin; y < y_end; y++, out += w) {
+      const uint8_t* row = col - sx0 + (size_t)y * src.pitch;
+      float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+      for (int i = -RT; i <= RT + 1; i++) {
+        const float v = u8f(__ldg(row + reflect101_once(sx0 + i, W)));
+        if (i <= RT) h0 = fmaf(pc.k[i < 0 ? -i : i], v, h0);
+        if (i >= -RT + 1) h1 = fmaf(pc.k[i - 1 < 0 ? 1 - i : i - 1], v, h1);
+      }
+      *out = fx == 0.f ? h0 : h0 * gx + h1 * fx;
+    }
   } else {
     for (int y = y_begin; y < y_end; y++, out += w) {
       const uint8_t* row = col - sx0 + (size_t)y * src.pitch;
@@ -145,6 +159,13 @@ __global__ void __launch_bounds__(256) k_pyr_v(const float* __restrict__ hb, int
       }
     }
     v1 = fmaf(pc.k[r], __ldg(c + (size_t)(r + 1) * w), v1);
+  } else if (RT > 0 && RT + 1 < H) {
+#pragma unroll
+    for (int t = -RT; t <= RT + 1; t++) {
+      const float v = __ldg(col + (size_t)reflect101_once(sy0 + t, H) * w);
+      if (t <= RT) v0 = fmaf(pc.k[t < 0 ? -t : t], v, v0);
+      if (t >= -RT + 1) v1 = fmaf(pc.k[t - 1 < 0 ? 1 - t : t - 1], v, v1);
+    }
   } else {
     for (int t = -r; t <= r + 1; t++) {
       const float v = __ldg(col + (size_t)reflect101(sy0 + t, H) * w);

@@ -8,6 +8,6 @@ for n in "$@"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -DOFB_DBG=$n \
        -c farneback.cu -o build/variants/farneback_dbg$n.o
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o build/variants/libofb_dbg$n.so \
-       build/variants/farneback_dbg$n.o build/api.o build/reduce.o build/sparse.o
+       build/variants/farneback_dbg$n.o $(ls build/*.o | grep -v farneback.o)
   echo built build/variants/libofb_dbg$n.so
 done
