@@ -550,15 +550,16 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": plain_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "farneback_1920x1080_single_stream", "params": PARAMS, "pairs_per_step_per_gpu": B,
+        "config": {"workload": "farneback_%dx%d_%s" % (W_, H_, "single_stream" if args.frame == "1080p" else "batched_pairs"),
+                   "params": PARAMS, "pairs_per_step_per_gpu": B,
                    "mode": args.mode, "parallelism": "frame-pair sharding x%d, no collective" % world,
                    "l2": "inputs rotate over %d frame sets (%.0f MB > 2x L2); per-step working set %.0f MB >> L2"
-                         % (n_sets, n_sets * frames_per_set * istride / 1e6, B * 232.0)},
+                         % (n_sets, n_sets * frames_per_set * istride / 1e6, B * 232.0 * W_ * H_ / 2073600.0)},
         "roofline": {"bound": "hbm", "kernel": "k_iter_v, level-0 launch (UpdateMatrices + box blur + 2x2 solve fused)",
                      "achieved": it_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": it_gbs / peaks["hbm_gbs"],
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_launch_bytes,
-                     "algorithmic_bytes_model": "56 B x 2073600 px x %d pairs" % B,
+                     "algorithmic_bytes_model": "56 B x %d px x %d pairs" % (nl[-1], B),
                      "launch_ms": l0_ms, "launches_timed": len(l0),
                      "level0_launch_share_of_step": (sum(l0) / dev_ms) if dev_ms > 0 else None,
                      "iteration_stage_all_levels_gbs": stage_gbs,
@@ -582,9 +583,10 @@ def run_ours(args, rank, local_rank, world):
         from oracle import cpu_bench
         cb = cpu_bench.farneback_cpu_throughput(H_, W_, target_seconds=args.cpu_seconds)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "reference",
-                                "sample": "cv2 %s calcOpticalFlowFarneback, %d processes x %d pairs of 1920x1080 "
+                                "sample": "cv2 %s calcOpticalFlowFarneback, %d processes x %d pairs of %dx%d "
                                           "(single-threaded algorithm; 1 pair = %.0f ms on one core)"
-                                          % (cb["cv2_version"], cb["cores"], cb["pairs_per_worker"], cb["single_pair_ms"])}
+                                          % (cb["cv2_version"], cb["cores"], cb["pairs_per_worker"], W_, H_,
+                                             cb["single_pair_ms"])}
     real_stdout.write(json.dumps(line) + "\n")
     real_stdout.flush()
     if world > 1:
@@ -598,6 +600,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frame pairs per step per GPU")
+    ap.add_argument("--frame", default="1080p", choices=["vga", "1080p", "4k"],
+                    help="frame size of the pairs/sequence modes (1080p = the BASELINE.json metric; vga = config 0, 4k = config 3)")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence", "tiled", "lk"])
     ap.add_argument("--tile-size", default="8k", choices=["8k", "4k", "1080p"], help="--mode tiled: frame size")
     ap.add_argument("--no-tiled-check", action="store_true")
@@ -610,6 +614,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    global W_, H_, METRIC
+    W_, H_ = {"vga": (640, 480), "1080p": (1920, 1080), "4k": (3840, 2160)}[args.frame]
+    if args.frame != "1080p":
+        METRIC = "farneback_%s_frame_pairs_per_s" % args.frame
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
