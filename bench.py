@@ -511,9 +511,11 @@ def run_ours(args, rank, local_rank, world):
         eng.farneback_batch_stats(pin_prev[i % len(pin_prev)].numpy(), pin_next[i % len(pin_prev)].numpy(), **PARAMS)
     barrier()
     t0 = time.perf_counter()
+    node_out = []
     for i in range(e2e_steps):
         s_ = i % len(pin_prev)
-        eng.farneback_batch_stats(pin_prev[s_].numpy(), pin_next[s_].numpy(), **PARAMS)
+        node_out.append(eng.farneback_batch_stats(pin_prev[s_].numpy(), pin_next[s_].numpy(), wait=args.e2e_sync, **PARAMS))
+    eng.wait()                                  # every step's mean/median of u is on the host here
     node_s = time.perf_counter() - t0
     t = torch.tensor([node_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -574,7 +576,8 @@ def run_ours(args, rank, local_rank, world):
                        " (host buffers, pinned; full float32 [H,W,2] flow of every pair returned to the host)"},
         "e2e_node_contract": {"value": node_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * W_ * H_,
                               "d2h_bytes_per_step": 12 * B, "steps": e2e_steps,
-                              "api": "ofb_farneback_batch_stats (host frames in, on-device mean + exact median of u out: "
+                              "api": ("ofb_farneback_batch_stats" if args.e2e_sync else "ofb_farneback_batch_stats_async + ofb_wait") +
+                                     " (host frames in, on-device mean + exact median of u out: "
                                      "the reduction every node applies, lfn3_sub_node.py:205-212)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -599,7 +602,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="frame pairs per step per GPU")
+    # 18 pairs: the level-0 launch of the iteration kernel is 8 strips x 2 row segments x 18 pairs = 288 CTAs on
+    # the 296 resident CTA slots of a B200 (16 pairs leave 40 slots, i.e. 40 SMs half empty)
+    ap.add_argument("--batch", type=int, default=18, help="frame pairs per step per GPU")
     ap.add_argument("--frame", default="1080p", choices=["vga", "1080p", "4k"],
                     help="frame size of the pairs/sequence modes (1080p = the BASELINE.json metric; vga = config 0, 4k = config 3)")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence", "tiled", "lk"])

@@ -137,7 +137,17 @@ int ofb_farneback_batch_async(ofb_handle* h, int n, const uint8_t* const* prev, 
 int ofb_farneback_batch_stats(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next,
                               int width, int height, size_t stride_bytes, const ofb_farneback_params* params,
                               const uint8_t* mask, double* out_mean, float* out_median);
-/* Blocks until everything enqueued on the handle (all three streams) has finished. */
+/* Asynchronous form of ofb_farneback_batch_stats for page-locked frames: returns once the work is enqueued, so
+ * the uploads and kernels of the next call run behind this one's (a camera node keeps a call in flight while it
+ * receives the next frames).  out_mean / out_median are written by ofb_wait (or by a later call, once more than
+ * a few reductions are pending) and must stay valid until then; the frames must stay untouched as for
+ * ofb_farneback_batch_async.  Pageable frames are served synchronously.
+ * Replaces the same node lines as ofb_farneback_batch_stats (lfn3_sub_node.py:194-212). */
+int ofb_farneback_batch_stats_async(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next,
+                                    int width, int height, size_t stride_bytes, const ofb_farneback_params* params,
+                                    const uint8_t* mask, double* out_mean, float* out_median);
+/* Blocks until everything enqueued on the handle (all three streams) has finished and hands the results of
+ * pending asynchronous reductions to their callers' arrays. */
 int ofb_wait(ofb_handle* h);
 
 /* Device-resident call, asynchronous on the handle's stream: d_prev/d_next are n

@@ -165,6 +165,7 @@ int ofb_destroy(ofb_handle* h) {
   if (h->h_lintab) cudaFreeHost(h->h_lintab);
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
+  if (h->h_stats) cudaFreeHost(h->h_stats);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->tile.imported && !h->tile.same_process) {
     for (int r = 0; r < h->tile.world; r++) {
@@ -230,6 +231,8 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     if (ip) h->iter_prefetch = ip[0] != '0';
     const char* ipd = getenv("OFB_ITER_PFD");
     if (ipd) h->iter_pfd = atoi(ipd) == 2 ? 2 : 3;
+    const char* ir = getenv("OFB_ITER_REUSE");
+    if (ir) h->iter_reuse = atoi(ir);
     const char* iw = getenv("OFB_ITER_WAVES");
     if (iw) h->iter_waves = std::max(1, atoi(iw));
     const char* pt = getenv("OFB_POLYEXP_TILE");
@@ -268,6 +271,7 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
   h->h_flow_bytes = max_batch * N * sizeof(float2);
   CREATE_CUDA(cudaHostAlloc(&h->h_src, h->h_src_bytes, cudaHostAllocDefault));
   CREATE_CUDA(cudaHostAlloc(&h->h_flow, h->h_flow_bytes, cudaHostAllocDefault));
+  CREATE_CUDA(cudaHostAlloc(&h->h_stats, (size_t)kStatSlots * max_batch * 16, cudaHostAllocDefault));
 #undef CREATE_CUDA
   *out = h;
   return OFB_OK;
@@ -490,7 +494,10 @@ static int farneback_batch_impl(ofb_handle* h, int n, const uint8_t* const* prev
     // With the asynchronous entry point the pipeline also runs ACROSS calls (the next call's uploads and
     // kernels overlap this call's downloads): every chunk slot keeps three events (upload done, kernels
     // done, download done) that the next call's work on the same staging regions waits for.
-    const int c = h->pipe_chunk > 0 ? std::min(h->pipe_chunk, n) : (n >= 16 ? 4 : (n >= 8 ? 2 : 1));
+    // Without a download to hide (the reduction call) two half-batch chunks are enough to keep the next
+    // upload behind the running kernels, and larger chunks fill the GPU better.
+    const int c = h->pipe_chunk > 0 ? std::min(h->pipe_chunk, n)
+                  : !download ? (n + 1) / 2 : (n >= 16 ? 4 : (n >= 8 ? 2 : 1));
     const int chunks = (n + c - 1) / c;
     while ((int)h->pipe_ev.size() < 3 * chunks) {
       cudaEvent_t e;
@@ -622,13 +629,22 @@ int ofb_farneback_batch_stats(ofb_handle* h, int n, const uint8_t* const* prev, 
   return flow_u_stats(h, n, mask, out_mean, out_median);   // synchronises the stream and copies n scalars back
 }
 
+int ofb_farneback_batch_stats_async(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next,
+                                    int width, int height, size_t stride_bytes, const ofb_farneback_params* params,
+                                    const uint8_t* mask, double* out_mean, float* out_median) {
+  int st = farneback_batch_impl(h, n, prev, next, width, height, stride_bytes, nullptr, 0, params, false);
+  if (st) return st;
+  if (h->pipe_n == 0) return flow_u_stats(h, n, mask, out_mean, out_median);   // pageable frames: served synchronously
+  return flow_u_stats(h, n, mask, out_mean, out_median, true);
+}
+
 int ofb_wait(ofb_handle* h) {
   if (!h) return OFB_ERR_INVALID_ARG;
   OFB_CUDA(h, cudaSetDevice(h->device));
   OFB_CUDA(h, cudaStreamSynchronize(h->s_in));
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
   OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
-  return OFB_OK;
+  return finish_pending_stats(h);
 }
 
 int ofb_farneback(ofb_handle* h, const uint8_t* prev, const uint8_t* next, int width, int height, size_t stride_bytes,

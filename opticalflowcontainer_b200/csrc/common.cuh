@@ -77,6 +77,7 @@ struct ofb_handle {
   int iter_ws = 4;             // OFB_ITER_WS=1: k_iter_ws (double vertical sums, cv2's scheme) instead of k_iter_v
   int iter_pfd = 3;            // OFB_ITER_PFD: L2 prefetch distance (rows) of k_iter_v (2 or 3)
   bool iter_prefetch = true;   // OFB_ITER_PREFETCH=0: no L2 prefetch of the next chunk in k_iter_ws2
+  int iter_reuse = 1;      // OFB_ITER_REUSE=0: full 2x2 gather for every pixel (no row reuse between consecutive rows)
   int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
   bool polyexp_tile = false;   // OFB_POLYEXP_TILE=1: 32x32-tile PolyExp kernel instead of the marching one
   bool no_fused_src = false;   // OFB_NO_FUSED_SRC=1: level-0 pyramid stage as separate kernels
@@ -131,6 +132,12 @@ struct ofb_handle {
   uint32_t* d_sel = nullptr;   // radix-select state of ofb_flow_u_stats (reduce.cu)
   uint8_t* d_mask = nullptr;
   float* d_scratch = nullptr;  // median selection scratch
+  // asynchronous reductions (ofb_farneback_batch_stats_async): results land in pinned slots and are handed
+  // to the caller's arrays by ofb_wait
+  struct PendingStats { double* out_mean; float* out_median; int n; int slot; };
+  std::vector<PendingStats> pending_stats;
+  char* h_stats = nullptr;     // pinned, kStatSlots x max_batch x 16 B
+  int stats_slot = 0;
   size_t scratch_bytes = 0;
 
   // pinned host staging
@@ -195,7 +202,9 @@ int farneback_run_tiled_emulated(ofb_handle* const* hs, int world, const uint8_t
                                  int width, int height, size_t pitch, float* d_flow_out,
                                  const ofb_farneback_params* p);
 
-int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mean, float* out_median);
+constexpr int kStatSlots = 4;   // reductions in flight before ofb_farneback_batch_stats_async drains them itself
+int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mean, float* out_median, bool async = false);
+int finish_pending_stats(ofb_handle* h);   // synchronises the stream, copies staged scalars to the callers' arrays
 
 // ---- sparse ---------------------------------------------------------------------------
 void sparse_destroy(ofb_handle* h);

@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(256) k_init_flow_area(const float2* __restrict
 // Driver: the multi-level schedule on the handle's stream (no host sync inside).
 // =====================================================================================
 // k_iter_v launcher.
-template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false>
+template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false,
+          bool REUSE = false>
 static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
                                  int f1_offset, int m, float reg, cudaStream_t st, int y_begin = 0, int y_end = -1,
                                  const PeerTab* tab = nullptr, int my_rank = 0) {
@@ -458,7 +459,7 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   static int configured[64] = {0};
   const int dev = h->device & 63;
   if (smem > configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED>,
+    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED, REUSE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured[dev] = smem;
@@ -472,7 +473,7 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   int seg_rows = std::max(16, (rows + segs - 1) / segs);
   segs = (rows + seg_rows - 1) / seg_rows;
   dim3 g(strips * segs, n_pairs);
-  k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED><<<g, COLS + (CH / CLOOP) * COLS / PXT, smem, st>>>(
+  k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED, REUSE><<<g, COLS + (CH / CLOOP) * COLS / PXT, smem, st>>>(
       h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank);
   return cudaGetLastError();
 }
@@ -622,6 +623,8 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
             } else {
               if (pfd == 0) e = launch_iter_v<7, 256, 2, 2, 0, 4>(OFB_V_ARGS);
               else if (pfd == 2) e = launch_iter_v<7, 256, 2, 2, 2, 4>(OFB_V_ARGS);
+              else if (h->iter_reuse == 2) e = launch_iter_v<7, 256, 2, 2, 3, 4, 2, 1>(OFB_V_ARGS);
+              else if (h->iter_reuse) e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>(OFB_V_ARGS);
               else e = launch_iter_v<7, 256, 2, 2, 3, 4>(OFB_V_ARGS);
             }
           } else {

@@ -27,6 +27,11 @@
 
 namespace ofb {
 
+// REUSE variant: the kernel is launched with 80 registers/thread (2 CTAs of 384 threads per SM); the consumer
+// warpgroup hands 24 of them back and the two producer warpgroups take 12 more each (setmaxnreg), so the
+// persistent corner rows do not push the producers' loads behind their first use.
+constexpr int REUSE_PROD_REGS = 88, REUSE_CONS_REGS = 56;
+
 template <int COLS, int CH>
 constexpr int iter_v_smem_floats(int m) { return (2 * CH + 2 * m + 1) * 5 * COLS; }
 
@@ -44,7 +49,10 @@ constexpr int iter_v_smem_floats(int m) { return (2 * CH + 2 * m + 1) * 5 * COLS
 // rank owns; R0 / R1 / flow rows owned by other ranks (the 2m halo rows of the blur and whatever the
 // displacement reaches) are read from those ranks' buffers through the NVLink peer pointers in `tab` —
 // the halo exchange is these loads, issued tile by tile inside the kernel that consumes them.
-template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false>
+// REUSE: row-reuse gather (fb_um.cuh): the top corner row of a pixel is taken from the registers of the pixel
+// above when the displacement allows it; needs RIF == 1, CH even, untiled.
+template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false,
+          bool REUSE = false>
 __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
     k_iter_v(const float4* __restrict__ RA, const float* __restrict__ RB, const float2* __restrict__ flow_in,
              float2* __restrict__ flow_out, int w, int h, int f1_offset, int m_rt, float reg, int seg_rows,
@@ -55,6 +63,7 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
   static_assert(CLOOP == 1 || CLOOP == CH, "consumer rows per thread: 1 or the whole chunk");
   constexpr int NCONS = (CH / CLOOP) * GROUPS;
   static_assert(NCONS % 32 == 0, "whole consumer warps");
+  static_assert(!REUSE || (RIF == 1 && !TILED && CH % 2 == 0), "row-reuse gather: one row in flight, even chunks, untiled");
   constexpr int NT = COLS + NCONS;
   enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3 };
   const int m = MT > 0 ? MT : m_rt;
@@ -78,6 +87,8 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
 
   if (tid < COLS) {
     // ------------------------------------------------------------------ PRODUCERS (one column each)
+    if constexpr (REUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REUSE_PROD_REGS));
+    else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(96));
     const float4* RA0 = RA + (size_t)pair * n;
     const float* RB0 = RB + (size_t)pair * n;
     const float4* RA1 = RA + (size_t)(pair + f1_offset) * n;
@@ -153,10 +164,84 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
     auto flow_at = [&](int t) {
       const int yc = clampi(t, 0, h - 1);
       const float2* f = TILED ? tab.flow[(yc >= tab.f_lo && yc < tab.f_hi) ? my_rank : tile_owner(yc, tab)] : fin;
+      if constexpr (RIF > 1) {
+        // volatile: keeps the load where it is written (between the gathers and the barrier); ptxas otherwise
+        // sinks it to the end of the loop body, right in front of the address arithmetic that needs it
+        float2 v;
+        asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(f + ((unsigned)yc * uw + (unsigned)x)));
+        return v;
+      }
       return __ldg(f + ((unsigned)yc * uw + (unsigned)x));
     };
 
-    if constexpr (RIF == 1) {
+    if constexpr (REUSE) {
+      // Row-reuse gather.  Two corner-row register sets alternate as "top" and "bottom" from one row to the
+      // next (rows are handled in pairs, so the alternation is in the register names, not in moves).
+      UmRow ra, rb;
+      UmPix px;
+      unsigned prev_g = ~0u - uw;
+      auto issue_r = [&](UmRow& top, UmRow& bot, float2 f, int t) {
+        const int y = clampi(t, 0, h - 1);
+        um_issue_rows(px, top, bot, prev_g, RA0, RB0, RA1, RB1, f, x, y, (unsigned)y * uw, uw, uh);
+        if (PFD > 0) {
+          static_assert(PFD + 1 <= kRowPad, "prefetch distance exceeds the row padding of the R buffers");
+          const unsigned op = (unsigned)clampi(t + PFD, 0, h - 1) * uw + (unsigned)x;
+          prefetch_l2(RA0 + op);
+          prefetch_l2(RB0 + op);
+          prefetch_l2(fin + ((unsigned)clampi(t + PFD + 1, 0, h - 1) * uw + (unsigned)x));
+          prefetch_l2(RA1 + (px.g + (PFD + 1) * uw));
+          prefetch_l2(RB1 + (px.g + (PFD + 1) * uw));
+        }
+      };
+      auto finish_r = [&](const UmRow& top, const UmRow& bot, int t, float (&V)[5]) {
+        const int y = clampi(t, 0, h - 1);
+        float old[5];
+#pragma unroll
+        for (int ch = 0; ch < 5; ch++) old[ch] = have_prev ? rcol[(k * 5 + ch) * COLS] : 0.f;
+        const M5 mm = um_finish_rows(px, top, bot, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h);
+        P[0] += mm.g11; P[1] += mm.g12; P[2] += mm.g22; P[3] += mm.h1; P[4] += mm.h2;
+#pragma unroll
+        for (int ch = 0; ch < 5; ch++) {
+          V[ch] = (Bp[ch] - old[ch]) + P[ch];
+          rcol[(k * 5 + ch) * COLS] = P[ch];
+        }
+        if (++k == R) {
+          k = 0;
+          have_prev = true;
+#pragma unroll
+          for (int ch = 0; ch < 5; ch++) { Bp[ch] = P[ch]; P[ch] = 0.f; }
+        }
+      };
+      float2 fl = flow_at(t_first);
+      // warm-up: the R-1 = 2m rows above the first output row, two at a time
+      for (int t = t_first; t < t_first + R - 1; t += 2) {
+        float V[5];
+        issue_r(ra, rb, fl, t);
+        fl = flow_at(t + 1);
+        finish_r(ra, rb, t, V);
+        issue_r(rb, ra, fl, t + 1);
+        fl = flow_at(t + 2);
+        finish_r(rb, ra, t + 1, V);
+      }
+      for (int c = 0; c < n_chunks; c++) {
+        const int buf = c & 1;
+        if (c >= 2) named_bar_sync(BAR_EMPTY0 + buf, NT);            // consumers released this buffer
+        float* srow = stage + buf * CH * 5 * COLS + tid;
+#pragma unroll
+        for (int rr = 0; rr < CH; rr++) {
+          const int yo = y0 + c * CH + rr;                           // output row; newest matrix row = yo + m
+          if (yo < y1) {
+            float V[5];
+            if (rr & 1) issue_r(rb, ra, fl, yo + m); else issue_r(ra, rb, fl, yo + m);
+            fl = flow_at(yo + m + 1);
+            if (rr & 1) finish_r(rb, ra, yo + m, V); else finish_r(ra, rb, yo + m, V);
+#pragma unroll
+            for (int ch = 0; ch < 5; ch++) srow[(rr * 5 + ch) * COLS] = V[ch];
+          }
+        }
+        named_bar_arrive(BAR_FULL0 + buf, NT);                       // staged rows of chunk c are ready
+      }
+    } else if constexpr (RIF == 1) {
       float2 fl = flow_at(t_first);
       // warm-up: the R-1 rows above the first output row (no hand-over)
       for (int t = t_first; t < t_first + R - 1; t++) {
@@ -239,6 +324,8 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
   }
 
   // -------------------------------------------------------------------- CONSUMERS (PXT adjacent pixels of one row each)
+  if constexpr (REUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REUSE_CONS_REGS));
+  else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
   float2* fout = flow_out + (size_t)pair * n;
   const int ct = tid - COLS;                         // 0..NCONS-1
   const int q_row0 = (ct / GROUPS) * CLOOP;          // first staged row of this thread's pixel group

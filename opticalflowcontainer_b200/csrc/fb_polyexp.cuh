@@ -24,6 +24,9 @@ constexpr int PX_HALO = 8;     // halo columns per side (>= poly_n, multiple of 
 constexpr int PX_TW = PX_COLS - 2 * PX_HALO;
 constexpr int PX_ROWS = 4;     // rows per step
 constexpr int PX_MAXN = 8;     // largest poly_n served by this kernel
+#ifndef PX_MINB
+#define PX_MINB 3        // resident CTAs per SM the register budget is held to (85 registers/thread)
+#endif
 
 // Level-image value feed of one thread (= one column xc, rows visited in increasing order).  Loading
 // and consuming a row are separate steps so the kernel can issue the loads of the NEXT step right
@@ -125,7 +128,7 @@ struct LevelColumn<1> {
 };
 
 template <int NT, int SRC>
-__global__ void __launch_bounds__(PX_COLS)
+__global__ void __launch_bounds__(PX_COLS, PX_MINB)
     k_polyexp_march(const float* __restrict__ I, FrameSrc src, float k0, float k1, float4* __restrict__ RA,
                     float* __restrict__ RB, int w, int h, int seg_rows, int strips, PolyCoef pc, int y_begin,
                     int y_end) {

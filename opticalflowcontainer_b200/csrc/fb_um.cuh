@@ -128,6 +128,93 @@ __device__ __forceinline__ M5 um_finish2(const UmLoads2& L, bool border, int x, 
   return m;
 }
 
+// ---- row-reuse gather (k_iter_v<..., REUSE>) -------------------------------------------------------
+// A producer thread walks down one column.  Where the displacement field is smooth, the 2x2 neighbourhood
+// of row y+1 sits exactly one row below that of row y (same floor(x+dx), floor(y+dy) one larger): its top
+// corner row IS the previous pixel's bottom corner row, still in registers.  Only the new bottom row is
+// loaded then (2 x LDG.128 + 2 x LDG.32 instead of 4 + 4: the gather was the largest share of the kernel's
+// L1 wavefronts).  Any other case (flow discontinuity, floor crossing, outside pixel, clamped warm-up rows)
+// loads both rows — values are bitwise the ones the full gather reads.
+struct UmRow {      // two horizontally adjacent R1 pixels
+  float4 q0, q1;
+  float s0, s1;
+};
+struct UmPix {
+  float4 a0;
+  float b0, fx, fy, dx, dy;
+  unsigned g;       // element offset of the top-left corner (0 when outside)
+  bool inside;
+};
+
+// prev_g: corner offset of the previous row's pixel (or an impossible value); `top` must still hold that
+// pixel's bottom row when prev_g + w == g.
+__device__ __forceinline__ void um_issue_rows(UmPix& P, UmRow& top, UmRow& bot, unsigned& prev_g,
+                                              const float4* __restrict__ RA0, const float* __restrict__ RB0,
+                                              const float4* __restrict__ RA1, const float* __restrict__ RB1, float2 fl,
+                                              int x, int y, unsigned yw, unsigned w, unsigned h) {
+  const unsigned o = yw + (unsigned)x;
+  P.a0 = __ldg(RA0 + o);
+  P.b0 = __ldg(RB0 + o);
+  P.dx = fl.x;
+  P.dy = fl.y;
+  const float fx = (float)x + fl.x, fy = (float)y + fl.y;
+  const int ix = __float2int_rd(fx), iy = __float2int_rd(fy);
+  P.fx = fx - (float)ix;
+  P.fy = fy - (float)iy;
+  P.inside = (unsigned)ix < w - 1u && (unsigned)iy < h - 1u;
+  const unsigned g = P.inside ? (unsigned)iy * w + (unsigned)ix : 0u;
+  P.g = g;
+  const float4* pa = RA1 + g;
+  const float* pb = RB1 + g;
+  if (g != prev_g + w) {     // (prev_g = ~0u - w after an outside pixel: never equal, g < 2^31)
+    top.q0 = __ldg(pa);
+    top.q1 = __ldg(pa + 1);
+    top.s0 = __ldg(pb);
+    top.s1 = __ldg(pb + 1);
+  }
+  bot.q0 = __ldg(pa + w);
+  bot.q1 = __ldg(pa + w + 1);
+  bot.s0 = __ldg(pb + w);
+  bot.s1 = __ldg(pb + w + 1);
+  prev_g = P.inside ? g : ~0u - w;
+}
+
+__device__ __forceinline__ M5 um_finish_rows(const UmPix& P, const UmRow& top, const UmRow& bot, bool border, int x,
+                                             int y, int w, int h) {
+  const float fx = P.fx, fy = P.fy;
+  const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+  float r2 = a00 * top.q0.x + a01 * top.q1.x + a10 * bot.q0.x + a11 * bot.q1.x;
+  float r3 = a00 * top.q0.y + a01 * top.q1.y + a10 * bot.q0.y + a11 * bot.q1.y;
+  float r4 = a00 * top.q0.z + a01 * top.q1.z + a10 * bot.q0.z + a11 * bot.q1.z;
+  float r5 = a00 * top.q0.w + a01 * top.q1.w + a10 * bot.q0.w + a11 * bot.q1.w;
+  float r6 = a00 * top.s0 + a01 * top.s1 + a10 * bot.s0 + a11 * bot.s1;
+  if (P.inside) {
+    r4 = (P.a0.z + r4) * 0.5f;
+    r5 = (P.a0.w + r5) * 0.5f;
+    r6 = (P.b0 + r6) * 0.25f;
+  } else {
+    r2 = r3 = 0.f;
+    r4 = P.a0.z;
+    r5 = P.a0.w;
+    r6 = P.b0 * 0.5f;
+  }
+  r2 = (P.a0.x - r2) * 0.5f;
+  r3 = (P.a0.y - r3) * 0.5f;
+  r2 += r4 * P.dy + r6 * P.dx;
+  r3 += r6 * P.dy + r5 * P.dx;
+  if (border) {
+    const float s = border_w(x, w) * border_w(y, h);
+    r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+  }
+  M5 m;
+  m.g11 = r4 * r4 + r6 * r6;
+  m.g12 = (r4 + r5) * r6;
+  m.g22 = r5 * r5 + r6 * r6;
+  m.h1 = r4 * r2 + r6 * r3;
+  m.h2 = r6 * r2 + r5 * r3;
+  return m;
+}
+
 // sums are unscaled window sums; reg = 1e-3 / scale^2 (scale = winsize^-2 folded into the regulariser)
 __device__ __forceinline__ float2 solve2x2_sums(float g11, float g12, float g22, float h1, float h2, float reg) {
   const float idet = rcp_approx(g11 * g22 - g12 * g12 + reg);

@@ -140,7 +140,23 @@ __global__ void k_sel_final(const uint32_t* __restrict__ sel, const double* __re
   median_out[i] = cnt ? (a + b) * 0.5f : __uint_as_float(0x7fc00000u);
 }
 
-int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mean, float* out_median) {
+int finish_pending_stats(ofb_handle* h) {
+  if (h->pending_stats.empty()) return OFB_OK;
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (const auto& ps : h->pending_stats) {
+    const char* slot = h->h_stats + (size_t)ps.slot * h->max_batch * 16;
+    const double* hm = reinterpret_cast<const double*>(slot);
+    const float* hd = reinterpret_cast<const float*>(slot + (size_t)h->max_batch * 8);
+    for (int i = 0; i < ps.n; i++) {
+      if (ps.out_mean) ps.out_mean[i] = hm[i];
+      if (ps.out_median) ps.out_median[i] = hd[i];
+    }
+  }
+  h->pending_stats.clear();
+  return OFB_OK;
+}
+
+int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mean, float* out_median, bool async) {
   if (!h->last_flow || n < 1 || n > h->last_n)
     return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_u_stats: no flow field of %d pair(s) on the device", n);
   OFB_CUDA(h, cudaSetDevice(h->device));
@@ -168,17 +184,16 @@ int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mea
   k_sel_final<<<(n + 127) / 128, 128, 0, st>>>(h->d_sel, sums, mean_d, med_d, n);
   OFB_LAUNCH_CHECK(h);
   if ((s = timing_end(h))) return s;
-  // results: n doubles + n floats through the pinned staging buffer
-  double* hm = reinterpret_cast<double*>(h->h_flow);
-  float* hd = reinterpret_cast<float*>(hm + n);
-  OFB_CUDA(h, cudaMemcpyAsync(hm, mean_d, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  OFB_CUDA(h, cudaMemcpyAsync(hd, med_d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-  OFB_CUDA(h, cudaStreamSynchronize(st));
-  for (int i = 0; i < n; i++) {
-    if (out_mean) out_mean[i] = hm[i];
-    if (out_median) out_median[i] = hd[i];
-  }
-  return OFB_OK;
+  // results: n doubles + n floats through a pinned slot; the caller's arrays are filled once the stream
+  // has got there (right away for the synchronous call, in ofb_wait for the asynchronous one)
+  if ((int)h->pending_stats.size() >= kStatSlots && (s = finish_pending_stats(h))) return s;
+  const int slot_i = h->stats_slot;
+  h->stats_slot = (h->stats_slot + 1) % kStatSlots;
+  char* slot = h->h_stats + (size_t)slot_i * h->max_batch * 16;
+  OFB_CUDA(h, cudaMemcpyAsync(slot, mean_d, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  OFB_CUDA(h, cudaMemcpyAsync(slot + (size_t)h->max_batch * 8, med_d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  h->pending_stats.push_back({out_mean, out_median, n, slot_i});
+  return async ? OFB_OK : finish_pending_stats(h);
 }
 
 }  // namespace ofb

@@ -40,6 +40,7 @@ class FlowEngine:
         self._h = h
         self.max_width, self.max_height, self.max_batch, self.device = max_width, max_height, max_batch, device
         self._lock = threading.Lock()
+        self._pending = []   # arrays the library still writes into (asynchronous reductions), released by wait()
 
     # -- lifetime
     def close(self):
@@ -151,7 +152,9 @@ class FlowEngine:
 
     def wait(self):
         """Block until everything enqueued by the asynchronous calls has finished (ofb_wait)."""
-        _lib.check(self._lib.ofb_wait(self._h), self._h)
+        with self._lock:
+            _lib.check(self._lib.ofb_wait(self._h), self._h)
+            self._pending.clear()
 
     def farneback_batch_into(self, prevs: np.ndarray, nexts: np.ndarray, out: np.ndarray, wait: bool = True,
                              **kw) -> np.ndarray:
@@ -177,9 +180,13 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out
 
-    def farneback_batch_stats(self, prevs: np.ndarray, nexts: np.ndarray, mask: Optional[np.ndarray] = None, **kw):
+    def farneback_batch_stats(self, prevs: np.ndarray, nexts: np.ndarray, mask: Optional[np.ndarray] = None,
+                              wait: bool = True, **kw):
         """The node contract in one call: flow of n pairs (uint8 [n,H,W] each) reduced on the device to
-        (mean_u [n] float64, median_u [n] float32); the field itself is not downloaded."""
+        (mean_u [n] float64, median_u [n] float32); the field itself is not downloaded.
+        ``wait=False`` (page-locked frames) returns as soon as the work is enqueued
+        (ofb_farneback_batch_stats_async): the two returned arrays are filled by :meth:`wait`, and successive
+        calls pipeline across calls — keep the frames untouched until then."""
         n, hgt, wid = prevs.shape
         if (nexts.shape != prevs.shape or prevs.dtype != np.uint8 or nexts.dtype != np.uint8
                 or not (prevs.flags.c_contiguous and nexts.flags.c_contiguous)):
@@ -190,18 +197,26 @@ class FlowEngine:
         ist = hgt * wid
         pp = (C.c_void_p * n)(*[prevs.ctypes.data + i * ist for i in range(n)])
         nn = (C.c_void_p * n)(*[nexts.ctypes.data + i * ist for i in range(n)])
-        mean = (C.c_double * n)()
-        med = (C.c_float * n)()
         mptr = None
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.uint8)
             if mask.shape != (hgt, wid):
                 raise OfbError(1, "mask must be uint8 [H,W]")
             mptr = mask.ctypes.data
+        mean = np.zeros(n, np.float64)
+        med = np.zeros(n, np.float32)
         with self._lock:
-            st = self._lib.ofb_farneback_batch_stats(self._h, n, pp, nn, wid, hgt, wid, C.byref(p), mptr, mean, med)
+            if wait:
+                st = self._lib.ofb_farneback_batch_stats(self._h, n, pp, nn, wid, hgt, wid, C.byref(p), mptr,
+                                                         mean.ctypes.data_as(C.POINTER(C.c_double)),
+                                                         med.ctypes.data_as(C.POINTER(C.c_float)))
+            else:
+                # the library writes into these arrays at ofb_wait: keep them (and the frames) alive until then
+                self._pending.append((mean, med, prevs, nexts))
+                st = self._lib.ofb_farneback_batch_stats_async(self._h, n, pp, nn, wid, hgt, wid, C.byref(p), mptr,
+                                                               mean.ctypes.data, med.ctypes.data)
             _lib.check(st, self._h)
-        return np.array(mean[:], np.float64), np.array(med[:], np.float32)
+        return mean, med
 
     def farneback_device(self, n: int, d_prev: int, d_next: int, width: int, height: int, pitch: int,
                          image_stride: int, d_flow: int, sequence: bool = False, **kw):

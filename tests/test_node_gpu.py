@@ -127,3 +127,31 @@ def test_batch_stats_matches_numpy(built_lib):
             assert med[i] == np.float32(np.median(u))
     finally:
         eng.close()
+
+
+def test_batch_stats_async_pipelines_across_calls(built_lib):
+    """ofb_farneback_batch_stats_async: several reductions in flight on page-locked frames, results handed over
+    by ofb_wait, equal to the synchronous call's (and to numpy on the downloaded field)."""
+    import torch
+    import opticalflowcontainer_b200 as ofb
+    n, h, w = 3, 200, 264
+    eng = ofb.FlowEngine(w, h, n, 0)
+    try:
+        sets = []
+        for s in range(6):       # more calls than the library keeps pending slots for
+            prs = [synth.synth_pair(h, w, 80 + 10 * s + i, (1.1 + 0.6 * i + 0.2 * s, 0.4 * i - 0.3 * s)) for i in range(n)]
+            a = torch.from_numpy(np.stack([p[0] for p in prs])).pin_memory()
+            b = torch.from_numpy(np.stack([p[1] for p in prs])).pin_memory()
+            sets.append((a, b))
+        sync = [eng.farneback_batch_stats(a.numpy(), b.numpy()) for a, b in sets]
+        pend = [eng.farneback_batch_stats(a.numpy(), b.numpy(), wait=False) for a, b in sets]
+        eng.wait()
+        for (m0, d0), (m1, d1) in zip(sync, pend):
+            assert np.array_equal(m0, m1) and np.array_equal(d0, d1)
+        # pageable frames through the async entry point are served synchronously
+        a, b = sets[0]
+        m2, d2 = eng.farneback_batch_stats(a.numpy().copy(), b.numpy().copy(), wait=False)
+        assert np.array_equal(m2, sync[0][0]) and np.array_equal(d2, sync[0][1])
+        eng.wait()
+    finally:
+        eng.close()
