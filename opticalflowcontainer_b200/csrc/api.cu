@@ -237,6 +237,8 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     if (iw) h->iter_waves = std::max(1, atoi(iw));
     const char* pt = getenv("OFB_POLYEXP_TILE");
     h->polyexp_tile = pt && pt[0] == '1';
+    const char* pf = getenv("OFB_PYR_FAST");
+    h->no_pyr_fast = pf && pf[0] == '0';
     const char* nf = getenv("OFB_NO_FUSED_SRC");
     h->no_fused_src = nf && nf[0] == '1';
     const char* pw = getenv("OFB_PX_WAVES");

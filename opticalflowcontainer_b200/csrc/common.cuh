@@ -80,6 +80,7 @@ struct ofb_handle {
   int iter_reuse = 1;      // OFB_ITER_REUSE=0: full 2x2 gather for every pixel (no row reuse between consecutive rows)
   int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
   bool polyexp_tile = false;   // OFB_POLYEXP_TILE=1: 32x32-tile PolyExp kernel instead of the marching one
+  bool no_pyr_fast = false;    // OFB_PYR_FAST=0: two-pass pyramid kernels also for the regular power-of-two levels
   bool no_fused_src = false;   // OFB_NO_FUSED_SRC=1: level-0 pyramid stage as separate kernels
   int px_waves = 4;            // OFB_PX_WAVES: target CTA waves of the marching PolyExp kernel
   // host-buffer pipeline: copy-in / copy-out streams and their events (api.cu)

@@ -553,7 +553,32 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
     // identity resize) the pyramid stage is fused into it and the level image never exists in HBM.
     const bool march = pc.n <= PX_MAXN && !h->polyexp_tile;
     const bool fused_src = march && w == width && hh == height && pyc.r == 1 && !h->no_fused_src;
-    if (!fused_src) {
+    // regular power-of-two level (fb_pyramid.cuh, k_pyr_fast): one kernel, source read once
+    int fastS = 0;
+    if (!fused_src && !h->no_pyr_fast && (width & 3) == 0 && (pitch & 3) == 0 && (image_stride & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(src.a) & 3) == 0 && (reinterpret_cast<uintptr_t>(src.b) & 3) == 0) {
+      for (int S = 2; S <= 8; S *= 2)
+        if (w * S == width && hh * S == height && pyc.r == (S == 2 ? 1 : (S == 4 ? 4 : 9))) fastS = S;
+    }
+    if (fastS) {
+      TB(OFB_STAGE_PYRAMID);
+      PyrFastCoef fc;
+      memset(&fc, 0, sizeof(fc));
+      for (int j = 1; j <= pyc.r + 1; j++) fc.c[j - 1] = 0.5f * (pyc.k[j - 1] + (j <= pyc.r ? pyc.k[j] : 0.f));
+      const int out_per = (PF_COLS - 2 * PF_HALO) / fastS;
+      const int chunks = (w + out_per - 1) / out_per;
+      // resident CTAs per SM by register use: 8 (S=2, 32 regs), 4 (S=4), 3 (S=8); two waves of short segments hide
+      // the per-row barrier better than one wave of long ones
+      const int per_sm = fastS == 2 ? 8 : (fastS == 4 ? 4 : 3);
+      const int segs = std::max(1, 2 * per_sm * h->num_sms / (chunks * frames));
+      const int seg_rows = std::max(4, (hh + segs - 1) / segs);
+      dim3 g(chunks, (hh + seg_rows - 1) / seg_rows, frames);
+      if (fastS == 2) k_pyr_fast<2, 1><<<g, PF_THREADS, 0, st>>>(src, width, height, h->d_img, w, hh, fc, seg_rows);
+      else if (fastS == 4) k_pyr_fast<4, 4><<<g, PF_THREADS, 0, st>>>(src, width, height, h->d_img, w, hh, fc, seg_rows);
+      else k_pyr_fast<8, 9><<<g, PF_THREADS, 0, st>>>(src, width, height, h->d_img, w, hh, fc, seg_rows);
+      OFB_LAUNCH_CHECK(h);
+      TE();
+    } else if (!fused_src) {
       TB(OFB_STAGE_PYRAMID);
       // pass H writes hb[frames][H][w] into d_MA (free here: the generic iteration path only uses it
       // after the pyramid stage of the level), pass V writes the level image.

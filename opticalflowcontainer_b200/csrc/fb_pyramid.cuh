@@ -176,4 +176,119 @@ __global__ void __launch_bounds__(256) k_pyr_v(const float* __restrict__ hb, int
   out[((size_t)blockIdx.z * h + y) * w + x] = v0 * (1.f - fy) + v1 * fy;
 }
 
+// =====================================================================================
+// Fast pyramid stage for the regular case: W = S * w_l, H = S * h_l with S = 2, 4, 8 (pyr_scale = 0.5, frame size
+// divisible by S) and W, pitch multiples of 4.  Every level pixel then samples the blurred image exactly half-way
+// between two source pixels in x and in y (fx = fy = 0.5), so blur + bilinear resize collapse into ONE symmetric
+// even-length filter per axis:
+//     I[y][x] = sum_{j=1..R+1} c[j] * ( T[cy - (j-1)][.] + T[cy + 1 + (j-1)][.] ),   cy = S*y + S/2 - 1,
+//     c[j] = 0.5 * (k[j-1] + k[j])   (k = cv2's Gaussian half kernel, k[R+1] = 0)
+// and the same along x.  Vertical pass first, on the u8 source: a thread owns 4 adjacent source columns (one 32-bit
+// word per row), keeps the 2R+2 rows of the window in registers split into even/odd byte lanes, adds the two rows
+// of a tap pair as packed 16-bit integers (exact) and converts each sum once (PRMT into 2^23 + s, FADD) — one
+// conversion and one FMA per TWO taps, where the two-pass kernels above spend a conversion and two FMAs per tap.
+// The 4 floats go to a shared-memory row (skewed so that the stride-S reads of the horizontal pass are
+// conflict-free); after one barrier the first OUT threads apply the same filter along x and store the level row.
+// HBM traffic per frame-level: N (u8, read once; the halo columns are L2 hits) + 4 n_l.
+constexpr int PF_THREADS = 256;
+constexpr int PF_COLS = 4 * PF_THREADS;   // source columns per CTA
+constexpr int PF_HALO = 8;                // halo columns per side (>= R + 1 - S/2 for the three instantiations)
+struct PyrFastCoef { float c[10]; };      // c[j-1] for tap pair j = 1..R+1
+
+__device__ __forceinline__ int pf_skew(int x) { return x + (x >> 5); }
+
+template <int S, int R>
+__global__ void __launch_bounds__(PF_THREADS) k_pyr_fast(FrameSrc src, int W, int H, float* __restrict__ out, int w, int h,
+                                                         PyrFastCoef pc, int seg_rows) {
+  constexpr int WIN = 2 * R + 2;
+  constexpr int OUT = (PF_COLS - 2 * PF_HALO) / S;      // level columns per CTA (even)
+  static_assert(S / 2 - 1 - R + PF_HALO >= 0 && S / 2 + R - (S - 1) <= PF_HALO, "halo too small");
+  __shared__ float rowbuf[2][PF_COLS + PF_COLS / 32 + 1];
+  const int tid = threadIdx.x;
+  const int xo0 = blockIdx.x * OUT;                     // first level column of the chunk
+  const int x = S * xo0 - PF_HALO + 4 * tid;            // first of this thread's 4 source columns (multiple of 4)
+  const int y0 = blockIdx.y * seg_rows, y1 = min(y0 + seg_rows, h);
+  const uint8_t* frame = src.frame(blockIdx.z);
+  const bool interior = x >= 0 && x + 3 < W;
+  const bool dead = x > S * (w - 1) + S / 2 + R;        // right of everything a level column of this frame reads
+  // the four source columns of a thread at the image border, REFLECT_101
+  const int bx0 = reflect101(x, W), bx1 = reflect101(x + 1, W), bx2 = reflect101(x + 2, W), bx3 = reflect101(x + 3, W);
+  const bool fastcol = interior && !dead;
+  auto load_row = [&](int ry) -> unsigned {             // source row ry (any integer: reflected)
+    if (fastcol && (unsigned)ry < (unsigned)H)
+      return __ldg(reinterpret_cast<const unsigned*>(frame + (size_t)ry * src.pitch + x));
+    const uint8_t* p = frame + (size_t)reflect101(ry, H) * src.pitch;
+    if (dead) return 0u;
+    if (interior) return __ldg(reinterpret_cast<const unsigned*>(p + x));
+    return (unsigned)__ldg(p + bx0) | ((unsigned)__ldg(p + bx1) << 8) | ((unsigned)__ldg(p + bx2) << 16) |
+           ((unsigned)__ldg(p + bx3) << 24);
+  };
+  // window rows cy - R .. cy + R + 1 as even / odd byte lanes (16 bits per lane)
+  unsigned we[WIN], wo[WIN];
+  {
+    const int top = S * y0 + S / 2 - 1 - R;
+#pragma unroll
+    for (int i = S; i < WIN; i++) {                     // rows the first step keeps; its S newest rows come as `nx`
+      const unsigned v = load_row(top + i - S);
+      we[i] = v & 0x00FF00FFu;
+      wo[i] = (v >> 8) & 0x00FF00FFu;
+    }
+  }
+  // the S rows entering the window at a step: one address computation and S word loads for interior threads on
+  // interior rows (the generic path costs ~60 instructions per row: reflection loop, border bytes)
+  const size_t pitch_w = src.pitch >> 2;
+  auto load_group = [&](int first, unsigned (&dst)[S]) {
+    if (fastcol && first >= 0 && first + S <= H) {
+      const unsigned* p = reinterpret_cast<const unsigned*>(frame + (size_t)first * src.pitch + x);
+#pragma unroll
+      for (int i = 0; i < S; i++) dst[i] = __ldg(p + (size_t)i * pitch_w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < S; i++) dst[i] = load_row(first + i);
+    }
+  };
+  unsigned nx[S];
+  load_group(S * y0 + S / 2 - 1 - R + WIN - S, nx);
+
+  for (int y = y0; y < y1; y++) {
+    // slide the window down by S rows: the S newest rows were loaded one step ahead
+#pragma unroll
+    for (int i = 0; i < WIN - S; i++) { we[i] = we[i + S]; wo[i] = wo[i + S]; }
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      we[WIN - S + i] = nx[i] & 0x00FF00FFu;
+      wo[WIN - S + i] = (nx[i] >> 8) & 0x00FF00FFu;
+    }
+    if (y + 1 < y1) load_group(S * (y + 1) + S / 2 - 1 - R + WIN - S, nx);
+    // vertical filter of the 4 columns
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int j = 1; j <= R + 1; j++) {
+      const unsigned e = we[R + 1 - j] + we[R + j];     // columns 0 and 2 (two 9-bit sums in 16-bit lanes)
+      const unsigned o = wo[R + 1 - j] + wo[R + j];     // columns 1 and 3
+      const float c = pc.c[j - 1];
+      a0 = fmaf(c, __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7610)) - 8388608.f, a0);
+      a2 = fmaf(c, __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7632)) - 8388608.f, a2);
+      a1 = fmaf(c, __uint_as_float(__byte_perm(o, 0x4B000000u, 0x7610)) - 8388608.f, a1);
+      a3 = fmaf(c, __uint_as_float(__byte_perm(o, 0x4B000000u, 0x7632)) - 8388608.f, a3);
+    }
+    float* rb = rowbuf[y & 1];
+    const int q = pf_skew(4 * tid);                     // 4*tid .. 4*tid+3 share one 32-group: contiguous after the skew
+    rb[q] = a0; rb[q + 1] = a1; rb[q + 2] = a2; rb[q + 3] = a3;
+    __syncthreads();                                    // (double-buffered: one barrier per level row)
+    // horizontal filter: level column xo0 + i needs chunk columns PF_HALO + S*i + S/2 - 1 - R .. + S/2 + R
+#pragma unroll
+    for (int i = tid; i < OUT; i += PF_THREADS) {
+      const int xo = xo0 + i;
+      if (xo < w) {
+        const int cl = PF_HALO + S * i + S / 2 - 1;     // chunk column of the left centre tap
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 1; j <= R + 1; j++) acc = fmaf(pc.c[j - 1], rb[pf_skew(cl - (j - 1))] + rb[pf_skew(cl + j)], acc);
+        out[((size_t)blockIdx.z * h + y) * w + xo] = acc;
+      }
+    }
+  }
+}
+
 }  // namespace ofb
