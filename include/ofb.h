@@ -229,6 +229,19 @@ int ofb_timing_read_samples(ofb_handle* h, int stage, double* ms_out, int capaci
  * out_mean / out_median: n values (u component); either may be NULL. */
 int ofb_flow_u_stats(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median);
 
+/* The "adapt" node's flow post-processing, on the device, applied to the field(s) of the last flow call on this
+ * handle (replaces ros2_ws/src/liteflownet3/liteflownet3/lfn3_adapt_node.py:236-251):
+ *   median_ksize 3 | 5 : u = cv2.medianBlur(u, k), v = cv2.medianBlur(v, k)   (0 = off; float32 fields allow 3 and 5)
+ *   magnitude_threshold >= 0 : u, v *= (sqrt(u*u + v*v) >= threshold)         (negative = off)
+ *   gray != NULL : u, v *= (gray < intensity_threshold); gray = n host uint8 [height][gray_stride_bytes] images
+ * in that order, bit-exact against cv2 / NumPy float32.  The filtered field replaces the handle's current field:
+ * ofb_flow_u_stats (np.mean(u), :254) and ofb_flow_download see it.  Asynchronous on the handle's stream. */
+int ofb_flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_threshold, const uint8_t* const* gray,
+                        size_t gray_stride_bytes, int intensity_threshold);
+/* Copies the handle's current field(s) (the last flow result, post-filtered or not) to n host float32
+ * [height][width][2] arrays (flow_stride_bytes = 0: packed rows).  Synchronous. */
+int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes);
+
 /* ---- frame ingest (the step in front of the flow call: lfn3_sub_node.py:148-159) --------------
  * cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) / COLOR_RGB2GRAY on an interleaved 8-bit 3-channel frame
  * (sensor_msgs/Image bgr8 / rgb8 with row `step`), bit-exact with cv2's 15-bit fixed-point formula.

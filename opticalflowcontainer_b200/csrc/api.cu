@@ -166,6 +166,7 @@ int ofb_destroy(ofb_handle* h) {
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
   if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->d_gray) cudaFree(h->d_gray);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->tile.imported && !h->tile.same_process) {
     for (int r = 0; r < h->tile.world; r++) {
@@ -655,6 +656,17 @@ int ofb_farneback(ofb_handle* h, const uint8_t* prev, const uint8_t* next, int w
   const uint8_t* nn[1] = {next};
   float* ff[1] = {flow};
   return ofb_farneback_batch(h, 1, pp, nn, width, height, stride_bytes, ff, flow_stride_bytes, params);
+}
+
+int ofb_flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_threshold, const uint8_t* const* gray,
+                        size_t gray_stride_bytes, int intensity_threshold) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  return flow_postfilter(h, n, median_ksize, magnitude_threshold, gray, gray_stride_bytes, intensity_threshold);
+}
+
+int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  return flow_download(h, n, flow, flow_stride_bytes);
 }
 
 int ofb_flow_u_stats(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median) {

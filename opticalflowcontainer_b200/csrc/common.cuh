@@ -132,6 +132,8 @@ struct ofb_handle {
   double* d_stats = nullptr;
   uint32_t* d_sel = nullptr;   // radix-select state of ofb_flow_u_stats (reduce.cu)
   uint8_t* d_mask = nullptr;
+  uint8_t* d_gray = nullptr;   // gray frames of the intensity mask (ofb_flow_postfilter), allocated on first use
+  size_t gray_bytes = 0;
   float* d_scratch = nullptr;  // median selection scratch
   // asynchronous reductions (ofb_farneback_batch_stats_async): results land in pinned slots and are handed
   // to the caller's arrays by ofb_wait
@@ -205,7 +207,11 @@ int farneback_run_tiled_emulated(ofb_handle* const* hs, int world, const uint8_t
 
 constexpr int kStatSlots = 4;   // reductions in flight before ofb_farneback_batch_stats_async drains them itself
 int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mean, float* out_median, bool async = false);
-int finish_pending_stats(ofb_handle* h);   // synchronises the stream, copies staged scalars to the callers' arrays
+int finish_pending_stats(ofb_handle* h);
+// ---- postfilter.cu
+int flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_threshold, const uint8_t* const* gray,
+                    size_t gray_stride, int intensity_threshold);
+int flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes);   // synchronises the stream, copies staged scalars to the callers' arrays
 
 // ---- sparse ---------------------------------------------------------------------------
 void sparse_destroy(ofb_handle* h);

@@ -1,0 +1,178 @@
+// postfilter.cu — the "adapt" node's flow post-processing on the device (SURVEY.md 8f rank 3 / rank 1 masks).
+//
+// ros2_ws/src/liteflownet3/liteflownet3/lfn3_adapt_node.py:
+//   :236-238  flow[c] = cv2.medianBlur(flow[c], k)              k = 3 | 5, float32, BORDER_REPLICATE, exact selection
+//   :241-244  m = sqrt(u*u + v*v) >= threshold ; u *= m ; v *= m   (float32, every operation rounded: no FMA)
+//   :247-251  m = gray < intensity_threshold   ; u *= m ; v *= m
+// followed by np.mean(u) (:254), which ofb_flow_u_stats computes on the result.  One kernel, one pass: 8 B in,
+// 8 B out per pixel (+1 B gray), the field never leaves HBM.  Bit-exact against cv2 / NumPy (signed zeros aside).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ofb {
+
+// moves the minimum of a[0..M) to a[0] and the maximum to a[M-1]
+template <int M, int CAP>
+__device__ __forceinline__ void extract_minmax(float (&a)[CAP]) {
+#pragma unroll
+  for (int i = 0; i < M / 2; i++) {
+    const float lo = fminf(a[i], a[M - 1 - i]), hi = fmaxf(a[i], a[M - 1 - i]);
+    a[i] = lo; a[M - 1 - i] = hi;
+  }
+#pragma unroll
+  for (int i = 1; i < (M + 1) / 2; i++) {
+    const float lo = fminf(a[0], a[i]), hi = fmaxf(a[0], a[i]);
+    a[0] = lo; a[i] = hi;
+  }
+#pragma unroll
+  for (int i = M / 2; i < M - 1; i++) {
+    const float lo = fminf(a[i], a[M - 1]), hi = fmaxf(a[i], a[M - 1]);
+    a[i] = lo; a[M - 1] = hi;
+  }
+}
+
+// Forgetful selection of the median of N = 2*W0 - 3 values: keep W0 = N/2 + 2 candidates, discard their minimum and
+// maximum (neither can be the median), take the next value in, until three are left.
+template <int M, int W0, int N>
+__device__ __forceinline__ float forget(float (&a)[W0], const float (&v)[N]) {
+  extract_minmax<M, W0>(a);
+  if constexpr (M == 3) {
+    return a[1];
+  } else {
+    a[0] = v[2 * W0 - M];          // replaces the minimum; the maximum a[M-1] drops out with the smaller M
+    return forget<M - 1, W0, N>(a, v);
+  }
+}
+
+template <int K>
+__device__ __forceinline__ float median_kk(const float (&v)[K * K]) {
+  constexpr int N = K * K, W0 = N / 2 + 2;
+  float a[W0];
+#pragma unroll
+  for (int i = 0; i < W0; i++) a[i] = v[i];
+  return forget<W0, W0, N>(a, v);
+}
+
+constexpr int PFX = 32, PFY = 8;
+
+// K = 0: masks only.  gray (optional): n images [h][gray_pitch] on the device.
+template <int K>
+__global__ void __launch_bounds__(PFX* PFY) k_flow_postfilter(const float2* __restrict__ in, float2* __restrict__ out, int w,
+                                                              int h, bool use_mag, float mag_thr,
+                                                              const uint8_t* __restrict__ gray, size_t gray_pitch,
+                                                              int intensity_thr) {
+  constexpr int R = K / 2;
+  __shared__ float2 tile[PFY + 2 * R][PFX + 2 * R];
+  const size_t n = (size_t)w * h;
+  const float2* f = in + (size_t)blockIdx.z * n;
+  const int bx = blockIdx.x * PFX, by = blockIdx.y * PFY;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (K > 0) {
+    for (int i = ty * PFX + tx; i < (PFY + 2 * R) * (PFX + 2 * R); i += PFX * PFY) {
+      const int ry = i / (PFX + 2 * R), rx = i - ry * (PFX + 2 * R);
+      const int sy = min(max(by + ry - R, 0), h - 1), sx = min(max(bx + rx - R, 0), w - 1);   // BORDER_REPLICATE
+      tile[ry][rx] = __ldg(f + (size_t)sy * w + sx);
+    }
+    __syncthreads();
+  }
+  const int x = bx + tx, y = by + ty;
+  if (x >= w || y >= h) return;
+  float u, v;
+  if constexpr (K > 0) {
+    float a[K * K > 0 ? K * K : 1];
+#pragma unroll
+    for (int j = 0; j < K; j++)
+#pragma unroll
+      for (int i = 0; i < K; i++) a[j * K + i] = tile[ty + j][tx + i].x;
+    u = median_kk<K>(a);
+#pragma unroll
+    for (int j = 0; j < K; j++)
+#pragma unroll
+      for (int i = 0; i < K; i++) a[j * K + i] = tile[ty + j][tx + i].y;
+    v = median_kk<K>(a);
+  } else {
+    const float2 t = __ldg(f + (size_t)y * w + x);
+    u = t.x; v = t.y;
+  }
+  if (use_mag) {
+    const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
+    const float m = mag >= mag_thr ? 1.f : 0.f;
+    u = __fmul_rn(u, m); v = __fmul_rn(v, m);
+  }
+  if (gray) {
+    const float m = (int)gray[(size_t)blockIdx.z * gray_pitch * h + (size_t)y * gray_pitch + x] < intensity_thr ? 1.f : 0.f;
+    u = __fmul_rn(u, m); v = __fmul_rn(v, m);
+  }
+  out[(size_t)blockIdx.z * n + (size_t)y * w + x] = make_float2(u, v);
+}
+
+int flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_threshold, const uint8_t* const* gray,
+                    size_t gray_stride, int intensity_threshold) {
+  if (!h->last_flow || n < 1 || n > h->last_n)
+    return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_postfilter: no flow field of %d pair(s) on the device", n);
+  if (median_ksize != 0 && median_ksize != 3 && median_ksize != 5)
+    return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_postfilter: median_ksize must be 0, 3 or 5 (cv2.medianBlur, float32)");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int w = h->last_w, hh = h->last_h;
+  const size_t npix = (size_t)w * hh;
+  const uint8_t* dgray = nullptr;
+  const size_t gpitch = ((size_t)w + 15) & ~(size_t)15;
+  if (gray) {
+    if (gray_stride == 0) gray_stride = (size_t)w;
+    if (gray_stride < (size_t)w) return set_error(h, OFB_ERR_INVALID_ARG, "gray stride smaller than width");
+    for (int i = 0; i < n; i++)
+      if (!gray[i]) return set_error(h, OFB_ERR_INVALID_ARG, "NULL gray image");
+    const size_t need = gpitch * hh * (size_t)n;
+    if (need > h->gray_bytes) {
+      OFB_CUDA(h, cudaStreamSynchronize(st));
+      if (h->d_gray) cudaFree(h->d_gray);
+      h->d_gray = nullptr; h->gray_bytes = 0;
+      OFB_CUDA(h, cudaMalloc(&h->d_gray, need));
+      h->gray_bytes = need;
+    }
+    for (int i = 0; i < n; i++)
+      OFB_CUDA(h, cudaMemcpy2DAsync(h->d_gray + (size_t)i * gpitch * hh, gpitch, gray[i], gray_stride, w, hh,
+                                    cudaMemcpyHostToDevice, st));
+    dgray = h->d_gray;
+  }
+  // the result goes to one of the level ping-pong buffers (free between calls) and becomes the handle's field
+  float2* dst = reinterpret_cast<const float2*>(h->last_flow) == h->d_flow[0] ? h->d_flow[1] : h->d_flow[0];
+  const float2* srcf = reinterpret_cast<const float2*>(h->last_flow);
+  dim3 blk(PFX, PFY), g((w + PFX - 1) / PFX, (hh + PFY - 1) / PFY, n);
+  const bool use_mag = magnitude_threshold >= 0.f;
+  int s;
+  if ((s = timing_begin(h, OFB_STAGE_OTHER))) return s;
+  if (median_ksize == 3)
+    k_flow_postfilter<3><<<g, blk, 0, st>>>(srcf, dst, w, hh, use_mag, magnitude_threshold, dgray, gpitch, intensity_threshold);
+  else if (median_ksize == 5)
+    k_flow_postfilter<5><<<g, blk, 0, st>>>(srcf, dst, w, hh, use_mag, magnitude_threshold, dgray, gpitch, intensity_threshold);
+  else
+    k_flow_postfilter<0><<<g, blk, 0, st>>>(srcf, dst, w, hh, use_mag, magnitude_threshold, dgray, gpitch, intensity_threshold);
+  OFB_LAUNCH_CHECK(h);
+  if ((s = timing_end(h))) return s;
+  h->last_flow = reinterpret_cast<const float*>(dst);
+  (void)npix;
+  return OFB_OK;
+}
+
+int flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes) {
+  if (!h->last_flow || n < 1 || n > h->last_n)
+    return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_download: no flow field of %d pair(s) on the device", n);
+  if (!flow) return set_error(h, OFB_ERR_INVALID_ARG, "NULL array pointer");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  const int w = h->last_w, hh = h->last_h;
+  const size_t row = (size_t)w * 2 * sizeof(float);
+  if (flow_stride_bytes == 0) flow_stride_bytes = row;
+  if (flow_stride_bytes < row) return set_error(h, OFB_ERR_INVALID_ARG, "flow stride smaller than a row");
+  for (int i = 0; i < n; i++) {
+    if (!flow[i]) return set_error(h, OFB_ERR_INVALID_ARG, "NULL flow pointer");
+    OFB_CUDA(h, cudaMemcpy2DAsync(flow[i], flow_stride_bytes, h->last_flow + (size_t)i * w * hh * 2, row, row, hh,
+                                  cudaMemcpyDeviceToHost, h->stream));
+  }
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+}  // namespace ofb

@@ -249,6 +249,38 @@ class FlowEngine:
         return (list(om) if mean else None), (list(od) if median else None)
 
     # -- sparse
+    def flow_postfilter(self, n: int = 1, median_ksize: int = 0, magnitude_threshold: Optional[float] = None,
+                        gray: Optional[np.ndarray] = None, intensity_threshold: Optional[int] = None):
+        """The adapt node's post-processing (lfn3_adapt_node.py:236-251) of the last flow result, on the device:
+        ``cv2.medianBlur`` of u and v (ksize 3 | 5), magnitude threshold mask, intensity mask from ``gray``
+        (uint8 [H,W] or [n,H,W]).  The filtered field replaces the handle's current one (see
+        :meth:`flow_u_stats`, :meth:`flow_download`)."""
+        gp = None
+        stride = 0
+        if intensity_threshold is not None:
+            if gray is None:
+                raise OfbError(1, "intensity mask needs the gray frame(s)")
+            g = np.ascontiguousarray(gray, dtype=np.uint8)
+            if g.ndim == 2:
+                g = g[None]
+            if g.ndim != 3 or g.shape[0] < n:
+                raise OfbError(1, "gray must be uint8 [H,W] or [n,H,W]")
+            gp = (C.c_void_p * n)(*[g.ctypes.data + i * g.shape[1] * g.shape[2] for i in range(n)])
+            stride = g.shape[2]
+        with self._lock:
+            st = self._lib.ofb_flow_postfilter(self._h, n, int(median_ksize),
+                                               -1.0 if magnitude_threshold is None else float(magnitude_threshold),
+                                               gp, stride, 0 if intensity_threshold is None else int(intensity_threshold))
+            _lib.check(st, self._h)
+
+    def flow_download(self, n: int, height: int, width: int) -> np.ndarray:
+        """The handle's current field(s) as float32 [n,H,W,2] (ofb_flow_download)."""
+        out = np.empty((n, height, width, 2), np.float32)
+        pp = (C.c_void_p * n)(*[out.ctypes.data + i * height * width * 8 for i in range(n)])
+        with self._lock:
+            _lib.check(self._lib.ofb_flow_download(self._h, n, pp, 0), self._h)
+        return out
+
     def cvt_gray(self, frame, rgb: bool = False) -> np.ndarray:
         """cv2.cvtColor(frame, COLOR_BGR2GRAY) (or RGB2GRAY with ``rgb=True``) of a uint8 [H,W,3] frame on
         the device, bit-exact with cv2 (the ingest step of the nodes: lfn3_sub_node.py:148-159)."""

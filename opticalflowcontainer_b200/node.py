@@ -61,6 +61,10 @@ class FarnebackVelocityNode:
     poly_sigma: float = 1.2
     flags: int = 0
     on_device_reduce: bool = False
+    # the "adapt" node's post-processing of the field (lfn3_adapt_node.py:236-251), applied on the device when set
+    median_kernel_size: int = 0                       # 3 | 5: cv2.medianBlur of u and v
+    flow_magnitude_threshold: Optional[float] = None  # u, v *= (|flow| >= threshold)
+    intensity_threshold: Optional[int] = None         # u, v *= (gray < threshold)
     engine: Optional[FlowEngine] = None
     prev_gray: Optional[np.ndarray] = field(default=None, repr=False)
     prev_time: Optional[float] = None
@@ -86,6 +90,11 @@ class FarnebackVelocityNode:
         self.prev_time = stamp
         flow = self.engine.farneback(self.prev_gray, gray, None, self.pyr_scale, self.levels, self.winsize,
                                      self.iterations, self.poly_n, self.poly_sigma, self.flags)
+        if self.median_kernel_size or self.flow_magnitude_threshold is not None or self.intensity_threshold is not None:
+            self.engine.flow_postfilter(1, self.median_kernel_size, self.flow_magnitude_threshold,
+                                        gray if self.intensity_threshold is not None else None, self.intensity_threshold)
+            if not self.on_device_reduce:
+                flow = self.engine.flow_download(1, self.height, self.width)[0]
         self.last_flow = flow
         flow_np = np.transpose(flow, (2, 0, 1))      # [2,H,W] as the reference nodes consume it
         if self.on_device_reduce:

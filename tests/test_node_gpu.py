@@ -155,3 +155,59 @@ def test_batch_stats_async_pipelines_across_calls(built_lib):
         eng.wait()
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("k", [0, 3, 5])
+def test_flow_postfilter_bit_exact(engine_factory, k):
+    """ofb_flow_postfilter == the adapt node's medianBlur + magnitude mask + intensity mask
+    (lfn3_adapt_node.py:236-251) computed by cv2 / NumPy on the same field, bit for bit; odd sizes included."""
+    from oracle import postfilter_np
+    for (h, w) in [(120, 160), (67, 93)]:
+        eng = engine_factory(w, h)
+        a, b = synth.synth_pair(h, w, 31 + k, (2.3, -1.2))
+        flow = eng.farneback(a, b, None, 0.5, 2, 9, 2, 5, 1.1, 0)
+        flow[::7, ::5] *= -3.0                      # outliers for the median to remove (re-upload below)
+        # put the modified field on the device: run the filter on a field we control exactly
+        eng.farneback(a, b, flow.copy(), 0.5, 0, 9, 0, 5, 1.1, 4)   # iterations=0 + USE_INITIAL_FLOW: field = input
+        base = eng.flow_download(1, h, w)[0]
+        assert np.array_equal(base, flow)
+        rng = np.random.default_rng(9)
+        gray = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+        thr = float(np.median(np.hypot(flow[..., 0], flow[..., 1])))
+        eng.flow_postfilter(1, k, thr, gray, 128)
+        got = eng.flow_download(1, h, w)[0]
+        ref = postfilter_np.adapt_postfilter_np(flow, k, thr, gray, 128, use_cv2_median=True)
+        assert np.array_equal(got, ref)
+        mean, _ = eng.flow_u_stats(1, median=False)
+        assert abs(mean[0] - float(ref[..., 0].astype(np.float64).mean())) <= 1e-6
+        # median only / masks only
+        eng.farneback(a, b, flow.copy(), 0.5, 0, 9, 0, 5, 1.1, 4)
+        eng.flow_postfilter(1, k)
+        got = eng.flow_download(1, h, w)[0]
+        assert np.array_equal(got, postfilter_np.adapt_postfilter_np(flow, k, use_cv2_median=True))
+
+
+def test_adapt_node_contract(engine_factory):
+    """FarnebackVelocityNode with the adapt node's parameters: same velocity whether the post-filter + mean run
+    on the device or in NumPy/cv2 on the downloaded field."""
+    import cv2
+    from opticalflowcontainer_b200.node import FarnebackVelocityNode
+    h, w = 120, 160
+    frames = [synth.synth_pair(h, w, 77, (1.0 + 0.5 * i, 0.2))[1] for i in range(3)]
+    kw = dict(width=w, height=h, reduce="mean", median_kernel_size=5, flow_magnitude_threshold=0.3, intensity_threshold=140)
+    n_dev = FarnebackVelocityNode(engine=engine_factory(w, h), on_device_reduce=True, **kw)
+    n_ref = FarnebackVelocityNode(engine=engine_factory(w, h), width=w, height=h, reduce="mean")
+    for i, f in enumerate(frames):
+        out = n_dev.image_callback(f, 0.1 * i)
+        ref = n_ref.image_callback(f, 0.1 * i)
+        if i == 0:
+            assert out is None and ref is None
+            continue
+        fl = np.transpose(n_ref.last_flow, (2, 0, 1)).copy()
+        fl[0] = cv2.medianBlur(fl[0], 5); fl[1] = cv2.medianBlur(fl[1], 5)
+        m = (np.sqrt(fl[0] ** 2 + fl[1] ** 2) >= 0.3).astype(np.float32)
+        fl[0] *= m; fl[1] *= m
+        mi = (f < 140).astype(np.float32)
+        fl[0] *= mi
+        vx = float(np.mean(fl[0]) / 0.1 * 0.0011)
+        assert abs(out[0].vector[0] - vx) <= 1e-6 * max(1.0, abs(vx))
