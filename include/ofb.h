@@ -241,6 +241,11 @@ int ofb_flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_
 /* Copies the handle's current field(s) (the last flow result, post-filtered or not) to n host float32
  * [height][width][2] arrays (flow_stride_bytes = 0: packed rows).  Synchronous. */
 int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes);
+/* Flow of pair `pair` of the handle's current field at n integer pixel positions xy = [n][2] (x, y): out_dxdy =
+ * [n][2] float32 (dx, dy), NaN for positions outside the frame.  The junction node's lookup of the predicted
+ * junction positions (ros2_ws/src/liteflownet3/liteflownet3/lfn3_junction_node.py:207-214) without downloading the
+ * field.  Synchronous. */
+int ofb_flow_sample(ofb_handle* h, int pair, int n_points, const int* xy, float* out_dxdy);
 
 /* ---- frame ingest (the step in front of the flow call: lfn3_sub_node.py:148-159) --------------
  * cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) / COLOR_RGB2GRAY on an interleaved 8-bit 3-channel frame

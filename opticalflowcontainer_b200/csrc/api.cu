@@ -664,6 +664,11 @@ int ofb_flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_
   return flow_postfilter(h, n, median_ksize, magnitude_threshold, gray, gray_stride_bytes, intensity_threshold);
 }
 
+int ofb_flow_sample(ofb_handle* h, int pair, int n_points, const int* xy, float* out_dxdy) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  return flow_sample(h, pair, n_points, xy, out_dxdy);
+}
+
 int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes) {
   if (!h) return OFB_ERR_INVALID_ARG;
   return flow_download(h, n, flow, flow_stride_bytes);

@@ -157,6 +157,37 @@ int flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_thre
   return OFB_OK;
 }
 
+// flow at integer pixel positions (the junction node's lookup, lfn3_junction_node.py:207-214); outside -> NaN
+__global__ void k_flow_sample(const float2* __restrict__ f, int w, int h, const int2* __restrict__ pts, int n,
+                              float2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int2 p = pts[i];
+  const float nanv = __int_as_float(0x7fc00000);
+  out[i] = (p.x >= 0 && p.x < w && p.y >= 0 && p.y < h) ? f[(size_t)p.y * w + p.x] : make_float2(nanv, nanv);
+}
+
+int flow_sample(ofb_handle* h, int pair, int n_points, const int* xy, float* out_dxdy) {
+  if (!h->last_flow || pair < 0 || pair >= h->last_n)
+    return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_sample: no flow field %d on the device", pair);
+  if (n_points < 0 || (n_points > 0 && (!xy || !out_dxdy))) return set_error(h, OFB_ERR_INVALID_ARG, "bad point arrays");
+  if (n_points == 0) return OFB_OK;
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  // the points and their results share the mask buffer (>= 16 B per point available: npix bytes)
+  const size_t npix = (size_t)h->max_w * h->max_h;
+  if ((size_t)n_points * 16 > npix) return set_error(h, OFB_ERR_INVALID_ARG, "too many points (%d)", n_points);
+  int2* dp = reinterpret_cast<int2*>(h->d_mask);
+  float2* dout = reinterpret_cast<float2*>(h->d_mask + (size_t)n_points * 8);
+  OFB_CUDA(h, cudaMemcpyAsync(dp, xy, (size_t)n_points * 8, cudaMemcpyHostToDevice, h->stream));
+  k_flow_sample<<<(n_points + 127) / 128, 128, 0, h->stream>>>(
+      reinterpret_cast<const float2*>(h->last_flow) + (size_t)pair * h->last_w * h->last_h, h->last_w, h->last_h, dp,
+      n_points, dout);
+  OFB_LAUNCH_CHECK(h);
+  OFB_CUDA(h, cudaMemcpyAsync(out_dxdy, dout, (size_t)n_points * 8, cudaMemcpyDeviceToHost, h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
 int flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes) {
   if (!h->last_flow || n < 1 || n > h->last_n)
     return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_download: no flow field of %d pair(s) on the device", n);

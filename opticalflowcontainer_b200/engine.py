@@ -273,6 +273,15 @@ class FlowEngine:
                                                gp, stride, 0 if intensity_threshold is None else int(intensity_threshold))
             _lib.check(st, self._h)
 
+    def flow_sample(self, points, pair: int = 0) -> np.ndarray:
+        """(dx, dy) of the handle's current field at integer pixel positions ``points`` [n,2] (x, y); NaN rows for
+        positions outside the frame (ofb_flow_sample)."""
+        pts = np.ascontiguousarray(np.asarray(points).reshape(-1, 2), dtype=np.int32)
+        out = np.empty((pts.shape[0], 2), np.float32)
+        with self._lock:
+            _lib.check(self._lib.ofb_flow_sample(self._h, int(pair), pts.shape[0], pts.ctypes.data, out.ctypes.data), self._h)
+        return out
+
     def flow_download(self, n: int, height: int, width: int) -> np.ndarray:
         """The handle's current field(s) as float32 [n,H,W,2] (ofb_flow_download)."""
         out = np.empty((n, height, width, 2), np.float32)

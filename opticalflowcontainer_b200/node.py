@@ -122,3 +122,28 @@ def junction_mask(points: Sequence[Sequence[float]], height: int, width: int, ra
         if 0 <= x < width and 0 <= y < height:
             mask[max(0, y - radius):min(height, y + radius + 1), max(0, x - radius):min(width, x + radius + 1)] = True
     return mask
+
+
+def junction_velocity(engine: FlowEngine, prev_junctions: Sequence[Sequence[float]],
+                      curr_junctions: Sequence[Sequence[float]], dt: float, pixel_to_meter: float,
+                      max_dist: float = 5.0, min_matches: int = 4, pair: int = 0) -> Optional[float]:
+    """The junction node's velocity (``lfn3_junction_node.py:203-231``) from the engine's current field: every previous
+    junction inside the frame is moved by the flow at its integer position (looked up on the device,
+    :meth:`FlowEngine.flow_sample`), matched to the nearest current junction closer than ``max_dist`` px, and the mean
+    x displacement of at least ``min_matches`` matches gives ``vx = mean_dx / dt * pixel_to_meter`` (None otherwise)."""
+    prev = np.asarray(prev_junctions, np.float64).reshape(-1, 2)
+    curr = np.asarray(curr_junctions, np.float64).reshape(-1, 2)
+    if prev.shape[0] == 0 or curr.shape[0] == 0:
+        return None
+    d = engine.flow_sample(prev.astype(np.int64), pair).astype(np.float64)   # int(p) truncates, as the node does
+    ok = ~np.isnan(d[:, 0])
+    if not ok.any():
+        return None
+    pred = prev[ok] + d[ok]
+    dist = np.sqrt(((pred[:, None, :] - curr[None, :, :]) ** 2).sum(-1))      # exact nearest neighbour (KDTree.query k=1)
+    idx = dist.argmin(1)
+    hit = dist[np.arange(pred.shape[0]), idx] < max_dist
+    if int(hit.sum()) < min_matches:
+        return None
+    disp = curr[idx[hit]] - prev[ok][hit]
+    return float(disp[:, 0].mean() / dt * pixel_to_meter)

@@ -211,3 +211,37 @@ def test_adapt_node_contract(engine_factory):
         fl[0] *= mi
         vx = float(np.mean(fl[0]) / 0.1 * 0.0011)
         assert abs(out[0].vector[0] - vx) <= 1e-6 * max(1.0, abs(vx))
+
+
+def test_junction_velocity_matches_reference_logic(engine_factory):
+    """flow_sample + junction_velocity == the junction node's Python (lfn3_junction_node.py:203-231) run on the
+    downloaded field."""
+    from opticalflowcontainer_b200.node import junction_velocity
+    h, w = 120, 160
+    eng = engine_factory(w, h)
+    a, b = synth.synth_pair(h, w, 12, (3.2, -1.4))
+    flow = eng.farneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    arr = np.transpose(flow, (2, 0, 1))
+    rng = np.random.default_rng(4)
+    prev = np.concatenate([rng.uniform([8, 8], [w - 8, h - 8], size=(12, 2)), [[-3.0, 5.0], [w + 2.0, 10.0]]])
+    curr = prev[:12] + np.array([3.2, -1.4]) + rng.normal(scale=0.4, size=(12, 2))
+    s = eng.flow_sample(prev.astype(np.int64))
+    assert np.isnan(s[12:]).all()
+    for i in range(12):
+        x, y = int(prev[i, 0]), int(prev[i, 1])
+        assert s[i, 0] == arr[0, y, x] and s[i, 1] == arr[1, y, x]
+    # the node's own loop
+    matches = []
+    for p in prev:
+        x, y = int(p[0]), int(p[1])
+        if 0 <= x < w and 0 <= y < h:
+            pp = np.array([p[0] + arr[0, y, x], p[1] + arr[1, y, x]])
+            dist = np.sqrt(((curr - pp) ** 2).sum(1))
+            j = int(dist.argmin())
+            if dist[j] < 5.0:
+                matches.append((p, curr[j]))
+    assert len(matches) >= 4
+    vx_ref = float(np.mean([c - p for p, c in matches], axis=0)[0] / 0.05 * 0.0011)
+    vx = junction_velocity(eng, prev, curr, 0.05, 0.0011)
+    assert vx is not None and abs(vx - vx_ref) <= 1e-12 + 1e-9 * abs(vx_ref)
+    assert junction_velocity(eng, prev[:2], curr, 0.05, 0.0011) is None      # fewer than 4 matches
