@@ -232,8 +232,8 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     if (ip) h->iter_prefetch = ip[0] != '0';
     const char* ipd = getenv("OFB_ITER_PFD");
     if (ipd) h->iter_pfd = atoi(ipd) == 2 ? 2 : 3;
-    const char* ir = getenv("OFB_ITER_REUSE");
-    if (ir) h->iter_reuse = atoi(ir);
+    const char* im = getenv("OFB_ITER_MODE");
+    if (im) h->iter_mode = std::min(2, std::max(0, atoi(im)));
     const char* iw = getenv("OFB_ITER_WAVES");
     if (iw) h->iter_waves = std::max(1, atoi(iw));
     const char* pt = getenv("OFB_POLYEXP_TILE");

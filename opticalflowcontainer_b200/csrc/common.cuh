@@ -16,7 +16,7 @@ namespace ofb {
 constexpr int kMaxLevels = 16;     // scales per call (cv2 clamps by the 32-px rule long before)
 constexpr int kMaxPolyN = 10;      // poly_n <= 10 (cv2 users: 5 or 7)
 constexpr int kMaxBlurRadius = 64; // winsize <= 129
-constexpr int kRowPad = 6;         // spare rows at the end of the R buffers (k_iter_ws2 prefetches up to 3 rows past a pixel)
+constexpr int kRowPad = 10;        // spare rows at the end of the R buffers (k_iter_ws2 prefetches up to 3 rows past a pixel)
 
 // One pyramid scale of the Farneback schedule (FarnebackOpticalFlowImpl::calc).
 struct Level {
@@ -77,7 +77,11 @@ struct ofb_handle {
   int iter_ws = 4;             // OFB_ITER_WS=1: k_iter_ws (double vertical sums, cv2's scheme) instead of k_iter_v
   int iter_pfd = 3;            // OFB_ITER_PFD: L2 prefetch distance (rows) of k_iter_v (2 or 3)
   bool iter_prefetch = true;   // OFB_ITER_PREFETCH=0: no L2 prefetch of the next chunk in k_iter_ws2
-  int iter_reuse = 1;      // OFB_ITER_REUSE=0: full 2x2 gather for every pixel (no row reuse between consecutive rows)
+  // OFB_ITER_MODE: producer load schedule of k_iter_v for the default window (measured, 18 pairs of 1080p, iteration
+  // stage): 2 = two rows of loads in flight, no L2 prefetch, producers at 96 registers by setmaxnreg (2.26 ms,
+  // default); 1 = one row in flight, row-reuse gather, L2 prefetch 3 rows ahead, producers at 88 registers (2.34 ms);
+  // 0 = one row in flight, full gather, L2 prefetch, 80 registers for every thread (2.37 ms)
+  int iter_mode = 2;
   int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
   bool polyexp_tile = false;   // OFB_POLYEXP_TILE=1: 32x32-tile PolyExp kernel instead of the marching one
   bool no_pyr_fast = false;    // OFB_PYR_FAST=0: two-pass pyramid kernels also for the regular power-of-two levels
