@@ -32,6 +32,10 @@ struct PolyCoef {
   int n;
   float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
   float ig11, ig03, ig33, ig55;
+  // the same weights duplicated into pairs (taps 0..8): 64-bit constant operands of the packed f32x2 arithmetic in
+  // the horizontal phase of k_polyexp_march
+  float2 g2[9], xg2[9], xxg2[9];
+  float2 ig11_2, ig03_2, ig33_2, ig55_2;
 };
 
 struct BlurCoef {

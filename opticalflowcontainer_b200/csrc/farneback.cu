@@ -122,6 +122,16 @@ void prepare_poly(int n, double sigma, PolyCoef* pc) {
   pc->ig03 = (float)inv[0][3];
   pc->ig33 = (float)inv[3][3];
   pc->ig55 = (float)inv[5][5];
+  for (int x = 0; x <= 8; x++) {
+    const float a = x <= n ? pc->g[x] : 0.f, b = x <= n ? pc->xg[x] : 0.f, c = x <= n ? pc->xxg[x] : 0.f;
+    pc->g2[x] = make_float2(a, a);
+    pc->xg2[x] = make_float2(b, b);
+    pc->xxg2[x] = make_float2(c, c);
+  }
+  pc->ig11_2 = make_float2(pc->ig11, pc->ig11);
+  pc->ig03_2 = make_float2(pc->ig03, pc->ig03);
+  pc->ig33_2 = make_float2(pc->ig33, pc->ig33);
+  pc->ig55_2 = make_float2(pc->ig55, pc->ig55);
 }
 
 // Box window (FarnebackUpdateFlow_Blur) or Gaussian (FarnebackUpdateFlow_GaussianBlur) weights.

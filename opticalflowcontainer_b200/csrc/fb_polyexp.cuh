@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(PX_COLS, PX_MINB)
   constexpr int NMAX = NT > 0 ? NT : PX_MAXN;
   const int n = NT > 0 ? NT : pc.n;
   constexpr int WIN = 2 * NMAX + PX_ROWS;
-  __shared__ __align__(16) float sV[2][PX_ROWS][3][PX_COLS];
+  // vertical moments of the step, rows interleaved in pairs: sV[buf][row pair][moment][column] = (row 2p, row 2p+1),
+  // so the horizontal phase works on two rows at once with packed f32x2 arithmetic (one issue slot, two FMAs)
+  __shared__ __align__(16) float2 sV[2][PX_ROWS / 2][3][PX_COLS];
 
   const int tid = threadIdx.x;
   const int strip = blockIdx.x % strips, seg = blockIdx.x / strips;
@@ -165,10 +167,10 @@ __global__ void __launch_bounds__(PX_COLS, PX_MINB)
 #pragma unroll
   for (int r = 0; r < PX_ROWS; r++) nx[r] = feed.load(y0 + NMAX + r);
 
-  // H-phase role
-  const int hr = tid >> 6;            // row within the step
-  const int q0 = (tid & 63) * 4;      // first of 4 adjacent strip columns
-  const int hx = x_base + q0;         // image x of that column (multiple of 4)
+  // H-phase role: 2 adjacent pixels of 2 adjacent rows
+  const int hp = tid >> 7;            // row pair within the step
+  const int q0 = (tid & 127) * 2;     // first of 2 adjacent strip columns (even)
+  const int hx = x_base + q0;         // image x of that column (even)
   const bool h_valid = q0 >= PX_HALO && q0 < PX_COLS - PX_HALO && hx < w;
 
   int buf = 0;
@@ -191,109 +193,116 @@ __global__ void __launch_bounds__(PX_COLS, PX_MINB)
       for (int r = 0; r < PX_ROWS; r++) nx[r] = feed.load(t0 + PX_ROWS + r);   // rows clamp: always valid
     }
 #pragma unroll
-    for (int r = 0; r < PX_ROWS; r++) {
-      const float* c = win + NMAX + r;   // centre of row ys + r
-      float r0 = c[0] * pc.g[0], r1 = 0.f, r2 = 0.f;
+    for (int rp = 0; rp < PX_ROWS / 2; rp++) {
+      float m0[2], m1[2], m2[2];
 #pragma unroll
-      for (int k = 1; k <= NMAX; k++) {
-        if (k <= n) {
-          const float a = c[-k], b = c[k];
-          const float p = a + b;
-          r0 = fmaf(pc.g[k], p, r0);
-          r1 = fmaf(pc.xg[k], b - a, r1);
-          r2 = fmaf(pc.xxg[k], p, r2);
+      for (int rr = 0; rr < 2; rr++) {
+        const float* c = win + NMAX + 2 * rp + rr;   // centre of row ys + 2*rp + rr
+        float r0 = c[0] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= NMAX; k++) {
+          if (k <= n) {
+            const float a = c[-k], b = c[k];
+            const float p = a + b;
+            r0 = fmaf(pc.g[k], p, r0);
+            r1 = fmaf(pc.xg[k], b - a, r1);
+            r2 = fmaf(pc.xxg[k], p, r2);
+          }
         }
+        m0[rr] = r0; m1[rr] = r1; m2[rr] = r2;
       }
-      sV[buf][r][0][tid] = r0;
-      sV[buf][r][1][tid] = r1;
-      sV[buf][r][2][tid] = r2;
+      sV[buf][rp][0][tid] = make_float2(m0[0], m0[1]);
+      sV[buf][rp][1][tid] = make_float2(m1[0], m1[1]);
+      sV[buf][rp][2][tid] = make_float2(m2[0], m2[1]);
     }
 #pragma unroll
     for (int i = 0; i < 2 * NMAX; i++) win[i] = win[i + PX_ROWS];
     __syncthreads();
-    // ---------------- H: horizontal moments of 4 adjacent pixels of row ys + hr
-    const int y = ys + hr;
+    // ---------------- H: horizontal moments of 2 adjacent pixels of rows ys + 2*hp, ys + 2*hp + 1 (packed pairs)
+    const int y = ys + 2 * hp;
     if (h_valid && y < y1) {
-      float4 o[4];
-      float ob[4];
+      constexpr int PAD = (NMAX + 1) / 2 * 2;        // even >= n: window columns q0 - PAD .. q0 + 1 + PAD
+      constexpr int NE = 2 * PAD + 2;
+      const float2 neg1 = make_float2(-1.f, -1.f);
+      float2 ox[2], oy[2], oz[2], ow[2], ob[2];      // per pixel: (row y, row y + 1)
       {
-        float e[20];   // e[i] = r0 at strip column q0 - 8 + i
+        float2 e[NE];   // e[i] = r0 at strip column q0 - PAD + i, rows (y, y + 1)
 #pragma unroll
-        for (int v = 0; v < 5; v++) {
-          const float4 t = *reinterpret_cast<const float4*>(&sV[buf][hr][0][q0 - 8 + 4 * v]);
-          e[4 * v] = t.x; e[4 * v + 1] = t.y; e[4 * v + 2] = t.z; e[4 * v + 3] = t.w;
+        for (int v = 0; v < NE / 2; v++) {
+          const float4 t = *reinterpret_cast<const float4*>(&sV[buf][hp][0][q0 - PAD + 2 * v]);
+          e[2 * v] = make_float2(t.x, t.y); e[2 * v + 1] = make_float2(t.z, t.w);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = 8 + j;
-          float b1 = e[c] * pc.g[0], b2 = 0.f, b4 = 0.f;
+        for (int j = 0; j < 2; j++) {
+          const int c = PAD + j;
+          float2 b1 = __fmul2_rn(e[c], pc.g2[0]), b2 = make_float2(0.f, 0.f), b4 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int k = 1; k <= NMAX; k++) {
             if (k <= n) {
-              const float tg = e[c + k] + e[c - k];
-              b1 = fmaf(tg, pc.g[k], b1);
-              b4 = fmaf(tg, pc.xxg[k], b4);
-              b2 = fmaf(e[c + k] - e[c - k], pc.xg[k], b2);
+              const float2 tg = __fadd2_rn(e[c + k], e[c - k]);
+              const float2 td = __ffma2_rn(e[c - k], neg1, e[c + k]);
+              b1 = __ffma2_rn(tg, pc.g2[k], b1);
+              b4 = __ffma2_rn(tg, pc.xxg2[k], b4);
+              b2 = __ffma2_rn(td, pc.xg2[k], b2);
             }
           }
-          o[j].y = b2 * pc.ig11;
-          o[j].z = b1 * pc.ig03;   // + b5 * ig33 below
-          o[j].w = b1 * pc.ig03 + b4 * pc.ig33;
+          oy[j] = __fmul2_rn(b2, pc.ig11_2);
+          oz[j] = __fmul2_rn(b1, pc.ig03_2);          // + b5 * ig33 below
+          ow[j] = __ffma2_rn(b4, pc.ig33_2, oz[j]);
         }
       }
       {
-        float e[20];   // r1
+        float2 e[NE];   // r1
 #pragma unroll
-        for (int v = 0; v < 5; v++) {
-          const float4 t = *reinterpret_cast<const float4*>(&sV[buf][hr][1][q0 - 8 + 4 * v]);
-          e[4 * v] = t.x; e[4 * v + 1] = t.y; e[4 * v + 2] = t.z; e[4 * v + 3] = t.w;
+        for (int v = 0; v < NE / 2; v++) {
+          const float4 t = *reinterpret_cast<const float4*>(&sV[buf][hp][1][q0 - PAD + 2 * v]);
+          e[2 * v] = make_float2(t.x, t.y); e[2 * v + 1] = make_float2(t.z, t.w);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = 8 + j;
-          float b3 = e[c] * pc.g[0], b6 = 0.f;
+        for (int j = 0; j < 2; j++) {
+          const int c = PAD + j;
+          float2 b3 = __fmul2_rn(e[c], pc.g2[0]), b6 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int k = 1; k <= NMAX; k++) {
             if (k <= n) {
-              b3 = fmaf(e[c + k] + e[c - k], pc.g[k], b3);
-              b6 = fmaf(e[c + k] - e[c - k], pc.xg[k], b6);
+              b3 = __ffma2_rn(__fadd2_rn(e[c + k], e[c - k]), pc.g2[k], b3);
+              b6 = __ffma2_rn(__ffma2_rn(e[c - k], neg1, e[c + k]), pc.xg2[k], b6);
             }
           }
-          o[j].x = b3 * pc.ig11;
-          ob[j] = b6 * pc.ig55;
+          ox[j] = __fmul2_rn(b3, pc.ig11_2);
+          ob[j] = __fmul2_rn(b6, pc.ig55_2);
         }
       }
       {
-        float e[20];   // r2
+        float2 e[NE];   // r2
 #pragma unroll
-        for (int v = 0; v < 5; v++) {
-          const float4 t = *reinterpret_cast<const float4*>(&sV[buf][hr][2][q0 - 8 + 4 * v]);
-          e[4 * v] = t.x; e[4 * v + 1] = t.y; e[4 * v + 2] = t.z; e[4 * v + 3] = t.w;
+        for (int v = 0; v < NE / 2; v++) {
+          const float4 t = *reinterpret_cast<const float4*>(&sV[buf][hp][2][q0 - PAD + 2 * v]);
+          e[2 * v] = make_float2(t.x, t.y); e[2 * v + 1] = make_float2(t.z, t.w);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = 8 + j;
-          float b5 = e[c] * pc.g[0];
+        for (int j = 0; j < 2; j++) {
+          const int c = PAD + j;
+          float2 b5 = __fmul2_rn(e[c], pc.g2[0]);
 #pragma unroll
           for (int k = 1; k <= NMAX; k++) {
-            if (k <= n) b5 = fmaf(e[c + k] + e[c - k], pc.g[k], b5);
+            if (k <= n) b5 = __ffma2_rn(__fadd2_rn(e[c + k], e[c - k]), pc.g2[k], b5);
           }
-          o[j].z += b5 * pc.ig33;
+          oz[j] = __ffma2_rn(b5, pc.ig33_2, oz[j]);
         }
       }
       const size_t ob0 = fbase + (size_t)y * w + hx;
-      if (hx + 3 < w && ((w & 3) == 0)) {
-        // rows are 16-byte aligned when w % 4 == 0: one float4 store for the 4 ch-4 values
-#pragma unroll
-        for (int j = 0; j < 4; j++) RA[ob0 + j] = o[j];
-        *reinterpret_cast<float4*>(RB + ob0) = make_float4(ob[0], ob[1], ob[2], ob[3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (hx + j < w) {
-            RA[ob0 + j] = o[j];
-            RB[ob0 + j] = ob[j];
-          }
+      const bool two = hx + 1 < w;
+      const bool vec = two && ((w & 1) == 0);        // hx is even: rows start 8-byte aligned when w is even
+      RA[ob0] = make_float4(ox[0].x, oy[0].x, oz[0].x, ow[0].x);
+      if (two) RA[ob0 + 1] = make_float4(ox[1].x, oy[1].x, oz[1].x, ow[1].x);
+      if (vec) *reinterpret_cast<float2*>(RB + ob0) = make_float2(ob[0].x, ob[1].x);
+      else { RB[ob0] = ob[0].x; if (two) RB[ob0 + 1] = ob[1].x; }
+      if (y + 1 < y1) {
+        RA[ob0 + w] = make_float4(ox[0].y, oy[0].y, oz[0].y, ow[0].y);
+        if (two) RA[ob0 + w + 1] = make_float4(ox[1].y, oy[1].y, oz[1].y, ow[1].y);
+        if (vec) *reinterpret_cast<float2*>(RB + ob0 + w) = make_float2(ob[0].y, ob[1].y);
+        else { RB[ob0 + w] = ob[0].y; if (two) RB[ob0 + w + 1] = ob[1].y; }
       }
     }
     buf ^= 1;
