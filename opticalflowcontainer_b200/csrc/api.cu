@@ -233,7 +233,7 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     const char* ipd = getenv("OFB_ITER_PFD");
     if (ipd) h->iter_pfd = atoi(ipd) == 2 ? 2 : 3;
     const char* im = getenv("OFB_ITER_MODE");
-    if (im) h->iter_mode = std::min(2, std::max(0, atoi(im)));
+    if (im) h->iter_mode = std::min(3, std::max(0, atoi(im)));
     const char* iw = getenv("OFB_ITER_WAVES");
     if (iw) h->iter_waves = std::max(1, atoi(iw));
     const char* pt = getenv("OFB_POLYEXP_TILE");

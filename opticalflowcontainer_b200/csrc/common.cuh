@@ -82,10 +82,11 @@ struct ofb_handle {
   int iter_pfd = 3;            // OFB_ITER_PFD: L2 prefetch distance (rows) of k_iter_v (2 or 3)
   bool iter_prefetch = true;   // OFB_ITER_PREFETCH=0: no L2 prefetch of the next chunk in k_iter_ws2
   // OFB_ITER_MODE: producer load schedule of k_iter_v for the default window (measured, 18 pairs of 1080p, iteration
-  // stage): 2 = two rows of loads in flight, no L2 prefetch, producers at 96 registers by setmaxnreg (2.26 ms,
-  // default); 1 = one row in flight, row-reuse gather, L2 prefetch 3 rows ahead, producers at 88 registers (2.34 ms);
+  // stage; all four produce the same bits): 3 = two rows of loads in flight + row-reuse gather, no L2 prefetch,
+  // producers at 96 registers by setmaxnreg (2.15 ms, default); 2 = the same with the full 2x2 gather (2.26 ms);
+  // 1 = one row in flight, row-reuse gather, L2 prefetch 3 rows ahead, producers at 88 registers (2.34 ms);
   // 0 = one row in flight, full gather, L2 prefetch, 80 registers for every thread (2.37 ms)
-  int iter_mode = 2;
+  int iter_mode = 3;
   int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
   bool polyexp_tile = false;   // OFB_POLYEXP_TILE=1: 32x32-tile PolyExp kernel instead of the marching one
   bool no_pyr_fast = false;    // OFB_PYR_FAST=0: two-pass pyramid kernels also for the regular power-of-two levels

@@ -658,7 +658,8 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
             } else {
               if (pfd == 0) e = launch_iter_v<7, 256, 2, 2, 0, 4>(OFB_V_ARGS);
               else if (pfd == 2) e = launch_iter_v<7, 256, 2, 2, 2, 4>(OFB_V_ARGS);
-              else if (h->iter_mode == 2) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1>(OFB_V_ARGS);     // default
+              else if (h->iter_mode == 3) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1, false, true>(OFB_V_ARGS);   // default
+              else if (h->iter_mode == 2) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1>(OFB_V_ARGS);
               else if (h->iter_mode == 1) e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>(OFB_V_ARGS);
               else e = launch_iter_v<7, 256, 2, 2, 3, 4>(OFB_V_ARGS);
             }

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
   static_assert(CLOOP == 1 || CLOOP == CH, "consumer rows per thread: 1 or the whole chunk");
   constexpr int NCONS = (CH / CLOOP) * GROUPS;
   static_assert(NCONS % 32 == 0, "whole consumer warps");
-  static_assert(!REUSE || (RIF == 1 && !TILED && CH % 2 == 0), "row-reuse gather: one row in flight, even chunks, untiled");
+  static_assert(!REUSE || (!TILED && CH == 2 && (RIF == 1 || RIF == 2)), "row-reuse gather: chunks of two rows, untiled");
   constexpr int NT = COLS + NCONS;
   enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3 };
   const int m = MT > 0 ? MT : m_rt;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
 
   if (tid < COLS) {
     // ------------------------------------------------------------------ PRODUCERS (one column each)
-    if constexpr (REUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REUSE_PROD_REGS));
+    if constexpr (REUSE && RIF == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REUSE_PROD_REGS));
     else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(96));
     const float4* RA0 = RA + (size_t)pair * n;
     const float* RB0 = RB + (size_t)pair * n;
@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
 #else
       const M5 mm = um_finish2(L, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h);
 #endif
-      P[0] += mm.g11; P[1] += mm.g12; P[2] += mm.g22; P[3] += mm.h1; P[4] += mm.h2;
+      P[0] = __fadd_rn(P[0], mm.g11); P[1] = __fadd_rn(P[1], mm.g12); P[2] = __fadd_rn(P[2], mm.g22);
+        P[3] = __fadd_rn(P[3], mm.h1); P[4] = __fadd_rn(P[4], mm.h2);
 #pragma unroll
       for (int ch = 0; ch < 5; ch++) {
         V[ch] = (Bp[ch] - old[ch]) + P[ch];
@@ -174,7 +175,83 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
       return __ldg(f + ((unsigned)yc * uw + (unsigned)x));
     };
 
-    if constexpr (REUSE) {
+    if constexpr (REUSE && RIF == 2) {
+      // Two rows in flight AND row-reuse gather.  Rows A = t, B = t + 1 of a chunk: all loads of both are issued
+      // before the first is consumed.  Corner-row register sets: X = top of A, Y = bottom of A (and top of B when B
+      // sits exactly one row below A), W = top of B otherwise, Z = bottom of B.  The next chunk's A takes Z as its top
+      // row when the displacement allows it (one register copy per chunk), so a smooth field costs two corner-row
+      // loads per chunk-row pair... i.e. 8 gather loads per chunk instead of 16.
+      UmRow X, Y, Z, W;
+      UmPix pa, pb;
+      unsigned prev_g = ~0u - uw;
+      bool reuse_b = false;
+      Z.q0 = Z.q1 = make_float4(0.f, 0.f, 0.f, 0.f); Z.s0 = Z.s1 = 0.f;
+      W = Z;
+      auto issue2 = [&](float2 fa, float2 fb, int t) {
+        const int ya = clampi(t, 0, h - 1), yb = clampi(t + 1, 0, h - 1);
+        X = Z;                                                     // bottom row of the previous chunk's row B
+        um_pix(pa, RA0, RB0, fa, x, ya, (unsigned)ya * uw, uw, uh);
+        if (pa.g != prev_g + uw) um_row_load(X, RA1, RB1, pa.g);
+        um_row_load(Y, RA1, RB1, pa.g + uw);
+        um_pix(pb, RA0, RB0, fb, x, yb, (unsigned)yb * uw, uw, uh);
+        reuse_b = pa.inside && pb.g == pa.g + uw;
+        if (!reuse_b) um_row_load(W, RA1, RB1, pb.g);
+        um_row_load(Z, RA1, RB1, pb.g + uw);
+        prev_g = pb.inside ? pb.g : ~0u - uw;
+      };
+      auto ring_step = [&](const M5& mm, float (&V)[5]) {
+        float old[5];
+#pragma unroll
+        for (int ch = 0; ch < 5; ch++) old[ch] = have_prev ? rcol[(k * 5 + ch) * COLS] : 0.f;
+        P[0] = __fadd_rn(P[0], mm.g11); P[1] = __fadd_rn(P[1], mm.g12); P[2] = __fadd_rn(P[2], mm.g22);
+        P[3] = __fadd_rn(P[3], mm.h1); P[4] = __fadd_rn(P[4], mm.h2);
+#pragma unroll
+        for (int ch = 0; ch < 5; ch++) {
+          V[ch] = (Bp[ch] - old[ch]) + P[ch];
+          rcol[(k * 5 + ch) * COLS] = P[ch];
+        }
+        if (++k == R) {
+          k = 0;
+          have_prev = true;
+#pragma unroll
+          for (int ch = 0; ch < 5; ch++) { Bp[ch] = P[ch]; P[ch] = 0.f; }
+        }
+      };
+      auto finish_a = [&](int t, float (&V)[5]) {
+        const int y = clampi(t, 0, h - 1);
+        ring_step(um_finish_rows(pa, X, Y, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
+      };
+      auto finish_b = [&](int t, float (&V)[5]) {
+        const int y = clampi(t, 0, h - 1);
+        if (reuse_b) W = Y;                                        // (select per thread: 10 predicated moves)
+        ring_step(um_finish_rows(pb, W, Z, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
+      };
+      float2 fa = flow_at(t_first), fb = flow_at(t_first + 1);
+      // warm-up: the R-1 = 2m rows above the first output row, chunk by chunk
+      for (int t = t_first; t < t_first + R - 1; t += 2) {
+        float V[5];
+        issue2(fa, fb, t);
+        fa = flow_at(t + 2); fb = flow_at(t + 3);
+        finish_a(t, V);
+        finish_b(t + 1, V);
+      }
+      for (int c = 0; c < n_chunks; c++) {
+        const int buf = c & 1;
+        const int tc = y0 + c * CH + m;                              // newest matrix row of output row y0 + c*CH
+        issue2(fa, fb, tc);
+        fa = flow_at(tc + 2); fb = flow_at(tc + 3);
+        if (c >= 2) named_bar_sync(BAR_EMPTY0 + buf, NT);            // consumers released this buffer
+        float* srow = stage + buf * CH * 5 * COLS + tid;
+        float V[5];
+        finish_a(tc, V);
+#pragma unroll
+        for (int ch = 0; ch < 5; ch++) srow[ch * COLS] = V[ch];
+        finish_b(tc + 1, V);                                         // (a row past y1 keeps the state consistent; never read)
+#pragma unroll
+        for (int ch = 0; ch < 5; ch++) srow[(5 + ch) * COLS] = V[ch];
+        named_bar_arrive(BAR_FULL0 + buf, NT);                       // staged rows of chunk c are ready
+      }
+    } else if constexpr (REUSE) {
       // Row-reuse gather.  Two corner-row register sets alternate as "top" and "bottom" from one row to the
       // next (rows are handled in pairs, so the alternation is in the register names, not in moves).
       UmRow ra, rb;
@@ -199,7 +276,8 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
 #pragma unroll
         for (int ch = 0; ch < 5; ch++) old[ch] = have_prev ? rcol[(k * 5 + ch) * COLS] : 0.f;
         const M5 mm = um_finish_rows(px, top, bot, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h);
-        P[0] += mm.g11; P[1] += mm.g12; P[2] += mm.g22; P[3] += mm.h1; P[4] += mm.h2;
+        P[0] = __fadd_rn(P[0], mm.g11); P[1] = __fadd_rn(P[1], mm.g12); P[2] = __fadd_rn(P[2], mm.g22);
+        P[3] = __fadd_rn(P[3], mm.h1); P[4] = __fadd_rn(P[4], mm.h2);
 #pragma unroll
         for (int ch = 0; ch < 5; ch++) {
           V[ch] = (Bp[ch] - old[ch]) + P[ch];
@@ -324,7 +402,7 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
   }
 
   // -------------------------------------------------------------------- CONSUMERS (PXT adjacent pixels of one row each)
-  if constexpr (REUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REUSE_CONS_REGS));
+  if constexpr (REUSE && RIF == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REUSE_CONS_REGS));
   else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
   float2* fout = flow_out + (size_t)pair * n;
   const int ct = tid - COLS;                         // 0..NCONS-1

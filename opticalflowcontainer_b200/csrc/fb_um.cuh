@@ -92,40 +92,52 @@ __device__ __forceinline__ void um_issue2_tiled(UmLoads2& L, const float4* __res
   L.s11 = __ldg(qb + 1);
 }
 
-// border: this pixel lies within 5 px of the level border (attenuation table applies)
-__device__ __forceinline__ M5 um_finish2(const UmLoads2& L, bool border, int x, int y, int w, int h) {
-  const float fx = L.fx, fy = L.fy;
-  const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-  float r2 = a00 * L.q00.x + a01 * L.q01.x + a10 * L.q10.x + a11 * L.q11.x;
-  float r3 = a00 * L.q00.y + a01 * L.q01.y + a10 * L.q10.y + a11 * L.q11.y;
-  float r4 = a00 * L.q00.z + a01 * L.q01.z + a10 * L.q10.z + a11 * L.q11.z;
-  float r5 = a00 * L.q00.w + a01 * L.q01.w + a10 * L.q10.w + a11 * L.q11.w;
-  float r6 = a00 * L.s00 + a01 * L.s01 + a10 * L.s10 + a11 * L.s11;
-  if (L.inside) {
-    r4 = (L.a0.z + r4) * 0.5f;
-    r5 = (L.a0.w + r5) * 0.5f;
-    r6 = (L.b0 + r6) * 0.25f;
+// The arithmetic of UpdateMatrices for one pixel, written with explicit roundings (no FMA contraction left to the
+// compiler), so that every load schedule of k_iter_v produces the same bits.  The fusion pattern is the one nvcc chose
+// for the original expression-form code.
+__device__ __forceinline__ M5 um_arith(const float4 a0, const float b0, const float4 q00, const float4 q01, const float4 q10,
+                                       const float4 q11, const float s00, const float s01, const float s10, const float s11,
+                                       const float fx, const float fy, const float dx, const float dy, const bool inside,
+                                       const bool border, int x, int y, int w, int h) {
+  const float gx = __fsub_rn(1.f, fx), gy = __fsub_rn(1.f, fy);
+  const float a00 = __fmul_rn(gx, gy), a01 = __fmul_rn(fx, gy), a10 = __fmul_rn(gx, fy), a11 = __fmul_rn(fx, fy);
+#define OFB_BIL(c00, c01, c10, c11) __fmaf_rn(a11, c11, __fmaf_rn(a10, c10, __fmaf_rn(a00, c00, __fmul_rn(a01, c01))))
+  float r2 = OFB_BIL(q00.x, q01.x, q10.x, q11.x);
+  float r3 = OFB_BIL(q00.y, q01.y, q10.y, q11.y);
+  float r4 = OFB_BIL(q00.z, q01.z, q10.z, q11.z);
+  float r5 = OFB_BIL(q00.w, q01.w, q10.w, q11.w);
+  float r6 = OFB_BIL(s00, s01, s10, s11);
+#undef OFB_BIL
+  if (inside) {
+    r4 = __fmul_rn(__fadd_rn(a0.z, r4), 0.5f);
+    r5 = __fmul_rn(__fadd_rn(a0.w, r5), 0.5f);
+    r6 = __fmul_rn(__fadd_rn(b0, r6), 0.25f);
   } else {
     r2 = r3 = 0.f;
-    r4 = L.a0.z;
-    r5 = L.a0.w;
-    r6 = L.b0 * 0.5f;
+    r4 = a0.z;
+    r5 = a0.w;
+    r6 = __fmul_rn(b0, 0.5f);
   }
-  r2 = (L.a0.x - r2) * 0.5f;
-  r3 = (L.a0.y - r3) * 0.5f;
-  r2 += r4 * L.dy + r6 * L.dx;
-  r3 += r6 * L.dy + r5 * L.dx;
+  r2 = __fmaf_rn(__fsub_rn(a0.x, r2), 0.5f, __fmaf_rn(r4, dy, __fmul_rn(r6, dx)));
+  r3 = __fmaf_rn(__fsub_rn(a0.y, r3), 0.5f, __fmaf_rn(r6, dy, __fmul_rn(r5, dx)));
   if (border) {
-    const float s = border_w(x, w) * border_w(y, h);
-    r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+    const float s = __fmul_rn(border_w(x, w), border_w(y, h));
+    r2 = __fmul_rn(r2, s); r3 = __fmul_rn(r3, s); r4 = __fmul_rn(r4, s); r5 = __fmul_rn(r5, s); r6 = __fmul_rn(r6, s);
   }
+  const float r66 = __fmul_rn(r6, r6);
   M5 m;
-  m.g11 = r4 * r4 + r6 * r6;
-  m.g12 = (r4 + r5) * r6;
-  m.g22 = r5 * r5 + r6 * r6;
-  m.h1 = r4 * r2 + r6 * r3;
-  m.h2 = r6 * r2 + r5 * r3;
+  m.g11 = __fmaf_rn(r4, r4, r66);
+  m.g12 = __fmul_rn(__fadd_rn(r4, r5), r6);
+  m.g22 = __fmaf_rn(r5, r5, r66);
+  m.h1 = __fmaf_rn(r4, r2, __fmul_rn(r6, r3));
+  m.h2 = __fmaf_rn(r5, r3, __fmul_rn(r6, r2));
   return m;
+}
+
+// border: this pixel lies within 5 px of the level border (attenuation table applies)
+__device__ __forceinline__ M5 um_finish2(const UmLoads2& L, bool border, int x, int y, int w, int h) {
+  return um_arith(L.a0, L.b0, L.q00, L.q01, L.q10, L.q11, L.s00, L.s01, L.s10, L.s11, L.fx, L.fy, L.dx, L.dy, L.inside,
+                  border, x, y, w, h);
 }
 
 // ---- row-reuse gather (k_iter_v<..., REUSE>) -------------------------------------------------------
@@ -181,38 +193,31 @@ __device__ __forceinline__ void um_issue_rows(UmPix& P, UmRow& top, UmRow& bot, 
 
 __device__ __forceinline__ M5 um_finish_rows(const UmPix& P, const UmRow& top, const UmRow& bot, bool border, int x,
                                              int y, int w, int h) {
-  const float fx = P.fx, fy = P.fy;
-  const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-  float r2 = a00 * top.q0.x + a01 * top.q1.x + a10 * bot.q0.x + a11 * bot.q1.x;
-  float r3 = a00 * top.q0.y + a01 * top.q1.y + a10 * bot.q0.y + a11 * bot.q1.y;
-  float r4 = a00 * top.q0.z + a01 * top.q1.z + a10 * bot.q0.z + a11 * bot.q1.z;
-  float r5 = a00 * top.q0.w + a01 * top.q1.w + a10 * bot.q0.w + a11 * bot.q1.w;
-  float r6 = a00 * top.s0 + a01 * top.s1 + a10 * bot.s0 + a11 * bot.s1;
-  if (P.inside) {
-    r4 = (P.a0.z + r4) * 0.5f;
-    r5 = (P.a0.w + r5) * 0.5f;
-    r6 = (P.b0 + r6) * 0.25f;
-  } else {
-    r2 = r3 = 0.f;
-    r4 = P.a0.z;
-    r5 = P.a0.w;
-    r6 = P.b0 * 0.5f;
-  }
-  r2 = (P.a0.x - r2) * 0.5f;
-  r3 = (P.a0.y - r3) * 0.5f;
-  r2 += r4 * P.dy + r6 * P.dx;
-  r3 += r6 * P.dy + r5 * P.dx;
-  if (border) {
-    const float s = border_w(x, w) * border_w(y, h);
-    r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
-  }
-  M5 m;
-  m.g11 = r4 * r4 + r6 * r6;
-  m.g12 = (r4 + r5) * r6;
-  m.g22 = r5 * r5 + r6 * r6;
-  m.h1 = r4 * r2 + r6 * r3;
-  m.h2 = r6 * r2 + r5 * r3;
-  return m;
+  return um_arith(P.a0, P.b0, top.q0, top.q1, bot.q0, bot.q1, top.s0, top.s1, bot.s0, bot.s1, P.fx, P.fy, P.dx, P.dy,
+                  P.inside, border, x, y, w, h);
+}
+
+// pieces of the row-reuse gather for the two-rows-in-flight schedule (k_iter_v<..., RIF = 2, REUSE>)
+__device__ __forceinline__ void um_pix(UmPix& P, const float4* __restrict__ RA0, const float* __restrict__ RB0, float2 fl,
+                                       int x, int y, unsigned yw, unsigned w, unsigned h) {
+  const unsigned o = yw + (unsigned)x;
+  P.a0 = __ldg(RA0 + o);
+  P.b0 = __ldg(RB0 + o);
+  P.dx = fl.x;
+  P.dy = fl.y;
+  const float fx = (float)x + fl.x, fy = (float)y + fl.y;
+  const int ix = __float2int_rd(fx), iy = __float2int_rd(fy);
+  P.fx = fx - (float)ix;
+  P.fy = fy - (float)iy;
+  P.inside = (unsigned)ix < w - 1u && (unsigned)iy < h - 1u;
+  P.g = P.inside ? (unsigned)iy * w + (unsigned)ix : 0u;
+}
+__device__ __forceinline__ void um_row_load(UmRow& r, const float4* __restrict__ RA1, const float* __restrict__ RB1,
+                                            unsigned g) {
+  r.q0 = __ldg(RA1 + g);
+  r.q1 = __ldg(RA1 + g + 1);
+  r.s0 = __ldg(RB1 + g);
+  r.s1 = __ldg(RB1 + g + 1);
 }
 
 // sums are unscaled window sums; reg = 1e-3 / scale^2 (scale = winsize^-2 folded into the regulariser)

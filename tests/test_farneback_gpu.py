@@ -207,3 +207,29 @@ def test_async_batch_pipelines_across_calls(built_lib):
         assert np.array_equal(outs[0].numpy(), ref[1])
     finally:
         eng.close()
+
+
+def test_iteration_schedules_bit_identical(built_lib):
+    """The four producer load schedules of k_iter_v (OFB_ITER_MODE 0..3: prefetch / row-reuse gather / two rows in
+    flight) are different instruction orders of the same arithmetic: the fields must agree bit for bit, also across a
+    flow discontinuity (where the row reuse has to fall back to the full gather) and on an odd size."""
+    import os
+    import opticalflowcontainer_b200 as ofb
+    old = os.environ.get("OFB_ITER_MODE")
+    try:
+        for (h, w, shift) in [(270, 480, (1.7, -0.9)), (213, 317, (-6.3, 4.2))]:
+            a, b = synth.synth_pair(h, w, 5, shift)
+            b = np.ascontiguousarray(np.roll(b, 5, axis=0))       # tear: large |flow| differences between rows
+            fields = []
+            for mode in ("0", "1", "2", "3"):
+                os.environ["OFB_ITER_MODE"] = mode
+                eng = ofb.FlowEngine(w, h, 1, 0)
+                fields.append(eng.farneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0).copy())
+                eng.close()
+            for f in fields[1:]:
+                assert np.array_equal(fields[0], f)
+    finally:
+        if old is None:
+            os.environ.pop("OFB_ITER_MODE", None)
+        else:
+            os.environ["OFB_ITER_MODE"] = old
