@@ -392,10 +392,11 @@ def run_ours(args, rank, local_rank, world):
 
     B = args.batch
     seq = args.mode == "sequence"
+    strm = args.mode == "stream"
     eng = ofb.FlowEngine(W_, H_, B, local_rank)
     pitch = W_
     istride = pitch * H_
-    frames_per_set = (B + 1) if seq else 2 * B
+    frames_per_set = (B + 1) if seq else (B if strm else 2 * B)
     n_sets = max(2, int(np.ceil(2.0 * L2_BYTES / (frames_per_set * istride))) + 1)
     # synthetic frames: a few distinct textures, shifted copies as "next"
     # (corpus C2: a panning texture, per-frame shift ~U(-8, 8) px — real-valued, so the
@@ -405,7 +406,12 @@ def run_ours(args, rank, local_rank, world):
     host_sets = []
     for s in range(n_sets):
         fr = np.empty((frames_per_set, H_, W_), np.uint8)
-        if seq:
+        if strm:
+            # set s = frame s of each of the B streams (stream i pans its own texture by a fixed sub-pixel velocity)
+            for i in range(B):
+                vx, vy = 0.9 + 0.37 * (i % 7), -0.6 + 0.29 * (i % 5)
+                fr[i] = synth.subpixel_shift(base[i % 4], vx * s, vy * s)
+        elif seq:
             t = base[s % 4]
             ox = oy = 0.0
             for i in range(frames_per_set):
@@ -421,10 +427,20 @@ def run_ours(args, rank, local_rank, world):
     d_flow = torch.empty((B, H_, W_, 2), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
 
+    # stream mode walks the time axis back and forth so that consecutive calls always see consecutive frames
+    order = list(range(n_sets)) + list(range(n_sets - 2, 0, -1))
+
     def step(i):
+        if strm:
+            d = dev_sets[order[i % len(order)]]
+            eng.farneback_stream_device(B, d.data_ptr(), W_, H_, pitch, istride, d_flow.data_ptr(), **PARAMS)
+            return
         d = dev_sets[i % n_sets]
         p0 = d.data_ptr()
         eng.farneback_device(B, p0, p0 + B * istride, W_, H_, pitch, istride, d_flow.data_ptr(), sequence=seq, **PARAMS)
+
+    if strm:
+        eng.farneback_stream_device(B, dev_sets[1].data_ptr(), W_, H_, pitch, istride, d_flow.data_ptr(), **PARAMS)  # prime
 
     stream = torch.cuda.ExternalStream(eng.stream)
 
@@ -477,16 +493,21 @@ def run_ours(args, rank, local_rank, world):
     value = pairs / (plain_ms_max * 1e-3)
 
     # ---- e2e: host-buffer C-ABI call, pinned host memory, H2D + D2H inside the timed region
-    pin_prev = [torch.from_numpy(host_sets[s][:B].copy()).pin_memory() for s in range(min(n_sets, 3))]
+    pin_prev = [torch.from_numpy(host_sets[s][:B].copy()).pin_memory() for s in range(0 if strm else min(n_sets, 3))]
     pin_next = [torch.from_numpy((host_sets[s][1:B + 1] if seq else host_sets[s][B:2 * B]).copy()).pin_memory()
-                for s in range(min(n_sets, 3))]
+                for s in range(0 if strm else min(n_sets, 3))]
     # two result buffers: the asynchronous batch call pipelines across calls (upload + kernels of step
     # i+1 overlap the download of step i); a step's result is complete before its buffer is reused
     # (the library orders that) and everything is complete at eng.wait() inside the timed region
     pin_flow = [torch.empty((B, H_, W_, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
     e2e_steps = args.steps if args.e2e_steps <= 0 else args.e2e_steps
 
+    pin_frames = [torch.from_numpy(fr).pin_memory() for fr in host_sets] if strm else []
+
     def e2e_step(i):
+        if strm:   # one new frame per stream up, the field of (previous, new) down; synchronous per call
+            eng.farneback_stream(pin_frames[order[i % len(order)]].numpy(), out=pin_flow[i % 2].numpy(), **PARAMS)
+            return
         s = i % len(pin_prev)
         eng.farneback_batch_into(pin_prev[s].numpy(), pin_next[s].numpy(), pin_flow[i % 2].numpy(),
                                  wait=args.e2e_sync, **PARAMS)
@@ -507,14 +528,20 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- e2e through the node contract: frames up, flow on the device, median/mean of u back (what every
     # node of the reference does right after the flow call) — the field never crosses PCIe
+    def node_step(i):
+        if strm:
+            eng.farneback_stream(pin_frames[order[i % len(order)]].numpy(), download=False, **PARAMS)
+            return eng.flow_u_stats(B)
+        s_ = i % len(pin_prev)
+        return eng.farneback_batch_stats(pin_prev[s_].numpy(), pin_next[s_].numpy(), wait=args.e2e_sync or i < 0, **PARAMS)
+
     for i in range(2):
-        eng.farneback_batch_stats(pin_prev[i % len(pin_prev)].numpy(), pin_next[i % len(pin_prev)].numpy(), **PARAMS)
+        node_step(i - 2)
     barrier()
     t0 = time.perf_counter()
     node_out = []
     for i in range(e2e_steps):
-        s_ = i % len(pin_prev)
-        node_out.append(eng.farneback_batch_stats(pin_prev[s_].numpy(), pin_next[s_].numpy(), wait=args.e2e_sync, **PARAMS))
+        node_out.append(node_step(i))
     eng.wait()                                  # every step's mean/median of u is on the host here
     node_s = time.perf_counter() - t0
     t = torch.tensor([node_s], dtype=torch.float64, device="cuda")
@@ -570,13 +597,15 @@ def run_ours(args, rank, local_rank, world):
                      "pipeline_bytes_per_pair": algorithmic_bytes_per_pair(W_, H_),
                      "stage_ms": {k: v[0] for k, v in stage.items()}, "stage_launch_groups": {k: v[1] for k, v in stage.items()},
                      "timed_region_ms_with_stage_events": dev_ms_max},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * W_ * H_,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (1 if strm else 2) * B * W_ * H_,
                 "d2h_bytes_per_step": 8 * B * W_ * H_, "steps": e2e_steps,
-                "api": ("ofb_farneback_batch" if args.e2e_sync else "ofb_farneback_batch_async + ofb_wait") +
+                "api": ("ofb_farneback_stream (one new frame per stream per call, synchronous)" if strm else
+                        "ofb_farneback_batch" if args.e2e_sync else "ofb_farneback_batch_async + ofb_wait") +
                        " (host buffers, pinned; full float32 [H,W,2] flow of every pair returned to the host)"},
-        "e2e_node_contract": {"value": node_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * W_ * H_,
+        "e2e_node_contract": {"value": node_value, "unit": UNIT, "h2d_bytes_per_step": (1 if strm else 2) * B * W_ * H_,
                               "d2h_bytes_per_step": 12 * B, "steps": e2e_steps,
-                              "api": ("ofb_farneback_batch_stats" if args.e2e_sync else "ofb_farneback_batch_stats_async + ofb_wait") +
+                              "api": ("ofb_farneback_stream + ofb_flow_u_stats (synchronous)" if strm else
+                                      "ofb_farneback_batch_stats" if args.e2e_sync else "ofb_farneback_batch_stats_async + ofb_wait") +
                                      " (host frames in, on-device mean + exact median of u out: "
                                      "the reduction every node applies, lfn3_sub_node.py:205-212)"},
         "gpu_launches": int(launches),
@@ -607,7 +636,9 @@ def main():
     ap.add_argument("--batch", type=int, default=18, help="frame pairs per step per GPU")
     ap.add_argument("--frame", default="1080p", choices=["vga", "1080p", "4k"],
                     help="frame size of the pairs/sequence modes (1080p = the BASELINE.json metric; vga = config 0, 4k = config 3)")
-    ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence", "tiled", "lk"])
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence", "stream", "tiled", "lk"],
+                    help="pairs: independent pairs (the headline); sequence: B+1 consecutive frames of one stream per call; "
+                         "stream: one new frame of each of B camera streams per call, temporal state kept on the GPU")
     ap.add_argument("--tile-size", default="8k", choices=["8k", "4k", "1080p"], help="--mode tiled: frame size")
     ap.add_argument("--no-tiled-check", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)

@@ -165,6 +165,28 @@ int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_f
                                   int height, size_t pitch_bytes, size_t image_stride_bytes,
                                   float* d_flow, const ofb_farneback_params* params);
 
+/* ---- camera streams: the temporal state stays on the GPU ---------------------------------------
+ * A node calls once per received frame (lfn3_sub_node.py:141-222 keeps `self.prev_tensor` and runs the flow on
+ * (previous, current)).  The handle keeps, per stream, what the next call needs from the current frame: the
+ * polynomial expansion at every pyramid level (default window; the previous uint8 frame otherwise), so a call
+ * uploads ONE frame per stream and expands only that frame.  Results are identical to ofb_farneback on
+ * (previous frame, frame).
+ *   frames[i]: the new frame of stream i, i < n_streams <= max_batch.  The first call — and the first after a change
+ *   of n_streams, size or parameters, or after ofb_stream_reset — only primes the state: *produced = 0 and no flow is
+ *   written (the node's "first frame only primes" branch, lfn3_sub_node.py:164-167).  Later calls write flow[i]
+ *   (float32 [height][width][2]; flow == NULL keeps the fields on the device for ofb_flow_u_stats /
+ *   ofb_flow_postfilter) and set *produced = n_streams.  Synchronous. */
+int ofb_farneback_stream(ofb_handle* h, int n_streams, const uint8_t* const* frames, int width, int height,
+                         size_t stride_bytes, float* const* flow, size_t flow_stride_bytes,
+                         const ofb_farneback_params* params, int* produced);
+/* The same on device-resident frames (n_streams images at d_frames, row pitch / image stride in bytes), asynchronous
+ * on the handle's stream; d_flow receives n_streams packed fields when *produced != 0. */
+int ofb_farneback_stream_device(ofb_handle* h, int n_streams, const uint8_t* d_frames, int width, int height,
+                                size_t pitch_bytes, size_t image_stride_bytes, float* d_flow,
+                                const ofb_farneback_params* params, int* produced);
+/* Forgets the streams' state: the next stream call primes again. */
+int ofb_stream_reset(ofb_handle* h);
+
 /* ---- spatially tiled mode: ONE frame pair split into row strips over the GPUs of a node -------
  * (BASELINE.json config 5: 7680x4320 over 8 B200.)  One handle per GPU ("rank"), all created with the
  * same max_width/max_height.  Every rank holds the two source frames and computes the rows it owns at

@@ -68,6 +68,11 @@ _SIGNATURES = {
                                        C.c_size_t, C.c_void_p, C.POINTER(FarnebackParams)]),
     "ofb_farneback_sequence_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
                                                 C.c_size_t, C.c_void_p, C.POINTER(FarnebackParams)]),
+    "ofb_farneback_stream": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_size_t,
+                                       C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(FarnebackParams), C.POINTER(C.c_int)]),
+    "ofb_farneback_stream_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                              C.c_void_p, C.POINTER(FarnebackParams), C.POINTER(C.c_int)]),
+    "ofb_stream_reset": (C.c_int, [C.c_void_p]),
     "ofb_launch_count": (C.c_uint64, [C.c_void_p]),
     "ofb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ofb_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -167,6 +167,8 @@ int ofb_destroy(ofb_handle* h) {
   if (h->h_flow) cudaFreeHost(h->h_flow);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->d_gray) cudaFree(h->d_gray);
+  if (h->stream_state.pool) cudaFree(h->stream_state.pool);
+  if (h->stream_state.d_prev) cudaFree(h->stream_state.d_prev);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->tile.imported && !h->tile.same_process) {
     for (int r = 0; r < h->tile.world; r++) {
@@ -461,6 +463,141 @@ int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_f
   OFB_CUDA(h, cudaSetDevice(h->device));
   return farneback_run(h, n_pairs, true, d_frames, d_frames, width, height, pitch_bytes, image_stride_bytes, d_flow,
                        nullptr, params);
+}
+
+// ---- camera streams: temporal state on the device --------------------------------------------------------------
+static bool same_params(const ofb_farneback_params& a, const ofb_farneback_params& b) {
+  return a.pyr_scale == b.pyr_scale && a.levels == b.levels && a.winsize == b.winsize && a.iterations == b.iterations &&
+         a.poly_n == b.poly_n && a.poly_sigma == b.poly_sigma && a.flags == b.flags;
+}
+
+// (re)build the stream cache for n streams of width x height; returns OFB_OK with st.n == n
+static int stream_prepare(ofb_handle* h, int n, int width, int height, const ofb_farneback_params* p) {
+  ofb_handle::Stream& st = h->stream_state;
+  const bool cached = farneback_stream_supported(h, p);
+  const size_t N = (size_t)width * height;
+  if (cached) {
+    Level sched[kMaxLevels];
+    int nl = 0;
+    if (farneback_levels(width, height, p, sched, &nl) != OFB_OK)
+      return set_error(h, OFB_ERR_INVALID_ARG, "too many pyramid levels");
+    size_t need = 0;
+    for (int l = 0; l < nl; l++)   // per level and half: n frames + spare rows (prefetching schedules read ahead)
+      need += 2 * (((size_t)n * sched[l].width * sched[l].height + (size_t)kRowPad * sched[l].width) * 20 + 512);
+    if (need > st.pool_bytes) {
+      OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (st.pool) cudaFree(st.pool);
+      st.pool = nullptr; st.pool_bytes = 0;
+      if (cudaMalloc(&st.pool, need) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(h, OFB_ERR_ALLOC, "stream cache: cannot allocate %zu MB", need >> 20);
+      }
+      st.pool_bytes = need;
+    }
+    char* q = static_cast<char*>(st.pool);
+    for (int half = 0; half < 2; half++)
+      for (int l = 0; l < nl; l++) {
+        const size_t e = (size_t)n * sched[l].width * sched[l].height + (size_t)kRowPad * sched[l].width;
+        st.ctx.RA[half][l] = reinterpret_cast<float4*>(q); q += align_up(e * 16, 256);
+        st.ctx.RB[half][l] = reinterpret_cast<float*>(q);  q += align_up(e * 4, 256);
+      }
+  } else if (2 * n * N > st.prev_bytes) {      // two packed frame sets: previous and current, alternating
+    OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (st.d_prev) cudaFree(st.d_prev);
+    st.d_prev = nullptr; st.prev_bytes = 0;
+    OFB_CUDA(h, cudaMalloc(&st.d_prev, 2 * n * N));
+    st.prev_bytes = 2 * n * N;
+  }
+  st.ctx.cur = 0;
+  st.cached = cached;
+  st.n = n; st.w = width; st.h = height; st.params = *p;
+  return OFB_OK;
+}
+
+int ofb_stream_reset(ofb_handle* h) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  h->stream_state.n = 0;
+  return OFB_OK;
+}
+
+int ofb_farneback_stream_device(ofb_handle* h, int n_streams, const uint8_t* d_frames, int width, int height,
+                                size_t pitch_bytes, size_t image_stride_bytes, float* d_flow,
+                                const ofb_farneback_params* params, int* produced) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (produced) *produced = 0;
+  if (!d_frames || !d_flow) return set_error(h, OFB_ERR_INVALID_ARG, "NULL device pointer");
+  int s = validate_farneback(h, n_streams, width, height, params);
+  if (s) return s;
+  if (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
+    return set_error(h, OFB_ERR_INVALID_ARG, "USE_INITIAL_FLOW is not supported by the stream call");
+  if (pitch_bytes < (size_t)width) return set_error(h, OFB_ERR_INVALID_ARG, "pitch smaller than width");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  ofb_handle::Stream& st = h->stream_state;
+  const bool prime = st.n != n_streams || st.w != width || st.h != height || !same_params(st.params, *params);
+  if (prime && (s = stream_prepare(h, n_streams, width, height, params))) return s;
+  const size_t N = (size_t)width * height;
+  if (st.cached) {
+    st.ctx.prime_only = prime;
+    st.ctx.cur ^= 1;                              // the new frames' expansions go to the other half
+    s = farneback_run(h, n_streams, false, nullptr, d_frames, width, height, pitch_bytes, image_stride_bytes, d_flow,
+                      nullptr, params, &st.ctx);
+    if (s) { st.n = 0; return s; }
+  } else {
+    // configurations the expansion cache does not serve (Gaussian window, unusual radii, ...): the previous frames are
+    // kept instead (packed, two alternating sets) and the pair path runs on (previous, current)
+    st.ctx.cur ^= 1;
+    uint8_t* cur = st.d_prev + (size_t)st.ctx.cur * n_streams * N;
+    const uint8_t* prev = st.d_prev + (size_t)(st.ctx.cur ^ 1) * n_streams * N;
+    for (int i = 0; i < n_streams; i++)
+      OFB_CUDA(h, cudaMemcpy2DAsync(cur + (size_t)i * N, (size_t)width, d_frames + (size_t)i * image_stride_bytes, pitch_bytes,
+                                    width, height, cudaMemcpyDeviceToDevice, h->stream));
+    if (!prime) {
+      s = farneback_run(h, n_streams, false, prev, cur, width, height, (size_t)width, N, d_flow, nullptr, params);
+      if (s) { st.n = 0; return s; }
+    }
+  }
+  if (produced) *produced = prime ? 0 : n_streams;
+  return OFB_OK;
+}
+
+int ofb_farneback_stream(ofb_handle* h, int n_streams, const uint8_t* const* frames, int width, int height,
+                         size_t stride_bytes, float* const* flow, size_t flow_stride_bytes,
+                         const ofb_farneback_params* params, int* produced) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (produced) *produced = 0;
+  if (!frames) return set_error(h, OFB_ERR_INVALID_ARG, "NULL array pointer");
+  int s = validate_farneback(h, n_streams, width, height, params);
+  if (s) return s;
+  if (stride_bytes == 0) stride_bytes = (size_t)width;
+  if (stride_bytes < (size_t)width) return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than width");
+  const size_t row_flow = (size_t)width * 2 * sizeof(float);
+  if (flow_stride_bytes == 0) flow_stride_bytes = row_flow;
+  if (flow_stride_bytes < row_flow) return set_error(h, OFB_ERR_INVALID_ARG, "flow stride smaller than a row");
+  for (int i = 0; i < n_streams; i++)
+    if (!frames[i]) return set_error(h, OFB_ERR_INVALID_ARG, "NULL frame pointer");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  // drain the pipelined batch calls: the stream call shares their staging
+  OFB_CUDA(h, cudaStreamSynchronize(h->s_in));
+  OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
+  h->pipe_n = 0;
+  const size_t pitch = align_up((size_t)width, 16), istride = pitch * height;
+  for (int i = 0; i < n_streams; i++)   // (pageable frames: the runtime stages them; pinned ones are DMA'd directly)
+    OFB_CUDA(h, cudaMemcpy2DAsync(h->d_src + (size_t)i * istride, pitch, frames[i], stride_bytes, width, height,
+                                  cudaMemcpyHostToDevice, h->stream));
+  int got = 0;
+  s = ofb_farneback_stream_device(h, n_streams, h->d_src, width, height, pitch, istride, h->d_flow_out, params, &got);
+  if (s) return s;
+  if (got && flow) {
+    const size_t fl_img = (size_t)width * height * 2;
+    for (int i = 0; i < n_streams; i++) {
+      if (!flow[i]) return set_error(h, OFB_ERR_INVALID_ARG, "NULL flow pointer");
+      OFB_CUDA(h, cudaMemcpy2DAsync(flow[i], flow_stride_bytes, h->d_flow_out + i * fl_img, row_flow, row_flow, height,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (produced) *produced = got;
+  return OFB_OK;
 }
 
 static int farneback_batch_impl(ofb_handle* h, int n, const uint8_t* const* prev, const uint8_t* const* next,

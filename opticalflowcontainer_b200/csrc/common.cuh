@@ -67,6 +67,16 @@ struct PeerTab {
   int r_lo, r_hi, f_lo, f_hi;
 };
 
+// Camera-stream cache (ofb_farneback_stream*): the polynomial expansions of the streams' latest frames at every pyramid
+// level, double-buffered — a call expands only the new frames into half `cur` and reads the previous frames' from the
+// other half.
+struct StreamCtx {
+  float4* RA[2][kMaxLevels];
+  float* RB[2][kMaxLevels];
+  int cur;
+  bool prime_only;     // first frame of the streams: expansions only, no flow
+};
+
 inline int cv_round(double v) { return (int)__builtin_nearbyint(v); }  // round-half-even like cvRound
 
 }  // namespace ofb
@@ -135,6 +145,16 @@ struct ofb_handle {
     unsigned epoch = 0;
     int r_lo = 0, r_hi = 0;          // R rows present locally at the current level (own + pulled halo)
   } tile;
+  // camera-stream state (api.cu: ofb_farneback_stream*)
+  struct Stream {
+    ofb::StreamCtx ctx = {};
+    void* pool = nullptr;        // one allocation behind ctx.RA / ctx.RB
+    uint8_t* d_prev = nullptr;   // the streams' previous frames (u8), for configurations the cache does not serve
+    size_t pool_bytes = 0, prev_bytes = 0;
+    int n = 0, w = 0, h = 0;     // streams and frame size of the cached state (n == 0: not primed)
+    ofb_farneback_params params = {};
+    bool cached = false;         // expansions cached (fused path) vs previous frames only
+  } stream_state;
   // last result bookkeeping for ofb_flow_u_stats
   const float* last_flow = nullptr;
   int last_n = 0, last_w = 0, last_h = 0;
@@ -204,7 +224,11 @@ void prepare_blur(int winsize, bool gaussian, BlurCoef* bc);
 //   sequence == true : d_prev holds n_pairs+1 consecutive frames (d_next ignored)
 int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
                   int width, int height, size_t pitch, size_t image_stride, float* d_flow_out,
-                  const float* d_init_flow, const ofb_farneback_params* p);
+                  const float* d_init_flow, const ofb_farneback_params* p, const StreamCtx* sc = nullptr);
+// the schedule farneback_run would use (level sizes), for sizing the stream cache
+int farneback_levels(int width, int height, const ofb_farneback_params* p, Level* out, int* n_out);
+// true if farneback_run can serve this configuration from the stream cache (fused box-window path, marching PolyExp)
+bool farneback_stream_supported(const ofb_handle* h, const ofb_farneback_params* p);
 
 // Spatially tiled mode (tiled.cuh)
 int farneback_run_tiled(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,

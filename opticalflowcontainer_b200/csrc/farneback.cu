@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(256) k_init_flow_area(const float2* __restrict
 template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false,
           bool REUSE = false>
 static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                 int f1_offset, int m, float reg, cudaStream_t st, int y_begin = 0, int y_end = -1,
+                                 const RSet& rs, int m, float reg, cudaStream_t st, int y_begin = 0, int y_end = -1,
                                  const PeerTab* tab = nullptr, int my_rank = 0) {
   if (y_end < 0) y_end = hh;
   if (y_end <= y_begin) return cudaSuccess;
@@ -484,15 +484,27 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   segs = (rows + seg_rows - 1) / seg_rows;
   dim3 g(strips * segs, n_pairs);
   k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED, REUSE><<<g, COLS + (CH / CLOOP) * COLS / PXT, smem, st>>>(
-      h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank);
+      rs, fin, fout, w, hh, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank);
   return cudaGetLastError();
+}
+
+int farneback_levels(int width, int height, const ofb_farneback_params* p, Level* out, int* n_out) {
+  return build_schedule(width, height, p->pyr_scale, p->levels, out, n_out);
+}
+
+bool farneback_stream_supported(const ofb_handle* h, const ofb_farneback_params* p) {
+  BlurCoef bc;
+  prepare_blur(p->winsize, (p->flags & OFB_OPTFLOW_FARNEBACK_GAUSSIAN) != 0, &bc);
+  const bool use_fused = !bc.gaussian && bc.m >= 2 && bc.m <= 19 && !h->force_generic;
+  return use_fused && h->iter_ws != 1 && p->poly_n <= PX_MAXN && !h->polyexp_tile &&
+         !(p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW);
 }
 
 static inline dim3 grid2d(int w, int h, int z, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y, z); }
 
 int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
                   int width, int height, size_t pitch, size_t image_stride, float* d_flow_out,
-                  const float* d_init_flow, const ofb_farneback_params* p) {
+                  const float* d_init_flow, const ofb_farneback_params* p, const StreamCtx* sc) {
   Level sched[kMaxLevels];
   int n_levels = 0;
   if (build_schedule(width, height, p->pyr_scale, p->levels, sched, &n_levels) != OFB_OK)
@@ -506,12 +518,14 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   BlurCoef bc;
   prepare_blur(p->winsize, (p->flags & OFB_OPTFLOW_FARNEBACK_GAUSSIAN) != 0, &bc);
 
-  const int frames = sequence ? n_pairs + 1 : 2 * n_pairs;
+  // camera-stream call (sc): only the n new frames (d_next) are expanded; the previous frames' expansions of every
+  // level are the ones the previous call left in the other half of the stream cache
+  const int frames = sc ? n_pairs : (sequence ? n_pairs + 1 : 2 * n_pairs);
   const int f1_offset = sequence ? 1 : n_pairs;
   FrameSrc src;
-  src.a = d_prev;
+  src.a = sc ? d_next : d_prev;
   src.b = sequence ? d_prev : d_next;
-  src.na = sequence ? frames : n_pairs;
+  src.na = (sc || sequence) ? frames : n_pairs;
   src.pitch = pitch;
   src.image_stride = image_stride;
   cudaStream_t st = h->stream;
@@ -525,12 +539,20 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
     OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
   }
 
+  if (sc && (!use_fused || h->iter_ws == 1 || pc.n > PX_MAXN || h->polyexp_tile || n_levels > kMaxLevels))
+    return set_error(h, OFB_ERR_INVALID_ARG, "internal: stream cache used with an unsupported configuration");
   float2* prev_flow = nullptr;
   int prev_w = 0, prev_h = 0;
   for (int li = 0; li < n_levels; li++) {
     const Level& lv = sched[li];
     const int w = lv.width, hh = lv.height;
     const bool last_level = li == n_levels - 1;
+    const size_t npx = (size_t)w * hh;
+    float4* const RAw = sc ? sc->RA[sc->cur][li] : h->d_RA;      // where this level's expansions are written
+    float* const RBw = sc ? sc->RB[sc->cur][li] : h->d_RB;
+    const RSet rs = sc ? RSet{sc->RA[sc->cur ^ 1][li], sc->RB[sc->cur ^ 1][li], RAw, RBw}
+                       : RSet{h->d_RA, h->d_RB, h->d_RA + (size_t)f1_offset * npx, h->d_RB + (size_t)f1_offset * npx};
+    const bool prime_only = sc && sc->prime_only;
     // flow buffers: cur (input of this level) must differ from the buffer holding the previous
     // level's result (read by the upsample); alt may alias it (first written after the upsample).
     float2* cur = prev_flow == h->d_flow[0] ? h->d_flow[1] : h->d_flow[0];
@@ -539,7 +561,9 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
 #define TE() do { int s__ = timing_end(h); if (s__) return s__; } while (0)
     // --- initial flow of the level
     TB(OFB_STAGE_FLOW_INIT);
-    if (prev_flow == nullptr) {
+    if (prime_only) {
+      // first frame of the streams: expansions only
+    } else if (prev_flow == nullptr) {
       if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
         k_init_flow_area<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>((const float2*)d_init_flow, width, height, cur, w,
                                                                       hh, (double)width / w, (double)height / hh,
@@ -621,10 +645,10 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
 #define OFB_PX_LAUNCH(NT)                                                                                           \
   do {                                                                                                              \
     if (fused_src)                                                                                                  \
-      k_polyexp_march<NT, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], h->d_RA, h->d_RB, w, hh,      \
+      k_polyexp_march<NT, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], RAw, RBw, w, hh,              \
                                                     seg_rows, strips, pc, 0, hh);                                   \
     else                                                                                                            \
-      k_polyexp_march<NT, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, h->d_RA, h->d_RB, w, hh, seg_rows,     \
+      k_polyexp_march<NT, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, RAw, RBw, w, hh, seg_rows,             \
                                                     strips, pc, 0, hh);                                             \
   } while (0)
       if (pc.n == 5) OFB_PX_LAUNCH(5); else if (pc.n == 7) OFB_PX_LAUNCH(7); else OFB_PX_LAUNCH(0);
@@ -640,7 +664,7 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
     TE();
     // --- iterations
     float2* fin = cur;
-    for (int it = 0; it < p->iterations; it++) {
+    for (int it = 0; it < (prime_only ? 0 : p->iterations); it++) {
       const bool last_it = it == p->iterations - 1;
       float2* fout = (last_level && last_it) ? (float2*)d_flow_out : (fin == cur ? alt : cur);
       TB(OFB_STAGE_ITERATION);
@@ -649,7 +673,7 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
           // k_iter_v: float van Herk / Gil-Werman vertical sums, no FP64 (default)
           const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
           cudaError_t e;
-#define OFB_V_ARGS h, fin, fout, w, hh, n_pairs, f1_offset, bc.m, reg, st
+#define OFB_V_ARGS h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st
           const int pfd = h->iter_prefetch ? h->iter_pfd : 0;
           if (bc.m == 7) {
             if (h->iter_cols == 128) {
@@ -701,7 +725,7 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
       TE();
       fin = fout;
     }
-    if (p->iterations == 0 && last_level) {
+    if (p->iterations == 0 && last_level && !prime_only) {
       OFB_CUDA(h, cudaMemcpyAsync(d_flow_out, fin, (size_t)n_pairs * w * hh * sizeof(float2),
                                   cudaMemcpyDeviceToDevice, st));
     }

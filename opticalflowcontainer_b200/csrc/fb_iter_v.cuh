@@ -32,6 +32,16 @@ namespace ofb {
 // persistent corner rows do not push the producers' loads behind their first use.
 constexpr int REUSE_PROD_REGS = 88, REUSE_CONS_REGS = 56;
 
+// Polynomial coefficients of the two frames of every pair: frame 0 of pair i at A0/B0 + i*n, frame 1 at A1/B1 + i*n
+// (n = level pixels).  Independent pairs: A1 = A0 + n_pairs*n; consecutive frames of a stream: A1 = A0 + n; the
+// camera-stream call: A0 = the expansions kept from the previous call, A1 = the new frames' (different arrays).
+struct RSet {
+  const float4* A0;
+  const float* B0;
+  const float4* A1;
+  const float* B1;
+};
+
 template <int COLS, int CH>
 constexpr int iter_v_smem_floats(int m) { return (2 * CH + 2 * m + 1) * 5 * COLS; }
 
@@ -54,8 +64,8 @@ constexpr int iter_v_smem_floats(int m) { return (2 * CH + 2 * m + 1) * 5 * COLS
 template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false,
           bool REUSE = false>
 __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
-    k_iter_v(const float4* __restrict__ RA, const float* __restrict__ RB, const float2* __restrict__ flow_in,
-             float2* __restrict__ flow_out, int w, int h, int f1_offset, int m_rt, float reg, int seg_rows,
+    k_iter_v(const RSet rs, const float2* __restrict__ flow_in,
+             float2* __restrict__ flow_out, int w, int h, int m_rt, float reg, int seg_rows,
              int strips, int y_begin, int y_end, PeerTab tab, int my_rank) {
   static_assert(PXT == 4 || PXT == 8, "4 or 8 adjacent pixels per consumer thread");
   constexpr int GROUPS = COLS / PXT;
@@ -89,10 +99,10 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
     // ------------------------------------------------------------------ PRODUCERS (one column each)
     if constexpr (REUSE && RIF == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REUSE_PROD_REGS));
     else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(96));
-    const float4* RA0 = RA + (size_t)pair * n;
-    const float* RB0 = RB + (size_t)pair * n;
-    const float4* RA1 = RA + (size_t)(pair + f1_offset) * n;
-    const float* RB1 = RB + (size_t)(pair + f1_offset) * n;
+    const float4* RA0 = rs.A0 + (size_t)pair * n;
+    const float* RB0 = rs.B0 + (size_t)pair * n;
+    const float4* RA1 = rs.A1 + (size_t)pair * n;
+    const float* RB1 = rs.B1 + (size_t)pair * n;
     const float2* fin = flow_in + (size_t)pair * n;
     asm volatile("" : "+l"(RA0), "+l"(RB0), "+l"(RA1), "+l"(RB1), "+l"(fin));   // keep the bases, do not re-derive
     const unsigned uw = (unsigned)w, uh = (unsigned)h;

@@ -261,11 +261,13 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
   TE();
   const float reg = (float)(1e-3 / ((double)pl.bc.scale * (double)pl.bc.scale));
   cudaError_t e;
+  // (the tiled kernel takes its R pointers per owner rank from the peer table; own buffers for the prefetch addresses)
+  const RSet rs1 = {h->d_RA, h->d_RB, h->d_RA + (size_t)w * hh, h->d_RB + (size_t)w * hh};
   TB(OFB_STAGE_ITERATION);
   if (pl.bc.m == 7)
-    e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, true>(h, fin, fout, w, hh, 1, 1, pl.bc.m, reg, st, yb, ye, &t, rank);
+    e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, yb, ye, &t, rank);
   else
-    e = launch_iter_v<0, 128, 4, 1, 0, 4, 1, 1, true>(h, fin, fout, w, hh, 1, 1, pl.bc.m, reg, st, yb, ye, &t, rank);
+    e = launch_iter_v<0, 128, 4, 1, 0, 4, 1, 1, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, yb, ye, &t, rank);
   if (e != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "tiled k_iter_v launch failed: %s", cudaGetErrorString(e));
   h->launches++;
   TE();

@@ -218,6 +218,52 @@ class FlowEngine:
             _lib.check(st, self._h)
         return mean, med
 
+    def farneback_stream(self, frames: np.ndarray, download: bool = True, out: Optional[np.ndarray] = None,
+                         **kw) -> Optional[np.ndarray]:
+        """Camera-stream call (ofb_farneback_stream): ``frames`` uint8 [n,H,W] = the new frame of each of n streams.
+        Returns None while priming (first call, or after a change of n / size / parameters / :meth:`stream_reset`),
+        then the flow of (previous frame, frame) per stream as float32 [n,H,W,2] — or True with ``download=False``
+        (fields stay on the device for :meth:`flow_u_stats` / :meth:`flow_postfilter`)."""
+        frames = np.asarray(frames)
+        if frames.ndim == 2:
+            frames = frames[None]
+        if frames.dtype != np.uint8 or frames.ndim != 3 or not frames.flags.c_contiguous:
+            raise OfbError(1, "farneback_stream: need contiguous uint8 [n,H,W]")
+        n, hgt, wid = frames.shape
+        p = self._fb_params(kw.get("pyr_scale", 0.5), kw.get("levels", 3), kw.get("winsize", 15),
+                            kw.get("iterations", 3), kw.get("poly_n", 5), kw.get("poly_sigma", 1.2),
+                            kw.get("flags", 0))
+        fp = (C.c_void_p * n)(*[frames.ctypes.data + i * hgt * wid for i in range(n)])
+        if download and out is None:
+            out = np.empty((n, hgt, wid, 2), np.float32)
+        if download and (out.shape != (n, hgt, wid, 2) or out.dtype != np.float32 or not out.flags.c_contiguous):
+            raise OfbError(1, "farneback_stream: out must be contiguous float32 [n,H,W,2]")
+        op = (C.c_void_p * n)(*[out.ctypes.data + i * hgt * wid * 8 for i in range(n)]) if download else None
+        got = C.c_int(0)
+        with self._lock:
+            st = self._lib.ofb_farneback_stream(self._h, n, fp, wid, hgt, wid, op, 0, C.byref(p), C.byref(got))
+            _lib.check(st, self._h)
+        if got.value == 0:
+            return None
+        return out if download else True
+
+    def farneback_stream_device(self, n: int, d_frames: int, width: int, height: int, pitch: int, image_stride: int,
+                                d_flow: int, **kw) -> int:
+        """Asynchronous device-pointer form (ofb_farneback_stream_device); returns the number of fields produced."""
+        p = self._fb_params(kw.get("pyr_scale", 0.5), kw.get("levels", 3), kw.get("winsize", 15),
+                            kw.get("iterations", 3), kw.get("poly_n", 5), kw.get("poly_sigma", 1.2),
+                            kw.get("flags", 0))
+        got = C.c_int(0)
+        with self._lock:
+            st = self._lib.ofb_farneback_stream_device(self._h, n, d_frames, width, height, pitch, image_stride, d_flow,
+                                                       C.byref(p), C.byref(got))
+            _lib.check(st, self._h)
+        return got.value
+
+    def stream_reset(self):
+        with self._lock:
+            _lib.check(self._lib.ofb_stream_reset(self._h), self._h)
+
     def farneback_device(self, n: int, d_prev: int, d_next: int, width: int, height: int, pitch: int,
                          image_stride: int, d_flow: int, sequence: bool = False, **kw):
         """Asynchronous device-pointer call on the handle's stream (see ofb_farneback_device /

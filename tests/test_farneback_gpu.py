@@ -233,3 +233,40 @@ def test_iteration_schedules_bit_identical(built_lib):
             os.environ.pop("OFB_ITER_MODE", None)
         else:
             os.environ["OFB_ITER_MODE"] = old
+
+
+@pytest.mark.parametrize("flags,winsize", [(0, 15), (0, 9), (256, 15)])
+def test_stream_call_equals_pair_calls(built_lib, flags, winsize):
+    """ofb_farneback_stream: one new frame per stream per call, the previous frame's state kept on the device.  Every
+    field equals ofb_farneback(previous, frame) bit for bit — for the cached-expansion path (box window) and for the
+    kept-frame path (Gaussian window) — across priming, a parameter change and a reset."""
+    import opticalflowcontainer_b200 as ofb
+    n, h, w = 3, 135, 240
+    eng = ofb.FlowEngine(w, h, n, 0)
+    ref = ofb.FlowEngine(w, h, n, 0)       # same batch size: same launch geometry, hence the same float summation order
+    try:
+        seqs = []
+        for s in range(n):
+            base = synth.synth_pair(h, w, 40 + s, (0.0, 0.0))[0]
+            seqs.append([synth.subpixel_shift(base, 1.3 * t * (s + 1), -0.7 * t) for t in range(4)])
+        kw = dict(pyr_scale=0.5, levels=3, winsize=winsize, iterations=3, poly_n=5, poly_sigma=1.2, flags=flags)
+        out = eng.farneback_stream(np.stack([seqs[s][0] for s in range(n)]), **kw)
+        assert out is None                                   # priming
+        for t in range(1, 4):
+            out = eng.farneback_stream(np.stack([seqs[s][t] for s in range(n)]), **kw)
+            assert out is not None and out.shape == (n, h, w, 2)
+            want = ref.farneback_batch([seqs[s][t - 1] for s in range(n)], [seqs[s][t] for s in range(n)], **kw)
+            assert np.array_equal(out, want)
+        # fields can stay on the device for the node reduction
+        assert eng.farneback_stream(np.stack([seqs[s][2] for s in range(n)]), download=False, **kw) is True
+        mean, med = eng.flow_u_stats(n)
+        want = ref.farneback_batch([seqs[s][3] for s in range(n)], [seqs[s][2] for s in range(n)], **kw)
+        assert med[0] == np.float32(np.median(want[0][..., 0]))
+        # a parameter change primes again; so does a reset
+        kw2 = dict(kw, levels=2)
+        assert eng.farneback_stream(np.stack([seqs[s][0] for s in range(n)]), **kw2) is None
+        assert eng.farneback_stream(np.stack([seqs[s][1] for s in range(n)]), **kw2) is not None
+        eng.stream_reset()
+        assert eng.farneback_stream(np.stack([seqs[s][1] for s in range(n)]), **kw2) is None
+    finally:
+        eng.close(); ref.close()
