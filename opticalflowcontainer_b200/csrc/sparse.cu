@@ -242,76 +242,118 @@ __global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ ei
   if (slot < cap) keys[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * w + x);
 }
 
-// Greedy minimum-distance selection in sorted order (lexicographically-first maximal independent
-// set): one warp, 32 candidates per round.  Each lane tests its candidate against the corners already
-// accepted (grid of cell = cvRound(minDistance), +-1 cell), then the round is resolved in order with
-// ballots/shuffles.
-__global__ void __launch_bounds__(32) k_greedy_select(const unsigned long long* __restrict__ keys,
-                                                      const unsigned int* __restrict__ count_ptr, unsigned int cap,
-                                                      int w, int h, float min_dist, int max_corners,
-                                                      unsigned int* __restrict__ grid_cnt, ushort2* __restrict__ grid_pts,
-                                                      float2* __restrict__ corners, unsigned int* __restrict__ n_out) {
-  const int lane = threadIdx.x;
+// Greedy minimum-distance selection in sorted order (lexicographically-first maximal independent set), exactly
+// cv2's sequential rule, in rounds of 1024 candidates by one CTA:
+//   phase 1 (1024 threads): every candidate of the round is tested against the corners accepted in EARLIER rounds
+//            (grid of cell = cvRound(minDistance), +-1 cell); the survivors are compacted in rank order;
+//   phase 2 (warp 0): the survivors are resolved in order, 32 at a time — tested against the grid again (it now also
+//            holds the corners accepted earlier in this round), then within the 32 by ballots/shuffles — and committed.
+// Most candidates die in phase 1, so the sequential part only sees (accepted + in-round conflicts) candidates: ~3x fewer
+// dependent global-memory round trips than the one-warp sweep over all candidates.
+constexpr int GS_THREADS = 1024;
+
+__device__ __forceinline__ bool gs_far_from_accepted(int x, int y, int cell, int gw, int gh, float md2,
+                                                     const unsigned int* grid_cnt, const ushort2* grid_pts) {
+  const int xc = x / cell, yc = y / cell;
+  for (int yy = max(0, yc - 1); yy <= min(gh - 1, yc + 1); yy++)
+    for (int xx = max(0, xc - 1); xx <= min(gw - 1, xc + 1); xx++) {
+      const int c = yy * gw + xx;
+      const unsigned int cnt = min(grid_cnt[c], (unsigned int)kGridSlots);   // (one CTA: barrier/fence-ordered, L1-coherent)
+      for (unsigned int k = 0; k < cnt; k++) {
+        const ushort2 p = grid_pts[c * kGridSlots + k];
+        const float dx = (float)(x - (int)p.x), dy = (float)(y - (int)p.y);
+        if (dx * dx + dy * dy < md2) return false;
+      }
+    }
+  return true;
+}
+
+__global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned long long* __restrict__ keys,
+                                                              const unsigned int* __restrict__ count_ptr, unsigned int cap,
+                                                              int w, int h, float min_dist, int max_corners,
+                                                              unsigned int* grid_cnt, ushort2* grid_pts,
+                                                              float2* __restrict__ corners, unsigned int* __restrict__ n_out) {
+  __shared__ unsigned int surv[GS_THREADS];          // x | y << 16, rank order
+  __shared__ unsigned int warp_cnt[GS_THREADS / 32];
+  __shared__ unsigned int s_nsurv, s_accepted;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned int total = min(*count_ptr, cap);
-  unsigned int accepted = 0;
   const unsigned int limit = max_corners > 0 ? (unsigned int)max_corners : 0xffffffffu;
   if (min_dist < 1.f) {
     const unsigned int n = min(total, limit);
-    for (unsigned int i = lane; i < n; i += 32) {
+    for (unsigned int i = tid; i < n; i += GS_THREADS) {
       const unsigned int idx = (unsigned int)(keys[i] & 0xffffffffu);
       corners[i] = make_float2((float)(idx % w), (float)(idx / w));
     }
-    if (lane == 0) *n_out = n;
+    if (tid == 0) *n_out = n;
     return;
   }
   const int cell = __float2int_rn(min_dist);
   const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
   const float md2 = min_dist * min_dist;
-  for (unsigned int base = 0; base < total && accepted < limit; base += 32) {
-    const unsigned int i = base + lane;
+  if (tid == 0) s_accepted = 0;
+  __syncthreads();
+  for (unsigned int base = 0; base < total; base += GS_THREADS) {
+    if (s_accepted >= limit) break;                  // (uniform: read after the barrier that ends a round)
+    // ---- phase 1
+    const unsigned int i = base + tid;
     bool alive = i < total;
     int x = 0, y = 0;
     if (alive) {
       const unsigned int idx = (unsigned int)(keys[i] & 0xffffffffu);
       x = idx % w;
       y = idx / w;
-      const int xc = x / cell, yc = y / cell;
-      for (int yy = max(0, yc - 1); yy <= min(gh - 1, yc + 1) && alive; yy++)
-        for (int xx = max(0, xc - 1); xx <= min(gw - 1, xc + 1) && alive; xx++) {
-          const int c = yy * gw + xx;
-          const unsigned int cnt = min(grid_cnt[c], (unsigned int)kGridSlots);
-          for (unsigned int k = 0; k < cnt; k++) {
-            const ushort2 p = grid_pts[c * kGridSlots + k];
-            const float dx = (float)(x - (int)p.x), dy = (float)(y - (int)p.y);
-            if (dx * dx + dy * dy < md2) { alive = false; break; }
-          }
+      alive = gs_far_from_accepted(x, y, cell, gw, gh, md2, grid_cnt, grid_pts);
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    unsigned int off = 0;
+    for (int k = 0; k < wid; k++) off += warp_cnt[k];
+    if (alive) surv[off + __popc(bal & ((1u << lane) - 1u))] = (unsigned int)x | ((unsigned int)y << 16);
+    if (tid == GS_THREADS - 1) s_nsurv = off + __popc(bal);
+    __syncthreads();
+    // ---- phase 2
+    if (wid == 0) {
+      const unsigned int ns = s_nsurv;
+      unsigned int accepted = s_accepted;
+      for (unsigned int cb = 0; cb < ns && accepted < limit; cb += 32) {
+        bool al = cb + lane < ns;
+        int sx = 0, sy = 0;
+        if (al) {
+          const unsigned int v = surv[cb + lane];
+          sx = (int)(v & 0xffffu);
+          sy = (int)(v >> 16);
+          al = gs_far_from_accepted(sx, sy, cell, gw, gh, md2, grid_cnt, grid_pts);
         }
-    }
-    // resolve the round in order
-    unsigned int alive_mask = __ballot_sync(0xffffffffu, alive);
-    unsigned int take_mask = 0;
-    while (alive_mask && accepted < limit) {
-      const int j = __ffs(alive_mask) - 1;
-      const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
-      take_mask |= 1u << j;
-      accepted++;
-      const float dx = (float)(x - xj), dy = (float)(y - yj);
-      const bool killed = lane > j && (dx * dx + dy * dy < md2);
-      alive_mask &= ~(1u << j);
-      alive_mask &= ~__ballot_sync(0xffffffffu, killed);
-    }
-    // commit the accepted ones (order inside the round = lane order)
-    if (take_mask >> lane & 1u) {
-      const unsigned int pos = accepted - __popc(take_mask) + __popc(take_mask & ((1u << lane) - 1u));
-      corners[pos] = make_float2((float)x, (float)y);
-      const int c = (y / cell) * gw + (x / cell);
-      const unsigned int s = atomicAdd(&grid_cnt[c], 1u);
-      if (s < (unsigned int)kGridSlots) grid_pts[c * kGridSlots + s] = make_ushort2((unsigned short)x, (unsigned short)y);
+        unsigned int alive_mask = __ballot_sync(0xffffffffu, al);
+        unsigned int take_mask = 0;
+        while (alive_mask && accepted < limit) {
+          const int j = __ffs(alive_mask) - 1;
+          const int xj = __shfl_sync(0xffffffffu, sx, j), yj = __shfl_sync(0xffffffffu, sy, j);
+          take_mask |= 1u << j;
+          accepted++;
+          const float dx = (float)(sx - xj), dy = (float)(sy - yj);
+          const bool killed = lane > j && (dx * dx + dy * dy < md2);
+          alive_mask &= ~(1u << j);
+          alive_mask &= ~__ballot_sync(0xffffffffu, killed);
+        }
+        if (take_mask >> lane & 1u) {
+          const unsigned int pos = accepted - __popc(take_mask) + __popc(take_mask & ((1u << lane) - 1u));
+          corners[pos] = make_float2((float)sx, (float)sy);
+          const int c = (sy / cell) * gw + (sx / cell);
+          const unsigned int sl = atomicAdd(&grid_cnt[c], 1u);
+          if (sl < (unsigned int)kGridSlots) grid_pts[c * kGridSlots + sl] = make_ushort2((unsigned short)sx, (unsigned short)sy);
+        }
+        __threadfence_block();
+        __syncwarp();
+      }
+      if (lane == 0) s_accepted = accepted;
     }
     __threadfence_block();
-    __syncwarp();
+    __syncthreads();
   }
-  if (lane == 0) *n_out = accepted;
+  if (tid == 0) *n_out = s_accepted;
 }
 
 // ======================================================================================
@@ -615,7 +657,7 @@ int ofb_good_features(ofb_handle* h, const uint8_t* image, int width, int height
   const int cell = p->min_distance >= 1 ? (int)__builtin_nearbyint(p->min_distance) : 1;
   const size_t cells = (size_t)((width + cell - 1) / cell) * ((height + cell - 1) / cell);
   if (p->min_distance >= 1) OFB_CUDA(h, cudaMemsetAsync(s->grid_cnt, 0, cells * sizeof(unsigned int), sm));
-  k_greedy_select<<<1, 32, 0, sm>>>(sorted, s->counters, (unsigned int)s->cand_cap, width, height, (float)p->min_distance,
+  k_greedy_select<<<1, GS_THREADS, 0, sm>>>(sorted, s->counters, (unsigned int)s->cand_cap, width, height, (float)p->min_distance,
                                     p->max_corners, s->grid_cnt, s->grid_pts, s->corners, s->counters + 2);
   OFB_LAUNCH_CHECK(h);
   OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, sm));

@@ -61,6 +61,7 @@ class FarnebackVelocityNode:
     poly_sigma: float = 1.2
     flags: int = 0
     on_device_reduce: bool = False
+    use_stream: bool = False      # keep the previous frame's state on the GPU (ofb_farneback_stream): one upload per frame
     # the "adapt" node's post-processing of the field (lfn3_adapt_node.py:236-251), applied on the device when set
     median_kernel_size: int = 0                       # 3 | 5: cv2.medianBlur of u and v
     flow_magnitude_threshold: Optional[float] = None  # u, v *= (|flow| >= threshold)
@@ -70,6 +71,7 @@ class FarnebackVelocityNode:
     prev_time: Optional[float] = None
     velocity_buffer: deque = field(default_factory=lambda: deque(maxlen=5), repr=False)
     last_flow: Optional[np.ndarray] = field(default=None, repr=False)
+    _stream_primed: bool = field(default=False, repr=False)
 
     def __post_init__(self):
         if self.engine is None:
@@ -88,8 +90,17 @@ class FarnebackVelocityNode:
         if dt <= 0:
             dt = 1e-3
         self.prev_time = stamp
-        flow = self.engine.farneback(self.prev_gray, gray, None, self.pyr_scale, self.levels, self.winsize,
-                                     self.iterations, self.poly_n, self.poly_sigma, self.flags)
+        if self.use_stream:
+            kw = dict(pyr_scale=self.pyr_scale, levels=self.levels, winsize=self.winsize, iterations=self.iterations,
+                      poly_n=self.poly_n, poly_sigma=self.poly_sigma, flags=self.flags)
+            if not self._stream_primed:                   # the engine primes on the frame the node primed on
+                self.engine.stream_reset()
+                self.engine.farneback_stream(self.prev_gray, **kw)
+                self._stream_primed = True
+            flow = self.engine.farneback_stream(gray, **kw)[0]
+        else:
+            flow = self.engine.farneback(self.prev_gray, gray, None, self.pyr_scale, self.levels, self.winsize,
+                                         self.iterations, self.poly_n, self.poly_sigma, self.flags)
         if self.median_kernel_size or self.flow_magnitude_threshold is not None or self.intensity_threshold is not None:
             self.engine.flow_postfilter(1, self.median_kernel_size, self.flow_magnitude_threshold,
                                         gray if self.intensity_threshold is not None else None, self.intensity_threshold)

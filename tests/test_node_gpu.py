@@ -245,3 +245,19 @@ def test_junction_velocity_matches_reference_logic(engine_factory):
     vx = junction_velocity(eng, prev, curr, 0.05, 0.0011)
     assert vx is not None and abs(vx - vx_ref) <= 1e-12 + 1e-9 * abs(vx_ref)
     assert junction_velocity(eng, prev[:2], curr, 0.05, 0.0011) is None      # fewer than 4 matches
+
+
+def test_node_stream_mode_equals_pair_mode(engine_factory):
+    """FarnebackVelocityNode(use_stream=True): previous frame's state on the GPU, same messages as the pair calls."""
+    from opticalflowcontainer_b200.node import FarnebackVelocityNode
+    h, w = 120, 160
+    base = synth.synth_pair(h, w, 21, (0.0, 0.0))[0]
+    frames = [synth.subpixel_shift(base, 1.1 * i, 0.4 * i) for i in range(4)]
+    a = FarnebackVelocityNode(engine=engine_factory(w, h), width=w, height=h, use_stream=True)
+    b = FarnebackVelocityNode(engine=engine_factory(w, h), width=w, height=h)
+    for i, f in enumerate(frames):
+        ra, rb = a.image_callback(f, 0.05 * i), b.image_callback(f, 0.05 * i)
+        assert (ra is None) == (rb is None)
+        if ra is not None:
+            assert ra[0].vector == rb[0].vector and ra[1].vector == rb[1].vector
+            assert np.array_equal(a.last_flow, b.last_flow)
