@@ -675,6 +675,18 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
           cudaError_t e;
 #define OFB_V_ARGS h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st
           const int pfd = h->iter_prefetch ? h->iter_pfd : 0;
+          // The setmaxnreg schedules move registers between the warpgroups of a CTA: 2 x 128 producers x 96 + 128
+          // consumers x 48 = 384 x 80.  They are only safe if the kernels really launch with 80 registers per thread
+          // (a smaller pool would leave the producers waiting for registers for ever); checked once, else mode 0.
+          static int regs_state = 0;   // 0 unknown, 1 ok, -1 not ok
+          if (regs_state == 0) {
+            cudaFuncAttributes a3, a2, a1;
+            const bool q = cudaFuncGetAttributes(&a3, k_iter_v<7, 256, 2, 2, 0, 4, 2, 1, false, true>) == cudaSuccess &&
+                           cudaFuncGetAttributes(&a2, k_iter_v<7, 256, 2, 2, 0, 4, 2, 1>) == cudaSuccess &&
+                           cudaFuncGetAttributes(&a1, k_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>) == cudaSuccess;
+            regs_state = (q && a3.numRegs >= 80 && a2.numRegs >= 80 && a1.numRegs >= 80) ? 1 : -1;
+          }
+          const bool regs_ok = regs_state == 1;
           if (bc.m == 7) {
             if (h->iter_cols == 128) {
               if (pfd == 0) e = launch_iter_v<7, 128, 2, 4, 0, 4>(OFB_V_ARGS);
@@ -682,9 +694,9 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
             } else {
               if (pfd == 0) e = launch_iter_v<7, 256, 2, 2, 0, 4>(OFB_V_ARGS);
               else if (pfd == 2) e = launch_iter_v<7, 256, 2, 2, 2, 4>(OFB_V_ARGS);
-              else if (h->iter_mode == 3) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1, false, true>(OFB_V_ARGS);   // default
-              else if (h->iter_mode == 2) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1>(OFB_V_ARGS);
-              else if (h->iter_mode == 1) e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>(OFB_V_ARGS);
+              else if (h->iter_mode == 3 && regs_ok) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1, false, true>(OFB_V_ARGS);   // default
+              else if (h->iter_mode == 2 && regs_ok) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1>(OFB_V_ARGS);
+              else if (h->iter_mode == 1 && regs_ok) e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>(OFB_V_ARGS);
               else e = launch_iter_v<7, 256, 2, 2, 3, 4>(OFB_V_ARGS);
             }
           } else {
