@@ -279,6 +279,18 @@ int ofb_cvt_gray(ofb_handle* h, const uint8_t* src, int width, int height, size_
 int ofb_cvt_gray_device(ofb_handle* h, const uint8_t* d_src, int width, int height, size_t src_pitch_bytes,
                         int rgb_order, uint8_t* d_dst, size_t dst_pitch_bytes);
 
+/* cv2.resize(src, (dst_width, dst_height)) — INTER_LINEAR on uint8, 1 or 3 interleaved channels, bit-exact with this
+ * cv2 build (11-bit fixed-point weights; oracle/resize_np.py).  The nodes resize every frame that does not have the
+ * configured size before anything else: lfn3_sub_node.py:152-153, lfn3_adapt_node.py:160-161.  Frames of any size
+ * (not limited by the handle's max_width/max_height).  Synchronous; stride 0 = packed. */
+int ofb_resize_u8(ofb_handle* h, const uint8_t* src, int src_width, int src_height, size_t src_stride_bytes, int channels,
+                  uint8_t* dst, int dst_width, int dst_height, size_t dst_stride_bytes);
+/* The whole ingest of a node in one call (lfn3_sub_node.py:148-159): a bgr8 / rgb8 frame of any size is uploaded once,
+ * resized to dst_width x dst_height if it has another size (cv2.resize, on the colour frame, as the nodes do) and
+ * converted to gray (cv2.cvtColor); dst receives the uint8 [dst_height][dst_width] frame the flow calls take. */
+int ofb_ingest_gray(ofb_handle* h, const uint8_t* src, int src_width, int src_height, size_t src_stride_bytes,
+                    int rgb_order, uint8_t* dst, int dst_width, int dst_height, size_t dst_stride_bytes);
+
 /* ---- sparse path: replaces cv2.goodFeaturesToTrack + cv2.calcOpticalFlowPyrLK -- */
 
 /* Shi-Tomasi corners of a uint8 image (host buffer).  corners_xy: capacity

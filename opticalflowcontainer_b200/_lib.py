@@ -73,6 +73,10 @@ _SIGNATURES = {
     "ofb_farneback_stream_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                               C.c_void_p, C.POINTER(FarnebackParams), C.POINTER(C.c_int)]),
     "ofb_stream_reset": (C.c_int, [C.c_void_p]),
+    "ofb_resize_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                C.c_size_t]),
+    "ofb_ingest_gray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_size_t]),
     "ofb_launch_count": (C.c_uint64, [C.c_void_p]),
     "ofb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ofb_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

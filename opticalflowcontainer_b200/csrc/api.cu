@@ -167,6 +167,10 @@ int ofb_destroy(ofb_handle* h) {
   if (h->h_flow) cudaFreeHost(h->h_flow);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->d_gray) cudaFree(h->d_gray);
+  if (h->ingest.d_a) cudaFree(h->ingest.d_a);
+  if (h->ingest.d_b) cudaFree(h->ingest.d_b);
+  if (h->ingest.d_tab) cudaFree(h->ingest.d_tab);
+  if (h->ingest.h_tab) cudaFreeHost(h->ingest.h_tab);
   if (h->stream_state.pool) cudaFree(h->stream_state.pool);
   if (h->stream_state.d_prev) cudaFree(h->stream_state.d_prev);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

@@ -145,6 +145,16 @@ struct ofb_handle {
     unsigned epoch = 0;
     int r_lo = 0, r_hi = 0;          // R rows present locally at the current level (own + pulled halo)
   } tile;
+  // frame ingest (ingest.cu): staging for frames of any size and the cached cv2.resize coordinate tables
+  struct Ingest {
+    uint8_t* d_a = nullptr;      // source frame
+    uint8_t* d_b = nullptr;      // result(s)
+    size_t a_bytes = 0, b_bytes = 0;
+    void* d_tab = nullptr;
+    void* h_tab = nullptr;
+    size_t tab_cap = 0;
+    int tab_sw = 0, tab_sh = 0, tab_dw = 0, tab_dh = 0;
+  } ingest;
   // camera-stream state (api.cu: ofb_farneback_stream*)
   struct Stream {
     ofb::StreamCtx ctx = {};

@@ -6,6 +6,9 @@
 // the single-channel uint8 frame the flow engine consumes, bit-exactly as this cv2 build does it:
 //   gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15          (15-bit fixed point)
 // so the 3N-byte colour frame is uploaded once and never converted on the host.
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 
 namespace ofb {
@@ -51,11 +54,158 @@ int cvt_gray_device(ofb_handle* h, const uint8_t* d_src, size_t src_pitch, uint8
   return OFB_OK;
 }
 
+// ---- cv2.resize(frame, (w, h)) — INTER_LINEAR on uint8, as this cv2 build computes it -----------------------------
+// (lfn3_sub_node.py:152-153, lfn3_adapt_node.py:160-161: frames that do not have the configured size are resized before
+// anything else.)  OpenCV's resizeGeneric_ / HResizeLinear / VResizeLinear<uchar,int,short>: 11-bit fixed-point weights
+// cvRound(w * 2048) of the float coordinate (d + 0.5) * scale - 0.5; columns clamp the coordinate, rows clip the two row
+// indices; out = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  Restated and pinned in
+// oracle/resize_np.py.  Tables are built on the host (double/float arithmetic exactly as cv2's) and cached per geometry.
+struct ResizeTab { int i0, i1; int w0, w1; };
+
+static void build_resize_tab(int dn, int sn, bool clamp_coord, ResizeTab* t) {
+  const double scale = (double)sn / dn;
+  for (int d = 0; d < dn; d++) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (clamp_coord) {
+      if (s < 0) { s = 0; f = 0.f; }
+      if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+    }
+    t[d].i0 = std::min(std::max(s, 0), sn - 1);
+    t[d].i1 = std::min(std::max(s + 1, 0), sn - 1);
+    t[d].w0 = (int)__builtin_nearbyintf((1.f - f) * 2048.f);
+    t[d].w1 = (int)__builtin_nearbyintf(f * 2048.f);
+  }
+}
+
+template <int CN>
+__global__ void __launch_bounds__(256) k_resize_u8(const uint8_t* __restrict__ src, size_t sp, uint8_t* __restrict__ dst,
+                                                   size_t dp, int dw, int dh, const ResizeTab* __restrict__ xt,
+                                                   const ResizeTab* __restrict__ yt) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw || y >= dh) return;
+  const ResizeTab tx = xt[x], ty = yt[y];
+  const uint8_t* r0 = src + (size_t)ty.i0 * sp;
+  const uint8_t* r1 = src + (size_t)ty.i1 * sp;
+#pragma unroll
+  for (int c = 0; c < CN; c++) {
+    const int s0 = (int)__ldg(r0 + tx.i0 * CN + c) * tx.w0 + (int)__ldg(r0 + tx.i1 * CN + c) * tx.w1;
+    const int s1 = (int)__ldg(r1 + tx.i0 * CN + c) * tx.w0 + (int)__ldg(r1 + tx.i1 * CN + c) * tx.w1;
+    dst[(size_t)y * dp + x * CN + c] = (uint8_t)((((ty.w0 * (s0 >> 4)) >> 16) + ((ty.w1 * (s1 >> 4)) >> 16) + 2) >> 2);
+  }
+}
+
+// src (sw x sh x cn, device) -> dst (dw x dh x cn, device), asynchronous on the handle's stream
+int resize_u8_device(ofb_handle* h, const uint8_t* d_src, size_t sp, int sw, int sh, int cn, uint8_t* d_dst, size_t dp,
+                     int dw, int dh) {
+  if (cn != 1 && cn != 3) return set_error(h, OFB_ERR_INVALID_ARG, "resize: 1 or 3 channels");
+  ofb_handle::Ingest& g = h->ingest;
+  if (g.tab_sw != sw || g.tab_sh != sh || g.tab_dw != dw || g.tab_dh != dh) {
+    const size_t n = (size_t)dw + dh;
+    if (n > g.tab_cap) {
+      OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (g.d_tab) cudaFree(g.d_tab);
+      if (g.h_tab) cudaFreeHost(g.h_tab);
+      g.d_tab = nullptr; g.h_tab = nullptr; g.tab_cap = 0;
+      OFB_CUDA(h, cudaMalloc(&g.d_tab, n * sizeof(ResizeTab)));
+      OFB_CUDA(h, cudaHostAlloc(&g.h_tab, n * sizeof(ResizeTab), cudaHostAllocDefault));
+      g.tab_cap = n;
+    } else {
+      OFB_CUDA(h, cudaStreamSynchronize(h->stream));   // the pinned table may still be in flight
+    }
+    ResizeTab* t = static_cast<ResizeTab*>(g.h_tab);
+    build_resize_tab(dw, sw, true, t);
+    build_resize_tab(dh, sh, false, t + dw);
+    OFB_CUDA(h, cudaMemcpyAsync(g.d_tab, t, n * sizeof(ResizeTab), cudaMemcpyHostToDevice, h->stream));
+    g.tab_sw = sw; g.tab_sh = sh; g.tab_dw = dw; g.tab_dh = dh;
+  }
+  const ResizeTab* xt = static_cast<const ResizeTab*>(g.d_tab);
+  dim3 grid((dw + 255) / 256, dh);
+  if (cn == 1) k_resize_u8<1><<<grid, 256, 0, h->stream>>>(d_src, sp, d_dst, dp, dw, dh, xt, xt + dw);
+  else k_resize_u8<3><<<grid, 256, 0, h->stream>>>(d_src, sp, d_dst, dp, dw, dh, xt, xt + dw);
+  OFB_LAUNCH_CHECK(h);
+  return OFB_OK;
+}
+
+static int ingest_reserve(ofb_handle* h, size_t bytes_a, size_t bytes_b) {
+  ofb_handle::Ingest& g = h->ingest;
+  if (bytes_a > g.a_bytes) {
+    OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (g.d_a) cudaFree(g.d_a);
+    g.d_a = nullptr; g.a_bytes = 0;
+    OFB_CUDA(h, cudaMalloc(&g.d_a, bytes_a));
+    g.a_bytes = bytes_a;
+  }
+  if (bytes_b > g.b_bytes) {
+    OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (g.d_b) cudaFree(g.d_b);
+    g.d_b = nullptr; g.b_bytes = 0;
+    OFB_CUDA(h, cudaMalloc(&g.d_b, bytes_b));
+    g.b_bytes = bytes_b;
+  }
+  return OFB_OK;
+}
+
 }  // namespace ofb
 
 using namespace ofb;
 
 extern "C" {
+
+int ofb_resize_u8(ofb_handle* h, const uint8_t* src, int src_width, int src_height, size_t src_stride_bytes, int channels,
+                  uint8_t* dst, int dst_width, int dst_height, size_t dst_stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!src || !dst) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  if (channels != 1 && channels != 3) return set_error(h, OFB_ERR_INVALID_ARG, "resize: 1 or 3 channels");
+  if (src_width < 1 || src_height < 1 || dst_width < 1 || dst_height < 1) return set_error(h, OFB_ERR_INVALID_ARG, "bad size");
+  const size_t srow = (size_t)src_width * channels, drow = (size_t)dst_width * channels;
+  if (src_stride_bytes == 0) src_stride_bytes = srow;
+  if (dst_stride_bytes == 0) dst_stride_bytes = drow;
+  if (src_stride_bytes < srow || dst_stride_bytes < drow) return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  int st = ingest_reserve(h, srow * src_height, drow * dst_height);
+  if (st) return st;
+  ofb_handle::Ingest& g = h->ingest;
+  OFB_CUDA(h, cudaMemcpy2DAsync(g.d_a, srow, src, src_stride_bytes, srow, src_height, cudaMemcpyHostToDevice, h->stream));
+  if ((st = resize_u8_device(h, g.d_a, srow, src_width, src_height, channels, g.d_b, drow, dst_width, dst_height))) return st;
+  OFB_CUDA(h, cudaMemcpy2DAsync(dst, dst_stride_bytes, g.d_b, drow, drow, dst_height, cudaMemcpyDeviceToHost, h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+int ofb_ingest_gray(ofb_handle* h, const uint8_t* src, int src_width, int src_height, size_t src_stride_bytes, int rgb_order,
+                    uint8_t* dst, int dst_width, int dst_height, size_t dst_stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!src || !dst) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  if (src_width < 1 || src_height < 1 || dst_width < 1 || dst_height < 1) return set_error(h, OFB_ERR_INVALID_ARG, "bad size");
+  const size_t srow = (size_t)src_width * 3, drow = (size_t)dst_width * 3;
+  if (src_stride_bytes == 0) src_stride_bytes = srow;
+  if (dst_stride_bytes == 0) dst_stride_bytes = (size_t)dst_width;
+  if (src_stride_bytes < srow || dst_stride_bytes < (size_t)dst_width)
+    return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  const bool same = src_width == dst_width && src_height == dst_height;
+  const size_t gpitch = ((size_t)dst_width + 15) & ~(size_t)15;
+  int st = ingest_reserve(h, srow * src_height, (same ? 0 : drow * dst_height) + gpitch * dst_height);
+  if (st) return st;
+  ofb_handle::Ingest& g = h->ingest;
+  OFB_CUDA(h, cudaMemcpy2DAsync(g.d_a, srow, src, src_stride_bytes, srow, src_height, cudaMemcpyHostToDevice, h->stream));
+  const uint8_t* col = g.d_a;
+  size_t col_pitch = srow;
+  uint8_t* gray = g.d_b;
+  if (!same) {
+    // cv2.resize on the colour frame first, as the nodes do, then the gray conversion
+    uint8_t* small = g.d_b + gpitch * dst_height;
+    if ((st = resize_u8_device(h, g.d_a, srow, src_width, src_height, 3, small, drow, dst_width, dst_height))) return st;
+    col = small;
+    col_pitch = drow;
+  }
+  if ((st = cvt_gray_device(h, col, col_pitch, gray, gpitch, dst_width, dst_height, rgb_order))) return st;
+  OFB_CUDA(h, cudaMemcpy2DAsync(dst, dst_stride_bytes, gray, gpitch, dst_width, dst_height, cudaMemcpyDeviceToHost, h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
 
 int ofb_cvt_gray_device(ofb_handle* h, const uint8_t* d_src, int width, int height, size_t src_pitch_bytes,
                         int rgb_order, uint8_t* d_dst, size_t dst_pitch_bytes) {

@@ -352,6 +352,38 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out
 
+    def resize(self, image, size) -> np.ndarray:
+        """``cv2.resize(image, size)`` (INTER_LINEAR) of a uint8 [H,W] or [H,W,3] image on the device, bit-exact with
+        cv2; ``size`` = (width, height) as in cv2."""
+        image = np.ascontiguousarray(image)
+        if image.dtype != np.uint8 or image.ndim not in (2, 3) or (image.ndim == 3 and image.shape[2] != 3):
+            raise OfbError(1, "resize needs a uint8 [H,W] or [H,W,3] image")
+        cn = 1 if image.ndim == 2 else 3
+        dw, dh = int(size[0]), int(size[1])
+        out = np.empty((dh, dw) if cn == 1 else (dh, dw, 3), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_resize_u8(self._h, image.ctypes.data, image.shape[1], image.shape[0], 0, cn,
+                                         out.ctypes.data, dw, dh, 0)
+            _lib.check(st, self._h)
+        return out
+
+    def ingest_gray(self, frame, size=None, rgb: bool = False) -> np.ndarray:
+        """The nodes' ingest in one call: a uint8 [H,W,3] bgr8 (``rgb=True``: rgb8) frame → ``cv2.resize`` to ``size`` =
+        (width, height) if it has another size → ``cv2.cvtColor(..., COLOR_BGR2GRAY)``; bit-exact with cv2."""
+        frame = np.asarray(frame)
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+            raise OfbError(1, "ingest_gray needs a uint8 [H,W,3] frame")
+        if frame.strides[2] != 1 or frame.strides[1] != 3:
+            frame = np.ascontiguousarray(frame)
+        hgt, wid = frame.shape[:2]
+        dw, dh = (wid, hgt) if size is None else (int(size[0]), int(size[1]))
+        out = np.empty((dh, dw), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_ingest_gray(self._h, frame.ctypes.data, wid, hgt, frame.strides[0], 1 if rgb else 0,
+                                           out.ctypes.data, dw, dh, 0)
+            _lib.check(st, self._h)
+        return out
+
     def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3) -> np.ndarray:
         image = _u8_image(image, "image")
         hgt, wid = image.shape

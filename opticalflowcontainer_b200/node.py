@@ -80,9 +80,17 @@ class FarnebackVelocityNode:
     def image_callback(self, image: np.ndarray, stamp: float, encoding: str = "bgr8",
                        mask: Optional[np.ndarray] = None) -> Optional[Tuple[Vector3Stamped, Vector3Stamped]]:
         """One camera frame in → (raw, smooth) velocity messages out (None on the priming frame)."""
-        gray = to_gray_u8(image, encoding)
-        if gray.shape != (self.height, self.width):
-            raise ValueError("frame is %s, node is configured for %s" % (gray.shape, (self.height, self.width)))
+        image = np.asarray(image)
+        if encoding not in ("bgr8", "rgb8", "mono8"):
+            raise ValueError("Unsupported image encoding: %s" % encoding)
+        if image.ndim == 3 and image.dtype == np.uint8 and image.shape[2] == 3:
+            # the nodes' ingest, on the device: cv2.resize to the configured size if needed (lfn3_sub_node.py:152-153),
+            # then cv2.cvtColor(..., BGR2GRAY) — one upload, bit-exact with cv2
+            gray = self.engine.ingest_gray(image, (self.width, self.height), rgb=encoding == "rgb8")
+        else:
+            gray = to_gray_u8(image, encoding)
+            if gray.shape != (self.height, self.width):
+                gray = self.engine.resize(gray, (self.width, self.height))
         if self.prev_gray is None:
             self.prev_gray, self.prev_time = gray, stamp
             return None

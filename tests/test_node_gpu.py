@@ -261,3 +261,36 @@ def test_node_stream_mode_equals_pair_mode(engine_factory):
         if ra is not None:
             assert ra[0].vector == rb[0].vector and ra[1].vector == rb[1].vector
             assert np.array_equal(a.last_flow, b.last_flow)
+
+
+@pytest.mark.parametrize("src,dst", [((720, 1280), (480, 640)), ((480, 640), (1080, 1920)), ((481, 637), (240, 320)),
+                                     ((100, 100), (50, 50)), ((48, 64), (108, 192)), ((37, 53), (37, 53)), ((64, 48), (5, 7))])
+def test_resize_bit_exact(engine_factory, src, dst):
+    """ofb_resize_u8 == cv2.resize (INTER_LINEAR, uint8), gray and 3-channel, down- and up-scaling, odd sizes."""
+    import cv2
+    eng = engine_factory(64, 64)           # frames of any size: not limited by the handle's capacity
+    rng = np.random.default_rng(src[0] + dst[1])
+    for cn in (1, 3):
+        img = rng.integers(0, 256, size=src if cn == 1 else src + (3,), dtype=np.uint8)
+        assert np.array_equal(eng.resize(img, (dst[1], dst[0])), cv2.resize(img, (dst[1], dst[0])))
+
+
+def test_ingest_gray_matches_node_ingest(engine_factory):
+    """ofb_ingest_gray == cv2.resize + cv2.cvtColor as the nodes run them (lfn3_sub_node.py:148-159); the node mirror
+    accepts camera frames larger than its configured size."""
+    import cv2
+    from opticalflowcontainer_b200.node import FarnebackVelocityNode
+    eng = engine_factory(160, 120)
+    rng = np.random.default_rng(2)
+    frame = rng.integers(0, 256, size=(360, 640, 3), dtype=np.uint8)
+    want = cv2.cvtColor(cv2.resize(frame, (160, 120)), cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(eng.ingest_gray(frame, (160, 120)), want)
+    assert np.array_equal(eng.ingest_gray(frame, (160, 120), rgb=True), cv2.cvtColor(cv2.resize(frame, (160, 120)), cv2.COLOR_RGB2GRAY))
+    assert np.array_equal(eng.ingest_gray(frame), cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY))
+    view = frame[:, :500]                                   # row step larger than the row
+    assert np.array_equal(eng.ingest_gray(view, (160, 120)), cv2.cvtColor(cv2.resize(np.ascontiguousarray(view), (160, 120)), cv2.COLOR_BGR2GRAY))
+    node = FarnebackVelocityNode(engine=eng, width=160, height=120)
+    big = [cv2.resize(np.dstack([synth.synth_pair(120, 160, 3, (1.5 * i, 0.5))[1]] * 3), (640, 360)) for i in range(2)]
+    assert node.image_callback(big[0], 0.0) is None
+    out = node.image_callback(big[1], 0.1)
+    assert out is not None and np.isfinite(out[0].vector[0])
