@@ -291,6 +291,12 @@ int ofb_resize_u8(ofb_handle* h, const uint8_t* src, int src_width, int src_heig
 int ofb_ingest_gray(ofb_handle* h, const uint8_t* src, int src_width, int src_height, size_t src_stride_bytes,
                     int rgb_order, uint8_t* dst, int dst_width, int dst_height, size_t dst_stride_bytes);
 
+/* cv2.createCLAHE(clip_limit, (tiles_x, tiles_y)).apply(src) on a uint8 single-channel image, bit-exact with this
+ * cv2 build (oracle/clahe_np.py).  The adapt node's contrast pre-filter: lfn3_adapt_node.py:164-182
+ * (`self.clahe.setClipLimit(clip); v_enhanced = self.clahe.apply(v)`).  Synchronous; stride 0 = packed. */
+int ofb_clahe(ofb_handle* h, const uint8_t* src, int width, int height, size_t src_stride_bytes, double clip_limit,
+              int tiles_x, int tiles_y, uint8_t* dst, size_t dst_stride_bytes);
+
 /* ---- sparse path: replaces cv2.goodFeaturesToTrack + cv2.calcOpticalFlowPyrLK -- */
 
 /* Shi-Tomasi corners of a uint8 image (host buffer).  corners_xy: capacity

@@ -77,6 +77,8 @@ _SIGNATURES = {
                                 C.c_size_t]),
     "ofb_ingest_gray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_int,
                                   C.c_int, C.c_size_t]),
+    "ofb_clahe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_void_p,
+                            C.c_size_t]),
     "ofb_launch_count": (C.c_uint64, [C.c_void_p]),
     "ofb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ofb_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

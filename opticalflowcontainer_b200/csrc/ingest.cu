@@ -128,6 +128,76 @@ int resize_u8_device(ofb_handle* h, const uint8_t* d_src, size_t sp, int sw, int
   return OFB_OK;
 }
 
+// ---- cv2.createCLAHE(clipLimit, tileGridSize).apply(img) on uint8 ---------------------------------------------------
+// (the adapt node's contrast pre-filter, lfn3_adapt_node.py:164-182.)  OpenCV's clahe.cpp restated in
+// oracle/clahe_np.py and pinned against the wheel: per-tile histogram (the image is extended to a multiple of the grid
+// with REFLECT_101), integer clip limit, excess redistributed, LUT = cvRound(cumsum * 255.f / tileArea); then every
+// pixel blends the LUTs of the four surrounding tiles in float with separate roundings (the cv2 build has no FMA here).
+__global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ src, size_t sp, int w, int h, int tw, int th,
+                                                   int clip, float lut_scale, uint8_t* __restrict__ luts) {
+  __shared__ int hist[256];
+  __shared__ int scan[256];
+  __shared__ int s_clipped;
+  const int t = threadIdx.x;
+  hist[t] = 0;
+  if (t == 0) s_clipped = 0;
+  __syncthreads();
+  const int x0 = blockIdx.x * tw, y0 = blockIdx.y * th;
+  for (int i = t; i < tw * th; i += 256) {
+    const int ey = y0 + i / tw, ex = x0 + i % tw;
+    const int sy = ey < h ? ey : 2 * (h - 1) - ey, sx = ex < w ? ex : 2 * (w - 1) - ex;   // REFLECT_101 of the extension
+    atomicAdd(&hist[__ldg(src + (size_t)sy * sp + sx)], 1);
+  }
+  __syncthreads();
+  int v = hist[t];
+  if (clip > 0) {
+    if (v > clip) { atomicAdd(&s_clipped, v - clip); v = clip; }
+    __syncthreads();
+    const int clipped = s_clipped;
+    const int batch = clipped / 256;
+    const int residual = clipped - batch * 256;
+    v += batch;
+    if (residual != 0) {
+      const int step = max(256 / residual, 1);
+      if (t % step == 0 && t / step < residual) v++;
+    }
+  }
+  scan[t] = v;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {            // inclusive scan
+    const int a = t >= d ? scan[t - d] : 0;
+    __syncthreads();
+    scan[t] += a;
+    __syncthreads();
+  }
+  const int r = __float2int_rn(__fmul_rn((float)scan[t], lut_scale));
+  luts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + t] = (uint8_t)min(max(r, 0), 255);
+}
+
+__global__ void __launch_bounds__(256) k_clahe_interp(const uint8_t* __restrict__ src, size_t sp, uint8_t* __restrict__ dst,
+                                                      size_t dp, int w, int h, int tiles_x, int tiles_y, float inv_tw,
+                                                      float inv_th, const uint8_t* __restrict__ luts) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+  const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+  int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+  const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+  const float xa1 = __fsub_rn(1.f, xa), ya1 = __fsub_rn(1.f, ya);
+  const int tx2 = min(tx1 + 1, tiles_x - 1), ty2 = min(ty1 + 1, tiles_y - 1);
+  tx1 = max(tx1, 0);
+  ty1 = max(ty1, 0);
+  const int v = src[(size_t)y * sp + x];
+  const uint8_t* p1 = luts + (size_t)ty1 * tiles_x * 256 + v;
+  const uint8_t* p2 = luts + (size_t)ty2 * tiles_x * 256 + v;
+  const float l11 = (float)__ldg(p1 + tx1 * 256), l12 = (float)__ldg(p1 + tx2 * 256);
+  const float l21 = (float)__ldg(p2 + tx1 * 256), l22 = (float)__ldg(p2 + tx2 * 256);
+  const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+  const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+  const int r = __float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya)));
+  dst[(size_t)y * dp + x] = (uint8_t)min(max(r, 0), 255);
+}
+
 static int ingest_reserve(ofb_handle* h, size_t bytes_a, size_t bytes_b) {
   ofb_handle::Ingest& g = h->ingest;
   if (bytes_a > g.a_bytes) {
@@ -240,6 +310,44 @@ int ofb_cvt_gray(ofb_handle* h, const uint8_t* src, int width, int height, size_
   int st = cvt_gray_device(h, d_col, col_pitch, h->d_src, h->src_pitch, width, height, rgb_order);
   if (st) return st;
   OFB_CUDA(h, cudaMemcpy2DAsync(dst, dst_stride_bytes, h->d_src, h->src_pitch, width, height, cudaMemcpyDeviceToHost, h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+int ofb_clahe(ofb_handle* h, const uint8_t* src, int width, int height, size_t src_stride_bytes, double clip_limit,
+              int tiles_x, int tiles_y, uint8_t* dst, size_t dst_stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!src || !dst) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  if (width < 1 || height < 1 || tiles_x < 1 || tiles_y < 1 || tiles_x > 256 || tiles_y > 256)
+    return set_error(h, OFB_ERR_INVALID_ARG, "bad size or tile grid");
+  if (src_stride_bytes == 0) src_stride_bytes = (size_t)width;
+  if (dst_stride_bytes == 0) dst_stride_bytes = (size_t)width;
+  if (src_stride_bytes < (size_t)width || dst_stride_bytes < (size_t)width)
+    return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row");
+  // the extension to a multiple of the grid (REFLECT_101) must stay inside one reflection
+  const bool exact = width % tiles_x == 0 && height % tiles_y == 0;
+  const int ew = exact ? width : width + tiles_x - width % tiles_x, eh = exact ? height : height + tiles_y - height % tiles_y;
+  if (ew - width >= width || eh - height >= height)
+    return set_error(h, OFB_ERR_INVALID_ARG, "image too small for a %dx%d tile grid", tiles_x, tiles_y);
+  const int tw = ew / tiles_x, th = eh / tiles_y;
+  const int area = tw * th;
+  int clip = 0;
+  if (clip_limit > 0.0) clip = std::max((int)(clip_limit * area / 256), 1);
+  const float lut_scale = 255.f / (float)area;
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t pitch = ((size_t)width + 15) & ~(size_t)15;
+  const size_t lut_bytes = (size_t)tiles_x * tiles_y * 256;
+  int st = ingest_reserve(h, pitch * height, pitch * height + lut_bytes);
+  if (st) return st;
+  ofb_handle::Ingest& g = h->ingest;
+  uint8_t* luts = g.d_b + pitch * height;
+  OFB_CUDA(h, cudaMemcpy2DAsync(g.d_a, pitch, src, src_stride_bytes, width, height, cudaMemcpyHostToDevice, h->stream));
+  k_clahe_lut<<<dim3(tiles_x, tiles_y), 256, 0, h->stream>>>(g.d_a, pitch, width, height, tw, th, clip, lut_scale, luts);
+  OFB_LAUNCH_CHECK(h);
+  k_clahe_interp<<<dim3((width + 255) / 256, height), 256, 0, h->stream>>>(g.d_a, pitch, g.d_b, pitch, width, height, tiles_x,
+                                                                          tiles_y, 1.f / (float)tw, 1.f / (float)th, luts);
+  OFB_LAUNCH_CHECK(h);
+  OFB_CUDA(h, cudaMemcpy2DAsync(dst, dst_stride_bytes, g.d_b, pitch, width, height, cudaMemcpyDeviceToHost, h->stream));
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
   return OFB_OK;
 }

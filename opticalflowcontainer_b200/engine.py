@@ -384,6 +384,21 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out
 
+    def clahe(self, image, clipLimit: float = 40.0, tileGridSize=(8, 8)) -> np.ndarray:
+        """``cv2.createCLAHE(clipLimit, tileGridSize).apply(image)`` of a uint8 [H,W] image on the device, bit-exact with
+        cv2 (the adapt node's pre-filter, lfn3_adapt_node.py:164-182)."""
+        image = np.asarray(image)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise OfbError(1, "clahe needs a uint8 [H,W] image")
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        out = np.empty(image.shape, np.uint8)
+        with self._lock:
+            st = self._lib.ofb_clahe(self._h, image.ctypes.data, image.shape[1], image.shape[0], image.strides[0],
+                                     float(clipLimit), int(tileGridSize[0]), int(tileGridSize[1]), out.ctypes.data, 0)
+            _lib.check(st, self._h)
+        return out
+
     def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3) -> np.ndarray:
         image = _u8_image(image, "image")
         hgt, wid = image.shape

@@ -166,3 +166,10 @@ def junction_velocity(engine: FlowEngine, prev_junctions: Sequence[Sequence[floa
         return None
     disp = curr[idx[hit]] - prev[ok][hit]
     return float(disp[:, 0].mean() / dt * pixel_to_meter)
+
+
+def adaptive_clip_limit(v: np.ndarray, clip_min: float, clip_max: float, c_min: float, c_max: float) -> float:
+    """The adapt node's clip limit from the contrast of the V channel (``lfn3_adapt_node.py:170-175``):
+    ``contrast = std(v) / (mean(v) + 1e-3)``, mapped linearly from [c_min, c_max] to [clip_min, clip_max] and clipped."""
+    contrast = np.std(v) / (np.mean(v) + 1e-3)
+    return float(np.clip(clip_min + (contrast - c_min) / (c_max - c_min) * (clip_max - clip_min), clip_min, clip_max))

@@ -294,3 +294,18 @@ def test_ingest_gray_matches_node_ingest(engine_factory):
     assert node.image_callback(big[0], 0.0) is None
     out = node.image_callback(big[1], 0.1)
     assert out is not None and np.isfinite(out[0].vector[0])
+
+
+@pytest.mark.parametrize("size", [(480, 640), (241, 317), (1080, 1920)])
+def test_clahe_bit_exact(engine_factory, size):
+    """ofb_clahe == cv2.createCLAHE(clip, grid).apply (lfn3_adapt_node.py:164-182), incl. the adaptive clip limit."""
+    import cv2
+    from opticalflowcontainer_b200.node import adaptive_clip_limit
+    eng = engine_factory(64, 64)
+    rng = np.random.default_rng(size[0])
+    a = cv2.GaussianBlur((rng.random(size) * 255).astype(np.float32), (0, 0), 3)
+    low = ((a - a.min()) / (a.max() - a.min()) * 120 + 40).astype(np.uint8)
+    noise = rng.integers(0, 256, size=size, dtype=np.uint8)
+    for im in (low, noise):
+        for clip, grid in [(2.0, (8, 8)), (40.0, (8, 8)), (0.0, (4, 6)), (adaptive_clip_limit(im, 1.0, 4.0, 0.1, 0.8), (8, 8))]:
+            assert np.array_equal(eng.clahe(im, clip, grid), cv2.createCLAHE(clipLimit=clip, tileGridSize=grid).apply(im))
