@@ -67,6 +67,16 @@ struct PeerTab {
   int r_lo, r_hi, f_lo, f_hi;
 };
 
+// Polynomial coefficients of the two frames of every pair: frame 0 of pair i at A0/B0 + i*n, frame 1 at A1/B1 + i*n
+// (n = level pixels).  Independent pairs: A1 = A0 + n_pairs*n; consecutive frames of a stream: A1 = A0 + n; the
+// camera-stream call: A0 = the expansions kept from the previous call, A1 = the new frames' (different arrays).
+struct RSet {
+  const float4* A0;
+  const float* B0;
+  const float4* A1;
+  const float* B1;
+};
+
 // Camera-stream cache (ofb_farneback_stream*): the polynomial expansions of the streams' latest frames at every pyramid
 // level, double-buffered — a call expands only the new frames into half `cur` and reads the previous frames' from the
 // other half.
@@ -235,6 +245,13 @@ void prepare_blur(int winsize, bool gaussian, BlurCoef* bc);
 int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
                   int width, int height, size_t pitch, size_t image_stride, float* d_flow_out,
                   const float* d_init_flow, const ofb_farneback_params* p, const StreamCtx* sc = nullptr);
+// k_iter_v with the window radius as a template argument for the common window sizes other than the default
+// (iter_fixed_a.cu, iter_fixed_b.cu: separate translation units so that they compile in parallel).  *served = false if
+// there is no instantiation for m (the caller then takes the run-time-radius kernel).
+cudaError_t launch_iter_fixed_a(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
+                                const RSet& rs, float reg, cudaStream_t st, bool* served);
+cudaError_t launch_iter_fixed_b(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
+                                const RSet& rs, float reg, cudaStream_t st, bool* served);
 // the schedule farneback_run would use (level sizes), for sizing the stream cache
 int farneback_levels(int width, int height, const ofb_farneback_params* p, Level* out, int* n_out);
 // true if farneback_run can serve this configuration from the stream cache (fused box-window path, marching PolyExp)

@@ -20,6 +20,7 @@
 #include "fb_device.cuh"
 #include "fb_iter_ws.cuh"
 #include "fb_iter_v.cuh"
+#include "fb_iter_launch.cuh"
 #include "fb_polyexp.cuh"
 #include "fb_pyramid.cuh"
 
@@ -454,40 +455,6 @@ __global__ void __launch_bounds__(256) k_init_flow_area(const float2* __restrict
 // =====================================================================================
 // Driver: the multi-level schedule on the handle's stream (no host sync inside).
 // =====================================================================================
-// k_iter_v launcher.
-template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false,
-          bool REUSE = false>
-static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                 const RSet& rs, int m, float reg, cudaStream_t st, int y_begin = 0, int y_end = -1,
-                                 const PeerTab* tab = nullptr, int my_rank = 0) {
-  if (y_end < 0) y_end = hh;
-  if (y_end <= y_begin) return cudaSuccess;
-  PeerTab t;
-  if (tab) t = *tab; else memset(&t, 0, sizeof(t));
-  const int smem = iter_v_smem_floats<COLS, CH>(m) * (int)sizeof(float);
-  // largest dynamic smem configured for this instantiation, per device (function attributes are per device)
-  static int configured[64] = {0};
-  const int dev = h->device & 63;
-  if (smem > configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED, REUSE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured[dev] = smem;
-  }
-  const int tw = COLS - 2 * m;
-  const int strips = (w + tw - 1) / tw;
-  const int slots = MINB * h->num_sms * h->iter_waves;
-  const int per = strips * n_pairs;
-  const int rows = y_end - y_begin;
-  int segs = per >= slots ? 1 : slots / per;
-  int seg_rows = std::max(16, (rows + segs - 1) / segs);
-  segs = (rows + seg_rows - 1) / seg_rows;
-  dim3 g(strips * segs, n_pairs);
-  k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED, REUSE><<<g, COLS + (CH / CLOOP) * COLS / PXT, smem, st>>>(
-      rs, fin, fout, w, hh, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank);
-  return cudaGetLastError();
-}
-
 int farneback_levels(int width, int height, const ofb_farneback_params* p, Level* out, int* n_out) {
   return build_schedule(width, height, p->pyr_scale, p->levels, out, n_out);
 }
@@ -684,7 +651,9 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
             const bool q = cudaFuncGetAttributes(&a3, k_iter_v<7, 256, 2, 2, 0, 4, 2, 1, false, true>) == cudaSuccess &&
                            cudaFuncGetAttributes(&a2, k_iter_v<7, 256, 2, 2, 0, 4, 2, 1>) == cudaSuccess &&
                            cudaFuncGetAttributes(&a1, k_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>) == cudaSuccess;
-            regs_state = (q && a3.numRegs >= 80 && a2.numRegs >= 80 && a1.numRegs >= 80) ? 1 : -1;
+            cudaFuncAttributes a0;
+            const bool q0 = cudaFuncGetAttributes(&a0, k_iter_v<0, 256, 2, 2, 0, 4, 2, 1, false, true>) == cudaSuccess;
+            regs_state = (q && q0 && a3.numRegs >= 80 && a2.numRegs >= 80 && a1.numRegs >= 80 && a0.numRegs >= 80) ? 1 : -1;
           }
           const bool regs_ok = regs_state == 1;
           if (bc.m == 7) {
@@ -698,6 +667,17 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
               else if (h->iter_mode == 2 && regs_ok) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1>(OFB_V_ARGS);
               else if (h->iter_mode == 1 && regs_ok) e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>(OFB_V_ARGS);
               else e = launch_iter_v<7, 256, 2, 2, 3, 4>(OFB_V_ARGS);
+            }
+          } else if (h->iter_mode >= 2) {
+            // other window sizes: the default schedule with the radius as a template argument where an instantiation
+            // exists (winsize 5..31), else with the radius at run time (its generic consumer loop is slow:
+            // winsize 13 measured 6.4 ms per 18 pairs against 3.0 ms with the templated kernel)
+            bool served = false;
+            e = bc.m <= 8 ? launch_iter_fixed_a(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, &served)
+                          : launch_iter_fixed_b(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, &served);
+            if (!served) {
+              if (bc.m <= 8 && regs_ok) e = launch_iter_v<0, 256, 2, 2, 0, 4, 2, 1, false, true>(OFB_V_ARGS);
+              else e = launch_iter_v<0, 128, 2, 3, 0, 4, 2, 1, false, true>(OFB_V_ARGS);
             }
           } else {
             e = launch_iter_v<0, 128, 4, 1, 0, 4>(OFB_V_ARGS);

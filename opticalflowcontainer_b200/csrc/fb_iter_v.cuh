@@ -32,16 +32,6 @@ namespace ofb {
 // persistent corner rows do not push the producers' loads behind their first use.
 constexpr int REUSE_PROD_REGS = 88, REUSE_CONS_REGS = 56;
 
-// Polynomial coefficients of the two frames of every pair: frame 0 of pair i at A0/B0 + i*n, frame 1 at A1/B1 + i*n
-// (n = level pixels).  Independent pairs: A1 = A0 + n_pairs*n; consecutive frames of a stream: A1 = A0 + n; the
-// camera-stream call: A0 = the expansions kept from the previous call, A1 = the new frames' (different arrays).
-struct RSet {
-  const float4* A0;
-  const float* B0;
-  const float4* A1;
-  const float* B1;
-};
-
 template <int COLS, int CH>
 constexpr int iter_v_smem_floats(int m) { return (2 * CH + 2 * m + 1) * 5 * COLS; }
 
@@ -98,7 +88,7 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
   if (tid < COLS) {
     // ------------------------------------------------------------------ PRODUCERS (one column each)
     if constexpr (REUSE && RIF == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REUSE_PROD_REGS));
-    else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(96));
+    else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1 && MINB == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(96));
     const float4* RA0 = rs.A0 + (size_t)pair * n;
     const float* RB0 = rs.B0 + (size_t)pair * n;
     const float4* RA1 = rs.A1 + (size_t)pair * n;
@@ -413,7 +403,7 @@ __global__ void __launch_bounds__(COLS + (CH / CLOOP) * COLS / PXT, MINB)
 
   // -------------------------------------------------------------------- CONSUMERS (PXT adjacent pixels of one row each)
   if constexpr (REUSE && RIF == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REUSE_CONS_REGS));
-  else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
+  else if constexpr (RIF > 1 && COLS == 256 && PXT == 4 && CLOOP == 1 && MINB == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
   float2* fout = flow_out + (size_t)pair * n;
   const int ct = tid - COLS;                         // 0..NCONS-1
   const int q_row0 = (ct / GROUPS) * CLOOP;          // first staged row of this thread's pixel group
