@@ -270,3 +270,20 @@ def test_stream_call_equals_pair_calls(built_lib, flags, winsize):
         assert eng.farneback_stream(np.stack([seqs[s][1] for s in range(n)]), **kw2) is None
     finally:
         eng.close(); ref.close()
+
+
+def test_repeated_calls_are_deterministic(built_lib):
+    """compute-sanitizer's racecheck is not available on the GPU pool: a race in the producer/consumer hand-over of the
+    fused kernels would show up as run-to-run differences.  Same batch, ten calls, three window sizes: identical bits."""
+    import opticalflowcontainer_b200 as ofb
+    n, h, w = 6, 270, 480
+    eng = ofb.FlowEngine(w, h, n, 0)
+    try:
+        prs = [synth.synth_pair(h, w, 70 + i, (2.0 + i, -1.0 - 0.5 * i)) for i in range(n)]
+        a = [p[0] for p in prs]; b = [p[1] for p in prs]
+        for winsize in (15, 9, 21):
+            first = eng.farneback_batch(a, b, winsize=winsize)
+            for _ in range(9):
+                assert np.array_equal(eng.farneback_batch(a, b, winsize=winsize), first)
+    finally:
+        eng.close()
