@@ -166,6 +166,7 @@ int ofb_destroy(ofb_handle* h) {
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
   if (h->h_stats) cudaFreeHost(h->h_stats);
+  for (auto& e : h->stats_ev) if (e) cudaEventDestroy(e);
   if (h->d_gray) cudaFree(h->d_gray);
   if (h->ingest.d_a) cudaFree(h->ingest.d_a);
   if (h->ingest.d_b) cudaFree(h->ingest.d_b);
@@ -256,10 +257,11 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     h->no_pipeline = np && np[0] == '1';
   }
   const size_t N = (size_t)max_width * max_height;
-  const size_t frames = 2 * (size_t)max_batch;
+  const size_t frames = 2 * (size_t)max_batch;            // prev + next of a full batch
+  const size_t staged_frames = 2 * frames;                // two such sets: the reduction calls alternate between them
   h->src_pitch = align_up((size_t)max_width, 256);
   h->src_image_stride = h->src_pitch * max_height;
-  CREATE_CUDA(cudaMalloc(&h->d_src, h->src_image_stride * frames));
+  CREATE_CUDA(cudaMalloc(&h->d_src, h->src_image_stride * staged_frames));
   CREATE_CUDA(cudaMalloc(&h->d_img, frames * N * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_RA, (frames * N + (size_t)kRowPad * max_width) * sizeof(float4)));
   CREATE_CUDA(cudaMalloc(&h->d_RB, (frames * N + (size_t)kRowPad * max_width) * sizeof(float)));
@@ -638,12 +640,13 @@ static int farneback_batch_impl(ofb_handle* h, int n, const uint8_t* const* prev
     // With the asynchronous entry point the pipeline also runs ACROSS calls (the next call's uploads and
     // kernels overlap this call's downloads): every chunk slot keeps three events (upload done, kernels
     // done, download done) that the next call's work on the same staging regions waits for.
-    // Without a download to hide (the reduction call) two half-batch chunks are enough to keep the next
-    // upload behind the running kernels, and larger chunks fill the GPU better.
-    const int c = h->pipe_chunk > 0 ? std::min(h->pipe_chunk, n)
-                  : !download ? (n + 1) / 2 : (n >= 16 ? 4 : (n >= 8 ? 2 : 1));
+    // Without a download to hide (the reduction call) the whole batch runs as ONE chunk — full-size launches — and
+    // successive calls alternate between two source staging sets, so the next call's upload runs behind this call's
+    // kernels.
+    const bool whole = !download && h->pipe_chunk == 0;
+    const int c = h->pipe_chunk > 0 ? std::min(h->pipe_chunk, n) : whole ? n : (n >= 16 ? 4 : (n >= 8 ? 2 : 1));
     const int chunks = (n + c - 1) / c;
-    while ((int)h->pipe_ev.size() < 3 * chunks) {
+    while ((int)h->pipe_ev.size() < 3 * std::max(chunks, 2)) {
       cudaEvent_t e;
       OFB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       h->pipe_ev.push_back(e);
@@ -656,10 +659,12 @@ static int farneback_batch_impl(ofb_handle* h, int n, const uint8_t* const* prev
       h->pipe_n = n; h->pipe_c = c; h->pipe_w = width; h->pipe_h = height;
     }
     const bool use_init = (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) != 0;
+    if (whole) h->pipe_parity ^= 1;
     for (int ci = 0; ci < chunks; ci++) {
       const int i0 = ci * c, cn = std::min(c, n - i0);
-      uint8_t* base = h->d_src + (size_t)2 * i0 * istride;   // [prev x cn][next x cn]
-      cudaEvent_t ev_in = h->pipe_ev[3 * ci], ev_comp = h->pipe_ev[3 * ci + 1], ev_out = h->pipe_ev[3 * ci + 2];
+      const int slot = whole ? h->pipe_parity : ci;             // staging region and its three events
+      uint8_t* base = h->d_src + (whole ? (size_t)slot * 2 * n * istride : (size_t)2 * i0 * istride);   // [prev x cn][next x cn]
+      cudaEvent_t ev_in = h->pipe_ev[3 * slot], ev_comp = h->pipe_ev[3 * slot + 1], ev_out = h->pipe_ev[3 * slot + 2];
       OFB_CUDA(h, cudaStreamWaitEvent(h->s_in, ev_comp, 0));     // previous call's kernels have read this source slot
       for (int i = 0; i < cn; i++) {
         OFB_CUDA(h, cudaMemcpy2DAsync(base + (size_t)i * istride, pitch, prev[i0 + i], stride_bytes, width, height,

@@ -116,6 +116,7 @@ struct ofb_handle {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> pipe_ev;
   int pipe_chunk = 0;          // OFB_PIPE_CHUNK: pairs per pipeline chunk of the host-buffer batch call (0 = auto)
+  int pipe_parity = 0;         // source staging set of the last whole-batch (reduction) call
   int pipe_n = 0, pipe_c = 0, pipe_w = 0, pipe_h = 0;   // staging layout of the previous pipelined call
   bool no_pipeline = false;    // OFB_NO_PIPELINE=1: serial upload -> compute -> download
   uint64_t launches = 0;
@@ -187,6 +188,7 @@ struct ofb_handle {
   // asynchronous reductions (ofb_farneback_batch_stats_async): results land in pinned slots and are handed
   // to the caller's arrays by ofb_wait
   struct PendingStats { double* out_mean; float* out_median; int n; int slot; };
+  cudaEvent_t stats_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // "results of slot i are in the pinned buffer"
   std::vector<PendingStats> pending_stats;
   char* h_stats = nullptr;     // pinned, kStatSlots x max_batch x 16 B
   int stats_slot = 0;

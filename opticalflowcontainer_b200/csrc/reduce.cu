@@ -140,18 +140,29 @@ __global__ void k_sel_final(const uint32_t* __restrict__ sel, const double* __re
   median_out[i] = cnt ? (a + b) * 0.5f : __uint_as_float(0x7fc00000u);
 }
 
+static void hand_over(ofb_handle* h, const ofb_handle::PendingStats& ps) {
+  const char* slot = h->h_stats + (size_t)ps.slot * h->max_batch * 16;
+  const double* hm = reinterpret_cast<const double*>(slot);
+  const float* hd = reinterpret_cast<const float*>(slot + (size_t)h->max_batch * 8);
+  for (int i = 0; i < ps.n; i++) {
+    if (ps.out_mean) ps.out_mean[i] = hm[i];
+    if (ps.out_median) ps.out_median[i] = hd[i];
+  }
+}
+
+int finish_oldest_stats(ofb_handle* h) {
+  if (h->pending_stats.empty()) return OFB_OK;
+  const ofb_handle::PendingStats ps = h->pending_stats.front();
+  OFB_CUDA(h, cudaEventSynchronize(h->stats_ev[ps.slot]));
+  hand_over(h, ps);
+  h->pending_stats.erase(h->pending_stats.begin());
+  return OFB_OK;
+}
+
 int finish_pending_stats(ofb_handle* h) {
   if (h->pending_stats.empty()) return OFB_OK;
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  for (const auto& ps : h->pending_stats) {
-    const char* slot = h->h_stats + (size_t)ps.slot * h->max_batch * 16;
-    const double* hm = reinterpret_cast<const double*>(slot);
-    const float* hd = reinterpret_cast<const float*>(slot + (size_t)h->max_batch * 8);
-    for (int i = 0; i < ps.n; i++) {
-      if (ps.out_mean) ps.out_mean[i] = hm[i];
-      if (ps.out_median) ps.out_median[i] = hd[i];
-    }
-  }
+  for (const auto& ps : h->pending_stats) hand_over(h, ps);
   h->pending_stats.clear();
   return OFB_OK;
 }
@@ -186,12 +197,14 @@ int flow_u_stats(ofb_handle* h, int n, const uint8_t* host_mask, double* out_mea
   if ((s = timing_end(h))) return s;
   // results: n doubles + n floats through a pinned slot; the caller's arrays are filled once the stream
   // has got there (right away for the synchronous call, in ofb_wait for the asynchronous one)
-  if ((int)h->pending_stats.size() >= kStatSlots && (s = finish_pending_stats(h))) return s;
+  if ((int)h->pending_stats.size() >= kStatSlots && (s = finish_oldest_stats(h))) return s;   // (no stream drain)
   const int slot_i = h->stats_slot;
   h->stats_slot = (h->stats_slot + 1) % kStatSlots;
   char* slot = h->h_stats + (size_t)slot_i * h->max_batch * 16;
   OFB_CUDA(h, cudaMemcpyAsync(slot, mean_d, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   OFB_CUDA(h, cudaMemcpyAsync(slot + (size_t)h->max_batch * 8, med_d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  if (!h->stats_ev[slot_i]) OFB_CUDA(h, cudaEventCreateWithFlags(&h->stats_ev[slot_i], cudaEventDisableTiming));
+  OFB_CUDA(h, cudaEventRecord(h->stats_ev[slot_i], st));
   h->pending_stats.push_back({out_mean, out_median, n, slot_i});
   return async ? OFB_OK : finish_pending_stats(h);
 }
