@@ -531,7 +531,7 @@ def run_ours(args, rank, local_rank, world):
     def node_step(i):
         if strm:
             eng.farneback_stream(pin_frames[order[i % len(order)]].numpy(), download=False, **PARAMS)
-            return eng.flow_u_stats(B)
+            return eng.flow_u_stats(B, wait=args.e2e_sync or i < 0)
         s_ = i % len(pin_prev)
         return eng.farneback_batch_stats(pin_prev[s_].numpy(), pin_next[s_].numpy(), wait=args.e2e_sync or i < 0, **PARAMS)
 
@@ -604,7 +604,7 @@ def run_ours(args, rank, local_rank, world):
                        " (host buffers, pinned; full float32 [H,W,2] flow of every pair returned to the host)"},
         "e2e_node_contract": {"value": node_value, "unit": UNIT, "h2d_bytes_per_step": (1 if strm else 2) * B * W_ * H_,
                               "d2h_bytes_per_step": 12 * B, "steps": e2e_steps,
-                              "api": ("ofb_farneback_stream + ofb_flow_u_stats (synchronous)" if strm else
+                              "api": ("ofb_farneback_stream(flow=NULL) + ofb_flow_u_stats_async + ofb_wait" if strm else
                                       "ofb_farneback_batch_stats" if args.e2e_sync else "ofb_farneback_batch_stats_async + ofb_wait") +
                                      " (host frames in, on-device mean + exact median of u out: "
                                      "the reduction every node applies, lfn3_sub_node.py:205-212)"},

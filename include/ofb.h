@@ -175,7 +175,8 @@ int ofb_farneback_sequence_device(ofb_handle* h, int n_pairs, const uint8_t* d_f
  *   of n_streams, size or parameters, or after ofb_stream_reset — only primes the state: *produced = 0 and no flow is
  *   written (the node's "first frame only primes" branch, lfn3_sub_node.py:164-167).  Later calls write flow[i]
  *   (float32 [height][width][2]; flow == NULL keeps the fields on the device for ofb_flow_u_stats /
- *   ofb_flow_postfilter) and set *produced = n_streams.  Synchronous. */
+ *   ofb_flow_postfilter) and set *produced = n_streams.  Synchronous when flow != NULL; with flow == NULL the call
+ *   returns once the work is enqueued (page-locked frames: keep them untouched until ofb_wait or a synchronous call). */
 int ofb_farneback_stream(ofb_handle* h, int n_streams, const uint8_t* const* frames, int width, int height,
                          size_t stride_bytes, float* const* flow, size_t flow_stride_bytes,
                          const ofb_farneback_params* params, int* produced);
@@ -250,6 +251,10 @@ int ofb_timing_read_samples(ofb_handle* h, int stage, double* ms_out, int capaci
  * mask: optional uint8 [height][width] host array (non-zero = use), NULL = all.
  * out_mean / out_median: n values (u component); either may be NULL. */
 int ofb_flow_u_stats(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median);
+/* The same, returning once the reduction is enqueued; out_mean / out_median are written by ofb_wait (or by a later
+ * asynchronous reduction once a few are pending) and must stay valid until then.  With ofb_farneback_stream(flow =
+ * NULL) this keeps a camera node's frame-by-frame loop fully asynchronous: the next frames upload behind the kernels. */
+int ofb_flow_u_stats_async(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median);
 
 /* The "adapt" node's flow post-processing, on the device, applied to the field(s) of the last flow call on this
  * handle (replaces ros2_ws/src/liteflownet3/liteflownet3/lfn3_adapt_node.py:236-251):

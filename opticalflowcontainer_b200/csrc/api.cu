@@ -582,17 +582,37 @@ int ofb_farneback_stream(ofb_handle* h, int n_streams, const uint8_t* const* fra
   for (int i = 0; i < n_streams; i++)
     if (!frames[i]) return set_error(h, OFB_ERR_INVALID_ARG, "NULL frame pointer");
   OFB_CUDA(h, cudaSetDevice(h->device));
-  // drain the pipelined batch calls: the stream call shares their staging
-  OFB_CUDA(h, cudaStreamSynchronize(h->s_in));
-  OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
-  h->pipe_n = 0;
+  // the stream call shares the batch calls' staging and events: their pipeline restarts after it
+  if (h->pipe_n != 0) {
+    OFB_CUDA(h, cudaStreamSynchronize(h->s_in));
+    OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    OFB_CUDA(h, cudaStreamSynchronize(h->s_out));
+    h->pipe_n = 0;
+  }
+  while ((int)h->pipe_ev.size() < 6) {
+    cudaEvent_t e;
+    OFB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->pipe_ev.push_back(e);
+  }
+  // Uploads go through the copy-in stream into two alternating staging halves, so that with flow == NULL (fields stay
+  // on the device, nothing to wait for) the next call's upload runs behind this call's kernels.
   const size_t pitch = align_up((size_t)width, 16), istride = pitch * height;
+  h->stream_state.up_parity ^= 1;
+  const int par = h->stream_state.up_parity;
+  uint8_t* stage = h->d_src + (size_t)par * n_streams * istride;
+  cudaEvent_t ev_in = h->pipe_ev[3 * par], ev_comp = h->pipe_ev[3 * par + 1];
+  OFB_CUDA(h, cudaStreamWaitEvent(h->s_in, ev_comp, 0));      // the kernels that read this half two calls ago are done
   for (int i = 0; i < n_streams; i++)   // (pageable frames: the runtime stages them; pinned ones are DMA'd directly)
-    OFB_CUDA(h, cudaMemcpy2DAsync(h->d_src + (size_t)i * istride, pitch, frames[i], stride_bytes, width, height,
-                                  cudaMemcpyHostToDevice, h->stream));
+    OFB_CUDA(h, cudaMemcpy2DAsync(stage + (size_t)i * istride, pitch, frames[i], stride_bytes, width, height,
+                                  cudaMemcpyHostToDevice, h->s_in));
+  OFB_CUDA(h, cudaEventRecord(ev_in, h->s_in));
+  OFB_CUDA(h, cudaStreamWaitEvent(h->stream, ev_in, 0));
   int got = 0;
-  s = ofb_farneback_stream_device(h, n_streams, h->d_src, width, height, pitch, istride, h->d_flow_out, params, &got);
+  s = ofb_farneback_stream_device(h, n_streams, stage, width, height, pitch, istride, h->d_flow_out, params, &got);
   if (s) return s;
+  OFB_CUDA(h, cudaEventRecord(ev_comp, h->stream));
+  if (produced) *produced = got;
+  if (!flow) return OFB_OK;                                   // asynchronous: ofb_wait / ofb_flow_u_stats synchronise
   if (got && flow) {
     const size_t fl_img = (size_t)width * height * 2;
     for (int i = 0; i < n_streams; i++) {
@@ -818,6 +838,11 @@ int ofb_flow_sample(ofb_handle* h, int pair, int n_points, const int* xy, float*
 int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes) {
   if (!h) return OFB_ERR_INVALID_ARG;
   return flow_download(h, n, flow, flow_stride_bytes);
+}
+
+int ofb_flow_u_stats_async(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  return flow_u_stats(h, n, mask, out_mean, out_median, true);
 }
 
 int ofb_flow_u_stats(ofb_handle* h, int n, const uint8_t* mask, double* out_mean, float* out_median) {

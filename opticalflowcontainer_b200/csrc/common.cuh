@@ -175,6 +175,7 @@ struct ofb_handle {
     int n = 0, w = 0, h = 0;     // streams and frame size of the cached state (n == 0: not primed)
     ofb_farneback_params params = {};
     bool cached = false;         // expansions cached (fused path) vs previous frames only
+    int up_parity = 0;           // staging half of the last host-buffer stream call
   } stream_state;
   // last result bookkeeping for ofb_flow_u_stats
   const float* last_flow = nullptr;

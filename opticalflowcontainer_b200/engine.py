@@ -241,6 +241,8 @@ class FlowEngine:
         op = (C.c_void_p * n)(*[out.ctypes.data + i * hgt * wid * 8 for i in range(n)]) if download else None
         got = C.c_int(0)
         with self._lock:
+            if not download:
+                self._pending.append((frames,))      # asynchronous: the upload may still be running when the call returns
             st = self._lib.ofb_farneback_stream(self._h, n, fp, wid, hgt, wid, op, 0, C.byref(p), C.byref(got))
             _lib.check(st, self._h)
         if got.value == 0:
@@ -280,15 +282,25 @@ class FlowEngine:
                                                     d_flow, C.byref(p))
             _lib.check(st, self._h)
 
-    def flow_u_stats(self, n: int = 1, mask: Optional[np.ndarray] = None, mean=True, median=True):
+    def flow_u_stats(self, n: int = 1, mask: Optional[np.ndarray] = None, mean=True, median=True, wait: bool = True):
         """Mean / median of the u component of the most recent flow field(s), reduced on the
-        device (the node contract, lfn3_sub_node.py:205-212)."""
-        om = (C.c_double * n)() if mean else None
-        od = (C.c_float * n)() if median else None
+        device (the node contract, lfn3_sub_node.py:205-212).  ``wait=False`` (ofb_flow_u_stats_async) returns two
+        NumPy arrays that :meth:`wait` fills."""
         mp = None
         if mask is not None:
             mask = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
             mp = mask.ctypes.data
+        if not wait:
+            om = np.zeros(n, np.float64)
+            od = np.zeros(n, np.float32)
+            with self._lock:
+                self._pending.append((om, od, mask))
+                st = self._lib.ofb_flow_u_stats_async(self._h, n, mp, om.ctypes.data if mean else None,
+                                                      od.ctypes.data if median else None)
+                _lib.check(st, self._h)
+            return (om if mean else None), (od if median else None)
+        om = (C.c_double * n)() if mean else None
+        od = (C.c_float * n)() if median else None
         with self._lock:
             st = self._lib.ofb_flow_u_stats(self._h, n, mp, om, od)
             _lib.check(st, self._h)

@@ -287,3 +287,34 @@ def test_repeated_calls_are_deterministic(built_lib):
                 assert np.array_equal(eng.farneback_batch(a, b, winsize=winsize), first)
     finally:
         eng.close()
+
+
+def test_stream_call_asynchronous_reduction(built_lib):
+    """ofb_farneback_stream(flow=NULL) + ofb_flow_u_stats_async: a camera loop that never waits — page-locked frames,
+    several calls in flight, results handed over at ofb_wait — gives the scalars of the synchronous loop."""
+    import torch
+    import opticalflowcontainer_b200 as ofb
+    n, h, w = 2, 135, 240
+    eng = ofb.FlowEngine(w, h, n, 0)
+    ref = ofb.FlowEngine(w, h, n, 0)
+    try:
+        base = [synth.synth_pair(h, w, 90 + s, (0.0, 0.0))[0] for s in range(n)]
+        T = 7
+        frames = [torch.from_numpy(np.stack([synth.subpixel_shift(base[s], 0.8 * t * (s + 1), 0.3 * t) for s in range(n)])).pin_memory()
+                  for t in range(T)]
+        want = []
+        for t in range(T):
+            r = ref.farneback_stream(frames[t].numpy(), download=False)
+            if r is not None:
+                want.append(ref.flow_u_stats(n))
+        got = []
+        for t in range(T):
+            r = eng.farneback_stream(frames[t].numpy(), download=False)
+            if r is not None:
+                got.append(eng.flow_u_stats(n, wait=False))
+        eng.wait()
+        assert len(got) == len(want) == T - 1
+        for (m0, d0), (m1, d1) in zip(want, got):
+            assert np.array_equal(np.asarray(m0), m1) and np.array_equal(np.asarray(d0, np.float32), d1)
+    finally:
+        eng.close(); ref.close()
