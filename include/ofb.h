@@ -302,6 +302,21 @@ int ofb_ingest_gray(ofb_handle* h, const uint8_t* src, int src_width, int src_he
 int ofb_clahe(ofb_handle* h, const uint8_t* src, int width, int height, size_t src_stride_bytes, double clip_limit,
               int tiles_x, int tiles_y, uint8_t* dst, size_t dst_stride_bytes);
 
+/* The adapt node's colour pre-filter in one call (lfn3_adapt_node.py:164-184): cv2.cvtColor(bgr, BGR2HSV), CLAHE on the V
+ * channel — with the node's adaptive clip limit (contrast = std(v) / (mean(v) + 1e-3) mapped linearly from
+ * [c_min, c_max] to [clip_min, clip_max]) when `adaptive` is set, else `clip_limit` — and cv2.cvtColor(..., HSV2RGB):
+ * a bgr8 frame in, the rgb8 frame the node continues with out, every step bit-exact with this cv2 build
+ * (oracle/prefilter_np.py).  *clip_used receives the clip limit applied.  The bilateral filter that may follow
+ * (:189-191) is NOT included: its restatement is not pinned bit-exactly yet.  Synchronous. */
+typedef struct ofb_clahe_params {
+  int adaptive;                              /* 1: clip limit from the frame's contrast, 0: clip_limit */
+  double clip_limit;
+  double clip_min, clip_max, c_min, c_max;   /* adaptive mapping */
+  int tiles_x, tiles_y;                      /* tileGridSize (cv2 default 8 x 8) */
+} ofb_clahe_params;
+int ofb_adapt_prefilter(ofb_handle* h, const uint8_t* bgr, int width, int height, size_t stride_bytes,
+                        const ofb_clahe_params* params, uint8_t* rgb, size_t rgb_stride_bytes, double* clip_used);
+
 /* ---- sparse path: replaces cv2.goodFeaturesToTrack + cv2.calcOpticalFlowPyrLK -- */
 
 /* Shi-Tomasi corners of a uint8 image (host buffer).  corners_xy: capacity

@@ -21,6 +21,11 @@ class OfbError(RuntimeError):
         self.status = status
 
 
+class ClaheParams(C.Structure):
+    _fields_ = [("adaptive", C.c_int), ("clip_limit", C.c_double), ("clip_min", C.c_double), ("clip_max", C.c_double),
+                ("c_min", C.c_double), ("c_max", C.c_double), ("tiles_x", C.c_int), ("tiles_y", C.c_int)]
+
+
 class FarnebackParams(C.Structure):
     _fields_ = [("pyr_scale", C.c_double), ("levels", C.c_int), ("winsize", C.c_int), ("iterations", C.c_int),
                 ("poly_n", C.c_int), ("poly_sigma", C.c_double), ("flags", C.c_int)]
@@ -80,6 +85,8 @@ _SIGNATURES = {
                                   C.c_int, C.c_size_t]),
     "ofb_clahe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_void_p,
                             C.c_size_t]),
+    "ofb_adapt_prefilter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_double)]),
     "ofb_launch_count": (C.c_uint64, [C.c_void_p]),
     "ofb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ofb_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

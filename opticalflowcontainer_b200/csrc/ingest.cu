@@ -198,6 +198,73 @@ __global__ void __launch_bounds__(256) k_clahe_interp(const uint8_t* __restrict_
   dst[(size_t)y * dp + x] = (uint8_t)min(max(r, 0), 255);
 }
 
+// ---- the adapt node's colour pre-filter: BGR -> HSV, CLAHE on V, HSV -> RGB (lfn3_adapt_node.py:164-184) -----------
+// cv2.cvtColor(BGR2HSV) on uint8 is 12-bit fixed point with two division tables; cv2.cvtColor(HSV2RGB) is float32 with
+// 1 - s*f fused, truncated in the 32-pixel vector steps of a row and rounded in the scalar tail (oracle/prefilter_np.py,
+// pinned against the wheel).
+__constant__ int c_sdiv[256];
+__constant__ int c_hdiv[256];
+
+__global__ void __launch_bounds__(256) k_bgr2hsv_planes(const uint8_t* __restrict__ src, size_t sp, int w, int h,
+                                                        uint8_t* __restrict__ Hp, uint8_t* __restrict__ Sp,
+                                                        uint8_t* __restrict__ Vp, size_t pp,
+                                                        unsigned long long* __restrict__ sums) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  unsigned long long sv = 0, sv2 = 0;
+  if (x < w && y < h) {
+    const uint8_t* p = src + (size_t)y * sp + (size_t)x * 3;
+    const int b = p[0], g = p[1], r = p[2];
+    const int v = max(max(b, g), r), vmin = min(min(b, g), r);
+    const int diff = v - vmin;
+    const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+    const int sat = (diff * c_sdiv[v] + (1 << 11)) >> 12;
+    int hh = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+    hh = (hh * c_hdiv[diff] + (1 << 11)) >> 12;
+    hh += hh < 0 ? 180 : 0;
+    const size_t o = (size_t)y * pp + x;
+    Hp[o] = (uint8_t)hh; Sp[o] = (uint8_t)sat; Vp[o] = (uint8_t)v;
+    sv = (unsigned long long)v; sv2 = (unsigned long long)(v * v);
+  }
+  // sum(v), sum(v^2) of the frame for the adaptive clip limit (exact integers)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sv += __shfl_down_sync(0xffffffffu, sv, o);
+    sv2 += __shfl_down_sync(0xffffffffu, sv2, o);
+  }
+  if ((threadIdx.x & 31) == 0 && sv2) { atomicAdd(sums, sv); atomicAdd(sums + 1, sv2); }
+}
+
+__global__ void __launch_bounds__(256) k_hsv2rgb_planes(const uint8_t* __restrict__ Hp, const uint8_t* __restrict__ Sp,
+                                                        const uint8_t* __restrict__ Vp, size_t pp, int w, int h,
+                                                        uint8_t* __restrict__ dst, size_t dp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const size_t o = (size_t)y * pp + x;
+  const float s = __fmul_rn((float)Sp[o], 1.f / 255.f), v = __fmul_rn((float)Vp[o], 1.f / 255.f);
+  float hf = __fmul_rn((float)Hp[o], 6.f / 180.f);
+  int sec = (int)floorf(hf);
+  const float f = __fsub_rn(hf, (float)sec);
+  sec %= 6;
+  const float t1 = __fmul_rn(v, __fsub_rn(1.f, s));
+  const float t2 = __fmul_rn(v, __fmaf_rn(-s, f, 1.f));
+  const float t3 = __fmul_rn(v, __fmaf_rn(-s, __fsub_rn(1.f, f), 1.f));
+  float b, g, r;
+  switch (sec) {            // sector table {b, g, r} <- {v, t1, t2, t3}
+    case 0: b = t1; g = t3; r = v; break;
+    case 1: b = t1; g = v; r = t2; break;
+    case 2: b = t3; g = v; r = t1; break;
+    case 3: b = v; g = t2; r = t1; break;
+    case 4: b = v; g = t1; r = t3; break;
+    default: b = t2; g = t1; r = v; break;
+  }
+  const bool body = x < (w / 32) * 32;       // the wheel's vector loop truncates, its scalar tail rounds
+  const float fr = __fmul_rn(r, 255.f), fg = __fmul_rn(g, 255.f), fb = __fmul_rn(b, 255.f);
+  const int ir = body ? (int)fr : __float2int_rn(fr), ig = body ? (int)fg : __float2int_rn(fg),
+            ib = body ? (int)fb : __float2int_rn(fb);
+  uint8_t* d = dst + (size_t)y * dp + (size_t)x * 3;
+  d[0] = (uint8_t)min(max(ir, 0), 255); d[1] = (uint8_t)min(max(ig, 0), 255); d[2] = (uint8_t)min(max(ib, 0), 255);
+}
+
 static int ingest_reserve(ofb_handle* h, size_t bytes_a, size_t bytes_b) {
   ofb_handle::Ingest& g = h->ingest;
   if (bytes_a > g.a_bytes) {
@@ -349,6 +416,73 @@ int ofb_clahe(ofb_handle* h, const uint8_t* src, int width, int height, size_t s
   OFB_LAUNCH_CHECK(h);
   OFB_CUDA(h, cudaMemcpy2DAsync(dst, dst_stride_bytes, g.d_b, pitch, width, height, cudaMemcpyDeviceToHost, h->stream));
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+int ofb_adapt_prefilter(ofb_handle* h, const uint8_t* bgr, int width, int height, size_t stride_bytes,
+                        const ofb_clahe_params* p, uint8_t* rgb, size_t rgb_stride_bytes, double* clip_used) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!bgr || !rgb || !p) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  if (width < 1 || height < 1 || p->tiles_x < 1 || p->tiles_y < 1 || p->tiles_x > 256 || p->tiles_y > 256)
+    return set_error(h, OFB_ERR_INVALID_ARG, "bad size or tile grid");
+  const size_t row3 = (size_t)width * 3;
+  if (stride_bytes == 0) stride_bytes = row3;
+  if (rgb_stride_bytes == 0) rgb_stride_bytes = row3;
+  if (stride_bytes < row3 || rgb_stride_bytes < row3) return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row");
+  const int tiles_x = p->tiles_x, tiles_y = p->tiles_y;
+  const bool exact = width % tiles_x == 0 && height % tiles_y == 0;
+  const int ew = exact ? width : width + tiles_x - width % tiles_x, eh = exact ? height : height + tiles_y - height % tiles_y;
+  if (ew - width >= width || eh - height >= height)
+    return set_error(h, OFB_ERR_INVALID_ARG, "image too small for a %dx%d tile grid", tiles_x, tiles_y);
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  static bool tables[64] = {false};
+  if (!tables[h->device & 63]) {
+    int sdiv[256], hdiv[256];
+    sdiv[0] = hdiv[0] = 0;
+    for (int i = 1; i < 256; i++) {
+      sdiv[i] = (int)__builtin_nearbyint((255 << 12) / (1.0 * i));
+      hdiv[i] = (int)__builtin_nearbyint((180 << 12) / (6.0 * i));
+    }
+    OFB_CUDA(h, cudaMemcpyToSymbol(c_sdiv, sdiv, sizeof(sdiv)));
+    OFB_CUDA(h, cudaMemcpyToSymbol(c_hdiv, hdiv, sizeof(hdiv)));
+    tables[h->device & 63] = true;
+  }
+  const size_t pp = ((size_t)width + 15) & ~(size_t)15, plane = pp * height;
+  const size_t lut_bytes = (size_t)tiles_x * tiles_y * 256;
+  int st = ingest_reserve(h, row3 * height, 4 * plane + row3 * height + lut_bytes + 64);
+  if (st) return st;
+  ofb_handle::Ingest& g = h->ingest;
+  unsigned long long* d_sums = reinterpret_cast<unsigned long long*>(g.d_b);   // (first: cudaMalloc alignment)
+  uint8_t *Hp = g.d_b + 64, *Sp = Hp + plane, *Vp = Sp + plane, *V2 = Vp + plane, *luts = V2 + plane, *out = luts + lut_bytes;
+  cudaStream_t sm = h->stream;
+  OFB_CUDA(h, cudaMemcpy2DAsync(g.d_a, row3, bgr, stride_bytes, row3, height, cudaMemcpyHostToDevice, sm));
+  OFB_CUDA(h, cudaMemsetAsync(d_sums, 0, 16, sm));
+  const dim3 grid((width + 255) / 256, height);
+  k_bgr2hsv_planes<<<grid, 256, 0, sm>>>(g.d_a, row3, width, height, Hp, Sp, Vp, pp, d_sums);
+  OFB_LAUNCH_CHECK(h);
+  double clip_limit = p->clip_limit;
+  if (p->adaptive) {
+    // contrast = std(v) / (mean(v) + 1e-3), mapped linearly to [clip_min, clip_max] (lfn3_adapt_node.py:170-175)
+    unsigned long long hs[2];
+    OFB_CUDA(h, cudaMemcpyAsync(hs, d_sums, 16, cudaMemcpyDeviceToHost, sm));
+    OFB_CUDA(h, cudaStreamSynchronize(sm));
+    const double n = (double)width * height, mean = (double)hs[0] / n;
+    const double var = std::max((double)hs[1] / n - mean * mean, 0.0);
+    const double contrast = std::sqrt(var) / (mean + 1e-3);
+    clip_limit = p->clip_min + (contrast - p->c_min) / (p->c_max - p->c_min) * (p->clip_max - p->clip_min);
+    clip_limit = std::min(std::max(clip_limit, p->clip_min), p->clip_max);
+  }
+  if (clip_used) *clip_used = clip_limit;
+  const int tw = ew / tiles_x, th = eh / tiles_y, area = tw * th;
+  const int clip = clip_limit > 0.0 ? std::max((int)(clip_limit * area / 256), 1) : 0;
+  k_clahe_lut<<<dim3(tiles_x, tiles_y), 256, 0, sm>>>(Vp, pp, width, height, tw, th, clip, 255.f / (float)area, luts);
+  OFB_LAUNCH_CHECK(h);
+  k_clahe_interp<<<grid, 256, 0, sm>>>(Vp, pp, V2, pp, width, height, tiles_x, tiles_y, 1.f / (float)tw, 1.f / (float)th, luts);
+  OFB_LAUNCH_CHECK(h);
+  k_hsv2rgb_planes<<<grid, 256, 0, sm>>>(Hp, Sp, V2, pp, width, height, out, row3);
+  OFB_LAUNCH_CHECK(h);
+  OFB_CUDA(h, cudaMemcpy2DAsync(rgb, rgb_stride_bytes, out, row3, row3, height, cudaMemcpyDeviceToHost, sm));
+  OFB_CUDA(h, cudaStreamSynchronize(sm));
   return OFB_OK;
 }
 

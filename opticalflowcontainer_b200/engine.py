@@ -411,6 +411,27 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out
 
+    def adapt_prefilter(self, bgr, clipLimit: Optional[float] = None, clip_range=(1.0, 4.0, 0.1, 0.8), tileGridSize=(8, 8)):
+        """The adapt node's colour pre-filter (lfn3_adapt_node.py:164-184) on the device: BGR2HSV, CLAHE on V with the
+        adaptive clip limit (``clipLimit=None``; ``clip_range`` = (clip_min, clip_max, C_min, C_max)) or a fixed one,
+        HSV2RGB.  Returns (rgb uint8 [H,W,3], clip limit used); bit-exact with cv2."""
+        bgr = np.asarray(bgr)
+        if bgr.dtype != np.uint8 or bgr.ndim != 3 or bgr.shape[2] != 3:
+            raise OfbError(1, "adapt_prefilter needs a uint8 [H,W,3] frame")
+        if bgr.strides[2] != 1 or bgr.strides[1] != 3:
+            bgr = np.ascontiguousarray(bgr)
+        hgt, wid = bgr.shape[:2]
+        out = np.empty((hgt, wid, 3), np.uint8)
+        cp = _lib.ClaheParams(1 if clipLimit is None else 0, 0.0 if clipLimit is None else float(clipLimit),
+                              float(clip_range[0]), float(clip_range[1]), float(clip_range[2]), float(clip_range[3]),
+                              int(tileGridSize[0]), int(tileGridSize[1]))
+        used = C.c_double(0.0)
+        with self._lock:
+            st = self._lib.ofb_adapt_prefilter(self._h, bgr.ctypes.data, wid, hgt, bgr.strides[0], C.byref(cp),
+                                               out.ctypes.data, 0, C.byref(used))
+            _lib.check(st, self._h)
+        return out, used.value
+
     def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3) -> np.ndarray:
         image = _u8_image(image, "image")
         hgt, wid = image.shape

@@ -309,3 +309,27 @@ def test_clahe_bit_exact(engine_factory, size):
     for im in (low, noise):
         for clip, grid in [(2.0, (8, 8)), (40.0, (8, 8)), (0.0, (4, 6)), (adaptive_clip_limit(im, 1.0, 4.0, 0.1, 0.8), (8, 8))]:
             assert np.array_equal(eng.clahe(im, clip, grid), cv2.createCLAHE(clipLimit=clip, tileGridSize=grid).apply(im))
+
+
+@pytest.mark.parametrize("size", [(480, 640), (243, 317), (96, 100)])
+def test_adapt_prefilter_bit_exact(engine_factory, size):
+    """ofb_adapt_prefilter == the adapt node's BGR2HSV -> adaptive CLAHE on V -> HSV2RGB in cv2 (lfn3_adapt_node.py:164-184),
+    bit for bit, for widths with and without a scalar tail in cv2's HSV2RGB."""
+    import cv2
+    eng = engine_factory(64, 64)
+    rng = np.random.default_rng(size[1])
+    bgr = cv2.GaussianBlur(rng.integers(0, 256, size=size + (3,), dtype=np.uint8), (0, 0), 1.5)
+    bgr[: size[0] // 4] = rng.integers(0, 256, size=(size[0] // 4, size[1], 3), dtype=np.uint8)
+    hsv = cv2.cvtColor(bgr, cv2.COLOR_BGR2HSV)
+    h, s, v = cv2.split(hsv)
+    for clip in (None, 2.0, 40.0):
+        c = clip
+        if clip is None:       # the node's adaptive clip limit
+            contrast = np.std(v) / (np.mean(v) + 1e-3)
+            c = float(np.clip(1.0 + (contrast - 0.1) / (0.8 - 0.1) * (4.0 - 1.0), 1.0, 4.0))
+        clahe = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8))
+        clahe.setClipLimit(c)
+        want = cv2.cvtColor(cv2.merge((h, s, clahe.apply(v))), cv2.COLOR_HSV2RGB)
+        got, used = eng.adapt_prefilter(bgr, clip, (1.0, 4.0, 0.1, 0.8), (8, 8))
+        assert abs(used - c) <= 1e-9 * max(1.0, abs(c))
+        assert np.array_equal(got, want)
