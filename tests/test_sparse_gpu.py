@@ -138,3 +138,30 @@ def test_pyrlk_1080p_2000_points_and_module_api(built_lib):
     _lk_check(ref, got)
     n, pyr = ofb.buildOpticalFlowPyramid(a, (21, 21), 3, True)
     assert n == 3 and np.array_equal(pyr[2], cv2.pyrDown(a))
+
+
+def test_handles_are_independent_across_threads(built_lib):
+    """One handle and one host thread per camera stream (how bench.py --mode lk and a multi-camera node run): the
+    concurrent results equal the sequential ones bit for bit."""
+    from concurrent.futures import ThreadPoolExecutor
+    import opticalflowcontainer_b200 as ofb
+    h, w, n = 270, 480, 4
+    pairs = [synth.synth_pair(h, w, 500 + s, (2.1 + 0.5 * s, -1.3 + 0.4 * s)) for s in range(n)]
+    engines = [ofb.FlowEngine(w, h, 1, 0) for _ in range(n)]
+    try:
+        def work(i):
+            a, b = pairs[i]
+            pts = engines[i].good_features(a, 500, 0.01, 7, 3)
+            nxt, st, err = engines[i].pyrlk(a, b, pts, None, (21, 21), 3, (3, 30, 0.01))
+            flow = engines[i].farneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+            return pts, nxt, st, err, flow
+        seq = [work(i) for i in range(n)]
+        with ThreadPoolExecutor(max_workers=n) as pool:
+            for _ in range(3):
+                par = list(pool.map(work, range(n)))
+                for s, p in zip(seq, par):
+                    for x, y in zip(s, p):
+                        assert np.array_equal(x, y)
+    finally:
+        for e in engines:
+            e.close()
