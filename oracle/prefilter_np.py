@@ -19,7 +19,9 @@ as this cv2 build (4.13, AVX2 dispatch) computes each step on uint8 images:
   ``(float)exp(-0.5 r^2 / sigma_space^2) * (float)exp(-0.5 c^2 / sigma_color^2)`` with c = |db| + |dg| + |dr|, sums
   accumulated in float in row-major support order, ``cvRound(sum * (1.f / wsum))``.
 BGR2HSV, HSV2RGB and the chain without the bilateral filter are pinned bit for bit against the wheel in
-``tests/test_oracle_prefilter.py``.  The bilateral restatement is NOT: it differs from the wheel at rounding ties
+``tests/test_oracle_prefilter.py``.  The bilateral restatement is NOT: this wheel routes the 8-bit bilateralFilter
+through Intel IPP (``cv2.ipp.useIPP()`` is True; with ``cv2.ipp.setUseIPP(False)`` the mismatches drop from 13 to 3 in
+1.9 M values), whose arithmetic is not published; the restatement of OpenCV's own code differs from it at rounding ties
 (a few values per 100 000, off by one) — parity unpinned for that step, which is therefore not built on the device.
 """
 from __future__ import annotations
