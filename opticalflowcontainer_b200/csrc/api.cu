@@ -165,6 +165,7 @@ int ofb_destroy(ofb_handle* h) {
   if (h->h_lintab) cudaFreeHost(h->h_lintab);
   if (h->h_src) cudaFreeHost(h->h_src);
   if (h->h_flow) cudaFreeHost(h->h_flow);
+  farneback_graphs_destroy(h);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   for (auto& e : h->stats_ev) if (e) cudaEventDestroy(e);
   if (h->d_gray) cudaFree(h->d_gray);
@@ -245,6 +246,8 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     if (iw) h->iter_waves = std::max(1, atoi(iw));
     const char* pt = getenv("OFB_POLYEXP_TILE");
     h->polyexp_tile = pt && pt[0] == '1';
+    const char* gr = getenv("OFB_GRAPH");
+    h->no_graph = gr && gr[0] == '0';
     const char* pf = getenv("OFB_PYR_FAST");
     h->no_pyr_fast = pf && pf[0] == '0';
     const char* nf = getenv("OFB_NO_FUSED_SRC");

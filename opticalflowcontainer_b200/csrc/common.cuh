@@ -109,6 +109,8 @@ struct ofb_handle {
   int iter_mode = 3;
   int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
   bool polyexp_tile = false;   // OFB_POLYEXP_TILE=1: 32x32-tile PolyExp kernel instead of the marching one
+  bool no_graph = false;       // OFB_GRAPH=0: no CUDA-graph replay of the launch sequence of small batches
+  void* graph_cache = nullptr; // farneback.cu: captured launch sequences (std::vector<GraphEntry>)
   bool no_pyr_fast = false;    // OFB_PYR_FAST=0: two-pass pyramid kernels also for the regular power-of-two levels
   bool no_fused_src = false;   // OFB_NO_FUSED_SRC=1: level-0 pyramid stage as separate kernels
   int px_waves = 4;            // OFB_PX_WAVES: target CTA waves of the marching PolyExp kernel
@@ -255,6 +257,7 @@ cudaError_t launch_iter_fixed_a(ofb_handle* h, int m, const float2* fin, float2*
                                 const RSet& rs, float reg, cudaStream_t st, bool* served);
 cudaError_t launch_iter_fixed_b(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
                                 const RSet& rs, float reg, cudaStream_t st, bool* served);
+void farneback_graphs_destroy(ofb_handle* h);
 // the schedule farneback_run would use (level sizes), for sizing the stream cache
 int farneback_levels(int width, int height, const ofb_farneback_params* p, Level* out, int* n_out);
 // true if farneback_run can serve this configuration from the stream cache (fused box-window path, marching PolyExp)

@@ -16,6 +16,8 @@
 
 #include <algorithm>
 
+#include <vector>
+
 #include "common.cuh"
 #include "fb_device.cuh"
 #include "fb_iter_ws.cuh"
@@ -469,17 +471,107 @@ bool farneback_stream_supported(const ofb_handle* h, const ofb_farneback_params*
 
 static inline dim3 grid2d(int w, int h, int z, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y, z); }
 
+static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
+                              int width, int height, size_t pitch, size_t image_stride, float* d_flow_out,
+                              const float* d_init_flow, const ofb_farneback_params* p, const StreamCtx* sc);
+
+// Small batches are launch-bound (a VGA pair is ~40 kernels of a few microseconds each): the launch sequence of a call
+// is captured once per distinct argument set into a CUDA graph and replayed.  The key holds everything the launches
+// depend on (pointers, geometry, parameters, stream-cache half); coordinate tables are brought up to date outside the
+// graph.  Not used while the stage timers are on (event timing cannot be captured) or with OFB_GRAPH=0.
+struct GraphKey {
+  int n_pairs, sequence, width, height, cur, prime_only;
+  const void *d_prev, *d_next, *d_flow_out, *d_init_flow;
+  size_t pitch, image_stride;
+  ofb_farneback_params p;
+  bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec;
+  uint64_t launches, stamp;
+};
+constexpr int kGraphMaxPairs = 4, kGraphCache = 16;
+
+void farneback_graphs_destroy(ofb_handle* h) {
+  auto* v = static_cast<std::vector<GraphEntry>*>(h->graph_cache);
+  if (!v) return;
+  for (auto& e : *v) cudaGraphExecDestroy(e.exec);
+  delete v;
+  h->graph_cache = nullptr;
+}
+
 int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
                   int width, int height, size_t pitch, size_t image_stride, float* d_flow_out,
                   const float* d_init_flow, const ofb_farneback_params* p, const StreamCtx* sc) {
+  {
+    Level sched[kMaxLevels];
+    int n_levels = 0;
+    if (build_schedule(width, height, p->pyr_scale, p->levels, sched, &n_levels) != OFB_OK)
+      return set_error(h, OFB_ERR_INVALID_ARG, "too many pyramid levels");
+    int s__ = ensure_lintabs(h, sched, n_levels, width, height, p->pyr_scale);
+    if (s__) return s__;
+  }
+  if (h->no_graph || h->timing || n_pairs > kGraphMaxPairs)
+    return farneback_run_impl(h, n_pairs, sequence, d_prev, d_next, width, height, pitch, image_stride, d_flow_out,
+                              d_init_flow, p, sc);
+  if (!h->graph_cache) h->graph_cache = new std::vector<GraphEntry>();
+  auto& cache = *static_cast<std::vector<GraphEntry>*>(h->graph_cache);
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.n_pairs = n_pairs; key.sequence = sequence; key.width = width; key.height = height;
+  key.cur = sc ? sc->cur : -1; key.prime_only = sc ? (int)sc->prime_only : 0;
+  key.d_prev = d_prev; key.d_next = d_next; key.d_flow_out = d_flow_out; key.d_init_flow = d_init_flow;
+  key.pitch = pitch; key.image_stride = image_stride;
+  key.p.pyr_scale = p->pyr_scale; key.p.levels = p->levels; key.p.winsize = p->winsize; key.p.iterations = p->iterations;
+  key.p.poly_n = p->poly_n; key.p.poly_sigma = p->poly_sigma; key.p.flags = p->flags;
+  static uint64_t clock = 0;
+  for (auto& e : cache)
+    if (e.key == key) {
+      e.stamp = ++clock;
+      OFB_CUDA(h, cudaGraphLaunch(e.exec, h->stream));
+      h->launches += e.launches;
+      h->last_flow = d_flow_out; h->last_n = n_pairs; h->last_w = width; h->last_h = height;
+      return OFB_OK;
+    }
+  const uint64_t l0 = h->launches;
+  OFB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = farneback_run_impl(h, n_pairs, sequence, d_prev, d_next, width, height, pitch, image_stride, d_flow_out,
+                                    d_init_flow, p, sc);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+  if (rc != OFB_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc;
+  }
+  if (ce != cudaSuccess || !graph) return set_error(h, OFB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+  GraphEntry e;
+  e.key = key;
+  e.launches = h->launches - l0;
+  e.stamp = ++clock;
+  const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
+  if ((int)cache.size() >= kGraphCache) {             // evict the least recently used
+    size_t lru = 0;
+    for (size_t i = 1; i < cache.size(); i++) if (cache[i].stamp < cache[lru].stamp) lru = i;
+    cudaGraphExecDestroy(cache[lru].exec);
+    cache[lru] = e;
+  } else {
+    cache.push_back(e);
+  }
+  OFB_CUDA(h, cudaGraphLaunch(e.exec, h->stream));
+  return OFB_OK;
+}
+
+static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_prev, const uint8_t* d_next,
+                              int width, int height, size_t pitch, size_t image_stride, float* d_flow_out,
+                              const float* d_init_flow, const ofb_farneback_params* p, const StreamCtx* sc) {
   Level sched[kMaxLevels];
   int n_levels = 0;
   if (build_schedule(width, height, p->pyr_scale, p->levels, sched, &n_levels) != OFB_OK)
     return set_error(h, OFB_ERR_INVALID_ARG, "too many pyramid levels");
-  {
-    int s__ = ensure_lintabs(h, sched, n_levels, width, height, p->pyr_scale);
-    if (s__) return s__;
-  }
   PolyCoef pc;
   prepare_poly(p->poly_n, p->poly_sigma, &pc);
   BlurCoef bc;
