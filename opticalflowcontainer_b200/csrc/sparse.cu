@@ -246,11 +246,10 @@ __global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ ei
 // cv2's sequential rule, in rounds of 1024 candidates by one CTA:
 //   phase 1 (1024 threads): every candidate of the round is tested against the corners accepted in EARLIER rounds
 //            (grid of cell = cvRound(minDistance), +-1 cell); the survivors are compacted in rank order;
-//   phase 2 (warp 0): the survivors are resolved in order, 32 at a time — tested against the grid again (it now also
-//            holds the corners accepted earlier in this round), then within the 32 by ballots/shuffles — and committed.
-// Most candidates die in phase 1, so the sequential part only sees (accepted + in-round conflicts) candidates: ~3x fewer
-// dependent global-memory round trips than the one-warp sweep over all candidates.
+//   phase 2 (1024 threads): the survivors decide among themselves by the parallel form of the same rule (see below)
+//            and the accepted ones are committed in rank order, up to the corner limit.
 constexpr int GS_THREADS = 1024;
+constexpr int GS_BUCKETS = 4096;
 
 __device__ __forceinline__ bool gs_far_from_accepted(int x, int y, int cell, int gw, int gh, float md2,
                                                      const unsigned int* grid_cnt, const ushort2* grid_pts) {
@@ -276,6 +275,9 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
   __shared__ unsigned int surv[GS_THREADS];          // x | y << 16, rank order
   __shared__ unsigned int warp_cnt[GS_THREADS / 32];
   __shared__ unsigned int s_nsurv, s_accepted;
+  __shared__ unsigned int bucket[GS_BUCKETS];        // head of the chain of in-round survivors per hashed grid cell
+  __shared__ unsigned short chain[GS_THREADS];
+  __shared__ unsigned char state[GS_THREADS];        // 0 undecided, 1 accepted, 2 rejected
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned int total = min(*count_ptr, cap);
   const unsigned int limit = max_corners > 0 ? (unsigned int)max_corners : 0xffffffffu;
@@ -313,42 +315,76 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
     if (alive) surv[off + __popc(bal & ((1u << lane) - 1u))] = (unsigned int)x | ((unsigned int)y << 16);
     if (tid == GS_THREADS - 1) s_nsurv = off + __popc(bal);
     __syncthreads();
-    // ---- phase 2
-    if (wid == 0) {
+    // ---- phase 2: the survivors of the round decide among themselves, all in parallel.  Survivor i (rank order) is
+    // rejected as soon as an EARLIER survivor within minDistance is accepted, and accepted once all of those are
+    // rejected; the lowest-ranked undecided survivor can always decide, so the loop ends, and the result is the
+    // sequential rule's (the lexicographically first maximal independent set is unique).  Neighbours are found through
+    // a hash of the grid cell into 4096 chains in shared memory.
+    {
       const unsigned int ns = s_nsurv;
-      unsigned int accepted = s_accepted;
-      for (unsigned int cb = 0; cb < ns && accepted < limit; cb += 32) {
-        bool al = cb + lane < ns;
-        int sx = 0, sy = 0;
-        if (al) {
-          const unsigned int v = surv[cb + lane];
-          sx = (int)(v & 0xffffu);
-          sy = (int)(v >> 16);
-          al = gs_far_from_accepted(sx, sy, cell, gw, gh, md2, grid_cnt, grid_pts);
-        }
-        unsigned int alive_mask = __ballot_sync(0xffffffffu, al);
-        unsigned int take_mask = 0;
-        while (alive_mask && accepted < limit) {
-          const int j = __ffs(alive_mask) - 1;
-          const int xj = __shfl_sync(0xffffffffu, sx, j), yj = __shfl_sync(0xffffffffu, sy, j);
-          take_mask |= 1u << j;
-          accepted++;
-          const float dx = (float)(sx - xj), dy = (float)(sy - yj);
-          const bool killed = lane > j && (dx * dx + dy * dy < md2);
-          alive_mask &= ~(1u << j);
-          alive_mask &= ~__ballot_sync(0xffffffffu, killed);
-        }
-        if (take_mask >> lane & 1u) {
-          const unsigned int pos = accepted - __popc(take_mask) + __popc(take_mask & ((1u << lane) - 1u));
-          corners[pos] = make_float2((float)sx, (float)sy);
-          const int c = (sy / cell) * gw + (sx / cell);
-          const unsigned int sl = atomicAdd(&grid_cnt[c], 1u);
-          if (sl < (unsigned int)kGridSlots) grid_pts[c * kGridSlots + sl] = make_ushort2((unsigned short)sx, (unsigned short)sy);
-        }
-        __threadfence_block();
-        __syncwarp();
+      for (int b = tid; b < GS_BUCKETS; b += GS_THREADS) bucket[b] = 0xffffu;
+      __syncthreads();
+      int sx = 0, sy = 0;
+      if ((unsigned int)tid < ns) {
+        const unsigned int v = surv[tid];
+        sx = (int)(v & 0xffffu);
+        sy = (int)(v >> 16);
+        state[tid] = 0;
       }
-      if (lane == 0) s_accepted = accepted;
+      __syncthreads();
+      // chain inserts in rank order by one warp per 32 survivors is not needed: chains are unordered, the rank test is
+      // explicit (j < i).  atomicExch on 32-bit words holding the 16-bit index.
+      if ((unsigned int)tid < ns) {
+        const unsigned int bk = ((unsigned int)(sy / cell) * 73u + (unsigned int)(sx / cell)) & (GS_BUCKETS - 1);
+        chain[tid] = (unsigned short)atomicExch(&bucket[bk], (unsigned int)tid);
+      }
+      __syncthreads();
+      for (;;) {
+        bool undecided = false;
+        if ((unsigned int)tid < ns && state[tid] == 0) {
+          bool blocked = false, rejected = false;
+          const int xc = sx / cell, yc = sy / cell;
+          for (int yy = max(0, yc - 1); yy <= min(gh - 1, yc + 1) && !rejected; yy++)
+            for (int xx = max(0, xc - 1); xx <= min(gw - 1, xc + 1) && !rejected; xx++) {
+              unsigned int k = bucket[((unsigned int)yy * 73u + (unsigned int)xx) & (GS_BUCKETS - 1)];
+              while (k != 0xffffu) {
+                if (k < (unsigned int)tid) {
+                  const unsigned int p = surv[k];
+                  const float dx = (float)(sx - (int)(p & 0xffffu)), dy = (float)(sy - (int)(p >> 16));
+                  if (dx * dx + dy * dy < md2) {
+                    const unsigned char sk = *(volatile unsigned char*)&state[k];
+                    if (sk == 1) { rejected = true; break; }
+                    if (sk == 0) blocked = true;
+                  }
+                }
+                k = chain[k];
+              }
+            }
+          if (rejected) state[tid] = 2;
+          else if (!blocked) state[tid] = 1;
+          else undecided = true;
+        }
+        if (!__syncthreads_or(undecided)) break;
+      }
+      // accepted survivors in rank order -> positions; stop at the corner limit
+      const bool acc = (unsigned int)tid < ns && state[tid] == 1;
+      const unsigned int bal2 = __ballot_sync(0xffffffffu, acc);
+      if (lane == 0) warp_cnt[wid] = __popc(bal2);
+      __syncthreads();
+      unsigned int before = 0, total_acc = 0;
+      for (int k = 0; k < GS_THREADS / 32; k++) {
+        if (k < wid) before += warp_cnt[k];
+        total_acc += warp_cnt[k];
+      }
+      const unsigned int pos = s_accepted + before + __popc(bal2 & ((1u << lane) - 1u));
+      if (acc && pos < limit) {
+        corners[pos] = make_float2((float)sx, (float)sy);
+        const int c = (sy / cell) * gw + (sx / cell);
+        const unsigned int sl = atomicAdd(&grid_cnt[c], 1u);
+        if (sl < (unsigned int)kGridSlots) grid_pts[c * kGridSlots + sl] = make_ushort2((unsigned short)sx, (unsigned short)sy);
+      }
+      __syncthreads();
+      if (tid == 0) s_accepted = min(s_accepted + total_acc, limit);
     }
     __threadfence_block();
     __syncthreads();
