@@ -111,6 +111,7 @@ struct ofb_handle {
   bool polyexp_tile = false;   // OFB_POLYEXP_TILE=1: 32x32-tile PolyExp kernel instead of the marching one
   bool no_graph = false;       // OFB_GRAPH=0: no CUDA-graph replay of the launch sequence of small batches
   void* graph_cache = nullptr; // farneback.cu: captured launch sequences (std::vector<GraphEntry>)
+  uint64_t graph_clock = 0;    // LRU stamp of the graph cache
   bool no_pyr_fast = false;    // OFB_PYR_FAST=0: two-pass pyramid kernels also for the regular power-of-two levels
   bool no_fused_src = false;   // OFB_NO_FUSED_SRC=1: level-0 pyramid stage as separate kernels
   int px_waves = 4;            // OFB_PX_WAVES: target CTA waves of the marching PolyExp kernel

@@ -525,10 +525,9 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   key.pitch = pitch; key.image_stride = image_stride;
   key.p.pyr_scale = p->pyr_scale; key.p.levels = p->levels; key.p.winsize = p->winsize; key.p.iterations = p->iterations;
   key.p.poly_n = p->poly_n; key.p.poly_sigma = p->poly_sigma; key.p.flags = p->flags;
-  static uint64_t clock = 0;
   for (auto& e : cache)
     if (e.key == key) {
-      e.stamp = ++clock;
+      e.stamp = ++h->graph_clock;
       OFB_CUDA(h, cudaGraphLaunch(e.exec, h->stream));
       h->launches += e.launches;
       h->last_flow = d_flow_out; h->last_n = n_pairs; h->last_w = width; h->last_h = height;
@@ -549,7 +548,7 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   GraphEntry e;
   e.key = key;
   e.launches = h->launches - l0;
-  e.stamp = ++clock;
+  e.stamp = ++h->graph_clock;
   const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (ie != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
