@@ -149,6 +149,15 @@ int ofb_synchronize(ofb_handle* h) {
   if (!h) return OFB_ERR_INVALID_ARG;
   OFB_CUDA(h, cudaSetDevice(h->device));
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->tile.imported && h->tile.d_err) {
+    // tiled mode: a flag barrier that timed out let later stages run on halo rows that were not final
+    int v = 0;
+    OFB_CUDA(h, cudaMemcpy(&v, h->tile.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (v) {
+      OFB_CUDA(h, cudaMemset(h->tile.d_err, 0, sizeof(int)));
+      return set_error(h, OFB_ERR_CUDA, "tiled mode: a peer did not reach the stage barrier in time; the field of this call is invalid");
+    }
+  }
   return OFB_OK;
 }
 
@@ -230,30 +239,9 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
   CREATE_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   {
-    const char* fg = getenv("OFB_FORCE_GENERIC");
-    h->force_generic = fg && fg[0] == '1';
-    const char* ic = getenv("OFB_ITER_COLS");
-    if (ic) h->iter_cols = atoi(ic) == 128 ? 128 : 256;
-    const char* ws = getenv("OFB_ITER_WS");
-    if (ws) h->iter_ws = std::min(4, std::max(0, atoi(ws)));
-    const char* ip = getenv("OFB_ITER_PREFETCH");
-    if (ip) h->iter_prefetch = ip[0] != '0';
-    const char* ipd = getenv("OFB_ITER_PFD");
-    if (ipd) h->iter_pfd = atoi(ipd) == 2 ? 2 : 3;
-    const char* im = getenv("OFB_ITER_MODE");
-    if (im) h->iter_mode = std::min(3, std::max(0, atoi(im)));
-    const char* iw = getenv("OFB_ITER_WAVES");
-    if (iw) h->iter_waves = std::max(1, atoi(iw));
-    const char* pt = getenv("OFB_POLYEXP_TILE");
-    h->polyexp_tile = pt && pt[0] == '1';
+    // host-side debugging knobs only (kernel experiments are compile-time: tools/build_variant.sh)
     const char* gr = getenv("OFB_GRAPH");
     h->no_graph = gr && gr[0] == '0';
-    const char* pf = getenv("OFB_PYR_FAST");
-    h->no_pyr_fast = pf && pf[0] == '0';
-    const char* nf = getenv("OFB_NO_FUSED_SRC");
-    h->no_fused_src = nf && nf[0] == '1';
-    const char* pw = getenv("OFB_PX_WAVES");
-    if (pw) h->px_waves = std::max(1, atoi(pw));
     const char* pch = getenv("OFB_PIPE_CHUNK");
     if (pch) h->pipe_chunk = std::max(0, atoi(pch));
     const char* np = getenv("OFB_NO_PIPELINE");
@@ -683,6 +671,10 @@ static int farneback_batch_impl(ofb_handle* h, int n, const uint8_t* const* prev
     }
     const bool use_init = (params->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) != 0;
     if (whole) h->pipe_parity ^= 1;
+    // every chunk has its own staging and result pointers, i.e. its own graph key: a batch split into more chunks than
+    // half the graph cache would evict its own entries on every call (capture + instantiate per chunk) — and such a
+    // batch is not launch-bound anyway
+    h->graph_bypass = chunks > 8;
     for (int ci = 0; ci < chunks; ci++) {
       const int i0 = ci * c, cn = std::min(c, n - i0);
       const int slot = whole ? h->pipe_parity : ci;             // staging region and its three events
@@ -703,7 +695,7 @@ static int farneback_batch_impl(ofb_handle* h, int n, const uint8_t* const* prev
       OFB_CUDA(h, cudaStreamWaitEvent(h->stream, ev_out, 0));    // previous call's download of this result slot is done
       st = farneback_run(h, cn, false, base, base + (size_t)cn * istride, width, height, pitch, istride,
                          h->d_flow_out + i0 * fl_img, use_init ? h->d_init_flow + i0 * fl_img : nullptr, params);
-      if (st) return st;
+      if (st) { h->graph_bypass = false; return st; }
       OFB_CUDA(h, cudaEventRecord(ev_comp, h->stream));
       OFB_CUDA(h, cudaStreamWaitEvent(h->s_out, ev_comp, 0));
       for (int i = 0; i < cn && download; i++)
@@ -711,6 +703,7 @@ static int farneback_batch_impl(ofb_handle* h, int n, const uint8_t* const* prev
                                       row_flow, height, cudaMemcpyDeviceToHost, h->s_out));
       OFB_CUDA(h, cudaEventRecord(ev_out, h->s_out));
     }
+    h->graph_bypass = false;
     h->last_flow = h->d_flow_out;
     h->last_n = n;
     if (wait) {

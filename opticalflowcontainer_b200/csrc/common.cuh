@@ -16,7 +16,8 @@ namespace ofb {
 constexpr int kMaxLevels = 16;     // scales per call (cv2 clamps by the 32-px rule long before)
 constexpr int kMaxPolyN = 10;      // poly_n <= 10 (cv2 users: 5 or 7)
 constexpr int kMaxBlurRadius = 64; // winsize <= 129
-constexpr int kRowPad = 10;        // spare rows at the end of the R buffers (k_iter_ws2 prefetches up to 3 rows past a pixel)
+constexpr int kRowPad = 10;        // spare rows at the end of the R buffers (the prefetching schedule reads up to 4 rows past a pixel)
+constexpr int kPxWaves = 4;        // target CTA waves of the marching PolyExp kernel
 
 // One pyramid scale of the Farneback schedule (FarnebackOpticalFlowImpl::calc).
 struct Level {
@@ -96,25 +97,10 @@ struct ofb_handle {
   int max_w = 0, max_h = 0, max_batch = 0;
   cudaStream_t stream = nullptr;
   int num_sms = 148;
-  bool force_generic = false;  // OFB_FORCE_GENERIC=1: always take the generic (unfused) kernels
-  int iter_cols = 256;         // OFB_ITER_COLS: strip width / CTA size of the fused iteration kernel (128|256)
-  int iter_ws = 4;             // OFB_ITER_WS=1: k_iter_ws (double vertical sums, cv2's scheme) instead of k_iter_v
-  int iter_pfd = 3;            // OFB_ITER_PFD: L2 prefetch distance (rows) of k_iter_v (2 or 3)
-  bool iter_prefetch = true;   // OFB_ITER_PREFETCH=0: no L2 prefetch of the next chunk in k_iter_ws2
-  // OFB_ITER_MODE: producer load schedule of k_iter_v for the default window (measured, 18 pairs of 1080p, iteration
-  // stage; all four produce the same bits): 3 = two rows of loads in flight + row-reuse gather, no L2 prefetch,
-  // producers at 96 registers by setmaxnreg (2.15 ms, default); 2 = the same with the full 2x2 gather (2.26 ms);
-  // 1 = one row in flight, row-reuse gather, L2 prefetch 3 rows ahead, producers at 88 registers (2.34 ms);
-  // 0 = one row in flight, full gather, L2 prefetch, 80 registers for every thread (2.37 ms)
-  int iter_mode = 3;
-  int iter_waves = 1;         // OFB_ITER_WAVES: target CTA waves of the fused iteration kernel
-  bool polyexp_tile = false;   // OFB_POLYEXP_TILE=1: 32x32-tile PolyExp kernel instead of the marching one
   bool no_graph = false;       // OFB_GRAPH=0: no CUDA-graph replay of the launch sequence of small batches
+  bool graph_bypass = false;   // set by the host-buffer batch call while a batch is split into more chunks than the cache holds
   void* graph_cache = nullptr; // farneback.cu: captured launch sequences (std::vector<GraphEntry>)
   uint64_t graph_clock = 0;    // LRU stamp of the graph cache
-  bool no_pyr_fast = false;    // OFB_PYR_FAST=0: two-pass pyramid kernels also for the regular power-of-two levels
-  bool no_fused_src = false;   // OFB_NO_FUSED_SRC=1: level-0 pyramid stage as separate kernels
-  int px_waves = 4;            // OFB_PX_WAVES: target CTA waves of the marching PolyExp kernel
   // host-buffer pipeline: copy-in / copy-out streams and their events (api.cu)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> pipe_ev;
@@ -254,10 +240,11 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
 // k_iter_v with the window radius as a template argument for the common window sizes other than the default
 // (iter_fixed_a.cu, iter_fixed_b.cu: separate translation units so that they compile in parallel).  *served = false if
 // there is no instantiation for m (the caller then takes the run-time-radius kernel).
+struct UpsSrc;
 cudaError_t launch_iter_fixed_a(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                const RSet& rs, float reg, cudaStream_t st, bool* served);
+                                const RSet& rs, float reg, cudaStream_t st, const UpsSrc* ups, bool* served);
 cudaError_t launch_iter_fixed_b(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                const RSet& rs, float reg, cudaStream_t st, bool* served);
+                                const RSet& rs, float reg, cudaStream_t st, const UpsSrc* ups, bool* served);
 void farneback_graphs_destroy(ofb_handle* h);
 // the schedule farneback_run would use (level sizes), for sizing the stream cache
 int farneback_levels(int width, int height, const ofb_farneback_params* p, Level* out, int* n_out);

@@ -20,11 +20,22 @@
 
 #include "common.cuh"
 #include "fb_device.cuh"
-#include "fb_iter_ws.cuh"
 #include "fb_iter_v.cuh"
 #include "fb_iter_launch.cuh"
 #include "fb_polyexp.cuh"
 #include "fb_pyramid.cuh"
+
+// Experiment builds only (tools/build_variant.sh passes -D flags; the shipped library has one path): ring of the default
+// iteration kernel in tensor memory or shared memory, depth of its staging pipeline, fused inter-level upsample.
+#ifndef OFB_EXP_TMEM
+#define OFB_EXP_TMEM true
+#endif
+#ifndef OFB_EXP_NBUF
+#define OFB_EXP_NBUF 4
+#endif
+#ifndef OFB_EXP_FUSE_UPS
+#define OFB_EXP_FUSE_UPS true
+#endif
 
 namespace ofb {
 
@@ -180,7 +191,7 @@ static int prepare_pyr(int ksize, double sigma, PyrCoef* pc) {
 }
 
 // =====================================================================================
-// Stage a4: FarnebackPolyExp.  32x32 output tile per 256-thread CTA; level image tile with an
+// Stage a4: FarnebackPolyExp for poly_n > 8 (the marching kernel of fb_polyexp.cuh serves 1..8).  32x32 output tile per 256-thread CTA; level image tile with an
 // n-pixel replicate halo staged in shared memory; vertical pass -> 3 moment planes in shared
 // memory; horizontal pass -> 5 coefficients, written as float4 + float.
 // =====================================================================================
@@ -343,7 +354,7 @@ __global__ void __launch_bounds__(256) k_upsample_flow(const float2* __restrict_
   const float2* p = prev + (size_t)blockIdx.z * pw * ph;
   const LinTab tx = tabx[x];
   const int x0 = tx.i0, x1 = min(x0 + 1, pw - 1);
-  const float fx = tx.f, ax0 = 1.f - fx;
+  const float fx = tx.f;
   float2 q00[UPS_ROWS], q01[UPS_ROWS], q10[UPS_ROWS], q11[UPS_ROWS];
   float fy[UPS_ROWS];
 #pragma unroll
@@ -359,12 +370,8 @@ __global__ void __launch_bounds__(256) k_upsample_flow(const float2* __restrict_
   }
   float2* o = out + (size_t)blockIdx.z * w * h + (size_t)yb * w + x;
 #pragma unroll
-  for (int j = 0; j < UPS_ROWS; j++) {
-    const float ay0 = 1.f - fy[j];
-    const float tx2 = q00[j].x * ax0 + q01[j].x * fx, ty2 = q00[j].y * ax0 + q01[j].y * fx;
-    const float bx = q10[j].x * ax0 + q11[j].x * fx, by = q10[j].y * ax0 + q11[j].y * fx;
-    if (yb + j < h) o[(size_t)j * w] = make_float2((tx2 * ay0 + bx * fy[j]) * mul, (ty2 * ay0 + by * fy[j]) * mul);
-  }
+  for (int j = 0; j < UPS_ROWS; j++)
+    if (yb + j < h) o[(size_t)j * w] = ups_blend(q00[j], q01[j], q10[j], q11[j], fx, fy[j], mul);
 }
 
 // cv::resize INTER_LINEAR source coordinate of destination index d (host twin of linear_coord).
@@ -462,11 +469,11 @@ int farneback_levels(int width, int height, const ofb_farneback_params* p, Level
 }
 
 bool farneback_stream_supported(const ofb_handle* h, const ofb_farneback_params* p) {
+  (void)h;
   BlurCoef bc;
   prepare_blur(p->winsize, (p->flags & OFB_OPTFLOW_FARNEBACK_GAUSSIAN) != 0, &bc);
-  const bool use_fused = !bc.gaussian && bc.m >= 2 && bc.m <= 19 && !h->force_generic;
-  return use_fused && h->iter_ws != 1 && p->poly_n <= PX_MAXN && !h->polyexp_tile &&
-         !(p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW);
+  const bool use_fused = !bc.gaussian && bc.m >= 2 && bc.m <= 19;
+  return use_fused && p->poly_n <= PX_MAXN && !(p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW);
 }
 
 static inline dim3 grid2d(int w, int h, int z, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y, z); }
@@ -482,6 +489,7 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
 struct GraphKey {
   int n_pairs, sequence, width, height, cur, prime_only;
   const void *d_prev, *d_next, *d_flow_out, *d_init_flow;
+  const void* sc_pool;   // base of the stream cache the launches were captured with (reallocated when it grows)
   size_t pitch, image_stride;
   ofb_farneback_params p;
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
@@ -512,7 +520,7 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
     int s__ = ensure_lintabs(h, sched, n_levels, width, height, p->pyr_scale);
     if (s__) return s__;
   }
-  if (h->no_graph || h->timing || n_pairs > kGraphMaxPairs)
+  if (h->no_graph || h->timing || n_pairs > kGraphMaxPairs || h->graph_bypass)
     return farneback_run_impl(h, n_pairs, sequence, d_prev, d_next, width, height, pitch, image_stride, d_flow_out,
                               d_init_flow, p, sc);
   if (!h->graph_cache) h->graph_cache = new std::vector<GraphEntry>();
@@ -521,6 +529,7 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
   memset(&key, 0, sizeof(key));
   key.n_pairs = n_pairs; key.sequence = sequence; key.width = width; key.height = height;
   key.cur = sc ? sc->cur : -1; key.prime_only = sc ? (int)sc->prime_only : 0;
+  key.sc_pool = sc ? (const void*)sc->RA[0][0] : nullptr;
   key.d_prev = d_prev; key.d_next = d_next; key.d_flow_out = d_flow_out; key.d_init_flow = d_init_flow;
   key.pitch = pitch; key.image_stride = image_stride;
   key.p.pyr_scale = p->pyr_scale; key.p.levels = p->levels; key.p.winsize = p->winsize; key.p.iterations = p->iterations;
@@ -588,16 +597,10 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
   src.image_stride = image_stride;
   cudaStream_t st = h->stream;
   const dim3 blk(32, 8);
-  // fused box-window iteration kernel: radius 2..19 (shared-memory ring of 2m+1 rows); the generic
+  // fused box-window iteration kernel: radius 2..19 (ring of 2m+1 rows in tensor memory or shared memory); the generic
   // three-kernel path covers the Gaussian window and every other radius.
-  const bool use_fused = !bc.gaussian && bc.m >= 2 && bc.m <= 19 && !h->force_generic;
-  if (use_fused && h->iter_ws == 1) {
-    const int ws_smem = (2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * (int)sizeof(float);
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
-    OFB_CUDA(h, cudaFuncSetAttribute(k_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
-  }
-
-  if (sc && (!use_fused || h->iter_ws == 1 || pc.n > PX_MAXN || h->polyexp_tile || n_levels > kMaxLevels))
+  const bool use_fused = !bc.gaussian && bc.m >= 2 && bc.m <= 19;
+  if (sc && (!use_fused || pc.n > PX_MAXN || n_levels > kMaxLevels))
     return set_error(h, OFB_ERR_INVALID_ARG, "internal: stream cache used with an unsupported configuration");
   float2* prev_flow = nullptr;
   int prev_w = 0, prev_h = 0;
@@ -617,10 +620,12 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
     float2* alt = cur == h->d_flow[0] ? h->d_flow[1] : h->d_flow[0];
 #define TB(stage) do { int s__ = timing_begin(h, stage); if (s__) return s__; } while (0)
 #define TE() do { int s__ = timing_end(h); if (s__) return s__; } while (0)
-    // --- initial flow of the level
+    // --- initial flow of the level.  With the fused iteration kernel the x2 upsample of the coarser level's result is
+    // computed by the first iteration's producers (UpsSrc): no launch, no write + read of the upsampled field.
+    const bool fuse_ups = OFB_EXP_FUSE_UPS && use_fused && prev_flow != nullptr && p->iterations > 0;
     TB(OFB_STAGE_FLOW_INIT);
-    if (prime_only) {
-      // first frame of the streams: expansions only
+    if (prime_only || fuse_ups) {
+      // first frame of the streams: expansions only / upsample fused into the first iteration
     } else if (prev_flow == nullptr) {
       if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
         k_init_flow_area<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>((const float2*)d_init_flow, width, height, cur, w,
@@ -643,11 +648,11 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
       return set_error(h, OFB_ERR_INVALID_ARG, "pyramid smoothing kernel too large (ksize=%d)", lv.ksize);
     // Marching PolyExp kernel (poly_n <= 8).  When the level has the source size (k = 0: 3-tap blur,
     // identity resize) the pyramid stage is fused into it and the level image never exists in HBM.
-    const bool march = pc.n <= PX_MAXN && !h->polyexp_tile;
-    const bool fused_src = march && w == width && hh == height && pyc.r == 1 && !h->no_fused_src;
+    const bool march = pc.n <= PX_MAXN;
+    const bool fused_src = march && w == width && hh == height && pyc.r == 1;
     // regular power-of-two level (fb_pyramid.cuh, k_pyr_fast): one kernel, source read once
     int fastS = 0;
-    if (!fused_src && !h->no_pyr_fast && (width & 3) == 0 && (pitch & 3) == 0 && (image_stride & 3) == 0 &&
+    if (!fused_src && (width & 3) == 0 && (pitch & 3) == 0 && (image_stride & 3) == 0 &&
         (reinterpret_cast<uintptr_t>(src.a) & 3) == 0 && (reinterpret_cast<uintptr_t>(src.b) & 3) == 0) {
       for (int S = 2; S <= 8; S *= 2)
         if (w * S == width && hh * S == height && pyc.r == (S == 2 ? 1 : (S == 4 ? 4 : 9))) fastS = S;
@@ -695,7 +700,7 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
     if (march) {
       const int strips = (w + PX_TW - 1) / PX_TW;
       const int per = strips * frames;
-      const int slots = 3 * h->num_sms * h->px_waves;
+      const int slots = 3 * h->num_sms * kPxWaves;
       int segs = std::max(1, slots / per);
       int seg_rows = std::max(16, ((hh + segs - 1) / segs + PX_ROWS - 1) / PX_ROWS * PX_ROWS);
       segs = (hh + seg_rows - 1) / seg_rows;
@@ -721,80 +726,37 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
     }
     TE();
     // --- iterations
-    float2* fin = cur;
+    // (fused upsample: the first iteration reads the coarser level's buffer — which `alt` aliases — and must not
+    // write it, so it writes `cur`)
+    float2* fin = fuse_ups ? alt : cur;
     for (int it = 0; it < (prime_only ? 0 : p->iterations); it++) {
       const bool last_it = it == p->iterations - 1;
       float2* fout = (last_level && last_it) ? (float2*)d_flow_out : (fin == cur ? alt : cur);
       TB(OFB_STAGE_ITERATION);
       if (use_fused) {
-        if (h->iter_ws != 1) {
-          // k_iter_v: float van Herk / Gil-Werman vertical sums, no FP64 (default)
-          const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
-          cudaError_t e;
-#define OFB_V_ARGS h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st
-          const int pfd = h->iter_prefetch ? h->iter_pfd : 0;
-          // The setmaxnreg schedules move registers between the warpgroups of a CTA: 2 x 128 producers x 96 + 128
-          // consumers x 48 = 384 x 80.  They are only safe if the kernels really launch with 80 registers per thread
-          // (a smaller pool would leave the producers waiting for registers for ever); checked once, else mode 0.
-          static int regs_state = 0;   // 0 unknown, 1 ok, -1 not ok
-          if (regs_state == 0) {
-            cudaFuncAttributes a3, a2, a1;
-            const bool q = cudaFuncGetAttributes(&a3, k_iter_v<7, 256, 2, 2, 0, 4, 2, 1, false, true>) == cudaSuccess &&
-                           cudaFuncGetAttributes(&a2, k_iter_v<7, 256, 2, 2, 0, 4, 2, 1>) == cudaSuccess &&
-                           cudaFuncGetAttributes(&a1, k_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>) == cudaSuccess;
-            cudaFuncAttributes a0;
-            const bool q0 = cudaFuncGetAttributes(&a0, k_iter_v<0, 256, 2, 2, 0, 4, 2, 1, false, true>) == cudaSuccess;
-            regs_state = (q && q0 && a3.numRegs >= 80 && a2.numRegs >= 80 && a1.numRegs >= 80 && a0.numRegs >= 80) ? 1 : -1;
-          }
-          const bool regs_ok = regs_state == 1;
-          if (bc.m == 7) {
-            if (h->iter_cols == 128) {
-              if (pfd == 0) e = launch_iter_v<7, 128, 2, 4, 0, 4>(OFB_V_ARGS);
-              else e = launch_iter_v<7, 128, 2, 4, 3, 4>(OFB_V_ARGS);
-            } else {
-              if (pfd == 0) e = launch_iter_v<7, 256, 2, 2, 0, 4>(OFB_V_ARGS);
-              else if (pfd == 2) e = launch_iter_v<7, 256, 2, 2, 2, 4>(OFB_V_ARGS);
-              else if (h->iter_mode == 3 && regs_ok) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1, false, true>(OFB_V_ARGS);   // default
-              else if (h->iter_mode == 2 && regs_ok) e = launch_iter_v<7, 256, 2, 2, 0, 4, 2, 1>(OFB_V_ARGS);
-              else if (h->iter_mode == 1 && regs_ok) e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, false, true>(OFB_V_ARGS);
-              else e = launch_iter_v<7, 256, 2, 2, 3, 4>(OFB_V_ARGS);
-            }
-          } else if (h->iter_mode >= 2) {
-            // other window sizes: the default schedule with the radius as a template argument where an instantiation
-            // exists (winsize 5..31), else with the radius at run time (its generic consumer loop is slow:
-            // winsize 13 measured 6.4 ms per 18 pairs against 3.0 ms with the templated kernel)
-            bool served = false;
-            e = bc.m <= 8 ? launch_iter_fixed_a(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, &served)
-                          : launch_iter_fixed_b(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, &served);
-            if (!served) {
-              if (bc.m <= 8 && regs_ok) e = launch_iter_v<0, 256, 2, 2, 0, 4, 2, 1, false, true>(OFB_V_ARGS);
-              else e = launch_iter_v<0, 128, 2, 3, 0, 4, 2, 1, false, true>(OFB_V_ARGS);
-            }
-          } else {
-            e = launch_iter_v<0, 128, 4, 1, 0, 4>(OFB_V_ARGS);
-          }
-#undef OFB_V_ARGS
-          if (e != cudaSuccess)
-            return set_error(h, OFB_ERR_CUDA, "k_iter_v launch failed: %s", cudaGetErrorString(e));
-        } else {
-          // k_iter_ws: cv2's double vertical running sums (OFB_ITER_WS=1; slower — XU-bound — kept as the
-          // precision reference for the float path)
-          const int tw = WS_COLS - 2 * bc.m;
-          const int strips = (w + tw - 1) / tw;
-          const int slots = 2 * h->num_sms * h->iter_waves;   // resident CTAs (x waves)
-          const int per = strips * n_pairs;
-          int segs = per >= slots ? 1 : slots / per;
-          int seg_rows = std::max(16, (hh + segs - 1) / segs);
-          segs = (hh + seg_rows - 1) / seg_rows;
-          const size_t smem = (size_t)(2 * WS_CH + 2 * bc.m + 1) * 5 * WS_COLS * sizeof(float);
-          dim3 g(strips * segs, n_pairs);
-          if (bc.m == 7)
-            k_iter_ws<7><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
-                                                      seg_rows, strips);
-          else
-            k_iter_ws<0><<<g, WS_THREADS, smem, st>>>(h->d_RA, h->d_RB, fin, fout, w, hh, f1_offset, bc.m, bc.scale,
-                                                      seg_rows, strips);
+        // k_iter_v: float van Herk / Gil-Werman vertical sums, no FP64
+        const float reg = (float)(1e-3 / ((double)bc.scale * (double)bc.scale));
+        UpsSrc ups;
+        const UpsSrc* up = nullptr;
+        if (fuse_ups && it == 0) {
+          ups.prev = prev_flow; ups.pw = prev_w; ups.ph = prev_h;
+          ups.tabx = h->d_lintab + h->tab_x_off[li]; ups.taby = h->d_lintab + h->tab_y_off[li];
+          ups.mul = (float)(1.0 / p->pyr_scale);
+          up = &ups;
         }
+        cudaError_t e;
+        if (bc.m == 7) {
+          e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, up);
+        } else {
+          // other window sizes: the radius as a template argument where an instantiation exists (winsize 5..31), else
+          // at run time (its generic consumer loop is slow: winsize 13 measured 6.4 ms per 18 pairs against 3.0 ms)
+          bool served = false;
+          e = bc.m <= 8 ? launch_iter_fixed_a(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, up, &served)
+                        : launch_iter_fixed_b(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, up, &served);
+          if (!served) e = launch_iter_v<0, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, up);
+        }
+        if (e != cudaSuccess)
+          return set_error(h, OFB_ERR_CUDA, "k_iter_v launch failed: %s", cudaGetErrorString(e));
         OFB_LAUNCH_CHECK(h);
       } else {
         k_update_matrices<<<grid2d(w, hh, n_pairs, blk), blk, 0, st>>>(h->d_RA, h->d_RB, fin, h->d_MA, h->d_MB, w, hh,

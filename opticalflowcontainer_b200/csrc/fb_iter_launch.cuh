@@ -8,47 +8,48 @@
 
 namespace ofb {
 
-// k_iter_v launcher.
-template <int MT, int COLS, int CH, int MINB, int PFD, int PXT, int RIF = 1, int CLOOP = 1, bool TILED = false,
-          bool REUSE = false>
+// k_iter_v launcher.  ups != nullptr: the launch is the first iteration of a level and upsamples its input flow from
+// the coarser level on the fly (fin is not read).
+template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF>
 static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                 const RSet& rs, int m, float reg, cudaStream_t st, int y_begin = 0, int y_end = -1,
-                                 const PeerTab* tab = nullptr, int my_rank = 0) {
+                                 const RSet& rs, int m, float reg, cudaStream_t st, const UpsSrc* ups = nullptr,
+                                 int y_begin = 0, int y_end = -1, const PeerTab* tab = nullptr, int my_rank = 0) {
   if (y_end < 0) y_end = hh;
   if (y_end <= y_begin) return cudaSuccess;
   PeerTab t;
   if (tab) t = *tab; else memset(&t, 0, sizeof(t));
-  const int smem = iter_v_smem_floats<COLS, CH>(m) * (int)sizeof(float);
+  UpsSrc u;
+  if (ups) u = *ups; else memset(&u, 0, sizeof(u));
+  auto kern = k_iter_v<MT, COLS, CH, MINB, PFD, TILED, REUSE, TMEM, NBUF>;
+  const int smem = iter_v_smem_floats<COLS, CH>(m, TMEM, NBUF) * (int)sizeof(float);
   // largest dynamic smem configured for this instantiation, per device (function attributes are per device)
   static int configured[64] = {0};
   const int dev = h->device & 63;
   if (smem > configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED, REUSE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
+    if (REUSE && COLS == 256 && MINB == 2) {
+      // The setmaxnreg schedule moves registers between the warpgroups of a CTA: 2 x 128 producers x 96 + 128 consumers
+      // x 48 = 384 x 80.  It only works if the kernel really launches with 80 registers per thread (a smaller pool
+      // would leave the producers waiting for registers for ever): checked once per instantiation.
+      cudaFuncAttributes a;
+      e = cudaFuncGetAttributes(&a, kern);
+      if (e != cudaSuccess) return e;
+      if (a.numRegs < 80) return cudaErrorLaunchOutOfResources;
+    }
     configured[dev] = smem;
   }
   const int tw = COLS - 2 * m;
   const int strips = (w + tw - 1) / tw;
-  const int slots = MINB * h->num_sms * h->iter_waves;
+  const int slots = MINB * h->num_sms;
   const int per = strips * n_pairs;
   const int rows = y_end - y_begin;
   int segs = per >= slots ? 1 : slots / per;
   int seg_rows = std::max(16, (rows + segs - 1) / segs);
   segs = (rows + seg_rows - 1) / seg_rows;
   dim3 g(strips * segs, n_pairs);
-  k_iter_v<MT, COLS, CH, MINB, PFD, PXT, RIF, CLOOP, TILED, REUSE><<<g, COLS + (CH / CLOOP) * COLS / PXT, smem, st>>>(
-      rs, fin, fout, w, hh, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank);
+  kern<<<g, COLS + CH * COLS / 4, smem, st>>>(rs, fin, fout, w, hh, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank, u);
   return cudaGetLastError();
-}
-
-
-// A setmaxnreg schedule (MINB == 2 instantiations) is only safe if the kernel really launches with 80 registers per
-// thread: 2 x 128 producers x 96 + 128 consumers x 48 = 384 x 80.
-template <typename K>
-static bool iter_regs_ok(K kernel) {
-  cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, kernel) == cudaSuccess && a.numRegs >= 80;
 }
 
 }  // namespace ofb

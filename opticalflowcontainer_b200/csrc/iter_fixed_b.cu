@@ -1,21 +1,21 @@
-// iter_fixed_b.cu — k_iter_v with the window radius as a template argument, default schedule (two rows of loads in flight, row-reuse
-// gather), for window sizes other than the default 15 (see fb_iter_launch.cuh, farneback.cu).
+// iter_fixed_b.cu — k_iter_v with the window radius as a template argument (128-column strips, 3 CTAs/SM, ring in
+// shared memory) for the window sizes 19..31 (see fb_iter_launch.cuh, farneback.cu).
 #include "common.cuh"
 #include "fb_iter_launch.cuh"
 
 namespace ofb {
 
-cudaError_t launch_iter_fixed_b(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs, const RSet& rs,
-                      float reg, cudaStream_t st, bool* served) {
+cudaError_t launch_iter_fixed_b(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
+                                const RSet& rs, float reg, cudaStream_t st, const UpsSrc* ups, bool* served) {
   *served = true;
   switch (m) {
-    case 9: return launch_iter_v<9, 128, 2, 3, 0, 4, 2, 1, false, true>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st);
-    case 10: return launch_iter_v<10, 128, 2, 3, 0, 4, 2, 1, false, true>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st);
-    case 12: return launch_iter_v<12, 128, 2, 3, 0, 4, 2, 1, false, true>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st);
-    case 15: return launch_iter_v<15, 128, 2, 3, 0, 4, 2, 1, false, true>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st);
-    case 11: return launch_iter_v<11, 128, 2, 3, 0, 4, 2, 1, false, true>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st);
-    case 13: return launch_iter_v<13, 128, 2, 3, 0, 4, 2, 1, false, true>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st);
-    case 14: return launch_iter_v<14, 128, 2, 3, 0, 4, 2, 1, false, true>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st);
+    case 9: return launch_iter_v<9, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
+    case 10: return launch_iter_v<10, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
+    case 11: return launch_iter_v<11, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
+    case 12: return launch_iter_v<12, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
+    case 13: return launch_iter_v<13, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
+    case 14: return launch_iter_v<14, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
+    case 15: return launch_iter_v<15, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
     default: break;
   }
   *served = false;

@@ -91,8 +91,9 @@ static int sparse_get(ofb_handle* h, SparseState** out) {
   SP_CUDA(h, cudaMalloc(&s->counters, 16 * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->grid_cnt, N * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->grid_pts, N * kGridSlots * sizeof(ushort2)));
-  SP_CUDA(h, cudaMalloc(&s->corners, N * sizeof(float2) / 4 + 1024));
-  s->h_stage_bytes = std::max<size_t>(2 * N, (N / 4 + 128) * sizeof(float2));
+  // the selection can keep every candidate (minDistance < 1, maxCorners <= 0): corner buffers sized like the candidate list
+  SP_CUDA(h, cudaMalloc(&s->corners, s->cand_cap * sizeof(float2)));
+  s->h_stage_bytes = std::max<size_t>(2 * N, s->cand_cap * sizeof(float2));
   SP_CUDA(h, cudaHostAlloc(&s->h_stage, s->h_stage_bytes, cudaHostAllocDefault));
   *out = s;
   return OFB_OK;
@@ -665,6 +666,10 @@ int ofb_good_features(ofb_handle* h, const uint8_t* image, int width, int height
   if (p->block_size < 1 || p->block_size % 2 == 0 || p->block_size > 31)
     return set_error(h, OFB_ERR_INVALID_ARG, "blockSize must be odd and in [1,31]");
   if (width > 65535 || height > 65535) return set_error(h, OFB_ERR_INVALID_ARG, "image larger than 65535 px");
+  if (width < 3 || height < 3) {     // no interior pixel: cv2 returns an empty list
+    *n_out = 0;
+    return OFB_OK;
+  }
   OFB_CUDA(h, cudaSetDevice(h->device));
   SparseState* s;
   int st = sparse_get(h, &s);

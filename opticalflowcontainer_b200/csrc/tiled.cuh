@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) k_upsample_flow_tiled(PeerTab prev, int p
   if (x >= w || yb >= y_end) return;
   const LinTab tx = tabx[x];
   const int x0 = tx.i0, x1 = min(x0 + 1, pw - 1);
-  const float fx = tx.f, ax0 = 1.f - fx;
+  const float fx = tx.f;
 #pragma unroll
   for (int j = 0; j < UPS_ROWS; j++) {
     const int y = yb + j;
@@ -89,10 +89,7 @@ __global__ void __launch_bounds__(256) k_upsample_flow_tiled(PeerTab prev, int p
     const float2* r0 = prev.flow[tile_owner(r0i, prev)] + (size_t)r0i * pw;
     const float2* r1 = prev.flow[tile_owner(r1i, prev)] + (size_t)r1i * pw;
     const float2 q00 = __ldg(r0 + x0), q01 = __ldg(r0 + x1), q10 = __ldg(r1 + x0), q11 = __ldg(r1 + x1);
-    const float fy = ty.f, ay0 = 1.f - fy;
-    const float tx2 = q00.x * ax0 + q01.x * fx, ty2 = q00.y * ax0 + q01.y * fx;
-    const float bx = q10.x * ax0 + q11.x * fx, by = q10.y * ax0 + q11.y * fx;
-    out[(size_t)y * w + x] = make_float2((tx2 * ay0 + bx * fy) * mul, (ty2 * ay0 + by * fy) * mul);
+    out[(size_t)y * w + x] = ups_blend(q00, q01, q10, q11, fx, ty.f, mul);
   }
 }
 
@@ -196,7 +193,7 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
     {
       const int strips = (w + PX_TW - 1) / PX_TW;
       const int per = strips * frames;
-      const int slots = 3 * h->num_sms * h->px_waves;
+      const int slots = 3 * h->num_sms * kPxWaves;
       int segs = std::max(1, slots / per);
       int seg_rows = std::max(16, ((ye - yb + segs - 1) / segs + PX_ROWS - 1) / PX_ROWS * PX_ROWS);
       segs = (ye - yb + seg_rows - 1) / seg_rows;
@@ -265,9 +262,9 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
   const RSet rs1 = {h->d_RA, h->d_RB, h->d_RA + (size_t)w * hh, h->d_RB + (size_t)w * hh};
   TB(OFB_STAGE_ITERATION);
   if (pl.bc.m == 7)
-    e = launch_iter_v<7, 256, 2, 2, 3, 4, 1, 1, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, yb, ye, &t, rank);
+    e = launch_iter_v<7, 256, 2, 2, 3, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
   else
-    e = launch_iter_v<0, 128, 4, 1, 0, 4, 1, 1, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, yb, ye, &t, rank);
+    e = launch_iter_v<0, 128, 4, 1, 0, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
   if (e != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "tiled k_iter_v launch failed: %s", cudaGetErrorString(e));
   h->launches++;
   TE();
@@ -304,10 +301,12 @@ static int tiled_barrier(ofb_handle* h) {
   PeerFlags pf;
   for (int r = 0; r < kMaxTileRanks; r++) pf.p[r] = r < h->tile.world ? h->tile.peer_flags[r] : nullptr;
   h->tile.epoch++;
-  // ~2 s at 1.9 GHz: a rank that died must not hang the others (and the GPU) forever
+  // ~2 s at 1.9 GHz: a rank that died must not hang the others (and the GPU) forever.  The first barriers of a handle
+  // get ~30 s: the peers may still be loading modules / setting function attributes.  A timeout sets d_err, which
+  // ofb_synchronize / ofb_tiled_status report as an error.
   TB(OFB_STAGE_OTHER);
   k_tile_barrier<<<1, 32, 0, h->stream>>>(h->tile.d_flags, pf, h->tile.rank, h->tile.world, h->tile.epoch,
-                                          h->tile.d_err, 4000000000LL);
+                                          h->tile.d_err, h->tile.epoch <= 2 ? 60000000000LL : 4000000000LL);
   OFB_LAUNCH_CHECK(h);
   TE();
   return OFB_OK;

@@ -209,30 +209,64 @@ def test_async_batch_pipelines_across_calls(built_lib):
         eng.close()
 
 
-def test_iteration_schedules_bit_identical(built_lib):
-    """The four producer load schedules of k_iter_v (OFB_ITER_MODE 0..3: prefetch / row-reuse gather / two rows in
-    flight) are different instruction orders of the same arithmetic: the fields must agree bit for bit, also across a
-    flow discontinuity (where the row reuse has to fall back to the full gather) and on an odd size."""
-    import os
+def test_flow_discontinuity_and_odd_size_match_cv2(engine_factory):
+    """A torn frame (large |flow| differences between neighbouring rows: the row-reuse gather of k_iter_v has to fall
+    back to the full 2x2 gather, and the fused inter-level upsample crosses the tear) on an even and an odd size (general
+    resize tables in the fused upsample): contract gate against cv2 (the tear itself is ill-conditioned)."""
+    for (h, w, shift) in [(270, 480, (1.7, -0.9)), (213, 317, (-6.3, 4.2))]:
+        a, b = synth.synth_pair(h, w, 5, shift)
+        b = np.ascontiguousarray(np.roll(b, 5, axis=0))
+        eng = engine_factory(w, h)
+        _check(C.farneback(a, b), eng.farneback(a, b), MEAN_GATE, MAX_GATE)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_corpus_c1_seeds_0_to_7(engine_factory, seed):
+    """SURVEY 8d corpus C1: seeds 0..7 of the VGA translation corpus, shifts spread over +-12 px."""
+    shift = (((seed * 37) % 25) - 12 + 0.3, ((seed * 53) % 17) - 8 - 0.4)
+    a, b = synth.synth_pair(480, 640, seed, shift)
+    eng = engine_factory(640, 480)
+    _check(C.farneback(a, b), eng.farneback(a, b))
+
+
+def test_full_size_4k_matches_cv2(engine_factory):
+    """BASELINE config[2] size (3840x2160): one pair against cv2 (about 3 s of cv2)."""
+    a, b = synth.synth_pair(2160, 3840, 3, (7.3, -4.6))
+    eng = engine_factory(3840, 2160)
+    _check(C.farneback(a, b), eng.farneback(a, b))
+
+
+def test_full_size_8k_matches_cv2(engine_factory):
+    """BASELINE config[4] size (7680x4320), whole frame on one GPU: one pair against cv2 (about 13 s of cv2).  The
+    multi-GPU tiled run of the same size is checked against cv2 by tests/test_tiled_gpu.py and by bench.py."""
+    a, b = synth.synth_pair(4320, 7680, 4, (-9.4, 5.2))
+    eng = engine_factory(7680, 4320)
+    _check(C.farneback(a, b), eng.farneback(a, b))
+
+
+def test_stream_cache_grow_then_shrink(built_lib):
+    """n_streams 1 -> 2 -> 1 with identical frames, sizes and staging pointers: the stream cache is reallocated when it
+    grows, so the CUDA graphs captured for the first configuration must not be replayed on the freed pool (the pool
+    base is part of the graph key)."""
     import opticalflowcontainer_b200 as ofb
-    old = os.environ.get("OFB_ITER_MODE")
+    h, w = 135, 240
+    eng = ofb.FlowEngine(w, h, 2, 0)
+    ref = ofb.FlowEngine(w, h, 2, 0)
     try:
-        for (h, w, shift) in [(270, 480, (1.7, -0.9)), (213, 317, (-6.3, 4.2))]:
-            a, b = synth.synth_pair(h, w, 5, shift)
-            b = np.ascontiguousarray(np.roll(b, 5, axis=0))       # tear: large |flow| differences between rows
-            fields = []
-            for mode in ("0", "1", "2", "3"):
-                os.environ["OFB_ITER_MODE"] = mode
-                eng = ofb.FlowEngine(w, h, 1, 0)
-                fields.append(eng.farneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0).copy())
-                eng.close()
-            for f in fields[1:]:
-                assert np.array_equal(fields[0], f)
+        base = synth.synth_pair(h, w, 77, (0.0, 0.0))[0]
+        fr = [synth.subpixel_shift(base, 1.1 * t, -0.6 * t) for t in range(8)]
+        kw = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+        t = 0
+        for n in (1, 2, 1, 2, 1):
+            assert eng.farneback_stream(np.stack([fr[t % 8]] * n), **kw) is None      # n changed: priming call
+            for _ in range(4):                                                        # every graph key comes round twice
+                out = eng.farneback_stream(np.stack([fr[(t + 1) % 8]] * n), **kw)
+                want = ref.farneback_batch([fr[t % 8]] * n, [fr[(t + 1) % 8]] * n, **kw)
+                assert out is not None and np.array_equal(out, want), (n, t)
+                t += 1
     finally:
-        if old is None:
-            os.environ.pop("OFB_ITER_MODE", None)
-        else:
-            os.environ["OFB_ITER_MODE"] = old
+        eng.close()
+        ref.close()
 
 
 @pytest.mark.parametrize("flags,winsize", [(0, 15), (0, 9), (256, 15)])
