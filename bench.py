@@ -55,6 +55,11 @@ def algorithmic_bytes_per_pair(w, h, iters=3):
     return len(nl) * 2 * w * h + (40 + 56 * iters) * sum(nl)
 
 
+def bench_config():
+    """The workload both arms run (same dict in the `ours` and the `reference` line)."""
+    return {"workload": "farneback_%dx%d_independent_frame_pairs" % (W_, H_), "params": PARAMS}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -140,8 +145,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "farneback_1920x1080_single_stream", "params": PARAMS,
-                   "pairs_per_step": workers * pairs_per_worker},
+        "config": bench_config(),
+        "run": {"pairs_per_step": workers * pairs_per_worker},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference",
                          "sample": "%d worker processes x %d pairs x %d steps of cv2 %s calcOpticalFlowFarneback "
                                    "(cv2.setNumThreads(1) per worker; the algorithm is single-threaded)"
@@ -153,13 +158,127 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ sparse path (config 4)
-def run_lk(args, rank, local_rank, world):
-    """BASELINE.json config 4: Shi-Tomasi (2000 corners) + pyramidal LK on 1080p camera streams, 8 streams
-    sharded over the ranks.  A step = one frame of every stream of this rank through the host-buffer API
-    (upload, corners, track, download).  Extra line, not the headline metric."""
+def _lk_cpu_worker(args):
+    """One camera stream on one host core: goodFeaturesToTrack + calcOpticalFlowPyrLK per frame."""
+    seed, reps = args
+    import cv2
+    from oracle import synth
+    cv2.setNumThreads(1)
+    a, b = synth.synth_pair(H_LK, W_LK, seed, (3.3, -2.1))
+    crit = (cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01)
+
+    def frame():
+        p = cv2.goodFeaturesToTrack(a, 2000, 0.01, 7, blockSize=3)
+        cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=3, criteria=crit)
+
+    frame()                                   # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        frame()
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+W_LK, H_LK = 1920, 1080
+
+
+def lk_cpu_baseline(reps=5):
+    """cv2 on the host cores, 8 independent streams process-parallel (one stream per worker), >= 5 timed repetitions
+    after a warm-up; aggregate frames/s from the slowest worker's median / best frame time."""
+    import multiprocessing as mp
+    import cv2
+    workers = min(8, os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        per = pool.map(_lk_cpu_worker, [(300 + i, reps) for i in range(workers)])
+    med = max(float(np.median(t)) for t in per)
+    best = max(float(np.min(t)) for t in per)
+    return {"value": workers / med, "unit": "frames/s", "cores": workers, "kind": "reference",
+            "best_frames_per_s": workers / best, "ms_per_frame_one_core_median": med * 1e3,
+            "sample": "cv2 %s goodFeaturesToTrack(2000, 0.01, 7, blockSize 3) + calcOpticalFlowPyrLK(21x21, maxLevel 3, "
+                      "(30, 0.01)), %d streams process-parallel (cv2.setNumThreads(1) each), %d timed frames per stream "
+                      "after 1 warm-up; value from the median frame time of the slowest worker" % (cv2.__version__, workers, reps)}
+
+
+def lk_record(args, rank, local_rank, world, steps, warmup, cpu=True):
+    """BASELINE.json config 4: Shi-Tomasi (2000 corners) + pyramidal LK on 1080p camera streams, 8 streams sharded over
+    the ranks.  A step = one new frame of every stream of this rank through the camera-stream call of the sparse path
+    (ofb_lk_stream: one upload per frame, the previous frame's pyramid and the corner list stay on the GPU).
+    Returns the record on rank 0 (None elsewhere).  The process group, if any, is already up."""
     import torch
     import torch.distributed as dist
+    import opticalflowcontainer_b200 as ofb
+    from opticalflowcontainer_b200 import sharding
+    from oracle import synth
+    from concurrent.futures import ThreadPoolExecutor
 
+    streams = sharding.shard_indices(8, rank, world)
+    base = [synth.synth_pair(H_LK, W_LK, 300 + s, (0.0, 0.0))[0] for s in streams]
+    seqs = [[synth.subpixel_shift(base[i], (1.3 + 0.2 * s) * t, (-0.9 + 0.1 * s) * t) for t in range(4)]
+            for i, s in enumerate(streams)]
+    # one handle (= one CUDA stream) and one host thread per camera stream, as a multi-camera node would run them:
+    # handles are independent and ctypes releases the GIL during a call, so the latency-bound kernels of different
+    # cameras overlap on the GPU
+    engines = [ofb.FlowEngine(W_LK, H_LK, 1, local_rank) for _ in streams]
+    pool = ThreadPoolExecutor(max_workers=max(1, len(streams)))
+    order = [0, 1, 2, 3, 2, 1]
+
+    def one(arg):
+        i, t = arg
+        r = engines[i].lk_stream(seqs[i][order[t % len(order)]], 2000, 0.01, 7, 3, (21, 21), 3, (3, 30, 0.01))
+        return 0 if r is None else int(r[2].sum())
+
+    def step(t):
+        return sum(pool.map(one, [(i, t) for i in range(len(streams))]))
+
+    tracked = 0
+    for t in range(max(warmup, 2)):
+        tracked = step(t)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t in range(steps):
+        step(max(warmup, 2) + t)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    frames = torch.tensor([len(streams) * steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(frames, op=dist.ReduceOp.SUM)
+    launches = int(sum(e.launch_count for e in engines))
+    # single camera, one frame per call, host to host
+    lat_ms = None
+    if streams:
+        e = engines[0]
+        t0 = time.perf_counter()
+        for t in range(20):
+            e.lk_stream(seqs[0][order[t % len(order)]], 2000, 0.01, 7, 3, (21, 21), 3, (3, 30, 0.01))
+        lat_ms = (time.perf_counter() - t0) / 20 * 1e3
+    pool.shutdown()
+    for e in engines:
+        e.close()
+    if rank != 0:
+        return None
+    value = float(frames.item()) / float(tt.item())
+    rec = {"metric": "shi_tomasi_pyrlk_1080p_2000pt_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
+           "steps": steps, "ms_per_step": float(tt.item()) / steps * 1e3, "scaling": "strong (8 streams over the ranks)",
+           "workload": "goodFeaturesToTrack(2000, 0.01, 7) + calcOpticalFlowPyrLK(21x21, maxLevel 3, (30, 0.01)) on 1920x1080, "
+                       "8 camera streams sharded over %d GPU(s)" % world,
+           "api": "ofb_lk_stream: one frame up per call (pinned staging), corners of the previous frame tracked into the new "
+                  "one, new corners detected for the next call; points, status and error back; one handle and host thread "
+                  "per stream",
+           "tracked_points_last_step_rank0": tracked, "single_camera_ms_per_frame_host_to_host": lat_ms,
+           "gpu_launches": launches}
+    if cpu:
+        rec["cpu_baseline"] = lk_cpu_baseline()
+    return rec
+
+
+def run_lk(args, rank, local_rank, world):
+    """--mode lk: the sparse-path record alone, as one JSON line."""
+    import torch
+    import torch.distributed as dist
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
@@ -170,109 +289,36 @@ def run_lk(args, rank, local_rank, world):
         ofb_build.build()
     if world > 1:
         dist.barrier()
-    import opticalflowcontainer_b200 as ofb
-    from opticalflowcontainer_b200 import sharding
-    from oracle import synth
-
-    streams = sharding.shard_indices(8, rank, world)
-    pairs = [synth.synth_pair(H_, W_, 300 + s, (3.3 + 0.4 * s, -2.1 + 0.3 * s)) for s in streams]
-    # one handle (= one CUDA stream) and one host thread per camera stream, as a multi-camera node would run them:
-    # handles are independent and ctypes releases the GIL during a call, so the latency-bound kernels of the sparse
-    # path (the ordered corner selection is a single CTA) of different cameras overlap on the GPU
-    from concurrent.futures import ThreadPoolExecutor
-    engines = [ofb.FlowEngine(W_, H_, 1, local_rank) for _ in pairs]
-    eng = engines[0]
-    pool = ThreadPoolExecutor(max_workers=max(1, len(pairs)))
-
-    def one(i):
-        a, b = pairs[i]
-        e = engines[i]
-        pts = e.good_features(a, 2000, 0.01, 7, 3)
-        if pts is None or len(pts) == 0:
-            return 0
-        nxt, st, err = e.pyrlk(a, b, pts, None, (21, 21), 3, (3, 30, 0.01))
-        return int(st.sum())
-
-    def step():
-        return sum(pool.map(one, range(len(pairs))))
-
-    for _ in range(max(args.warmup, 1)):
-        tracked = step()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    frames = torch.tensor([len(pairs) * args.steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(frames, op=dist.ReduceOp.SUM)
+    rec = lk_record(args, rank, local_rank, world, args.steps, args.warmup, cpu=not args.no_cpu_baseline)
     if rank == 0:
-        import cv2
-        cv2.setNumThreads(0)
-        a, b = pairs[0]
-        t1 = time.perf_counter()
-        reps = 5
-        for _ in range(reps):
-            p = cv2.goodFeaturesToTrack(a, 2000, 0.01, 7, blockSize=3)
-            cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=3,
-                                     criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01))
-        cpu_ms = (time.perf_counter() - t1) / reps * 1e3
-        value = float(frames.item()) / float(tt.item())
-        line = {"metric": "shi_tomasi_pyrlk_1080p_2000pt_frames_per_s", "value": value, "unit": "frames/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(tt.item()) / args.steps * 1e3,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic",
-                "config": {"workload": "goodFeaturesToTrack(2000, 0.01, 7) + calcOpticalFlowPyrLK(21x21, maxLevel 3, (30, 0.01)) "
-                                       "on 1920x1080, 8 camera streams", "streams_this_rank": len(pairs),
-                           "tracked_points_last_step_rank0": tracked,
-                           "api": "host buffers in and out (ofb_good_features + ofb_pyrlk), synchronous; one handle and one "
-                                  "host thread per camera stream"},
-                "cpu_baseline": {"value": 1e3 / cpu_ms, "unit": "frames/s", "cores": cv2.getNumThreads(), "kind": "reference",
-                                 "sample": "cv2 %s goodFeaturesToTrack + calcOpticalFlowPyrLK, %d frames of stream 0, "
-                                           "default cv2 threads (%.1f ms per frame)" % (cv2.__version__, reps, cpu_ms)},
-                "gpu_launches": int(sum(e.launch_count for e in engines))}
-        real_stdout.write(json.dumps(line) + "\n")
+        rec.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "s32/f32", "data": "synthetic"})
+        real_stdout.write(json.dumps(rec) + "\n")
         real_stdout.flush()
-    pool.shutdown()
-    for e in engines:
-        e.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------ tiled mode (config 5)
-def run_tiled(args, rank, local_rank, world):
+def tiled_record(args, rank, local_rank, world, size, steps, warmup, parity=True, whole=True):
     """One frame pair spatially tiled over the N ranks (BASELINE.json config 5: 7680x4320 over 8 B200).
-    A step = one tiled pair; value = pairs/s of the whole job.  Not the headline metric: an extra line."""
+    A step = one tiled pair.  Parity: EVERY rank's rows against cv2 on the same pair (rank 0 runs cv2, the field is
+    broadcast, each rank compares the rows it owns).  Returns the record on rank 0."""
     import torch
     import torch.distributed as dist
-
-    real_stdout = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from opticalflowcontainer_b200 import build as ofb_build
-    if rank == 0:
-        ofb_build.build()
-    if world > 1:
-        dist.barrier()
     import opticalflowcontainer_b200 as ofb
     from opticalflowcontainer_b200 import tiled
     from oracle import synth
 
-    W, H = {"8k": (7680, 4320), "4k": (3840, 2160), "1080p": (1920, 1080)}[args.tile_size]
+    W, H = {"8k": (7680, 4320), "4k": (3840, 2160), "1080p": (1920, 1080)}[size]
     eng = ofb.FlowEngine(W, H, 1, local_rank)
     tiled.setup_distributed(eng, rank, world)
     t = synth.cheap_texture(H, W, 400)
     n_sets = 3
-    frames = []
+    host_frames, frames = [], []
     for s in range(n_sets):
         a = np.roll(t, (17 * s, 29 * s), axis=(0, 1))
         b = synth.subpixel_shift(a, 9.5 - s, -4.25 + s)
+        host_frames.append((a, b))
         frames.append((torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()))
     d_flow = torch.zeros((H, W, 2), dtype=torch.float32, device="cuda")
     stream = torch.cuda.ExternalStream(eng.stream)
@@ -288,7 +334,8 @@ def run_tiled(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    rows = (0, 0)
+    for i in range(warmup):
         rows = step(i)
     timed_out = tiled.tiled_status(eng)
     barrier()
@@ -298,85 +345,146 @@ def run_tiled(args, rank, local_rank, world):
     sampler.start()
     l0 = eng.launch_count
     ev0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
     ev1.record(stream)
     timed_out = tiled.tiled_status(eng) or timed_out
     barrier()
     clocks = sampler.stop()
     launches = eng.launch_count - l0
     tms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    # per-stage event times of one more (untimed) step on this rank; "other" = the cross-GPU barriers
+    # per-stage event times of one more (untimed) step on this rank; "other" = the cross-GPU barriers + halo pulls
     eng.timing_enable(True)
-    rows = step(args.warmup + args.steps)
+    last = warmup + steps
+    rows = step(last)
     stage = eng.timing_read()
     barrier()
     all_stage = [None] * world
+    mine = {k: round(v[0], 3) for k, v in stage.items()}
     if world > 1:
-        mine = {k: round(v[0], 3) for k, v in stage.items()}
-        mine["iter_launch_ms"] = [round(x, 3) for x in eng.timing_samples("iteration")]
-        mine["other_launch_ms"] = [round(x, 3) for x in eng.timing_samples("other")]
         dist.all_gather_object(all_stage, mine)
     else:
-        all_stage = [{k: round(v[0], 3) for k, v in stage.items()}]
+        all_stage = [mine]
     eng.timing_enable(False)
-    # floor of the cross-GPU flag barrier: 50 of them back to back on already-synchronised ranks
-    bar_us = None
-    if world > 1:
-        eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tiled.tiled_barrier(eng)
-        eb0.record(stream)
-        for _ in range(50):
-            tiled.tiled_barrier(eng)
-        eb1.record(stream)
-        timed_out = tiled.tiled_status(eng) or timed_out
-        bar_us = eb0.elapsed_time(eb1) / 50 * 1e3
-        barrier()
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
-    # single-GPU whole-frame reference on rank 0 (same engine, untiled) for the speed-up and a parity check
-    whole_ms, max_diff = None, None
-    if rank == 0 and not args.no_tiled_check:
-        ref = torch.zeros((H, W, 2), dtype=torch.float32, device="cuda")
-        a, b = frames[(args.warmup + args.steps) % n_sets]
+    # ---- parity of the tiled field against cv2, every rank's rows
+    par = None
+    if parity:
+        ref = torch.empty((H, W, 2), dtype=torch.float32, device="cuda")
+        cv2_s = 0.0
+        if rank == 0:
+            import cv2
+            a, b = host_frames[last % n_sets]
+            t0 = time.perf_counter()
+            f = cv2.calcOpticalFlowFarneback(a, b, None, PARAMS["pyr_scale"], PARAMS["levels"], PARAMS["winsize"],
+                                             PARAMS["iterations"], PARAMS["poly_n"], PARAMS["poly_sigma"], PARAMS["flags"])
+            cv2_s = time.perf_counter() - t0
+            ref.copy_(torch.from_numpy(f))
+        if world > 1:
+            dist.broadcast(ref, 0)
+        yb, ye = rows
+        d = (ref[yb:ye] - d_flow[yb:ye]).double()
+        epe = torch.sqrt((d * d).sum(-1))
+        acc = torch.tensor([float(epe.sum().item()), float(epe.numel())], dtype=torch.float64, device="cuda")
+        mx = torch.tensor([float(epe.max().item()) if epe.numel() else 0.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        import cv2
+        par = {"mean_epe": float(acc[0].item() / max(acc[1].item(), 1.0)), "max_epe": float(mx.item()),
+               "pixels_compared": int(acc[1].item()), "vs": "cv2 %s calcOpticalFlowFarneback, same pair" % cv2.__version__,
+               "rows": "every rank's own rows (all %d ranks)" % world, "cv2_seconds": cv2_s}
+        del ref
+    # single-GPU whole-frame time on rank 0 (same engine, untiled) for the speed-up
+    whole_ms = None
+    if whole and rank == 0:
+        tmp = torch.zeros((H, W, 2), dtype=torch.float32, device="cuda")
+        a, b = frames[last % n_sets]
         for _ in range(2):
-            eng.farneback_device(1, a.data_ptr(), b.data_ptr(), W, H, W, W * H, ref.data_ptr(), **PARAMS)
+            eng.farneback_device(1, a.data_ptr(), b.data_ptr(), W, H, W, W * H, tmp.data_ptr(), **PARAMS)
         eng.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(3):
-            eng.farneback_device(1, a.data_ptr(), b.data_ptr(), W, H, W, W * H, ref.data_ptr(), **PARAMS)
+            eng.farneback_device(1, a.data_ptr(), b.data_ptr(), W, H, W, W * H, tmp.data_ptr(), **PARAMS)
         e1.record(stream)
         eng.synchronize()
         whole_ms = e0.elapsed_time(e1) / 3
-        yb, ye = rows
-        max_diff = float((ref[yb:ye] - d_flow[yb:ye]).abs().max().item())
     if world > 1:
         dist.barrier()
-    if rank == 0:
-        peaks, peak_src = measured_peaks()
-        value = args.steps / (ms * 1e-3)
-        bytes_pair = algorithmic_bytes_per_pair(W, H)
-        line = {"metric": "farneback_%s_tiled_frame_pairs_per_s" % args.tile_size, "value": value, "unit": UNIT,
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "farneback_%dx%d_spatially_tiled_x%d" % (W, H, world), "params": PARAMS,
-                           "parallelism": "row strips x%d, NVLink peer loads inside the kernels + peer-memory flag barrier, "
-                                          "no collective" % world,
-                           "l2": "frame working set %.0f MB >> L2; inputs rotate over %d frame sets" % (bytes_pair / 1e6, n_sets)},
-                "roofline": {"bound": "hbm", "achieved": bytes_pair * value / 1e9, "peak": peaks["hbm_gbs"] * world,
-                             "unit": "GB/s", "frac": bytes_pair * value / 1e9 / (peaks["hbm_gbs"] * world),
-                             "traffic": None, "peak_source": peak_src + " x n_gpus",
-                             "algorithmic_bytes_per_pair": bytes_pair},
-                "stage_ms_per_rank": all_stage, "barrier_floor_us": bar_us,
-                "whole_frame_single_gpu_ms": whole_ms, "tiled_vs_whole_max_abs_diff_px": max_diff,
-                "barrier_timed_out": bool(timed_out), "gpu_launches": int(launches), "clocks": clocks}
-        real_stdout.write(json.dumps(line) + "\n")
-        real_stdout.flush()
     eng.close()
+    if rank != 0:
+        return None
+    peaks, peak_src = measured_peaks()
+    value = steps / (ms * 1e-3)
+    bytes_pair = algorithmic_bytes_per_pair(W, H)
+    return {"metric": "farneback_%s_tiled_frame_pairs_per_s" % size, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": steps, "ms_per_pair": ms / steps, "scaling": "strong",
+            "workload": "farneback_%dx%d_spatially_tiled_x%d" % (W, H, world),
+            "parallelism": "row strips x%d, halo rows pulled over NVLink peer pointers, neighbour flag barriers in peer "
+                           "memory, no collective" % world,
+            "roofline": {"bound": "hbm", "achieved": bytes_pair * value / 1e9, "peak": peaks["hbm_gbs"] * world,
+                         "unit": "GB/s", "frac": bytes_pair * value / 1e9 / (peaks["hbm_gbs"] * world),
+                         "peak_source": peak_src + " x n_gpus", "algorithmic_bytes_per_pair": bytes_pair},
+            "stage_ms_per_rank": all_stage, "whole_frame_single_gpu_ms": whole_ms,
+            "speedup_vs_whole_frame_single_gpu": (whole_ms / (ms / steps)) if whole_ms else None,
+            "parity": par, "barrier_timed_out": bool(timed_out), "gpu_launches": int(launches), "clocks": clocks}
+
+
+def run_tiled(args, rank, local_rank, world):
+    """--mode tiled: the tiled record alone, as one JSON line."""
+    import torch
+    import torch.distributed as dist
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from opticalflowcontainer_b200 import build as ofb_build
+    if rank == 0:
+        ofb_build.build()
+    if world > 1:
+        dist.barrier()
+    rec = tiled_record(args, rank, local_rank, world, args.tile_size, args.steps, args.warmup,
+                       parity=not args.no_tiled_check, whole=not args.no_tiled_check)
+    if rank == 0:
+        rec.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic"})
+        real_stdout.write(json.dumps(rec) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ extras of the main line
+def e2e_copy_ceiling(torch, dist, world, h2d_bytes, d2h_bytes, steps=10):
+    """Bare pinned-memory copies of one step's traffic (H2D of the frames, D2H of the fields, on two streams, all ranks
+    at once): the pairs/s the host link allows with NO kernel at all — the ceiling of the full-field e2e number."""
+    up = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    down = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    d_up = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    d_down = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def one():
+        with torch.cuda.stream(s1):
+            d_up.copy_(up, non_blocking=True)
+        with torch.cuda.stream(s2):
+            down.copy_(d_down, non_blocking=True)
+
+    one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return float(dt.item()) / steps
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -560,6 +668,75 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     node_value = B * e2e_steps * world / float(t.item())
 
+    # ---- extras (all ranks take part; rank 0 reports) ---------------------------------------------------------
+    extras = {}
+    if not args.no_extras and args.mode == "pairs":
+        # (1) parity of the timed workload: pair 0 of the last timed step's frame set against cv2 on this host
+        last = (args.warmup + 2 * args.steps - 1) % n_sets
+        if rank == 0:
+            import cv2
+            eng.farneback_device(B, dev_sets[last].data_ptr(), dev_sets[last].data_ptr() + B * istride, W_, H_, pitch, istride,
+                                 d_flow.data_ptr(), **PARAMS)
+            eng.synchronize()
+            got = d_flow[0].cpu().numpy().astype(np.float64)
+            t0 = time.perf_counter()
+            ref = cv2.calcOpticalFlowFarneback(host_sets[last][0], host_sets[last][B], None, PARAMS["pyr_scale"],
+                                               PARAMS["levels"], PARAMS["winsize"], PARAMS["iterations"], PARAMS["poly_n"],
+                                               PARAMS["poly_sigma"], PARAMS["flags"])
+            cv2_s = time.perf_counter() - t0
+            epe = np.sqrt(((got - ref) ** 2).sum(-1))
+            extras["parity"] = {"mean_epe": float(epe.mean()), "max_epe": float(epe.max()),
+                                "vs": "cv2 %s calcOpticalFlowFarneback on the same pair (pair 0 of the last timed step, "
+                                      "computed by the same %d-pair launch sequence)" % (cv2.__version__, B),
+                                "gate": "mean <= 0.01 px, max <= 0.1 px", "cv2_seconds": cv2_s,
+                                "ok": bool(epe.mean() <= 0.01 and epe.max() <= 0.1)}
+        # (2) one pair per call: what a single camera node sees (BASELINE.json configs[1] read literally)
+        if rank == 0:
+            one = dev_sets[0]
+            for _ in range(5):
+                eng.farneback_device(1, one.data_ptr(), one.data_ptr() + B * istride, W_, H_, pitch, istride, d_flow.data_ptr(), **PARAMS)
+            eng.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 50
+            e0.record(stream)
+            for i in range(reps):
+                d = dev_sets[i % n_sets]
+                eng.farneback_device(1, d.data_ptr(), d.data_ptr() + B * istride, W_, H_, pitch, istride, d_flow.data_ptr(), **PARAMS)
+            e1.record(stream)
+            eng.synchronize()
+            dev1 = e0.elapsed_time(e1) / reps
+            p1, n1, f1 = pin_prev[0][0].numpy(), pin_next[0][0].numpy(), pin_flow[0][0].numpy()
+            for _ in range(3):
+                eng.farneback(p1, n1, f1, **PARAMS)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                eng.farneback(p1, n1, f1, **PARAMS)
+            host1 = (time.perf_counter() - t0) / reps * 1e3
+            extras["batch1"] = {"device_resident_ms_per_pair": dev1, "device_resident_pairs_per_s": 1e3 / dev1,
+                                "host_to_host_full_field_ms_per_pair": host1, "host_to_host_pairs_per_s": 1e3 / host1,
+                                "calls": reps, "api": "ofb_farneback_device / ofb_farneback (one pair per call, CUDA-graph replay)"}
+        # (3) bare-copy ceiling of the full-field e2e number, all ranks at once
+        ceil_s = e2e_copy_ceiling(torch, dist, world, 2 * B * W_ * H_, 8 * B * W_ * H_)
+        extras["e2e_ceiling"] = {"value": B * world / ceil_s, "unit": UNIT, "seconds_per_step": ceil_s,
+                                 "what": "pinned cudaMemcpyAsync of one step's frames up (%d B) and fields down (%d B) on two "
+                                         "streams, all %d rank(s) concurrently, no kernels: the pairs/s the host link allows "
+                                         "for the full-field path" % (2 * B * W_ * H_, 8 * B * W_ * H_, world),
+                                 "aggregate_d2h_gbs": 8 * B * W_ * H_ * world / ceil_s / 1e9,
+                                 "aggregate_h2d_gbs": 2 * B * W_ * H_ * world / ceil_s / 1e9}
+    eng.close()
+    del dev_sets, d_flow
+    torch.cuda.empty_cache()
+    if not args.no_extras and args.mode == "pairs" and args.frame == "1080p":
+        # (4) BASELINE.json config 4: sparse path, 8 camera streams sharded over the ranks
+        rec = lk_record(args, rank, local_rank, world, steps=5, warmup=2, cpu=(world == 1 and not args.no_cpu_baseline))
+        if rank == 0:
+            extras["lk_8_streams"] = rec
+        # (5) BASELINE.json config 5: one 8K pair tiled over the ranks (needs >= 2 GPUs)
+        if world >= 2:
+            rec = tiled_record(args, rank, local_rank, world, "8k", steps=5, warmup=3, parity=True, whole=True)
+            if rank == 0:
+                extras["tiled_8k"] = rec
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -579,10 +756,12 @@ def run_ours(args, rank, local_rank, world):
     it_gbs = alg_launch_bytes / (l0_ms * 1e-3) / 1e9 if l0_ms > 0 else 0.0
     stage_gbs = 56.0 * sum(nl) * iters * B * args.steps / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0
     pipe_gbs = algorithmic_bytes_per_pair(W_, H_) * (value / world) / 1e9
-    traffic = None                                                  # DRAM bytes per launch from the committed ncu capture
+    # DRAM bytes per launch from the committed ncu capture of the same kernel (a 1080p level-0 launch), scaled by the
+    # pixels of this run's launch; None for other frame sizes (the halo / L2 behaviour is not the same there)
+    traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_iter_v_ncu.json")))
-        if prof.get("pairs_per_launch"):
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r2_iter_v_ncu.json")))
+        if prof.get("pairs_per_launch") and (W_, H_) == (prof.get("width", 1920), prof.get("height", 1080)):
             traffic = prof["dram_bytes_per_launch"] * B / prof["pairs_per_launch"]
     except Exception:
         pass
@@ -590,11 +769,13 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": plain_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "farneback_%dx%d_%s" % (W_, H_, "single_stream" if args.frame == "1080p" else "batched_pairs"),
-                   "params": PARAMS, "pairs_per_step_per_gpu": B,
-                   "mode": args.mode, "parallelism": "frame-pair sharding x%d, no collective" % world,
-                   "l2": "inputs rotate over %d frame sets (%.0f MB > 2x L2); per-step working set %.0f MB >> L2"
-                         % (n_sets, n_sets * frames_per_set * istride / 1e6, B * 232.0 * W_ * H_ / 2073600.0)},
+        "config": bench_config(),
+        "run": {"pairs_per_step_per_gpu": B, "mode": args.mode,
+                "parallelism": "frame-pair sharding x%d, no collective" % world,
+                "l2": "inputs rotate over %d frame sets (%.0f MB > 2x L2); per-step working set %.0f MB >> L2"
+                      % (n_sets, n_sets * frames_per_set * istride / 1e6, B * 232.0 * W_ * H_ / 2073600.0),
+                "note": "a step = ONE launch sequence over %d independent pairs (the batch fills the 296 resident CTA "
+                        "slots of the iteration kernel); one pair per call is reported under batch1" % B},
         "roofline": {"bound": "hbm", "kernel": "k_iter_v, level-0 launch (UpdateMatrices + box blur + 2x2 solve fused)",
                      "achieved": it_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": it_gbs / peaks["hbm_gbs"],
                      "traffic": traffic, "peak_source": peak_src,
@@ -622,6 +803,7 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_bench
         cb = cpu_bench.farneback_cpu_throughput(H_, W_, target_seconds=args.cpu_seconds)
@@ -657,6 +839,8 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=2, help="--impl reference: pairs per worker per step")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records of the main line (parity vs cv2, batch-1 latency, copy ceiling, LK streams, tiled 8K)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -82,7 +82,8 @@ typedef struct ofb_lk_params {
 } ofb_lk_params;
 
 /* cv2.goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask,
- *                         blockSize, useHarrisDetector=False, k) — Shi-Tomasi only. */
+ *                         blockSize, useHarrisDetector=False, k) — Shi-Tomasi (the Harris response of the
+ * wheel is not reproduced: useHarrisDetector=True is refused by the Python mirror). */
 typedef struct ofb_gftt_params {
   int max_corners;
   double quality_level;
@@ -324,6 +325,12 @@ int ofb_adapt_prefilter(ofb_handle* h, const uint8_t* bgr, int width, int height
 int ofb_good_features(ofb_handle* h, const uint8_t* image, int width, int height, size_t stride_bytes,
                       const ofb_gftt_params* params, float* corners_xy, int* n_out);
 
+/* The same with cv2's `mask` argument (uint8 [height][width], 0 = excluded, `mask_stride_bytes` per row, 0 = packed;
+ * mask == NULL: no mask).  As in cv2 the quality threshold is relative to the strongest response INSIDE the mask. */
+int ofb_good_features_masked(ofb_handle* h, const uint8_t* image, int width, int height, size_t stride_bytes,
+                             const uint8_t* mask, size_t mask_stride_bytes, const ofb_gftt_params* params,
+                             float* corners_xy, int* n_out);
+
 /* cv2.cornerMinEigenVal(image, blockSize=3, ksize=3) — exposed for bit-exact parity tests. */
 int ofb_corner_min_eigenval(ofb_handle* h, const uint8_t* image, int width, int height,
                             size_t stride_bytes, int block_size, float* eig_out);
@@ -342,6 +349,23 @@ int ofb_lk_pyramid(ofb_handle* h, const uint8_t* image, int width, int height, s
 int ofb_pyrlk(ofb_handle* h, const uint8_t* prev, const uint8_t* next, int width, int height,
               size_t stride_bytes, const float* prev_pts, int n_points, float* next_pts,
               uint8_t* status, float* err, const ofb_lk_params* params);
+
+/* Camera-stream form of the sparse path — the worker loop of a direct-camera node
+ * (ros2_ws/src/liteflownet3/liteflownet3/lfn3_node.py:145-210: keep the previous frame, process the new one) with
+ * goodFeaturesToTrack + calcOpticalFlowPyrLK as the flow call.  One new frame per call; the previous frame's pyramid,
+ * Scharr derivatives and corner list stay on the GPU, so a frame is uploaded ONCE and nothing but the results comes
+ * back.  Call t tracks the corners detected in frame t-1 into frame t and detects the corners of frame t for call t+1:
+ *   prev_pts / next_pts / status / err : the tracked points of (frame t-1 -> frame t), *n_tracked of them
+ *                                        (capacity params->max_corners each; any may be NULL); *n_tracked = -1 on a
+ *                                        priming call (first frame, or the stream was re-primed)
+ *   new_corners / n_new                : the corners of frame t (optional)
+ * Bit-identical to ofb_good_features(frame t-1) + ofb_pyrlk(frame t-1, frame t, those corners).  Needs
+ * max_corners > 0 (fixed-size result block) and no OFB_OPTFLOW_USE_INITIAL_FLOW.  A change of size or parameters, or
+ * any other sparse call on the handle, re-primes the stream. */
+int ofb_lk_stream(ofb_handle* h, const uint8_t* frame, int width, int height, size_t stride_bytes,
+                  const ofb_gftt_params* gftt, const ofb_lk_params* lk, float* prev_pts, float* next_pts,
+                  uint8_t* status, float* err, int* n_tracked, float* new_corners, int* n_new);
+int ofb_lk_stream_reset(ofb_handle* h);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

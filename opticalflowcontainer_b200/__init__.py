@@ -52,12 +52,14 @@ def calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, itera
 
 def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None, blockSize=3,
                         useHarrisDetector=False, k=0.04):
-    """Drop-in for ``cv2.goodFeaturesToTrack`` (Shi-Tomasi; no mask / Harris)."""
-    if mask is not None or useHarrisDetector:
-        raise OfbError(1, "goodFeaturesToTrack: mask and useHarrisDetector are not supported")
+    """Drop-in for ``cv2.goodFeaturesToTrack`` (Shi-Tomasi, optional ``mask``).  ``useHarrisDetector=True`` is refused:
+    the wheel's Harris response is not reproduced bit for bit, and a corner list that merely resembles cv2's is not a
+    drop-in (out of scope)."""
+    if useHarrisDetector:
+        raise OfbError(1, "goodFeaturesToTrack: useHarrisDetector is not supported")
     image = np.asarray(image)
     r = _engine_for(image.shape[0], image.shape[1]).good_features(image, maxCorners, qualityLevel, minDistance,
-                                                                  blockSize)
+                                                                  blockSize, mask)
     return r if len(r) else None
 
 
@@ -81,9 +83,29 @@ def buildOpticalFlowPyramid(img, winSize, maxLevel, withDerivatives=True):
     return len(lv) - 1, out
 
 
+def _pyramid_level0(img):
+    """(image, depth): an image as it is (depth None), or level 0 of a buildOpticalFlowPyramid list and the index of its
+    last level."""
+    if isinstance(img, (list, tuple)):
+        if not img:
+            raise OfbError(1, "calcOpticalFlowPyrLK: empty pyramid")
+        # with derivatives the list alternates [level, deriv, level, deriv, ...]; derivative images are int16 2-channel
+        with_deriv = len(img) > 1 and np.asarray(img[1]).dtype == np.int16
+        n_levels = len(img) // 2 if with_deriv else len(img)
+        return np.asarray(img[0]), n_levels - 1
+    return np.asarray(img), None
+
+
 def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=None, winSize=(21, 21), maxLevel=3,
                          criteria=(3, 30, 0.01), flags=0, minEigThreshold=1e-4):
-    """Drop-in for ``cv2.calcOpticalFlowPyrLK`` → (nextPts [N,1,2], status [N,1], err [N,1])."""
-    prevImg = np.asarray(prevImg)
+    """Drop-in for ``cv2.calcOpticalFlowPyrLK`` → (nextPts [N,1,2], status [N,1], err [N,1]).
+    ``prevImg`` / ``nextImg`` may also be pyramids as ``buildOpticalFlowPyramid`` returns them (with or without the
+    derivative images): level 0 is taken and ``maxLevel`` is clamped to the pyramid's depth, as cv2 does — the engine
+    rebuilds the (bit-identical) uint8 pyramid on the GPU."""
+    prevImg, d0 = _pyramid_level0(prevImg)
+    nextImg, d1 = _pyramid_level0(nextImg)
+    for d in (d0, d1):
+        if d is not None:
+            maxLevel = min(maxLevel, d)
     return _engine_for(prevImg.shape[0], prevImg.shape[1]).pyrlk(prevImg, nextImg, prevPts, nextPts, winSize, maxLevel,
                                                                 criteria, flags, minEigThreshold)

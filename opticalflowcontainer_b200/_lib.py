@@ -108,6 +108,12 @@ _SIGNATURES = {
                                       C.c_size_t]),
     "ofb_good_features": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.POINTER(GfttParams),
                                     C.c_void_p, C.POINTER(C.c_int)]),
+    "ofb_good_features_masked": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, _u8p, C.c_size_t,
+                                           C.POINTER(GfttParams), C.c_void_p, C.POINTER(C.c_int)]),
+    "ofb_lk_stream": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.POINTER(GfttParams), C.POINTER(LKParams),
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
+                                C.POINTER(C.c_int)]),
+    "ofb_lk_stream_reset": (C.c_int, [C.c_void_p]),
     "ofb_corner_min_eigenval": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p]),
     "ofb_lk_pyramid": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),

@@ -190,8 +190,8 @@ int ofb_destroy(ofb_handle* h) {
       if (r == h->tile.rank) continue;
       cudaIpcCloseMemHandle(h->tile.peer_RA[r]);
       cudaIpcCloseMemHandle(h->tile.peer_RB[r]);
-      cudaIpcCloseMemHandle(h->tile.peer_flow[0][r]);
-      cudaIpcCloseMemHandle(h->tile.peer_flow[1][r]);
+      cudaIpcCloseMemHandle(h->tile.peer_MA[r]);
+      cudaIpcCloseMemHandle(h->tile.peer_MB[r]);
       cudaIpcCloseMemHandle(h->tile.peer_flags[r]);
     }
   }
@@ -331,8 +331,8 @@ int ofb_tiled_export(ofb_handle* h, void* blob) {
   cudaIpcMemHandle_t* out = reinterpret_cast<cudaIpcMemHandle_t*>(blob);
   OFB_CUDA(h, cudaIpcGetMemHandle(&out[0], h->d_RA));
   OFB_CUDA(h, cudaIpcGetMemHandle(&out[1], h->d_RB));
-  OFB_CUDA(h, cudaIpcGetMemHandle(&out[2], h->d_flow[0]));
-  OFB_CUDA(h, cudaIpcGetMemHandle(&out[3], h->d_flow[1]));
+  OFB_CUDA(h, cudaIpcGetMemHandle(&out[2], h->d_MA));
+  OFB_CUDA(h, cudaIpcGetMemHandle(&out[3], h->d_MB));
   OFB_CUDA(h, cudaIpcGetMemHandle(&out[4], h->tile.d_flags));
   return OFB_OK;
 }
@@ -341,8 +341,8 @@ static void tiled_set_self(ofb_handle* h) {
   const int r = h->tile.rank;
   h->tile.peer_RA[r] = h->d_RA;
   h->tile.peer_RB[r] = h->d_RB;
-  h->tile.peer_flow[0][r] = h->d_flow[0];
-  h->tile.peer_flow[1][r] = h->d_flow[1];
+  h->tile.peer_MA[r] = h->d_MA;
+  h->tile.peer_MB[r] = h->d_MB;
   h->tile.peer_flags[r] = h->tile.d_flags;
 }
 
@@ -358,8 +358,8 @@ int ofb_tiled_import(ofb_handle* h, const void* all_blobs) {
       OFB_CUDA(h, cudaIpcOpenMemHandle(&p[k], in[r * 5 + k], cudaIpcMemLazyEnablePeerAccess));
     h->tile.peer_RA[r] = p[0];
     h->tile.peer_RB[r] = p[1];
-    h->tile.peer_flow[0][r] = p[2];
-    h->tile.peer_flow[1][r] = p[3];
+    h->tile.peer_MA[r] = p[2];
+    h->tile.peer_MB[r] = p[3];
     h->tile.peer_flags[r] = reinterpret_cast<unsigned*>(p[4]);
   }
   tiled_set_self(h);
@@ -384,8 +384,8 @@ int ofb_tiled_import_local(ofb_handle* h, ofb_handle* const* handles) {
     }
     h->tile.peer_RA[r] = q->d_RA;
     h->tile.peer_RB[r] = q->d_RB;
-    h->tile.peer_flow[0][r] = q->d_flow[0];
-    h->tile.peer_flow[1][r] = q->d_flow[1];
+    h->tile.peer_MA[r] = q->d_MA;
+    h->tile.peer_MB[r] = q->d_MB;
     h->tile.peer_flags[r] = q->tile.d_flags;
   }
   h->tile.imported = true;

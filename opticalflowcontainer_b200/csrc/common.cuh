@@ -60,12 +60,11 @@ constexpr int kMaxTileRanks = 8;
 struct PeerTab {
   const float4* RA[kMaxTileRanks];
   const float* RB[kMaxTileRanks];
-  const float2* flow[kMaxTileRanks];   // the flow buffer the launch reads (ping or pong of every rank)
   int rpr;                             // rows per rank at the level of the launch
   int world;
-  // rows [r_lo, r_hi) of R and [f_lo, f_hi) of the flow are present in THIS rank's buffers (own rows
-  // plus the halo rows pulled from the neighbours before the launch); other rows are read remotely
-  int r_lo, r_hi, f_lo, f_hi;
+  // rows [r_lo, r_hi) of R are valid in THIS rank's buffers (the band it computed); rows outside are read from the
+  // rank that owns them.  The flow a launch reads is always local (independent bands, tiled.cuh).
+  int r_lo, r_hi;
 };
 
 // Polynomial coefficients of the two frames of every pair: frame 0 of pair i at A0/B0 + i*n, frame 1 at A1/B1 + i*n
@@ -138,12 +137,12 @@ struct ofb_handle {
     bool imported = false, same_process = false;
     void* peer_RA[ofb::kMaxTileRanks] = {nullptr};
     void* peer_RB[ofb::kMaxTileRanks] = {nullptr};
-    void* peer_flow[2][ofb::kMaxTileRanks] = {{nullptr}};
+    void* peer_MA[ofb::kMaxTileRanks] = {nullptr};   // expansions of the coarser levels (the generic path's buffers)
+    void* peer_MB[ofb::kMaxTileRanks] = {nullptr};
     unsigned* peer_flags[ofb::kMaxTileRanks] = {nullptr};
     unsigned* d_flags = nullptr;     // [world] written by the peers
     int* d_err = nullptr;            // barrier timeout flag
     unsigned epoch = 0;
-    int r_lo = 0, r_hi = 0;          // R rows present locally at the current level (own + pulled halo)
   } tile;
   // frame ingest (ingest.cu): staging for frames of any size and the cached cv2.resize coordinate tables
   struct Ingest {

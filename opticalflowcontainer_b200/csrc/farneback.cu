@@ -649,7 +649,7 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
     // Marching PolyExp kernel (poly_n <= 8).  When the level has the source size (k = 0: 3-tap blur,
     // identity resize) the pyramid stage is fused into it and the level image never exists in HBM.
     const bool march = pc.n <= PX_MAXN;
-    const bool fused_src = march && w == width && hh == height && pyc.r == 1;
+    const bool fused_src = march && w == width && hh == height && pyc.r == 1 && pyc.k[0] == 0.5f && pyc.k[1] == 0.25f;
     // regular power-of-two level (fb_pyramid.cuh, k_pyr_fast): one kernel, source read once
     int fastS = 0;
     if (!fused_src && (width & 3) == 0 && (pitch & 3) == 0 && (image_stride & 3) == 0 &&

@@ -100,8 +100,8 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 
 // MT: window radius (0 = run time).  COLS: strip width = producer threads.  CH: rows per chunk.  MINB: CTAs per SM the
 // register budget is held to.  PFD: L2 prefetch distance of the plain schedule.  TILED (spatially tiled mode, one pair):
-// the CTA grid covers only the level rows [y_begin, y_end) this rank owns; R0 / R1 / flow rows owned by other ranks are
-// read from those ranks' buffers through the NVLink peer pointers in `tab`.
+// the CTA grid covers only the level rows [y_begin, y_end) of this rank's band; R1 rows the displacement reaches outside
+// the band are read from the owner's buffer through the NVLink peer pointers in `tab` (the flow and R0 are local).
 template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF>
 __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     k_iter_v(const RSet rs, const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int w, int h, int m_rt,
@@ -199,28 +199,33 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     // fused upsample: per-thread column entry of the resize table
     int ux0 = 0, ux1 = 0;
     float ufx = 0.f;
-    const bool do_ups = !TILED && ups.prev != nullptr;
+    const bool do_ups = ups.prev != nullptr;
     const float2* uprev = nullptr;
     if (do_ups) {
       const int2 tx = __ldg(reinterpret_cast<const int2*>(ups.tabx + x));   // {i0, f}
       ux0 = tx.x; ux1 = min(tx.x + 1, ups.pw - 1); ufx = __int_as_float(tx.y);
-      uprev = ups.prev + (size_t)pair * ups.pw * ups.ph;
+      uprev = ups.prev + (size_t)pair * ups.pw * ups.ph;   // (tiled mode: the rank's own coarse band, one pair)
     }
     // input flow of matrix row t at this column (volatile loads: they stay where they are written, between the gathers
-    // and the barrier; ptxas otherwise sinks them to the end of the loop body, in front of the address arithmetic)
-    auto flow_at = [&](int t) -> float2 {
+    // and the barrier; ptxas otherwise sinks them to the end of the loop body, in front of the address arithmetic).
+    // Fused upsample: the row's resize-table entry is fetched by ups_row() one chunk BEFORE the coarse flow is read — a
+    // table load in front of the four flow loads put a second dependent memory round trip on every chunk's critical
+    // path (measured: the first iteration of levels 1-3 ran 2x longer).
+    auto ups_row = [&](int t) -> int2 {
+      return do_ups ? __ldg(reinterpret_cast<const int2*>(ups.taby + clampi(t, 0, h - 1))) : make_int2(0, 0);
+    };
+    auto flow_at = [&](int t, int2 ty) -> float2 {
       const int yc = clampi(t, 0, h - 1);
       if (do_ups) {
-        const int2 ty = __ldg(reinterpret_cast<const int2*>(ups.taby + yc));
         const float2* r0 = uprev + (unsigned)ty.x * (unsigned)ups.pw;
         const float2* r1 = uprev + (unsigned)min(ty.x + 1, ups.ph - 1) * (unsigned)ups.pw;
-        const float2 q00 = ld_volatile_f2(r0 + ux0), q01 = ld_volatile_f2(r0 + ux1);
-        const float2 q10 = ld_volatile_f2(r1 + ux0), q11 = ld_volatile_f2(r1 + ux1);
+        // (cached loads: the coarse rows are shared by neighbouring fine rows and columns; the branch keeps them here)
+        const float2 q00 = __ldg(r0 + ux0), q01 = __ldg(r0 + ux1);
+        const float2 q10 = __ldg(r1 + ux0), q11 = __ldg(r1 + ux1);
         return ups_blend(q00, q01, q10, q11, ufx, __int_as_float(ty.y), ups.mul);
       }
-      const float2* f = TILED ? tab.flow[(yc >= tab.f_lo && yc < tab.f_hi) ? my_rank : tile_owner(yc, tab)] : fin;
-      if constexpr (REUSE) return ld_volatile_f2(f + ((unsigned)yc * uw + (unsigned)x));
-      return __ldg(f + ((unsigned)yc * uw + (unsigned)x));
+      if constexpr (REUSE) return ld_volatile_f2(fin + ((unsigned)yc * uw + (unsigned)x));
+      return __ldg(fin + ((unsigned)yc * uw + (unsigned)x));
     };
     auto stage_row = [&](int buf, int rr) { return stage + ((buf * CH + rr) * 5) * COLS + tid; };
 
@@ -256,12 +261,15 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         if (reuse_b) W = Y;                                        // (select per thread: 10 predicated moves)
         ring_step(um_finish_rows(pb, W, Z, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
       };
-      float2 fa = flow_at(t_first), fb = flow_at(t_first + 1);
-      // warm-up: the R-1 = 2m rows above the first output row, chunk by chunk
+      float2 fa = flow_at(t_first, ups_row(t_first)), fb = flow_at(t_first + 1, ups_row(t_first + 1));
+      int2 ua = ups_row(t_first + 2), ub = ups_row(t_first + 3);      // table entries of the next chunk's rows
+      // warm-up: the R-1 = 2m rows above the first output row, chunk by chunk (unrolled for a compile-time radius: the
+      // rolled loop measured 3 % slower over a whole 1080p step)
       for (int t = t_first; t < t_first + R - 1; t += 2) {
         float V[5];
         issue2(fa, fb, t);
-        fa = flow_at(t + 2); fb = flow_at(t + 3);
+        fa = flow_at(t + 2, ua); fb = flow_at(t + 3, ub);
+        ua = ups_row(t + 4); ub = ups_row(t + 5);
         finish_a(t, V);
         finish_b(t + 1, V);
       }
@@ -269,7 +277,8 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
       for (int c = 0; c < n_chunks; c++) {
         const int tc = y0 + c * CH + m;                              // newest matrix row of output row y0 + c*CH
         issue2(fa, fb, tc);
-        fa = flow_at(tc + 2); fb = flow_at(tc + 3);
+        fa = flow_at(tc + 2, ua); fb = flow_at(tc + 3, ub);
+        ua = ups_row(tc + 4); ub = ups_row(tc + 5);
         if (c >= NBUF) named_bar_sync(BAR_EMPTY0 + buf, NT);         // consumers released this buffer
         float V[5];
         finish_a(tc, V);
@@ -309,13 +318,16 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         const int y = clampi(t, 0, h - 1);
         ring_step(um_finish2(L, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
       };
-      float2 fl = flow_at(t_first);
+      float2 fl = flow_at(t_first, ups_row(t_first));
+      int2 un = ups_row(t_first + 1);
       // warm-up: the R-1 rows above the first output row (no hand-over)
+#pragma unroll 1
       for (int t = t_first; t < t_first + R - 1; t++) {
         UmLoads2 L;
         float V[5];
         issue(L, fl, t);
-        fl = flow_at(t + 1);
+        fl = flow_at(t + 1, un);
+        un = ups_row(t + 2);
         finish(L, t, V);
       }
       int buf = 0;
@@ -328,7 +340,8 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
             UmLoads2 L;
             float V[5];
             issue(L, fl, yo + m);
-            fl = flow_at(yo + m + 1);
+            fl = flow_at(yo + m + 1, un);
+            un = ups_row(yo + m + 2);
             finish(L, yo + m, V);
             float* srow = stage_row(buf, rr);
 #pragma unroll

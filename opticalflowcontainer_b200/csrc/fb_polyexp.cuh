@@ -54,9 +54,18 @@ struct LevelColumn<0> {
   __device__ __forceinline__ float consume_fast(int, Raw r) { return r; }
 };
 
-// SRC = 1: uint8 source frame of the level's size; I = Gv * (Gh * float(src)), 3 taps, REFLECT_101.
-// Horizontally blurred rows tc-1, tc, tc+1 are kept while the row index advances by 0 or 1 per call;
-// the only new data a row needs is the source row below it.
+// SRC = 1: uint8 source frame of the level's size; I = Gv * (Gh * float(src)) with the fixed 3-tap kernel
+// [1/4, 1/2, 1/4] of the k = 0 level (sigma = 0), REFLECT_101.  Every product and sum of that blur is exact in float
+// (u8 values, weights 2^-1 / 2^-2), so it is computed in INTEGERS — h = a + 2b + c per row, I = (h- + 2 h0 + h+) / 16
+// — and converted once per pixel by dropping the 12-bit sum into the mantissa of 2^19 (whose last mantissa bit is worth
+// 2^-4): bit-identical to cv2's float arithmetic at 6 ALU instructions per pixel instead of 15.  Horizontally summed
+// rows tc-1, tc, tc+1 are kept while the row index advances by 0 or 1 per call; the only new data a row needs is the
+// source row below it.
+__device__ __forceinline__ unsigned ldg_u8(const uint8_t* p) {      // zero-extended into a 32-bit register: no mask
+  unsigned v;
+  asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 template <>
 struct LevelColumn<1> {
   struct Raw { unsigned a, b, c; };
@@ -64,27 +73,28 @@ struct LevelColumn<1> {
   size_t pitch;
   int xl, xc, xr, h;
   int tc;            // row the state is centred on
-  float k0, k1, hm, h0, hp, cur;
-  __device__ __forceinline__ void init(const uint8_t* frame, size_t pitch_, int xc_, int w, int h_, float k0_,
-                                       float k1_) {
+  unsigned hm, h0, hp;
+  float cur;
+  __device__ __forceinline__ void init(const uint8_t* frame, size_t pitch_, int xc_, int w, int h_, float, float) {
     base = frame;
     pitch = pitch_;
     xc = xc_;
     xl = reflect101(xc_ - 1, w);
     xr = reflect101(xc_ + 1, w);
     h = h_;
-    k0 = k0_;
-    k1 = k1_;
   }
   __device__ __forceinline__ Raw raw_row(int s) const {
     const uint8_t* p = base + (size_t)s * pitch;
     Raw r;
-    r.a = __ldg(p + xl);
-    r.b = __ldg(p + xc);
-    r.c = __ldg(p + xr);
+    r.a = ldg_u8(p + xl);
+    r.b = ldg_u8(p + xc);
+    r.c = ldg_u8(p + xr);
     return r;
   }
-  __device__ __forceinline__ float hval(Raw r) const { return fmaf(k1, u8f(r.a) + u8f(r.c), k0 * u8f(r.b)); }
+  __device__ __forceinline__ unsigned hval(Raw r) const { return r.a + 2u * r.b + r.c; }
+  __device__ __forceinline__ float blur() const {
+    return __uint_as_float(0x49000000u | (hm + 2u * h0 + hp)) - 524288.f;     // (sum <= 4080) / 16, exact
+  }
   // centre the state on the first row to be consumed (direct loads, once per segment)
   __device__ __forceinline__ void start(int t) {
     const int n = clampi(t, 0, h - 1);
@@ -92,7 +102,7 @@ struct LevelColumn<1> {
     hm = hval(raw_row(reflect101(n - 1, h)));
     hp = hval(raw_row(reflect101(n + 1, h)));
     tc = n;
-    cur = fmaf(k1, hm + hp, k0 * h0);
+    cur = blur();
   }
   __device__ __forceinline__ Raw load(int t) const { return raw_row(reflect101_once(clampi(t, 0, h - 1) + 1, h)); }
   // Fast path for interior rows (1 <= t, t + 1 <= h - 1) of interior columns: no clamp, no reflection,
@@ -101,9 +111,9 @@ struct LevelColumn<1> {
   __device__ __forceinline__ Raw load_fast(int t) const {
     const uint8_t* p = base + (size_t)(t + 1) * pitch + xc;
     Raw r;
-    r.a = __ldg(p - 1);
-    r.b = __ldg(p);
-    r.c = __ldg(p + 1);
+    r.a = ldg_u8(p - 1);
+    r.b = ldg_u8(p);
+    r.c = ldg_u8(p + 1);
     return r;
   }
   __device__ __forceinline__ float consume_fast(int t, Raw r) {   // t == tc + 1
@@ -111,7 +121,7 @@ struct LevelColumn<1> {
     h0 = hp;
     hp = hval(r);
     tc = t;
-    cur = fmaf(k1, hm + hp, k0 * h0);
+    cur = blur();
     return cur;
   }
   __device__ __forceinline__ float consume(int t, Raw r) {
@@ -121,7 +131,7 @@ struct LevelColumn<1> {
       h0 = hp;
       hp = hval(r);
       tc = n;
-      cur = fmaf(k1, hm + hp, k0 * h0);
+      cur = blur();
     }
     return cur;
   }

@@ -8,8 +8,14 @@
 // Integer stages (pyrDown, Scharr, the LK fixed-point patches) are bit-exact; the eigenvalue map
 // reproduces the wheel's optimized (FMA) float recipe bit for bit so that the corner ranking, and
 // therefore the corner list, is identical.
-#include <cub/device/device_radix_sort.cuh>
-
+//
+// Everything between the upload of a frame and the download of its results runs on the handle's stream
+// without a host round trip: candidate and corner counts stay on the device (kernels read them there,
+// grids are sized by capacity), and the candidates are ordered by a bucketed partial sort of our own
+// (k_candidates / k_bucket_scan / k_bucket_scatter + an in-CTA bitonic sort per selection round) — the
+// greedy selection stops at maxCorners, so only the strongest few thousand candidates are ever sorted.
+// ofb_lk_stream keeps a camera's temporal state (previous frame's pyramid, Scharr derivatives and corner
+// list) on the GPU: one upload per frame.
 #include <algorithm>
 
 #include "common.cuh"
@@ -20,21 +26,33 @@ namespace ofb {
 constexpr int kMaxLkLevels = 8;
 constexpr int kGridSlots = 4;
 
+constexpr int kLogBuckets = 16, kBuckets = 1 << kLogBuckets;   // value buckets of the candidate ordering
+
+// One frame of a camera: level 0 + the pyrDown chain + the Scharr derivatives of every level.
+struct FramePyr {
+  int n_levels = 0;
+  const uint8_t* lv[kMaxLkLevels] = {nullptr};
+  const short2* D[kMaxLkLevels] = {nullptr};
+  int w[kMaxLkLevels] = {0}, h[kMaxLkLevels] = {0};
+};
+
 struct SparseState {
   int cap_w = 0, cap_h = 0;
-  uint8_t* img[2] = {nullptr, nullptr};        // staged level-0 images (prev, next), packed pitch = width
+  uint8_t* img[2] = {nullptr, nullptr};        // level-0 images of the two frame slots, packed pitch = width
   uint8_t* pyr[2] = {nullptr, nullptr};        // levels 1.. of both pyramids, packed one after another
-  short2* deriv = nullptr;                     // Scharr (dx,dy) of every level of `prev`
+  short2* deriv[2] = {nullptr, nullptr};       // Scharr (dx,dy) of every level of a slot
   float* cov = nullptr;                        // 3 planes
   float* eig = nullptr;
-  unsigned long long* keys = nullptr;          // 2 x cand_cap (radix sort in/out)
-  size_t cand_cap = 0;
-  void* cub_tmp = nullptr;
-  size_t cub_tmp_bytes = 0;
-  unsigned int* counters = nullptr;            // [0] candidate count, [1] max(eig) bits, [2] corner count
+  unsigned long long* keys = nullptr;          // 2 x cand_cap: candidates as found | bucket order
+  unsigned long long* sortbuf = nullptr;       // power-of-two scratch of the oversized-bucket path
+  size_t cand_cap = 0, sort_cap = 0;
+  unsigned int* hist = nullptr;                // kBuckets: candidates per value bucket, then the scatter cursors
+  unsigned int* bstart = nullptr;              // kBuckets + 1: first position of every bucket, strongest bucket first
+  unsigned int* counters = nullptr;            // [0] candidate count, [1] max(eig) bits, [4 + slot] corner count of a slot
   unsigned int* grid_cnt = nullptr;            // per cell
   ushort2* grid_pts = nullptr;                 // per cell x kGridSlots
-  float2* corners = nullptr;                   // accepted corners (device)
+  float2* corners[2] = {nullptr, nullptr};     // accepted corners of a slot (device)
+  uint8_t* mask = nullptr;                     // goodFeaturesToTrack mask (device), allocated on first use
   float2* pts_prev = nullptr;                  // LK inputs / outputs (device)
   float2* pts_next = nullptr;
   uint8_t* lk_status = nullptr;
@@ -43,13 +61,23 @@ struct SparseState {
   // pinned host staging
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
+  // camera-stream state (ofb_lk_stream)
+  struct Stream {
+    bool primed = false;
+    int cur = 0, w = 0, h = 0;
+    ofb_gftt_params gp = {};
+    ofb_lk_params lp = {};
+    FramePyr fp[2];
+    int n_host[2] = {0, 0};                    // corner count of a slot as last downloaded
+    std::vector<float> host_corners[2];        // ... and the list itself (what the next call reports as prev_pts)
+  } st;
 };
 
 static void sparse_free(SparseState* s) {
   if (!s) return;
-  for (int i = 0; i < 2; i++) { cudaFree(s->img[i]); cudaFree(s->pyr[i]); }
-  cudaFree(s->deriv); cudaFree(s->cov); cudaFree(s->eig); cudaFree(s->keys); cudaFree(s->cub_tmp);
-  cudaFree(s->counters); cudaFree(s->grid_cnt); cudaFree(s->grid_pts); cudaFree(s->corners);
+  for (int i = 0; i < 2; i++) { cudaFree(s->img[i]); cudaFree(s->pyr[i]); cudaFree(s->deriv[i]); cudaFree(s->corners[i]); }
+  cudaFree(s->cov); cudaFree(s->eig); cudaFree(s->keys); cudaFree(s->sortbuf); cudaFree(s->hist); cudaFree(s->bstart);
+  cudaFree(s->counters); cudaFree(s->grid_cnt); cudaFree(s->grid_pts); cudaFree(s->mask);
   cudaFree(s->pts_prev); cudaFree(s->pts_next); cudaFree(s->lk_status); cudaFree(s->lk_err);
   if (s->h_stage) cudaFreeHost(s->h_stage);
   delete s;
@@ -79,21 +107,23 @@ static int sparse_get(ofb_handle* h, SparseState** out) {
     SP_CUDA(h, cudaMalloc(&s->img[i], N));
     SP_CUDA(h, cudaMalloc(&s->pyr[i], N));     // sum of levels >= 1 is < N/2 (+ rounding)
   }
-  SP_CUDA(h, cudaMalloc(&s->deriv, 2 * N * sizeof(short2)));
+  for (int i = 0; i < 2; i++) SP_CUDA(h, cudaMalloc(&s->deriv[i], 2 * N * sizeof(short2)));
   SP_CUDA(h, cudaMalloc(&s->cov, 3 * N * sizeof(float)));
   SP_CUDA(h, cudaMalloc(&s->eig, N * sizeof(float)));
   s->cand_cap = N / 2 + 1024;
   SP_CUDA(h, cudaMalloc(&s->keys, 2 * s->cand_cap * sizeof(unsigned long long)));
-  size_t tmp = 0;
-  cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp, s->keys, s->keys + s->cand_cap, (int)s->cand_cap);
-  s->cub_tmp_bytes = tmp;
-  SP_CUDA(h, cudaMalloc(&s->cub_tmp, tmp));
+  s->sort_cap = 1024;
+  while (s->sort_cap < s->cand_cap) s->sort_cap *= 2;
+  SP_CUDA(h, cudaMalloc(&s->sortbuf, s->sort_cap * sizeof(unsigned long long)));
+  SP_CUDA(h, cudaMalloc(&s->hist, kBuckets * sizeof(unsigned int)));
+  SP_CUDA(h, cudaMalloc(&s->bstart, (kBuckets + 1) * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->counters, 16 * sizeof(unsigned int)));
+  SP_CUDA(h, cudaMemset(s->counters, 0, 16 * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->grid_cnt, N * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->grid_pts, N * kGridSlots * sizeof(ushort2)));
   // the selection can keep every candidate (minDistance < 1, maxCorners <= 0): corner buffers sized like the candidate list
-  SP_CUDA(h, cudaMalloc(&s->corners, s->cand_cap * sizeof(float2)));
-  s->h_stage_bytes = std::max<size_t>(2 * N, s->cand_cap * sizeof(float2));
+  for (int i = 0; i < 2; i++) SP_CUDA(h, cudaMalloc(&s->corners[i], s->cand_cap * sizeof(float2)));
+  s->h_stage_bytes = std::max<size_t>(2 * N, s->cand_cap * sizeof(float2) + 64);
   SP_CUDA(h, cudaHostAlloc(&s->h_stage, s->h_stage_bytes, cudaHostAllocDefault));
   *out = s;
   return OFB_OK;
@@ -192,7 +222,8 @@ __global__ void __launch_bounds__(256) k_sobel_cov(const uint8_t* __restrict__ s
 // unnormalised blockSize^2 box sum in double (exact for these magnitudes), then
 // eig = (a + c) - sqrt((a - c)^2 + b^2), a = Sxx/2, c = Syy/2 — plain mul/add, no FMA.
 __global__ void __launch_bounds__(256) k_min_eig(const float* __restrict__ cov, int w, int h, int block_size,
-                                                 float* __restrict__ eig, unsigned int* __restrict__ max_bits) {
+                                                 float* __restrict__ eig, unsigned int* __restrict__ max_bits,
+                                                 const uint8_t* __restrict__ mask) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   float e = 0.f;
@@ -214,23 +245,49 @@ __global__ void __launch_bounds__(256) k_min_eig(const float* __restrict__ cov, 
     e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
     eig[(size_t)y * w + x] = e;
   }
-  // max over the image (minMaxLoc); the map is >= 0 up to rounding, a negative max means "no corners"
+  // max over the image — over the masked pixels with a mask — (minMaxLoc); the map is >= 0 up to rounding, a negative
+  // max means "no corners"
+  if (mask && x < w && y < h && mask[(size_t)y * w + x] == 0) e = 0.f;
   float m = fmaxf(e, 0.f);
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && m > 0.f) atomicMax(max_bits, __float_as_uint(m));
 }
 
-// threshold (THRESH_TOZERO at max*quality, strict >) + 3x3 local maximum, 1-px frame skipped.
-// Candidates are packed as (value bits << 32 | linear index): descending sort = value descending,
-// ties by DESCENDING address — cv2's greaterThanPtr.
+// Candidate ordering.  cv2 sorts all candidates (std::sort, value descending, ties by DESCENDING address) and walks the
+// sorted list until maxCorners are accepted.  Here a candidate is the 64-bit key (value bits << 32 | linear index) —
+// descending key order IS cv2's order — and only the part of the order the walk consumes is ever established:
+//   * k_candidates drops every candidate into one of 65536 VALUE buckets (order-preserving: positive floats compare
+//     like their bit patterns; bucket = (bits - threshold bits) >> shift) and counts the buckets;
+//   * k_bucket_scan turns the counts into bucket positions, strongest bucket first; k_bucket_scatter moves the keys
+//     there (unordered inside a bucket);
+//   * the selection kernel takes whole buckets, <= 1024 keys per round, and sorts a round in shared memory (bitonic).
+// No candidate count crosses to the host; a bucket larger than a round (many equal values: checkerboards) is sorted
+// by the CTA in global memory first.
+struct CandRange {
+  unsigned int thr_bits;
+  int shift;
+};
+__device__ __forceinline__ CandRange cand_range(unsigned int max_bits, double quality, float* thr_out) {
+  const float thr = (float)((double)__uint_as_float(max_bits) * quality);
+  *thr_out = thr;
+  CandRange r;
+  r.thr_bits = __float_as_uint(fmaxf(thr, 0.f));
+  const unsigned int range = max_bits > r.thr_bits ? max_bits - r.thr_bits : 1u;
+  r.shift = max(0, 32 - __clz(range) - kLogBuckets);
+  return r;
+}
+
+// threshold (THRESH_TOZERO at max*quality, strict >) + 3x3 local maximum, 1-px frame skipped, optional mask.
 __global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ eig, int w, int h, double quality,
                                                     const unsigned int* __restrict__ max_bits,
                                                     unsigned long long* __restrict__ keys, unsigned int* __restrict__ count,
-                                                    unsigned int cap) {
+                                                    unsigned int cap, unsigned int* __restrict__ hist,
+                                                    const uint8_t* __restrict__ mask) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (x >= w - 1 || y >= h - 1) return;
-  const float thr = (float)((double)__uint_as_float(*max_bits) * quality);
+  float thr;
+  const CandRange cr = cand_range(*max_bits, quality, &thr);
   const float v = eig[(size_t)y * w + x];
   if (!(v > thr)) return;
   float mx = v;
@@ -239,16 +296,71 @@ __global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ ei
 #pragma unroll
     for (int i = -1; i <= 1; i++) mx = fmaxf(mx, eig[(size_t)(y + j) * w + x + i]);
   if (v != mx) return;
+  if (mask && mask[(size_t)y * w + x] == 0) return;
   const unsigned int slot = atomicAdd(count, 1u);
-  if (slot < cap) keys[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * w + x);
+  if (slot < cap) {
+    keys[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * w + x);
+    atomicAdd(&hist[min((__float_as_uint(v) - cr.thr_bits) >> cr.shift, (unsigned int)kBuckets - 1u)], 1u);
+  }
 }
 
-// Greedy minimum-distance selection in sorted order (lexicographically-first maximal independent set), exactly
-// cv2's sequential rule, in rounds of 1024 candidates by one CTA:
-//   phase 1 (1024 threads): every candidate of the round is tested against the corners accepted in EARLIER rounds
-//            (grid of cell = cvRound(minDistance), +-1 cell); the survivors are compacted in rank order;
-//   phase 2 (1024 threads): the survivors decide among themselves by the parallel form of the same rule (see below)
-//            and the accepted ones are committed in rank order, up to the corner limit.
+// bstart[r] = first position of the r-th strongest bucket (r = kBuckets - 1 - bucket), bstart[kBuckets] = total;
+// the counts are cleared: the scatter uses them as cursors.
+__global__ void __launch_bounds__(1024) k_bucket_scan(unsigned int* __restrict__ hist, unsigned int* __restrict__ bstart) {
+  constexpr int PER = kBuckets / 1024;
+  __shared__ unsigned int wsum[32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  unsigned int sum = 0;
+  for (int j = 0; j < PER; j++) sum += hist[kBuckets - 1 - (t * PER + j)];
+  unsigned int inc = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned int v = wsum[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    wsum[lane] = v;
+  }
+  __syncthreads();
+  unsigned int run = inc - sum + (wid ? wsum[wid - 1] : 0u);
+  for (int j = 0; j < PER; j++) {
+    const int r = t * PER + j, b = kBuckets - 1 - r;
+    const unsigned int c = hist[b];
+    bstart[r] = run;
+    run += c;
+    hist[b] = 0;
+  }
+  if (t == 1023) bstart[kBuckets] = run;
+}
+
+__global__ void __launch_bounds__(256) k_bucket_scatter(const unsigned long long* __restrict__ keys,
+                                                        const unsigned int* __restrict__ count, unsigned int cap,
+                                                        double quality, const unsigned int* __restrict__ max_bits,
+                                                        unsigned int* __restrict__ cursor, const unsigned int* __restrict__ bstart,
+                                                        unsigned long long* __restrict__ out) {
+  const unsigned int n = min(*count, cap);
+  float thr;
+  const CandRange cr = cand_range(*max_bits, quality, &thr);
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    const unsigned int b = min(((unsigned int)(k >> 32) - cr.thr_bits) >> cr.shift, (unsigned int)kBuckets - 1u);
+    out[bstart[kBuckets - 1 - b] + atomicAdd(&cursor[b], 1u)] = k;
+  }
+}
+
+// Greedy minimum-distance selection in descending key order (lexicographically-first maximal independent set), exactly
+// cv2's sequential rule, in rounds of <= 1024 candidates by one CTA:
+//   fetch   : the next run of whole buckets (<= 1024 keys), sorted in shared memory;
+//   phase 1 : every candidate of the round is tested against the corners accepted in EARLIER rounds
+//             (grid of cell = cvRound(minDistance), +-1 cell); the survivors are compacted in rank order;
+//   phase 2 : the survivors decide among themselves by the parallel form of the same rule (see below)
+//             and the accepted ones are committed in rank order, up to the corner limit.
 constexpr int GS_THREADS = 1024;
 constexpr int GS_BUCKETS = 4096;
 
@@ -268,11 +380,29 @@ __device__ __forceinline__ bool gs_far_from_accepted(int x, int y, int cell, int
   return true;
 }
 
-__global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned long long* __restrict__ keys,
-                                                              const unsigned int* __restrict__ count_ptr, unsigned int cap,
+// descending bitonic sort of n = 2^k keys by the whole CTA; keys live in shared or global memory
+__device__ __forceinline__ void gs_bitonic_desc(unsigned long long* a, unsigned int n) {
+  for (unsigned int k = 2; k <= n; k <<= 1)
+    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned int i = threadIdx.x; i < n; i += GS_THREADS) {
+        const unsigned int p = i ^ j;
+        if (p > i) {
+          const unsigned long long u = a[i], v = a[p];
+          if (((i & k) == 0) ? (u < v) : (u > v)) { a[i] = v; a[p] = u; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned long long* __restrict__ bkeys,
+                                                              const unsigned int* __restrict__ bstart,
+                                                              unsigned long long* __restrict__ sortbuf,
                                                               int w, int h, float min_dist, int max_corners,
-                                                              unsigned int* grid_cnt, ushort2* grid_pts,
-                                                              float2* __restrict__ corners, unsigned int* __restrict__ n_out) {
+                                                              unsigned int corner_cap, unsigned int* grid_cnt,
+                                                              ushort2* grid_pts, float2* __restrict__ corners,
+                                                              unsigned int* __restrict__ n_out) {
+  __shared__ unsigned long long rk[GS_THREADS];      // the round's keys, descending
   __shared__ unsigned int surv[GS_THREADS];          // x | y << 16, rank order
   __shared__ unsigned int warp_cnt[GS_THREADS / 32];
   __shared__ unsigned int s_nsurv, s_accepted;
@@ -280,30 +410,75 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
   __shared__ unsigned short chain[GS_THREADS];
   __shared__ unsigned char state[GS_THREADS];        // 0 undecided, 1 accepted, 2 rejected
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned int total = min(*count_ptr, cap);
-  const unsigned int limit = max_corners > 0 ? (unsigned int)max_corners : 0xffffffffu;
-  if (min_dist < 1.f) {
-    const unsigned int n = min(total, limit);
-    for (unsigned int i = tid; i < n; i += GS_THREADS) {
-      const unsigned int idx = (unsigned int)(keys[i] & 0xffffffffu);
-      corners[i] = make_float2((float)(idx % w), (float)(idx / w));
-    }
-    if (tid == 0) *n_out = n;
-    return;
-  }
-  const int cell = __float2int_rn(min_dist);
+  const unsigned int total = bstart[kBuckets];
+  const unsigned int limit = min(max_corners > 0 ? (unsigned int)max_corners : 0xffffffffu, corner_cap);
+  const bool use_dist = min_dist >= 1.f;
+  const int cell = use_dist ? __float2int_rn(min_dist) : 1;
   const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
   const float md2 = min_dist * min_dist;
   if (tid == 0) s_accepted = 0;
   __syncthreads();
-  for (unsigned int base = 0; base < total; base += GS_THREADS) {
+  // walk state (uniform over the CTA): next bucket rank, next key position, keys left of an oversized bucket
+  unsigned int rb = 0, pos = 0, ov_left = 0, ov_pos = 0;
+  for (;;) {
     if (s_accepted >= limit) break;                  // (uniform: read after the barrier that ends a round)
+    // ---- fetch the next round
+    unsigned int nr = 0;
+    if (ov_left > 0) {
+      nr = min(ov_left, (unsigned int)GS_THREADS);
+      rk[tid] = (unsigned int)tid < nr ? sortbuf[ov_pos + tid] : 0ull;
+      ov_pos += nr;
+      ov_left -= nr;
+      __syncthreads();
+    } else {
+      if (pos >= total) break;
+      unsigned int rb_end = rb;
+      for (;;) {                                     // how many whole buckets fit into one round
+        const unsigned int probe = rb_end + 1 + tid;
+        const bool ok = probe <= (unsigned int)kBuckets && bstart[probe] - pos <= (unsigned int)GS_THREADS;
+        const unsigned int adv = (unsigned int)__syncthreads_count(ok);
+        rb_end += adv;
+        if (adv < (unsigned int)GS_THREADS || rb_end >= (unsigned int)kBuckets) break;
+      }
+      if (rb_end == rb) {
+        // the strongest remaining bucket alone is larger than a round: order it in global memory first
+        const unsigned int m_b = bstart[rb + 1] - pos;
+        unsigned int p2 = GS_THREADS;
+        while (p2 < m_b) p2 <<= 1;
+        for (unsigned int i = tid; i < p2; i += GS_THREADS) sortbuf[i] = i < m_b ? bkeys[pos + i] : 0ull;
+        __syncthreads();
+        gs_bitonic_desc(sortbuf, p2);
+        ov_left = m_b;
+        ov_pos = 0;
+        pos += m_b;
+        rb += 1;
+        continue;
+      }
+      nr = bstart[rb_end] - pos;
+      rk[tid] = (unsigned int)tid < nr ? bkeys[pos + tid] : 0ull;
+      pos += nr;
+      rb = rb_end;
+      __syncthreads();
+      if (nr > 1) gs_bitonic_desc(rk, GS_THREADS);
+    }
+    if (nr == 0) continue;
+    if (!use_dist) {
+      // minDistance < 1: every candidate is a corner, in order
+      const unsigned int o = s_accepted + tid;
+      if ((unsigned int)tid < nr && o < limit) {
+        const unsigned int idx = (unsigned int)(rk[tid] & 0xffffffffu);
+        corners[o] = make_float2((float)(idx % w), (float)(idx / w));
+      }
+      __syncthreads();
+      if (tid == 0) s_accepted = min(s_accepted + nr, limit);
+      __syncthreads();
+      continue;
+    }
     // ---- phase 1
-    const unsigned int i = base + tid;
-    bool alive = i < total;
+    bool alive = (unsigned int)tid < nr;
     int x = 0, y = 0;
     if (alive) {
-      const unsigned int idx = (unsigned int)(keys[i] & 0xffffffffu);
+      const unsigned int idx = (unsigned int)(rk[tid] & 0xffffffffu);
       x = idx % w;
       y = idx / w;
       alive = gs_far_from_accepted(x, y, cell, gw, gh, md2, grid_cnt, grid_pts);
@@ -333,8 +508,6 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
         state[tid] = 0;
       }
       __syncthreads();
-      // chain inserts in rank order by one warp per 32 survivors is not needed: chains are unordered, the rank test is
-      // explicit (j < i).  atomicExch on 32-bit words holding the 16-bit index.
       if ((unsigned int)tid < ns) {
         const unsigned int bk = ((unsigned int)(sy / cell) * 73u + (unsigned int)(sx / cell)) & (GS_BUCKETS - 1);
         chain[tid] = (unsigned short)atomicExch(&bucket[bk], (unsigned int)tid);
@@ -377,9 +550,9 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
         if (k < wid) before += warp_cnt[k];
         total_acc += warp_cnt[k];
       }
-      const unsigned int pos = s_accepted + before + __popc(bal2 & ((1u << lane) - 1u));
-      if (acc && pos < limit) {
-        corners[pos] = make_float2((float)sx, (float)sy);
+      const unsigned int o = s_accepted + before + __popc(bal2 & ((1u << lane) - 1u));
+      if (acc && o < limit) {
+        corners[o] = make_float2((float)sx, (float)sy);
         const int c = (sy / cell) * gw + (sx / cell);
         const unsigned int sl = atomicAdd(&grid_cnt[c], 1u);
         if (sl < (unsigned int)kGridSlots) grid_pts[c * kGridSlots + sl] = make_ushort2((unsigned short)sx, (unsigned short)sy);
@@ -439,12 +612,14 @@ constexpr int LK_WARPS = 4;
 
 __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const float2* __restrict__ prev_pts,
                                                             float2* __restrict__ next_pts, uint8_t* __restrict__ status,
-                                                            float* __restrict__ err, int n_points, int ww, int wh,
+                                                            float* __restrict__ err, int n_points,
+                                                            const unsigned int* __restrict__ n_dev, int ww, int wh,
                                                             int max_count, double eps2, int flags, double min_eig_thr) {
   extern __shared__ short lk_smem[];  // per warp: Iwin[area], dIx[area], dIy[area]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pid = blockIdx.x * LK_WARPS + warp;
-  if (pid >= n_points) return;
+  // n_dev: the point count is a device-side value (corner list of the previous frame); the grid covers n_points = its bound
+  if (pid >= (n_dev ? (int)min(*n_dev, (unsigned int)n_points) : n_points)) return;
   const int area = ww * wh;
   short* Iwin = lk_smem + (size_t)warp * 3 * area;
   short* dIx = Iwin + area;
@@ -587,6 +762,7 @@ static int upload_image(ofb_handle* h, SparseState* s, int which, const uint8_t*
   const uint8_t* from = host;
   size_t from_stride = stride;
   if (!pinned) {
+    SP_CUDA(h, cudaStreamSynchronize(h->stream));   // the staging half may still be read by the previous call's copy
     uint8_t* stg = reinterpret_cast<uint8_t*>(s->h_stage) + (size_t)which * width * height;
     for (int y = 0; y < height; y++) memcpy(stg + (size_t)y * width, host + (size_t)y * stride, width);
     from = stg;
@@ -596,41 +772,131 @@ static int upload_image(ofb_handle* h, SparseState* s, int which, const uint8_t*
   return OFB_OK;
 }
 
-// Builds levels 1.. of pyramid `which` (level 0 = s->img[which]); fills sizes; returns number of levels.
+// Builds levels 1.. of the pyramid of slot `which` (level 0 = s->img[which]) and, with `derivs`, the Scharr derivatives
+// of every level.
 static int build_pyr(ofb_handle* h, SparseState* s, int which, int width, int height, int win_w, int win_h,
-                     int max_level, const uint8_t** lv_ptr, int* lv_w, int* lv_h, int* n_levels) {
-  lv_ptr[0] = s->img[which];
-  lv_w[0] = width;
-  lv_h[0] = height;
+                     int max_level, bool derivs, FramePyr* fp) {
+  fp->lv[0] = s->img[which];
+  fp->w[0] = width;
+  fp->h[0] = height;
   int n = 1;
   uint8_t* next = s->pyr[which];
+  dim3 b(32, 8);
   for (int l = 1; l <= max_level && l < kMaxLkLevels; l++) {
-    const int ow = (lv_w[l - 1] + 1) / 2, oh = (lv_h[l - 1] + 1) / 2;
+    const int ow = (fp->w[l - 1] + 1) / 2, oh = (fp->h[l - 1] + 1) / 2;
     if (ow <= win_w || oh <= win_h) break;
-    dim3 b(32, 8);
-    k_pyrdown_u8<<<g2(ow, oh, b), b, 0, h->stream>>>(lv_ptr[l - 1], lv_w[l - 1], lv_h[l - 1], (size_t)lv_w[l - 1], next,
+    k_pyrdown_u8<<<g2(ow, oh, b), b, 0, h->stream>>>(fp->lv[l - 1], fp->w[l - 1], fp->h[l - 1], (size_t)fp->w[l - 1], next,
                                                      ow, oh);
     OFB_LAUNCH_CHECK(h);
-    lv_ptr[l] = next;
-    lv_w[l] = ow;
-    lv_h[l] = oh;
+    fp->lv[l] = next;
+    fp->w[l] = ow;
+    fp->h[l] = oh;
     next += (size_t)ow * oh;
     n++;
   }
-  *n_levels = n;
+  fp->n_levels = n;
+  short2* d = s->deriv[which];
+  for (int l = 0; l < n; l++) {
+    fp->D[l] = nullptr;
+    if (!derivs) continue;
+    k_scharr<<<g2(fp->w[l], fp->h[l], b), b, 0, h->stream>>>(fp->lv[l], fp->w[l], fp->h[l], (size_t)fp->w[l], d);
+    OFB_LAUNCH_CHECK(h);
+    fp->D[l] = d;
+    d += (size_t)fp->w[l] * fp->h[l];
+  }
   return OFB_OK;
 }
 
-static int eigen_map(ofb_handle* h, SparseState* s, int width, int height, int block_size) {
+static int eigen_map(ofb_handle* h, SparseState* s, int which, int width, int height, int block_size,
+                     const uint8_t* d_mask) {
   const double scale = 1.0 / (4.0 * block_size * 255.0);
   const float k0 = (float)(1.0 * scale), k1 = (float)(2.0 * scale), k2 = (float)(1.0 * scale);
   dim3 b(32, 8);
-  SP_CUDA(h, cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned int), h->stream));
-  k_sobel_cov<<<g2(width, height, b), b, 0, h->stream>>>(s->img[0], width, height, (size_t)width, s->cov, k0, k1, k2,
+  SP_CUDA(h, cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned int), h->stream));
+  // columns past the last full block of 32 take the row filter's scalar tail (no FMA): the same on the AVX2 and the
+  // AVX-512 dispatch of the wheel (tests/test_oracle_sparse.py probes both with OPENCV_CPU_DISABLE)
+  k_sobel_cov<<<g2(width, height, b), b, 0, h->stream>>>(s->img[which], width, height, (size_t)width, s->cov, k0, k1, k2,
                                                          (width / 32) * 32);
   OFB_LAUNCH_CHECK(h);
-  k_min_eig<<<g2(width, height, b), b, 0, h->stream>>>(s->cov, width, height, block_size, s->eig, s->counters + 1);
+  k_min_eig<<<g2(width, height, b), b, 0, h->stream>>>(s->cov, width, height, block_size, s->eig, s->counters + 1, d_mask);
   OFB_LAUNCH_CHECK(h);
+  return OFB_OK;
+}
+
+static int validate_gftt(ofb_handle* h, const ofb_gftt_params* p, int width, int height) {
+  if (!(p->quality_level > 0) || p->min_distance < 0)
+    return set_error(h, OFB_ERR_INVALID_ARG, "qualityLevel must be > 0 and minDistance >= 0");
+  if (p->block_size < 1 || p->block_size % 2 == 0 || p->block_size > 31)
+    return set_error(h, OFB_ERR_INVALID_ARG, "blockSize must be odd and in [1,31]");
+  if (width > 65535 || height > 65535) return set_error(h, OFB_ERR_INVALID_ARG, "image larger than 65535 px");
+  return OFB_OK;
+}
+
+// goodFeaturesToTrack of the image in slot `which`; the list lands in s->corners[which], its length in
+// s->counters[4 + which] — both on the device, nothing is synchronised.
+static int detect_corners(ofb_handle* h, SparseState* s, int which, int width, int height, const ofb_gftt_params* p,
+                          const uint8_t* d_mask) {
+  cudaStream_t sm = h->stream;
+  int st = eigen_map(h, s, which, width, height, p->block_size, d_mask);
+  if (st) return st;
+  SP_CUDA(h, cudaMemsetAsync(s->hist, 0, kBuckets * sizeof(unsigned int), sm));
+  dim3 b(32, 8);
+  k_candidates<<<g2(width - 2, height - 2, b), b, 0, sm>>>(s->eig, width, height, p->quality_level, s->counters + 1,
+                                                          s->keys, s->counters, (unsigned int)s->cand_cap, s->hist, d_mask);
+  OFB_LAUNCH_CHECK(h);
+  k_bucket_scan<<<1, 1024, 0, sm>>>(s->hist, s->bstart);
+  OFB_LAUNCH_CHECK(h);
+  k_bucket_scatter<<<2 * h->num_sms, 256, 0, sm>>>(s->keys, s->counters, (unsigned int)s->cand_cap, p->quality_level,
+                                                   s->counters + 1, s->hist, s->bstart, s->keys + s->cand_cap);
+  OFB_LAUNCH_CHECK(h);
+  const int cell = p->min_distance >= 1 ? (int)__builtin_nearbyint(p->min_distance) : 1;
+  const size_t cells = (size_t)((width + cell - 1) / cell) * ((height + cell - 1) / cell);
+  if (p->min_distance >= 1) SP_CUDA(h, cudaMemsetAsync(s->grid_cnt, 0, cells * sizeof(unsigned int), sm));
+  k_greedy_select<<<1, GS_THREADS, 0, sm>>>(s->keys + s->cand_cap, s->bstart, s->sortbuf, width, height,
+                                            (float)p->min_distance, p->max_corners, (unsigned int)s->cand_cap, s->grid_cnt,
+                                            s->grid_pts, s->corners[which], s->counters + 4 + which);
+  OFB_LAUNCH_CHECK(h);
+  return OFB_OK;
+}
+
+static int upload_mask(ofb_handle* h, SparseState* s, const uint8_t* mask, int width, int height, size_t stride,
+                       const uint8_t** d_mask) {
+  *d_mask = nullptr;
+  if (!mask) return OFB_OK;
+  if (stride == 0) stride = width;
+  if (stride < (size_t)width) return set_error(h, OFB_ERR_INVALID_ARG, "mask stride smaller than width");
+  if (!s->mask) SP_CUDA(h, cudaMalloc(&s->mask, (size_t)s->cap_w * s->cap_h));
+  SP_CUDA(h, cudaMemcpy2DAsync(s->mask, width, mask, stride, width, height, cudaMemcpyHostToDevice, h->stream));
+  *d_mask = s->mask;
+  return OFB_OK;
+}
+
+static int lk_launch(ofb_handle* h, SparseState* s, const FramePyr& I, const FramePyr& J, int width, const float2* d_prev,
+                     int n_bound, const unsigned int* n_dev, const ofb_lk_params* p) {
+  LkLevels lv;
+  lv.n_levels = I.n_levels;
+  lv.pitch0 = (size_t)width;
+  for (int l = 0; l < I.n_levels; l++) {
+    lv.I[l] = I.lv[l]; lv.J[l] = J.lv[l]; lv.D[l] = I.D[l]; lv.w[l] = I.w[l]; lv.h[l] = I.h[l];
+  }
+  const int max_count = std::min(std::max(p->max_count, 0), 100);
+  double eps = std::min(std::max(p->epsilon, 0.0), 10.0);
+  eps *= eps;
+  const size_t smem = (size_t)p->win_w * p->win_h * 3 * sizeof(short) * LK_WARPS;
+  if (smem > 48 * 1024)
+    OFB_CUDA(h, cudaFuncSetAttribute(k_lk_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_lk_track<<<(n_bound + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, smem, h->stream>>>(
+      lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound, n_dev, p->win_w, p->win_h, max_count, eps, p->flags,
+      p->min_eig_threshold);
+  OFB_LAUNCH_CHECK(h);
+  return OFB_OK;
+}
+
+static int validate_lk(ofb_handle* h, const ofb_lk_params* p) {
+  if (p->win_w <= 2 || p->win_h <= 2) return set_error(h, OFB_ERR_INVALID_ARG, "winSize must be > 2x2");
+  if (p->max_level < 0) return set_error(h, OFB_ERR_INVALID_ARG, "maxLevel must be >= 0");
+  if ((size_t)p->win_w * p->win_h * 3 * sizeof(short) * LK_WARPS > 200 * 1024)
+    return set_error(h, OFB_ERR_INVALID_ARG, "winSize too large");
   return OFB_OK;
 }
 
@@ -650,68 +916,54 @@ int ofb_corner_min_eigenval(ofb_handle* h, const uint8_t* image, int width, int 
   SparseState* s;
   int st = sparse_get(h, &s);
   if (st) return st;
+  s->st.primed = false;
   if ((st = upload_image(h, s, 0, image, width, height, stride_bytes))) return st;
-  if ((st = eigen_map(h, s, width, height, block_size))) return st;
+  if ((st = eigen_map(h, s, 0, width, height, block_size, nullptr))) return st;
   OFB_CUDA(h, cudaMemcpyAsync(eig_out, s->eig, (size_t)width * height * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
   return OFB_OK;
 }
 
-int ofb_good_features(ofb_handle* h, const uint8_t* image, int width, int height, size_t stride_bytes,
-                      const ofb_gftt_params* p, float* corners_xy, int* n_out) {
+int ofb_good_features_masked(ofb_handle* h, const uint8_t* image, int width, int height, size_t stride_bytes,
+                             const uint8_t* mask, size_t mask_stride_bytes, const ofb_gftt_params* p,
+                             float* corners_xy, int* n_out) {
   if (!h) return OFB_ERR_INVALID_ARG;
   if (!image || !p || !corners_xy || !n_out) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
-  if (!(p->quality_level > 0) || p->min_distance < 0)
-    return set_error(h, OFB_ERR_INVALID_ARG, "qualityLevel must be > 0 and minDistance >= 0");
-  if (p->block_size < 1 || p->block_size % 2 == 0 || p->block_size > 31)
-    return set_error(h, OFB_ERR_INVALID_ARG, "blockSize must be odd and in [1,31]");
-  if (width > 65535 || height > 65535) return set_error(h, OFB_ERR_INVALID_ARG, "image larger than 65535 px");
+  int st = validate_gftt(h, p, width, height);
+  if (st) return st;
   if (width < 3 || height < 3) {     // no interior pixel: cv2 returns an empty list
     *n_out = 0;
     return OFB_OK;
   }
   OFB_CUDA(h, cudaSetDevice(h->device));
   SparseState* s;
-  int st = sparse_get(h, &s);
-  if (st) return st;
+  if ((st = sparse_get(h, &s))) return st;
+  s->st.primed = false;
   if ((st = upload_image(h, s, 0, image, width, height, stride_bytes))) return st;
-  if ((st = eigen_map(h, s, width, height, p->block_size))) return st;
+  const uint8_t* d_mask;
+  if ((st = upload_mask(h, s, mask, width, height, mask_stride_bytes, &d_mask))) return st;
+  if ((st = detect_corners(h, s, 0, width, height, p, d_mask))) return st;
   cudaStream_t sm = h->stream;
-  dim3 b(32, 8);
-  k_candidates<<<g2(width - 2, height - 2, b), b, 0, sm>>>(s->eig, width, height, p->quality_level, s->counters + 1,
-                                                          s->keys, s->counters, (unsigned int)s->cand_cap);
-  OFB_LAUNCH_CHECK(h);
-  // the candidate count is needed on the host to size the sort (a 4-byte D2H)
   unsigned int* hc = reinterpret_cast<unsigned int*>(s->h_stage);
-  OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters, sizeof(unsigned int), cudaMemcpyDeviceToHost, sm));
-  OFB_CUDA(h, cudaStreamSynchronize(sm));
-  const unsigned int n_cand = std::min<unsigned int>(hc[0], (unsigned int)s->cand_cap);
-  const unsigned long long* sorted = s->keys;
-  if (n_cand > 1) {
-    size_t tmp = s->cub_tmp_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortKeysDescending(s->cub_tmp, tmp, s->keys, s->keys + s->cand_cap, (int)n_cand,
-                                                             0, 64, sm);
-    if (e != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(e));
-    h->launches += 4;
-    sorted = s->keys + s->cand_cap;
-  }
-  const int cell = p->min_distance >= 1 ? (int)__builtin_nearbyint(p->min_distance) : 1;
-  const size_t cells = (size_t)((width + cell - 1) / cell) * ((height + cell - 1) / cell);
-  if (p->min_distance >= 1) OFB_CUDA(h, cudaMemsetAsync(s->grid_cnt, 0, cells * sizeof(unsigned int), sm));
-  k_greedy_select<<<1, GS_THREADS, 0, sm>>>(sorted, s->counters, (unsigned int)s->cand_cap, width, height, (float)p->min_distance,
-                                    p->max_corners, s->grid_cnt, s->grid_pts, s->corners, s->counters + 2);
-  OFB_LAUNCH_CHECK(h);
-  OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, sm));
+  float* hp = reinterpret_cast<float*>(reinterpret_cast<char*>(s->h_stage) + 64);
+  OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters + 4, sizeof(unsigned int), cudaMemcpyDeviceToHost, sm));
+  // a bounded list comes back with its count in ONE synchronisation; an unbounded one (maxCorners <= 0) needs the count first
+  const size_t bound = p->max_corners > 0 ? std::min<size_t>((size_t)p->max_corners, s->cand_cap) : 0;
+  if (bound) OFB_CUDA(h, cudaMemcpyAsync(hp, s->corners[0], bound * sizeof(float2), cudaMemcpyDeviceToHost, sm));
   OFB_CUDA(h, cudaStreamSynchronize(sm));
   const unsigned int n = hc[0];
-  if (n) {
-    float* hp = reinterpret_cast<float*>(s->h_stage);
-    OFB_CUDA(h, cudaMemcpyAsync(hp, s->corners, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, sm));
+  if (n && !bound) {
+    OFB_CUDA(h, cudaMemcpyAsync(hp, s->corners[0], (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, sm));
     OFB_CUDA(h, cudaStreamSynchronize(sm));
-    memcpy(corners_xy, hp, (size_t)n * sizeof(float2));
   }
+  if (n) memcpy(corners_xy, hp, (size_t)n * sizeof(float2));
   *n_out = (int)n;
   return OFB_OK;
+}
+
+int ofb_good_features(ofb_handle* h, const uint8_t* image, int width, int height, size_t stride_bytes,
+                      const ofb_gftt_params* p, float* corners_xy, int* n_out) {
+  return ofb_good_features_masked(h, image, width, height, stride_bytes, nullptr, 0, p, corners_xy, n_out);
 }
 
 int ofb_lk_pyramid(ofb_handle* h, const uint8_t* image, int width, int height, size_t stride_bytes, int win_w,
@@ -723,25 +975,19 @@ int ofb_lk_pyramid(ofb_handle* h, const uint8_t* image, int width, int height, s
   SparseState* s;
   int st = sparse_get(h, &s);
   if (st) return st;
+  s->st.primed = false;
   if ((st = upload_image(h, s, 0, image, width, height, stride_bytes))) return st;
-  const uint8_t* lp[kMaxLkLevels];
-  int lw[kMaxLkLevels], lh[kMaxLkLevels], nl = 0;
-  if ((st = build_pyr(h, s, 0, width, height, win_w, win_h, max_level, lp, lw, lh, &nl))) return st;
-  short2* d = s->deriv;
-  for (int l = 0; l < nl; l++) {
+  FramePyr fp;
+  if ((st = build_pyr(h, s, 0, width, height, win_w, win_h, max_level, deriv_out != nullptr, &fp))) return st;
+  for (int l = 0; l < fp.n_levels; l++) {
     if (level_out && level_out[l])
-      OFB_CUDA(h, cudaMemcpyAsync(level_out[l], lp[l], (size_t)lw[l] * lh[l], cudaMemcpyDeviceToHost, h->stream));
-    if (deriv_out && deriv_out[l]) {
-      dim3 b(32, 8);
-      k_scharr<<<g2(lw[l], lh[l], b), b, 0, h->stream>>>(lp[l], lw[l], lh[l], (size_t)lw[l], d);
-      OFB_LAUNCH_CHECK(h);
-      OFB_CUDA(h, cudaMemcpyAsync(deriv_out[l], d, (size_t)lw[l] * lh[l] * sizeof(short2), cudaMemcpyDeviceToHost,
+      OFB_CUDA(h, cudaMemcpyAsync(level_out[l], fp.lv[l], (size_t)fp.w[l] * fp.h[l], cudaMemcpyDeviceToHost, h->stream));
+    if (deriv_out && deriv_out[l])
+      OFB_CUDA(h, cudaMemcpyAsync(deriv_out[l], fp.D[l], (size_t)fp.w[l] * fp.h[l] * sizeof(short2), cudaMemcpyDeviceToHost,
                                   h->stream));
-      d += (size_t)lw[l] * lh[l];
-    }
   }
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  *n_levels_out = nl;
+  *n_levels_out = fp.n_levels;
   return OFB_OK;
 }
 
@@ -752,51 +998,106 @@ int ofb_pyrlk(ofb_handle* h, const uint8_t* prev, const uint8_t* next, int width
   if (!prev || !next || !p || !status || !next_pts || (!prev_pts && n_points > 0))
     return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
   if (n_points < 0) return set_error(h, OFB_ERR_INVALID_ARG, "negative point count");
-  if (p->win_w <= 2 || p->win_h <= 2) return set_error(h, OFB_ERR_INVALID_ARG, "winSize must be > 2x2");
-  if (p->max_level < 0) return set_error(h, OFB_ERR_INVALID_ARG, "maxLevel must be >= 0");
-  if ((size_t)p->win_w * p->win_h * 3 * sizeof(short) * LK_WARPS > 200 * 1024)
-    return set_error(h, OFB_ERR_INVALID_ARG, "winSize too large");
+  int st = validate_lk(h, p);
+  if (st) return st;
   if (n_points == 0) return OFB_OK;
   OFB_CUDA(h, cudaSetDevice(h->device));
   SparseState* s;
-  int st = sparse_get(h, &s);
-  if (st) return st;
+  if ((st = sparse_get(h, &s))) return st;
+  s->st.primed = false;
   if ((st = sparse_points(h, s, n_points))) return st;
   if ((st = upload_image(h, s, 0, prev, width, height, stride_bytes))) return st;
   if ((st = upload_image(h, s, 1, next, width, height, stride_bytes))) return st;
   cudaStream_t sm = h->stream;
-  LkLevels lv;
-  int nl0 = 0, nl1 = 0;
-  if ((st = build_pyr(h, s, 0, width, height, p->win_w, p->win_h, p->max_level, lv.I, lv.w, lv.h, &nl0))) return st;
-  int w2[kMaxLkLevels], h2[kMaxLkLevels];
-  if ((st = build_pyr(h, s, 1, width, height, p->win_w, p->win_h, p->max_level, lv.J, w2, h2, &nl1))) return st;
-  lv.n_levels = nl0;
-  lv.pitch0 = (size_t)width;
-  short2* d = s->deriv;
-  for (int l = 0; l < nl0; l++) {
-    dim3 b(32, 8);
-    k_scharr<<<g2(lv.w[l], lv.h[l], b), b, 0, sm>>>(lv.I[l], lv.w[l], lv.h[l], (size_t)lv.w[l], d);
-    OFB_LAUNCH_CHECK(h);
-    lv.D[l] = d;
-    d += (size_t)lv.w[l] * lv.h[l];
-  }
+  FramePyr fi, fj;
+  if ((st = build_pyr(h, s, 0, width, height, p->win_w, p->win_h, p->max_level, true, &fi))) return st;
+  if ((st = build_pyr(h, s, 1, width, height, p->win_w, p->win_h, p->max_level, false, &fj))) return st;
   OFB_CUDA(h, cudaMemcpyAsync(s->pts_prev, prev_pts, (size_t)n_points * sizeof(float2), cudaMemcpyHostToDevice, sm));
   if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
     OFB_CUDA(h, cudaMemcpyAsync(s->pts_next, next_pts, (size_t)n_points * sizeof(float2), cudaMemcpyHostToDevice, sm));
-  const int max_count = std::min(std::max(p->max_count, 0), 100);
-  double eps = std::min(std::max(p->epsilon, 0.0), 10.0);
-  eps *= eps;
-  const size_t smem = (size_t)p->win_w * p->win_h * 3 * sizeof(short) * LK_WARPS;
-  if (smem > 48 * 1024)
-    OFB_CUDA(h, cudaFuncSetAttribute(k_lk_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_lk_track<<<(n_points + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, smem, sm>>>(
-      lv, s->pts_prev, s->pts_next, s->lk_status, s->lk_err, n_points, p->win_w, p->win_h, max_count, eps, p->flags,
-      p->min_eig_threshold);
-  OFB_LAUNCH_CHECK(h);
+  if ((st = lk_launch(h, s, fi, fj, width, s->pts_prev, n_points, nullptr, p))) return st;
   OFB_CUDA(h, cudaMemcpyAsync(next_pts, s->pts_next, (size_t)n_points * sizeof(float2), cudaMemcpyDeviceToHost, sm));
   OFB_CUDA(h, cudaMemcpyAsync(status, s->lk_status, (size_t)n_points, cudaMemcpyDeviceToHost, sm));
   if (err) OFB_CUDA(h, cudaMemcpyAsync(err, s->lk_err, (size_t)n_points * sizeof(float), cudaMemcpyDeviceToHost, sm));
   OFB_CUDA(h, cudaStreamSynchronize(sm));
+  return OFB_OK;
+}
+
+// Camera-stream form of the sparse path: one new frame per call, the temporal state stays on the GPU.
+//   call t:  upload frame t (ONE copy) -> pyramid of t -> track the corners of frame t-1 (their list, the pyramid and the
+//            Scharr derivatives of t-1 are on the device) into t -> Scharr derivatives of t -> corners of t for the next
+//            call -> ONE download (counts, tracked points, status, error, the new corner list) -> ONE synchronisation.
+// Same kernels and arguments as ofb_good_features(t-1) followed by ofb_pyrlk(t-1, t, corners): identical bits.
+int ofb_lk_stream(ofb_handle* h, const uint8_t* frame, int width, int height, size_t stride_bytes,
+                  const ofb_gftt_params* gp, const ofb_lk_params* lp, float* prev_pts, float* next_pts, uint8_t* status,
+                  float* err, int* n_tracked, float* new_corners, int* n_new) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!frame || !gp || !lp || !n_tracked) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  *n_tracked = -1;
+  if (n_new) *n_new = 0;
+  int st = validate_gftt(h, gp, width, height);
+  if (st) return st;
+  if ((st = validate_lk(h, lp))) return st;
+  if (gp->max_corners <= 0) return set_error(h, OFB_ERR_INVALID_ARG, "the stream call needs maxCorners > 0 (fixed-size result buffers)");
+  if (lp->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
+    return set_error(h, OFB_ERR_INVALID_ARG, "USE_INITIAL_FLOW is not supported by the stream call");
+  if (width < 3 || height < 3) return set_error(h, OFB_ERR_INVALID_ARG, "image must be at least 3x3");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  SparseState* s;
+  if ((st = sparse_get(h, &s))) return st;
+  const int bound = (int)std::min<size_t>((size_t)gp->max_corners, s->cand_cap);
+  if ((st = sparse_points(h, s, bound))) return st;
+  SparseState::Stream& S = s->st;
+  const bool same = S.primed && S.w == width && S.h == height && memcmp(&S.gp, gp, sizeof(*gp)) == 0 &&
+                    memcmp(&S.lp, lp, sizeof(*lp)) == 0;
+  if (!same) S.primed = false;
+  const int cur = S.primed ? (S.cur ^ 1) : 0, prv = cur ^ 1;
+  cudaStream_t sm = h->stream;
+  if ((st = upload_image(h, s, cur, frame, width, height, stride_bytes))) { S.primed = false; return st; }
+  // pyramid of the new frame, and its Scharr derivatives for the call in which it is the previous frame
+  if ((st = build_pyr(h, s, cur, width, height, lp->win_w, lp->win_h, lp->max_level, true, &S.fp[cur]))) { S.primed = false; return st; }
+  // result block in pinned memory: [count prev, count cur | next pts | err | new corners | status]
+  char* hb = reinterpret_cast<char*>(s->h_stage);
+  const size_t need = 64 + (size_t)bound * (8 + 4 + 8 + 1);
+  if (need > s->h_stage_bytes) { S.primed = false; return set_error(h, OFB_ERR_CAPACITY, "maxCorners exceeds the staging capacity"); }
+  unsigned int* hc = reinterpret_cast<unsigned int*>(hb);
+  float* h_next = reinterpret_cast<float*>(hb + 64);
+  float* h_err = h_next + 2 * (size_t)bound;
+  float* h_new = h_err + bound;
+  uint8_t* h_status = reinterpret_cast<uint8_t*>(h_new + 2 * (size_t)bound);
+  const bool track = S.primed;
+  if (track) {
+    if ((st = lk_launch(h, s, S.fp[prv], S.fp[cur], width, s->corners[prv], bound, s->counters + 4 + prv, lp))) { S.primed = false; return st; }
+    OFB_CUDA(h, cudaMemcpyAsync(h_next, s->pts_next, (size_t)bound * sizeof(float2), cudaMemcpyDeviceToHost, sm));
+    OFB_CUDA(h, cudaMemcpyAsync(h_status, s->lk_status, (size_t)bound, cudaMemcpyDeviceToHost, sm));
+    OFB_CUDA(h, cudaMemcpyAsync(h_err, s->lk_err, (size_t)bound * sizeof(float), cudaMemcpyDeviceToHost, sm));
+  }
+  if ((st = detect_corners(h, s, cur, width, height, gp, nullptr))) { S.primed = false; return st; }
+  OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters + 4, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sm));
+  OFB_CUDA(h, cudaMemcpyAsync(h_new, s->corners[cur], (size_t)bound * sizeof(float2), cudaMemcpyDeviceToHost, sm));
+  OFB_CUDA(h, cudaStreamSynchronize(sm));
+  const int n_cur = (int)std::min<unsigned int>(hc[cur], (unsigned int)bound);
+  if (track) {
+    const int n_prev = S.n_host[prv];
+    if (prev_pts) memcpy(prev_pts, S.host_corners[prv].data(), (size_t)n_prev * sizeof(float2));
+    if (next_pts) memcpy(next_pts, h_next, (size_t)n_prev * sizeof(float2));
+    if (status) memcpy(status, h_status, (size_t)n_prev);
+    if (err) memcpy(err, h_err, (size_t)n_prev * sizeof(float));
+    *n_tracked = n_prev;
+  }
+  S.host_corners[cur].assign(h_new, h_new + 2 * (size_t)n_cur);
+  S.n_host[cur] = n_cur;
+  if (new_corners) memcpy(new_corners, h_new, (size_t)n_cur * sizeof(float2));
+  if (n_new) *n_new = n_cur;
+  S.cur = cur;
+  S.w = width; S.h = height; S.gp = *gp; S.lp = *lp;
+  S.primed = true;
+  return OFB_OK;
+}
+
+int ofb_lk_stream_reset(ofb_handle* h) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (h->sparse) reinterpret_cast<SparseState*>(h->sparse)->st.primed = false;
   return OFB_OK;
 }
 

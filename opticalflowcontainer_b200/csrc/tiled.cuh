@@ -1,20 +1,21 @@
 // tiled.cuh — spatially tiled Farneback: ONE frame pair split into row strips over the GPUs of a node
 // (BASELINE.json config 5: 7680x4320 over 8 B200).  Included by farneback.cu.
 //
-// Every rank (one process and one ofb_handle per GPU) holds full-size level buffers but computes only
-// the level rows it owns, rank r -> [r*rpr, min((r+1)*rpr, h_l)), rpr = ceil(h_l / world):
-//   * pyramid + PolyExp of the own rows are local (each rank has the source frames; the level image
-//     is produced for the own rows +- poly_n, nothing is exchanged);
-//   * the fused iteration kernel needs, besides the own rows, R0 and the flow of the 2m halo rows of the
-//     blur window and R1 wherever the displacement points.  It reads them where they live: through
-//     NVLink peer pointers into the neighbours' buffers (k_iter_v<..., TILED>, um_issue2_tiled) — the
-//     halo exchange is the kernel's own loads, overlapped tile by tile with the arithmetic, there is
-//     no staging copy and no NCCL call on the data path;
-//   * the inter-level flow upsample reads the coarse rows it needs the same way.
-// What has to be ordered across GPUs is "all ranks finished stage s" before anyone reads a neighbour's
-// rows in stage s+1: a flag barrier in peer memory (k_tile_barrier: every rank stores its epoch into
-// every peer's flag array and spins until all peers' epochs arrived, with a timeout) enqueued on the
-// stream between stages — 4 per level, no host round trip.
+// Every rank (one process and one ofb_handle per GPU) produces the rows of the final field it owns,
+// rank r -> [r*rpr, min((r+1)*rpr, H)), rpr = ceil(H / world), and works on INDEPENDENT BANDS:
+//   * what a rank needs from its neighbours at a level is a halo of the input flow (the blur window, m rows per
+//     iteration) and of the expansions.  Instead of exchanging halos every iteration (round 1: 17 cross-GPU barriers
+//     and 15 halo pulls per pair, 0.78 of 1.24 ms on 8 GPUs) a rank RECOMPUTES them: the band it computes at a
+//     level is widened so that after `iterations` shrinking steps of m rows the rows the next finer level needs are
+//     still valid (need_l, derived top-down from the rows the rank owns at level 0).  Every rank holds the two source
+//     frames, so pyramid and PolyExp of the wider band are local.  Redundant work at 8K over 8 GPUs: +8 % at level
+//     0, +24 % at level 1, more at the two small levels — about +15 % in all — for NO flow exchange at all;
+//   * the inter-level upsample is fused into the first iteration of a level (UpsSrc), reading the rank's own coarse band;
+//   * the only cross-rank access left is the bilinear gather of R1 where the displacement points more than
+//     kTileGatherMargin rows outside the rank's band: a peer-pointer load over NVLink from the rank that owns the row.
+//     It needs that rank's PolyExp of the level to be complete: ONE flag barrier in peer memory per level
+//     (k_tile_barrier, enqueued on the stream — no host round trip, no NCCL on the data path).  The expansions of
+//     every level have their own buffer, so no other ordering is needed, not even between consecutive pairs.
 //
 // With fewer GPUs than ranks (tests on one GPU) the ranks are emulated in ONE process: the stages of
 // all ranks are launched in order on one device with a device synchronisation in between, and no
@@ -48,51 +49,6 @@ __global__ void k_tile_barrier(volatile unsigned* my_flags, PeerFlags peers, int
   __threadfence_system();
 }
 
-// Halo pull: copies the level rows [lo, yb) and [ye, hi) of a row-major buffer from their owners into this
-// rank's buffer (same offsets), 16 bytes per thread, so that the compute kernel that follows finds the
-// blur halo (and a margin for the displacement) locally.  One bulk NVLink transfer per stage instead of
-// a remote round trip per halo row inside the marching producers (measured: the rank below a boundary
-// ran its iteration kernels 44 % slower without it).
-struct PullSrc {
-  const uint4* p[kMaxTileRanks];
-};
-__global__ void __launch_bounds__(256) k_tile_pull(uint4* __restrict__ dst, PullSrc src, int rpr, int world,
-                                                   int row_vec, int lo, int yb, int ye, int hi, size_t frame_vec) {
-  // grid.y enumerates halo rows: first the rows above [lo, yb), then the rows below [ye, hi)
-  int r = lo + blockIdx.y;
-  if (r >= yb) r = ye + (r - yb);
-  if (r >= hi) return;
-  const int owner = min(r / rpr, world - 1);
-  const size_t off = (size_t)blockIdx.z * frame_vec + (size_t)r * row_vec;
-  const uint4* s = src.p[owner] + off;
-  uint4* d = dst + off;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_vec; i += gridDim.x * blockDim.x) d[i] = s[i];
-}
-
-// Inter-level flow upsample of the own rows [y_begin, y_end); the coarse rows come from their owners.
-__global__ void __launch_bounds__(256) k_upsample_flow_tiled(PeerTab prev, int pw, int ph, float2* __restrict__ out,
-                                                             int w, int h, const LinTab* __restrict__ tabx,
-                                                             const LinTab* __restrict__ taby, float mul, int y_begin,
-                                                             int y_end) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int yb = y_begin + (blockIdx.y * blockDim.y + threadIdx.y) * UPS_ROWS;
-  if (x >= w || yb >= y_end) return;
-  const LinTab tx = tabx[x];
-  const int x0 = tx.i0, x1 = min(x0 + 1, pw - 1);
-  const float fx = tx.f;
-#pragma unroll
-  for (int j = 0; j < UPS_ROWS; j++) {
-    const int y = yb + j;
-    if (y >= y_end) break;
-    const LinTab ty = taby[y];
-    const int r0i = ty.i0, r1i = min(ty.i0 + 1, ph - 1);
-    const float2* r0 = prev.flow[tile_owner(r0i, prev)] + (size_t)r0i * pw;
-    const float2* r1 = prev.flow[tile_owner(r1i, prev)] + (size_t)r1i * pw;
-    const float2 q00 = __ldg(r0 + x0), q01 = __ldg(r0 + x1), q10 = __ldg(r1 + x0), q11 = __ldg(r1 + x1);
-    out[(size_t)y * w + x] = ups_blend(q00, q01, q10, q11, fx, ty.f, mul);
-  }
-}
-
 struct TiledPlan {
   Level sched[kMaxLevels];
   int n_levels;
@@ -104,8 +60,13 @@ struct TiledPlan {
   const uint8_t* d_next;
   float* d_flow_out;
   const ofb_farneback_params* p;
-  int cur_idx[kMaxLevels];   // ping-pong buffer that holds the level's initial flow (same on every rank)
-  int res_idx[kMaxLevels];   // buffer that holds the level's result
+  // per level (coarse -> fine): rows whose final flow of the level must be valid on this rank, rows of the level's
+  // input flow / matrices, rows of the expansions; element offset of the level's expansions in the R buffers
+  int need_lo[kMaxLevels], need_hi[kMaxLevels];
+  int in_lo[kMaxLevels], in_hi[kMaxLevels];
+  int r_lo[kMaxLevels], r_hi[kMaxLevels];
+  size_t r_off[kMaxLevels];
+  int res_idx[kMaxLevels];   // ping-pong buffer that holds the level's result
 };
 
 static inline void tile_rows(int hh, int world, int rank, int* rpr, int* yb, int* ye) {
@@ -114,47 +75,30 @@ static inline void tile_rows(int hh, int world, int rank, int* rpr, int* yb, int
   *ye = std::min(*yb + *rpr, hh);
 }
 
-static int tiled_pull(ofb_handle* h, void* dst, void* const* peers, int w, int hh, int elem_bytes, int frames,
-                      int halo, int* lo_out, int* hi_out);
+// Expansions of level li of rank r: level 0 (the last of the schedule) lives in d_RA / d_RB, the coarser levels one
+// after another in d_MA / d_MB (the generic path's buffers, unused in tiled mode).
+static inline const float4* tiled_RA(const ofb_handle* h, const TiledPlan& pl, int li, int r) {
+  return li == pl.n_levels - 1 ? (const float4*)h->tile.peer_RA[r] : (const float4*)h->tile.peer_MA[r] + pl.r_off[li];
+}
+static inline const float* tiled_RB(const ofb_handle* h, const TiledPlan& pl, int li, int r) {
+  return li == pl.n_levels - 1 ? (const float*)h->tile.peer_RB[r] : (const float*)h->tile.peer_MB[r] + pl.r_off[li];
+}
 
-// One stage of one rank.  kind 0 = flow init / upsample + pyramid + PolyExp of level li; kind 1 = iteration `it`.
+// One stage of one rank.  kind 0 = pyramid + PolyExp of the band of level li; kind 1 = iteration `it`.
 static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int it) {
   const int world = h->tile.world, rank = h->tile.rank;
   const Level& lv = pl.sched[li];
   const int w = lv.width, hh = lv.height;
   const bool last_level = li == pl.n_levels - 1;
-  int rpr, yb, ye;
-  tile_rows(hh, world, rank, &rpr, &yb, &ye);
   cudaStream_t st = h->stream;
-  const dim3 blk(32, 8);
-  const int ci = pl.cur_idx[li];
-  float2* cur = h->d_flow[ci];
   const ofb_farneback_params* p = pl.p;
+  if (pl.need_hi[li] <= pl.need_lo[li]) return OFB_OK;      // (more ranks than rows: nothing to do at any level)
+  float4* const RA = const_cast<float4*>(tiled_RA(h, pl, li, rank));
+  float* const RB = const_cast<float*>(tiled_RB(h, pl, li, rank));
 
   if (kind == 0) {
-    // ---- initial flow of the level (own rows)
-    TB(OFB_STAGE_FLOW_INIT);
-    if (ye > yb) {
-      if (li == 0) {
-        OFB_CUDA(h, cudaMemsetAsync(cur + (size_t)yb * w, 0, (size_t)(ye - yb) * w * sizeof(float2), st));
-      } else {
-        // the previous level ended in buffer prev_idx on every rank
-        const Level& pv = pl.sched[li - 1];
-        const int prev_idx = pl.res_idx[li - 1];
-        PeerTab t;
-        memset(&t, 0, sizeof(t));
-        for (int r = 0; r < world; r++) t.flow[r] = (const float2*)h->tile.peer_flow[prev_idx][r];
-        t.rpr = (pv.height + world - 1) / world;
-        t.world = world;
-        dim3 g((w + blk.x - 1) / blk.x, ((ye - yb + UPS_ROWS - 1) / UPS_ROWS + blk.y - 1) / blk.y);
-        k_upsample_flow_tiled<<<g, blk, 0, st>>>(t, pv.width, pv.height, cur, w, hh, h->d_lintab + h->tab_x_off[li],
-                                                 h->d_lintab + h->tab_y_off[li], (float)(1.0 / p->pyr_scale), yb, ye);
-        OFB_LAUNCH_CHECK(h);
-      }
-    }
-    TE();
-    if (ye <= yb) return OFB_OK;
-    // ---- pyramid + PolyExp of the own rows (local)
+    const int yb = pl.r_lo[li], ye = pl.r_hi[li];
+    // ---- pyramid + PolyExp of the band (local: every rank has the source frames)
     PyrCoef pyc;
     if (prepare_pyr(lv.ksize, lv.sigma, &pyc) != OFB_OK)
       return set_error(h, OFB_ERR_INVALID_ARG, "pyramid smoothing kernel too large (ksize=%d)", lv.ksize);
@@ -165,13 +109,13 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
     src.pitch = pl.pitch;
     src.image_stride = 0;
     const int frames = 2;
-    const bool fused_src = w == pl.width && hh == pl.height && pyc.r == 1;
+    const bool fused_src = w == pl.width && hh == pl.height && pyc.r == 1 && pyc.k[0] == 0.5f && pyc.k[1] == 0.25f;
     if (!fused_src) {
       const int lb = std::max(yb - pl.pc.n, 0), le = std::min(ye + pl.pc.n, hh);   // level rows PolyExp reads
       const double sy = 1.0 / ((double)hh / pl.height);
       const int sb = std::max(lin_entry(lb, sy, pl.height).i0 - pyc.r - 1, 0);
       const int se = std::min(lin_entry(le - 1, sy, pl.height).i0 + pyc.r + 3, pl.height);
-      float* hb = reinterpret_cast<float*>(h->d_MA);
+      float* hb = reinterpret_cast<float*>(h->d_VA);
       dim3 gh((w + 127) / 128, (se - sb + PYR_RPT - 1) / PYR_RPT, frames);
       dim3 bv(128, 2), gv((w + 127) / 128, (le - lb + 1) / 2, frames);
       TB(OFB_STAGE_PYRAMID);
@@ -200,18 +144,16 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
       dim3 g(strips * segs, frames);
       if (fused_src) {
         if (pl.pc.n == 5)
-          k_polyexp_march<5, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], h->d_RA, h->d_RB, w, hh, seg_rows,
-                                                       strips, pl.pc, yb, ye);
+          k_polyexp_march<5, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], RA, RB, w, hh, seg_rows, strips,
+                                                       pl.pc, yb, ye);
         else
-          k_polyexp_march<0, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], h->d_RA, h->d_RB, w, hh, seg_rows,
-                                                       strips, pl.pc, yb, ye);
+          k_polyexp_march<0, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], RA, RB, w, hh, seg_rows, strips,
+                                                       pl.pc, yb, ye);
       } else {
         if (pl.pc.n == 5)
-          k_polyexp_march<5, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, h->d_RA, h->d_RB, w, hh, seg_rows, strips,
-                                                       pl.pc, yb, ye);
+          k_polyexp_march<5, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
         else
-          k_polyexp_march<0, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, h->d_RA, h->d_RB, w, hh, seg_rows, strips,
-                                                       pl.pc, yb, ye);
+          k_polyexp_march<0, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
       }
       OFB_LAUNCH_CHECK(h);
     }
@@ -219,81 +161,55 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
     return OFB_OK;
   }
 
-  // ---- iteration `it` of level li: own rows, neighbours' rows through the peer table
-  if (ye <= yb) return OFB_OK;
-  const bool last_it = it == p->iterations - 1;
-  const int fin_idx = ci ^ (it & 1);
-  const float2* fin = h->d_flow[fin_idx];
-  float2* fout = (last_level && last_it) ? (float2*)pl.d_flow_out : h->d_flow[fin_idx ^ 1];
-  (void)cur;
+  // ---- iteration `it` of level li on the rows need +- (iterations - 1 - it) * m (all inputs local; R1 gathers beyond the
+  // band go to the owner's buffer through the peer table)
+  const int n_it = p->iterations, m = pl.bc.m;
+  const int yb = std::max(pl.need_lo[li] - (n_it - 1 - it) * m, 0), ye = std::min(pl.need_hi[li] + (n_it - 1 - it) * m, hh);
+  const bool last_it = it == n_it - 1;
+  // flow ping-pong as in the whole-frame driver: the first iteration of a level reads the coarser level's result (fused
+  // upsample) and must not write the buffer that holds it
+  const int prev_idx = li > 0 ? pl.res_idx[li - 1] : 1;
+  const int first_out = prev_idx ^ 1;
+  const int out_idx = first_out ^ (it & 1);
+  const float2* fin = h->d_flow[out_idx ^ 1];
+  float2* fout = (last_level && last_it) ? (float2*)pl.d_flow_out : h->d_flow[out_idx];
+  UpsSrc ups;
+  const UpsSrc* up = nullptr;
+  if (it == 0) {
+    if (li == 0) {
+      TB(OFB_STAGE_FLOW_INIT);
+      OFB_CUDA(h, cudaMemsetAsync(h->d_flow[out_idx ^ 1] + (size_t)pl.in_lo[li] * w, 0,
+                                  (size_t)(pl.in_hi[li] - pl.in_lo[li]) * w * sizeof(float2), st));
+      TE();
+    } else {
+      ups.prev = h->d_flow[prev_idx]; ups.pw = pl.sched[li - 1].width; ups.ph = pl.sched[li - 1].height;
+      ups.tabx = h->d_lintab + h->tab_x_off[li]; ups.taby = h->d_lintab + h->tab_y_off[li];
+      ups.mul = (float)(1.0 / p->pyr_scale);
+      up = &ups;
+    }
+  }
   PeerTab t;
   memset(&t, 0, sizeof(t));
   for (int r = 0; r < world; r++) {
-    t.RA[r] = (const float4*)h->tile.peer_RA[r];
-    t.RB[r] = (const float*)h->tile.peer_RB[r];
-    t.flow[r] = (const float2*)h->tile.peer_flow[fin_idx][r];
+    t.RA[r] = tiled_RA(h, pl, li, r);
+    t.RB[r] = tiled_RB(h, pl, li, r);
   }
-  t.rpr = rpr;
+  t.rpr = (hh + world - 1) / world;
   t.world = world;
-  // halo pulls (the barrier before this stage guarantees the neighbours' rows are final)
-  TB(OFB_STAGE_OTHER);
-  {
-    int st2;
-    const int halo_f = pl.bc.m + 2;                 // blur halo + the row the producers prefetch
-    const int halo_r = pl.bc.m + kTileGatherMargin;  // blur halo + margin for the displacement of the gather
-    if ((st2 = tiled_pull(h, h->d_flow[fin_idx], h->tile.peer_flow[fin_idx], w, hh, 8, 1, halo_f, &t.f_lo, &t.f_hi))) return st2;
-    if (it == 0) {
-      int a, b;
-      if ((st2 = tiled_pull(h, h->d_RA, h->tile.peer_RA, w, hh, 16, 2, halo_r, &t.r_lo, &t.r_hi))) return st2;
-      if ((st2 = tiled_pull(h, h->d_RB, h->tile.peer_RB, w, hh, 4, 2, halo_r, &a, &b))) return st2;
-      t.r_lo = std::max(t.r_lo, a);                 // both R arrays must be local for a row to count as local
-      t.r_hi = std::min(t.r_hi, b);
-      h->tile.r_lo = t.r_lo;
-      h->tile.r_hi = t.r_hi;
-    } else {
-      t.r_lo = h->tile.r_lo;
-      t.r_hi = h->tile.r_hi;
-    }
-  }
-  TE();
+  t.r_lo = pl.r_lo[li];
+  t.r_hi = pl.r_hi[li];
   const float reg = (float)(1e-3 / ((double)pl.bc.scale * (double)pl.bc.scale));
   cudaError_t e;
-  // (the tiled kernel takes its R pointers per owner rank from the peer table; own buffers for the prefetch addresses)
-  const RSet rs1 = {h->d_RA, h->d_RB, h->d_RA + (size_t)w * hh, h->d_RB + (size_t)w * hh};
+  // (own buffers for the prefetch addresses; the kernel takes remote rows from the peer table)
+  const RSet rs1 = {RA, RB, RA + (size_t)w * hh, RB + (size_t)w * hh};
   TB(OFB_STAGE_ITERATION);
   if (pl.bc.m == 7)
-    e = launch_iter_v<7, 256, 2, 2, 3, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
+    e = launch_iter_v<7, 256, 2, 2, 3, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
   else
-    e = launch_iter_v<0, 128, 4, 1, 0, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
+    e = launch_iter_v<0, 128, 4, 1, 0, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
   if (e != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "tiled k_iter_v launch failed: %s", cudaGetErrorString(e));
   h->launches++;
   TE();
-  return OFB_OK;
-}
-
-// Pull halo rows [yb - halo, yb) and [ye, ye + halo) of a buffer with `elem_bytes` per pixel and `frames`
-// frames of hh x w pixels.  Rows must be a multiple of 16 bytes (else the halo stays remote: returns 0 rows).
-static int tiled_pull(ofb_handle* h, void* dst, void* const* peers, int w, int hh, int elem_bytes, int frames,
-                      int halo, int* lo_out, int* hi_out) {
-  const int world = h->tile.world, rank = h->tile.rank;
-  int rpr, yb, ye;
-  tile_rows(hh, world, rank, &rpr, &yb, &ye);
-  *lo_out = yb;
-  *hi_out = ye;
-  const size_t row_bytes = (size_t)w * elem_bytes;
-  if (world == 1 || ye <= yb || (row_bytes & 15) || (((size_t)hh * row_bytes) & 15)) return OFB_OK;
-  const int lo = std::max(yb - halo, 0), hi = std::min(ye + halo, hh);
-  const int nrows = (yb - lo) + (hi - ye);
-  if (nrows <= 0) return OFB_OK;
-  PullSrc ps;
-  for (int r = 0; r < kMaxTileRanks; r++) ps.p[r] = r < world ? (const uint4*)peers[r] : nullptr;
-  const int row_vec = (int)(row_bytes / 16);
-  dim3 g(std::min((row_vec + 255) / 256, 8), nrows, frames);
-  k_tile_pull<<<g, 256, 0, h->stream>>>((uint4*)dst, ps, rpr, world, row_vec, lo, yb, ye, hi,
-                                        (size_t)hh * row_bytes / 16);
-  OFB_LAUNCH_CHECK(h);
-  *lo_out = lo;
-  *hi_out = hi;
   return OFB_OK;
 }
 
@@ -324,10 +240,43 @@ static int tiled_make_plan(ofb_handle* h, TiledPlan* pl, const uint8_t* d_prev, 
   if (pl->bc.m < 2 || pl->bc.m > 19) return set_error(h, OFB_ERR_INVALID_ARG, "tiled mode needs winsize in [4, 39]");
   if (pl->pc.n > PX_MAXN) return set_error(h, OFB_ERR_INVALID_ARG, "tiled mode needs poly_n <= %d", PX_MAXN);
   if (p->iterations < 1) return set_error(h, OFB_ERR_INVALID_ARG, "tiled mode needs iterations >= 1");
-  // ping-pong roles: a level's initial flow goes to the buffer that does NOT hold the previous result
-  for (int li = 0; li < pl->n_levels; li++) {
-    pl->cur_idx[li] = li == 0 ? 0 : (pl->res_idx[li - 1] ^ 1);
-    pl->res_idx[li] = pl->cur_idx[li] ^ (p->iterations & 1);
+  const int world = h->tile.world, rank = h->tile.rank, nl = pl->n_levels, halo = p->iterations * pl->bc.m;
+  // bands, from the finest level (where the rank must deliver exactly the rows it owns) down to the coarsest:
+  //   need_l : rows of the level's FINAL flow that must be valid here
+  //   in_l   : rows of the level's input flow and of the matrices = need_l +- iterations * m
+  //   coarser need = the rows the bilinear upsample of in_l touches (cv::resize coordinates, +-2 rows of slack)
+  int rpr;
+  tile_rows(height, world, rank, &rpr, &pl->need_lo[nl - 1], &pl->need_hi[nl - 1]);
+  for (int li = nl - 1; li >= 0; li--) {
+    const int hh = pl->sched[li].height;
+    if (pl->need_hi[li] <= pl->need_lo[li]) {          // nothing owned: empty at every level
+      pl->in_lo[li] = pl->in_hi[li] = pl->r_lo[li] = pl->r_hi[li] = 0;
+      if (li > 0) pl->need_lo[li - 1] = pl->need_hi[li - 1] = 0;
+      continue;
+    }
+    pl->in_lo[li] = std::max(pl->need_lo[li] - halo, 0);
+    pl->in_hi[li] = std::min(pl->need_hi[li] + halo, hh);
+    pl->r_lo[li] = std::max(pl->in_lo[li] - kTileGatherMargin, 0);
+    pl->r_hi[li] = std::min(pl->in_hi[li] + kTileGatherMargin, hh);
+    if (li > 0) {
+      const int ph = pl->sched[li - 1].height;
+      const double sy = 1.0 / ((double)hh / ph);
+      pl->need_lo[li - 1] = std::max(lin_entry(pl->in_lo[li], sy, ph).i0 - 2, 0);
+      pl->need_hi[li - 1] = std::min(lin_entry(pl->in_hi[li] - 1, sy, ph).i0 + 4, ph);
+    }
+  }
+  // expansions of the coarser levels: one after another in d_MA / d_MB (two frames + spare rows each)
+  size_t off = 0;
+  for (int li = 0; li < nl - 1; li++) {
+    pl->r_off[li] = off;
+    off += 2 * (size_t)pl->sched[li].width * pl->sched[li].height + (size_t)kRowPad * pl->sched[li].width;
+  }
+  pl->r_off[nl - 1] = 0;
+  if (off > (size_t)h->max_batch * h->max_w * h->max_h)
+    return set_error(h, OFB_ERR_CAPACITY, "tiled mode: the coarser levels' expansions do not fit (pyr_scale too close to 1)");
+  for (int li = 0; li < nl; li++) {
+    const int prev_idx = li > 0 ? pl->res_idx[li - 1] : 1;
+    pl->res_idx[li] = (prev_idx ^ 1) ^ ((p->iterations - 1) & 1);
   }
   pl->width = width;
   pl->height = height;
@@ -341,16 +290,19 @@ static int tiled_make_plan(ofb_handle* h, TiledPlan* pl, const uint8_t* d_prev, 
 
 int tiled_barrier_public(ofb_handle* h) { return tiled_barrier(h); }
 
-// Real multi-GPU run of this rank: stages with the peer-memory flag barrier in between.
+// Real multi-GPU run of this rank: per level PolyExp of the band, ONE flag barrier (the peers' expansions of the level
+// are complete: remote gathers may read them), then the iterations.
 int farneback_run_tiled(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_next, int width, int height,
                         size_t pitch, float* d_flow_out, const ofb_farneback_params* p, int* row_begin,
                         int* row_end) {
   TiledPlan pl;
   int st = tiled_make_plan(h, &pl, d_prev, d_next, width, height, pitch, d_flow_out, p);
   if (st) return st;
-  // entry barrier: nobody overwrites buffers a peer may still read from the previous call
-  st = tiled_barrier(h);
-  if (st) return st;
+  if (pl.n_levels == 1) {
+    // a single level re-uses its expansion buffer from pair to pair: nobody may still be gathering from it
+    st = tiled_barrier(h);
+    if (st) return st;
+  }
   for (int li = 0; li < pl.n_levels; li++) {
     st = tiled_stage(h, pl, li, 0, 0);
     if (st) return st;
@@ -359,10 +311,6 @@ int farneback_run_tiled(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_n
     for (int it = 0; it < p->iterations; it++) {
       st = tiled_stage(h, pl, li, 1, it);
       if (st) return st;
-      if (!(li == pl.n_levels - 1 && it == p->iterations - 1)) {
-        st = tiled_barrier(h);
-        if (st) return st;
-      }
     }
   }
   int rpr;
@@ -386,18 +334,13 @@ int farneback_run_tiled_emulated(ofb_handle* const* hs, int world, const uint8_t
   int st = sync_all();
   if (st) return st;
   for (int li = 0; li < pls[0].n_levels; li++) {
-    // (each rank's stage runs alone: the streams are synchronised after every rank, so per-rank stage
-    //  timers are clean and no two ranks' kernels share the device)
-    for (int r = 0; r < world; r++) {
+    for (int r = 0; r < world; r++)
       if ((st = tiled_stage(hs[r], pls[r], li, 0, 0))) return st;
-      if ((st = sync_all())) return st;
-    }
-    for (int it = 0; it < p->iterations; it++) {
-      for (int r = 0; r < world; r++) {
+    if ((st = sync_all())) return st;                   // stands in for the per-level flag barrier
+    for (int r = 0; r < world; r++)
+      for (int it = 0; it < p->iterations; it++)
         if ((st = tiled_stage(hs[r], pls[r], li, 1, it))) return st;
-        if ((st = sync_all())) return st;
-      }
-    }
+    if ((st = sync_all())) return st;
   }
   return OFB_OK;
 }

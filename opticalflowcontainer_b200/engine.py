@@ -432,18 +432,65 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out, used.value
 
-    def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3) -> np.ndarray:
+    def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3, mask=None) -> np.ndarray:
         image = _u8_image(image, "image")
         hgt, wid = image.shape
         cap = int(maxCorners) if maxCorners > 0 else hgt * wid
         out = np.empty((max(cap, 1), 2), np.float32)
         n = C.c_int(0)
         p = GfttParams(int(maxCorners), float(qualityLevel), float(minDistance), int(blockSize))
+        mptr, mstride = None, 0
+        if mask is not None:
+            mask = _u8_image(mask, "mask")
+            if mask.shape != image.shape:
+                raise OfbError(1, "goodFeaturesToTrack: mask must have the image's size")
+            mptr, mstride = mask.ctypes.data, mask.strides[0]
         with self._lock:
-            st = self._lib.ofb_good_features(self._h, image.ctypes.data, wid, hgt, image.strides[0], C.byref(p),
-                                             out.ctypes.data, C.byref(n))
+            st = self._lib.ofb_good_features_masked(self._h, image.ctypes.data, wid, hgt, image.strides[0], mptr, mstride,
+                                                    C.byref(p), out.ctypes.data, C.byref(n))
             _lib.check(st, self._h)
         return out[:n.value].reshape(-1, 1, 2).copy()
+
+    def lk_stream(self, frame, maxCorners=2000, qualityLevel=0.01, minDistance=7, blockSize=3, winSize=(21, 21),
+                  maxLevel=3, criteria=(3, 30, 0.01), minEigThreshold=1e-4, flags=0):
+        """Camera-stream form of goodFeaturesToTrack + calcOpticalFlowPyrLK (ofb_lk_stream): one new frame per call, the
+        previous frame's pyramid, derivatives and corners stay on the GPU.  Returns None on the priming call, then
+        ``(prevPts [N,1,2], nextPts [N,1,2], status [N,1], err [N,1])`` for (previous frame -> frame); the corners of
+        ``frame`` (tracked by the next call) are in :attr:`last_corners`."""
+        frame = _u8_image(frame, "frame")
+        hgt, wid = frame.shape
+        cap = int(maxCorners)
+        if cap <= 0:
+            raise OfbError(1, "lk_stream: maxCorners must be > 0")
+        gp = GfttParams(cap, float(qualityLevel), float(minDistance), int(blockSize))
+        ctype, max_count, eps = criteria
+        if not (ctype & 1):
+            max_count = 30
+        if not (ctype & 2):
+            eps = 0.01
+        lp = LKParams(int(winSize[0]), int(winSize[1]), int(maxLevel), int(max_count), float(eps), int(flags),
+                      float(minEigThreshold))
+        prev = np.empty((cap, 2), np.float32)
+        nxt = np.empty((cap, 2), np.float32)
+        status = np.zeros((cap,), np.uint8)
+        err = np.zeros((cap,), np.float32)
+        new = np.empty((cap, 2), np.float32)
+        n, n_new = C.c_int(0), C.c_int(0)
+        with self._lock:
+            st = self._lib.ofb_lk_stream(self._h, frame.ctypes.data, wid, hgt, frame.strides[0], C.byref(gp), C.byref(lp),
+                                         prev.ctypes.data, nxt.ctypes.data, status.ctypes.data, err.ctypes.data,
+                                         C.byref(n), new.ctypes.data, C.byref(n_new))
+            _lib.check(st, self._h)
+        self.last_corners = new[:n_new.value].reshape(-1, 1, 2).copy()
+        if n.value < 0:
+            return None
+        k = n.value
+        return (prev[:k].reshape(-1, 1, 2).copy(), nxt[:k].reshape(-1, 1, 2).copy(), status[:k].reshape(-1, 1).copy(),
+                err[:k].reshape(-1, 1).copy())
+
+    def lk_stream_reset(self):
+        with self._lock:
+            _lib.check(self._lib.ofb_lk_stream_reset(self._h), self._h)
 
     def corner_min_eigenval(self, image, blockSize=3) -> np.ndarray:
         image = _u8_image(image, "image")

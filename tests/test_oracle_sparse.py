@@ -86,3 +86,33 @@ def test_pyrlk_matches_cv2():
     ok = rs.ravel() == 1
     assert np.abs(rn - mn)[ok].max() < 1e-3
     assert np.allclose(re, me, rtol=1e-3, atol=1e-6)
+
+
+def test_sobel_simd_tail_rule_is_the_same_on_every_fma_dispatch_level():
+    """The eigenvalue map depends on WHERE the wheel's Sobel row filter stops using FMA: columns past the last full block
+    of 32 take the scalar tail.  That block size is a property of the wheel's dispatched code, so it is probed here on
+    the wheel's AVX-512 path (if this host has it) and with AVX512-SKX disabled (its AVX2 path, what a host without
+    AVX-512 runs): the block-of-32 restatement must match cv2 on both, at widths with every tail length class."""
+    import os
+    import subprocess
+    import sys
+    child = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import cv2\n"
+        "from oracle import features_np as F, synth\n"
+        "bad = 0\n"
+        "for (h, w, seed) in [(60, 67, 1), (48, 100, 2), (40, 131, 3), (64, 250, 4), (33, 255, 5), (50, 96, 6)]:\n"
+        "    a, _ = synth.synth_pair(h, w, seed)\n"
+        "    bad += int((F.corner_min_eigenval(a, 3) != cv2.cornerMinEigenVal(a, 3, ksize=3)).sum())\n"
+        "print('MISMATCH', bad, cv2.getCPUFeaturesLine())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    for disable in ("", "AVX512-SKX"):
+        env = dict(os.environ)
+        if disable:
+            env["OPENCV_CPU_DISABLE"] = disable
+        out = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300)
+        line = [l for l in out.stdout.splitlines() if l.startswith("MISMATCH")]
+        assert line, out.stderr[-2000:]
+        assert line[0].split()[1] == "0", (disable, line[0])
+        if disable and "AVX512-SKX" in line[0]:
+            assert "AVX512-SKX?" in line[0]              # cv2 marks a disabled feature with '?': the level really was lowered

@@ -45,9 +45,10 @@ def test_min_eigenval_bit_exact(engine_factory, shape, seed):
     a, _ = synth.synth_pair(shape[0], shape[1], seed)
     eng = engine_factory(shape[1], shape[0])
     got = eng.corner_min_eigenval(a, 3)
-    assert np.array_equal(got, FT.corner_min_eigenval(a, 3))          # oracle restatement: every size
-    if shape[1] % 32 == 0:                                              # live cv2: SIMD-tail-free widths
-        assert np.array_equal(got, cv2.cornerMinEigenVal(a, 3, ksize=3))
+    assert np.array_equal(got, FT.corner_min_eigenval(a, 3))          # oracle restatement
+    # live cv2 on this host, also where the width is not a multiple of 32 (the wheel's row filter takes its scalar,
+    # FMA-free tail there — the same on its AVX2 and AVX-512 dispatch, tests/test_oracle_sparse.py)
+    assert np.array_equal(got, cv2.cornerMinEigenVal(a, 3, ksize=3))
 
 
 @pytest.mark.parametrize("shape,seed,maxc,q,md", [((480, 640), 0, 2000, 0.01, 7), ((480, 640), 1, 100, 0.05, 3.5),
@@ -59,6 +60,118 @@ def test_good_features_exact_list(engine_factory, shape, seed, maxc, q, md):
     got = eng.good_features(a, maxc, q, md, 3)
     ref = cv2.goodFeaturesToTrack(a, maxc, q, md, blockSize=3)
     assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("shape,seed,maxc,q,md", [((481, 637), 7, 2000, 0.01, 7), ((270, 487), 8, 500, 0.01, 5),
+                                                    ((1080, 1917), 9, 2000, 0.01, 7), ((135, 241), 2, 300, 0.02, 3)])
+def test_good_features_exact_list_widths_not_multiple_of_32(engine_factory, shape, seed, maxc, q, md):
+    """Corner list against LIVE cv2 on this host where the Sobel row filter has a SIMD tail (width % 32 != 0)."""
+    a, _ = synth.synth_pair(shape[0], shape[1], seed)
+    eng = engine_factory(shape[1], shape[0])
+    got = eng.good_features(a, maxc, q, md, 3)
+    ref = cv2.goodFeaturesToTrack(a, maxc, q, md, blockSize=3)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_good_features_mask(engine_factory):
+    """cv2's mask argument: candidates outside the mask are dropped AND the quality threshold is relative to the
+    strongest response inside the mask."""
+    import opticalflowcontainer_b200 as ofb
+    a, _ = synth.synth_pair(270, 480, 11)
+    mask = np.zeros((270, 480), np.uint8)
+    mask[40:200, 100:400] = 255
+    mask[90:120, 150:300] = 0
+    eng = engine_factory(480, 270)
+    for (maxc, q, md) in [(300, 0.01, 7), (0, 0.05, 0), (50, 0.2, 12.5)]:
+        ref = cv2.goodFeaturesToTrack(a, maxc, q, md, mask=mask, blockSize=3)
+        got = eng.good_features(a, maxc, q, md, 3, mask=mask)
+        assert ref is not None and np.array_equal(got, ref)
+        assert np.array_equal(ofb.goodFeaturesToTrack(a, maxc, q, md, mask=mask, blockSize=3), ref)
+    # a strided (non-contiguous) mask view
+    big = np.zeros((270, 512), np.uint8); big[:, :480] = mask
+    assert np.array_equal(eng.good_features(a, 300, 0.01, 7, 3, mask=big[:, :480]),
+                          cv2.goodFeaturesToTrack(a, 300, 0.01, 7, mask=mask, blockSize=3))
+    with pytest.raises(ofb.OfbError):
+        ofb.goodFeaturesToTrack(a, 10, 0.01, 7, useHarrisDetector=True)
+
+
+def test_good_features_many_equal_responses(engine_factory):
+    """A checkerboard: thousands of candidates share one response value, so one value bucket of the candidate ordering
+    is larger than a selection round (the CTA orders it in global memory) and cv2's tie rule — descending address —
+    decides the whole list."""
+    t = (((np.arange(512)[:, None] // 16) + (np.arange(512)[None, :] // 16)) % 2 * 200 + 20).astype(np.uint8)
+    eng = engine_factory(512, 512)
+    for (maxc, md) in [(0, 0), (700, 0), (0, 9), (300, 20)]:
+        ref = cv2.goodFeaturesToTrack(t, maxc, 0.01, md, blockSize=3)
+        got = eng.good_features(t, maxc, 0.01, md, 3)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (maxc, md)
+
+
+def test_good_features_unbounded_and_tiny(engine_factory):
+    """maxCorners <= 0 with minDistance < 1 keeps every candidate (corner buffers are sized like the candidate list);
+    images without an interior pixel give an empty list, as cv2 does."""
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, size=(240, 320), dtype=np.uint8)
+    eng = engine_factory(320, 240)
+    ref = cv2.goodFeaturesToTrack(a, 0, 0.001, 0, blockSize=3)
+    got = eng.good_features(a, 0, 0.001, 0, 3)
+    assert len(ref) > 240 * 320 // 16 and np.array_equal(got, ref)
+    assert len(eng.good_features(np.zeros((2, 100), np.uint8), 10, 0.01, 3, 3)) == 0
+    assert len(eng.good_features(np.zeros((100, 2), np.uint8), 10, 0.01, 3, 3)) == 0
+
+
+def test_lk_stream_equals_pair_calls(built_lib):
+    """ofb_lk_stream keeps the previous frame's pyramid, derivatives and corner list on the GPU (one upload per frame):
+    what it returns for (frame t-1 -> frame t) equals good_features(t-1) + pyrlk(t-1, t) bit for bit, and cv2 within
+    the LK gate; a change of parameters or another sparse call on the handle re-primes it."""
+    import opticalflowcontainer_b200 as ofb
+    h, w = 270, 480
+    base = synth.synth_pair(h, w, 61, (0.0, 0.0))[0]
+    fr = [synth.subpixel_shift(base, 1.7 * t, -0.8 * t) for t in range(5)]
+    eng, ref = ofb.FlowEngine(w, h, 1, 0), ofb.FlowEngine(w, h, 1, 0)
+    kw = dict(maxCorners=400, qualityLevel=0.01, minDistance=7, blockSize=3, winSize=(21, 21), maxLevel=3,
+              criteria=(3, 30, 0.01))
+    try:
+        assert eng.lk_stream(fr[0], **kw) is None
+        assert np.array_equal(eng.last_corners, ref.good_features(fr[0], 400, 0.01, 7, 3))
+        for t in range(1, 5):
+            prev, nxt, st, err = eng.lk_stream(fr[t], **kw)
+            pts = ref.good_features(fr[t - 1], 400, 0.01, 7, 3)
+            want = ref.pyrlk(fr[t - 1], fr[t], pts, None, (21, 21), 3, (3, 30, 0.01))
+            assert np.array_equal(prev, pts)
+            assert np.array_equal(nxt, want[0]) and np.array_equal(st, want[1]) and np.array_equal(err, want[2])
+            cpts = cv2.goodFeaturesToTrack(fr[t - 1], 400, 0.01, 7, blockSize=3)
+            assert np.array_equal(prev, cpts)
+            _lk_check(cv2.calcOpticalFlowPyrLK(fr[t - 1], fr[t], cpts, None, winSize=(21, 21), maxLevel=3,
+                                               criteria=(3, 30, 0.01)), (nxt, st, err))
+        # another sparse call on the handle re-primes the stream; so does a parameter change
+        eng.good_features(fr[0], 10, 0.01, 7, 3)
+        assert eng.lk_stream(fr[1], **kw) is None
+        assert eng.lk_stream(fr[2], **kw) is not None
+        assert eng.lk_stream(fr[3], **dict(kw, maxCorners=200)) is None
+        eng.lk_stream_reset()
+        assert eng.lk_stream(fr[4], **dict(kw, maxCorners=200)) is None
+        with pytest.raises(ofb.OfbError):
+            eng.lk_stream(fr[0], **dict(kw, maxCorners=0))
+    finally:
+        eng.close()
+        ref.close()
+
+
+def test_pyrlk_accepts_pyramids(built_lib):
+    """cv2.calcOpticalFlowPyrLK also takes pyramids from buildOpticalFlowPyramid (with or without derivative images)."""
+    import opticalflowcontainer_b200 as ofb
+    a, b = synth.synth_pair(270, 480, 14, (2.6, 1.4))
+    pts = cv2.goodFeaturesToTrack(a, 200, 0.01, 7, blockSize=3)
+    for with_d in (True, False):
+        _, pa = cv2.buildOpticalFlowPyramid(a, (21, 21), 2, withDerivatives=with_d)
+        _, pb = cv2.buildOpticalFlowPyramid(b, (21, 21), 2, withDerivatives=with_d)
+        ref = cv2.calcOpticalFlowPyrLK(pa, pb, pts, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+        got = ofb.calcOpticalFlowPyrLK(pa, pb, pts, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+        _lk_check(ref, got)
+        # the pyramid's depth (2) limits maxLevel: the same as images with maxLevel=2
+        same = ofb.calcOpticalFlowPyrLK(a, b, pts, None, winSize=(21, 21), maxLevel=2, criteria=(3, 30, 0.01))
+        assert np.array_equal(got[0], same[0]) and np.array_equal(got[1], same[1])
 
 
 def test_good_features_1080p_2000_corners(engine_factory):
