@@ -239,11 +239,10 @@ int farneback_run(ofb_handle* h, int n_pairs, bool sequence, const uint8_t* d_pr
 // k_iter_v with the window radius as a template argument for the common window sizes other than the default
 // (iter_fixed_a.cu, iter_fixed_b.cu: separate translation units so that they compile in parallel).  *served = false if
 // there is no instantiation for m (the caller then takes the run-time-radius kernel).
-struct UpsSrc;
 cudaError_t launch_iter_fixed_a(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                const RSet& rs, float reg, cudaStream_t st, const UpsSrc* ups, bool* served);
+                                const RSet& rs, float reg, cudaStream_t st, bool* served);
 cudaError_t launch_iter_fixed_b(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                const RSet& rs, float reg, cudaStream_t st, const UpsSrc* ups, bool* served);
+                                const RSet& rs, float reg, cudaStream_t st, bool* served);
 void farneback_graphs_destroy(ofb_handle* h);
 // the schedule farneback_run would use (level sizes), for sizing the stream cache
 int farneback_levels(int width, int height, const ofb_farneback_params* p, Level* out, int* n_out);

@@ -622,7 +622,7 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
 #define TE() do { int s__ = timing_end(h); if (s__) return s__; } while (0)
     // --- initial flow of the level.  With the fused iteration kernel the x2 upsample of the coarser level's result is
     // computed by the first iteration's producers (UpsSrc): no launch, no write + read of the upsampled field.
-    const bool fuse_ups = OFB_EXP_FUSE_UPS && use_fused && prev_flow != nullptr && p->iterations > 0;
+    const bool fuse_ups = OFB_EXP_FUSE_UPS && use_fused && bc.m == 7 && prev_flow != nullptr && p->iterations > 0;   // (default window: the UPS instantiation)
     TB(OFB_STAGE_FLOW_INIT);
     if (prime_only || fuse_ups) {
       // first frame of the streams: expansions only / upsample fused into the first iteration
@@ -742,18 +742,20 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
           ups.prev = prev_flow; ups.pw = prev_w; ups.ph = prev_h;
           ups.tabx = h->d_lintab + h->tab_x_off[li]; ups.taby = h->d_lintab + h->tab_y_off[li];
           ups.mul = (float)(1.0 / p->pyr_scale);
+          ups.exact2y = hh == 2 * prev_h;
           up = &ups;
         }
         cudaError_t e;
         if (bc.m == 7) {
-          e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, up);
+          if (up) e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF, true>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, up);
+          else e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, nullptr);
         } else {
           // other window sizes: the radius as a template argument where an instantiation exists (winsize 5..31), else
           // at run time (its generic consumer loop is slow: winsize 13 measured 6.4 ms per 18 pairs against 3.0 ms)
           bool served = false;
-          e = bc.m <= 8 ? launch_iter_fixed_a(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, up, &served)
-                        : launch_iter_fixed_b(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, up, &served);
-          if (!served) e = launch_iter_v<0, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, up);
+          e = bc.m <= 8 ? launch_iter_fixed_a(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, &served)
+                        : launch_iter_fixed_b(h, bc.m, fin, fout, w, hh, n_pairs, rs, reg, st, &served);
+          if (!served) e = launch_iter_v<0, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, nullptr);
         }
         if (e != cudaSuccess)
           return set_error(h, OFB_ERR_CUDA, "k_iter_v launch failed: %s", cudaGetErrorString(e));

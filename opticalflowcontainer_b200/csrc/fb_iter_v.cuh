@@ -30,7 +30,17 @@
 #include "fb_device.cuh"
 #include "fb_um.cuh"
 
+// Experiment builds only: bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the R0 / flow rows OFB_EXP_L2PF chunks ahead,
+// issued by one thread of the CTA in the two-rows-in-flight schedule (0 = off).
+#ifndef OFB_EXP_L2PF
+#define OFB_EXP_L2PF 0
+#endif
+
 namespace ofb {
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 template <int COLS, int CH>
 constexpr int iter_v_smem_floats(int m, bool tmem, int nbuf) {
@@ -47,6 +57,7 @@ struct UpsSrc {
   const LinTab* taby;
   int pw, ph;
   float mul;              // 1 / pyr_scale
+  int exact2y;            // the level has exactly twice the coarser level's rows: row coordinates without the table
 };
 
 // resize(prevFlow, INTER_LINEAR) * mul at one pixel — the arithmetic of k_upsample_flow, shared so the fused and the
@@ -102,7 +113,10 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 // register budget is held to.  PFD: L2 prefetch distance of the plain schedule.  TILED (spatially tiled mode, one pair):
 // the CTA grid covers only the level rows [y_begin, y_end) of this rank's band; R1 rows the displacement reaches outside
 // the band are read from the owner's buffer through the NVLink peer pointers in `tab` (the flow and R0 are local).
-template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF>
+// UPS: first iteration of a level — the input flow is the bilinear upsample of the coarser level's result (UpsSrc),
+// computed by the producers: a thread marching down its column keeps the horizontally blended coarse flow of the two
+// coarse rows around it and loads a new coarse row only when it crosses one (every second row at pyr_scale 0.5).
+template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF, bool UPS>
 __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     k_iter_v(const RSet rs, const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int w, int h, int m_rt,
              float reg, int seg_rows, int strips, int y_begin, int y_end, PeerTab tab, int my_rank, UpsSrc ups) {
@@ -196,36 +210,57 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
       }
     };
 
-    // fused upsample: per-thread column entry of the resize table
-    int ux0 = 0, ux1 = 0;
-    float ufx = 0.f;
-    const bool do_ups = ups.prev != nullptr;
+    // fused upsample: per-thread column entry of the resize table, cache of the two coarse rows around the current row
+    int ux0 = 0, ux1 = 0, u_ca = -1, u_cb = -1;
+    float ufx = 0.f, uax0 = 1.f;
+    float2 uHa = make_float2(0.f, 0.f), uHb = uHa;
     const float2* uprev = nullptr;
-    if (do_ups) {
+    if constexpr (UPS) {
       const int2 tx = __ldg(reinterpret_cast<const int2*>(ups.tabx + x));   // {i0, f}
-      ux0 = tx.x; ux1 = min(tx.x + 1, ups.pw - 1); ufx = __int_as_float(tx.y);
+      ux0 = tx.x; ux1 = min(tx.x + 1, ups.pw - 1); ufx = __int_as_float(tx.y); uax0 = __fsub_rn(1.f, ufx);
       uprev = ups.prev + (size_t)pair * ups.pw * ups.ph;   // (tiled mode: the rank's own coarse band, one pair)
     }
-    // input flow of matrix row t at this column (volatile loads: they stay where they are written, between the gathers
-    // and the barrier; ptxas otherwise sinks them to the end of the loop body, in front of the address arithmetic).
-    // Fused upsample: the row's resize-table entry is fetched by ups_row() one chunk BEFORE the coarse flow is read — a
-    // table load in front of the four flow loads put a second dependent memory round trip on every chunk's critical
-    // path (measured: the first iteration of levels 1-3 ran 2x longer).
-    auto ups_row = [&](int t) -> int2 {
-      return do_ups ? __ldg(reinterpret_cast<const int2*>(ups.taby + clampi(t, 0, h - 1))) : make_int2(0, 0);
+    // coarse flow of row r blended along x at this column (the horizontal half of ups_blend, same operations)
+    auto ups_hrow = [&](int r) -> float2 {
+      const float2* p = uprev + (unsigned)r * (unsigned)ups.pw;
+      const float2 q0 = __ldg(p + ux0), q1 = __ldg(p + ux1);
+      return make_float2(__fmaf_rn(q1.x, ufx, __fmul_rn(q0.x, uax0)), __fmaf_rn(q1.y, ufx, __fmul_rn(q0.y, uax0)));
     };
-    auto flow_at = [&](int t, int2 ty) -> float2 {
+    // input flow of matrix row t at this column.  Plain launches: one load (volatile in the two-rows-in-flight schedule:
+    // it stays where it is written, between the gathers and the barrier; ptxas otherwise sinks it to the end of the loop
+    // body, in front of the address arithmetic).  Rows are visited in increasing order.
+    auto flow_at = [&](int t) -> float2 {
       const int yc = clampi(t, 0, h - 1);
-      if (do_ups) {
-        const float2* r0 = uprev + (unsigned)ty.x * (unsigned)ups.pw;
-        const float2* r1 = uprev + (unsigned)min(ty.x + 1, ups.ph - 1) * (unsigned)ups.pw;
-        // (cached loads: the coarse rows are shared by neighbouring fine rows and columns; the branch keeps them here)
-        const float2 q00 = __ldg(r0 + ux0), q01 = __ldg(r0 + ux1);
-        const float2 q10 = __ldg(r1 + ux0), q11 = __ldg(r1 + ux1);
-        return ups_blend(q00, q01, q10, q11, ufx, __int_as_float(ty.y), ups.mul);
+      if constexpr (UPS) {
+        int r0;
+        float fy;
+        if (ups.exact2y) {                 // cv::resize coordinates of an exact x2: (y + 0.5) / 2 - 0.5
+          r0 = (yc - 1) >> 1;
+          fy = (yc & 1) ? 0.25f : 0.75f;
+          if (r0 < 0) { r0 = 0; fy = 0.f; }
+          if (r0 >= ups.ph - 1) { r0 = ups.ph - 1; fy = 0.f; }
+        } else {
+          const int2 ty = __ldg(reinterpret_cast<const int2*>(ups.taby + yc));
+          r0 = ty.x;
+          fy = __int_as_float(ty.y);
+        }
+        const int r1 = min(r0 + 1, ups.ph - 1);
+        // (all of this is uniform over the CTA: it depends on the row only)
+        if (r0 != u_ca) {
+          if (r0 == u_cb) uHa = uHb; else uHa = ups_hrow(r0);
+          u_ca = r0;
+        }
+        if (r1 != u_cb) {
+          if (r1 == u_ca) uHb = uHa; else uHb = ups_hrow(r1);
+          u_cb = r1;
+        }
+        const float ay0 = __fsub_rn(1.f, fy);
+        return make_float2(__fmul_rn(__fmaf_rn(uHb.x, fy, __fmul_rn(uHa.x, ay0)), ups.mul),
+                           __fmul_rn(__fmaf_rn(uHb.y, fy, __fmul_rn(uHa.y, ay0)), ups.mul));
+      } else {
+        if constexpr (REUSE) return ld_volatile_f2(fin + ((unsigned)yc * uw + (unsigned)x));
+        return __ldg(fin + ((unsigned)yc * uw + (unsigned)x));
       }
-      if constexpr (REUSE) return ld_volatile_f2(fin + ((unsigned)yc * uw + (unsigned)x));
-      return __ldg(fin + ((unsigned)yc * uw + (unsigned)x));
     };
     auto stage_row = [&](int buf, int rr) { return stage + ((buf * CH + rr) * 5) * COLS + tid; };
 
@@ -261,24 +296,36 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         if (reuse_b) W = Y;                                        // (select per thread: 10 predicated moves)
         ring_step(um_finish_rows(pb, W, Z, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
       };
-      float2 fa = flow_at(t_first, ups_row(t_first)), fb = flow_at(t_first + 1, ups_row(t_first + 1));
-      int2 ua = ups_row(t_first + 2), ub = ups_row(t_first + 3);      // table entries of the next chunk's rows
+      float2 fa = flow_at(t_first), fb = flow_at(t_first + 1);
       // warm-up: the R-1 = 2m rows above the first output row, chunk by chunk (unrolled for a compile-time radius: the
       // rolled loop measured 3 % slower over a whole 1080p step)
       for (int t = t_first; t < t_first + R - 1; t += 2) {
         float V[5];
         issue2(fa, fb, t);
-        fa = flow_at(t + 2, ua); fb = flow_at(t + 3, ub);
-        ua = ups_row(t + 4); ub = ups_row(t + 5);
+        fa = flow_at(t + 2); fb = flow_at(t + 3);
         finish_a(t, V);
         finish_b(t + 1, V);
       }
       int buf = 0;
+#if OFB_EXP_L2PF > 0
+      const int pf_xs = max(x_base & ~3, 0), pf_n = min((x_base + COLS + 3) & ~3, w) - pf_xs;
+      const bool pf_on = tid == 0 && (w & 3) == 0 && pf_n > 0;
+#endif
       for (int c = 0; c < n_chunks; c++) {
         const int tc = y0 + c * CH + m;                              // newest matrix row of output row y0 + c*CH
+#if OFB_EXP_L2PF > 0
+        if (pf_on) {
+#pragma unroll
+          for (int rr = 0; rr < 2; rr++) {
+            const unsigned o = (unsigned)clampi(tc + 2 * OFB_EXP_L2PF + rr, 0, h - 1) * uw + (unsigned)pf_xs;
+            bulk_prefetch_l2(RA0 + o, (unsigned)pf_n * 16u);
+            bulk_prefetch_l2(RB0 + o, (unsigned)pf_n * 4u);
+            if constexpr (!UPS) bulk_prefetch_l2(fin + o, (unsigned)pf_n * 8u);
+          }
+        }
+#endif
         issue2(fa, fb, tc);
-        fa = flow_at(tc + 2, ua); fb = flow_at(tc + 3, ub);
-        ua = ups_row(tc + 4); ub = ups_row(tc + 5);
+        fa = flow_at(tc + 2); fb = flow_at(tc + 3);
         if (c >= NBUF) named_bar_sync(BAR_EMPTY0 + buf, NT);         // consumers released this buffer
         float V[5];
         finish_a(tc, V);
@@ -308,7 +355,7 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
           const unsigned op = (unsigned)clampi(t + PFD, 0, h - 1) * uw + (unsigned)x;
           prefetch_l2(RA0 + op);
           prefetch_l2(RB0 + op);
-          if (!do_ups) prefetch_l2(fin + ((unsigned)clampi(t + PFD + 1, 0, h - 1) * uw + (unsigned)x));
+          if constexpr (!UPS) prefetch_l2(fin + ((unsigned)clampi(t + PFD + 1, 0, h - 1) * uw + (unsigned)x));
           const unsigned g = L.inside ? (unsigned)__float2int_rd((float)y + L.dy) * uw + (unsigned)__float2int_rd((float)x + L.dx) : 0u;
           prefetch_l2(RA1 + (g + (PFD + 1) * uw));
           prefetch_l2(RB1 + (g + (PFD + 1) * uw));
@@ -318,16 +365,14 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         const int y = clampi(t, 0, h - 1);
         ring_step(um_finish2(L, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
       };
-      float2 fl = flow_at(t_first, ups_row(t_first));
-      int2 un = ups_row(t_first + 1);
+      float2 fl = flow_at(t_first);
       // warm-up: the R-1 rows above the first output row (no hand-over)
 #pragma unroll 1
       for (int t = t_first; t < t_first + R - 1; t++) {
         UmLoads2 L;
         float V[5];
         issue(L, fl, t);
-        fl = flow_at(t + 1, un);
-        un = ups_row(t + 2);
+        fl = flow_at(t + 1);
         finish(L, t, V);
       }
       int buf = 0;
@@ -340,8 +385,7 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
             UmLoads2 L;
             float V[5];
             issue(L, fl, yo + m);
-            fl = flow_at(yo + m + 1, un);
-            un = ups_row(yo + m + 2);
+            fl = flow_at(yo + m + 1);
             finish(L, yo + m, V);
             float* srow = stage_row(buf, rr);
 #pragma unroll

@@ -6,16 +6,16 @@
 namespace ofb {
 
 cudaError_t launch_iter_fixed_b(ofb_handle* h, int m, const float2* fin, float2* fout, int w, int hh, int n_pairs,
-                                const RSet& rs, float reg, cudaStream_t st, const UpsSrc* ups, bool* served) {
+                                const RSet& rs, float reg, cudaStream_t st, bool* served) {
   *served = true;
   switch (m) {
-    case 9: return launch_iter_v<9, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
-    case 10: return launch_iter_v<10, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
-    case 11: return launch_iter_v<11, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
-    case 12: return launch_iter_v<12, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
-    case 13: return launch_iter_v<13, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
-    case 14: return launch_iter_v<14, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
-    case 15: return launch_iter_v<15, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, ups);
+    case 9: return launch_iter_v<9, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, nullptr);
+    case 10: return launch_iter_v<10, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, nullptr);
+    case 11: return launch_iter_v<11, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, nullptr);
+    case 12: return launch_iter_v<12, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, nullptr);
+    case 13: return launch_iter_v<13, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, nullptr);
+    case 14: return launch_iter_v<14, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, nullptr);
+    case 15: return launch_iter_v<15, 128, 2, 3, 0, false, true, false, 2>(h, fin, fout, w, hh, n_pairs, rs, m, reg, st, nullptr);
     default: break;
   }
   *served = false;

@@ -185,6 +185,7 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
       ups.prev = h->d_flow[prev_idx]; ups.pw = pl.sched[li - 1].width; ups.ph = pl.sched[li - 1].height;
       ups.tabx = h->d_lintab + h->tab_x_off[li]; ups.taby = h->d_lintab + h->tab_y_off[li];
       ups.mul = (float)(1.0 / p->pyr_scale);
+      ups.exact2y = hh == 2 * ups.ph;
       up = &ups;
     }
   }
@@ -203,10 +204,13 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
   // (own buffers for the prefetch addresses; the kernel takes remote rows from the peer table)
   const RSet rs1 = {RA, RB, RA + (size_t)w * hh, RB + (size_t)w * hh};
   TB(OFB_STAGE_ITERATION);
-  if (pl.bc.m == 7)
-    e = launch_iter_v<7, 256, 2, 2, 3, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
-  else
-    e = launch_iter_v<0, 128, 4, 1, 0, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
+  if (pl.bc.m == 7) {
+    if (up) e = launch_iter_v<7, 256, 2, 2, 3, true, false, false, 2, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
+    else e = launch_iter_v<7, 256, 2, 2, 3, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
+  } else {
+    if (up) e = launch_iter_v<0, 128, 4, 1, 0, true, false, false, 2, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
+    else e = launch_iter_v<0, 128, 4, 1, 0, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
+  }
   if (e != cudaSuccess) return set_error(h, OFB_ERR_CUDA, "tiled k_iter_v launch failed: %s", cudaGetErrorString(e));
   h->launches++;
   TE();
