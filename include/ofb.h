@@ -269,6 +269,11 @@ int ofb_flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_
 /* Copies the handle's current field(s) (the last flow result, post-filtered or not) to n host float32
  * [height][width][2] arrays (flow_stride_bytes = 0: packed rows).  Synchronous. */
 int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes);
+/* The nodes' flow visualisation `flow_to_color` (ros2_ws/src/liteflownet3/liteflownet3/sub_n_pub_lfn3_node.py:132-140:
+ * cartToPolar -> hue = angle / 2, value = magnitude normalised to 0..255 over the frame, saturation 255 -> HSV2BGR) of
+ * field `pair` of the handle's current result, computed on the device, bit-exact against the cv2 recipe.
+ * bgr_out: host uint8 [height][width][3] (stride_bytes = 0: packed rows).  Synchronous. */
+int ofb_flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes);
 /* Flow of pair `pair` of the handle's current field at n integer pixel positions xy = [n][2] (x, y): out_dxdy =
  * [n][2] float32 (dx, dy), NaN for positions outside the frame.  The junction node's lookup of the predicted
  * junction positions (ros2_ws/src/liteflownet3/liteflownet3/lfn3_junction_node.py:207-214) without downloading the

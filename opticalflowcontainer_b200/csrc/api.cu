@@ -831,6 +831,11 @@ int ofb_flow_sample(ofb_handle* h, int pair, int n_points, const int* xy, float*
   return flow_sample(h, pair, n_points, xy, out_dxdy);
 }
 
+int ofb_flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  return flow_to_bgr(h, pair, bgr_out, stride_bytes);
+}
+
 int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes) {
   if (!h) return OFB_ERR_INVALID_ARG;
   return flow_download(h, n, flow, flow_stride_bytes);

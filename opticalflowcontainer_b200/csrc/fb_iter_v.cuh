@@ -42,9 +42,19 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// Per-warp staging ring of the regular inputs of the two-rows-in-flight schedule (TMAR): the R0 rows (float4 + float) and
+// the input-flow rows of the warp's 32 columns arrive by bulk copies TR_CHUNKS chunks ahead of their use.
+#ifndef OFB_EXP_TR_CHUNKS
+#define OFB_EXP_TR_CHUNKS 3
+#endif
+constexpr int TR_CHUNKS = OFB_EXP_TR_CHUNKS;  // chunk slots per warp (2 rows each); shared memory spent here is L1 lost to the gathers
+constexpr int TR_W = 36;                     // columns per slot row: the 4-aligned hull of 32 columns
+constexpr int TR_ROW_BYTES = TR_W * (16 + 8 + 4);
+constexpr int TR_WARP_BYTES = 2 * TR_CHUNKS * TR_ROW_BYTES + 64;     // + the slots' mbarriers
+
 template <int COLS, int CH>
-constexpr int iter_v_smem_floats(int m, bool tmem, int nbuf) {
-  return (nbuf * CH + (tmem ? 0 : 2 * m + 1)) * 5 * COLS;
+constexpr int iter_v_smem_floats(int m, bool tmem, int nbuf, bool tmar = false) {
+  return (nbuf * CH + (tmem ? 0 : 2 * m + 1)) * 5 * COLS + (tmar ? (COLS / 32) * TR_WARP_BYTES / 4 : 0);
 }
 
 constexpr int kTmemRingStride = 8;    // TMEM columns per ring slot (5 used; x4 + x1 accesses stay aligned)
@@ -102,6 +112,30 @@ __device__ __forceinline__ void tmem_st5(uint32_t taddr, const float (&v)[5]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) completing on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -116,7 +150,13 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 // UPS: first iteration of a level — the input flow is the bilinear upsample of the coarser level's result (UpsSrc),
 // computed by the producers: a thread marching down its column keeps the horizontally blended coarse flow of the two
 // coarse rows around it and loads a new coarse row only when it crosses one (every second row at pyr_scale 0.5).
-template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF, bool UPS>
+// TMAR: the regular inputs of the two-rows-in-flight schedule — the R0 rows and (plain launches) the input-flow rows — are
+// staged in shared memory by bulk asynchronous copies (TMA, cp.async.bulk completing on mbarriers), per warp, TR_CHUNKS
+// chunks ahead.  They cost no registers while in flight, the flow of the NEXT chunk is at hand early, and the gather of
+// chunk v+1 is issued between the two halves of chunk v (its top row as soon as chunk v's top half is consumed), so
+// every R1 load has about half an iteration to land instead of being waited for right after its issue (ncu before:
+// long-scoreboard the top producer stall, issue 59 %, L1 62 %, DRAM 38 %).  Needs w % 4 == 0 (16-byte copy granules).
+template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF, bool UPS, bool TMAR = false>
 __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     k_iter_v(const RSet rs, const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int w, int h, int m_rt,
              float reg, int seg_rows, int strips, int y_begin, int y_end, PeerTab tab, int my_rank, UpsSrc ups) {
@@ -128,6 +168,7 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
   static_assert(!TMEM || (COLS == 256 && MT >= 1 && (2 * MT + 1) * kTmemRingStride <= kTmemWgCols),
                 "TMEM ring: two producer warpgroups, ring slots within the warpgroup's columns");
   static_assert(NBUF >= 2 && 1 + 2 * NBUF <= 16, "named barriers");
+  static_assert(!TMAR || (REUSE && TMEM && MT > 0), "staged inputs: the default schedule only");
   constexpr bool REGMOVE = REUSE && COLS == 256 && MINB == 2;   // setmaxnreg 96 / 48
   constexpr int NT = COLS + NCONS;
   constexpr int BAR_FULL0 = 1, BAR_EMPTY0 = 1 + NBUF;
@@ -224,6 +265,9 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     auto ups_hrow = [&](int r) -> float2 {
       const float2* p = uprev + (unsigned)r * (unsigned)ups.pw;
       const float2 q0 = __ldg(p + ux0), q1 = __ldg(p + ux1);
+      // the next coarse row this column will cross, pulled into L1 now: the blend below waits for q0 / q1 right away
+      // (ncu: 20 % of the producers' samples sat on that wait when every new row came from L2)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (r + 1 < ups.ph ? ups.pw : 0) + ux1));
       return make_float2(__fmaf_rn(q1.x, ufx, __fmul_rn(q0.x, uax0)), __fmaf_rn(q1.y, ufx, __fmul_rn(q0.y, uax0)));
     };
     // input flow of matrix row t at this column.  Plain launches: one load (volatile in the two-rows-in-flight schedule:
@@ -264,7 +308,119 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     };
     auto stage_row = [&](int buf, int rr) { return stage + ((buf * CH + rr) * 5) * COLS + tid; };
 
-    if constexpr (REUSE) {
+    if constexpr (REUSE && TMAR) {
+      // ---- staged inputs + interleaved gathers (see TMAR above).  Virtual chunk v = matrix rows t_first + 2v, + 1:
+      // the m warm-up chunks, then the output chunks.
+      const int wid = tid >> 5, lane = tid & 31;
+      char* wbase = reinterpret_cast<char*>(smem + NBUF * CH * 5 * COLS) + wid * TR_WARP_BYTES;
+      float4* s_ra = reinterpret_cast<float4*>(wbase);                                   // [2 * TR_CHUNKS][TR_W]
+      float2* s_fl = reinterpret_cast<float2*>(wbase + 2 * TR_CHUNKS * TR_W * 16);
+      float* s_rb = reinterpret_cast<float*>(wbase + 2 * TR_CHUNKS * TR_W * 24);
+      uint64_t* s_bar = reinterpret_cast<uint64_t*>(wbase + 2 * TR_CHUNKS * TR_ROW_BYTES);
+      // the warp's column slice: 4-aligned hull of its (clamped) columns
+      const int xmin = clampi(x_base + 32 * wid, 0, w - 1), xmax = clampi(x_base + 32 * wid + 31, 0, w - 1);
+      const int xs = xmin & ~3, xn = min((xmax + 4) & ~3, w) - xs;
+      const int cx = x - xs;
+      const int nv = m + n_chunks;
+      auto copy_chunk = [&](int v) {            // lane 0: rows of virtual chunk v -> slot v % TR_CHUNKS
+        const int sl = v % TR_CHUNKS;
+        uint64_t* bar = s_bar + sl;
+        mbar_expect_tx(bar, 2u * (unsigned)xn * (UPS ? 20u : 28u));
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const unsigned o = (unsigned)clampi(t_first + 2 * v + j, 0, h - 1) * uw + (unsigned)xs;
+          bulk_g2s(s_ra + (2 * sl + j) * TR_W, RA0 + o, (unsigned)xn * 16u, bar);
+          bulk_g2s(s_rb + (2 * sl + j) * TR_W, RB0 + o, (unsigned)xn * 4u, bar);
+          if constexpr (!UPS) bulk_g2s(s_fl + (2 * sl + j) * TR_W, fin + o, (unsigned)xn * 8u, bar);
+        }
+      };
+      if (lane == 0) {
+        for (int i = 0; i < TR_CHUNKS; i++) mbar_init(s_bar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int v = 0; v < min(TR_CHUNKS, nv); v++) copy_chunk(v);
+      }
+      __syncwarp();
+      UmRow X, Y, Z, W;
+      struct { float fx, fy; unsigned g; bool inside; } pa, pb;
+      float2 fa = make_float2(0.f, 0.f), fb = fa;                    // UPS: the chunk's input flow (computed, not staged)
+      bool reuse_b = false;
+      Z.q0 = Z.q1 = make_float4(0.f, 0.f, 0.f, 0.f); Z.s0 = Z.s1 = 0.f;
+      W = Z; X = Z; Y = Z;
+      auto pix = [&](decltype(pa)& P, float2 fl, int y) {            // (um_pix without the R0 loads)
+        const float fx = (float)x + fl.x, fy = (float)y + fl.y;
+        const int ix = __float2int_rd(fx), iy = __float2int_rd(fy);
+        P.fx = fx - (float)ix;
+        P.fy = fy - (float)iy;
+        P.inside = (unsigned)ix < uw - 1u && (unsigned)iy < uh - 1u;
+        P.g = P.inside ? (unsigned)iy * uw + (unsigned)ix : 0u;
+      };
+      auto wait_chunk = [&](int v) { mbar_wait(s_bar + v % TR_CHUNKS, (unsigned)(v / TR_CHUNKS) & 1u); };
+      auto flow_of = [&](int v, int j) -> float2 {
+        if constexpr (UPS) return flow_at(t_first + 2 * v + j);
+        else return s_fl[(2 * (v % TR_CHUNKS) + j) * TR_W + cx];
+      };
+      // top half of chunk v: pixel A; top corner row from the previous chunk's bottom row (Z) when it lines up
+      auto issue_a = [&](int v, unsigned prev_g) {
+        const int ya = clampi(t_first + 2 * v, 0, h - 1);
+        fa = flow_of(v, 0);
+        pix(pa, fa, ya);
+        if (pa.g != prev_g + uw) um_row_load(X, RA1, RB1, pa.g); else X = Z;
+        um_row_load(Y, RA1, RB1, pa.g + uw);
+      };
+      auto issue_b = [&](int v) {
+        const int yb = clampi(t_first + 2 * v + 1, 0, h - 1);
+        fb = flow_of(v, 1);
+        pix(pb, fb, yb);
+        reuse_b = pa.inside && pb.g == pa.g + uw;
+        if (!reuse_b) um_row_load(W, RA1, RB1, pb.g);
+        um_row_load(Z, RA1, RB1, pb.g + uw);
+      };
+      auto finish_half = [&](int v, int j, const decltype(pa)& P, const UmRow& top, const UmRow& bot, float2 fl, float (&V)[5]) {
+        const int y = clampi(t_first + 2 * v + j, 0, h - 1);
+        const int si = (2 * (v % TR_CHUNKS) + j) * TR_W + cx;
+        const float4 a0 = s_ra[si];
+        const float b0 = s_rb[si];
+        if constexpr (!UPS) fl = s_fl[si];
+        ring_step(um_arith(a0, b0, top.q0, top.q1, bot.q0, bot.q1, top.s0, top.s1, bot.s0, bot.s1, P.fx, P.fy, fl.x, fl.y,
+                           P.inside, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
+      };
+      wait_chunk(0);
+      issue_a(0, ~0u - uw);
+      issue_b(0);
+      int buf = 0;
+      for (int v = 0; v < nv; v++) {
+        const int c = v - m;                                         // output chunk (negative: warm-up)
+        if (c >= NBUF) named_bar_sync(BAR_EMPTY0 + buf, NT);         // consumers released this buffer
+        float V[5];
+        finish_half(v, 0, pa, X, Y, fa, V);
+        if (c >= 0) {
+          float* s0 = stage_row(buf, 0);
+#pragma unroll
+          for (int ch = 0; ch < 5; ch++) s0[ch * COLS] = V[ch];
+        }
+        if (reuse_b) W = Y;                                          // B's top row is A's bottom row: keep it, Y is refilled now
+        const unsigned g_b = pb.inside ? pb.g : ~0u - uw;
+        if (v + 1 < nv) {
+          wait_chunk(v + 1);                                         // (requested TR_CHUNKS - 1 chunks ago)
+          issue_a(v + 1, g_b);                                       // X <- Z (copy) or load; Y <- load: both free now
+        }
+        finish_half(v, 1, pb, W, Z, fb, V);                          // (a row past y1 keeps the state consistent; never read)
+        if (c >= 0) {
+          float* s1 = stage_row(buf, 1);
+#pragma unroll
+          for (int ch = 0; ch < 5; ch++) s1[ch * COLS] = V[ch];
+          named_bar_arrive(BAR_FULL0 + buf, NT);                     // staged rows of chunk c are ready
+          if (++buf == NBUF) buf = 0;
+        }
+        if (v + 1 < nv) issue_b(v + 1);                              // W, Z free now
+        // the warp is done with the slot of chunk v: refill it
+        __syncwarp();
+        if (lane == 0 && v + TR_CHUNKS < nv) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          copy_chunk(v + TR_CHUNKS);
+        }
+      }
+    } else if constexpr (REUSE) {
       // Two rows in flight AND row-reuse gather.  Rows A = t, B = t + 1 of a chunk: all loads of both are issued
       // before the first is consumed.  Corner-row register sets: X = top of A, Y = bottom of A (and top of B when B
       // sits exactly one row below A), W = top of B otherwise, Z = bottom of B.  The next chunk's A takes Z as its top

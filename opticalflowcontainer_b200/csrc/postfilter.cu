@@ -188,6 +188,109 @@ int flow_sample(ofb_handle* h, int pair, int n_points, const int* xy, float* out
   return OFB_OK;
 }
 
+// ---- flow visualisation: the nodes' flow_to_color (sub_n_pub_lfn3_node.py:132-140) on the device ------------------
+//   mag, ang = cv2.cartToPolar(u, v); H = uint8(ang * 180 / pi / 2); S = 255;
+//   V = uint8(cv2.normalize(mag, None, 0, 255, NORM_MINMAX)); cv2.cvtColor(hsv, COLOR_HSV2BGR)
+// with the wheel's arithmetic (oracle/visual_np.py, pinned bit for bit): magnitude sqrt(fma(u, u, v*v)); fastAtan's
+// 7th-order polynomial evaluated with FMAs in degrees, times pi/180; normalisation fma(mag, scale, shift) with scale and
+// shift from the field's min / max in double; HSV2BGR as in the colour pre-filter (truncating in the 32-pixel vector body
+// of a row, rounding in its tail).
+__device__ __forceinline__ float viz_mag(float2 f) { return __fsqrt_rn(__fmaf_rn(f.x, f.x, __fmul_rn(f.y, f.y))); }
+
+__global__ void __launch_bounds__(256) k_viz_minmax(const float2* __restrict__ f, size_t n, unsigned int* __restrict__ mm) {
+  float lo = __int_as_float(0x7f800000), hi = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float m = viz_mag(f[i]);
+    lo = fminf(lo, m);
+    hi = fmaxf(hi, m);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {      // magnitudes are >= 0: float order = unsigned bit order
+    atomicMin(mm, __float_as_uint(lo));
+    atomicMax(mm + 1, __float_as_uint(hi));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_viz_color(const float2* __restrict__ f, int w, int h, const unsigned int* __restrict__ mm,
+                                                   uint8_t* __restrict__ dst, size_t dp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const float2 v = f[(size_t)y * w + x];
+  // cartToPolar angle (v_atan_f32): degrees by the polynomial, then * pi/180
+  const float k = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = __fmul_rn(0.9997878412794807f, k), p3 = __fmul_rn(-0.3258083974640975f, k);
+  const float p5 = __fmul_rn(0.1555786518463281f, k), p7 = __fmul_rn(-0.04432655554792128f, k);
+  const float ax = fabsf(v.x), ay = fabsf(v.y);
+  const float c = __fdiv_rn(fminf(ax, ay), __fadd_rn(fmaxf(ax, ay), 2.220446049250313e-16f));
+  const float cc = __fmul_rn(c, c);
+  float a = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmaf_rn(cc, p7, p5), cc, p3), cc, p1), c);
+  a = ax >= ay ? a : __fsub_rn(90.f, a);
+  a = v.x < 0.f ? __fsub_rn(180.f, a) : a;
+  a = v.y < 0.f ? __fsub_rn(360.f, a) : a;
+  const float ang = __fmul_rn(a, (float)(3.14159265358979323846 / 180.0));
+  const int H = (int)__fdiv_rn(__fdiv_rn(__fmul_rn(ang, 180.f), (float)3.14159265358979323846), 2.f) & 255;
+  // normalize(NORM_MINMAX, 0..255): scale / shift in double from the field's extrema, applied as one float FMA
+  const double smin = (double)__uint_as_float(mm[0]), smax = (double)__uint_as_float(mm[1]);
+  const double scale = 255.0 * (smax - smin > 2.220446049250313e-16 ? 1.0 / (smax - smin) : 0.0);
+  const double shift = 0.0 - smin * scale;
+  const int V = (int)__fmaf_rn(viz_mag(v), (float)scale, (float)shift) & 255;
+  // HSV -> BGR, S = 255
+  const float s = __fmul_rn(255.f, 1.f / 255.f), vv = __fmul_rn((float)V, 1.f / 255.f);
+  const float hf = __fmul_rn((float)H, 6.f / 180.f);
+  int sec = (int)floorf(hf);
+  const float fr = __fsub_rn(hf, (float)sec);
+  sec %= 6;
+  const float t1 = __fmul_rn(vv, __fsub_rn(1.f, s));
+  const float t2 = __fmul_rn(vv, __fmaf_rn(-s, fr, 1.f));
+  const float t3 = __fmul_rn(vv, __fmaf_rn(-s, __fsub_rn(1.f, fr), 1.f));
+  float b, g, r;
+  switch (sec) {
+    case 0: b = t1; g = t3; r = vv; break;
+    case 1: b = t1; g = vv; r = t2; break;
+    case 2: b = t3; g = vv; r = t1; break;
+    case 3: b = vv; g = t2; r = t1; break;
+    case 4: b = vv; g = t1; r = t3; break;
+    default: b = t2; g = t1; r = vv; break;
+  }
+  const bool body = x < (w / 32) * 32;
+  const float fR = __fmul_rn(r, 255.f), fG = __fmul_rn(g, 255.f), fB = __fmul_rn(b, 255.f);
+  uint8_t* o = dst + (size_t)y * dp + (size_t)x * 3;
+  o[0] = (uint8_t)min(max(body ? (int)fB : __float2int_rn(fB), 0), 255);
+  o[1] = (uint8_t)min(max(body ? (int)fG : __float2int_rn(fG), 0), 255);
+  o[2] = (uint8_t)min(max(body ? (int)fR : __float2int_rn(fR), 0), 255);
+}
+
+int flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes) {
+  if (!h->last_flow || pair < 0 || pair >= h->last_n)
+    return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_to_bgr: no flow field %d on the device", pair);
+  if (!bgr_out) return set_error(h, OFB_ERR_INVALID_ARG, "NULL output pointer");
+  const int w = h->last_w, hh = h->last_h;
+  if (stride_bytes == 0) stride_bytes = (size_t)w * 3;
+  if (stride_bytes < (size_t)w * 3) return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // the image and the two extrema live in the scratch the reductions use (3 B per pixel <= the 8 B per pixel of d_flow[x])
+  const float2* f = reinterpret_cast<const float2*>(h->last_flow) + (size_t)pair * w * hh;
+  float2* freebuf = reinterpret_cast<const float2*>(h->last_flow) == h->d_flow[0] ? h->d_flow[1] : h->d_flow[0];
+  uint8_t* img = reinterpret_cast<uint8_t*>(freebuf) + 256;
+  unsigned int* mm = reinterpret_cast<unsigned int*>(freebuf);
+  const unsigned int init[2] = {0x7f800000u, 0u};
+  OFB_CUDA(h, cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  int s;
+  if ((s = timing_begin(h, OFB_STAGE_OTHER))) return s;
+  k_viz_minmax<<<2 * h->num_sms, 256, 0, st>>>(f, (size_t)w * hh, mm);
+  OFB_LAUNCH_CHECK(h);
+  k_viz_color<<<dim3((w + 255) / 256, hh), 256, 0, st>>>(f, w, hh, mm, img, (size_t)w * 3);
+  OFB_LAUNCH_CHECK(h);
+  if ((s = timing_end(h))) return s;
+  OFB_CUDA(h, cudaMemcpy2DAsync(bgr_out, stride_bytes, img, (size_t)w * 3, (size_t)w * 3, hh, cudaMemcpyDeviceToHost, st));
+  OFB_CUDA(h, cudaStreamSynchronize(st));
+  return OFB_OK;
+}
+
 int flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes) {
   if (!h->last_flow || n < 1 || n > h->last_n)
     return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_download: no flow field of %d pair(s) on the device", n);

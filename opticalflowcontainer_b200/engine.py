@@ -451,6 +451,15 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out[:n.value].reshape(-1, 1, 2).copy()
 
+    def flow_to_color(self, height: int, width: int, pair: int = 0) -> np.ndarray:
+        """The nodes' ``flow_to_color`` (sub_n_pub_lfn3_node.py:132-140) of the handle's current field ``pair`` (of
+        ``height`` x ``width``, as for :meth:`flow_download`), computed on the device → uint8 [H,W,3] BGR."""
+        out = np.empty((height, width, 3), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_flow_to_bgr(self._h, int(pair), out.ctypes.data, 0)
+            _lib.check(st, self._h)
+        return out
+
     def lk_stream(self, frame, maxCorners=2000, qualityLevel=0.01, minDistance=7, blockSize=3, winSize=(21, 21),
                   maxLevel=3, criteria=(3, 30, 0.01), minEigThreshold=1e-4, flags=0):
         """Camera-stream form of goodFeaturesToTrack + calcOpticalFlowPyrLK (ofb_lk_stream): one new frame per call, the

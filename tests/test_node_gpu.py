@@ -333,3 +333,26 @@ def test_adapt_prefilter_bit_exact(engine_factory, size):
         got, used = eng.adapt_prefilter(bgr, clip, (1.0, 4.0, 0.1, 0.8), (8, 8))
         assert abs(used - c) <= 1e-9 * max(1.0, abs(c))
         assert np.array_equal(got, want)
+
+
+def test_flow_to_color_matches_cv2_recipe(built_lib):
+    """ofb_flow_to_bgr: the nodes' flow_to_color (sub_n_pub_lfn3_node.py:132-140) on the device, bit for bit against the
+    cv2 recipe applied to the downloaded field — at a width with a 32-pixel vector body and a scalar tail."""
+    import cv2
+    import opticalflowcontainer_b200 as ofb
+    from oracle import visual_np as V
+    for (h, w) in [(135, 240), (97, 131)]:
+        a, b = synth.synth_warp_pair(h, w, 23, angle_deg=2.0, zoom=1.03)
+        eng = ofb.FlowEngine(w, h, 1, 0)
+        try:
+            flow = eng.farneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+            got = eng.flow_to_color(h, w)
+            hsv = np.zeros((h, w, 3), np.uint8)
+            hsv[..., 1] = 255
+            mag, ang = cv2.cartToPolar(flow[..., 0], flow[..., 1])
+            hsv[..., 0] = (ang * 180 / np.pi / 2).astype(np.uint8)
+            hsv[..., 2] = cv2.normalize(mag, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+            assert np.array_equal(got, cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR))
+            assert np.array_equal(got, V.flow_to_color(flow))
+        finally:
+            eng.close()

@@ -166,7 +166,9 @@ def test_pyrlk_accepts_pyramids(built_lib):
     for with_d in (True, False):
         _, pa = cv2.buildOpticalFlowPyramid(a, (21, 21), 2, withDerivatives=with_d)
         _, pb = cv2.buildOpticalFlowPyramid(b, (21, 21), 2, withDerivatives=with_d)
-        ref = cv2.calcOpticalFlowPyrLK(pa, pb, pts, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+        # (the Python binding of the wheel rejects pyramid tuples — "prevImg is not a numerical tuple" — so the reference is
+        # the image call at the pyramid's depth, which is what the C++ function computes from such pyramids)
+        ref = cv2.calcOpticalFlowPyrLK(a, b, pts, None, winSize=(21, 21), maxLevel=2, criteria=(3, 30, 0.01))
         got = ofb.calcOpticalFlowPyrLK(pa, pb, pts, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
         _lk_check(ref, got)
         # the pyramid's depth (2) limits maxLevel: the same as images with maxLevel=2
