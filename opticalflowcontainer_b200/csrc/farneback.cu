@@ -36,9 +36,6 @@
 #ifndef OFB_EXP_FUSE_UPS
 #define OFB_EXP_FUSE_UPS true
 #endif
-#ifndef OFB_EXP_TMAR
-#define OFB_EXP_TMAR false
-#endif
 
 namespace ofb {
 
@@ -750,11 +747,7 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
         }
         cudaError_t e;
         if (bc.m == 7) {
-          // staged inputs (TMA) where the rows are multiples of 16 bytes; else the same schedule with register loads
-          const bool tmar = OFB_EXP_TMAR && OFB_EXP_TMEM && (w & 3) == 0;
-          if (up && tmar) e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF, true, OFB_EXP_TMAR && OFB_EXP_TMEM>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, up);
-          else if (up) e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF, true>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, up);
-          else if (tmar) e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF, false, OFB_EXP_TMAR && OFB_EXP_TMEM>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, nullptr);
+          if (up) e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF, true>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, up);
           else e = launch_iter_v<7, 256, 2, 2, 0, false, true, OFB_EXP_TMEM, OFB_EXP_NBUF>(h, fin, fout, w, hh, n_pairs, rs, bc.m, reg, st, nullptr);
         } else {
           // other window sizes: the radius as a template argument where an instantiation exists (winsize 5..31), else

@@ -10,8 +10,7 @@ namespace ofb {
 
 // k_iter_v launcher.  ups != nullptr: the launch is the first iteration of a level and upsamples its input flow from
 // the coarser level on the fly (fin is not read).
-template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF, bool UPS = false,
-          bool TMAR = false>
+template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF, bool UPS = false>
 static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout, int w, int hh, int n_pairs,
                                  const RSet& rs, int m, float reg, cudaStream_t st, const UpsSrc* ups = nullptr,
                                  int y_begin = 0, int y_end = -1, const PeerTab* tab = nullptr, int my_rank = 0) {
@@ -22,9 +21,8 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   UpsSrc u;
   if (ups) u = *ups; else memset(&u, 0, sizeof(u));
   if (UPS != (ups != nullptr)) return cudaErrorInvalidValue;   // the instantiation and the launch must agree
-  if (TMAR && (w & 3)) return cudaErrorInvalidValue;           // bulk copies move 16-byte granules of 4-byte rows
-  auto kern = k_iter_v<MT, COLS, CH, MINB, PFD, TILED, REUSE, TMEM, NBUF, UPS, TMAR>;
-  const int smem = iter_v_smem_floats<COLS, CH>(m, TMEM, NBUF, TMAR) * (int)sizeof(float);
+  auto kern = k_iter_v<MT, COLS, CH, MINB, PFD, TILED, REUSE, TMEM, NBUF, UPS>;
+  const int smem = iter_v_smem_floats<COLS, CH>(m, TMEM, NBUF) * (int)sizeof(float);
   // largest dynamic smem configured for this instantiation, per device (function attributes are per device)
   static int configured[64] = {0};
   const int dev = h->device & 63;
@@ -42,13 +40,14 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
     }
     configured[dev] = smem;
   }
-  const int tw = COLS - 2 * m;
+  const int tw = COLS - 2 * iter_v_halo(MT, m);
   const int strips = (w + tw - 1) / tw;
   const int slots = MINB * h->num_sms;
   const int per = strips * n_pairs;
   const int rows = y_end - y_begin;
   int segs = per >= slots ? 1 : slots / per;
   int seg_rows = std::max(16, (rows + segs - 1) / segs);
+  seg_rows += seg_rows & 1;       // even: the chunks of the fused upsample then start on odd rows (fb_iter_v.cuh)
   segs = (rows + seg_rows - 1) / seg_rows;
   dim3 g(strips * segs, n_pairs);
   kern<<<g, COLS + CH * COLS / 4, smem, st>>>(rs, fin, fout, w, hh, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank, u);

@@ -27,6 +27,7 @@
 //     two producer warpgroups (96).
 //   plain: one row in flight + L2 prefetch PFD rows ahead (tiled mode, run-time radius fallback).
 #pragma once
+#include <type_traits>
 #include "fb_device.cuh"
 #include "fb_um.cuh"
 
@@ -42,19 +43,16 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// Per-warp staging ring of the regular inputs of the two-rows-in-flight schedule (TMAR): the R0 rows (float4 + float) and
-// the input-flow rows of the warp's 32 columns arrive by bulk copies TR_CHUNKS chunks ahead of their use.
-#ifndef OFB_EXP_TR_CHUNKS
-#define OFB_EXP_TR_CHUNKS 3
-#endif
-constexpr int TR_CHUNKS = OFB_EXP_TR_CHUNKS;  // chunk slots per warp (2 rows each); shared memory spent here is L1 lost to the gathers
-constexpr int TR_W = 36;                     // columns per slot row: the 4-aligned hull of 32 columns
-constexpr int TR_ROW_BYTES = TR_W * (16 + 8 + 4);
-constexpr int TR_WARP_BYTES = 2 * TR_CHUNKS * TR_ROW_BYTES + 64;     // + the slots' mbarriers
+// Columns of window halo on each side of a strip.  Radius 7 (winsize 15, the default) and 15 take one column more than the
+// window needs: strips then start at a multiple of 8 pixels, so the R0 rows (16 B per pixel) are read in whole 128-byte
+// lines, the flow rows in whole sectors, and the consumers' 16-byte flow stores are always aligned (with a halo of 7 every
+// strip started at an odd x: 5 lines per LDG.128 instead of 4 and four 8-byte stores per thread instead of two 16-byte ones).
+// 1920 / 960 / 480 / 240 / 3840 split into the same number of 240-column strips as of 242-column ones.
+__host__ __device__ constexpr int iter_v_halo(int mt, int m) { return (mt == 7 || mt == 15) ? mt + 1 : m; }
 
 template <int COLS, int CH>
-constexpr int iter_v_smem_floats(int m, bool tmem, int nbuf, bool tmar = false) {
-  return (nbuf * CH + (tmem ? 0 : 2 * m + 1)) * 5 * COLS + (tmar ? (COLS / 32) * TR_WARP_BYTES / 4 : 0);
+constexpr int iter_v_smem_floats(int m, bool tmem, int nbuf) {
+  return (nbuf * CH + (tmem ? 0 : 2 * m + 1)) * 5 * COLS;
 }
 
 constexpr int kTmemRingStride = 8;    // TMEM columns per ring slot (5 used; x4 + x1 accesses stay aligned)
@@ -110,30 +108,47 @@ __device__ __forceinline__ void tmem_st5(uint32_t taddr, const float (&v)[5]) {
                "f"(v[2]), "f"(v[3]) : "memory");
   asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + 4u), "f"(v[4]) : "memory");
 }
+// one ring slot (8 columns, 5 used) in one instruction each way; the three spare columns carry don't-care registers
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld8(float (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4])::"memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[5]) {
+  asm volatile("{\n.reg .b32 u;\ntcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, u, u, u};\n}" ::"r"(taddr),
+               "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]) : "memory");
+}
+__device__ __forceinline__ void lds_f4(uint32_t addr, float& a, float& b, float& c, float& d) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// ---- bulk asynchronous copies (TMA, cp.async.bulk) completing on an mbarrier ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// ---- mbarriers (shared memory): the FULL / EMPTY hand-over of the staging buffers.  One elected lane per warp arrives
+// (after __syncwarp, so the warp's shared-memory accesses are ordered before the release); waiters only wait — unlike
+// bar.sync on a named barrier, the producer warps do not wait for EACH OTHER, so they drift apart by up to NBUF chunks
+// and hide one another's load latency (ncu on the named-barrier version: 27 % of the producers' samples at the EMPTY
+// barrier although the consumers were idle half of the time).
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -150,13 +165,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 // UPS: first iteration of a level — the input flow is the bilinear upsample of the coarser level's result (UpsSrc),
 // computed by the producers: a thread marching down its column keeps the horizontally blended coarse flow of the two
 // coarse rows around it and loads a new coarse row only when it crosses one (every second row at pyr_scale 0.5).
-// TMAR: the regular inputs of the two-rows-in-flight schedule — the R0 rows and (plain launches) the input-flow rows — are
-// staged in shared memory by bulk asynchronous copies (TMA, cp.async.bulk completing on mbarriers), per warp, TR_CHUNKS
-// chunks ahead.  They cost no registers while in flight, the flow of the NEXT chunk is at hand early, and the gather of
-// chunk v+1 is issued between the two halves of chunk v (its top row as soon as chunk v's top half is consumed), so
-// every R1 load has about half an iteration to land instead of being waited for right after its issue (ncu before:
-// long-scoreboard the top producer stall, issue 59 %, L1 62 %, DRAM 38 %).  Needs w % 4 == 0 (16-byte copy granules).
-template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF, bool UPS, bool TMAR = false>
+template <int MT, int COLS, int CH, int MINB, int PFD, bool TILED, bool REUSE, bool TMEM, int NBUF, bool UPS>
 __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     k_iter_v(const RSet rs, const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int w, int h, int m_rt,
              float reg, int seg_rows, int strips, int y_begin, int y_end, PeerTab tab, int my_rank, UpsSrc ups) {
@@ -167,23 +176,24 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
   static_assert(!REUSE || (!TILED && CH == 2), "row-reuse schedule: chunks of two rows, untiled");
   static_assert(!TMEM || (COLS == 256 && MT >= 1 && (2 * MT + 1) * kTmemRingStride <= kTmemWgCols),
                 "TMEM ring: two producer warpgroups, ring slots within the warpgroup's columns");
-  static_assert(NBUF >= 2 && 1 + 2 * NBUF <= 16, "named barriers");
-  static_assert(!TMAR || (REUSE && TMEM && MT > 0), "staged inputs: the default schedule only");
+  static_assert(NBUF >= 2 && NBUF <= 8, "staging buffers");
   constexpr bool REGMOVE = REUSE && COLS == 256 && MINB == 2;   // setmaxnreg 96 / 48
-  constexpr int NT = COLS + NCONS;
-  constexpr int BAR_FULL0 = 1, BAR_EMPTY0 = 1 + NBUF;
   const int m = MT > 0 ? MT : m_rt;
   const int R = 2 * m + 1;
-  const int tw = COLS - 2 * m;
+  const int halo = iter_v_halo(MT, m);
+  const int tw = COLS - 2 * halo;
   extern __shared__ float smem[];
   float* stage = smem;                               // [NBUF][CH][5][COLS]   vertically summed rows
   float* ring = smem + NBUF * CH * 5 * COLS;         // [R][5][COLS]          P_prev[k] (TMEM = false)
   __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t handover[2 * NBUF];            // mbarriers: FULL[NBUF] (producer warps arrive), EMPTY[NBUF] (consumer warps)
+  const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(handover);
+  const uint32_t bar_empty = bar_full + 8u * NBUF;
 
   const int strip = blockIdx.x % strips;
   const int seg = blockIdx.x / strips;
   const int pair = blockIdx.y;
-  const int x_base = strip * tw - m;                 // image x of strip column 0
+  const int x_base = strip * tw - halo;              // image x of strip column 0
   const int y0 = y_begin + seg * seg_rows;
   const int y1 = min(y0 + seg_rows, y_end);          // exclusive
   const int t_first = y0 - m;                        // first matrix row the segment needs
@@ -192,12 +202,20 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
   const size_t n = (size_t)w * h;
   const int tid = threadIdx.x;
 
+  if (tid == COLS) {                                 // (a consumer thread: the first warp may be busy allocating)
+    for (int i = 0; i < NBUF; i++) {
+      mbar_init(bar_full + 8u * i, COLS / 32);
+      mbar_init(bar_empty + 8u * i, NCONS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if constexpr (TMEM) {
     if (tid < 32) tmem_alloc<2 * kTmemWgCols>(&tmem_slot);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  __syncthreads();
+  if constexpr (TMEM) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const bool lane0 = (tid & 31) == 0;
 
   if (tid < COLS) {
     // ------------------------------------------------------------------ PRODUCERS (one column each)
@@ -218,23 +236,29 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     float P[5] = {0.f, 0.f, 0.f, 0.f, 0.f};          // prefix sums of the current block
     float Bp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};         // sum of the previous block
     int k = 0;                                       // offset of row t inside its block
-    bool have_prev = false;
+    // The ring starts zero-filled, so the first block subtracts zeros: no "have a previous block" flag in the row step.
+    if constexpr (TMEM) {
+      const float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < R; i++) tmem_st8(tring + (uint32_t)i * kTmemRingStride, z);
+    } else {
+      for (int i = 0; i < R * 5; i++) rcol[i * COLS] = 0.f;
+    }
 
     // vertical van Herk step: P += M(t); V = (Bp - P_prev[k]) + P; ring[k] = P; block bookkeeping
     auto ring_step = [&](const M5& mm, float (&V)[5]) {
-      float old[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      float old[8];
       if constexpr (TMEM) {
         tmem_wait_st();                              // the slot read below was written R rows ago: long complete
-        if (have_prev) tmem_ld5(tring + tk, old);    // (uniform over the CTA: depends on the row count only)
+        tmem_ld8(tring + tk, old);
       } else {
 #pragma unroll
-        for (int ch = 0; ch < 5; ch++) old[ch] = have_prev ? rcol[(k * 5 + ch) * COLS] : 0.f;
+        for (int ch = 0; ch < 5; ch++) old[ch] = rcol[(k * 5 + ch) * COLS];
       }
       P[0] = __fadd_rn(P[0], mm.g11); P[1] = __fadd_rn(P[1], mm.g12); P[2] = __fadd_rn(P[2], mm.g22);
       P[3] = __fadd_rn(P[3], mm.h1); P[4] = __fadd_rn(P[4], mm.h2);
       if constexpr (TMEM) {
-        if (have_prev) tmem_wait_ld5(old);
-        tmem_st5(tring + tk, P);
+        tmem_wait_ld8(old);
+        tmem_st8(tring + tk, P);
         tk += kTmemRingStride;
       }
 #pragma unroll
@@ -245,7 +269,6 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
       if (++k == R) {
         k = 0;
         tk = 0;
-        have_prev = true;
 #pragma unroll
         for (int ch = 0; ch < 5; ch++) { Bp[ch] = P[ch]; P[ch] = 0.f; }
       }
@@ -265,9 +288,6 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     auto ups_hrow = [&](int r) -> float2 {
       const float2* p = uprev + (unsigned)r * (unsigned)ups.pw;
       const float2 q0 = __ldg(p + ux0), q1 = __ldg(p + ux1);
-      // the next coarse row this column will cross, pulled into L1 now: the blend below waits for q0 / q1 right away
-      // (ncu: 20 % of the producers' samples sat on that wait when every new row came from L2)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (r + 1 < ups.ph ? ups.pw : 0) + ux1));
       return make_float2(__fmaf_rn(q1.x, ufx, __fmul_rn(q0.x, uax0)), __fmaf_rn(q1.y, ufx, __fmul_rn(q0.y, uax0)));
     };
     // input flow of matrix row t at this column.  Plain launches: one load (volatile in the two-rows-in-flight schedule:
@@ -308,192 +328,170 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     };
     auto stage_row = [&](int buf, int rr) { return stage + ((buf * CH + rr) * 5) * COLS + tid; };
 
-    if constexpr (REUSE && TMAR) {
-      // ---- staged inputs + interleaved gathers (see TMAR above).  Virtual chunk v = matrix rows t_first + 2v, + 1:
-      // the m warm-up chunks, then the output chunks.
-      const int wid = tid >> 5, lane = tid & 31;
-      char* wbase = reinterpret_cast<char*>(smem + NBUF * CH * 5 * COLS) + wid * TR_WARP_BYTES;
-      float4* s_ra = reinterpret_cast<float4*>(wbase);                                   // [2 * TR_CHUNKS][TR_W]
-      float2* s_fl = reinterpret_cast<float2*>(wbase + 2 * TR_CHUNKS * TR_W * 16);
-      float* s_rb = reinterpret_cast<float*>(wbase + 2 * TR_CHUNKS * TR_W * 24);
-      uint64_t* s_bar = reinterpret_cast<uint64_t*>(wbase + 2 * TR_CHUNKS * TR_ROW_BYTES);
-      // the warp's column slice: 4-aligned hull of its (clamped) columns
-      const int xmin = clampi(x_base + 32 * wid, 0, w - 1), xmax = clampi(x_base + 32 * wid + 31, 0, w - 1);
-      const int xs = xmin & ~3, xn = min((xmax + 4) & ~3, w) - xs;
-      const int cx = x - xs;
-      const int nv = m + n_chunks;
-      auto copy_chunk = [&](int v) {            // lane 0: rows of virtual chunk v -> slot v % TR_CHUNKS
-        const int sl = v % TR_CHUNKS;
-        uint64_t* bar = s_bar + sl;
-        mbar_expect_tx(bar, 2u * (unsigned)xn * (UPS ? 20u : 28u));
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          const unsigned o = (unsigned)clampi(t_first + 2 * v + j, 0, h - 1) * uw + (unsigned)xs;
-          bulk_g2s(s_ra + (2 * sl + j) * TR_W, RA0 + o, (unsigned)xn * 16u, bar);
-          bulk_g2s(s_rb + (2 * sl + j) * TR_W, RB0 + o, (unsigned)xn * 4u, bar);
-          if constexpr (!UPS) bulk_g2s(s_fl + (2 * sl + j) * TR_W, fin + o, (unsigned)xn * 8u, bar);
-        }
-      };
-      if (lane == 0) {
-        for (int i = 0; i < TR_CHUNKS; i++) mbar_init(s_bar + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int v = 0; v < min(TR_CHUNKS, nv); v++) copy_chunk(v);
-      }
-      __syncwarp();
-      UmRow X, Y, Z, W;
-      struct { float fx, fy; unsigned g; bool inside; } pa, pb;
-      float2 fa = make_float2(0.f, 0.f), fb = fa;                    // UPS: the chunk's input flow (computed, not staged)
-      bool reuse_b = false;
-      Z.q0 = Z.q1 = make_float4(0.f, 0.f, 0.f, 0.f); Z.s0 = Z.s1 = 0.f;
-      W = Z; X = Z; Y = Z;
-      auto pix = [&](decltype(pa)& P, float2 fl, int y) {            // (um_pix without the R0 loads)
-        const float fx = (float)x + fl.x, fy = (float)y + fl.y;
-        const int ix = __float2int_rd(fx), iy = __float2int_rd(fy);
-        P.fx = fx - (float)ix;
-        P.fy = fy - (float)iy;
-        P.inside = (unsigned)ix < uw - 1u && (unsigned)iy < uh - 1u;
-        P.g = P.inside ? (unsigned)iy * uw + (unsigned)ix : 0u;
-      };
-      auto wait_chunk = [&](int v) { mbar_wait(s_bar + v % TR_CHUNKS, (unsigned)(v / TR_CHUNKS) & 1u); };
-      auto flow_of = [&](int v, int j) -> float2 {
-        if constexpr (UPS) return flow_at(t_first + 2 * v + j);
-        else return s_fl[(2 * (v % TR_CHUNKS) + j) * TR_W + cx];
-      };
-      // top half of chunk v: pixel A; top corner row from the previous chunk's bottom row (Z) when it lines up
-      auto issue_a = [&](int v, unsigned prev_g) {
-        const int ya = clampi(t_first + 2 * v, 0, h - 1);
-        fa = flow_of(v, 0);
-        pix(pa, fa, ya);
-        if (pa.g != prev_g + uw) um_row_load(X, RA1, RB1, pa.g); else X = Z;
-        um_row_load(Y, RA1, RB1, pa.g + uw);
-      };
-      auto issue_b = [&](int v) {
-        const int yb = clampi(t_first + 2 * v + 1, 0, h - 1);
-        fb = flow_of(v, 1);
-        pix(pb, fb, yb);
-        reuse_b = pa.inside && pb.g == pa.g + uw;
-        if (!reuse_b) um_row_load(W, RA1, RB1, pb.g);
-        um_row_load(Z, RA1, RB1, pb.g + uw);
-      };
-      auto finish_half = [&](int v, int j, const decltype(pa)& P, const UmRow& top, const UmRow& bot, float2 fl, float (&V)[5]) {
-        const int y = clampi(t_first + 2 * v + j, 0, h - 1);
-        const int si = (2 * (v % TR_CHUNKS) + j) * TR_W + cx;
-        const float4 a0 = s_ra[si];
-        const float b0 = s_rb[si];
-        if constexpr (!UPS) fl = s_fl[si];
-        ring_step(um_arith(a0, b0, top.q0, top.q1, bot.q0, bot.q1, top.s0, top.s1, bot.s0, bot.s1, P.fx, P.fy, fl.x, fl.y,
-                           P.inside, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
-      };
-      wait_chunk(0);
-      issue_a(0, ~0u - uw);
-      issue_b(0);
-      int buf = 0;
-      for (int v = 0; v < nv; v++) {
-        const int c = v - m;                                         // output chunk (negative: warm-up)
-        if (c >= NBUF) named_bar_sync(BAR_EMPTY0 + buf, NT);         // consumers released this buffer
-        float V[5];
-        finish_half(v, 0, pa, X, Y, fa, V);
-        if (c >= 0) {
-          float* s0 = stage_row(buf, 0);
-#pragma unroll
-          for (int ch = 0; ch < 5; ch++) s0[ch * COLS] = V[ch];
-        }
-        if (reuse_b) W = Y;                                          // B's top row is A's bottom row: keep it, Y is refilled now
-        const unsigned g_b = pb.inside ? pb.g : ~0u - uw;
-        if (v + 1 < nv) {
-          wait_chunk(v + 1);                                         // (requested TR_CHUNKS - 1 chunks ago)
-          issue_a(v + 1, g_b);                                       // X <- Z (copy) or load; Y <- load: both free now
-        }
-        finish_half(v, 1, pb, W, Z, fb, V);                          // (a row past y1 keeps the state consistent; never read)
-        if (c >= 0) {
-          float* s1 = stage_row(buf, 1);
-#pragma unroll
-          for (int ch = 0; ch < 5; ch++) s1[ch * COLS] = V[ch];
-          named_bar_arrive(BAR_FULL0 + buf, NT);                     // staged rows of chunk c are ready
-          if (++buf == NBUF) buf = 0;
-        }
-        if (v + 1 < nv) issue_b(v + 1);                              // W, Z free now
-        // the warp is done with the slot of chunk v: refill it
-        __syncwarp();
-        if (lane == 0 && v + TR_CHUNKS < nv) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          copy_chunk(v + TR_CHUNKS);
-        }
-      }
-    } else if constexpr (REUSE) {
-      // Two rows in flight AND row-reuse gather.  Rows A = t, B = t + 1 of a chunk: all loads of both are issued
-      // before the first is consumed.  Corner-row register sets: X = top of A, Y = bottom of A (and top of B when B
-      // sits exactly one row below A), W = top of B otherwise, Z = bottom of B.  The next chunk's A takes Z as its top
-      // row when the displacement allows it, so a smooth field costs 8 gather loads per chunk instead of 16.
-      UmRow X, Y, Z, W;
-      UmPix pa, pb;
+    if constexpr (REUSE) {
+      // Two rows in flight AND row-reuse gather.  Rows A = t, B = t + 1 of a chunk: all loads of both are issued before
+      // the first is consumed.  Corner-row register sets: TA = top of A, Y = bottom of A (and top of B when B sits exactly
+      // one row below A), W = top of B otherwise, BZ = bottom of B.  The next chunk's A takes BZ as its top row when the
+      // displacement allows it, so a smooth field costs 8 gather loads per chunk instead of 16.
+      //
+      // The kernel is ISSUE-bound (ncu: 334 instructions per pixel-iteration, 250 of them in this loop, issue slots 59 %
+      // busy, every other unit below that), so the loop is written for instruction count:
+      //   * interior chunks (rows 5 .. h-6, no clamps, no border rows) run a body without row clamping, unrolled in
+      //     PAIRS with the roles of the two register sets S1 / S2 (top of A <-> bottom of B) and of the flow registers
+      //     swapped, so nothing is copied between chunks;
+      //   * where every lane of the warp is inside, lines up (B's top row = A's bottom row) and is not a border column
+      //     — a warp-uniform vote, the common case — the arithmetic runs without selects and predicated moves;
+      //   * the staging address is a 32-bit shared address kept in a register; the ring slot moves in ONE tcgen05.ld /
+      //     tcgen05.st (x8) each way; no "first block" flag (zero-filled ring).
+      // Bits are those of every other schedule (um_arith is the one arithmetic).
+      constexpr unsigned FULLMASK = 0xffffffffu;
+      constexpr uint32_t ROWB = 5u * COLS * 4u, BUFB = CH * ROWB;      // bytes of a staged row / staging buffer
+      const float xf = (float)x;
+      const uint32_t st0 = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)tid * 4u;
+      UmRow S1, S2, Y, W;
+      S1.q0 = S1.q1 = make_float4(0.f, 0.f, 0.f, 0.f); S1.s0 = S1.s1 = 0.f;
+      S2 = S1; W = S1; Y = S1;
       unsigned prev_g = ~0u - uw;
-      bool reuse_b = false;
-      Z.q0 = Z.q1 = make_float4(0.f, 0.f, 0.f, 0.f); Z.s0 = Z.s1 = 0.f;
-      W = Z;
-      auto issue2 = [&](float2 fa, float2 fb, int t) {
-        const int ya = clampi(t, 0, h - 1), yb = clampi(t + 1, 0, h - 1);
-        X = Z;                                                     // bottom row of the previous chunk's row B
-        um_pix(pa, RA0, RB0, fa, x, ya, (unsigned)ya * uw, uw, uh);
-        if (pa.g != prev_g + uw) um_row_load(X, RA1, RB1, pa.g);
-        um_row_load(Y, RA1, RB1, pa.g + uw);
-        um_pix(pb, RA0, RB0, fb, x, yb, (unsigned)yb * uw, uw, uh);
-        reuse_b = pa.inside && pb.g == pa.g + uw;
-        if (!reuse_b) um_row_load(W, RA1, RB1, pb.g);
-        um_row_load(Z, RA1, RB1, pb.g + uw);
-        prev_g = pb.inside ? pb.g : ~0u - uw;
-      };
-      auto finish_a = [&](int t, float (&V)[5]) {
-        const int y = clampi(t, 0, h - 1);
-        ring_step(um_finish_rows(pa, X, Y, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
-      };
-      auto finish_b = [&](int t, float (&V)[5]) {
-        const int y = clampi(t, 0, h - 1);
-        if (reuse_b) W = Y;                                        // (select per thread: 10 predicated moves)
-        ring_step(um_finish_rows(pb, W, Z, xborder || (unsigned)(y - 5) >= (unsigned)(h - 10), x, y, w, h), V);
-      };
-      float2 fa = flow_at(t_first), fb = flow_at(t_first + 1);
-      // warm-up: the R-1 = 2m rows above the first output row, chunk by chunk (unrolled for a compile-time radius: the
-      // rolled loop measured 3 % slower over a whole 1080p step)
-      for (int t = t_first; t < t_first + R - 1; t += 2) {
-        float V[5];
-        issue2(fa, fb, t);
-        fa = flow_at(t + 2); fb = flow_at(t + 3);
-        finish_a(t, V);
-        finish_b(t + 1, V);
-      }
+      float2 rq0 = make_float2(0.f, 0.f), rq1 = rq0;                  // fused upsample: see chunk()
+      bool hvalid = false;
       int buf = 0;
-#if OFB_EXP_L2PF > 0
-      const int pf_xs = max(x_base & ~3, 0), pf_n = min((x_base + COLS + 3) & ~3, w) - pf_xs;
-      const bool pf_on = tid == 0 && (w & 3) == 0 && pf_n > 0;
-#endif
-      for (int c = 0; c < n_chunks; c++) {
-        const int tc = y0 + c * CH + m;                              // newest matrix row of output row y0 + c*CH
-#if OFB_EXP_L2PF > 0
-        if (pf_on) {
-#pragma unroll
-          for (int rr = 0; rr < 2; rr++) {
-            const unsigned o = (unsigned)clampi(tc + 2 * OFB_EXP_L2PF + rr, 0, h - 1) * uw + (unsigned)pf_xs;
-            bulk_prefetch_l2(RA0 + o, (unsigned)pf_n * 16u);
-            bulk_prefetch_l2(RB0 + o, (unsigned)pf_n * 4u);
-            if constexpr (!UPS) bulk_prefetch_l2(fin + o, (unsigned)pf_n * 8u);
+      unsigned par = 0;                                               // parity of the staging round (flips when buf wraps)
+      uint32_t stb = st0;                                             // staging address of buffer `buf`
+
+      // One chunk: matrix rows t, t + 1; output chunk c (negative: warm-up, nothing staged).  FA / FB: input flow of the
+      // two rows (loaded by the previous chunk); NA / NB receive the next chunk's.  TA holds the previous chunk's bottom
+      // row on entry; BZ receives this chunk's.
+      auto chunk = [&](auto interior, const int t, const int c, UmRow& TA, UmRow& BZ, const float2& FA, const float2& FB,
+                       float2& NA, float2& NB) {
+        constexpr bool INT = decltype(interior)::value;
+        const int ya = INT ? t : clampi(t, 0, h - 1), yb = INT ? t + 1 : clampi(t + 1, 0, h - 1);
+        const unsigned oa = (unsigned)ya * uw + (unsigned)x, ob = INT ? oa + uw : (unsigned)yb * uw + (unsigned)x;
+        const float4 a0a = __ldg(RA0 + oa);
+        const float b0a = __ldg(RB0 + oa);
+        const float4 a0b = __ldg(RA0 + ob);
+        const float b0b = __ldg(RB0 + ob);
+        // Input flow of the two rows.  Plain launches: loaded by the previous chunk.  Fused upsample: blended here from the
+        // coarse level's rows.  Interior chunks (the level has exactly twice the coarse rows and the chunk starts on an odd
+        // row t = 2k + 1, see the loop below) need the horizontally blended coarse rows k and k + 1 only (uHa, uHb): one
+        // new coarse row per chunk, whose two loads were issued a whole chunk earlier (rq0, rq1), so nothing here waits for
+        // memory (ncu before: long-scoreboard 5.8 warps per issue against 2.4 of the plain launch, 30 % more
+        // instructions).  cv::resize rows of an exact x2: y = 2k + 1 blends rows (k, k+1) with weight 0.25 on the second,
+        // y = 2k + 2 the same rows with 0.75.  Edge chunks use the general row-by-row form (flow_at).
+        float2 fa_, fb_;
+        if constexpr (!UPS) {
+          fa_ = FA;
+          fb_ = FB;
+        } else if constexpr (INT) {
+          const int r = t >> 1;
+          if (!hvalid) {
+            uHa = ups_hrow(r); uHb = ups_hrow(r + 1);
+            hvalid = true;
+          } else {
+            uHa = uHb;
+            uHb = make_float2(__fmaf_rn(rq1.x, ufx, __fmul_rn(rq0.x, uax0)), __fmaf_rn(rq1.y, ufx, __fmul_rn(rq0.y, uax0)));
           }
+          {   // the row the NEXT chunk adds: r + 2 <= ph - 1 for every interior chunk
+            const float2* p = uprev + (unsigned)(r + 2) * (unsigned)ups.pw;
+            rq0 = __ldg(p + ux0);
+            rq1 = __ldg(p + ux1);
+          }
+          fa_ = make_float2(__fmul_rn(__fmaf_rn(uHb.x, 0.25f, __fmul_rn(uHa.x, 0.75f)), ups.mul),
+                            __fmul_rn(__fmaf_rn(uHb.y, 0.25f, __fmul_rn(uHa.y, 0.75f)), ups.mul));
+          fb_ = make_float2(__fmul_rn(__fmaf_rn(uHb.x, 0.75f, __fmul_rn(uHa.x, 0.25f)), ups.mul),
+                            __fmul_rn(__fmaf_rn(uHb.y, 0.75f, __fmul_rn(uHa.y, 0.25f)), ups.mul));
+        } else {
+          if (hvalid) { hvalid = false; u_ca = u_cb = -1; }           // (the general form keeps its own row ids)
+          fa_ = flow_at(t);
+          fb_ = flow_at(t + 1);
         }
-#endif
-        issue2(fa, fb, tc);
-        fa = flow_at(tc + 2); fb = flow_at(tc + 3);
-        if (c >= NBUF) named_bar_sync(BAR_EMPTY0 + buf, NT);         // consumers released this buffer
+        const float2 FA_ = fa_, FB_ = fb_;
+        // pixel A
+        const float pxa = xf + FA_.x, pya = (float)ya + FA_.y;
+        const int ixa = __float2int_rd(pxa), iya = __float2int_rd(pya);
+        const float fxa = pxa - (float)ixa, fya = pya - (float)iya;
+        const bool ina = (unsigned)ixa < uw - 1u && (unsigned)iya < uh - 1u;
+        const unsigned ga = ina ? (unsigned)iya * uw + (unsigned)ixa : 0u;
+        if (ga != prev_g + uw) um_row_load(TA, RA1, RB1, ga);
+        um_row_load(Y, RA1, RB1, ga + uw);
+        // pixel B
+        const float pxb = xf + FB_.x, pyb = (float)yb + FB_.y;
+        const int ixb = __float2int_rd(pxb), iyb = __float2int_rd(pyb);
+        const float fxb = pxb - (float)ixb, fyb = pyb - (float)iyb;
+        const bool inb = (unsigned)ixb < uw - 1u && (unsigned)iyb < uh - 1u;
+        const unsigned gb = inb ? (unsigned)iyb * uw + (unsigned)ixb : 0u;
+        const bool reuse_b = ina && gb == ga + uw;
+        if (!reuse_b) um_row_load(W, RA1, RB1, gb);
+        um_row_load(BZ, RA1, RB1, gb + uw);
+        prev_g = inb ? gb : ~0u - uw;
+        // input flow of the next chunk (volatile: it stays here, in front of the barrier and the arithmetic)
+        if constexpr (UPS) {
+          // (computed by the next chunk itself)
+        } else if constexpr (INT) {
+          NA = ld_volatile_f2(fin + (ob + uw));
+          NB = ld_volatile_f2(fin + (ob + 2u * uw));
+        } else {
+          NA = ld_volatile_f2(fin + ((unsigned)clampi(t + 2, 0, h - 1) * uw + (unsigned)x));
+          NB = ld_volatile_f2(fin + ((unsigned)clampi(t + 3, 0, h - 1) * uw + (unsigned)x));
+        }
+        // consumers released this buffer (first round: the wait on the preceding phase of a fresh barrier passes)
+        if (c >= 0) mbar_wait(bar_empty + 8u * buf, par ^ 1u);
         float V[5];
-        finish_a(tc, V);
-        float* s0 = stage_row(buf, 0);
+        // (reuse_b implies that B is inside: its corner offset is A's plus one row, never 0)
+        const bool fast = INT && __all_sync(FULLMASK, reuse_b && !xborder);
+        if (fast) {
+          ring_step(um_arith(a0a, b0a, TA.q0, TA.q1, Y.q0, Y.q1, TA.s0, TA.s1, Y.s0, Y.s1, fxa, fya, FA_.x, FA_.y, true, false,
+                             x, ya, w, h), V);
+          if (c >= 0) {
 #pragma unroll
-        for (int ch = 0; ch < 5; ch++) s0[ch * COLS] = V[ch];
-        finish_b(tc + 1, V);                                         // (a row past y1 keeps the state consistent; never read)
-        float* s1 = stage_row(buf, 1);
+            for (int ch = 0; ch < 5; ch++) sts_f32(stb + ch * COLS * 4, V[ch]);
+          }
+          ring_step(um_arith(a0b, b0b, Y.q0, Y.q1, BZ.q0, BZ.q1, Y.s0, Y.s1, BZ.s0, BZ.s1, fxb, fyb, FB_.x, FB_.y, true, false,
+                             x, yb, w, h), V);
+        } else {
+          ring_step(um_arith(a0a, b0a, TA.q0, TA.q1, Y.q0, Y.q1, TA.s0, TA.s1, Y.s0, Y.s1, fxa, fya, FA_.x, FA_.y, ina,
+                             xborder || (unsigned)(ya - 5) >= (unsigned)(h - 10), x, ya, w, h), V);
+          if (c >= 0) {
 #pragma unroll
-        for (int ch = 0; ch < 5; ch++) s1[ch * COLS] = V[ch];
-        named_bar_arrive(BAR_FULL0 + buf, NT);                       // staged rows of chunk c are ready
-        if (++buf == NBUF) buf = 0;
+            for (int ch = 0; ch < 5; ch++) sts_f32(stb + ch * COLS * 4, V[ch]);
+          }
+          if (reuse_b) W = Y;                                        // (select per thread: 10 predicated moves)
+          ring_step(um_arith(a0b, b0b, W.q0, W.q1, BZ.q0, BZ.q1, W.s0, W.s1, BZ.s0, BZ.s1, fxb, fyb, FB_.x, FB_.y, inb,
+                             xborder || (unsigned)(yb - 5) >= (unsigned)(h - 10), x, yb, w, h), V);
+        }
+        if (c >= 0) {                                                // (a row past y1 keeps the state consistent; never read)
+#pragma unroll
+          for (int ch = 0; ch < 5; ch++) sts_f32(stb + ROWB + ch * COLS * 4, V[ch]);
+          __syncwarp();
+          if (lane0) mbar_arrive(bar_full + 8u * buf);               // this warp's columns of chunk c are staged
+          stb += BUFB;
+          if (++buf == NBUF) { buf = 0; stb = st0; par ^= 1u; }
+        }
+      };
+      const std::true_type kInterior{};
+      const std::false_type kEdge{};
+      // rows t, t+1 off the border band; t+2, t+3 exist; fused upsample: only the exact x2 row mapping has an interior form
+      // (on odd rows: the launcher makes the segments an even number of rows, so t_first = y0 - m is odd for odd m)
+      const bool can_int = !UPS || (ups.exact2y != 0 && (t_first & 1) != 0);
+      auto interior = [&](int t) { return can_int && t >= 5 && t <= h - 7; };
+      float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0, f3 = f0;
+      if constexpr (!UPS) {
+        f0 = __ldg(fin + ((unsigned)clampi(t_first, 0, h - 1) * uw + (unsigned)x));
+        f1 = __ldg(fin + ((unsigned)clampi(t_first + 1, 0, h - 1) * uw + (unsigned)x));
+      }
+      const int nv = m + n_chunks;                                   // the m warm-up chunks, then the output chunks
+      int v = 0;
+      while (v < nv) {
+        const int t = t_first + 2 * v;
+        if (v + 1 < nv && interior(t) && interior(t + 2)) {
+          chunk(kInterior, t, v - m, S1, S2, f0, f1, f2, f3);
+          chunk(kInterior, t + 2, v + 1 - m, S2, S1, f2, f3, f0, f1);
+          v += 2;
+        } else {
+          chunk(kEdge, t, v - m, S1, S2, f0, f1, f2, f3);
+          S1 = S2;
+          f0 = f2; f1 = f3;
+          v += 1;
+        }
       }
     } else {
       // one row in flight; prefetch.global.L2 PFD rows ahead (R0, flow, the predicted corner row of the R1 gather)
@@ -532,8 +530,9 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         finish(L, t, V);
       }
       int buf = 0;
+      unsigned par = 0;
       for (int c = 0; c < n_chunks; c++) {
-        if (c >= NBUF) named_bar_sync(BAR_EMPTY0 + buf, NT);         // consumers released this buffer
+        mbar_wait(bar_empty + 8u * buf, par ^ 1u);                   // consumers released this buffer
 #pragma unroll
         for (int rr = 0; rr < CH; rr++) {
           const int yo = y0 + c * CH + rr;                           // output row; newest matrix row = yo + m
@@ -548,8 +547,9 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
             for (int ch = 0; ch < 5; ch++) srow[ch * COLS] = V[ch];
           }
         }
-        named_bar_arrive(BAR_FULL0 + buf, NT);                       // staged rows of chunk c are ready
-        if (++buf == NBUF) buf = 0;
+        __syncwarp();
+        if (lane0) mbar_arrive(bar_full + 8u * buf);                 // this warp's columns of chunk c are staged
+        if (++buf == NBUF) { buf = 0; par ^= 1u; }
       }
     }
     if constexpr (TMEM) tmem_wait_st();                // drained before the columns are freed
@@ -565,15 +565,23 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     unsigned vmask = 0;
 #pragma unroll
     for (int j = 0; j < PXT; j++)
-      if (q0 + j >= m && q0 + j < COLS - m && ox + j < w) vmask |= 1u << j;
+      if (q0 + j >= halo && q0 + j < COLS - halo && ox + j < w) vmask |= 1u << j;
     constexpr unsigned ALL = (1u << PXT) - 1u;
 
     int buf = 0;
+    unsigned par = 0;
     for (int c = 0; c < n_chunks; c++) {
-      named_bar_sync(BAR_FULL0 + buf, NT);             // producers finished staging chunk c
+      mbar_wait(bar_full + 8u * buf, par);             // every producer warp has staged chunk c
       const int yo = y0 + c * CH + q_row;
       if (yo < y1 && vmask) {
         const float* srow = stage + (buf * CH + q_row) * 5 * COLS;
+        // shared address of this thread's first quad in channel 0 of its staged row (PAD columns left of its pixels).
+        // Where the strip halo equals PAD (radius 7 / 15) every thread with a valid output reads inside the row: one
+        // base address, immediate offsets.  Otherwise the quads clamp at the row ends (the clamped values are unused).
+        constexpr int CPAD = MT > 0 ? (MT + 3) / 4 * 4 : 0;
+        constexpr bool NOCLAMP = MT > 0 && iter_v_halo(MT, MT) == CPAD;
+        const uint32_t c_row = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)((buf * CH + q_row) * 5 * COLS) * 4u;
+        const uint32_t c_first = c_row + (uint32_t)(q0 - CPAD) * 4u;
         float sum[5][PXT];
 #pragma unroll
         for (int ch = 0; ch < 5; ch++) {
@@ -585,9 +593,14 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
             float e[NE];
 #pragma unroll
             for (int v = 0; v < NE / 4; v++) {
-              const int cq = min(max(q0 - PAD + 4 * v, 0), COLS - 4);
-              const float4 t4 = *reinterpret_cast<const float4*>(s + cq);
-              e[4 * v] = t4.x; e[4 * v + 1] = t4.y; e[4 * v + 2] = t4.z; e[4 * v + 3] = t4.w;
+              // always a whole 16-byte read: a quad of which only part is used would otherwise be narrowed to LDS.64 +
+              // LDS.32, whose 16-byte lane stride is a 2-way / 4-way bank conflict (8 wavefronts instead of 4)
+              if constexpr (NOCLAMP) {
+                lds_f4(c_first + (uint32_t)(ch * COLS + 4 * v) * 4u, e[4 * v], e[4 * v + 1], e[4 * v + 2], e[4 * v + 3]);
+              } else {
+                const int cq = min(max(q0 - PAD + 4 * v, 0), COLS - 4);
+                lds_f4(c_row + (uint32_t)(ch * COLS + cq) * 4u, e[4 * v], e[4 * v + 1], e[4 * v + 2], e[4 * v + 3]);
+              }
             }
             // columns common to all PXT windows: [PAD + PXT-1 - MT, PAD + MT]
             constexpr int C0 = PAD + PXT - 1 - MT, C1 = PAD + MT;
@@ -642,8 +655,9 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
             if ((vmask >> j) & 1u) fout[(unsigned)(oi + j)] = f[j];
         }
       }
-      if (c + NBUF < n_chunks) named_bar_arrive(BAR_EMPTY0 + buf, NT);   // staging buffer may be refilled
-      if (++buf == NBUF) buf = 0;
+      __syncwarp();
+      if (lane0) mbar_arrive(bar_empty + 8u * buf);    // staging buffer may be refilled
+      if (++buf == NBUF) { buf = 0; par ^= 1u; }
     }
   }
 
