@@ -36,6 +36,9 @@
 #ifndef OFB_EXP_FUSE_UPS
 #define OFB_EXP_FUSE_UPS true
 #endif
+#ifndef OFB_EXP_PYR3
+#define OFB_EXP_PYR3 true
+#endif
 
 namespace ofb {
 
@@ -604,6 +607,34 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
     return set_error(h, OFB_ERR_INVALID_ARG, "internal: stream cache used with an unsupported configuration");
   float2* prev_flow = nullptr;
   int prev_w = 0, prev_h = 0;
+  // The three regular levels S = 8, 4, 2 in one pass over the source (k_pyr_fast3): when the schedule ends
+  // ... 8, 4, 2, 1 with the default smoothing radii 9, 4, 1.  Their level images then live side by side in d_img
+  // (which holds frames * N floats; the three take 21/64 of it).
+  int fused3_li = -1;
+  float* img3[3] = {nullptr, nullptr, nullptr};          // S = 2, 4, 8
+  PyrFast3Coef fc3;
+  if (OFB_EXP_PYR3 && n_levels >= 4 && (width & 7) == 0 && (height & 7) == 0 && (pitch & 3) == 0 && (image_stride & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(src.a) & 3) == 0 && (reinterpret_cast<uintptr_t>(src.b) & 3) == 0 && pc.n <= PX_MAXN) {
+    bool ok = true;
+    memset(&fc3, 0, sizeof(fc3));
+    for (int q = 0; q < 3 && ok; q++) {                  // q = 0, 1, 2: S = 2, 4, 8
+      const Level& lq = sched[n_levels - 2 - q];
+      const int S = 2 << q, r = q == 0 ? 1 : (q == 1 ? 4 : 9);
+      PyrCoef pq;
+      ok = lq.width * S == width && lq.height * S == height && prepare_pyr(lq.ksize, lq.sigma, &pq) == OFB_OK && pq.r == r;
+      if (ok) {
+        float* c = q == 0 ? fc3.c1 : (q == 1 ? fc3.c2 : fc3.c3);
+        for (int j = 1; j <= r + 1; j++) c[j - 1] = 0.5f * (pq.k[j - 1] + (j <= r ? pq.k[j] : 0.f));
+      }
+    }
+    if (ok) {
+      fused3_li = n_levels - 4;
+      const size_t n1 = (size_t)(width / 2) * (height / 2), n2 = n1 / 4;
+      img3[0] = h->d_img;
+      img3[1] = img3[0] + (size_t)frames * n1;
+      img3[2] = img3[1] + (size_t)frames * n2;
+    }
+  }
   for (int li = 0; li < n_levels; li++) {
     const Level& lv = sched[li];
     const int w = lv.width, hh = lv.height;
@@ -657,7 +688,23 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
       for (int S = 2; S <= 8; S *= 2)
         if (w * S == width && hh * S == height && pyc.r == (S == 2 ? 1 : (S == 4 ? 4 : 9))) fastS = S;
     }
-    if (fastS) {
+    const float* level_img = h->d_img;
+    if (fused3_li >= 0 && li >= fused3_li && li < n_levels - 1) {
+      level_img = img3[n_levels - 2 - li];
+      if (li == fused3_li) {
+        TB(OFB_STAGE_PYRAMID);
+        constexpr int out3 = (PF_COLS - 2 * PF_HALO) / 8;
+        const int w3 = width / 8, h3 = height / 8;
+        const int chunks = (w3 + out3 - 1) / out3;
+        // about two waves of CTAs at 3 resident per SM (the window takes ~70 registers)
+        const int segs = std::max(1, 2 * 3 * h->num_sms / (chunks * frames));
+        const int seg_rows = std::max(2, (h3 + segs - 1) / segs);
+        dim3 g(chunks, (h3 + seg_rows - 1) / seg_rows, frames);
+        k_pyr_fast3<<<g, PF_THREADS, 0, st>>>(src, width, height, img3[0], img3[1], img3[2], fc3, seg_rows);
+        OFB_LAUNCH_CHECK(h);
+        TE();
+      }
+    } else if (fastS) {
       TB(OFB_STAGE_PYRAMID);
       PyrFastCoef fc;
       memset(&fc, 0, sizeof(fc));
@@ -711,7 +758,7 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
       k_polyexp_march<NT, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], RAw, RBw, w, hh,              \
                                                     seg_rows, strips, pc, 0, hh);                                   \
     else                                                                                                            \
-      k_polyexp_march<NT, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, RAw, RBw, w, hh, seg_rows,             \
+      k_polyexp_march<NT, 0><<<g, PX_COLS, 0, st>>>(level_img, src, 0.f, 0.f, RAw, RBw, w, hh, seg_rows,            \
                                                     strips, pc, 0, hh);                                             \
   } while (0)
       if (pc.n == 5) OFB_PX_LAUNCH(5); else if (pc.n == 7) OFB_PX_LAUNCH(7); else OFB_PX_LAUNCH(0);

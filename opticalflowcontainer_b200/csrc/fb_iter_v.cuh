@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     if constexpr (REUSE) {
       // Two rows in flight AND row-reuse gather.  Rows A = t, B = t + 1 of a chunk: all loads of both are issued before
       // the first is consumed.  Corner-row register sets: TA = top of A, Y = bottom of A (and top of B when B sits exactly
-      // one row below A), W = top of B otherwise, BZ = bottom of B.  The next chunk's A takes BZ as its top row when the
+      // one row below A; otherwise B's top row is loaded late, see below), BZ = bottom of B.  The next chunk's A takes BZ as its top row when the
       // displacement allows it, so a smooth field costs 8 gather loads per chunk instead of 16.
       //
       // The kernel is ISSUE-bound (ncu: 334 instructions per pixel-iteration, 250 of them in this loop, issue slots 59 %
@@ -348,9 +348,9 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
       constexpr uint32_t ROWB = 5u * COLS * 4u, BUFB = CH * ROWB;      // bytes of a staged row / staging buffer
       const float xf = (float)x;
       const uint32_t st0 = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)tid * 4u;
-      UmRow S1, S2, Y, W;
+      UmRow S1, S2, Y;
       S1.q0 = S1.q1 = make_float4(0.f, 0.f, 0.f, 0.f); S1.s0 = S1.s1 = 0.f;
-      S2 = S1; W = S1; Y = S1;
+      S2 = S1; Y = S1;
       unsigned prev_g = ~0u - uw;
       float2 rq0 = make_float2(0.f, 0.f), rq1 = rq0;                  // fused upsample: see chunk()
       bool hvalid = false;
@@ -420,7 +420,6 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         const bool inb = (unsigned)ixb < uw - 1u && (unsigned)iyb < uh - 1u;
         const unsigned gb = inb ? (unsigned)iyb * uw + (unsigned)ixb : 0u;
         const bool reuse_b = ina && gb == ga + uw;
-        if (!reuse_b) um_row_load(W, RA1, RB1, gb);
         um_row_load(BZ, RA1, RB1, gb + uw);
         prev_g = inb ? gb : ~0u - uw;
         // input flow of the next chunk (volatile: it stays here, in front of the barrier and the arithmetic)
@@ -454,6 +453,11 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
 #pragma unroll
             for (int ch = 0; ch < 5; ch++) sts_f32(stb + ch * COLS * 4, V[ch]);
           }
+          // B's top row where it is not A's bottom row (flow discontinuity, floor crossing, outside pixel): loaded late
+          // into A's top-row registers, free now — a wait for memory in the rare case instead of ten registers held
+          // through every chunk
+          if (!reuse_b) um_row_load(TA, RA1, RB1, gb);
+          UmRow W = TA;
           if (reuse_b) W = Y;                                        // (select per thread: 10 predicated moves)
           ring_step(um_arith(a0b, b0b, W.q0, W.q1, BZ.q0, BZ.q1, W.s0, W.s1, BZ.s0, BZ.s1, fxb, fyb, FB_.x, FB_.y, inb,
                              xborder || (unsigned)(yb - 5) >= (unsigned)(h - 10), x, yb, w, h), V);

@@ -291,4 +291,129 @@ __global__ void __launch_bounds__(PF_THREADS) k_pyr_fast(FrameSrc src, int W, in
   }
 }
 
+// =====================================================================================
+// The three regular levels S = 2, 4, 8 (R = 1, 4, 9: the node defaults at pyr_scale 0.5, three levels) in ONE pass over
+// the source.  Launched one after the other, each k_pyr_fast reads the whole u8 frame again and is a ~65 us launch of
+// its own whatever the level's size (36 frames of 1080p: 3 x 65 us for 0.33 N of output).  The 20-row window of the
+// coarsest level (source rows 8Y-6 .. 8Y+13 for its row Y) contains the windows of the two rows 2Y, 2Y+1 of the S = 4
+// level (10 rows each) and of the four rows 4Y .. 4Y+3 of the S = 2 level (4 rows each), so one register window
+// serves all three: per step of 8 source rows a thread (4 source columns) emits 1 + 2 + 4 vertically filtered rows
+// into shared memory and the CTA then applies each level's horizontal filter.  Same arithmetic, same order of
+// operations per level as k_pyr_fast: identical bits.
+struct PyrFast3Coef { float c1[2], c2[5], c3[10]; };
+constexpr int PF3_STRIDE = PF_COLS + PF_COLS / 32 + 1;
+
+template <int I0, int NP>
+__device__ __forceinline__ void pf3_vfilt(const unsigned (&we)[20], const unsigned (&wo)[20], const float* __restrict__ c,
+                                          float* __restrict__ rb) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int j = 1; j <= NP; j++) {
+    const unsigned e = we[I0 - (j - 1)] + we[I0 + j];
+    const unsigned o = wo[I0 - (j - 1)] + wo[I0 + j];
+    const float cj = c[j - 1];
+    a0 = fmaf(cj, __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7610)) - 8388608.f, a0);
+    a2 = fmaf(cj, __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7632)) - 8388608.f, a2);
+    a1 = fmaf(cj, __uint_as_float(__byte_perm(o, 0x4B000000u, 0x7610)) - 8388608.f, a1);
+    a3 = fmaf(cj, __uint_as_float(__byte_perm(o, 0x4B000000u, 0x7632)) - 8388608.f, a3);
+  }
+  rb[0] = a0; rb[1] = a1; rb[2] = a2; rb[3] = a3;
+}
+
+// horizontal filter of NROWS staged rows of one level: level column xo0 + i reads chunk columns
+// PF_HALO + S*i + S/2 - 1 - R .. + S/2 + R
+template <int S, int R, int NROWS>
+__device__ __forceinline__ void pf3_hfilt(const float* __restrict__ rows, const float* __restrict__ c, float* __restrict__ out,
+                                          int w, int h, int frame, int y_first, int xo0, int tid) {
+  constexpr int OUT = (PF_COLS - 2 * PF_HALO) / S;
+  for (int i = tid; i < NROWS * OUT; i += PF_THREADS) {
+    const int s = i / OUT, col = i - s * OUT;
+    const int xo = xo0 + col;
+    if (xo < w) {
+      const float* rb = rows + s * PF3_STRIDE;
+      const int cl = PF_HALO + S * col + S / 2 - 1;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 1; j <= R + 1; j++) acc = fmaf(c[j - 1], rb[pf_skew(cl - (j - 1))] + rb[pf_skew(cl + j)], acc);
+      out[((size_t)frame * h + (y_first + s)) * w + xo] = acc;
+    }
+  }
+}
+
+// grid: (ceil(w3 / 126), ceil(h3 / seg_rows), frames); out1/2/3: the level images [frames][h_l][w_l] of S = 2, 4, 8.
+__global__ void __launch_bounds__(PF_THREADS, 3) k_pyr_fast3(FrameSrc src, int W, int H, float* __restrict__ out1,
+                                                          float* __restrict__ out2, float* __restrict__ out3,
+                                                          PyrFast3Coef pc, int seg_rows) {
+  constexpr int S = 8, R = 9, WIN = 20;
+  constexpr int OUT3 = (PF_COLS - 2 * PF_HALO) / 8;
+  __shared__ float rowbuf[7 * PF3_STRIDE];              // row 0: S = 8; rows 1, 2: S = 4; rows 3..6: S = 2
+  const int w3 = W >> 3, h3 = H >> 3;
+  const int tid = threadIdx.x;
+  const int xo0 = blockIdx.x * OUT3;                    // first S = 8 level column of the chunk
+  const int x = S * xo0 - PF_HALO + 4 * tid;            // first of this thread's 4 source columns (multiple of 4)
+  const int y0 = blockIdx.y * seg_rows, y1 = min(y0 + seg_rows, h3);
+  const uint8_t* frame = src.frame(blockIdx.z);
+  const bool interior = x >= 0 && x + 3 < W;
+  const bool dead = x > W + 5;                          // right of everything a level column of this frame reads
+  const int bx0 = reflect101(x, W), bx1 = reflect101(x + 1, W), bx2 = reflect101(x + 2, W), bx3 = reflect101(x + 3, W);
+  const bool fastcol = interior && !dead;
+  auto load_row = [&](int ry) -> unsigned {             // source row ry (any integer: reflected)
+    if (fastcol && (unsigned)ry < (unsigned)H)
+      return __ldg(reinterpret_cast<const unsigned*>(frame + (size_t)ry * src.pitch + x));
+    const uint8_t* p = frame + (size_t)reflect101(ry, H) * src.pitch;
+    if (dead) return 0u;
+    if (interior) return __ldg(reinterpret_cast<const unsigned*>(p + x));
+    return (unsigned)__ldg(p + bx0) | ((unsigned)__ldg(p + bx1) << 8) | ((unsigned)__ldg(p + bx2) << 16) |
+           ((unsigned)__ldg(p + bx3) << 24);
+  };
+  unsigned we[WIN], wo[WIN];
+  {
+    const int top = S * y0 + S / 2 - 1 - R;
+#pragma unroll
+    for (int i = S; i < WIN; i++) {
+      const unsigned v = load_row(top + i - S);
+      we[i] = v & 0x00FF00FFu;
+      wo[i] = (v >> 8) & 0x00FF00FFu;
+    }
+  }
+  const size_t pitch_w = src.pitch >> 2;
+  auto load_group = [&](int first, unsigned (&dst)[S]) {
+    if (fastcol && first >= 0 && first + S <= H) {
+      const unsigned* p = reinterpret_cast<const unsigned*>(frame + (size_t)first * src.pitch + x);
+#pragma unroll
+      for (int i = 0; i < S; i++) dst[i] = __ldg(p + (size_t)i * pitch_w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < S; i++) dst[i] = load_row(first + i);
+    }
+  };
+  unsigned nx[S];
+  load_group(S * y0 + S / 2 - 1 - R + WIN - S, nx);
+  float* mine = rowbuf + pf_skew(4 * tid);              // 4*tid .. 4*tid+3 share one 32-group: contiguous after the skew
+
+  for (int y = y0; y < y1; y++) {
+#pragma unroll
+    for (int i = 0; i < WIN - S; i++) { we[i] = we[i + S]; wo[i] = wo[i + S]; }
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      we[WIN - S + i] = nx[i] & 0x00FF00FFu;
+      wo[WIN - S + i] = (nx[i] >> 8) & 0x00FF00FFu;
+    }
+    if (y + 1 < y1) load_group(S * (y + 1) + S / 2 - 1 - R + WIN - S, nx);
+    // window index i = source row 8y - 6 + i.  Left centre tap of a level row: S_l * y_l + S_l/2 - 1.
+    pf3_vfilt<9, 10>(we, wo, pc.c3, mine);                              // S = 8, row y:        8y + 3
+    pf3_vfilt<7, 5>(we, wo, pc.c2, mine + 1 * PF3_STRIDE);              // S = 4, row 2y:       8y + 1
+    pf3_vfilt<11, 5>(we, wo, pc.c2, mine + 2 * PF3_STRIDE);             //        row 2y + 1:   8y + 5
+    pf3_vfilt<6, 2>(we, wo, pc.c1, mine + 3 * PF3_STRIDE);              // S = 2, row 4y:       8y
+    pf3_vfilt<8, 2>(we, wo, pc.c1, mine + 4 * PF3_STRIDE);              //        row 4y + 1:   8y + 2
+    pf3_vfilt<10, 2>(we, wo, pc.c1, mine + 5 * PF3_STRIDE);             //        row 4y + 2:   8y + 4
+    pf3_vfilt<12, 2>(we, wo, pc.c1, mine + 6 * PF3_STRIDE);             //        row 4y + 3:   8y + 6
+    __syncthreads();
+    pf3_hfilt<2, 1, 4>(rowbuf + 3 * PF3_STRIDE, pc.c1, out1, W >> 1, H >> 1, blockIdx.z, 4 * y, 4 * xo0, tid);
+    pf3_hfilt<4, 4, 2>(rowbuf + 1 * PF3_STRIDE, pc.c2, out2, W >> 2, H >> 2, blockIdx.z, 2 * y, 2 * xo0, tid);
+    pf3_hfilt<8, 9, 1>(rowbuf, pc.c3, out3, w3, h3, blockIdx.z, y, xo0, tid);
+    __syncthreads();                                    // the rows are rewritten by the next step
+  }
+}
+
 }  // namespace ofb
