@@ -123,6 +123,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[5]) {
 __device__ __forceinline__ void lds_f4(uint32_t addr, float& a, float& b, float& c, float& d) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
 }
+__device__ __forceinline__ void stg_f8(void* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
+               "f"(f), "f"(g), "f"(h) : "memory");
+}
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -648,7 +652,11 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         for (int j = 0; j < PXT; j++) f[j] = solve2x2_sums(sum[0][j], sum[1][j], sum[2][j], sum[3][j], sum[4][j], reg);
         const int oi = yo * w + ox;                    // (oi + j >= 0 for every valid column j)
         float2* o = fout + (unsigned)max(oi, 0);
-        if (vmask == ALL && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        if (PXT == 4 && vmask == ALL && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+          // 32-byte aligned (always, where strips start at multiples of 8 pixels and w % 4 == 0): the thread's four flow
+          // vectors in ONE 256-bit store — a warp writes 1 KB of contiguous row in a single instruction
+          stg_f8(o, f[0].x, f[0].y, f[1].x, f[1].y, f[2].x, f[2].y, f[3].x, f[3].y);
+        } else if (vmask == ALL && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
           // 16-byte aligned: 128-bit stores
 #pragma unroll
           for (int j = 0; j < PXT; j += 2)

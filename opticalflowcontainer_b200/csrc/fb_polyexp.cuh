@@ -303,14 +303,25 @@ __global__ void __launch_bounds__(PX_COLS, PX_MINB)
       }
       const size_t ob0 = fbase + (size_t)y * w + hx;
       const bool two = hx + 1 < w;
-      const bool vec = two && ((w & 1) == 0);        // hx is even: rows start 8-byte aligned when w is even
-      RA[ob0] = make_float4(ox[0].x, oy[0].x, oz[0].x, ow[0].x);
-      if (two) RA[ob0 + 1] = make_float4(ox[1].x, oy[1].x, oz[1].x, ow[1].x);
+      const bool vec = two && ((w & 1) == 0) && (reinterpret_cast<uintptr_t>(RA) & 31) == 0 && (reinterpret_cast<uintptr_t>(RB) & 7) == 0;   // hx is even: pixel pairs are aligned when w is even
+      // (w even, hx even: the two pixels' float4 are 32 contiguous, 32-byte aligned bytes: one 256-bit store each row)
+      if (vec) {
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(RA + ob0), "f"(ox[0].x), "f"(oy[0].x),
+                     "f"(oz[0].x), "f"(ow[0].x), "f"(ox[1].x), "f"(oy[1].x), "f"(oz[1].x), "f"(ow[1].x) : "memory");
+      } else {
+        RA[ob0] = make_float4(ox[0].x, oy[0].x, oz[0].x, ow[0].x);
+        if (two) RA[ob0 + 1] = make_float4(ox[1].x, oy[1].x, oz[1].x, ow[1].x);
+      }
       if (vec) *reinterpret_cast<float2*>(RB + ob0) = make_float2(ob[0].x, ob[1].x);
       else { RB[ob0] = ob[0].x; if (two) RB[ob0 + 1] = ob[1].x; }
       if (y + 1 < y1) {
-        RA[ob0 + w] = make_float4(ox[0].y, oy[0].y, oz[0].y, ow[0].y);
-        if (two) RA[ob0 + w + 1] = make_float4(ox[1].y, oy[1].y, oz[1].y, ow[1].y);
+        if (vec) {
+          asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(RA + ob0 + w), "f"(ox[0].y),
+                       "f"(oy[0].y), "f"(oz[0].y), "f"(ow[0].y), "f"(ox[1].y), "f"(oy[1].y), "f"(oz[1].y), "f"(ow[1].y) : "memory");
+        } else {
+          RA[ob0 + w] = make_float4(ox[0].y, oy[0].y, oz[0].y, ow[0].y);
+          if (two) RA[ob0 + w + 1] = make_float4(ox[1].y, oy[1].y, oz[1].y, ow[1].y);
+        }
         if (vec) *reinterpret_cast<float2*>(RB + ob0 + w) = make_float2(ob[0].y, ob[1].y);
         else { RB[ob0 + w] = ob[0].y; if (two) RB[ob0 + w + 1] = ob[1].y; }
       }
