@@ -31,10 +31,12 @@
 #include "fb_device.cuh"
 #include "fb_um.cuh"
 
-// Experiment builds only: bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the R0 / flow rows OFB_EXP_L2PF chunks ahead,
-// issued by one thread of the CTA in the two-rows-in-flight schedule (0 = off).
+// Bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the R0 / flow / R1 rows OFB_EXP_L2PF chunks ahead,
+// issued by one thread of the CTA in the two-rows-in-flight schedule (0 = off).  Measured (iteration stage of an 18-pair
+// 1080p step): off 1.851 ms, 1 chunk ahead 1.749, 2: 1.767, 3: 1.803, 5: 1.850 (L2 turns over every ~25 us at this
+// traffic); one prefetch set per producer WARP instead of per CTA: 2.05 ms (many small bulk requests).
 #ifndef OFB_EXP_L2PF
-#define OFB_EXP_L2PF 0
+#define OFB_EXP_L2PF 1
 #endif
 
 namespace ofb {
@@ -362,6 +364,11 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
       unsigned par = 0;                                               // parity of the staging round (flips when buf wraps)
       uint32_t stb = st0;                                             // staging address of buffer `buf`
 
+#if OFB_EXP_L2PF > 0
+      // columns of the strip, 4-pixel aligned hull (bulk prefetches move 16-byte granules; rows of w % 4 == 0 pixels)
+      const int pf_xs = max(x_base, 0) & ~3, pf_n = min((x_base + COLS + 3) & ~3, w) - pf_xs;
+      const bool pf_on = tid == 0 && (w & 3) == 0 && pf_n >= 4 && h >= 4;
+#endif
       // One chunk: matrix rows t, t + 1; output chunk c (negative: warm-up, nothing staged).  FA / FB: input flow of the
       // two rows (loaded by the previous chunk); NA / NB receive the next chunk's.  TA holds the previous chunk's bottom
       // row on entry; BZ receives this chunk's.
@@ -436,6 +443,35 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
           NA = ld_volatile_f2(fin + ((unsigned)clampi(t + 2, 0, h - 1) * uw + (unsigned)x));
           NB = ld_volatile_f2(fin + ((unsigned)clampi(t + 3, 0, h - 1) * uw + (unsigned)x));
         }
+#if OFB_EXP_L2PF > 0
+        // One thread of the CTA pulls the rows of the chunk OFB_EXP_L2PF chunks ahead into L2 with bulk prefetches: the
+        // strip's R0 and flow rows, and the R1 rows where this thread's displacement points (a smooth field moves the
+        // whole strip's gather by about the same whole pixels).  With the producers' loads consumed right after their
+        // issue (ncu: long scoreboard 6 warps per issue, the top stall), an L2 hit instead of a DRAM access is a third
+        // of the wait.
+        if constexpr (INT) {
+          if (pf_on) {
+            const int tp = min(t + 2 * OFB_EXP_L2PF, h - 2);
+            const unsigned o0 = (unsigned)tp * uw + (unsigned)pf_xs;
+            bulk_prefetch_l2(RA0 + o0, (unsigned)pf_n * 16u);
+            bulk_prefetch_l2(RA0 + o0 + uw, (unsigned)pf_n * 16u);
+            bulk_prefetch_l2(RB0 + o0, (unsigned)pf_n * 4u);
+            bulk_prefetch_l2(RB0 + o0 + uw, (unsigned)pf_n * 4u);
+            if constexpr (!UPS) {
+              bulk_prefetch_l2(fin + o0, (unsigned)pf_n * 8u);
+              bulk_prefetch_l2(fin + o0 + uw, (unsigned)pf_n * 8u);
+            }
+            // R1: rows tp + (iyb - yb) + 1, + 2 (the two bottom corner rows the chunk will load), columns shifted by ixb - x
+            const int ry = min(max(tp + (iyb - yb) + 1, 0), h - 2);
+            const int rx = min(max(pf_xs + ((ixb - x) & ~3), 0), w - pf_n);
+            const unsigned o1 = (unsigned)ry * uw + (unsigned)rx;
+            bulk_prefetch_l2(RA1 + o1, (unsigned)pf_n * 16u);
+            bulk_prefetch_l2(RA1 + o1 + uw, (unsigned)pf_n * 16u);
+            bulk_prefetch_l2(RB1 + o1, (unsigned)pf_n * 4u);
+            bulk_prefetch_l2(RB1 + o1 + uw, (unsigned)pf_n * 4u);
+          }
+        }
+#endif
         // consumers released this buffer (first round: the wait on the preceding phase of a fresh barrier passes)
         if (c >= 0) mbar_wait(bar_empty + 8u * buf, par ^ 1u);
         float V[5];

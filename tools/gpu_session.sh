@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 V=opticalflowcontainer_b200/csrc/build/variants
 {
 echo "##### smoke"; timeout 180 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-for o in $V/libofb_noups.so $V/libofb_nopyr3.so; do
+for o in $V/libofb_pf0.so; do
   [ -f $o ] && { echo "##### bitwise: default vs $o"; timeout 300 python tools/compare_variants.py opticalflowcontainer_b200/libofb.so $o 2>&1 | tail -4; }
 done
 } > gpurun_out/s_smoke.log 2>&1
