@@ -193,6 +193,26 @@ static int prepare_pyr(int ksize, double sigma, PyrCoef* pc) {
   return OFB_OK;
 }
 
+// The three regular levels S = 8, 4, 2 in one pass over the source (k_pyr_fast3): applicable when the schedule ends
+// ... 8, 4, 2, 1 with the default smoothing radii 9, 4, 1 and the frames are word-aligned multiples of 8 pixels.
+static bool pyr3_applicable(const Level* sched, int n_levels, int width, int height, size_t pitch, const uint8_t* a,
+                            const uint8_t* b, PyrFast3Coef* fc3) {
+  if (n_levels < 4 || (width & 7) || (height & 7) || (pitch & 3) || (reinterpret_cast<uintptr_t>(a) & 3) ||
+      (reinterpret_cast<uintptr_t>(b) & 3))
+    return false;
+  memset(fc3, 0, sizeof(*fc3));
+  for (int q = 0; q < 3; q++) {                          // q = 0, 1, 2: S = 2, 4, 8
+    const Level& lq = sched[n_levels - 2 - q];
+    const int S = 2 << q, r = q == 0 ? 1 : (q == 1 ? 4 : 9);
+    PyrCoef pq;
+    if (!(lq.width * S == width && lq.height * S == height && prepare_pyr(lq.ksize, lq.sigma, &pq) == OFB_OK && pq.r == r))
+      return false;
+    float* c = q == 0 ? fc3->c1 : (q == 1 ? fc3->c2 : fc3->c3);
+    for (int j = 1; j <= r + 1; j++) c[j - 1] = 0.5f * (pq.k[j - 1] + (j <= r ? pq.k[j] : 0.f));
+  }
+  return true;
+}
+
 // =====================================================================================
 // Stage a4: FarnebackPolyExp for poly_n > 8 (the marching kernel of fb_polyexp.cuh serves 1..8).  32x32 output tile per 256-thread CTA; level image tile with an
 // n-pixel replicate halo staged in shared memory; vertical pass -> 3 moment planes in shared
@@ -613,20 +633,8 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
   int fused3_li = -1;
   float* img3[3] = {nullptr, nullptr, nullptr};          // S = 2, 4, 8
   PyrFast3Coef fc3;
-  if (OFB_EXP_PYR3 && n_levels >= 4 && (width & 7) == 0 && (height & 7) == 0 && (pitch & 3) == 0 && (image_stride & 3) == 0 &&
-      (reinterpret_cast<uintptr_t>(src.a) & 3) == 0 && (reinterpret_cast<uintptr_t>(src.b) & 3) == 0 && pc.n <= PX_MAXN) {
-    bool ok = true;
-    memset(&fc3, 0, sizeof(fc3));
-    for (int q = 0; q < 3 && ok; q++) {                  // q = 0, 1, 2: S = 2, 4, 8
-      const Level& lq = sched[n_levels - 2 - q];
-      const int S = 2 << q, r = q == 0 ? 1 : (q == 1 ? 4 : 9);
-      PyrCoef pq;
-      ok = lq.width * S == width && lq.height * S == height && prepare_pyr(lq.ksize, lq.sigma, &pq) == OFB_OK && pq.r == r;
-      if (ok) {
-        float* c = q == 0 ? fc3.c1 : (q == 1 ? fc3.c2 : fc3.c3);
-        for (int j = 1; j <= r + 1; j++) c[j - 1] = 0.5f * (pq.k[j - 1] + (j <= r ? pq.k[j] : 0.f));
-      }
-    }
+  if (OFB_EXP_PYR3 && (image_stride & 3) == 0 && pc.n <= PX_MAXN) {
+    const bool ok = pyr3_applicable(sched, n_levels, width, height, pitch, src.a, src.b, &fc3);
     if (ok) {
       fused3_li = n_levels - 4;
       const size_t n1 = (size_t)(width / 2) * (height / 2), n2 = n1 / 4;
@@ -700,7 +708,7 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
         const int segs = std::max(1, 2 * 3 * h->num_sms / (chunks * frames));
         const int seg_rows = std::max(2, (h3 + segs - 1) / segs);
         dim3 g(chunks, (h3 + seg_rows - 1) / seg_rows, frames);
-        k_pyr_fast3<<<g, PF_THREADS, 0, st>>>(src, width, height, img3[0], img3[1], img3[2], fc3, seg_rows);
+        k_pyr_fast3<<<g, PF_THREADS, 0, st>>>(src, width, height, img3[0], img3[1], img3[2], fc3, seg_rows, 0, h3);
         OFB_LAUNCH_CHECK(h);
         TE();
       }

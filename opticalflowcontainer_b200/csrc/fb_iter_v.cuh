@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
   constexpr int GROUPS = COLS / PXT;
   constexpr int NCONS = CH * GROUPS;
   static_assert(NCONS % 32 == 0, "whole consumer warps");
-  static_assert(!REUSE || (!TILED && CH == 2), "row-reuse schedule: chunks of two rows, untiled");
+  static_assert(!REUSE || CH == 2, "row-reuse schedule: chunks of two rows");
   static_assert(!TMEM || (COLS == 256 && MT >= 1 && (2 * MT + 1) * kTmemRingStride <= kTmemWgCols),
                 "TMEM ring: two producer warpgroups, ring slots within the warpgroup's columns");
   static_assert(NBUF >= 2 && NBUF <= 8, "staging buffers");
@@ -421,17 +421,34 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         const int ixa = __float2int_rd(pxa), iya = __float2int_rd(pya);
         const float fxa = pxa - (float)ixa, fya = pya - (float)iya;
         const bool ina = (unsigned)ixa < uw - 1u && (unsigned)iya < uh - 1u;
-        const unsigned ga = ina ? (unsigned)iya * uw + (unsigned)ixa : 0u;
-        if (ga != prev_g + uw) um_row_load(TA, RA1, RB1, ga);
-        um_row_load(Y, RA1, RB1, ga + uw);
+        // (outside pixels gather — and discard — from (0, 0); tiled mode: from the start of their own row, always local)
+        const unsigned ga = ina ? (unsigned)iya * uw + (unsigned)ixa : (TILED ? (unsigned)ya * uw : 0u);
         // pixel B
         const float pxb = xf + FB_.x, pyb = (float)yb + FB_.y;
         const int ixb = __float2int_rd(pxb), iyb = __float2int_rd(pyb);
         const float fxb = pxb - (float)ixb, fyb = pyb - (float)iyb;
         const bool inb = (unsigned)ixb < uw - 1u && (unsigned)iyb < uh - 1u;
-        const unsigned gb = inb ? (unsigned)iyb * uw + (unsigned)ixb : 0u;
+        const unsigned gb = inb ? (unsigned)iyb * uw + (unsigned)ixb : (TILED ? (unsigned)yb * uw : 0u);
         const bool reuse_b = ina && gb == ga + uw;
-        um_row_load(BZ, RA1, RB1, gb + uw);
+        // Tiled mode: corner rows outside the band this rank computed live in their owner's buffer (NVLink peer pointer).
+        // A warp whose rows are all local (the common case) takes the plain loads.
+        const int rowa = ina ? iya : ya, rowb = inb ? iyb : yb;
+        bool all_local = true;
+        if constexpr (TILED)
+          all_local = __all_sync(FULLMASK, min(rowa, rowb) >= tab.r_lo && max(rowa, rowb) + 1 < tab.r_hi);
+        auto ldrow = [&](UmRow& R, unsigned g, int row) {
+          if constexpr (TILED) {
+            if (!all_local) {
+              const int o = (row >= tab.r_lo && row < tab.r_hi) ? my_rank : tile_owner(row, tab);
+              um_row_load(R, tab.RA[o] + n, tab.RB[o] + n, g);
+              return;
+            }
+          }
+          um_row_load(R, RA1, RB1, g);
+        };
+        if (ga != prev_g + uw) ldrow(TA, ga, rowa);
+        ldrow(Y, ga + uw, rowa + 1);
+        ldrow(BZ, gb + uw, rowb + 1);
         prev_g = inb ? gb : ~0u - uw;
         // input flow of the next chunk (volatile: it stays here, in front of the barrier and the arithmetic)
         if constexpr (UPS) {
@@ -496,7 +513,7 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
           // B's top row where it is not A's bottom row (flow discontinuity, floor crossing, outside pixel): loaded late
           // into A's top-row registers, free now — a wait for memory in the rare case instead of ten registers held
           // through every chunk
-          if (!reuse_b) um_row_load(TA, RA1, RB1, gb);
+          if (!reuse_b) ldrow(TA, gb, rowb);
           UmRow W = TA;
           if (reuse_b) W = Y;                                        // (select per thread: 10 predicated moves)
           ring_step(um_arith(a0b, b0b, W.q0, W.q1, BZ.q0, BZ.q1, W.s0, W.s1, BZ.s0, BZ.s1, fxb, fyb, FB_.x, FB_.y, inb,

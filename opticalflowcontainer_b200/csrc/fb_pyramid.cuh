@@ -340,10 +340,10 @@ __device__ __forceinline__ void pf3_hfilt(const float* __restrict__ rows, const 
   }
 }
 
-// grid: (ceil(w3 / 126), ceil(h3 / seg_rows), frames); out1/2/3: the level images [frames][h_l][w_l] of S = 2, 4, 8.
+// grid: (ceil(w3 / 126), ceil((y3_end - y3_begin) / seg_rows), frames); out1/2/3: the level images [frames][h_l][w_l] of S = 2, 4, 8.
 __global__ void __launch_bounds__(PF_THREADS, 3) k_pyr_fast3(FrameSrc src, int W, int H, float* __restrict__ out1,
                                                           float* __restrict__ out2, float* __restrict__ out3,
-                                                          PyrFast3Coef pc, int seg_rows) {
+                                                          PyrFast3Coef pc, int seg_rows, int y3_begin, int y3_end) {
   constexpr int S = 8, R = 9, WIN = 20;
   constexpr int OUT3 = (PF_COLS - 2 * PF_HALO) / 8;
   __shared__ float rowbuf[7 * PF3_STRIDE];              // row 0: S = 8; rows 1, 2: S = 4; rows 3..6: S = 2
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) k_pyr_fast3(FrameSrc src, int W
   const int tid = threadIdx.x;
   const int xo0 = blockIdx.x * OUT3;                    // first S = 8 level column of the chunk
   const int x = S * xo0 - PF_HALO + 4 * tid;            // first of this thread's 4 source columns (multiple of 4)
-  const int y0 = blockIdx.y * seg_rows, y1 = min(y0 + seg_rows, h3);
+  const int y0 = y3_begin + blockIdx.y * seg_rows, y1 = min(y0 + seg_rows, y3_end);   // rows [y3_begin, y3_end) of the S = 8 level
   const uint8_t* frame = src.frame(blockIdx.z);
   const bool interior = x >= 0 && x + 3 < W;
   const bool dead = x > W + 5;                          // right of everything a level column of this frame reads

@@ -67,6 +67,11 @@ struct TiledPlan {
   int r_lo[kMaxLevels], r_hi[kMaxLevels];
   size_t r_off[kMaxLevels];
   int res_idx[kMaxLevels];   // ping-pong buffer that holds the level's result
+  // the three regular levels in one pass over the source (k_pyr_fast3): level index of the S = 8 level (-1: per level),
+  // rows of that level to run, the level images' offsets in d_img (S = 2, 4, 8)
+  int fused3_li, y3_lo, y3_hi;
+  size_t img3_off[3];
+  PyrFast3Coef fc3;
 };
 
 static inline void tile_rows(int hh, int world, int rank, int* rpr, int* yb, int* ye) {
@@ -110,7 +115,23 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
     src.image_stride = 0;
     const int frames = 2;
     const bool fused_src = w == pl.width && hh == pl.height && pyc.r == 1 && pyc.k[0] == 0.5f && pyc.k[1] == 0.25f;
-    if (!fused_src) {
+    const float* level_img = h->d_img;
+    const bool in_fused3 = pl.fused3_li >= 0 && li >= pl.fused3_li && li < pl.n_levels - 1;
+    if (in_fused3) {
+      level_img = h->d_img + pl.img3_off[pl.n_levels - 2 - li];
+      if (li == pl.fused3_li) {
+        TB(OFB_STAGE_PYRAMID);
+        constexpr int out3 = (PF_COLS - 2 * PF_HALO) / 8;
+        const int chunks = (pl.width / 8 + out3 - 1) / out3, rows = pl.y3_hi - pl.y3_lo;
+        const int segs = std::max(1, 2 * 3 * h->num_sms / (chunks * frames));
+        const int seg_rows = std::max(2, (rows + segs - 1) / segs);
+        dim3 g(chunks, (rows + seg_rows - 1) / seg_rows, frames);
+        k_pyr_fast3<<<g, PF_THREADS, 0, st>>>(src, pl.width, pl.height, h->d_img + pl.img3_off[0], h->d_img + pl.img3_off[1],
+                                              h->d_img + pl.img3_off[2], pl.fc3, seg_rows, pl.y3_lo, pl.y3_hi);
+        OFB_LAUNCH_CHECK(h);
+        TE();
+      }
+    } else if (!fused_src) {
       const int lb = std::max(yb - pl.pc.n, 0), le = std::min(ye + pl.pc.n, hh);   // level rows PolyExp reads
       const double sy = 1.0 / ((double)hh / pl.height);
       const int sb = std::max(lin_entry(lb, sy, pl.height).i0 - pyc.r - 1, 0);
@@ -151,9 +172,9 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
                                                        pl.pc, yb, ye);
       } else {
         if (pl.pc.n == 5)
-          k_polyexp_march<5, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
+          k_polyexp_march<5, 0><<<g, PX_COLS, 0, st>>>(level_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
         else
-          k_polyexp_march<0, 0><<<g, PX_COLS, 0, st>>>(h->d_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
+          k_polyexp_march<0, 0><<<g, PX_COLS, 0, st>>>(level_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
       }
       OFB_LAUNCH_CHECK(h);
     }
@@ -164,8 +185,13 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
   // ---- iteration `it` of level li on the rows need +- (iterations - 1 - it) * m (all inputs local; R1 gathers beyond the
   // band go to the owner's buffer through the peer table)
   const int n_it = p->iterations, m = pl.bc.m;
-  const int yb = std::max(pl.need_lo[li] - (n_it - 1 - it) * m, 0), ye = std::min(pl.need_hi[li] + (n_it - 1 - it) * m, hh);
+  int yb = std::max(pl.need_lo[li] - (n_it - 1 - it) * m, 0);
+  const int ye = std::min(pl.need_hi[li] + (n_it - 1 - it) * m, hh);
   const bool last_it = it == n_it - 1;
+  // the fused upsample's interior form starts its chunks on odd matrix rows (even band start, odd radius): one more row
+  // at the top where needed — local scratch rows (never the final field: a level's first iteration is not its last
+  // unless iterations == 1, where the owned rows start at a multiple of the even rows-per-rank or this is skipped)
+  if (it == 0 && li > 0 && !(last_level && last_it) && (yb & 1) && yb > 0) yb -= 1;
   // flow ping-pong as in the whole-frame driver: the first iteration of a level reads the coarser level's result (fused
   // upsample) and must not write the buffer that holds it
   const int prev_idx = li > 0 ? pl.res_idx[li - 1] : 1;
@@ -205,8 +231,9 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
   const RSet rs1 = {RA, RB, RA + (size_t)w * hh, RB + (size_t)w * hh};
   TB(OFB_STAGE_ITERATION);
   if (pl.bc.m == 7) {
-    if (up) e = launch_iter_v<7, 256, 2, 2, 3, true, false, false, 2, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
-    else e = launch_iter_v<7, 256, 2, 2, 3, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
+    // (the default schedule: two rows in flight, row-reuse gather, ring in tensor memory — as the whole-frame path)
+    if (up) e = launch_iter_v<7, 256, 2, 2, 0, true, true, true, 4, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
+    else e = launch_iter_v<7, 256, 2, 2, 0, true, true, true, 4>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
   } else {
     if (up) e = launch_iter_v<0, 128, 4, 1, 0, true, false, false, 2, true>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, up, yb, ye, &t, rank);
     else e = launch_iter_v<0, 128, 4, 1, 0, true, false, false, 2>(h, fin, fout, w, hh, 1, rs1, pl.bc.m, reg, st, nullptr, yb, ye, &t, rank);
@@ -281,6 +308,24 @@ static int tiled_make_plan(ofb_handle* h, TiledPlan* pl, const uint8_t* d_prev, 
   for (int li = 0; li < nl; li++) {
     const int prev_idx = li > 0 ? pl->res_idx[li - 1] : 1;
     pl->res_idx[li] = (prev_idx ^ 1) ^ ((p->iterations - 1) & 1);
+  }
+  pl->fused3_li = -1;
+  if (OFB_EXP_PYR3 && pyr3_applicable(pl->sched, nl, width, height, pitch, d_prev, d_next, &pl->fc3) &&
+      pl->need_hi[nl - 1] > pl->need_lo[nl - 1]) {
+    pl->fused3_li = nl - 4;
+    const size_t n1 = (size_t)(width / 2) * (height / 2);
+    pl->img3_off[0] = 0;
+    pl->img3_off[1] = 2 * n1;
+    pl->img3_off[2] = 2 * n1 + 2 * (n1 / 4);
+    int lo = height, hi = 0;
+    for (int q = 0; q < 3; q++) {                        // S = 2, 4, 8: level rows PolyExp reads -> rows of the S = 8 level
+      const int li = nl - 2 - q, hh = pl->sched[li].height, per = 4 >> q;
+      const int lb = std::max(pl->r_lo[li] - pl->pc.n, 0), le = std::min(pl->r_hi[li] + pl->pc.n, hh);
+      lo = std::min(lo, lb / per);
+      hi = std::max(hi, (le + per - 1) / per);
+    }
+    pl->y3_lo = lo;
+    pl->y3_hi = std::min(hi, height / 8);
   }
   pl->width = width;
   pl->height = height;
