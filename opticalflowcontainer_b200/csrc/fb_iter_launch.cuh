@@ -46,7 +46,11 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   const int per = strips * n_pairs;
   const int rows = y_end - y_begin;
   int segs = per >= slots ? 1 : slots / per;
-  int seg_rows = std::max(16, (rows + segs - 1) / segs);
+  // Tiled mode (one pair, narrow bands): at least 6 rows per segment — a segment pays 2m warm-up rows, but these are
+  // latency-bound launches, where more, shorter CTAs on otherwise idle SMs finish sooner.  Whole frames: at least 16,
+  // which also keeps the segmentation of small frames (and with it the rounding of the vertical block sums) the same
+  // for every batch size.
+  int seg_rows = std::max(REUSE && TILED ? 6 : 16, (rows + segs - 1) / segs);
   seg_rows += seg_rows & 1;       // even: the chunks of the fused upsample then start on odd rows (fb_iter_v.cuh)
   segs = (rows + seg_rows - 1) / seg_rows;
   dim3 g(strips * segs, n_pairs);
