@@ -313,7 +313,7 @@ int ofb_clahe(ofb_handle* h, const uint8_t* src, int width, int height, size_t s
  * [c_min, c_max] to [clip_min, clip_max]) when `adaptive` is set, else `clip_limit` — and cv2.cvtColor(..., HSV2RGB):
  * a bgr8 frame in, the rgb8 frame the node continues with out, every step bit-exact with this cv2 build
  * (oracle/prefilter_np.py).  *clip_used receives the clip limit applied.  The bilateral filter that may follow
- * (:189-191) is NOT included: its restatement is not pinned bit-exactly yet.  Synchronous. */
+ * (:186-190) is ofb_bilateral_u8c3.  Synchronous. */
 typedef struct ofb_clahe_params {
   int adaptive;                              /* 1: clip limit from the frame's contrast, 0: clip_limit */
   double clip_limit;
@@ -322,6 +322,15 @@ typedef struct ofb_clahe_params {
 } ofb_clahe_params;
 int ofb_adapt_prefilter(ofb_handle* h, const uint8_t* bgr, int width, int height, size_t stride_bytes,
                         const ofb_clahe_params* params, uint8_t* rgb, size_t rgb_stride_bytes, double* clip_used);
+
+/* cv2.bilateralFilter(src, d, sigmaColor, sigmaSpace) on a uint8 3-channel frame: the optional last step of the adapt
+ * node's pre-filter chain (lfn3_adapt_node.py:186-190, applied to the rgb frame ofb_adapt_prefilter returns).  OpenCV's
+ * own 8UC3 algorithm (circular support of radius d/2 — round(1.5 sigmaSpace) for d <= 0 —, REFLECT_101 border, float
+ * space / colour weight tables, out = round(sum * (1 / wsum))), bit-exact with its restatement
+ * oracle/prefilter_np.py::bilateral_u8c3.  The installed wheel sends 8-bit images through Intel IPP instead and
+ * differs from both at rounding ties (a few values per 100 000, by one).  Radius <= 15.  Synchronous. */
+int ofb_bilateral_u8c3(ofb_handle* h, const uint8_t* src, int width, int height, size_t src_stride_bytes, int d,
+                       double sigma_color, double sigma_space, uint8_t* dst, size_t dst_stride_bytes);
 
 /* ---- sparse path: replaces cv2.goodFeaturesToTrack + cv2.calcOpticalFlowPyrLK -- */
 

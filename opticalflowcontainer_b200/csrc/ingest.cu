@@ -10,6 +10,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "fb_device.cuh"
 
 namespace ofb {
 
@@ -284,6 +285,76 @@ static int ingest_reserve(ofb_handle* h, size_t bytes_a, size_t bytes_b) {
   return OFB_OK;
 }
 
+// ---- bilateral filter of the adapt node (lfn3_adapt_node.py:186-190: cv2.bilateralFilter(rgb, d, sigmaColor, sigmaSpace)) ----
+// OpenCV's own algorithm for 8UC3 (modules/imgproc/src/bilateral_filter.dispatch.cpp / .simd.hpp, restated in
+// oracle/prefilter_np.py::bilateral_u8c3): a circular support of radius d/2 (REFLECT_101 border), per tap
+//   w = space_weight[k] * color_weight[|db| + |dg| + |dr|]        (float product of two float tables)
+//   wsum += w ; sum_c = fma(neighbour_c, w, sum_c)                 (taps in row-major order of the support)
+// and out_c = round(sum_c * (1 / wsum)).  Bit-exact against the restatement; against the installed wheel the result
+// differs at rounding ties only (a few values per 100 000, by one): the wheel routes 8-bit bilateralFilter through Intel
+// IPP, whose arithmetic is not published (tests/test_node_gpu.py::test_bilateral states both facts).
+constexpr int kBilMaxTaps = 1024;                     // (2 * 15 + 1)^2 = 961 >= the support of radius 15
+__constant__ float c_bil_cw[768];
+__constant__ float c_bil_sw[kBilMaxTaps];
+__constant__ short2 c_bil_off[kBilMaxTaps];           // (dy, dx)
+
+__global__ void __launch_bounds__(256) k_bilateral_u8c3(const uint8_t* __restrict__ src, size_t sp, int w, int h, int n_taps,
+                                                        uint8_t* __restrict__ dst, size_t dp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t* c = src + (size_t)y * sp + (size_t)x * 3;
+  const int c0 = c[0], c1 = c[1], c2 = c[2];
+  float wsum = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < n_taps; k++) {
+    const short2 o = c_bil_off[k];
+    const int yy = reflect101(y + o.x, h), xx = reflect101(x + o.y, w);
+    const uint8_t* q = src + (size_t)yy * sp + (size_t)xx * 3;
+    const int b = q[0], g = q[1], r = q[2];
+    const float wgt = __fmul_rn(c_bil_sw[k], c_bil_cw[abs(b - c0) + abs(g - c1) + abs(r - c2)]);
+    wsum = __fadd_rn(wsum, wgt);
+    s0 = __fmaf_rn((float)b, wgt, s0);
+    s1 = __fmaf_rn((float)g, wgt, s1);
+    s2 = __fmaf_rn((float)r, wgt, s2);
+  }
+  const float inv = __fdiv_rn(1.f, wsum);
+  uint8_t* o = dst + (size_t)y * dp + (size_t)x * 3;
+  o[0] = (uint8_t)min(max(__float2int_rn(__fmul_rn(s0, inv)), 0), 255);
+  o[1] = (uint8_t)min(max(__float2int_rn(__fmul_rn(s1, inv)), 0), 255);
+  o[2] = (uint8_t)min(max(__float2int_rn(__fmul_rn(s2, inv)), 0), 255);
+}
+
+// the filter on a device frame (3 bytes per pixel): tables to constant memory, one launch
+static int bilateral_device(ofb_handle* h, const uint8_t* d_src, size_t sp, int width, int height, int d, double sigma_color,
+                            double sigma_space, uint8_t* d_dst, size_t dp) {
+  if (sigma_color <= 0) sigma_color = 1.0;
+  if (sigma_space <= 0) sigma_space = 1.0;
+  int radius = d <= 0 ? (int)__builtin_nearbyint(sigma_space * 1.5) : d / 2;
+  radius = std::max(radius, 1);
+  if (radius > 15) return set_error(h, OFB_ERR_INVALID_ARG, "bilateral filter: radius %d > 15", radius);
+  if (radius >= width || radius >= height) return set_error(h, OFB_ERR_INVALID_ARG, "bilateral filter: image smaller than the support");
+  const double gc = -0.5 / (sigma_color * sigma_color), gs = -0.5 / (sigma_space * sigma_space);
+  static thread_local float cw[768], sw[kBilMaxTaps];
+  static thread_local short2 off[kBilMaxTaps];
+  for (int i = 0; i < 768; i++) cw[i] = (float)std::exp((double)i * i * gc);
+  int n = 0;
+  for (int i = -radius; i <= radius; i++)
+    for (int j = -radius; j <= radius; j++) {
+      const double r = std::sqrt((double)i * i + (double)j * j);
+      if (r > radius) continue;
+      sw[n] = (float)std::exp(r * r * gs);
+      off[n] = make_short2((short)i, (short)j);
+      n++;
+    }
+  cudaStream_t sm = h->stream;
+  OFB_CUDA(h, cudaMemcpyToSymbolAsync(c_bil_cw, cw, sizeof(cw), 0, cudaMemcpyHostToDevice, sm));
+  OFB_CUDA(h, cudaMemcpyToSymbolAsync(c_bil_sw, sw, n * sizeof(float), 0, cudaMemcpyHostToDevice, sm));
+  OFB_CUDA(h, cudaMemcpyToSymbolAsync(c_bil_off, off, n * sizeof(short2), 0, cudaMemcpyHostToDevice, sm));
+  OFB_CUDA(h, cudaStreamSynchronize(sm));               // (the host tables are reused by the next call)
+  k_bilateral_u8c3<<<dim3((width + 255) / 256, height), 256, 0, sm>>>(d_src, sp, width, height, n, d_dst, dp);
+  OFB_LAUNCH_CHECK(h);
+  return OFB_OK;
+}
+
 }  // namespace ofb
 
 using namespace ofb;
@@ -415,6 +486,28 @@ int ofb_clahe(ofb_handle* h, const uint8_t* src, int width, int height, size_t s
                                                                           tiles_y, 1.f / (float)tw, 1.f / (float)th, luts);
   OFB_LAUNCH_CHECK(h);
   OFB_CUDA(h, cudaMemcpy2DAsync(dst, dst_stride_bytes, g.d_b, pitch, width, height, cudaMemcpyDeviceToHost, h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+int ofb_bilateral_u8c3(ofb_handle* h, const uint8_t* src, int width, int height, size_t src_stride_bytes, int d,
+                       double sigma_color, double sigma_space, uint8_t* dst, size_t dst_stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!src || !dst) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  if (width < 2 || height < 2) return set_error(h, OFB_ERR_INVALID_ARG, "bad size");
+  const size_t row3 = (size_t)width * 3;
+  if (src_stride_bytes == 0) src_stride_bytes = row3;
+  if (dst_stride_bytes == 0) dst_stride_bytes = row3;
+  if (src_stride_bytes < row3 || dst_stride_bytes < row3) return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row");
+  OFB_CUDA(h, cudaSetDevice(h->device));
+  int st = ingest_reserve(h, row3 * height, row3 * height);
+  if (st) return st;
+  ofb_handle::Ingest& g = h->ingest;
+  OFB_CUDA(h, cudaMemcpy2DAsync(g.d_a, row3, src, src_stride_bytes, row3, height, cudaMemcpyHostToDevice, h->stream));
+  if ((st = timing_begin(h, OFB_STAGE_OTHER))) return st;
+  if ((st = bilateral_device(h, g.d_a, row3, width, height, d, sigma_color, sigma_space, g.d_b, row3))) return st;
+  if ((st = timing_end(h))) return st;
+  OFB_CUDA(h, cudaMemcpy2DAsync(dst, dst_stride_bytes, g.d_b, row3, row3, height, cudaMemcpyDeviceToHost, h->stream));
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
   return OFB_OK;
 }

@@ -432,6 +432,24 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out, used.value
 
+    def bilateral_filter(self, src, d: int, sigmaColor: float, sigmaSpace: float) -> np.ndarray:
+        """``cv2.bilateralFilter(src, d, sigmaColor, sigmaSpace)`` on a uint8 [H,W,3] frame (the last, optional step of the
+        adapt node's pre-filter, lfn3_adapt_node.py:186-190).  OpenCV's own algorithm, bit-exact with
+        ``oracle/prefilter_np.py::bilateral_u8c3``; the installed wheel (Intel IPP for 8-bit images) differs by one at
+        rounding ties in a few values per 100 000."""
+        src = np.asarray(src)
+        if src.dtype != np.uint8 or src.ndim != 3 or src.shape[2] != 3:
+            raise OfbError(1, "bilateral_filter needs a uint8 [H,W,3] frame")
+        if src.strides[2] != 1 or src.strides[1] != 3:
+            src = np.ascontiguousarray(src)
+        hgt, wid = src.shape[:2]
+        out = np.empty((hgt, wid, 3), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_bilateral_u8c3(self._h, src.ctypes.data, wid, hgt, src.strides[0], int(d), float(sigmaColor),
+                                              float(sigmaSpace), out.ctypes.data, 0)
+            _lib.check(st, self._h)
+        return out
+
     def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3, mask=None) -> np.ndarray:
         image = _u8_image(image, "image")
         hgt, wid = image.shape

@@ -22,7 +22,8 @@ BGR2HSV, HSV2RGB and the chain without the bilateral filter are pinned bit for b
 ``tests/test_oracle_prefilter.py``.  The bilateral restatement is NOT: this wheel routes the 8-bit bilateralFilter
 through Intel IPP (``cv2.ipp.useIPP()`` is True; with ``cv2.ipp.setUseIPP(False)`` the mismatches drop from 13 to 3 in
 1.9 M values), whose arithmetic is not published; the restatement of OpenCV's own code differs from it at rounding ties
-(a few values per 100 000, off by one) — parity unpinned for that step, which is therefore not built on the device.
+(a few values per 100 000, off by one) — parity UNPINNED for that step: the device filter (``ofb_bilateral_u8c3``) is
+bit-exact with this restatement and held to "at most one grey level in at most 1 value per 10 000" against the wheel.
 """
 from __future__ import annotations
 

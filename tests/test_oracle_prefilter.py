@@ -39,8 +39,8 @@ def test_hsv2rgb_equals_cv2(width):
 @pytest.mark.parametrize("params", [(9, 75.0, 75.0), (5, 50.0, 50.0), (9, 25.5, 10.0), (0, 30.0, 3.0), (7, 12.0, 2.5)])
 def test_bilateral_restatement_is_not_pinned_yet(params):
     """The bilateral restatement agrees with cv2 except at rounding ties (values within one float ulp of x.5, where the
-    wheel rounds up): at most a few values per 100 000, off by one.  NOT bit-exact -> the filter is not built on the
-    device; this test records how close the restatement is."""
+    wheel rounds up): at most a few values per 100 000, off by one.  NOT bit-exact (the wheel's IPP path; parity unpinned,
+    DESIGN.md 7); this test records how close the restatement is — the device filter equals the restatement bit for bit."""
     img = _frame(150, 200, int(params[1]))
     d = np.abs(P.bilateral_u8c3(img, *params).astype(int) - cv2.bilateralFilter(img, *params).astype(int))
     assert d.max() <= 1 and (d > 0).sum() <= 1e-4 * d.size
