@@ -48,7 +48,8 @@ typedef enum ofb_status {
   OFB_ERR_CUDA = 2,        /* a CUDA runtime call or kernel launch failed */
   OFB_ERR_NO_DEVICE = 3,   /* no usable CUDA device: there is no CPU fallback */
   OFB_ERR_CAPACITY = 4,    /* frame or batch larger than the handle was created for */
-  OFB_ERR_ALLOC = 5
+  OFB_ERR_ALLOC = 5,
+  OFB_ERR_UNSUPPORTED = 6  /* a stream the device path does not decode (e.g. progressive JPEG): decode it on the host */
 } ofb_status;
 
 /* cv2 flag values (cv2.OPTFLOW_*), identical numbers */
@@ -301,6 +302,28 @@ int ofb_resize_u8(ofb_handle* h, const uint8_t* src, int src_width, int src_heig
  * converted to gray (cv2.cvtColor); dst receives the uint8 [dst_height][dst_width] frame the flow calls take. */
 int ofb_ingest_gray(ofb_handle* h, const uint8_t* src, int src_width, int src_height, size_t src_stride_bytes,
                     int rgb_order, uint8_t* dst, int dst_width, int dst_height, size_t dst_stride_bytes);
+
+/* ---- JPEG frames (sensor_msgs/CompressedImage): cv2.imdecode(np.frombuffer(msg.data, np.uint8), cv2.IMREAD_COLOR) of the
+ * compressed-image node, ros2_ws/src/optical_flow/optical_flow/opticalflow_comprerssed_node.py:43-46.  Baseline JPEG
+ * (SOF0/SOF1, 8 bit, Huffman, one interleaved scan; gray-scale or YCbCr 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0, restart intervals),
+ * bit-exact with the libjpeg-turbo 3.1.2 build inside the cv2 wheel (islow IDCT, fancy up-sampling, BGR output;
+ * oracle/jpeg_np.py).  The host walks the entropy-coded bit stream into coefficient blocks; dequantisation, IDCT,
+ * chroma up-sampling, colour conversion and the gray conversion run on the device.  Anything else (progressive,
+ * arithmetic, 12 bit, CMYK) returns OFB_ERR_UNSUPPORTED — never a wrong frame, never a CPU decode. */
+/* Frame header only (no handle, no device work): size and component count for sizing the output arrays. */
+int ofb_jpeg_info(const uint8_t* jpeg, size_t n_bytes, int* width, int* height, int* components);
+/* The host half on its own (no handle, no device work): the quantised DCT coefficients of the scan, int16, component
+ * after component (Y, Cb, Cr), each a row-major grid of whole blocks (padded to whole MCUs) of 64 coefficients in
+ * natural (row-major) order.  coef may be NULL to query *n_coef. */
+int ofb_jpeg_entropy_decode(const uint8_t* jpeg, size_t n_bytes, int16_t* coef, size_t coef_capacity, size_t* n_coef);
+/* bgr: host uint8 [height][width][3] = cv2.imdecode(buf, IMREAD_COLOR), and/or gray: host uint8 [height][width] =
+ * cv2.cvtColor(that, COLOR_BGR2GRAY); either may be NULL, strides 0 = packed.  Synchronous. */
+int ofb_jpeg_decode(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* bgr, size_t bgr_stride_bytes, uint8_t* gray,
+                    size_t gray_stride_bytes);
+/* ofb_ingest_gray for a compressed frame: decode, cv2.resize of the colour frame to dst_width x dst_height if it has
+ * another size, cv2.cvtColor(BGR2GRAY); only the gray frame crosses PCIe back.  Synchronous. */
+int ofb_ingest_jpeg_gray(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* dst, int dst_width, int dst_height,
+                         size_t dst_stride_bytes);
 
 /* cv2.createCLAHE(clip_limit, (tiles_x, tiles_y)).apply(src) on a uint8 single-channel image, bit-exact with this
  * cv2 build (oracle/clahe_np.py).  The adapt node's contrast pre-filter: lfn3_adapt_node.py:164-182

@@ -90,6 +90,10 @@ _SIGNATURES = {
                                       C.POINTER(C.c_double)]),
     "ofb_bilateral_u8c3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double,
                                      C.c_void_p, C.c_size_t]),
+    "ofb_jpeg_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ofb_jpeg_entropy_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ofb_jpeg_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "ofb_ingest_jpeg_gray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
     "ofb_launch_count": (C.c_uint64, [C.c_void_p]),
     "ofb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ofb_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

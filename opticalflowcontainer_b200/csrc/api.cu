@@ -94,6 +94,7 @@ const char* ofb_status_string(int s) {
     case OFB_ERR_NO_DEVICE: return "no usable CUDA device (libofb has no CPU fallback)";
     case OFB_ERR_CAPACITY: return "request exceeds handle capacity";
     case OFB_ERR_ALLOC: return "allocation failed";
+    case OFB_ERR_UNSUPPORTED: return "stream not decoded on the device";
     default: return "unknown status";
   }
 }
@@ -166,6 +167,7 @@ int ofb_destroy(ofb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   sparse_destroy(h);
+  jpeg_destroy(h);
   cudaFree(h->d_src); cudaFree(h->d_img); cudaFree(h->d_RA); cudaFree(h->d_RB);
   cudaFree(h->d_MA); cudaFree(h->d_MB); cudaFree(h->d_VA); cudaFree(h->d_VB);
   for (int i = 0; i < 3; i++) cudaFree(h->d_flow[i]);

@@ -190,6 +190,7 @@ struct ofb_handle {
 
   // sparse path buffers are owned by lk.cu / features.cu state
   void* sparse = nullptr;
+  void* jpeg = nullptr;         // jpeg.cu: coefficient staging and sample planes
 
   // per-stage event timing (ofb_timing_enable / ofb_timing_read)
   bool timing = false;
@@ -266,6 +267,14 @@ int flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_thre
 int flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes);
 int flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes);
 int flow_sample(ofb_handle* h, int pair, int n_points, const int* xy, float* out_dxdy);   // synchronises the stream, copies staged scalars to the callers' arrays
+
+// ---- ingest.cu / jpeg.cu
+int ingest_reserve(ofb_handle* h, size_t bytes_a, size_t bytes_b);
+int resize_u8_device(ofb_handle* h, const uint8_t* d_src, size_t sp, int sw, int sh, int cn, uint8_t* d_dst, size_t dp,
+                     int dw, int dh);
+int cvt_gray_device(ofb_handle* h, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch, int w,
+                    int hh, int rgb_order);
+void jpeg_destroy(ofb_handle* h);
 
 // ---- sparse ---------------------------------------------------------------------------
 void sparse_destroy(ofb_handle* h);

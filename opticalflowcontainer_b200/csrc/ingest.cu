@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k_hsv2rgb_planes(const uint8_t* __restric
   d[0] = (uint8_t)min(max(ir, 0), 255); d[1] = (uint8_t)min(max(ig, 0), 255); d[2] = (uint8_t)min(max(ib, 0), 255);
 }
 
-static int ingest_reserve(ofb_handle* h, size_t bytes_a, size_t bytes_b) {
+int ingest_reserve(ofb_handle* h, size_t bytes_a, size_t bytes_b) {
   ofb_handle::Ingest& g = h->ingest;
   if (bytes_a > g.a_bytes) {
     OFB_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -1,0 +1,629 @@
+// jpeg.cu — baseline-JPEG frame ingest: cv2.imdecode(buf, cv2.IMREAD_COLOR) of the compressed-image node
+// (ros2_ws/src/optical_flow/optical_flow/opticalflow_comprerssed_node.py:43-46), bit-exact with the wheel's
+// libjpeg-turbo 3.1.2 defaults (JDCT_ISLOW, fancy upsampling, JCS_EXT_BGR).  Restated in oracle/jpeg_np.py.
+//
+// Split of the work: the entropy-coded segment is a serial bit stream (every symbol's position depends on all symbols
+// before it), so the HOST walks it — marker parsing and Huffman decoding into quantised coefficient blocks written
+// straight into pinned staging — and everything that is per-sample arithmetic runs on the DEVICE:
+//   k_jpeg_idct   dequantisation + the 13-bit fixed-point LL&M inverse DCT (jidctint.c::jpeg_idct_islow), one thread
+//                 per block column / row, workspace in shared memory, planes of 8-bit samples out;
+//   k_jpeg_color  chroma up-sampling with the triangle filter (jdsample.c: h2v1 / h2v2 / h1v2 "fancy", edge rules of
+//                 the library) fused with YCbCr -> BGR (jdcolor.c, 16-bit fixed point) and, when asked for, the gray
+//                 conversion the nodes apply next (cv2.cvtColor BGR2GRAY, 15-bit fixed point).
+// The decoded frame never exists on the host unless the caller asks for it.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ofb {
+
+namespace {
+
+constexpr int kMaxComp = 3;
+
+struct HuffTab {
+  // canonical code tables (T.81 F.2.2.3) + a kLook-bit look-ahead table: entry = (length << 8) | symbol, 0 = longer code
+  static constexpr int kLook = 10;
+  uint16_t look[1 << kLook];
+  int32_t maxcode[18];   // largest code of each length, -1 if none; [17] = sentinel
+  int32_t valoff[17];    // index of the first symbol of a length minus its first code
+  uint8_t vals[256];
+  bool present = false;
+};
+
+struct Comp {
+  int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
+  int blocks_x = 0, blocks_y = 0;     // whole blocks of the padded plane
+  int dw = 0, dh = 0;                 // real samples (ceil(width * h / hmax), ceil(height * v / vmax))
+  size_t coef_off = 0;                // first coefficient of the component in the staging array (int16 units)
+};
+
+struct Frame {
+  int width = 0, height = 0, nc = 0, hmax = 1, vmax = 1, mcux = 0, mcuy = 0, dri = 0;
+  Comp comp[kMaxComp];
+  uint16_t qt[4][64];                 // natural order
+  bool qt_present[4] = {false, false, false, false};
+  HuffTab dc[4], ac[4];
+  const uint8_t* data = nullptr;      // entropy-coded segment
+  size_t n_data = 0;
+  size_t n_coef = 0;                  // int16 coefficients of all components
+};
+
+const uint8_t kZigzag[64 + 16] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
+                                  6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31,
+                                  39, 46, 53, 60, 61, 54, 47, 55, 62, 63,
+                                  63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};   // corrupt runs land on 63
+
+bool build_huff(const uint8_t* counts, const uint8_t* vals, int n, HuffTab* t) {
+  memset(t->look, 0, sizeof(t->look));
+  memcpy(t->vals, vals, n);
+  int code = 0, k = 0;
+  for (int len = 1; len <= 16; len++) {
+    t->valoff[len] = k - code;
+    if (counts[len - 1]) {
+      for (int i = 0; i < counts[len - 1]; i++, code++, k++) {
+        if (len <= HuffTab::kLook) {
+          const int lo = code << (HuffTab::kLook - len);
+          for (int j = 0; j < (1 << (HuffTab::kLook - len)); j++) t->look[lo + j] = (uint16_t)((len << 8) | vals[k]);
+        }
+      }
+      t->maxcode[len] = code - 1;
+    } else {
+      t->maxcode[len] = -1;
+    }
+    if (code > (1 << len)) return false;
+    code <<= 1;
+  }
+  t->maxcode[17] = 0x7fffffff;
+  t->present = true;
+  return true;
+}
+
+// Markers up to the first SOS.  Returns NULL or the reason the stream is not served.
+const char* parse_jpeg(const uint8_t* b, size_t n, Frame* f, bool header_only) {
+  if (n < 4 || b[0] != 0xFF || b[1] != 0xD8) return "not a JPEG stream";
+  size_t pos = 2;
+  bool have_sof = false;
+  while (true) {
+    while (pos < n && b[pos] != 0xFF) pos++;
+    while (pos < n && b[pos] == 0xFF) pos++;
+    if (pos >= n) return "no scan in the JPEG stream";
+    const int m = b[pos++];
+    if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+    if (m == 0xD9) return "no scan in the JPEG stream";
+    if (pos + 2 > n) return "truncated JPEG stream";
+    const size_t len = ((size_t)b[pos] << 8) | b[pos + 1];
+    if (len < 2 || pos + len > n) return "truncated JPEG stream";
+    const uint8_t* s = b + pos + 2;
+    const size_t sl = len - 2;
+    if (m == 0xDB) {
+      size_t i = 0;
+      while (i < sl) {
+        const int pq = s[i] >> 4, tq = s[i] & 15;
+        i++;
+        if (tq > 3 || i + (pq ? 128 : 64) > sl) return "bad quantisation table";
+        for (int k = 0; k < 64; k++) {
+          f->qt[tq][kZigzag[k]] = pq ? (uint16_t)((s[i + 2 * k] << 8) | s[i + 2 * k + 1]) : s[i + k];
+        }
+        f->qt_present[tq] = true;
+        i += pq ? 128 : 64;
+      }
+    } else if (m == 0xC4) {
+      size_t i = 0;
+      while (i < sl) {
+        if (i + 17 > sl) return "bad Huffman table";
+        const int tc = s[i] >> 4, th = s[i] & 15;
+        int cnt = 0;
+        for (int k = 0; k < 16; k++) cnt += s[i + 1 + k];
+        if (tc > 1 || th > 3 || cnt > 256 || i + 17 + cnt > sl) return "bad Huffman table";
+        if (!build_huff(s + i + 1, s + i + 17, cnt, tc ? &f->ac[th] : &f->dc[th])) return "bad Huffman table";
+        i += 17 + cnt;
+      }
+    } else if (m == 0xC0 || m == 0xC1) {
+      if (sl < 6) return "bad frame header";
+      if (s[0] != 8) return "only 8-bit JPEG is decoded on the device";
+      f->height = (s[1] << 8) | s[2];
+      f->width = (s[3] << 8) | s[4];
+      f->nc = s[5];
+      if (f->nc != 1 && f->nc != 3) return "only gray-scale and YCbCr JPEG (1 or 3 components) are decoded on the device";
+      if (sl < (size_t)6 + 3 * f->nc || f->width < 1 || f->height < 1) return "bad frame header";
+      for (int c = 0; c < f->nc; c++) {
+        Comp& k = f->comp[c];
+        k.id = s[6 + 3 * c];
+        k.h = s[7 + 3 * c] >> 4;
+        k.v = s[7 + 3 * c] & 15;
+        k.tq = s[8 + 3 * c];
+        if (k.tq > 3 || k.h < 1 || k.v < 1 || k.h > 2 || k.v > 2) return "sampling factors beyond 2 are not decoded on the device";
+      }
+      have_sof = true;
+      if (header_only) return nullptr;
+    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      return "only baseline (SOF0/SOF1, Huffman, sequential) JPEG is decoded on the device";
+    } else if (m == 0xDD) {
+      if (sl < 2) return "bad restart interval";
+      f->dri = (s[0] << 8) | s[1];
+    } else if (m == 0xDA) {
+      if (!have_sof) return "scan before the frame header";
+      if (sl < 1 || s[0] != f->nc || sl < (size_t)1 + 2 * f->nc + 3) return "non-interleaved scans are not decoded on the device";
+      for (int c = 0; c < f->nc; c++) {
+        Comp* k = nullptr;
+        for (int j = 0; j < f->nc; j++)
+          if (f->comp[j].id == s[1 + 2 * c]) k = &f->comp[j];
+        if (!k || k != &f->comp[c]) return "scan component order differs from the frame header";
+        k->td = s[2 + 2 * c] >> 4;
+        k->ta = s[2 + 2 * c] & 15;
+        if (k->td > 3 || k->ta > 3 || !f->dc[k->td].present || !f->ac[k->ta].present || !f->qt_present[k->tq])
+          return "scan refers to a missing table";
+      }
+      f->data = b + pos + len;
+      f->n_data = n - (pos + len);
+      break;
+    }
+    pos += len;
+  }
+  if (f->nc == 1) f->comp[0].h = f->comp[0].v = 1;       // a one-component scan is never interleaved
+  f->hmax = f->vmax = 1;
+  for (int c = 0; c < f->nc; c++) { f->hmax = std::max(f->hmax, f->comp[c].h); f->vmax = std::max(f->vmax, f->comp[c].v); }
+  if (f->nc == 3) {
+    // luma at full resolution, both chroma planes with the same factors: 4:4:4, 4:2:2, 4:2:0, 4:4:0
+    if (f->comp[0].h != f->hmax || f->comp[0].v != f->vmax || f->comp[1].h != f->comp[2].h || f->comp[1].v != f->comp[2].v ||
+        f->comp[1].h != 1 || f->comp[1].v != 1)
+      return "chroma sampling other than 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 is not decoded on the device";
+    if (f->hmax == 2 && (f->width + 1) / 2 <= 2) return "frame too narrow";   // (the library switches to box up-sampling there)
+  }
+  f->mcux = (f->width + 8 * f->hmax - 1) / (8 * f->hmax);
+  f->mcuy = (f->height + 8 * f->vmax - 1) / (8 * f->vmax);
+  size_t off = 0;
+  for (int c = 0; c < f->nc; c++) {
+    Comp& k = f->comp[c];
+    k.blocks_x = f->mcux * k.h;
+    k.blocks_y = f->mcuy * k.v;
+    k.dw = (f->width * k.h + f->hmax - 1) / f->hmax;
+    k.dh = (f->height * k.v + f->vmax - 1) / f->vmax;
+    k.coef_off = off;
+    off += (size_t)k.blocks_x * k.blocks_y * 64;
+  }
+  f->n_coef = off;
+  return nullptr;
+}
+
+// MSB-first bit reader over the entropy-coded segment: FF00 -> FF, any other marker ends the data (zeros are fed, as
+// libjpeg does, so a truncated stream decodes to grey rather than failing).
+struct BitReader {
+  const uint8_t* p;
+  const uint8_t* end;
+  uint64_t acc = 0;
+  int n = 0;
+  bool marker = false;
+  inline void fill() {
+    while (n <= 56) {
+      uint64_t v = 0;
+      if (!marker && p < end) {
+        v = *p;
+        if (v == 0xFF) {
+          if (p + 1 < end && p[1] == 0) p += 2;
+          else { marker = true; v = 0; }
+        } else {
+          p++;
+        }
+      }
+      acc |= v << (56 - n);
+      n += 8;
+    }
+  }
+  inline uint32_t peek(int k) const { return (uint32_t)(acc >> (64 - k)); }
+  inline void skip(int k) { acc <<= k; n -= k; }
+  // restart marker: drop the partial byte, move behind the next RSTn
+  void restart() {
+    acc = 0; n = 0;
+    if (!marker) {   // the reader may not have run into the marker yet
+      while (p + 1 < end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) p++;
+    }
+    if (p + 1 < end && p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7) { p += 2; marker = false; }
+  }
+};
+
+inline int huff_decode(BitReader& br, const HuffTab& t) {
+  const uint32_t e = t.look[br.peek(HuffTab::kLook)];
+  if (e) { br.skip(e >> 8); return e & 255; }
+  int len = HuffTab::kLook + 1;
+  int32_t code = (int32_t)br.peek(len);
+  while (len <= 16 && code > t.maxcode[len]) { len++; code = (int32_t)br.peek(len); }
+  if (len > 16) { br.skip(16); return 0; }          // corrupt code: libjpeg warns and returns 0
+  br.skip(len);
+  return t.vals[(code + t.valoff[len]) & 255];
+}
+
+inline int extend(uint32_t v, int s) { return (int)v - ((v >> (s - 1)) ? 0 : (1 << s) - 1); }
+
+// All MCUs of the scan into `coef` (zeroed by the caller): component planes of blocks, 64 int16 each in natural order.
+void decode_scan(const Frame& f, int16_t* coef) {
+  BitReader br{f.data, f.data + f.n_data};
+  int pred[kMaxComp] = {0, 0, 0};
+  int until_restart = f.dri;
+  for (int my = 0; my < f.mcuy; my++)
+    for (int mx = 0; mx < f.mcux; mx++) {
+      if (f.dri) {
+        if (until_restart == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; until_restart = f.dri; }
+        until_restart--;
+      }
+      for (int c = 0; c < f.nc; c++) {
+        const Comp& k = f.comp[c];
+        const HuffTab& dct = f.dc[k.td];
+        const HuffTab& act = f.ac[k.ta];
+        for (int by = 0; by < k.v; by++)
+          for (int bx = 0; bx < k.h; bx++) {
+            int16_t* blk = coef + k.coef_off + ((size_t)(my * k.v + by) * k.blocks_x + (mx * k.h + bx)) * 64;
+            br.fill();
+            int s = huff_decode(br, dct) & 15;
+            if (s) { br.fill(); pred[c] += extend(br.peek(s), s); br.skip(s); }
+            blk[0] = (int16_t)pred[c];
+            for (int i = 1; i < 64;) {
+              br.fill();                                 // >= 57 bits: a code (<= 16) and its value bits (<= 15), twice
+              int rs = huff_decode(br, act);
+              int r = rs >> 4;
+              s = rs & 15;
+              if (s == 0) {
+                if (r != 15) break;
+                i += 16;
+                continue;
+              }
+              i += r;
+              blk[kZigzag[std::min(i, 79)]] = (int16_t)extend(br.peek(s), s);
+              br.skip(s);
+              i++;
+            }
+          }
+      }
+    }
+}
+
+// ---- device ----
+struct IdctPlane {
+  const int16_t* coef;     // [blocks][64]
+  uint8_t* plane;          // [blocks_y * 8][pitch]
+  int blocks_x, n_blocks;
+  size_t pitch;
+  int first_block;         // index of the component's first block in the launch
+  uint16_t q[64];
+};
+struct IdctArgs {
+  IdctPlane p[kMaxComp];
+  int nc, total_blocks;
+};
+
+// jidctint.c constants (CONST_BITS = 13)
+#define J_0_298 2446
+#define J_0_390 3196
+#define J_0_541 4433
+#define J_0_765 6270
+#define J_0_899 7373
+#define J_1_175 9633
+#define J_1_501 12299
+#define J_1_847 15137
+#define J_1_961 16069
+#define J_2_053 16819
+#define J_2_562 20995
+#define J_3_072 25172
+
+template <int SHIFT>
+__device__ __forceinline__ void idct8(const int (&x)[8], int (&o)[8]) {
+  int z1 = (x[2] + x[6]) * J_0_541;
+  const int tmp2 = z1 - x[6] * J_1_847, tmp3 = z1 + x[2] * J_0_765;
+  const int tmp0 = (x[0] + x[4]) << 13, tmp1 = (x[0] - x[4]) << 13;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  int t0 = x[7], t1 = x[5], t2 = x[3], t3 = x[1];
+  z1 = t0 + t3;
+  int z2 = t1 + t2, z3 = t0 + t2, z4 = t1 + t3;
+  const int z5 = (z3 + z4) * J_1_175;
+  t0 *= J_0_298; t1 *= J_2_053; t2 *= J_3_072; t3 *= J_1_501;
+  z1 *= -J_0_899; z2 *= -J_2_562;
+  z3 = z3 * -J_1_961 + z5;
+  z4 = z4 * -J_0_390 + z5;
+  t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
+  constexpr int R = 1 << (SHIFT - 1);
+  o[0] = (tmp10 + t3 + R) >> SHIFT; o[7] = (tmp10 - t3 + R) >> SHIFT;
+  o[1] = (tmp11 + t2 + R) >> SHIFT; o[6] = (tmp11 - t2 + R) >> SHIFT;
+  o[2] = (tmp12 + t1 + R) >> SHIFT; o[5] = (tmp12 - t1 + R) >> SHIFT;
+  o[3] = (tmp13 + t0 + R) >> SHIFT; o[4] = (tmp13 - t0 + R) >> SHIFT;
+}
+
+// 256 threads = 32 blocks; thread (b, t): column t of block b in pass 1, row t in pass 2.
+__global__ void __launch_bounds__(256) k_jpeg_idct(const __grid_constant__ IdctArgs a) {
+  __shared__ int ws[32][8][9];
+  const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
+  const int gb = blockIdx.x * 32 + lb;
+  const bool live = gb < a.total_blocks;
+  int c = 0;
+  if (live) {
+    if (a.nc > 1 && gb >= a.p[1].first_block) c = 1;
+    if (a.nc > 2 && gb >= a.p[2].first_block) c = 2;
+  }
+  const IdctPlane& P = a.p[c];
+  const int b = gb - P.first_block;
+  if (live) {
+    const int16_t* cf = P.coef + (size_t)b * 64;
+    int x[8], o[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = (int)(int16_t)((int)cf[r * 8 + t] * (int)P.q[r * 8 + t]);   // 16-bit product, as the library's vector code
+    idct8<11>(x, o);
+#pragma unroll
+    for (int r = 0; r < 8; r++) ws[lb][r][t] = min(max(o[r], -32768), 32767);
+  }
+  __syncwarp();
+  if (live) {
+    int x[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = ws[lb][t][k];
+    idct8<18>(x, o);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      lo |= (uint32_t)(min(max(o[k], -128), 127) + 128) << (8 * k);
+      hi |= (uint32_t)(min(max(o[k + 4], -128), 127) + 128) << (8 * k);
+    }
+    const int by = b / P.blocks_x, bx = b - by * P.blocks_x;
+    *reinterpret_cast<uint2*>(P.plane + (size_t)(by * 8 + t) * P.pitch + (size_t)bx * 8) = make_uint2(lo, hi);
+  }
+}
+
+struct ColorArgs {
+  const uint8_t *Y, *Cb, *Cr;
+  size_t y_pitch, c_pitch;
+  int w, h, cw, ch;        // frame size; real chroma samples
+  int fh, fv;              // chroma up-sampling factors (1 or 2)
+  int gray_only_source;    // 1: one-component JPEG (B = G = R = Y)
+  uint8_t* bgr;            // may be NULL
+  size_t bgr_pitch;
+  uint8_t* gray;           // may be NULL
+  size_t gray_pitch;
+};
+
+__device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ C, size_t pitch, int x, int y, int cw, int ch, int fh, int fv) {
+  if (fh == 1 && fv == 1) return C[(size_t)y * pitch + x];
+  if (fv == 1) {                                         // h2v1_fancy_upsample
+    const int cx = x >> 1;
+    const uint8_t* r = C + (size_t)y * pitch;
+    const int cur = r[cx];
+    if (x & 1) return cx == cw - 1 ? cur : (3 * cur + r[cx + 1] + 2) >> 2;
+    return cx == 0 ? cur : (3 * cur + r[cx - 1] + 1) >> 2;
+  }
+  const int cy = y >> 1;
+  const int oy = (y & 1) ? min(cy + 1, ch - 1) : max(cy - 1, 0);
+  const uint8_t* r0 = C + (size_t)cy * pitch;
+  const uint8_t* r1 = C + (size_t)oy * pitch;
+  if (fh == 1) return (3 * r0[x] + r1[x] + ((y & 1) ? 2 : 1)) >> 2;   // h1v2_fancy_upsample
+  const int cx = x >> 1;                                 // h2v2_fancy_upsample
+  const int cs = 3 * r0[cx] + r1[cx];
+  if (x & 1) return cx == cw - 1 ? (4 * cs + 7) >> 4 : (3 * cs + 3 * r0[cx + 1] + r1[cx + 1] + 7) >> 4;
+  return cx == 0 ? (4 * cs + 8) >> 4 : (3 * cs + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
+}
+
+// One thread = 4 consecutive pixels of a row: 12 bytes of BGR (three 32-bit stores on a 4-byte-aligned row) and 4 of gray.
+__global__ void __launch_bounds__(256) k_jpeg_color(const __grid_constant__ ColorArgs a) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  if (x4 >= a.w) return;
+  const int n = min(4, a.w - x4);
+  uint8_t px[12], g[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int x = min(x4 + j, a.w - 1);
+    const int yy = a.Y[(size_t)y * a.y_pitch + x];
+    int b = yy, gg = yy, r = yy;
+    if (!a.gray_only_source) {
+      const int cb = chroma_at(a.Cb, a.c_pitch, x, y, a.cw, a.ch, a.fh, a.fv) - 128;
+      const int cr = chroma_at(a.Cr, a.c_pitch, x, y, a.cw, a.ch, a.fh, a.fv) - 128;
+      r = min(max(yy + ((91881 * cr + 32768) >> 16), 0), 255);
+      b = min(max(yy + ((116130 * cb + 32768) >> 16), 0), 255);
+      gg = min(max(yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16), 0), 255);
+    }
+    px[3 * j] = (uint8_t)b; px[3 * j + 1] = (uint8_t)gg; px[3 * j + 2] = (uint8_t)r;
+    g[j] = (uint8_t)((b * 3735 + gg * 19235 + r * 9798 + 16384) >> 15);
+  }
+  if (a.bgr) {
+    uint8_t* d = a.bgr + (size_t)y * a.bgr_pitch + (size_t)x4 * 3;
+    if (n == 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+      d32[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+      d32[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+      d32[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+    } else {
+      for (int i = 0; i < 3 * n; i++) d[i] = px[i];
+    }
+  }
+  if (a.gray) {
+    uint8_t* d = a.gray + (size_t)y * a.gray_pitch + x4;
+    if (n == 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) *reinterpret_cast<uint32_t*>(d) = g[0] | (g[1] << 8) | (g[2] << 16) | ((uint32_t)g[3] << 24);
+    else for (int j = 0; j < n; j++) d[j] = g[j];
+  }
+}
+
+struct JpegState {
+  int16_t* h_coef = nullptr;    // pinned
+  int16_t* d_coef = nullptr;
+  uint8_t* d_planes = nullptr;
+  size_t coef_cap = 0, plane_cap = 0;
+};
+
+}  // namespace
+
+void jpeg_destroy(ofb_handle* h) {
+  JpegState* s = static_cast<JpegState*>(h->jpeg);
+  if (!s) return;
+  if (s->h_coef) cudaFreeHost(s->h_coef);
+  if (s->d_coef) cudaFree(s->d_coef);
+  if (s->d_planes) cudaFree(s->d_planes);
+  delete s;
+  h->jpeg = nullptr;
+}
+
+// Decodes `jpeg` into device frames on the handle's stream: d_bgr ([height][width][3], pitch bgr_pitch) and/or d_gray.
+// Returns after the launches are enqueued; the pinned coefficient staging is reused by the next call, which
+// synchronises first.
+static int jpeg_decode_device(ofb_handle* h, const Frame& f, uint8_t* d_bgr, size_t bgr_pitch, uint8_t* d_gray, size_t gray_pitch) {
+  if (!h->jpeg) h->jpeg = new JpegState();
+  JpegState* s = static_cast<JpegState*>(h->jpeg);
+  cudaStream_t sm = h->stream;
+  size_t plane_bytes = 0, plane_off[kMaxComp], pitch[kMaxComp];
+  for (int c = 0; c < f.nc; c++) {
+    pitch[c] = ((size_t)f.comp[c].blocks_x * 8 + 15) & ~(size_t)15;
+    plane_off[c] = plane_bytes;
+    plane_bytes += pitch[c] * f.comp[c].blocks_y * 8;
+  }
+  OFB_CUDA(h, cudaStreamSynchronize(sm));                 // the previous frame's coefficients may still be in flight
+  if (f.n_coef > s->coef_cap) {
+    if (s->h_coef) cudaFreeHost(s->h_coef);
+    if (s->d_coef) cudaFree(s->d_coef);
+    s->h_coef = nullptr; s->d_coef = nullptr; s->coef_cap = 0;
+    OFB_CUDA(h, cudaHostAlloc(&s->h_coef, f.n_coef * sizeof(int16_t), cudaHostAllocDefault));
+    OFB_CUDA(h, cudaMalloc(&s->d_coef, f.n_coef * sizeof(int16_t)));
+    s->coef_cap = f.n_coef;
+  }
+  if (plane_bytes > s->plane_cap) {
+    if (s->d_planes) cudaFree(s->d_planes);
+    s->d_planes = nullptr; s->plane_cap = 0;
+    OFB_CUDA(h, cudaMalloc(&s->d_planes, plane_bytes));
+    s->plane_cap = plane_bytes;
+  }
+  memset(s->h_coef, 0, f.n_coef * sizeof(int16_t));
+  decode_scan(f, s->h_coef);
+  OFB_CUDA(h, cudaMemcpyAsync(s->d_coef, s->h_coef, f.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, sm));
+  IdctArgs ia = {};
+  ia.nc = f.nc;
+  int first = 0;
+  for (int c = 0; c < f.nc; c++) {
+    const Comp& k = f.comp[c];
+    IdctPlane& P = ia.p[c];
+    P.coef = s->d_coef + k.coef_off;
+    P.plane = s->d_planes + plane_off[c];
+    P.blocks_x = k.blocks_x;
+    P.n_blocks = k.blocks_x * k.blocks_y;
+    P.pitch = pitch[c];
+    P.first_block = first;
+    memcpy(P.q, f.qt[k.tq], sizeof(P.q));
+    first += P.n_blocks;
+  }
+  ia.total_blocks = first;
+  int st;
+  if ((st = timing_begin(h, OFB_STAGE_OTHER))) return st;
+  k_jpeg_idct<<<(first + 31) / 32, 256, 0, sm>>>(ia);
+  OFB_LAUNCH_CHECK(h);
+  ColorArgs ca = {};
+  ca.Y = s->d_planes + plane_off[0];
+  ca.y_pitch = pitch[0];
+  ca.w = f.width; ca.h = f.height;
+  ca.gray_only_source = f.nc == 1;
+  if (f.nc == 3) {
+    ca.Cb = s->d_planes + plane_off[1];
+    ca.Cr = s->d_planes + plane_off[2];
+    ca.c_pitch = pitch[1];
+    ca.cw = f.comp[1].dw; ca.ch = f.comp[1].dh;
+    ca.fh = f.hmax / f.comp[1].h; ca.fv = f.vmax / f.comp[1].v;
+  }
+  ca.bgr = d_bgr; ca.bgr_pitch = bgr_pitch;
+  ca.gray = d_gray; ca.gray_pitch = gray_pitch;
+  k_jpeg_color<<<dim3(((f.width + 3) / 4 + 255) / 256, f.height), 256, 0, sm>>>(ca);
+  OFB_LAUNCH_CHECK(h);
+  if ((st = timing_end(h))) return st;
+  return OFB_OK;
+}
+
+}  // namespace ofb
+
+using namespace ofb;
+
+extern "C" {
+
+int ofb_jpeg_info(const uint8_t* jpeg, size_t n_bytes, int* width, int* height, int* components) {
+  if (!jpeg) return OFB_ERR_INVALID_ARG;
+  Frame* f = new Frame();
+  const char* why = parse_jpeg(jpeg, n_bytes, f, true);
+  if (!why) {
+    if (width) *width = f->width;
+    if (height) *height = f->height;
+    if (components) *components = f->nc;
+  }
+  delete f;
+  return why ? OFB_ERR_UNSUPPORTED : OFB_OK;
+}
+
+int ofb_jpeg_entropy_decode(const uint8_t* jpeg, size_t n_bytes, int16_t* coef, size_t coef_capacity, size_t* n_coef) {
+  if (!jpeg) return OFB_ERR_INVALID_ARG;
+  Frame* f = new Frame();
+  const char* why = parse_jpeg(jpeg, n_bytes, f, false);
+  int st = why ? OFB_ERR_UNSUPPORTED : OFB_OK;
+  if (!st) {
+    if (n_coef) *n_coef = f->n_coef;
+    if (coef) {
+      if (coef_capacity < f->n_coef) st = OFB_ERR_CAPACITY;
+      else { memset(coef, 0, f->n_coef * sizeof(int16_t)); decode_scan(*f, coef); }
+    }
+  }
+  delete f;
+  return st;
+}
+
+int ofb_jpeg_decode(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* bgr, size_t bgr_stride_bytes, uint8_t* gray,
+                    size_t gray_stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!jpeg || (!bgr && !gray)) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  Frame* fp = new Frame();
+  const char* why = parse_jpeg(jpeg, n_bytes, fp, false);
+  if (why) { delete fp; return set_error(h, OFB_ERR_UNSUPPORTED, "JPEG: %s", why); }
+  const Frame& f = *fp;
+  const size_t row3 = (size_t)f.width * 3, gpitch = ((size_t)f.width + 15) & ~(size_t)15;
+  if (bgr_stride_bytes == 0) bgr_stride_bytes = row3;
+  if (gray_stride_bytes == 0) gray_stride_bytes = (size_t)f.width;
+  int st = OFB_OK;
+  if ((bgr && bgr_stride_bytes < row3) || (gray && gray_stride_bytes < (size_t)f.width))
+    st = set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row");
+  if (!st && cudaSetDevice(h->device) != cudaSuccess) st = set_error(h, OFB_ERR_CUDA, "cudaSetDevice failed");
+  if (!st) st = ingest_reserve(h, bgr ? row3 * f.height : 0, gray ? gpitch * f.height : 0);
+  ofb_handle::Ingest& g = h->ingest;
+  if (!st) st = jpeg_decode_device(h, f, bgr ? g.d_a : nullptr, row3, gray ? g.d_b : nullptr, gpitch);
+  const int w = f.width, hh = f.height;
+  delete fp;
+  if (st) return st;
+  if (bgr) OFB_CUDA(h, cudaMemcpy2DAsync(bgr, bgr_stride_bytes, g.d_a, row3, row3, hh, cudaMemcpyDeviceToHost, h->stream));
+  if (gray) OFB_CUDA(h, cudaMemcpy2DAsync(gray, gray_stride_bytes, g.d_b, gpitch, w, hh, cudaMemcpyDeviceToHost, h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+int ofb_ingest_jpeg_gray(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* dst, int dst_width, int dst_height,
+                         size_t dst_stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!jpeg || !dst) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  if (dst_width < 1 || dst_height < 1) return set_error(h, OFB_ERR_INVALID_ARG, "bad size");
+  if (dst_stride_bytes == 0) dst_stride_bytes = (size_t)dst_width;
+  if (dst_stride_bytes < (size_t)dst_width) return set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row");
+  Frame* fp = new Frame();
+  const char* why = parse_jpeg(jpeg, n_bytes, fp, false);
+  if (why) { delete fp; return set_error(h, OFB_ERR_UNSUPPORTED, "JPEG: %s", why); }
+  const Frame& f = *fp;
+  const bool same = f.width == dst_width && f.height == dst_height;
+  const size_t srow = (size_t)f.width * 3, drow = (size_t)dst_width * 3, gpitch = ((size_t)dst_width + 15) & ~(size_t)15;
+  int st = OFB_OK;
+  if (cudaSetDevice(h->device) != cudaSuccess) st = set_error(h, OFB_ERR_CUDA, "cudaSetDevice failed");
+  if (!st) st = ingest_reserve(h, same ? 0 : srow * f.height, (same ? 0 : drow * dst_height) + gpitch * dst_height);
+  ofb_handle::Ingest& g = h->ingest;
+  uint8_t* gray = g.d_b;
+  if (!st) {
+    if (same) {
+      st = jpeg_decode_device(h, f, nullptr, 0, gray, gpitch);         // gray straight out of the colour kernel
+    } else {
+      // the nodes resize the colour frame first (lfn3_sub_node.py:152-153), then convert
+      st = jpeg_decode_device(h, f, g.d_a, srow, nullptr, 0);
+      uint8_t* small = g.d_b + gpitch * dst_height;
+      if (!st) st = resize_u8_device(h, g.d_a, srow, f.width, f.height, 3, small, drow, dst_width, dst_height);
+      if (!st) st = cvt_gray_device(h, small, drow, gray, gpitch, dst_width, dst_height, 0);
+    }
+  }
+  delete fp;
+  if (st) return st;
+  OFB_CUDA(h, cudaMemcpy2DAsync(dst, dst_stride_bytes, gray, gpitch, dst_width, dst_height, cudaMemcpyDeviceToHost, h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+}  // extern "C"

@@ -396,6 +396,47 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out
 
+    @staticmethod
+    def _jpeg_bytes(buf):
+        buf = np.ascontiguousarray(np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray, memoryview)) else
+                                   np.asarray(buf, np.uint8).reshape(-1))
+        return buf
+
+    def jpeg_info(self, buf):
+        """(width, height, components) of a baseline JPEG stream (header parse on the host, no device work)."""
+        buf = self._jpeg_bytes(buf)
+        w, h, c = C.c_int(), C.c_int(), C.c_int()
+        st = self._lib.ofb_jpeg_info(buf.ctypes.data, buf.size, C.byref(w), C.byref(h), C.byref(c))
+        if st:
+            raise OfbError(st, "not a baseline JPEG stream the device path decodes")
+        return w.value, h.value, c.value
+
+    def imdecode(self, buf, gray: bool = False) -> np.ndarray:
+        """``cv2.imdecode(buf, cv2.IMREAD_COLOR)`` of a baseline JPEG (``sensor_msgs/CompressedImage.data``; the
+        compressed-image node, opticalflow_comprerssed_node.py:43-46): uint8 [H,W,3] BGR, bit-exact with the wheel's
+        libjpeg-turbo.  ``gray=True``: ``cv2.cvtColor(that, COLOR_BGR2GRAY)`` instead, uint8 [H,W] (a third of the bytes
+        back over PCIe).  Raises ``OfbError`` (status 6) for streams the device path does not decode."""
+        buf = self._jpeg_bytes(buf)
+        w, h, _ = self.jpeg_info(buf)
+        out = np.empty((h, w) if gray else (h, w, 3), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_jpeg_decode(self._h, buf.ctypes.data, buf.size, None if gray else out.ctypes.data, 0,
+                                           out.ctypes.data if gray else None, 0)
+            _lib.check(st, self._h)
+        return out
+
+    def ingest_jpeg_gray(self, buf, size=None) -> np.ndarray:
+        """``ingest_gray`` for a compressed frame: decode → ``cv2.resize`` of the colour frame to ``size`` = (width, height)
+        if it has another size → ``cv2.cvtColor(..., COLOR_BGR2GRAY)``; the uint8 [H,W] frame the flow calls take."""
+        buf = self._jpeg_bytes(buf)
+        w, h, _ = self.jpeg_info(buf)
+        dw, dh = (w, h) if size is None else (int(size[0]), int(size[1]))
+        out = np.empty((dh, dw), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_ingest_jpeg_gray(self._h, buf.ctypes.data, buf.size, out.ctypes.data, dw, dh, 0)
+            _lib.check(st, self._h)
+        return out
+
     def clahe(self, image, clipLimit: float = 40.0, tileGridSize=(8, 8)) -> np.ndarray:
         """``cv2.createCLAHE(clipLimit, tileGridSize).apply(image)`` of a uint8 [H,W] image on the device, bit-exact with
         cv2 (the adapt node's pre-filter, lfn3_adapt_node.py:164-182)."""

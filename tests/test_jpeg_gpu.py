@@ -1,0 +1,71 @@
+"""JPEG frame ingest on the device (ofb_jpeg_decode / ofb_ingest_jpeg_gray) against ``cv2.imdecode`` of the wheel:
+bit-exact BGR, gray and resized-gray frames.  Anchor: opticalflow_comprerssed_node.py:43-46."""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+from test_oracle_jpeg import encode, jpeg_frame  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("size,sampling,quality,rst", [
+    ((48, 64), "420", 95, 0), ((37, 53), "420", 50, 3), ((37, 53), "422", 90, 0), ((16, 16), "444", 10, 0),
+    ((9, 21), "440", 75, 2), ((481, 637), "420", 85, 0), ((1080, 1920), "420", 90, 0), ((1080, 1920), "422", 60, 16),
+    ((539, 959), "444", 97, 0)])
+def test_imdecode_equals_cv2(engine_factory, size, sampling, quality, rst):
+    h, w = size
+    buf = encode(jpeg_frame(h, w, quality), sampling, quality, rst)
+    ref = cv2.imdecode(buf, cv2.IMREAD_COLOR)
+    eng = engine_factory(64, 64)
+    assert eng.jpeg_info(buf) == (w, h, 3)
+    got = eng.imdecode(buf)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert np.array_equal(eng.imdecode(buf.tobytes(), gray=True), cv2.cvtColor(ref, cv2.COLOR_BGR2GRAY))
+
+
+def test_gray_jpeg_and_repeated_calls(engine_factory):
+    eng = engine_factory(64, 64)
+    for seed, (h, w) in enumerate([(40, 56), (200, 312), (33, 35)]):      # staging grows and is reused
+        buf = encode(jpeg_frame(h, w, seed, channels=1), quality=80)
+        assert np.array_equal(eng.imdecode(buf), cv2.imdecode(buf, cv2.IMREAD_COLOR))
+    buf = encode(jpeg_frame(64, 64, 9), "420", 70)
+    assert np.array_equal(eng.imdecode(buf), cv2.imdecode(buf, cv2.IMREAD_COLOR))
+
+
+@pytest.mark.parametrize("size,dst", [((480, 640), None), ((1080, 1920), (640, 480)), ((300, 400), (512, 384))])
+def test_ingest_jpeg_gray_equals_node_chain(engine_factory, size, dst):
+    """decode -> resize (colour frame, if the size differs) -> gray, as lfn3_sub_node.py:148-159 does after imdecode."""
+    buf = encode(jpeg_frame(size[0], size[1], 4), "420", 88)
+    ref = cv2.imdecode(buf, cv2.IMREAD_COLOR)
+    if dst is not None:
+        ref = cv2.resize(ref, dst)
+    ref = cv2.cvtColor(ref, cv2.COLOR_BGR2GRAY)
+    eng = engine_factory(64, 64)
+    assert np.array_equal(eng.ingest_jpeg_gray(buf, dst), ref)
+
+
+def test_decoded_frames_feed_the_flow_call(engine_factory):
+    """Two JPEG frames -> gray on the device -> Farneback: same field as cv2 on cv2-decoded frames."""
+    from oracle import synth
+    a, b = synth.synth_pair(240, 320, 2, (2.5, -1.25))
+    ja, jb = (cv2.imencode(".jpg", cv2.cvtColor(x, cv2.COLOR_GRAY2BGR), [cv2.IMWRITE_JPEG_QUALITY, 92])[1] for x in (a, b))
+    eng = engine_factory(320, 240)
+    ga, gb = eng.ingest_jpeg_gray(ja), eng.ingest_jpeg_gray(jb)
+    ra, rb = (cv2.cvtColor(cv2.imdecode(j, cv2.IMREAD_COLOR), cv2.COLOR_BGR2GRAY) for j in (ja, jb))
+    assert np.array_equal(ga, ra) and np.array_equal(gb, rb)
+    got = eng.farneback(ga, gb, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    ref = cv2.calcOpticalFlowFarneback(ra, rb, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    epe = np.sqrt(((got - ref) ** 2).sum(-1))
+    assert epe.mean() <= 0.01 and epe.max() <= 0.1
+
+
+def test_unsupported_streams_fail_loudly(engine_factory):
+    from opticalflowcontainer_b200 import OfbError
+    eng = engine_factory(64, 64)
+    ok, prog = cv2.imencode(".jpg", jpeg_frame(32, 32, 1), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(OfbError) as e:
+        eng.imdecode(prog)
+    assert e.value.status == 6
+    with pytest.raises(OfbError):
+        eng.imdecode(b"\xff\xd8\xff\xd9")
