@@ -12,6 +12,7 @@
 //                 conversion the nodes apply next (cv2.cvtColor BGR2GRAY, 15-bit fixed point).
 // The decoded frame never exists on the host unless the caller asks for it.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -187,41 +188,56 @@ const char* parse_jpeg(const uint8_t* b, size_t n, Frame* f, bool header_only) {
   return nullptr;
 }
 
-// MSB-first bit reader over the entropy-coded segment: FF00 -> FF, any other marker ends the data (zeros are fed, as
-// libjpeg does, so a truncated stream decodes to grey rather than failing).
+// The entropy-coded segment with the byte stuffing removed (FF00 -> FF) so that the bit reader loads whole words:
+// restart markers are dropped and their byte positions recorded, any other marker ends the data, and zeros follow it
+// (libjpeg feeds zeros past the end too: a truncated stream decodes to grey instead of failing).
+struct Unstuffed {
+  std::vector<uint8_t> buf;
+  std::vector<size_t> rst;       // byte offset (in buf) of the data behind the i-th restart marker
+};
+
+void unstuff(const uint8_t* p, size_t n, Unstuffed* u) {
+  u->buf.resize(n + 64);
+  u->rst.clear();
+  uint8_t* o = u->buf.data();
+  const uint8_t* end = p + n;
+  while (p < end) {
+    const uint8_t* q = static_cast<const uint8_t*>(memchr(p, 0xFF, end - p));
+    if (!q) q = end;
+    memcpy(o, p, q - p);
+    o += q - p;
+    p = q;
+    if (p >= end) break;
+    if (p + 1 >= end) break;
+    const uint8_t m = p[1];
+    if (m == 0) { *o++ = 0xFF; p += 2; }
+    else if (m >= 0xD0 && m <= 0xD7) { u->rst.push_back((size_t)(o - u->buf.data())); p += 2; }
+    else if (m == 0xFF) { p++; }                         // fill byte
+    else break;                                          // EOI or another marker
+  }
+  const size_t used = o - u->buf.data();
+  memset(o, 0, u->buf.size() - used);
+  u->buf.resize(used + 64);                              // (no reallocation: shrinking)
+}
+
 struct BitReader {
   const uint8_t* p;
-  const uint8_t* end;
+  const uint8_t* end;            // 32 readable bytes before the end of the padded buffer
   uint64_t acc = 0;
   int n = 0;
-  bool marker = false;
-  inline void fill() {
-    while (n <= 56) {
-      uint64_t v = 0;
-      if (!marker && p < end) {
-        v = *p;
-        if (v == 0xFF) {
-          if (p + 1 < end && p[1] == 0) p += 2;
-          else { marker = true; v = 0; }
-        } else {
-          p++;
-        }
-      }
-      acc |= v << (56 - n);
-      n += 8;
+  inline void fill() {           // >= 32 valid bits afterwards
+    if (n < 32) {
+      uint32_t v = 0;
+      if (p < end) { memcpy(&v, p, 4); p += 4; }
+      acc |= (uint64_t)__builtin_bswap32(v) << (32 - n);
+      n += 32;
     }
   }
   inline uint32_t peek(int k) const { return (uint32_t)(acc >> (64 - k)); }
   inline void skip(int k) { acc <<= k; n -= k; }
-  // restart marker: drop the partial byte, move behind the next RSTn
-  void restart() {
-    acc = 0; n = 0;
-    if (!marker) {   // the reader may not have run into the marker yet
-      while (p + 1 < end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) p++;
-    }
-    if (p + 1 < end && p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7) { p += 2; marker = false; }
-  }
 };
+
+inline int extend(uint32_t v, int s) { return (int)v - ((v >> (s - 1)) ? 0 : (1 << s) - 1); }
 
 inline int huff_decode(BitReader& br, const HuffTab& t) {
   const uint32_t e = t.look[br.peek(HuffTab::kLook)];
@@ -234,23 +250,51 @@ inline int huff_decode(BitReader& br, const HuffTab& t) {
   return t.vals[(code + t.valoff[len]) & 255];
 }
 
-inline int extend(uint32_t v, int s) { return (int)v - ((v >> (s - 1)) ? 0 : (1 << s) - 1); }
+// AC look-ahead with the value bits folded in: for the next kLook bits, entry = value << 16 | run << 8 | bits consumed
+// when the code AND its value bits fit (the common case: short codes of small coefficients); 0 otherwise.
+struct AcFast { int32_t e[1 << HuffTab::kLook]; };
+
+void build_ac_fast(const HuffTab& t, AcFast* f) {
+  for (int i = 0; i < (1 << HuffTab::kLook); i++) {
+    f->e[i] = 0;
+    const uint32_t e = t.look[i];
+    if (!e) continue;
+    const int len = e >> 8, rs = e & 255, r = rs >> 4, s = rs & 15;
+    if (s == 0 || len + s > HuffTab::kLook) continue;
+    const uint32_t bits = ((uint32_t)i >> (HuffTab::kLook - len - s)) & ((1u << s) - 1);
+    f->e[i] = (int32_t)(((uint32_t)(extend(bits, s) & 0xffff) << 16) | (uint32_t)(r << 8) | (uint32_t)(len + s));
+  }
+}
 
 // All MCUs of the scan into `coef` (zeroed by the caller): component planes of blocks, 64 int16 each in natural order.
 void decode_scan(const Frame& f, int16_t* coef) {
-  BitReader br{f.data, f.data + f.n_data};
+  static thread_local Unstuffed u;
+  unstuff(f.data, f.n_data, &u);
+  static thread_local AcFast fast[4];
+  for (int c = 0; c < f.nc; c++) build_ac_fast(f.ac[f.comp[c].ta], &fast[f.comp[c].ta]);
+  const uint8_t* base = u.buf.data();
+  BitReader br{base, base + u.buf.size() - 32};
   int pred[kMaxComp] = {0, 0, 0};
   int until_restart = f.dri;
+  size_t n_rst = 0;
   for (int my = 0; my < f.mcuy; my++)
     for (int mx = 0; mx < f.mcux; mx++) {
       if (f.dri) {
-        if (until_restart == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; until_restart = f.dri; }
+        if (until_restart == 0) {
+          // behind the next restart marker (a stream that has run out of markers continues in zeros)
+          br.p = n_rst < u.rst.size() ? base + u.rst[n_rst] : br.end;
+          n_rst++;
+          br.acc = 0; br.n = 0;
+          pred[0] = pred[1] = pred[2] = 0;
+          until_restart = f.dri;
+        }
         until_restart--;
       }
       for (int c = 0; c < f.nc; c++) {
         const Comp& k = f.comp[c];
         const HuffTab& dct = f.dc[k.td];
         const HuffTab& act = f.ac[k.ta];
+        const int32_t* fa = fast[k.ta].e;
         for (int by = 0; by < k.v; by++)
           for (int bx = 0; bx < k.h; bx++) {
             int16_t* blk = coef + k.coef_off + ((size_t)(my * k.v + by) * k.blocks_x + (mx * k.h + bx)) * 64;
@@ -259,9 +303,17 @@ void decode_scan(const Frame& f, int16_t* coef) {
             if (s) { br.fill(); pred[c] += extend(br.peek(s), s); br.skip(s); }
             blk[0] = (int16_t)pred[c];
             for (int i = 1; i < 64;) {
-              br.fill();                                 // >= 57 bits: a code (<= 16) and its value bits (<= 15), twice
-              int rs = huff_decode(br, act);
-              int r = rs >> 4;
+              br.fill();                                 // >= 32 bits: a code (<= 16) and its value bits (<= 15)
+              const int32_t e = fa[br.peek(HuffTab::kLook)];
+              if (e) {
+                i += (e >> 8) & 15;
+                br.skip(e & 31);
+                blk[kZigzag[i]] = (int16_t)(e >> 16);   // i <= 78: the table is padded
+                i++;
+                continue;
+              }
+              const int rs = huff_decode(br, act);
+              const int r = rs >> 4;
               s = rs & 15;
               if (s == 0) {
                 if (r != 15) break;
@@ -269,7 +321,7 @@ void decode_scan(const Frame& f, int16_t* coef) {
                 continue;
               }
               i += r;
-              blk[kZigzag[std::min(i, 79)]] = (int16_t)extend(br.peek(s), s);
+              blk[kZigzag[i]] = (int16_t)extend(br.peek(s), s);
               br.skip(s);
               i++;
             }

@@ -46,7 +46,17 @@ def gpu_post():
     return eng.flow_u_stats(1, median=False)
 
 
+jpg = cv2.imencode(".jpg", big, [cv2.IMWRITE_JPEG_QUALITY, 90])[1]
+jpg_vga = cv2.imencode(".jpg", small, [cv2.IMWRITE_JPEG_QUALITY, 90])[1]
+bil = lambda x: cv2.bilateralFilter(x, 9, 75.0, 75.0)
+
 rows = [
+    ("JPEG 1080p q90 (%d kB) -> bgr (imdecode)" % (jpg.size // 1000), lambda: eng.imdecode(jpg), lambda: cv2.imdecode(jpg, cv2.IMREAD_COLOR)),
+    ("JPEG 1080p -> gray (imdecode + cvtColor)", lambda: eng.imdecode(jpg, gray=True), lambda: cv2.cvtColor(cv2.imdecode(jpg, cv2.IMREAD_COLOR), cv2.COLOR_BGR2GRAY)),
+    ("JPEG 1080p -> 640x480 gray (imdecode + resize + cvtColor)", lambda: eng.ingest_jpeg_gray(jpg, (640, 480)), lambda: cv2.cvtColor(cv2.resize(cv2.imdecode(jpg, cv2.IMREAD_COLOR), (640, 480)), cv2.COLOR_BGR2GRAY)),
+    ("JPEG 640x480 q90 (%d kB) -> gray" % (jpg_vga.size // 1000), lambda: eng.ingest_jpeg_gray(jpg_vga), lambda: cv2.cvtColor(cv2.imdecode(jpg_vga, cv2.IMREAD_COLOR), cv2.COLOR_BGR2GRAY)),
+    ("bilateral 640x480 rgb (d 9, 75, 75)", lambda: eng.bilateral_filter(small, 9, 75.0, 75.0), lambda: bil(small)),
+    ("bilateral 1080p rgb (d 9, 75, 75)", lambda: eng.bilateral_filter(big, 9, 75.0, 75.0), lambda: bil(big)),
     ("ingest 1080p bgr8 -> 640x480 gray (resize + cvtColor)", lambda: eng.ingest_gray(big, (640, 480)), lambda: cv2.cvtColor(cv2.resize(big, (640, 480)), cv2.COLOR_BGR2GRAY)),
     ("cvtColor BGR2GRAY 1080p", lambda: eng.ingest_gray(big), lambda: cv2.cvtColor(big, cv2.COLOR_BGR2GRAY)),
     ("resize 1080p bgr -> 640x480", lambda: eng.resize(big, (640, 480)), lambda: cv2.resize(big, (640, 480))),
