@@ -355,6 +355,37 @@ int ofb_adapt_prefilter(ofb_handle* h, const uint8_t* bgr, int width, int height
 int ofb_bilateral_u8c3(ofb_handle* h, const uint8_t* src, int width, int height, size_t src_stride_bytes, int d,
                        double sigma_color, double sigma_space, uint8_t* dst, size_t dst_stride_bytes);
 
+/* ---- junction detector: the reference's own sparse point source --------------------------------------------------
+ * find_junctions_not_rotated(img, grid_area, grid_area_threshold, false, eps) of
+ * ros2_ws/src/junction_point_detector/src/junction_detector.cpp:31-214, optionally preceded by dampenIntensity(img,
+ * dampen_min, dampen_max) (:3-28; the ROS wrapper fishnet_detector_ros.cpp:49-58 calls dampenIntensity(img, -20, 15) and
+ * find_junctions_not_rotated(img, 200, 2.0, false, 6)).  cvtColor -> GaussianBlur 3x3 -> adaptiveThreshold (Gaussian 11, 2)
+ * -> findContours(RETR_TREE) -> contourArea / boundingRect tests -> box corners -> nanoflann radius clusters.  Pixel
+ * stages and contour measurements run on the device, bit-exact with the cv2 4.13.0 wheel; the contours come from two
+ * connected-component labellings instead of border following (same areas, boxes and order as cv2.findContours); the
+ * final ordering of the passing contours and the KD-tree clustering run on the host exactly as nanoflann does them
+ * (approximate search with eps 10 included).  Output: junction centres (x, y) float32, in the reference's order — the
+ * points the junction node tracks (lfn3_junction_node.py:203-231) and a point source for ofb_pyrlk. */
+typedef struct ofb_junction_params {
+  int grid_area;              /* expected cell area in pixels (header default 250; the ROS node passes 200) */
+  float grid_area_threshold;  /* accepted area window: grid_area / (2 t) < area < grid_area * 2 t (default 2) */
+  int eps;                    /* cluster radius in pixels (header default 4; the ROS node passes 6) */
+  int dampen;                 /* 1: dampenIntensity(img, dampen_min, dampen_max) first (3-channel frames only) */
+  double dampen_min, dampen_max;
+} ofb_junction_params;
+/* img: host uint8, 1 channel (gray) or 3 (bgr8).  junctions_xy: capacity x 2 floats, *n_out receives the count.
+ * candidates_xy (may be NULL): the box corners before clustering, candidate_capacity x 2 floats, *n_candidates their
+ * count.  Synchronous.  OFB_ERR_CAPACITY if an output is too small or contours nest deeper than 48 levels. */
+int ofb_find_junctions(ofb_handle* h, const uint8_t* img, int width, int height, size_t stride_bytes, int channels,
+                       const ofb_junction_params* params, float* junctions_xy, int capacity, int* n_out,
+                       float* candidates_xy, int candidate_capacity, int* n_candidates);
+/* The detector's binary image (adaptiveThreshold output, 0 / 255) for inspection and stage-level tests. */
+int ofb_junction_threshold(ofb_handle* h, const uint8_t* img, int width, int height, size_t stride_bytes, int channels,
+                           const ofb_junction_params* params, uint8_t* thresh, size_t thresh_stride_bytes);
+/* The clustering step alone (host only, no handle): candidates -> cluster centres, junction_detector.cpp:123-185. */
+int ofb_cluster_junctions(const float* candidates_xy, int n_candidates, int eps, float* junctions_xy, int capacity,
+                          int* n_out);
+
 /* ---- sparse path: replaces cv2.goodFeaturesToTrack + cv2.calcOpticalFlowPyrLK -- */
 
 /* Shi-Tomasi corners of a uint8 image (host buffer).  corners_xy: capacity

@@ -21,6 +21,11 @@ class OfbError(RuntimeError):
         self.status = status
 
 
+class JunctionParams(C.Structure):
+    _fields_ = [("grid_area", C.c_int), ("grid_area_threshold", C.c_float), ("eps", C.c_int), ("dampen", C.c_int),
+                ("dampen_min", C.c_double), ("dampen_max", C.c_double)]
+
+
 class ClaheParams(C.Structure):
     _fields_ = [("adaptive", C.c_int), ("clip_limit", C.c_double), ("clip_min", C.c_double), ("clip_max", C.c_double),
                 ("c_min", C.c_double), ("c_max", C.c_double), ("tiles_x", C.c_int), ("tiles_y", C.c_int)]
@@ -94,6 +99,11 @@ _SIGNATURES = {
     "ofb_jpeg_entropy_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ofb_jpeg_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "ofb_ingest_jpeg_gray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
+    "ofb_find_junctions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(JunctionParams),
+                                     C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "ofb_junction_threshold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int,
+                                         C.POINTER(JunctionParams), C.c_void_p, C.c_size_t]),
+    "ofb_cluster_junctions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "ofb_launch_count": (C.c_uint64, [C.c_void_p]),
     "ofb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ofb_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

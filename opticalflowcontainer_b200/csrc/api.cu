@@ -168,6 +168,7 @@ int ofb_destroy(ofb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   sparse_destroy(h);
   jpeg_destroy(h);
+  junction_destroy(h);
   cudaFree(h->d_src); cudaFree(h->d_img); cudaFree(h->d_RA); cudaFree(h->d_RB);
   cudaFree(h->d_MA); cudaFree(h->d_MB); cudaFree(h->d_VA); cudaFree(h->d_VB);
   for (int i = 0; i < 3; i++) cudaFree(h->d_flow[i]);

@@ -190,6 +190,7 @@ struct ofb_handle {
 
   // sparse path buffers are owned by lk.cu / features.cu state
   void* sparse = nullptr;
+  void* junction = nullptr;     // junction.cu: planes, labels and contour records of the junction detector
   void* jpeg = nullptr;         // jpeg.cu: coefficient staging and sample planes
 
   // per-stage event timing (ofb_timing_enable / ofb_timing_read)
@@ -275,6 +276,7 @@ int resize_u8_device(ofb_handle* h, const uint8_t* d_src, size_t sp, int sw, int
 int cvt_gray_device(ofb_handle* h, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch, int w,
                     int hh, int rgb_order);
 void jpeg_destroy(ofb_handle* h);
+void junction_destroy(ofb_handle* h);
 
 // ---- sparse ---------------------------------------------------------------------------
 void sparse_destroy(ofb_handle* h);

@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import FarnebackParams, GfttParams, LKParams, OfbError
+from ._lib import FarnebackParams, GfttParams, JunctionParams, LKParams, OfbError
 
 OPTFLOW_USE_INITIAL_FLOW = 4
 OPTFLOW_LK_GET_MIN_EIGENVALS = 8
@@ -434,6 +434,54 @@ class FlowEngine:
         out = np.empty((dh, dw), np.uint8)
         with self._lock:
             st = self._lib.ofb_ingest_jpeg_gray(self._h, buf.ctypes.data, buf.size, out.ctypes.data, dw, dh, 0)
+            _lib.check(st, self._h)
+        return out
+
+    @staticmethod
+    def _junction_args(img, grid_area, grid_area_threshold, eps, dampen):
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
+            raise OfbError(1, "the junction detector needs a uint8 [H,W] or [H,W,3] frame")
+        cn = 1 if img.ndim == 2 else 3
+        if img.strides[-1] != 1 or (cn == 3 and img.strides[1] != 3):
+            img = np.ascontiguousarray(img)
+        p = JunctionParams(int(grid_area), float(grid_area_threshold), int(eps), 0, 0.0, 0.0)
+        if dampen is not None:
+            p.dampen, p.dampen_min, p.dampen_max = 1, float(dampen[0]), float(dampen[1])
+        return img, cn, p
+
+    def find_junctions(self, img, grid_area: int = 250, grid_area_threshold: float = 2.0, eps: int = 4, dampen=None,
+                       return_candidates: bool = False):
+        """``find_junctions_not_rotated(img, grid_area, grid_area_threshold, false, eps)`` of the reference's junction
+        detector (junction_detector.cpp:31-214) on a uint8 gray or bgr8 frame; ``dampen=(min, max)`` applies
+        ``dampenIntensity`` first (:3-28; the ROS node uses (-20, 15), grid_area 200, eps 6).  Returns the junction
+        centres, float32 [n, 2] (x, y) in the reference's order (and the box corners before clustering if asked)."""
+        img, cn, p = self._junction_args(img, grid_area, grid_area_threshold, eps, dampen)
+        hgt, wid = img.shape[:2]
+        cap = 4096
+        while True:
+            out = np.empty((cap, 2), np.float32)
+            cand = np.empty((4 * cap, 2), np.float32)
+            n, nc = C.c_int(), C.c_int()
+            with self._lock:
+                st = self._lib.ofb_find_junctions(self._h, img.ctypes.data, wid, hgt, img.strides[0], cn, C.byref(p),
+                                                  out.ctypes.data, cap, C.byref(n), cand.ctypes.data, 4 * cap, C.byref(nc))
+                if st == 4 and cap < (1 << 20) and max(n.value, nc.value // 4) > cap:
+                    cap *= 8
+                    continue
+                _lib.check(st, self._h)
+            break
+        res = out[:n.value].copy()
+        return (res, cand[:nc.value].copy()) if return_candidates else res
+
+    def junction_threshold(self, img, dampen=None) -> np.ndarray:
+        """The detector's binary image: gray -> ``GaussianBlur(3x3)`` -> ``adaptiveThreshold(GAUSSIAN_C, BINARY, 11, 2)``."""
+        img, cn, p = self._junction_args(img, 250, 2.0, 4, dampen)
+        hgt, wid = img.shape[:2]
+        out = np.empty((hgt, wid), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_junction_threshold(self._h, img.ctypes.data, wid, hgt, img.strides[0], cn, C.byref(p),
+                                                  out.ctypes.data, 0)
             _lib.check(st, self._h)
         return out
 

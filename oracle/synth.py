@@ -121,3 +121,25 @@ def high_contrast_pair(h: int, w: int, seed: int, roll=(2, -3)):
     a = (a + rng.integers(0, 3, size=a.shape)).astype(np.uint8)
     b = np.roll(a, roll, axis=(0, 1))
     return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
+def synth_net(h: int, w: int, seed: int, pitch: float = 17.0, line: int = 3, bgr: bool = True):
+    """A fishing-net-like frame for the junction detector (junction_detector.cpp): dark, slightly wavy grid lines of
+    width `line` every `pitch` pixels on a brighter noisy background -> cells of about (pitch - line)^2 pixels."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    ang = rng.uniform(-0.15, 0.15)
+    u = xx * np.cos(ang) + yy * np.sin(ang) + 2.0 * np.sin(yy / 23.0 + rng.uniform(0, 6))
+    v = -xx * np.sin(ang) + yy * np.cos(ang) + 2.0 * np.sin(xx / 19.0 + rng.uniform(0, 6))
+    du = np.abs((u + rng.uniform(0, pitch)) % pitch - pitch / 2)
+    dv = np.abs((v + rng.uniform(0, pitch)) % pitch - pitch / 2)
+    net = (np.minimum(du, dv) < line / 2.0)
+    base = 150 + 40 * np.sin(xx / 90.0) * np.cos(yy / 70.0) + rng.normal(0, 6, (h, w))
+    img = np.where(net, 40 + rng.normal(0, 5, (h, w)), base)
+    img = cv2.GaussianBlur(img.astype(np.float32), (0, 0), 0.8)
+    g = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    if not bgr:
+        return g
+    out = np.stack([np.clip(g.astype(np.int32) + rng.integers(-8, 9, (h, w)), 0, 255) for _ in range(3)], -1)
+    return out.astype(np.uint8)
