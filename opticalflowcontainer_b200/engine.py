@@ -458,7 +458,7 @@ class FlowEngine:
         centres, float32 [n, 2] (x, y) in the reference's order (and the box corners before clustering if asked)."""
         img, cn, p = self._junction_args(img, grid_area, grid_area_threshold, eps, dampen)
         hgt, wid = img.shape[:2]
-        cap = 4096
+        cap = max(4096, (wid * hgt) // 128)         # a junction per ~128 px is far beyond any net; grown on demand
         while True:
             out = np.empty((cap, 2), np.float32)
             cand = np.empty((4 * cap, 2), np.float32)

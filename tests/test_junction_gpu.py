@@ -99,7 +99,7 @@ def test_junctions_feed_the_tracker(engine_factory):
     pts = eng.find_junctions(a, 200, 2.0, 6)
     assert len(pts) > 20
     p0 = pts.reshape(-1, 1, 2)
-    nxt, st, err = eng.pyrlk(a, b, p0, (21, 21), 3, (3, 30, 0.01))
+    nxt, st, err = eng.pyrlk(a, b, p0, None, (21, 21), 3, (3, 30, 0.01))
     rn, rs, re = cv2.calcOpticalFlowPyrLK(a, b, p0, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
     assert np.array_equal(st.reshape(-1), rs.reshape(-1))
     ok = rs.reshape(-1) == 1
