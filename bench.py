@@ -201,6 +201,56 @@ def lk_cpu_baseline(reps=5):
                       "after 1 warm-up; value from the median frame time of the slowest worker" % (cv2.__version__, workers, reps)}
 
 
+def around_record(local_rank, cpu=True):
+    """The calls in front of the flow call that round 2 added, host buffer in -> host result out,
+    with cv2 on one host core beside them and a bit-exactness check of each: JPEG CompressedImage ingest
+    (opticalflow_comprerssed_node.py:43-46) and the junction detector (junction_detector.cpp:31-214)."""
+    import cv2
+    import opticalflowcontainer_b200 as ofb
+    from oracle import synth
+    cv2.setNumThreads(1)
+    eng = ofb.FlowEngine(64, 64, 1, local_rank)
+
+    def ms(fn, reps=8):
+        fn(); fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    rec = {}
+    frame = synth.synth_net(1080, 1920, 3)
+    jpg = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, 90])[1]
+    ref = cv2.cvtColor(cv2.imdecode(jpg, cv2.IMREAD_COLOR), cv2.COLOR_BGR2GRAY)
+    l0 = eng.launch_count
+    got = eng.ingest_jpeg_gray(jpg)
+    rec["jpeg_ingest_1080p"] = {
+        "ms_per_frame": ms(lambda: eng.ingest_jpeg_gray(jpg)), "jpeg_bytes": int(jpg.size), "bit_exact_vs_cv2": bool(np.array_equal(got, ref)),
+        "gpu_launches_per_frame": int(eng.launch_count - l0),
+        "api": "ofb_ingest_jpeg_gray (host Huffman walk into pinned coefficient blocks; IDCT, up-sampling, YCbCr->BGR->gray on the device)",
+        "cv2_ms_per_frame": ms(lambda: cv2.cvtColor(cv2.imdecode(jpg, cv2.IMREAD_COLOR), cv2.COLOR_BGR2GRAY)) if cpu else None}
+    net = synth.synth_net(480, 640, 1)
+    th = cv2.adaptiveThreshold(cv2.GaussianBlur(cv2.cvtColor(net, cv2.COLOR_BGR2GRAY), (3, 3), 0), 255,
+                               cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY, 11, 2)
+
+    def cv_chain():
+        g = cv2.cvtColor(net, cv2.COLOR_BGR2GRAY)
+        t = cv2.adaptiveThreshold(cv2.GaussianBlur(g, (3, 3), 0), 255, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY, 11, 2)
+        cs, _ = cv2.findContours(t, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        return [(cv2.contourArea(c), cv2.boundingRect(c)) for c in cs]
+
+    l0 = eng.launch_count
+    pts = eng.find_junctions(net, 200, 2.0, 6)
+    rec["junction_detector_640x480"] = {
+        "ms_per_frame": ms(lambda: eng.find_junctions(net, 200, 2.0, 6)), "junctions": int(len(pts)),
+        "threshold_bit_exact_vs_cv2": bool(np.array_equal(eng.junction_threshold(net), th)),
+        "gpu_launches_per_frame": int(eng.launch_count - l0),
+        "api": "ofb_find_junctions (pixel stages + contours by component labelling on the device; ordering + nanoflann-exact clustering on the host)",
+        "cv2_ms_per_frame_without_clustering": ms(cv_chain) if cpu else None}
+    eng.close()
+    return rec
+
+
 def lk_record(args, rank, local_rank, world, steps, warmup, cpu=True):
     """BASELINE.json config 4: Shi-Tomasi (2000 corners) + pyramidal LK on 1080p camera streams, 8 streams sharded over
     the ranks.  A step = one new frame of every stream of this rank through the camera-stream call of the sparse path
@@ -731,6 +781,11 @@ def run_ours(args, rank, local_rank, world):
         rec = lk_record(args, rank, local_rank, world, steps=5, warmup=2, cpu=(world == 1 and not args.no_cpu_baseline))
         if rank == 0:
             extras["lk_8_streams"] = rec
+        if rank == 0:
+            try:
+                extras["around_the_path"] = around_record(local_rank, cpu=not args.no_cpu_baseline)
+            except Exception as e:     # (never lose the headline line to a side record)
+                extras["around_the_path"] = {"error": repr(e)}
         # (5) BASELINE.json config 5: one 8K pair tiled over the ranks (needs >= 2 GPUs)
         if world >= 2:
             rec = tiled_record(args, rank, local_rank, world, "8k", steps=5, warmup=3, parity=True, whole=True)

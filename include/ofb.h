@@ -307,8 +307,9 @@ int ofb_ingest_gray(ofb_handle* h, const uint8_t* src, int src_width, int src_he
  * compressed-image node, ros2_ws/src/optical_flow/optical_flow/opticalflow_comprerssed_node.py:43-46.  Baseline JPEG
  * (SOF0/SOF1, 8 bit, Huffman, one interleaved scan; gray-scale or YCbCr 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0, restart intervals),
  * bit-exact with the libjpeg-turbo 3.1.2 build inside the cv2 wheel (islow IDCT, fancy up-sampling, BGR output;
- * oracle/jpeg_np.py).  The host walks the entropy-coded bit stream into coefficient blocks; dequantisation, IDCT,
- * chroma up-sampling, colour conversion and the gray conversion run on the device.  Anything else (progressive,
+ * oracle/jpeg_np.py).  Entropy decoding (self-synchronising parallel Huffman decode), dequantisation, IDCT, chroma
+ * up-sampling, colour conversion and the gray conversion run on the device; the host parses the markers and removes the
+ * byte stuffing (scans with restart intervals are walked on the host instead).  Anything else (progressive,
  * arithmetic, 12 bit, CMYK) returns OFB_ERR_UNSUPPORTED — never a wrong frame, never a CPU decode. */
 /* Frame header only (no handle, no device work): size and component count for sizing the output arrays. */
 int ofb_jpeg_info(const uint8_t* jpeg, size_t n_bytes, int* width, int* height, int* components);
@@ -316,6 +317,10 @@ int ofb_jpeg_info(const uint8_t* jpeg, size_t n_bytes, int* width, int* height, 
  * after component (Y, Cb, Cr), each a row-major grid of whole blocks (padded to whole MCUs) of 64 coefficients in
  * natural (row-major) order.  coef may be NULL to query *n_coef. */
 int ofb_jpeg_entropy_decode(const uint8_t* jpeg, size_t n_bytes, int16_t* coef, size_t coef_capacity, size_t* n_coef);
+/* Where the Huffman stream is walked.  Default (0): on the device for scans without restart intervals (self-synchronising
+ * parallel decode: only the compressed bytes cross PCIe), on the host for scans with restart intervals.  1: always on the
+ * host (coefficient blocks cross PCIe).  Same coefficients either way. */
+int ofb_jpeg_set_host_entropy(ofb_handle* h, int on);
 /* bgr: host uint8 [height][width][3] = cv2.imdecode(buf, IMREAD_COLOR), and/or gray: host uint8 [height][width] =
  * cv2.cvtColor(that, COLOR_BGR2GRAY); either may be NULL, strides 0 = packed.  Synchronous. */
 int ofb_jpeg_decode(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* bgr, size_t bgr_stride_bytes, uint8_t* gray,

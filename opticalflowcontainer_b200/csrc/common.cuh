@@ -191,6 +191,7 @@ struct ofb_handle {
   // sparse path buffers are owned by lk.cu / features.cu state
   void* sparse = nullptr;
   void* junction = nullptr;     // junction.cu: planes, labels and contour records of the junction detector
+  bool jpeg_host_entropy = false;   // ofb_jpeg_set_host_entropy: Huffman decoding on the host even without restart markers
   void* jpeg = nullptr;         // jpeg.cu: coefficient staging and sample planes
 
   // per-stage event timing (ofb_timing_enable / ofb_timing_read)

@@ -29,6 +29,8 @@ struct HuffTab {
   int32_t maxcode[18];   // largest code of each length, -1 if none; [17] = sentinel
   int32_t valoff[17];    // index of the first symbol of a length minus its first code
   uint8_t vals[256];
+  uint8_t counts[16];
+  int n_vals = 0;
   bool present = false;
 };
 
@@ -57,7 +59,10 @@ const uint8_t kZigzag[64 + 16] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25
 
 bool build_huff(const uint8_t* counts, const uint8_t* vals, int n, HuffTab* t) {
   memset(t->look, 0, sizeof(t->look));
+  memset(t->vals, 0, sizeof(t->vals));
   memcpy(t->vals, vals, n);
+  memcpy(t->counts, counts, 16);
+  t->n_vals = n;
   int code = 0, k = 0;
   for (int len = 1; len <= 16; len++) {
     t->valoff[len] = k - code;
@@ -337,6 +342,8 @@ struct IdctPlane {
   int blocks_x, n_blocks;
   size_t pitch;
   int first_block;         // index of the component's first block in the launch
+  const int16_t* dc;       // device entropy decoding: DC values in the component's scan order (NULL: coefficient 0 holds the DC)
+  int h, v, mcux;          // blocks per MCU of the component, MCUs per row (for dc)
   uint16_t q[64];
 };
 struct IdctArgs {
@@ -398,6 +405,11 @@ __global__ void __launch_bounds__(256) k_jpeg_idct(const __grid_constant__ IdctA
     int x[8], o[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) x[r] = (int)(int16_t)((int)cf[r * 8 + t] * (int)P.q[r * 8 + t]);   // 16-bit product, as the library's vector code
+    if (t == 0 && P.dc) {
+      const int by = b / P.blocks_x, bx = b - by * P.blocks_x;
+      const int mcu = (by / P.v) * P.mcux + bx / P.h, j = (by % P.v) * P.h + bx % P.h;
+      x[0] = (int)(int16_t)((int)P.dc[(size_t)mcu * (P.h * P.v) + j] * (int)P.q[0]);
+    }
     idct8<11>(x, o);
 #pragma unroll
     for (int r = 0; r < 8; r++) ws[lb][r][t] = min(max(o[r], -32768), 32767);
@@ -490,11 +502,229 @@ __global__ void __launch_bounds__(256) k_jpeg_color(const __grid_constant__ Colo
   }
 }
 
+// ---- entropy decoding on the device (streams without restart markers) ----
+// A Huffman stream has no entry points, but a JPEG decoder started at an arbitrary bit in an arbitrary state falls
+// into step with the true decode after a few symbols, and from then on stays in step (self-synchronisation; Klein &
+// Wiseman 2003, Weissenberger & Schmidt 2018).  The bit stream is cut into subsequences of kSubBits bits, one thread
+// each.  The decoder state at a bit position is (bit position, block index within the MCU, zig-zag index within the
+// block).  k_huff_sync finds every subsequence's TRUE entry state as a fixed point: a thread decodes its subsequence
+// from its predecessor's current exit state and publishes its own exit state; subsequence 0 starts from the true
+// state, so once nothing changes any more every entry state is the true one.  Rounds inside a CTA of 256 consecutive
+// subsequences cost no launch (shared memory + barrier); the dependency across CTAs is carried by re-launching until a
+// launch changes nothing (typically three launches).  The same pass counts the blocks each subsequence completes; an
+// exclusive scan of the counts gives each subsequence the number of its first block, and k_huff_write decodes once more
+// into the coefficient planes (DC differences first; k_dc_prefix turns them into DC values per component).
+constexpr int kSubBits = 512;
+constexpr int kSyncThreads = 256;
+
+struct HuffLayout {
+  const uint32_t* bits;        // unstuffed stream as big-endian bytes, zero padded
+  uint32_t total_bits;
+  int n_sub;
+  int bpm;                     // blocks per MCU
+  int blk_comp[6];             // component of block b of an MCU
+  int blk_j[6];                // index of the block among its component's blocks in the MCU
+  int blk_dc[6], blk_ac[6];    // Huffman tables (0, 1)
+  uint32_t blk_tabs;           // the same, 4 bits per block: bit 0 DC table, bit 1 AC table
+  int comp_h[kMaxComp], comp_v[kMaxComp], comp_blocks_x[kMaxComp];
+  unsigned long long comp_off[kMaxComp];   // int16 offset of the component's first coefficient
+  unsigned long long dc_off[kMaxComp];     // offset of the component's DC differences in the compact array
+  int mcux, total_blocks;
+  const uint16_t* lut;         // [4][65536]: DC 0, DC 1, AC 0, AC 1; entry = length << 8 | symbol (0: no such code)
+};
+
+__device__ __forceinline__ uint32_t be32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+// the 32 bits that start at bit position p
+__device__ __forceinline__ uint32_t peek32(const uint32_t* __restrict__ bits, uint32_t p) {
+  const uint32_t i = p >> 5, o = p & 31;
+  return __funnelshift_l(be32(__ldg(bits + i + 1)), be32(__ldg(bits + i)), o);
+}
+
+__device__ __forceinline__ unsigned long long pack_state(uint32_t p, int blk, int z) {
+  return ((unsigned long long)p << 16) | (unsigned long long)(blk << 8) | (unsigned long long)z;
+}
+
+__constant__ uint8_t c_zigzag[80];
+
+constexpr int kPrimBits = 12;          // primary look-up (shared memory); longer codes go to the full table in global memory
+
+// Decodes from `state` until the bit position reaches end_bit; returns the exit state, counts completed blocks.
+// WRITE: coefficients go to their blocks, numbered from first_block on; DC differences to dc_diff (component, scan order).
+// The stream is read through a three-word register window (the word after next is always in flight); a code and its
+// value bits (<= 31 bits) come out of one 32-bit view.
+template <bool WRITE>
+__device__ __forceinline__ unsigned long long huff_run(const HuffLayout& L, const uint16_t* __restrict__ prim, unsigned long long state,
+                                                       uint32_t end_bit, int* n_blocks, int first_block, int16_t* __restrict__ coef,
+                                                       int16_t* __restrict__ dc_diff) {
+  uint32_t p = (uint32_t)(state >> 16);
+  int blk = (int)(state >> 8) & 0xff, z = (int)state & 0xff;
+  int done = 0;
+  int16_t* dst = nullptr;
+  int16_t* dcp = nullptr;
+  auto open_block = [&](int g) {
+    dst = nullptr;
+    if (g >= L.total_blocks) return;
+    const int mcu = g / L.bpm, b = g - mcu * L.bpm;
+    const int c = L.blk_comp[b], j = L.blk_j[b], ch = L.comp_h[c], cv = L.comp_v[c];
+    const int my = mcu / L.mcux, mx = mcu - my * L.mcux;
+    const int jy = ch == 1 ? j : j >> 1, jx = ch == 1 ? 0 : j & 1;
+    dst = coef + L.comp_off[c] + ((size_t)(my * cv + jy) * L.comp_blocks_x[c] + (mx * ch + jx)) * 64;
+    dcp = dc_diff + L.dc_off[c] + (size_t)mcu * (ch * cv) + j;
+  };
+  if (WRITE) open_block(first_block);
+  uint32_t idx = p >> 5;
+  uint32_t w0 = be32(__ldg(L.bits + idx)), w1 = be32(__ldg(L.bits + idx + 1)), w2 = be32(__ldg(L.bits + idx + 2));
+  const uint32_t tabs = L.blk_tabs;          // per block of the MCU: bit 0 DC table, bit 1 AC table (4 bits per block)
+  const int bpm = L.bpm;
+  // the loop body is written without data-dependent branches (the 32 lanes of a warp are at 32 unrelated places of
+  // the stream: DC / AC / end-of-block / zero-run decisions as selects keep the warp converged)
+  while (p < end_bit) {
+    const uint32_t w = __funnelshift_l(w1, w0, p & 31);
+    const bool dc = z == 0;
+    const uint32_t tb = tabs >> (blk << 2);
+    const int t = dc ? (int)(tb & 1) : 2 + (int)((tb >> 1) & 1);
+    uint32_t e = prim[(t << kPrimBits) + (w >> (32 - kPrimBits))];
+    if (!e) e = __ldg(L.lut + (t << 16) + (w >> 16));          // code longer than kPrimBits (rare)
+    const int len = e ? (int)(e >> 8) : 16, rs = e & 255;
+    const int s = rs & 15, r = rs >> 4;
+    const uint32_t v = (uint32_t)((unsigned long long)(w << len) >> (32 - s));
+    const int val = (int)v - (((v >> max(s - 1, 0)) & 1) ? 0 : (1 << s) - 1);
+    p += len + s;
+    const int zw = z + r;                                       // AC: where the coefficient goes
+    const int zn = dc ? 1 : (s == 0 ? (r == 15 ? z + 16 : 64) : zw + 1);
+    if (WRITE && dst) {
+      if (dc) *dcp = (int16_t)val;
+      else if (s) dst[c_zigzag[min(zw, 79)]] = (int16_t)val;
+    }
+    const bool complete = zn >= 64;
+    z = complete ? 0 : zn;
+    blk = complete ? (blk + 1 == bpm ? 0 : blk + 1) : blk;
+    done += complete ? 1 : 0;
+    if (WRITE && complete) open_block(first_block + done);
+    if ((p >> 5) != idx) {
+      idx++;
+      w0 = w1; w1 = w2;
+      w2 = be32(__ldg(L.bits + idx + 2));
+    }
+  }
+  *n_blocks = done;
+  return pack_state(p, blk, z);
+}
+
+// the first kPrimBits of every table into shared memory: entry of the full table if the code is that short, else 0
+__device__ __forceinline__ void load_primary(const HuffLayout& L, uint16_t* prim) {
+  for (int k = threadIdx.x; k < (4 << kPrimBits); k += blockDim.x) {
+    const int t = k >> kPrimBits, i = k & ((1 << kPrimBits) - 1);
+    const uint16_t e = L.lut[(t << 16) + (i << (16 - kPrimBits))];
+    prim[k] = (e >> 8) <= kPrimBits ? e : 0;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSyncThreads) k_huff_sync(const __grid_constant__ HuffLayout L, unsigned long long* __restrict__ exit_state,
+                                                            int* __restrict__ counts, int first_launch, int* __restrict__ changed) {
+  __shared__ unsigned long long sh_exit[kSyncThreads];
+  __shared__ uint16_t prim[4 << kPrimBits];
+  load_primary(L, prim);
+  const int tid = threadIdx.x, i = blockIdx.x * kSyncThreads + tid;
+  const bool live = i < L.n_sub;
+  const uint32_t end_bit = live ? min((uint32_t)(i + 1) * kSubBits, L.total_bits) : 0;
+  // entry state: the true start for subsequence 0; in the first launch a guess (block 0, DC next) at the subsequence's
+  // first bit, afterwards the predecessor's exit state of the previous launch
+  unsigned long long entry = pack_state((uint32_t)i * kSubBits, 0, 0);
+  if (live && i > 0 && !first_launch) entry = exit_state[i - 1];
+  unsigned long long last_entry = ~0ull, my_exit = 0;
+  int cnt = 0;
+  while (true) {
+    bool redo = false;
+    if (live && entry != last_entry) {
+      my_exit = huff_run<false>(L, prim, entry, end_bit, &cnt, 0, nullptr, nullptr);
+      last_entry = entry;
+      redo = true;
+    }
+    sh_exit[tid] = my_exit;
+    if (!__syncthreads_or(redo)) break;
+    if (tid > 0 && live) entry = sh_exit[tid - 1];
+    __syncthreads();
+  }
+  if (live) {
+    if (first_launch || exit_state[i] != my_exit) { exit_state[i] = my_exit; *changed = 1; }
+    counts[i] = cnt;
+  }
+}
+
+// exclusive scan of the block counts (one CTA; n_sub is a few thousand)
+__global__ void __launch_bounds__(1024) k_huff_scan(const int* __restrict__ counts, int* __restrict__ first_block, int n) {
+  __shared__ int sh[1024];
+  const int tid = threadIdx.x, per = (n + 1023) / 1024;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  int s = 0;
+  for (int k = lo; k < hi; k++) s += counts[k];
+  sh[tid] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int a = tid >= d ? sh[tid - d] : 0;
+    __syncthreads();
+    sh[tid] += a;
+    __syncthreads();
+  }
+  int run = sh[tid] - s;
+  for (int k = lo; k < hi; k++) { first_block[k] = run; run += counts[k]; }
+}
+
+__global__ void __launch_bounds__(kSyncThreads) k_huff_write(const __grid_constant__ HuffLayout L, const unsigned long long* __restrict__ exit_state,
+                                                             const int* __restrict__ first_block, int16_t* __restrict__ coef,
+                                                             int16_t* __restrict__ dc_diff) {
+  __shared__ uint16_t prim[4 << kPrimBits];
+  load_primary(L, prim);
+  const int i = blockIdx.x * kSyncThreads + threadIdx.x;
+  if (i >= L.n_sub) return;
+  const unsigned long long entry = i == 0 ? pack_state(0, 0, 0) : exit_state[i - 1];
+  int cnt;
+  huff_run<true>(L, prim, entry, min((uint32_t)(i + 1) * kSubBits, L.total_bits), &cnt, first_block[i], coef, dc_diff);
+}
+
+// DC differences -> DC values, in place in the compact array (scan order of the component): one CTA per component.
+// k_jpeg_idct takes a block's DC from there.
+__global__ void __launch_bounds__(1024) k_dc_prefix(const __grid_constant__ HuffLayout L, int16_t* __restrict__ dc, int n_mcu) {
+  __shared__ int sh[1024];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int n = n_mcu * L.comp_h[c] * L.comp_v[c], per = (n + 1023) / 1024;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  int16_t* d = dc + L.dc_off[c];
+  int s = 0;
+  for (int k = lo; k < hi; k++) s += d[k];
+  sh[tid] = s;
+  __syncthreads();
+  for (int dd = 1; dd < 1024; dd <<= 1) {
+    const int a = tid >= dd ? sh[tid - dd] : 0;
+    __syncthreads();
+    sh[tid] += a;
+    __syncthreads();
+  }
+  int run = sh[tid] - s;
+  for (int k = lo; k < hi; k++) { run += d[k]; d[k] = (int16_t)run; }
+}
+
 struct JpegState {
   int16_t* h_coef = nullptr;    // pinned
   int16_t* d_coef = nullptr;
   uint8_t* d_planes = nullptr;
   size_t coef_cap = 0, plane_cap = 0;
+  // device entropy decoding
+  uint8_t* h_bits = nullptr;    // pinned, unstuffed stream
+  uint32_t* d_bits = nullptr;
+  size_t bits_cap = 0;
+  uint16_t* h_lut = nullptr;    // pinned [4][65536]
+  uint16_t* d_lut = nullptr;
+  uint8_t lut_key[4][16 + 256]; // the DHT contents the device tables were built from
+  bool lut_valid = false;
+  unsigned long long* d_exit = nullptr;
+  int *d_counts = nullptr, *d_first = nullptr, *d_changed = nullptr, *h_changed = nullptr;
+  int16_t* d_dc = nullptr;      // DC differences, compact
+  size_t sub_cap = 0, dc_cap = 0;
+  bool zigzag_up = false;
 };
 
 }  // namespace
@@ -505,8 +735,155 @@ void jpeg_destroy(ofb_handle* h) {
   if (s->h_coef) cudaFreeHost(s->h_coef);
   if (s->d_coef) cudaFree(s->d_coef);
   if (s->d_planes) cudaFree(s->d_planes);
+  if (s->h_bits) cudaFreeHost(s->h_bits);
+  if (s->h_lut) cudaFreeHost(s->h_lut);
+  if (s->h_changed) cudaFreeHost(s->h_changed);
+  cudaFree(s->d_bits); cudaFree(s->d_lut); cudaFree(s->d_exit); cudaFree(s->d_counts); cudaFree(s->d_first); cudaFree(s->d_changed); cudaFree(s->d_dc);
   delete s;
   h->jpeg = nullptr;
+}
+
+// Copies the entropy-coded segment without its byte stuffing into `out` (capacity n + 64), zero padded; returns the bytes.
+static size_t unstuff_into(const uint8_t* p, size_t n, uint8_t* out) {
+  uint8_t* o = out;
+  const uint8_t* end = p + n;
+  while (p < end) {
+    const uint8_t* q = static_cast<const uint8_t*>(memchr(p, 0xFF, end - p));
+    if (!q) q = end;
+    memcpy(o, p, q - p);
+    o += q - p;
+    p = q;
+    if (p + 1 >= end) break;
+    if (p[1] == 0) { *o++ = 0xFF; p += 2; }
+    else if (p[1] == 0xFF) p++;
+    else break;                                          // a marker ends the data (no restart markers on this path)
+  }
+  const size_t used = o - out;
+  memset(o, 0, 64);
+  return used;
+}
+
+// Huffman decoding of a scan without restart intervals on the device: coefficient planes in s->d_coef.
+static int entropy_decode_device(ofb_handle* h, JpegState* s, const Frame& f) {
+  cudaStream_t sm = h->stream;
+  if (f.n_data + 64 > s->bits_cap) {
+    if (s->h_bits) cudaFreeHost(s->h_bits);
+    cudaFree(s->d_bits);
+    s->h_bits = nullptr; s->d_bits = nullptr; s->bits_cap = 0;
+    const size_t cap = (f.n_data + 64 + 4095) & ~(size_t)4095;
+    OFB_CUDA(h, cudaHostAlloc(&s->h_bits, cap, cudaHostAllocDefault));
+    OFB_CUDA(h, cudaMalloc(&s->d_bits, cap));
+    s->bits_cap = cap;
+  }
+  if (!s->d_lut) {
+    OFB_CUDA(h, cudaHostAlloc(&s->h_lut, 4 * 65536 * sizeof(uint16_t), cudaHostAllocDefault));
+    OFB_CUDA(h, cudaMalloc(&s->d_lut, 4 * 65536 * sizeof(uint16_t)));
+    OFB_CUDA(h, cudaMalloc(&s->d_changed, 16 * sizeof(int)));
+    OFB_CUDA(h, cudaHostAlloc(&s->h_changed, sizeof(int), cudaHostAllocDefault));
+  }
+  if (!s->zigzag_up) {
+    OFB_CUDA(h, cudaMemcpyToSymbolAsync(c_zigzag, kZigzag, 80, 0, cudaMemcpyHostToDevice, sm));
+    s->zigzag_up = true;
+  }
+  const size_t used = unstuff_into(f.data, f.n_data, s->h_bits);
+  const size_t up_bytes = (used + 32 + 3) & ~(size_t)3;
+  OFB_CUDA(h, cudaMemcpyAsync(s->d_bits, s->h_bits, up_bytes, cudaMemcpyHostToDevice, sm));
+  // full 16-bit code tables, rebuilt only when the stream's DHT segments change (cameras send the same ones every frame)
+  const HuffTab* tabs[4] = {&f.dc[0], &f.dc[1], &f.ac[0], &f.ac[1]};
+  bool same = s->lut_valid;
+  for (int t = 0; t < 4 && same; t++) {
+    uint8_t key[16 + 256] = {0};
+    if (tabs[t]->present) { memcpy(key, tabs[t]->counts, 16); memcpy(key + 16, tabs[t]->vals, 256); }
+    same = memcmp(key, s->lut_key[t], sizeof(key)) == 0;
+  }
+  if (!same) {
+    for (int t = 0; t < 4; t++) {
+      uint16_t* lut = s->h_lut + (size_t)t * 65536;
+      memset(lut, 0, 65536 * sizeof(uint16_t));
+      memset(s->lut_key[t], 0, sizeof(s->lut_key[t]));
+      if (!tabs[t]->present) continue;
+      memcpy(s->lut_key[t], tabs[t]->counts, 16);
+      memcpy(s->lut_key[t] + 16, tabs[t]->vals, 256);
+      int code = 0, k = 0;
+      for (int len = 1; len <= 16; len++) {
+        for (int i = 0; i < tabs[t]->counts[len - 1]; i++, code++, k++) {
+          const uint16_t e = (uint16_t)((len << 8) | tabs[t]->vals[k]);
+          const int lo = code << (16 - len);
+          for (int j = 0; j < (1 << (16 - len)); j++) lut[lo + j] = e;
+        }
+        code <<= 1;
+      }
+    }
+    OFB_CUDA(h, cudaMemcpyAsync(s->d_lut, s->h_lut, 4 * 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice, sm));
+    s->lut_valid = true;
+  }
+  HuffLayout L = {};
+  L.bits = s->d_bits;
+  L.total_bits = (uint32_t)(used * 8);
+  L.n_sub = (int)((L.total_bits + kSubBits - 1) / kSubBits);
+  if (L.n_sub < 1) L.n_sub = 1;
+  int b = 0;
+  for (int c = 0; c < f.nc; c++) {
+    const Comp& k = f.comp[c];
+    L.comp_h[c] = k.h; L.comp_v[c] = k.v; L.comp_blocks_x[c] = k.blocks_x; L.comp_off[c] = k.coef_off;
+    for (int j = 0; j < k.h * k.v; j++, b++) {
+      if (b >= 6) return set_error(h, OFB_ERR_UNSUPPORTED, "JPEG: more than 6 blocks per MCU");
+      L.blk_comp[b] = c; L.blk_j[b] = j; L.blk_dc[b] = k.td; L.blk_ac[b] = k.ta;
+      L.blk_tabs |= (uint32_t)(k.td | (k.ta << 1)) << (4 * b);
+    }
+  }
+  L.bpm = b;
+  size_t n_dc = 0;
+  for (int c = 0; c < f.nc; c++) { L.dc_off[c] = n_dc; n_dc += (size_t)f.mcux * f.mcuy * f.comp[c].h * f.comp[c].v; }
+  if (n_dc > s->dc_cap) {
+    cudaFree(s->d_dc);
+    s->d_dc = nullptr; s->dc_cap = 0;
+    OFB_CUDA(h, cudaMalloc(&s->d_dc, n_dc * sizeof(int16_t)));
+    s->dc_cap = n_dc;
+  }
+  L.mcux = f.mcux;
+  L.total_blocks = f.mcux * f.mcuy * b;
+  L.lut = s->d_lut;
+  if ((size_t)L.n_sub > s->sub_cap) {
+    cudaFree(s->d_exit); cudaFree(s->d_counts); cudaFree(s->d_first);
+    s->d_exit = nullptr; s->d_counts = nullptr; s->d_first = nullptr; s->sub_cap = 0;
+    const size_t cap = ((size_t)L.n_sub + 1023) & ~(size_t)1023;
+    OFB_CUDA(h, cudaMalloc(&s->d_exit, cap * sizeof(unsigned long long)));
+    OFB_CUDA(h, cudaMalloc(&s->d_counts, cap * sizeof(int)));
+    OFB_CUDA(h, cudaMalloc(&s->d_first, cap * sizeof(int)));
+    s->sub_cap = cap;
+  }
+  int st;
+  if ((st = timing_begin(h, OFB_STAGE_OTHER))) return st;
+  OFB_CUDA(h, cudaMemsetAsync(s->d_coef, 0, f.n_coef * sizeof(int16_t), sm));
+  OFB_CUDA(h, cudaMemsetAsync(s->d_dc, 0, n_dc * sizeof(int16_t), sm));
+  OFB_CUDA(h, cudaMemsetAsync(s->d_changed, 0, 16 * sizeof(int), sm));
+  const int ctas = (L.n_sub + kSyncThreads - 1) / kSyncThreads;
+  // a CTA settles its own 256 subsequences in one launch; the exit state of a CTA reaches the next CTA in the next
+  // launch, from where on that CTA is right too: two launches make every state true in all but pathological streams,
+  // the third (or a later one) proves it by changing nothing
+  int round = 0;
+  for (; round < 3; round++) {
+    k_huff_sync<<<ctas, kSyncThreads, 0, sm>>>(L, s->d_exit, s->d_counts, round == 0, s->d_changed + round);
+    OFB_LAUNCH_CHECK(h);
+  }
+  while (true) {
+    OFB_CUDA(h, cudaMemcpyAsync(s->h_changed, s->d_changed + (round - 1) % 16, sizeof(int), cudaMemcpyDeviceToHost, sm));
+    OFB_CUDA(h, cudaStreamSynchronize(sm));
+    if (!*s->h_changed) break;
+    if (round > ctas + 3) return set_error(h, OFB_ERR_CUDA, "JPEG: entropy decoder did not settle");
+    OFB_CUDA(h, cudaMemsetAsync(s->d_changed + round % 16, 0, sizeof(int), sm));
+    k_huff_sync<<<ctas, kSyncThreads, 0, sm>>>(L, s->d_exit, s->d_counts, 0, s->d_changed + round % 16);
+    OFB_LAUNCH_CHECK(h);
+    round++;
+  }
+  k_huff_scan<<<1, 1024, 0, sm>>>(s->d_counts, s->d_first, L.n_sub);
+  OFB_LAUNCH_CHECK(h);
+  k_huff_write<<<ctas, kSyncThreads, 0, sm>>>(L, s->d_exit, s->d_first, s->d_coef, s->d_dc);
+  OFB_LAUNCH_CHECK(h);
+  k_dc_prefix<<<f.nc, 1024, 0, sm>>>(L, s->d_dc, f.mcux * f.mcuy);
+  OFB_LAUNCH_CHECK(h);
+  return timing_end(h);
 }
 
 // Decodes `jpeg` into device frames on the handle's stream: d_bgr ([height][width][3], pitch bgr_pitch) and/or d_gray.
@@ -537,12 +914,21 @@ static int jpeg_decode_device(ofb_handle* h, const Frame& f, uint8_t* d_bgr, siz
     OFB_CUDA(h, cudaMalloc(&s->d_planes, plane_bytes));
     s->plane_cap = plane_bytes;
   }
-  memset(s->h_coef, 0, f.n_coef * sizeof(int16_t));
-  decode_scan(f, s->h_coef);
-  OFB_CUDA(h, cudaMemcpyAsync(s->d_coef, s->h_coef, f.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, sm));
+  bool on_device = f.dri == 0 && f.n_data < (1u << 27) && !h->jpeg_host_entropy;
+  for (int c = 0; c < f.nc; c++) on_device = on_device && f.comp[c].td <= 1 && f.comp[c].ta <= 1;
+  if (on_device) {
+    int st = entropy_decode_device(h, s, f);
+    if (st) return st;
+  } else {
+    // restart intervals (or unusual table numbering): the host walks the stream
+    memset(s->h_coef, 0, f.n_coef * sizeof(int16_t));
+    decode_scan(f, s->h_coef);
+    OFB_CUDA(h, cudaMemcpyAsync(s->d_coef, s->h_coef, f.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, sm));
+  }
   IdctArgs ia = {};
   ia.nc = f.nc;
   int first = 0;
+  size_t dc_off = 0;
   for (int c = 0; c < f.nc; c++) {
     const Comp& k = f.comp[c];
     IdctPlane& P = ia.p[c];
@@ -552,6 +938,9 @@ static int jpeg_decode_device(ofb_handle* h, const Frame& f, uint8_t* d_bgr, siz
     P.n_blocks = k.blocks_x * k.blocks_y;
     P.pitch = pitch[c];
     P.first_block = first;
+    P.dc = on_device ? s->d_dc + dc_off : nullptr;
+    P.h = k.h; P.v = k.v; P.mcux = f.mcux;
+    dc_off += (size_t)f.mcux * f.mcuy * k.h * k.v;
     memcpy(P.q, f.qt[k.tq], sizeof(P.q));
     first += P.n_blocks;
   }
@@ -597,6 +986,12 @@ int ofb_jpeg_info(const uint8_t* jpeg, size_t n_bytes, int* width, int* height, 
   }
   delete f;
   return why ? OFB_ERR_UNSUPPORTED : OFB_OK;
+}
+
+int ofb_jpeg_set_host_entropy(ofb_handle* h, int on) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  h->jpeg_host_entropy = on != 0;
+  return OFB_OK;
 }
 
 int ofb_jpeg_entropy_decode(const uint8_t* jpeg, size_t n_bytes, int16_t* coef, size_t coef_capacity, size_t* n_coef) {

@@ -411,6 +411,11 @@ class FlowEngine:
             raise OfbError(st, "not a baseline JPEG stream the device path decodes")
         return w.value, h.value, c.value
 
+    def jpeg_host_entropy(self, on: bool):
+        """Walk the Huffman stream on the host (True) instead of on the device (default for scans without restart
+        intervals); same result."""
+        _lib.check(self._lib.ofb_jpeg_set_host_entropy(self._h, 1 if on else 0), self._h)
+
     def imdecode(self, buf, gray: bool = False) -> np.ndarray:
         """``cv2.imdecode(buf, cv2.IMREAD_COLOR)`` of a baseline JPEG (``sensor_msgs/CompressedImage.data``; the
         compressed-image node, opticalflow_comprerssed_node.py:43-46): uint8 [H,W,3] BGR, bit-exact with the wheel's

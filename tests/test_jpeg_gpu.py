@@ -24,6 +24,35 @@ def test_imdecode_equals_cv2(engine_factory, size, sampling, quality, rst):
     assert np.array_equal(eng.imdecode(buf.tobytes(), gray=True), cv2.cvtColor(ref, cv2.COLOR_BGR2GRAY))
 
 
+@pytest.mark.parametrize("size,sampling,quality", [((1080, 1920), "420", 90), ((481, 637), "422", 35), ((539, 959), "444", 98),
+                                                   ((64, 4000), "420", 75), ((2160, 3840), "420", 80)])
+def test_device_and_host_entropy_decoders_agree(engine_factory, size, sampling, quality):
+    """Scans without restart intervals are Huffman-decoded on the device (self-synchronising subsequences); forcing the
+    host walk must give the same frame, and both equal cv2."""
+    h, w = size
+    buf = encode(jpeg_frame(h, w, quality + 1), sampling, quality, 0)
+    ref = cv2.imdecode(buf, cv2.IMREAD_COLOR)
+    eng = engine_factory(64, 64)
+    dev = eng.imdecode(buf)
+    eng.jpeg_host_entropy(True)
+    try:
+        host = eng.imdecode(buf)
+    finally:
+        eng.jpeg_host_entropy(False)
+    assert np.array_equal(dev, ref) and np.array_equal(host, ref)
+
+
+def test_device_entropy_on_smooth_and_flat_frames(engine_factory):
+    """Few bits per block (flat frames: an MCU is a handful of bits, a subsequence holds dozens of blocks) and a gray JPEG."""
+    eng = engine_factory(64, 64)
+    flat = np.full((240, 320, 3), 77, np.uint8)
+    ramp = np.dstack([np.tile(np.linspace(0, 255, 640).astype(np.uint8), (480, 1))] * 3)
+    for img in (flat, ramp, ramp[..., 0]):
+        for q in (95, 20):
+            buf = encode(img, "420", q, 0)
+            assert np.array_equal(eng.imdecode(buf), cv2.imdecode(buf, cv2.IMREAD_COLOR))
+
+
 def test_gray_jpeg_and_repeated_calls(engine_factory):
     eng = engine_factory(64, 64)
     for seed, (h, w) in enumerate([(40, 56), (200, 312), (33, 35)]):      # staging grows and is reused
