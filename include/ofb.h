@@ -309,7 +309,7 @@ int ofb_ingest_gray(ofb_handle* h, const uint8_t* src, int src_width, int src_he
  * bit-exact with the libjpeg-turbo 3.1.2 build inside the cv2 wheel (islow IDCT, fancy up-sampling, BGR output;
  * oracle/jpeg_np.py).  Entropy decoding (self-synchronising parallel Huffman decode), dequantisation, IDCT, chroma
  * up-sampling, colour conversion and the gray conversion run on the device; the host parses the markers and removes the
- * byte stuffing (scans with restart intervals are walked on the host instead).  Anything else (progressive,
+ * byte stuffing.  Anything else (progressive,
  * arithmetic, 12 bit, CMYK) returns OFB_ERR_UNSUPPORTED — never a wrong frame, never a CPU decode. */
 /* Frame header only (no handle, no device work): size and component count for sizing the output arrays. */
 int ofb_jpeg_info(const uint8_t* jpeg, size_t n_bytes, int* width, int* height, int* components);
@@ -317,9 +317,9 @@ int ofb_jpeg_info(const uint8_t* jpeg, size_t n_bytes, int* width, int* height, 
  * after component (Y, Cb, Cr), each a row-major grid of whole blocks (padded to whole MCUs) of 64 coefficients in
  * natural (row-major) order.  coef may be NULL to query *n_coef. */
 int ofb_jpeg_entropy_decode(const uint8_t* jpeg, size_t n_bytes, int16_t* coef, size_t coef_capacity, size_t* n_coef);
-/* Where the Huffman stream is walked.  Default (0): on the device for scans without restart intervals (self-synchronising
- * parallel decode: only the compressed bytes cross PCIe), on the host for scans with restart intervals.  1: always on the
- * host (coefficient blocks cross PCIe).  Same coefficients either way. */
+/* Where the Huffman stream is walked.  Default (0): on the device (self-synchronising parallel decode, restart intervals
+ * as independent chains: only the compressed bytes cross PCIe).  1: on the host (coefficient blocks cross PCIe).  Same
+ * coefficients either way. */
 int ofb_jpeg_set_host_entropy(ofb_handle* h, int on);
 /* bgr: host uint8 [height][width][3] = cv2.imdecode(buf, IMREAD_COLOR), and/or gray: host uint8 [height][width] =
  * cv2.cvtColor(that, COLOR_BGR2GRAY); either may be NULL, strides 0 = packed.  Synchronous. */

@@ -531,6 +531,14 @@ struct HuffLayout {
   unsigned long long dc_off[kMaxComp];     // offset of the component's DC differences in the compact array
   int mcux, total_blocks;
   const uint16_t* lut;         // [4][65536]: DC 0, DC 1, AC 0, AC 1; entry = length << 8 | symbol (0: no such code)
+  // subsequences: bit range, and for the first subsequence of a restart interval (whose entry state is known: block 0,
+  // DC next, at the interval's first bit) the number of the interval's first block; -1 otherwise.  sub_headidx = index of
+  // the interval's first subsequence.
+  const uint32_t* sub_start;
+  const uint32_t* sub_end;
+  const int* sub_head_block;
+  const int* sub_headidx;
+  int dri_blocks;              // blocks of one component-independent restart interval in MCUs (0: no restart intervals)
 };
 
 __device__ __forceinline__ uint32_t be32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
@@ -555,8 +563,8 @@ constexpr int kPrimBits = 12;          // primary look-up (shared memory); longe
 // value bits (<= 31 bits) come out of one 32-bit view.
 template <bool WRITE>
 __device__ __forceinline__ unsigned long long huff_run(const HuffLayout& L, const uint16_t* __restrict__ prim, unsigned long long state,
-                                                       uint32_t end_bit, int* n_blocks, int first_block, int16_t* __restrict__ coef,
-                                                       int16_t* __restrict__ dc_diff) {
+                                                       uint32_t end_bit, int* n_blocks, int first_block, int block_limit,
+                                                       int16_t* __restrict__ coef, int16_t* __restrict__ dc_diff) {
   uint32_t p = (uint32_t)(state >> 16);
   int blk = (int)(state >> 8) & 0xff, z = (int)state & 0xff;
   int done = 0;
@@ -564,7 +572,7 @@ __device__ __forceinline__ unsigned long long huff_run(const HuffLayout& L, cons
   int16_t* dcp = nullptr;
   auto open_block = [&](int g) {
     dst = nullptr;
-    if (g >= L.total_blocks) return;
+    if (g >= block_limit) return;      // past the interval's (or the scan's) last block: padding bits, or a corrupt stream
     const int mcu = g / L.bpm, b = g - mcu * L.bpm;
     const int c = L.blk_comp[b], j = L.blk_j[b], ch = L.comp_h[c], cv = L.comp_v[c];
     const int my = mcu / L.mcux, mx = mcu - my * L.mcux;
@@ -629,23 +637,25 @@ __global__ void __launch_bounds__(kSyncThreads) k_huff_sync(const __grid_constan
   load_primary(L, prim);
   const int tid = threadIdx.x, i = blockIdx.x * kSyncThreads + tid;
   const bool live = i < L.n_sub;
-  const uint32_t end_bit = live ? min((uint32_t)(i + 1) * kSubBits, L.total_bits) : 0;
-  // entry state: the true start for subsequence 0; in the first launch a guess (block 0, DC next) at the subsequence's
-  // first bit, afterwards the predecessor's exit state of the previous launch
-  unsigned long long entry = pack_state((uint32_t)i * kSubBits, 0, 0);
-  if (live && i > 0 && !first_launch) entry = exit_state[i - 1];
+  const uint32_t end_bit = live ? L.sub_end[i] : 0;
+  // entry state: the true start for the first subsequence of a restart interval (or of the scan); otherwise, in the
+  // first launch, a guess (block 0, DC next) at the subsequence's first bit, afterwards the predecessor's exit state of
+  // the previous launch
+  const bool head = live && L.sub_head_block[i] >= 0;
+  unsigned long long entry = pack_state(live ? L.sub_start[i] : 0, 0, 0);
+  if (live && !head && !first_launch) entry = exit_state[i - 1];
   unsigned long long last_entry = ~0ull, my_exit = 0;
   int cnt = 0;
   while (true) {
     bool redo = false;
     if (live && entry != last_entry) {
-      my_exit = huff_run<false>(L, prim, entry, end_bit, &cnt, 0, nullptr, nullptr);
+      my_exit = huff_run<false>(L, prim, entry, end_bit, &cnt, 0, 0, nullptr, nullptr);
       last_entry = entry;
       redo = true;
     }
     sh_exit[tid] = my_exit;
     if (!__syncthreads_or(redo)) break;
-    if (tid > 0 && live) entry = sh_exit[tid - 1];
+    if (tid > 0 && live && !head) entry = sh_exit[tid - 1];
     __syncthreads();
   }
   if (live) {
@@ -673,6 +683,14 @@ __global__ void __launch_bounds__(1024) k_huff_scan(const int* __restrict__ coun
   for (int k = lo; k < hi; k++) { first_block[k] = run; run += counts[k]; }
 }
 
+// blocks before a subsequence = the interval's first block + the blocks completed since the interval's first subsequence
+__global__ void __launch_bounds__(256) k_huff_rebase(const __grid_constant__ HuffLayout L, const int* __restrict__ excl, int* __restrict__ first_block) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= L.n_sub) return;
+  const int hd = L.sub_headidx[i];
+  first_block[i] = L.sub_head_block[hd] + excl[i] - excl[hd];
+}
+
 __global__ void __launch_bounds__(kSyncThreads) k_huff_write(const __grid_constant__ HuffLayout L, const unsigned long long* __restrict__ exit_state,
                                                              const int* __restrict__ first_block, int16_t* __restrict__ coef,
                                                              int16_t* __restrict__ dc_diff) {
@@ -680,9 +698,11 @@ __global__ void __launch_bounds__(kSyncThreads) k_huff_write(const __grid_consta
   load_primary(L, prim);
   const int i = blockIdx.x * kSyncThreads + threadIdx.x;
   if (i >= L.n_sub) return;
-  const unsigned long long entry = i == 0 ? pack_state(0, 0, 0) : exit_state[i - 1];
+  const unsigned long long entry = L.sub_head_block[i] >= 0 ? pack_state(L.sub_start[i], 0, 0) : exit_state[i - 1];
   int cnt;
-  huff_run<true>(L, prim, entry, min((uint32_t)(i + 1) * kSubBits, L.total_bits), &cnt, first_block[i], coef, dc_diff);
+  const int head_block = L.sub_head_block[L.sub_headidx[i]];
+  const int limit = L.dri_blocks ? min(head_block + L.dri_blocks, L.total_blocks) : L.total_blocks;
+  huff_run<true>(L, prim, entry, L.sub_end[i], &cnt, first_block[i], limit, coef, dc_diff);
 }
 
 // DC differences -> DC values, in place in the compact array (scan order of the component): one CTA per component.
@@ -707,6 +727,30 @@ __global__ void __launch_bounds__(1024) k_dc_prefix(const __grid_constant__ Huff
   for (int k = lo; k < hi; k++) { run += d[k]; d[k] = (int16_t)run; }
 }
 
+// the same with restart intervals (the prediction restarts with every interval): one warp per (component, interval)
+__global__ void __launch_bounds__(256) k_dc_prefix_intervals(const __grid_constant__ HuffLayout L, int16_t* __restrict__ dc, int n_mcu,
+                                                             int dri, int n_int, int nc) {
+  const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_int * nc) return;
+  const int c = wid / n_int, k = wid - c * n_int;
+  const int hv = L.comp_h[c] * L.comp_v[c];
+  const int lo = k * dri * hv, hi = min((k + 1) * dri, n_mcu) * hv;
+  int16_t* d = dc + L.dc_off[c];
+  int carry = 0;
+  for (int base = lo; base < hi; base += 32) {
+    const int idx = base + lane;
+    int v = idx < hi ? d[idx] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    v += carry;
+    if (idx < hi) d[idx] = (int16_t)v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+
 struct JpegState {
   int16_t* h_coef = nullptr;    // pinned
   int16_t* d_coef = nullptr;
@@ -723,6 +767,9 @@ struct JpegState {
   unsigned long long* d_exit = nullptr;
   int *d_counts = nullptr, *d_first = nullptr, *d_changed = nullptr, *h_changed = nullptr;
   int16_t* d_dc = nullptr;      // DC differences, compact
+  uint32_t* d_subtab = nullptr; // [4][sub_cap]: start bit, end bit, head block, head index
+  uint32_t* h_subtab = nullptr; // pinned
+  int* d_excl = nullptr;
   size_t sub_cap = 0, dc_cap = 0;
   bool zigzag_up = false;
 };
@@ -738,13 +785,14 @@ void jpeg_destroy(ofb_handle* h) {
   if (s->h_bits) cudaFreeHost(s->h_bits);
   if (s->h_lut) cudaFreeHost(s->h_lut);
   if (s->h_changed) cudaFreeHost(s->h_changed);
-  cudaFree(s->d_bits); cudaFree(s->d_lut); cudaFree(s->d_exit); cudaFree(s->d_counts); cudaFree(s->d_first); cudaFree(s->d_changed); cudaFree(s->d_dc);
+  cudaFree(s->d_bits); cudaFree(s->d_lut); cudaFree(s->d_exit); cudaFree(s->d_counts); cudaFree(s->d_first); cudaFree(s->d_changed); cudaFree(s->d_dc); cudaFree(s->d_subtab); cudaFree(s->d_excl);
+  if (s->h_subtab) cudaFreeHost(s->h_subtab);
   delete s;
   h->jpeg = nullptr;
 }
 
 // Copies the entropy-coded segment without its byte stuffing into `out` (capacity n + 64), zero padded; returns the bytes.
-static size_t unstuff_into(const uint8_t* p, size_t n, uint8_t* out) {
+static size_t unstuff_into(const uint8_t* p, size_t n, uint8_t* out, std::vector<size_t>* rst) {
   uint8_t* o = out;
   const uint8_t* end = p + n;
   while (p < end) {
@@ -756,14 +804,15 @@ static size_t unstuff_into(const uint8_t* p, size_t n, uint8_t* out) {
     if (p + 1 >= end) break;
     if (p[1] == 0) { *o++ = 0xFF; p += 2; }
     else if (p[1] == 0xFF) p++;
-    else break;                                          // a marker ends the data (no restart markers on this path)
+    else if (p[1] >= 0xD0 && p[1] <= 0xD7) { rst->push_back((size_t)(o - out)); p += 2; }   // the next interval starts here
+    else break;                                          // any other marker ends the data
   }
   const size_t used = o - out;
   memset(o, 0, 64);
   return used;
 }
 
-// Huffman decoding of a scan without restart intervals on the device: coefficient planes in s->d_coef.
+// Huffman decoding of the scan on the device: coefficient planes in s->d_coef, DC values in s->d_dc.
 static int entropy_decode_device(ofb_handle* h, JpegState* s, const Frame& f) {
   cudaStream_t sm = h->stream;
   if (f.n_data + 64 > s->bits_cap) {
@@ -785,7 +834,9 @@ static int entropy_decode_device(ofb_handle* h, JpegState* s, const Frame& f) {
     OFB_CUDA(h, cudaMemcpyToSymbolAsync(c_zigzag, kZigzag, 80, 0, cudaMemcpyHostToDevice, sm));
     s->zigzag_up = true;
   }
-  const size_t used = unstuff_into(f.data, f.n_data, s->h_bits);
+  static thread_local std::vector<size_t> rst;
+  rst.clear();
+  const size_t used = unstuff_into(f.data, f.n_data, s->h_bits, &rst);
   const size_t up_bytes = (used + 32 + 3) & ~(size_t)3;
   OFB_CUDA(h, cudaMemcpyAsync(s->d_bits, s->h_bits, up_bytes, cudaMemcpyHostToDevice, sm));
   // full 16-bit code tables, rebuilt only when the stream's DHT segments change (cameras send the same ones every frame)
@@ -820,8 +871,17 @@ static int entropy_decode_device(ofb_handle* h, JpegState* s, const Frame& f) {
   HuffLayout L = {};
   L.bits = s->d_bits;
   L.total_bits = (uint32_t)(used * 8);
-  L.n_sub = (int)((L.total_bits + kSubBits - 1) / kSubBits);
-  if (L.n_sub < 1) L.n_sub = 1;
+  // restart intervals: [start byte, end byte) of each; without DRI the whole scan is one interval
+  const int n_mcu = f.mcux * f.mcuy;
+  const int n_int = f.dri ? (n_mcu + f.dri - 1) / f.dri : 1;
+  static thread_local std::vector<size_t> ibeg;
+  ibeg.assign(1, 0);
+  for (size_t k = 0; k < rst.size() && (int)ibeg.size() < n_int; k++) ibeg.push_back(rst[k]);
+  while ((int)ibeg.size() < n_int) ibeg.push_back(used);            // missing markers: empty intervals (blocks stay zero)
+  ibeg.push_back(used);
+  size_t n_sub = 0;
+  for (int k = 0; k < n_int; k++) n_sub += std::max<size_t>(1, ((ibeg[k + 1] - ibeg[k]) * 8 + kSubBits - 1) / kSubBits);
+  L.n_sub = (int)n_sub;
   int b = 0;
   for (int c = 0; c < f.nc; c++) {
     const Comp& k = f.comp[c];
@@ -833,6 +893,7 @@ static int entropy_decode_device(ofb_handle* h, JpegState* s, const Frame& f) {
     }
   }
   L.bpm = b;
+  L.dri_blocks = f.dri * b;
   size_t n_dc = 0;
   for (int c = 0; c < f.nc; c++) { L.dc_off[c] = n_dc; n_dc += (size_t)f.mcux * f.mcuy * f.comp[c].h * f.comp[c].v; }
   if (n_dc > s->dc_cap) {
@@ -851,7 +912,35 @@ static int entropy_decode_device(ofb_handle* h, JpegState* s, const Frame& f) {
     OFB_CUDA(h, cudaMalloc(&s->d_exit, cap * sizeof(unsigned long long)));
     OFB_CUDA(h, cudaMalloc(&s->d_counts, cap * sizeof(int)));
     OFB_CUDA(h, cudaMalloc(&s->d_first, cap * sizeof(int)));
+    cudaFree(s->d_subtab); cudaFree(s->d_excl);
+    if (s->h_subtab) cudaFreeHost(s->h_subtab);
+    s->d_subtab = nullptr; s->d_excl = nullptr; s->h_subtab = nullptr;
+    OFB_CUDA(h, cudaMalloc(&s->d_subtab, 4 * cap * sizeof(uint32_t)));
+    OFB_CUDA(h, cudaMalloc(&s->d_excl, cap * sizeof(int)));
+    OFB_CUDA(h, cudaHostAlloc(&s->h_subtab, 4 * cap * sizeof(uint32_t), cudaHostAllocDefault));
     s->sub_cap = cap;
+  }
+  {
+    uint32_t* t0 = s->h_subtab;
+    uint32_t* t1 = t0 + s->sub_cap;
+    int* t2 = reinterpret_cast<int*>(t1 + s->sub_cap);
+    int* t3 = t2 + s->sub_cap;
+    size_t i = 0;
+    for (int k = 0; k < n_int; k++) {
+      const uint32_t b0 = (uint32_t)(ibeg[k] * 8), b1 = (uint32_t)(ibeg[k + 1] * 8);
+      const size_t m = std::max<size_t>(1, ((size_t)(b1 - b0) + kSubBits - 1) / kSubBits), head = i;
+      for (size_t q = 0; q < m; q++, i++) {
+        t0[i] = b0 + (uint32_t)(q * kSubBits);
+        t1[i] = std::min(b0 + (uint32_t)((q + 1) * kSubBits), b1);
+        t2[i] = q == 0 ? k * (f.dri ? f.dri : 0) * L.bpm : -1;
+        t3[i] = (int)head;
+      }
+    }
+    OFB_CUDA(h, cudaMemcpyAsync(s->d_subtab, s->h_subtab, 4 * s->sub_cap * sizeof(uint32_t), cudaMemcpyHostToDevice, sm));
+    L.sub_start = s->d_subtab;
+    L.sub_end = s->d_subtab + s->sub_cap;
+    L.sub_head_block = reinterpret_cast<const int*>(s->d_subtab + 2 * s->sub_cap);
+    L.sub_headidx = reinterpret_cast<const int*>(s->d_subtab + 3 * s->sub_cap);
   }
   int st;
   if ((st = timing_begin(h, OFB_STAGE_OTHER))) return st;
@@ -877,11 +966,14 @@ static int entropy_decode_device(ofb_handle* h, JpegState* s, const Frame& f) {
     OFB_LAUNCH_CHECK(h);
     round++;
   }
-  k_huff_scan<<<1, 1024, 0, sm>>>(s->d_counts, s->d_first, L.n_sub);
+  k_huff_scan<<<1, 1024, 0, sm>>>(s->d_counts, s->d_excl, L.n_sub);
+  OFB_LAUNCH_CHECK(h);
+  k_huff_rebase<<<(L.n_sub + 255) / 256, 256, 0, sm>>>(L, s->d_excl, s->d_first);
   OFB_LAUNCH_CHECK(h);
   k_huff_write<<<ctas, kSyncThreads, 0, sm>>>(L, s->d_exit, s->d_first, s->d_coef, s->d_dc);
   OFB_LAUNCH_CHECK(h);
-  k_dc_prefix<<<f.nc, 1024, 0, sm>>>(L, s->d_dc, f.mcux * f.mcuy);
+  if (f.dri) k_dc_prefix_intervals<<<(n_int * f.nc * 32 + 255) / 256, 256, 0, sm>>>(L, s->d_dc, n_mcu, f.dri, n_int, f.nc);
+  else k_dc_prefix<<<f.nc, 1024, 0, sm>>>(L, s->d_dc, n_mcu);
   OFB_LAUNCH_CHECK(h);
   return timing_end(h);
 }
@@ -914,13 +1006,13 @@ static int jpeg_decode_device(ofb_handle* h, const Frame& f, uint8_t* d_bgr, siz
     OFB_CUDA(h, cudaMalloc(&s->d_planes, plane_bytes));
     s->plane_cap = plane_bytes;
   }
-  bool on_device = f.dri == 0 && f.n_data < (1u << 27) && !h->jpeg_host_entropy;
+  bool on_device = f.n_data < (1u << 27) && !h->jpeg_host_entropy;
   for (int c = 0; c < f.nc; c++) on_device = on_device && f.comp[c].td <= 1 && f.comp[c].ta <= 1;
   if (on_device) {
     int st = entropy_decode_device(h, s, f);
     if (st) return st;
   } else {
-    // restart intervals (or unusual table numbering): the host walks the stream
+    // (unusual table numbering, or asked for: the host walks the stream)
     memset(s->h_coef, 0, f.n_coef * sizeof(int16_t));
     decode_scan(f, s->h_coef);
     OFB_CUDA(h, cudaMemcpyAsync(s->d_coef, s->h_coef, f.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, sm));

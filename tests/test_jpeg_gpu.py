@@ -98,3 +98,35 @@ def test_unsupported_streams_fail_loudly(engine_factory):
     assert e.value.status == 6
     with pytest.raises(OfbError):
         eng.imdecode(b"\xff\xd8\xff\xd9")
+
+
+def test_corrupt_streams_do_not_take_the_device_down(engine_factory):
+    """Bit flips, truncation and garbage in the entropy-coded segment: the call returns a frame of the right size or an
+    OfbError — never a CUDA fault — and the next good frame still decodes bit-exactly (both entropy decoders)."""
+    from opticalflowcontainer_b200 import OfbError
+    eng = engine_factory(64, 64)
+    good = encode(jpeg_frame(120, 176, 2), "420", 85, 0)
+    ref = cv2.imdecode(good, cv2.IMREAD_COLOR)
+    rng = np.random.default_rng(11)
+    sos = good.tobytes().rfind(b"\xff\xda")
+    for host in (False, True):
+        eng.jpeg_host_entropy(host)
+        try:
+            for trial in range(24):
+                bad = good.copy()
+                if trial % 3 == 0:
+                    bad = bad[: int(rng.integers(sos + 20, bad.size - 2))]                      # truncated inside the scan
+                elif trial % 3 == 1:
+                    for k in rng.integers(sos + 14, bad.size - 2, 12):
+                        bad[k] ^= 1 << int(rng.integers(0, 8))                                   # bit flips
+                else:
+                    a = int(rng.integers(sos + 14, bad.size - 40))
+                    bad[a:a + 32] = rng.integers(0, 255, 32, dtype=np.uint8)                     # a burst of garbage
+                try:
+                    out = eng.imdecode(np.ascontiguousarray(bad))
+                    assert out.shape == ref.shape
+                except OfbError:
+                    pass
+                assert np.array_equal(eng.imdecode(good), ref)
+        finally:
+            eng.jpeg_host_entropy(False)
