@@ -203,6 +203,9 @@ int ofb_destroy(ofb_handle* h) {
   for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
+  if (h->s_px) cudaStreamDestroy(h->s_px);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < ofb::kMaxLevels; i++) if (h->ev_px[i]) cudaEventDestroy(h->ev_px[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OFB_OK;
@@ -237,7 +240,16 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     }                                                                                          \
   } while (0)
   CREATE_CUDA(cudaSetDevice(device));
-  CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    // the compute stream outranks the expansion stream: when both have CTAs waiting, the critical path (the iterations)
+    // gets the SM first and the expansions of the finer levels fill what is left
+    int least = 0, greatest = 0;
+    CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&h->s_px, cudaStreamNonBlocking, least));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < ofb::kMaxLevels; i++) CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_px[i], cudaEventDisableTiming));
+  }
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
   CREATE_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -247,6 +259,8 @@ int ofb_create(int device, int max_width, int max_height, int max_batch, ofb_han
     h->no_graph = gr && gr[0] == '0';
     const char* pch = getenv("OFB_PIPE_CHUNK");
     if (pch) h->pipe_chunk = std::max(0, atoi(pch));
+    const char* ov = getenv("OFB_OVERLAP");
+    h->no_overlap = ov && ov[0] == '0';
     const char* np = getenv("OFB_NO_PIPELINE");
     h->no_pipeline = np && np[0] == '1';
   }

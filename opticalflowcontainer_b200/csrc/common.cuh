@@ -102,6 +102,10 @@ struct ofb_handle {
   uint64_t graph_clock = 0;    // LRU stamp of the graph cache
   // host-buffer pipeline: copy-in / copy-out streams and their events (api.cu)
   cudaStream_t s_in = nullptr, s_out = nullptr;
+  // expansion stream (farneback.cu): the polynomial expansions of the finer levels run beside the coarse levels' iterations
+  cudaStream_t s_px = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_px[ofb::kMaxLevels] = {nullptr};
+  bool no_overlap = false;     // OFB_OVERLAP=0: everything on the one stream
   std::vector<cudaEvent_t> pipe_ev;
   int pipe_chunk = 0;          // OFB_PIPE_CHUNK: pairs per pipeline chunk of the host-buffer batch call (0 = auto)
   int pipe_parity = 0;         // source staging set of the last whole-batch (reduction) call

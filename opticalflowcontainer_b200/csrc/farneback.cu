@@ -643,15 +643,65 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
       img3[2] = img3[1] + (size_t)frames * n2;
     }
   }
+  // Expansions beside iterations: the coarse levels' iteration launches are small and latency-bound (a few CTAs
+  // marching a few rows), while the expansions of the finer levels depend on nothing but the level images.  In the
+  // default schedule (four regular levels, all level images from the one k_pyr_fast3 pass) the expansions of levels
+  // 1 .. 3 are launched on the handle's expansion stream right after the pyramid pass and fill the SMs the coarse
+  // iterations leave idle; the compute stream waits for a level's expansions just before that level's iterations.  The
+  // coarse levels then need expansion buffers of their own (d_MA / d_MB, unused by the fused path; the camera-stream
+  // cache has per-level buffers anyway).  Off while the stage timers run (their events assume one stream).
+  const bool overlap = !h->no_overlap && !h->timing && use_fused && fused3_li == 0 && n_levels == 4 && h->s_px != nullptr;
+  size_t coarse_off[kMaxLevels] = {0};
+  if (overlap && !sc) {
+    size_t off = 0;
+    for (int li = 0; li < n_levels - 1; li++) {
+      coarse_off[li] = off;
+      off += (size_t)frames * sched[li].width * sched[li].height + (size_t)kRowPad * sched[li].width;
+    }
+  }
+  auto level_RA = [&](int li) -> float4* {
+    if (sc) return sc->RA[sc->cur][li];
+    return (overlap && li < n_levels - 1) ? h->d_MA + coarse_off[li] : h->d_RA;
+  };
+  auto level_RB = [&](int li) -> float* {
+    if (sc) return sc->RB[sc->cur][li];
+    return (overlap && li < n_levels - 1) ? h->d_MB + coarse_off[li] : h->d_RB;
+  };
+  // marching PolyExp of level li (level image -> expansions) on stream s
+  auto launch_px = [&](int li, cudaStream_t s, const float* level_img, bool fused_src, const PyrCoef& pyc) -> int {
+    const int w = sched[li].width, hh = sched[li].height;
+    float4* const RAw = level_RA(li);
+    float* const RBw = level_RB(li);
+    const int strips = (w + PX_TW - 1) / PX_TW;
+    const int per = strips * frames;
+    const int slots = 3 * h->num_sms * kPxWaves;
+    int segs = std::max(1, slots / per);
+    int seg_rows = std::max(16, ((hh + segs - 1) / segs + PX_ROWS - 1) / PX_ROWS * PX_ROWS);
+    segs = (hh + seg_rows - 1) / seg_rows;
+    dim3 g(strips * segs, frames);
+#define OFB_PX_LAUNCH(NT)                                                                                           \
+  do {                                                                                                              \
+    if (fused_src)                                                                                                  \
+      k_polyexp_march<NT, 1><<<g, PX_COLS, 0, s>>>(nullptr, src, pyc.k[0], pyc.k[1], RAw, RBw, w, hh,               \
+                                                   seg_rows, strips, pc, 0, hh);                                    \
+    else                                                                                                            \
+      k_polyexp_march<NT, 0><<<g, PX_COLS, 0, s>>>(level_img, src, 0.f, 0.f, RAw, RBw, w, hh, seg_rows,             \
+                                                   strips, pc, 0, hh);                                              \
+  } while (0)
+    if (pc.n == 5) OFB_PX_LAUNCH(5); else if (pc.n == 7) OFB_PX_LAUNCH(7); else OFB_PX_LAUNCH(0);
+#undef OFB_PX_LAUNCH
+    OFB_LAUNCH_CHECK(h);
+    return OFB_OK;
+  };
   for (int li = 0; li < n_levels; li++) {
     const Level& lv = sched[li];
     const int w = lv.width, hh = lv.height;
     const bool last_level = li == n_levels - 1;
     const size_t npx = (size_t)w * hh;
-    float4* const RAw = sc ? sc->RA[sc->cur][li] : h->d_RA;      // where this level's expansions are written
-    float* const RBw = sc ? sc->RB[sc->cur][li] : h->d_RB;
+    float4* const RAw = level_RA(li);                            // where this level's expansions are written
+    float* const RBw = level_RB(li);
     const RSet rs = sc ? RSet{sc->RA[sc->cur ^ 1][li], sc->RB[sc->cur ^ 1][li], RAw, RBw}
-                       : RSet{h->d_RA, h->d_RB, h->d_RA + (size_t)f1_offset * npx, h->d_RB + (size_t)f1_offset * npx};
+                       : RSet{RAw, RBw, RAw + (size_t)f1_offset * npx, RBw + (size_t)f1_offset * npx};
     const bool prime_only = sc && sc->prime_only;
     // flow buffers: cur (input of this level) must differ from the buffer holding the previous
     // level's result (read by the upsample); alt may alias it (first written after the upsample).
@@ -752,26 +802,27 @@ static int farneback_run_impl(ofb_handle* h, int n_pairs, bool sequence, const u
       TE();
     }
     TB(OFB_STAGE_POLYEXP);
-    if (march) {
-      const int strips = (w + PX_TW - 1) / PX_TW;
-      const int per = strips * frames;
-      const int slots = 3 * h->num_sms * kPxWaves;
-      int segs = std::max(1, slots / per);
-      int seg_rows = std::max(16, ((hh + segs - 1) / segs + PX_ROWS - 1) / PX_ROWS * PX_ROWS);
-      segs = (hh + seg_rows - 1) / seg_rows;
-      dim3 g(strips * segs, frames);
-#define OFB_PX_LAUNCH(NT)                                                                                           \
-  do {                                                                                                              \
-    if (fused_src)                                                                                                  \
-      k_polyexp_march<NT, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], RAw, RBw, w, hh,              \
-                                                    seg_rows, strips, pc, 0, hh);                                   \
-    else                                                                                                            \
-      k_polyexp_march<NT, 0><<<g, PX_COLS, 0, st>>>(level_img, src, 0.f, 0.f, RAw, RBw, w, hh, seg_rows,            \
-                                                    strips, pc, 0, hh);                                             \
-  } while (0)
-      if (pc.n == 5) OFB_PX_LAUNCH(5); else if (pc.n == 7) OFB_PX_LAUNCH(7); else OFB_PX_LAUNCH(0);
-#undef OFB_PX_LAUNCH
-      OFB_LAUNCH_CHECK(h);
+    if (march && overlap) {
+      if (li == 0) {
+        // fork: the finer levels' expansions on the expansion stream, behind the pyramid pass
+        OFB_CUDA(h, cudaEventRecord(h->ev_fork, st));
+        OFB_CUDA(h, cudaStreamWaitEvent(h->s_px, h->ev_fork, 0));
+        for (int l = 1; l < n_levels; l++) {
+          PyrCoef pl;
+          if (prepare_pyr(sched[l].ksize, sched[l].sigma, &pl) != OFB_OK) return set_error(h, OFB_ERR_INVALID_ARG, "pyramid smoothing kernel too large");
+          const bool fsrc = l == n_levels - 1;
+          int s__ = launch_px(l, h->s_px, fsrc ? nullptr : img3[n_levels - 2 - l], fsrc, pl);
+          if (s__) return s__;
+          OFB_CUDA(h, cudaEventRecord(h->ev_px[l], h->s_px));
+        }
+        int s__ = launch_px(0, st, level_img, false, pyc);
+        if (s__) return s__;
+      } else {
+        OFB_CUDA(h, cudaStreamWaitEvent(st, h->ev_px[li], 0));   // join: this level's expansions are complete
+      }
+    } else if (march) {
+      int s__ = launch_px(li, st, level_img, fused_src, pyc);
+      if (s__) return s__;
     } else {
       dim3 g((w + PE_T - 1) / PE_T, (hh + PE_T - 1) / PE_T, frames);
       if (pc.n == 5) k_polyexp<5><<<g, blk, 0, st>>>(h->d_img, h->d_RA, h->d_RB, w, hh, pc);
