@@ -10,6 +10,12 @@ mean for the smooth topic, and a ``Vector3Stamped{stamp = image stamp, frame_id 
 vector = (vx, 0, 0)}``.  ``FarnebackVelocityNode`` is that logic with the flow call swapped for
 the B200 engine; messages are plain dataclasses so the class runs (and is tested) without ROS.
 ``examples/farneback_sub_node.py`` shows the same class wired to rclpy.
+
+``FarnebackVelocityNode.compressed_callback`` is the same for ``sensor_msgs/CompressedImage`` (JPEG) frames
+(``ros2_ws/src/optical_flow/optical_flow/opticalflow_comprerssed_node.py:41-62``: ``cv2.imdecode`` first), and
+``JunctionDetectorNode`` mirrors the C++ detector node (``ros2_ws/src/junction_point_detector/src/fishnet_detector_ros.cpp:30-80``:
+``dampenIntensity(img, -20, 15)``, ``find_junctions_not_rotated(img, 200, 2.0, false, 6)``, a ``PointCloud`` with z = 0,
+nothing published for fewer than 4 junctions).
 """
 from __future__ import annotations
 
@@ -19,6 +25,7 @@ from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
+from ._lib import OfbError
 from .engine import FlowEngine
 
 
@@ -91,6 +98,20 @@ class FarnebackVelocityNode:
             gray = to_gray_u8(image, encoding)
             if gray.shape != (self.height, self.width):
                 gray = self.engine.resize(gray, (self.width, self.height))
+        return self._on_gray(gray, stamp, mask)
+
+    def compressed_callback(self, data, stamp: float, mask: Optional[np.ndarray] = None):
+        """One ``sensor_msgs/CompressedImage`` (JPEG bytes) in → the same messages: ``cv2.imdecode(..., IMREAD_COLOR)``
+        (opticalflow_comprerssed_node.py:43-46), resize to the configured size and gray conversion on the device, bit-exact
+        with cv2; only the compressed bytes go up and the gray frame comes back.  A stream that cannot be decoded returns
+        None, as the node logs and returns when ``cv2.imdecode`` gives None."""
+        try:
+            gray = self.engine.ingest_jpeg_gray(data, (self.width, self.height))
+        except OfbError:
+            return None
+        return self._on_gray(gray, stamp, mask)
+
+    def _on_gray(self, gray: np.ndarray, stamp: float, mask: Optional[np.ndarray]):
         if self.prev_gray is None:
             self.prev_gray, self.prev_time = gray, stamp
             return None
@@ -131,6 +152,40 @@ class FarnebackVelocityNode:
         self.prev_gray = gray
         return (Vector3Stamped(stamp, "camera_link", (vx, 0.0, 0.0)),
                 Vector3Stamped(stamp, "camera_link", (vx_smooth, 0.0, 0.0)))
+
+
+@dataclass
+class PointCloud:
+    """sensor_msgs/PointCloud look-alike: points [n, 3] float32 (x, y, 0)."""
+    stamp: float
+    frame_id: str
+    points: np.ndarray
+
+
+@dataclass
+class JunctionDetectorNode:
+    """The junction detector node (fishnet_detector_ros.cpp:30-80) on the B200 engine.  The C++ node converts the message
+    to rgb8 and hands that buffer to functions written for BGR; the bytes are taken here exactly as the node passes them."""
+    grid_area: int = 200
+    grid_area_threshold: float = 2.0
+    eps: int = 6
+    dampen: Optional[Tuple[float, float]] = (-20.0, 15.0)
+    device: int = 0
+    engine: Optional[FlowEngine] = None
+
+    def __post_init__(self):
+        if self.engine is None:
+            self.engine = FlowEngine(64, 64, 1, self.device)
+
+    def image_callback(self, image: np.ndarray, stamp: float, frame_id: str = "camera_link") -> Optional[PointCloud]:
+        image = np.asarray(image)
+        pts = self.engine.find_junctions(image, self.grid_area, self.grid_area_threshold, self.eps,
+                                         dampen=self.dampen if image.ndim == 3 else None)
+        if len(pts) < 4:
+            return None                                   # "No junctions found": nothing is published
+        cloud = np.zeros((len(pts), 3), np.float32)
+        cloud[:, :2] = pts
+        return PointCloud(stamp, frame_id, cloud)
 
 
 def junction_mask(points: Sequence[Sequence[float]], height: int, width: int, radius: int = 5) -> np.ndarray:

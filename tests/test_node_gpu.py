@@ -375,3 +375,44 @@ def test_bilateral_filter(engine_factory, size, d, sc, ss):
     ref = cv2.bilateralFilter(img, d, sc, ss)
     diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
     assert diff.max() <= 1 and (diff > 0).mean() <= 1e-4, (diff.max(), (diff > 0).mean())
+
+
+def test_compressed_callback_equals_image_callback_on_decoded_frames(built_lib):
+    """CompressedImage (JPEG) frames through the node contract: same velocities as feeding cv2.imdecode's frames to
+    image_callback (opticalflow_comprerssed_node.py:41-62)."""
+    import cv2
+    from opticalflowcontainer_b200.node import FarnebackVelocityNode
+    from oracle import synth
+    frames = [synth.synth_pair(240, 320, 3 + i, (1.5 + i, -0.5))[0] for i in range(3)]
+    jpgs = [cv2.imencode(".jpg", cv2.cvtColor(f, cv2.COLOR_GRAY2BGR), [cv2.IMWRITE_JPEG_QUALITY, 90])[1] for f in frames]
+    a = FarnebackVelocityNode(width=320, height=240)
+    b = FarnebackVelocityNode(width=320, height=240, engine=a.engine)
+    try:
+        for i, j in enumerate(jpgs):
+            ra = a.compressed_callback(j.tobytes(), 0.1 * i)
+            rb = b.image_callback(cv2.imdecode(j, cv2.IMREAD_COLOR), 0.1 * i)
+            assert (ra is None) == (rb is None)
+            if ra is not None:
+                assert ra[0].vector == rb[0].vector and ra[1].vector == rb[1].vector
+        assert a.compressed_callback(b"garbage", 1.0) is None
+    finally:
+        a.engine.close()
+
+
+def test_junction_detector_node_contract(built_lib):
+    """fishnet_detector_ros.cpp:30-80: dampenIntensity(-20, 15) + find_junctions_not_rotated(200, 2.0, false, 6) -> a
+    PointCloud with z = 0; nothing for fewer than 4 junctions."""
+    import cv2
+    from opticalflowcontainer_b200.node import JunctionDetectorNode
+    from oracle import junction_np as J
+    from oracle import synth
+    node = JunctionDetectorNode()
+    try:
+        img = synth.synth_net(240, 320, 6)
+        msg = node.image_callback(img, 12.5, "cam")
+        want = J.find_junctions(J.dampen_intensity(img, -20, 15), 200, 2.0, 6)
+        assert msg is not None and msg.stamp == 12.5 and msg.frame_id == "cam"
+        assert np.array_equal(msg.points[:, :2], want) and not msg.points[:, 2].any()
+        assert node.image_callback(np.full((120, 160, 3), 90, np.uint8), 13.0) is None
+    finally:
+        node.engine.close()
