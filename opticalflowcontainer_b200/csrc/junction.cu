@@ -258,16 +258,25 @@ struct KdNode {
 // while mindist * (1 + eps) <= radius^2 — the result depends on the tree, so the tree is built the same way.
 struct KdTree {
   const std::vector<float>& px;        // x0 y0 x1 y1 ...
-  std::vector<int> acc;
+  std::vector<int> acc;                // nanoflann's vAcc_: tree order -> point index
+  std::vector<float> perm;             // the points in tree order (kept in step with acc: the build and the leaf scans
+                                       // then stream memory instead of chasing indices; same comparisons, same result)
   std::vector<KdNode> nodes;
   float root_lo[2], root_hi[2];
   int leaf_max;
-  float at(int i, int d) const { return px[2 * acc[i] + d]; }
+  float at(int i, int d) const { return perm[2 * i + d]; }
+  void swap_pts(int a, int b) {
+    std::swap(acc[a], acc[b]);
+    std::swap(perm[2 * a], perm[2 * b]);
+    std::swap(perm[2 * a + 1], perm[2 * b + 1]);
+  }
 
   KdTree(const std::vector<float>& pts, int leaf) : px(pts), leaf_max(leaf) {
     const int n = (int)pts.size() / 2;
     acc.resize(n);
     for (int i = 0; i < n; i++) acc[i] = i;
+    perm = pts;
+    nodes.reserve((size_t)n / 2 + 16);
     float lo[2] = {pts[0], pts[1]}, hi[2] = {pts[0], pts[1]};
     for (int i = 1; i < n; i++)
       for (int d = 0; d < 2; d++) { lo[d] = std::min(lo[d], pts[2 * i + d]); hi[d] = std::max(hi[d], pts[2 * i + d]); }
@@ -331,7 +340,7 @@ struct KdTree {
       while (left <= right && at(ind + left, feat) < cutval) ++left;
       while (right && left <= right && at(ind + right, feat) >= cutval) --right;
       if (left > right || !right) break;
-      std::swap(acc[ind + left], acc[ind + right]);
+      swap_pts(ind + left, ind + right);
       ++left; --right;
     }
     *lim1 = left;
@@ -340,7 +349,7 @@ struct KdTree {
       while (left <= right && at(ind + left, feat) <= cutval) ++left;
       while (right && left <= right && at(ind + right, feat) > cutval) --right;
       if (left > right || !right) break;
-      std::swap(acc[ind + left], acc[ind + right]);
+      swap_pts(ind + left, ind + right);
       ++left; --right;
     }
     *lim2 = left;
@@ -350,12 +359,11 @@ struct KdTree {
     const KdNode& nd = nodes[node];
     if (nd.child1 < 0) {
       for (int i = nd.left; i < nd.right; i++) {
-        const int j = acc[i];
-        const float d0 = q[0] - px[2 * j], d1 = q[1] - px[2 * j + 1];
+        const float d0 = q[0] - perm[2 * i], d1 = q[1] - perm[2 * i + 1];
         float dist = 0;
         dist += d0 * d0;
         dist += d1 * d1;
-        if (dist < radius2) out->push_back(j);
+        if (dist < radius2) out->push_back(acc[i]);
       }
       return;
     }
