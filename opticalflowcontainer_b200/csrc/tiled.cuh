@@ -89,8 +89,10 @@ static inline const float* tiled_RB(const ofb_handle* h, const TiledPlan& pl, in
   return li == pl.n_levels - 1 ? (const float*)h->tile.peer_RB[r] : (const float*)h->tile.peer_MB[r] + pl.r_off[li];
 }
 
-// One stage of one rank.  kind 0 = pyramid + PolyExp of the band of level li; kind 1 = iteration `it`.
-static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int it) {
+// One stage of one rank.  kind 0 = pyramid + PolyExp of the band of level li; kind 1 = iteration `it`; kind 2 = the
+// pyramid part of kind 0 only, kind 3 = its PolyExp part only, on stream `px_stream` (the two-stream schedule of
+// farneback_run_tiled).
+static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int it, cudaStream_t px_stream = nullptr) {
   const int world = h->tile.world, rank = h->tile.rank;
   const Level& lv = pl.sched[li];
   const int w = lv.width, hh = lv.height;
@@ -101,7 +103,9 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
   float4* const RA = const_cast<float4*>(tiled_RA(h, pl, li, rank));
   float* const RB = const_cast<float*>(tiled_RB(h, pl, li, rank));
 
-  if (kind == 0) {
+  if (kind == 0 || kind == 2 || kind == 3) {
+    const bool do_pyr = kind != 3, do_px = kind != 2;
+    cudaStream_t sp = (kind == 3 && px_stream) ? px_stream : st;
     const int yb = pl.r_lo[li], ye = pl.r_hi[li];
     // ---- pyramid + PolyExp of the band (local: every rank has the source frames)
     PyrCoef pyc;
@@ -119,7 +123,7 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
     const bool in_fused3 = pl.fused3_li >= 0 && li >= pl.fused3_li && li < pl.n_levels - 1;
     if (in_fused3) {
       level_img = h->d_img + pl.img3_off[pl.n_levels - 2 - li];
-      if (li == pl.fused3_li) {
+      if (li == pl.fused3_li && do_pyr) {
         TB(OFB_STAGE_PYRAMID);
         constexpr int out3 = (PF_COLS - 2 * PF_HALO) / 8;
         const int chunks = (pl.width / 8 + out3 - 1) / out3, rows = pl.y3_hi - pl.y3_lo;
@@ -131,7 +135,7 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
         OFB_LAUNCH_CHECK(h);
         TE();
       }
-    } else if (!fused_src) {
+    } else if (!fused_src && do_pyr) {
       const int lb = std::max(yb - pl.pc.n, 0), le = std::min(ye + pl.pc.n, hh);   // level rows PolyExp reads
       const double sy = 1.0 / ((double)hh / pl.height);
       const int sb = std::max(lin_entry(lb, sy, pl.height).i0 - pyc.r - 1, 0);
@@ -154,6 +158,7 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
 #undef OFB_PYR_LAUNCH
       TE();
     }
+    if (!do_px) return OFB_OK;
     TB(OFB_STAGE_POLYEXP);
     {
       const int strips = (w + PX_TW - 1) / PX_TW;
@@ -165,16 +170,16 @@ static int tiled_stage(ofb_handle* h, const TiledPlan& pl, int li, int kind, int
       dim3 g(strips * segs, frames);
       if (fused_src) {
         if (pl.pc.n == 5)
-          k_polyexp_march<5, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], RA, RB, w, hh, seg_rows, strips,
+          k_polyexp_march<5, 1><<<g, PX_COLS, 0, sp>>>(nullptr, src, pyc.k[0], pyc.k[1], RA, RB, w, hh, seg_rows, strips,
                                                        pl.pc, yb, ye);
         else
-          k_polyexp_march<0, 1><<<g, PX_COLS, 0, st>>>(nullptr, src, pyc.k[0], pyc.k[1], RA, RB, w, hh, seg_rows, strips,
+          k_polyexp_march<0, 1><<<g, PX_COLS, 0, sp>>>(nullptr, src, pyc.k[0], pyc.k[1], RA, RB, w, hh, seg_rows, strips,
                                                        pl.pc, yb, ye);
       } else {
         if (pl.pc.n == 5)
-          k_polyexp_march<5, 0><<<g, PX_COLS, 0, st>>>(level_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
+          k_polyexp_march<5, 0><<<g, PX_COLS, 0, sp>>>(level_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
         else
-          k_polyexp_march<0, 0><<<g, PX_COLS, 0, st>>>(level_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
+          k_polyexp_march<0, 0><<<g, PX_COLS, 0, sp>>>(level_img, src, 0.f, 0.f, RA, RB, w, hh, seg_rows, strips, pl.pc, yb, ye);
       }
       OFB_LAUNCH_CHECK(h);
     }
@@ -347,14 +352,33 @@ int farneback_run_tiled(ofb_handle* h, const uint8_t* d_prev, const uint8_t* d_n
   TiledPlan pl;
   int st = tiled_make_plan(h, &pl, d_prev, d_next, width, height, pitch, d_flow_out, p);
   if (st) return st;
-  if (pl.n_levels == 1) {
-    // a single level re-uses its expansion buffer from pair to pair: nobody may still be gathering from it
-    st = tiled_barrier(h);
-    if (st) return st;
+  // Everybody has finished the previous pair: with the two-stream schedule below a rank writes the expansions of every
+  // level right after its pyramid pass — a peer that is still iterating on the previous pair may be gathering from those
+  // buffers.  (Taken on every call, whatever the schedule, so that the ranks' barrier epochs can never drift apart.)
+  st = tiled_barrier(h);
+  if (st) return st;
+  // Two-stream schedule (as the whole-frame driver): all level images come from the one k_pyr_fast3 pass, every level
+  // has expansion buffers of its own, and the coarse levels' iteration launches are a few CTAs marching a few rows — so
+  // the expansions of ALL levels go to the expansion stream right behind the pyramid pass and run beside the coarse
+  // iterations; the compute stream waits for a level's expansions, passes the level's flag barrier, iterates.
+  const bool overlap = !h->no_overlap && !h->timing && h->s_px && pl.fused3_li == 0 && pl.n_levels == 4;
+  if (overlap) {
+    for (int li = 0; li < pl.n_levels; li++)
+      if ((st = tiled_stage(h, pl, li, 2, 0))) return st;
+    OFB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    OFB_CUDA(h, cudaStreamWaitEvent(h->s_px, h->ev_fork, 0));
+    for (int li = 0; li < pl.n_levels; li++) {
+      if ((st = tiled_stage(h, pl, li, 3, 0, h->s_px))) return st;
+      OFB_CUDA(h, cudaEventRecord(h->ev_px[li], h->s_px));
+    }
   }
   for (int li = 0; li < pl.n_levels; li++) {
-    st = tiled_stage(h, pl, li, 0, 0);
-    if (st) return st;
+    if (overlap) {
+      OFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_px[li], 0));
+    } else {
+      st = tiled_stage(h, pl, li, 0, 0);
+      if (st) return st;
+    }
     st = tiled_barrier(h);
     if (st) return st;
     for (int it = 0; it < p->iterations; it++) {
