@@ -325,6 +325,9 @@ int ofb_jpeg_set_host_entropy(ofb_handle* h, int on);
  * cv2.cvtColor(that, COLOR_BGR2GRAY); either may be NULL, strides 0 = packed.  Synchronous. */
 int ofb_jpeg_decode(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* bgr, size_t bgr_stride_bytes, uint8_t* gray,
                     size_t gray_stride_bytes);
+/* gray: host uint8 [height][width] = cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE): the luma plane as libjpeg delivers it
+ * (no colour conversion; differs from cvtColor(BGR2GRAY) of the colour decode by rounding).  Synchronous. */
+int ofb_jpeg_decode_luma(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* gray, size_t gray_stride_bytes);
 /* ofb_ingest_gray for a compressed frame: decode, cv2.resize of the colour frame to dst_width x dst_height if it has
  * another size, cv2.cvtColor(BGR2GRAY); only the gray frame crosses PCIe back.  Synchronous. */
 int ofb_ingest_jpeg_gray(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* dst, int dst_width, int dst_height,

@@ -20,7 +20,10 @@ from .engine import (FlowEngine, OPTFLOW_FARNEBACK_GAUSSIAN, OPTFLOW_LK_GET_MIN_
 
 __all__ = ["FlowEngine", "OfbError", "calcOpticalFlowFarneback", "calcOpticalFlowPyrLK", "goodFeaturesToTrack",
            "buildOpticalFlowPyramid", "cornerMinEigenVal", "OPTFLOW_USE_INITIAL_FLOW", "OPTFLOW_FARNEBACK_GAUSSIAN",
-           "OPTFLOW_LK_GET_MIN_EIGENVALS", "set_device"]
+           "OPTFLOW_LK_GET_MIN_EIGENVALS", "set_device", "imdecode", "find_junctions", "IMREAD_GRAYSCALE", "IMREAD_COLOR"]
+
+IMREAD_GRAYSCALE = 0   # cv2.IMREAD_GRAYSCALE
+IMREAD_COLOR = 1       # cv2.IMREAD_COLOR
 
 _engines = {}
 _engines_lock = threading.Lock()
@@ -48,6 +51,27 @@ def calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, itera
     prev = np.asarray(prev)
     return _engine_for(prev.shape[0], prev.shape[1]).farneback(prev, next, flow, pyr_scale, levels, winsize,
                                                                iterations, poly_n, poly_sigma, flags)
+
+
+def imdecode(buf, flags=IMREAD_COLOR):
+    """Drop-in for ``cv2.imdecode(buf, flags)`` on baseline JPEG streams (the compressed-image node,
+    opticalflow_comprerssed_node.py:43-46): ``IMREAD_COLOR`` -> uint8 [H,W,3] BGR, ``IMREAD_GRAYSCALE`` -> uint8 [H,W].
+    Returns None — as cv2 does — for a stream the device path does not decode."""
+    if flags not in (IMREAD_COLOR, IMREAD_GRAYSCALE):
+        raise OfbError(1, "imdecode: flags must be IMREAD_COLOR or IMREAD_GRAYSCALE")
+    eng = _engine_for(64, 64)
+    try:
+        return eng.imdecode(buf) if flags == IMREAD_COLOR else eng.imdecode_grayscale(buf)
+    except OfbError as e:
+        if e.status == 6:
+            return None
+        raise
+
+
+def find_junctions(img, grid_area=250, grid_area_threshold=2.0, eps=4, dampen=None):
+    """``find_junctions_not_rotated(img, grid_area, grid_area_threshold, false, eps)`` of the reference's junction detector
+    (junction_detector.cpp:31-214; ``dampen=(min, max)``: ``dampenIntensity`` first) -> float32 [n, 2] junction centres."""
+    return _engine_for(64, 64).find_junctions(img, grid_area, grid_area_threshold, eps, dampen=dampen)
 
 
 def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None, blockSize=3,

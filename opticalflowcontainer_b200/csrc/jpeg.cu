@@ -981,7 +981,8 @@ static int entropy_decode_device(ofb_handle* h, JpegState* s, const Frame& f) {
 // Decodes `jpeg` into device frames on the handle's stream: d_bgr ([height][width][3], pitch bgr_pitch) and/or d_gray.
 // Returns after the launches are enqueued; the pinned coefficient staging is reused by the next call, which
 // synchronises first.
-static int jpeg_decode_device(ofb_handle* h, const Frame& f, uint8_t* d_bgr, size_t bgr_pitch, uint8_t* d_gray, size_t gray_pitch) {
+static int jpeg_decode_device(ofb_handle* h, const Frame& f, uint8_t* d_bgr, size_t bgr_pitch, uint8_t* d_gray, size_t gray_pitch,
+                              bool luma_only = false) {
   if (!h->jpeg) h->jpeg = new JpegState();
   JpegState* s = static_cast<JpegState*>(h->jpeg);
   cudaStream_t sm = h->stream;
@@ -1045,8 +1046,8 @@ static int jpeg_decode_device(ofb_handle* h, const Frame& f, uint8_t* d_bgr, siz
   ca.Y = s->d_planes + plane_off[0];
   ca.y_pitch = pitch[0];
   ca.w = f.width; ca.h = f.height;
-  ca.gray_only_source = f.nc == 1;
-  if (f.nc == 3) {
+  ca.gray_only_source = f.nc == 1 || luma_only;   // (B = G = R = Y: the gray weights add up to 2^15, so gray == Y)
+  if (f.nc == 3 && !luma_only) {
     ca.Cb = s->d_planes + plane_off[1];
     ca.Cr = s->d_planes + plane_off[2];
     ca.c_pitch = pitch[1];
@@ -1125,6 +1126,26 @@ int ofb_jpeg_decode(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t*
   if (st) return st;
   if (bgr) OFB_CUDA(h, cudaMemcpy2DAsync(bgr, bgr_stride_bytes, g.d_a, row3, row3, hh, cudaMemcpyDeviceToHost, h->stream));
   if (gray) OFB_CUDA(h, cudaMemcpy2DAsync(gray, gray_stride_bytes, g.d_b, gpitch, w, hh, cudaMemcpyDeviceToHost, h->stream));
+  OFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return OFB_OK;
+}
+
+int ofb_jpeg_decode_luma(ofb_handle* h, const uint8_t* jpeg, size_t n_bytes, uint8_t* gray, size_t gray_stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!jpeg || !gray) return set_error(h, OFB_ERR_INVALID_ARG, "NULL pointer");
+  Frame* fp = new Frame();
+  const char* why = parse_jpeg(jpeg, n_bytes, fp, false);
+  if (why) { delete fp; return set_error(h, OFB_ERR_UNSUPPORTED, "JPEG: %s", why); }
+  const int w = fp->width, hh = fp->height;
+  const size_t gpitch = ((size_t)w + 15) & ~(size_t)15;
+  if (gray_stride_bytes == 0) gray_stride_bytes = (size_t)w;
+  int st = gray_stride_bytes < (size_t)w ? set_error(h, OFB_ERR_INVALID_ARG, "stride smaller than a row") : OFB_OK;
+  if (!st && cudaSetDevice(h->device) != cudaSuccess) st = set_error(h, OFB_ERR_CUDA, "cudaSetDevice failed");
+  if (!st) st = ingest_reserve(h, 0, gpitch * hh);
+  if (!st) st = jpeg_decode_device(h, *fp, nullptr, 0, h->ingest.d_b, gpitch, true);
+  delete fp;
+  if (st) return st;
+  OFB_CUDA(h, cudaMemcpy2DAsync(gray, gray_stride_bytes, h->ingest.d_b, gpitch, w, hh, cudaMemcpyDeviceToHost, h->stream));
   OFB_CUDA(h, cudaStreamSynchronize(h->stream));
   return OFB_OK;
 }

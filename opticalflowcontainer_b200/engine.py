@@ -416,6 +416,15 @@ class FlowEngine:
         intervals); same result."""
         _lib.check(self._lib.ofb_jpeg_set_host_entropy(self._h, 1 if on else 0), self._h)
 
+    def imdecode_grayscale(self, buf) -> np.ndarray:
+        """``cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE)`` of a baseline JPEG: the luma plane, uint8 [H,W]."""
+        buf = self._jpeg_bytes(buf)
+        w, h, _ = self.jpeg_info(buf)
+        out = np.empty((h, w), np.uint8)
+        with self._lock:
+            _lib.check(self._lib.ofb_jpeg_decode_luma(self._h, buf.ctypes.data, buf.size, out.ctypes.data, 0), self._h)
+        return out
+
     def imdecode(self, buf, gray: bool = False) -> np.ndarray:
         """``cv2.imdecode(buf, cv2.IMREAD_COLOR)`` of a baseline JPEG (``sensor_msgs/CompressedImage.data``; the
         compressed-image node, opticalflow_comprerssed_node.py:43-46): uint8 [H,W,3] BGR, bit-exact with the wheel's

@@ -53,6 +53,19 @@ def test_device_entropy_on_smooth_and_flat_frames(engine_factory):
             assert np.array_equal(eng.imdecode(buf), cv2.imdecode(buf, cv2.IMREAD_COLOR))
 
 
+def test_module_level_imdecode_color_and_grayscale(built_lib):
+    """cv2.imdecode's two flags the nodes could pass; None for an undecodable stream, like cv2."""
+    import opticalflowcontainer_b200 as ofb
+    for (h, w), samp in (((97, 131), "420"), ((64, 80), "444"), ((50, 66), "422")):
+        buf = encode(jpeg_frame(h, w, h), samp, 88, 0)
+        assert np.array_equal(ofb.imdecode(buf, ofb.IMREAD_COLOR), cv2.imdecode(buf, cv2.IMREAD_COLOR))
+        assert np.array_equal(ofb.imdecode(buf, ofb.IMREAD_GRAYSCALE), cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE))
+    g = encode(jpeg_frame(40, 56, 3, channels=1), quality=80)
+    assert np.array_equal(ofb.imdecode(g, ofb.IMREAD_GRAYSCALE), cv2.imdecode(g, cv2.IMREAD_GRAYSCALE))
+    ok, prog = cv2.imencode(".jpg", jpeg_frame(32, 32, 1), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    assert ofb.imdecode(prog) is None
+
+
 def test_gray_jpeg_and_repeated_calls(engine_factory):
     eng = engine_factory(64, 64)
     for seed, (h, w) in enumerate([(40, 56), (200, 312), (33, 35)]):      # staging grows and is reused
