@@ -275,6 +275,11 @@ int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stri
  * field `pair` of the handle's current result, computed on the device, bit-exact against the cv2 recipe.
  * bgr_out: host uint8 [height][width][3] (stride_bytes = 0: packed rows).  Synchronous. */
 int ofb_flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes);
+/* The sub node's dense view (ros2_ws/src/liteflownet3/liteflownet3/lfn3_sub_node.py:244-262): hue = uint8(ang * 90 / pi),
+ * saturation 255, value = uint8(clip(mag / dt * pixel_to_meter / max_speed, 0, 1) * 255) -> HSV2BGR; float32 arithmetic
+ * in NumPy's evaluation order, bit-exact against the recipe (oracle/visual_np.py::flow_to_color_speed).  Synchronous. */
+int ofb_flow_to_bgr_speed(ofb_handle* h, int pair, double dt, double pixel_to_meter, double max_speed, uint8_t* bgr_out,
+                          size_t stride_bytes);
 /* Flow of pair `pair` of the handle's current field at n integer pixel positions xy = [n][2] (x, y): out_dxdy =
  * [n][2] float32 (dx, dy), NaN for positions outside the frame.  The junction node's lookup of the predicted
  * junction positions (ros2_ws/src/liteflownet3/liteflownet3/lfn3_junction_node.py:207-214) without downloading the

@@ -75,6 +75,7 @@ _SIGNATURES = {
     "ofb_flow_postfilter": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
     "ofb_flow_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ofb_flow_to_bgr": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "ofb_flow_to_bgr_speed": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_size_t]),
     "ofb_flow_download": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]),
     "ofb_farneback_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
                                        C.c_size_t, C.c_void_p, C.POINTER(FarnebackParams)]),

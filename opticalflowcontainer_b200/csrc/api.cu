@@ -853,6 +853,13 @@ int ofb_flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_byt
   return flow_to_bgr(h, pair, bgr_out, stride_bytes);
 }
 
+int ofb_flow_to_bgr_speed(ofb_handle* h, int pair, double dt, double pixel_to_meter, double max_speed, uint8_t* bgr_out,
+                          size_t stride_bytes) {
+  if (!h) return OFB_ERR_INVALID_ARG;
+  if (!(dt > 0) || !(max_speed > 0)) return set_error(h, OFB_ERR_INVALID_ARG, "dt and max_speed must be positive");
+  return flow_to_bgr(h, pair, bgr_out, stride_bytes, 1, (float)dt, (float)pixel_to_meter, (float)max_speed);
+}
+
 int ofb_flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes) {
   if (!h) return OFB_ERR_INVALID_ARG;
   return flow_download(h, n, flow, flow_stride_bytes);

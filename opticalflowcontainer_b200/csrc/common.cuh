@@ -271,7 +271,8 @@ int finish_pending_stats(ofb_handle* h);
 int flow_postfilter(ofb_handle* h, int n, int median_ksize, float magnitude_threshold, const uint8_t* const* gray,
                     size_t gray_stride, int intensity_threshold);
 int flow_download(ofb_handle* h, int n, float* const* flow, size_t flow_stride_bytes);
-int flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes);
+int flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes, int mode = 0, float dt = 1.f, float p2m = 1.f,
+                float vmax = 1.f);
 int flow_sample(ofb_handle* h, int pair, int n_points, const int* xy, float* out_dxdy);   // synchronises the stream, copies staged scalars to the callers' arrays
 
 // ---- ingest.cu / jpeg.cu

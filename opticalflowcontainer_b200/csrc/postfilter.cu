@@ -214,8 +214,11 @@ __global__ void __launch_bounds__(256) k_viz_minmax(const float2* __restrict__ f
   }
 }
 
+// mode 0: flow_to_color (sub_n_pub_lfn3_node.py:132-140): H = angle / 2 in degrees, V = min-max normalised magnitude.
+// mode 1: the sub node's dense view (lfn3_sub_node.py:244-262): H = uint8(ang * 90 / pi), V = uint8(clip(mag / dt *
+// pixel_to_meter / max_speed, 0, 1) * 255), every operation a float32 operation as NumPy evaluates the expression.
 __global__ void __launch_bounds__(256) k_viz_color(const float2* __restrict__ f, int w, int h, const unsigned int* __restrict__ mm,
-                                                   uint8_t* __restrict__ dst, size_t dp) {
+                                                   uint8_t* __restrict__ dst, size_t dp, int mode, float dt, float p2m, float vmax) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= w || y >= h) return;
   const float2 v = f[(size_t)y * w + x];
@@ -231,12 +234,19 @@ __global__ void __launch_bounds__(256) k_viz_color(const float2* __restrict__ f,
   a = v.x < 0.f ? __fsub_rn(180.f, a) : a;
   a = v.y < 0.f ? __fsub_rn(360.f, a) : a;
   const float ang = __fmul_rn(a, (float)(3.14159265358979323846 / 180.0));
-  const int H = (int)__fdiv_rn(__fdiv_rn(__fmul_rn(ang, 180.f), (float)3.14159265358979323846), 2.f) & 255;
-  // normalize(NORM_MINMAX, 0..255): scale / shift in double from the field's extrema, applied as one float FMA
-  const double smin = (double)__uint_as_float(mm[0]), smax = (double)__uint_as_float(mm[1]);
-  const double scale = 255.0 * (smax - smin > 2.220446049250313e-16 ? 1.0 / (smax - smin) : 0.0);
-  const double shift = 0.0 - smin * scale;
-  const int V = (int)__fmaf_rn(viz_mag(v), (float)scale, (float)shift) & 255;
+  int H, V;
+  if (mode == 0) {
+    H = (int)__fdiv_rn(__fdiv_rn(__fmul_rn(ang, 180.f), (float)3.14159265358979323846), 2.f) & 255;
+    // normalize(NORM_MINMAX, 0..255): scale / shift in double from the field's extrema, applied as one float FMA
+    const double smin = (double)__uint_as_float(mm[0]), smax = (double)__uint_as_float(mm[1]);
+    const double scale = 255.0 * (smax - smin > 2.220446049250313e-16 ? 1.0 / (smax - smin) : 0.0);
+    const double shift = 0.0 - smin * scale;
+    V = (int)__fmaf_rn(viz_mag(v), (float)scale, (float)shift) & 255;
+  } else {
+    H = (int)__fdiv_rn(__fmul_rn(ang, 90.f), (float)3.14159265358979323846) & 255;
+    const float t = __fdiv_rn(__fmul_rn(__fdiv_rn(viz_mag(v), dt), p2m), vmax);
+    V = (int)__fmul_rn(fminf(fmaxf(t, 0.f), 1.f), 255.f) & 255;
+  }
   // HSV -> BGR, S = 255
   const float s = __fmul_rn(255.f, 1.f / 255.f), vv = __fmul_rn((float)V, 1.f / 255.f);
   const float hf = __fmul_rn((float)H, 6.f / 180.f);
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(256) k_viz_color(const float2* __restrict__ f,
   o[2] = (uint8_t)min(max(body ? (int)fR : __float2int_rn(fR), 0), 255);
 }
 
-int flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes) {
+int flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes, int mode, float dt, float p2m, float vmax) {
   if (!h->last_flow || pair < 0 || pair >= h->last_n)
     return set_error(h, OFB_ERR_INVALID_ARG, "ofb_flow_to_bgr: no flow field %d on the device", pair);
   if (!bgr_out) return set_error(h, OFB_ERR_INVALID_ARG, "NULL output pointer");
@@ -281,9 +291,11 @@ int flow_to_bgr(ofb_handle* h, int pair, uint8_t* bgr_out, size_t stride_bytes) 
   OFB_CUDA(h, cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
   int s;
   if ((s = timing_begin(h, OFB_STAGE_OTHER))) return s;
-  k_viz_minmax<<<2 * h->num_sms, 256, 0, st>>>(f, (size_t)w * hh, mm);
-  OFB_LAUNCH_CHECK(h);
-  k_viz_color<<<dim3((w + 255) / 256, hh), 256, 0, st>>>(f, w, hh, mm, img, (size_t)w * 3);
+  if (mode == 0) {
+    k_viz_minmax<<<2 * h->num_sms, 256, 0, st>>>(f, (size_t)w * hh, mm);
+    OFB_LAUNCH_CHECK(h);
+  }
+  k_viz_color<<<dim3((w + 255) / 256, hh), 256, 0, st>>>(f, w, hh, mm, img, (size_t)w * 3, mode, dt, p2m, vmax);
   OFB_LAUNCH_CHECK(h);
   if ((s = timing_end(h))) return s;
   OFB_CUDA(h, cudaMemcpy2DAsync(bgr_out, stride_bytes, img, (size_t)w * 3, (size_t)w * 3, hh, cudaMemcpyDeviceToHost, st));

@@ -581,6 +581,17 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out
 
+    def flow_to_color_speed(self, height: int, width: int, dt: float, pixel_to_meter: float, max_speed: float,
+                            pair: int = 0) -> np.ndarray:
+        """The sub node's dense view (lfn3_sub_node.py:244-262) of the current field: hue from the angle, value =
+        ``clip(|flow| / dt * pixel_to_meter / max_speed, 0, 1) * 255`` → uint8 [H,W,3] BGR, on the device."""
+        out = np.empty((height, width, 3), np.uint8)
+        with self._lock:
+            st = self._lib.ofb_flow_to_bgr_speed(self._h, int(pair), float(dt), float(pixel_to_meter), float(max_speed),
+                                                 out.ctypes.data, 0)
+            _lib.check(st, self._h)
+        return out
+
     def lk_stream(self, frame, maxCorners=2000, qualityLevel=0.01, minDistance=7, blockSize=3, winSize=(21, 21),
                   maxLevel=3, criteria=(3, 30, 0.01), minEigThreshold=1e-4, flags=0):
         """Camera-stream form of goodFeaturesToTrack + calcOpticalFlowPyrLK (ofb_lk_stream): one new frame per call, the

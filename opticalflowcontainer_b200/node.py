@@ -223,6 +223,18 @@ def junction_velocity(engine: FlowEngine, prev_junctions: Sequence[Sequence[floa
     return float(disp[:, 0].mean() / dt * pixel_to_meter)
 
 
+def flow_arrows(engine: FlowEngine, height: int, width: int, step: int = 20, pair: int = 0) -> np.ndarray:
+    """End points of the sub node's arrow overlay (``lfn3_sub_node.py:225-238``: a grid of ``cv2.arrowedLine`` segments
+    (x, y) -> (x + int(u), y + int(v)) every ``step`` pixels) from the engine's current field, sampled on the device
+    (:meth:`FlowEngine.flow_sample`) instead of downloading the field: int32 [n, 4] (x1, y1, x2, y2) in the node's loop
+    order.  Drawing stays with the caller (``cv2.arrowedLine(img, (x1, y1), (x2, y2), (0, 255, 0), 1, tipLength=0.4)``)."""
+    ys, xs = np.meshgrid(np.arange(0, height, step), np.arange(0, width, step), indexing="ij")
+    pts = np.stack([xs.ravel(), ys.ravel()], -1).astype(np.int64)
+    d = engine.flow_sample(pts, pair)
+    end = pts + np.trunc(d).astype(np.int64)             # int() truncates towards zero
+    return np.concatenate([pts, end], 1).astype(np.int32)
+
+
 def adaptive_clip_limit(v: np.ndarray, clip_min: float, clip_max: float, c_min: float, c_max: float) -> float:
     """The adapt node's clip limit from the contrast of the V channel (``lfn3_adapt_node.py:170-175``):
     ``contrast = std(v) / (mean(v) + 1e-3)``, mapped linearly from [c_min, c_max] to [clip_min, clip_max] and clipped."""

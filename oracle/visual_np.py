@@ -61,3 +61,25 @@ def flow_to_color(flow_hw2: np.ndarray) -> np.ndarray:
     hsv[..., 0] = hue.astype(np.uint8)
     hsv[..., 2] = normalize_minmax_0_255(mag).astype(np.uint8)
     return prefilter_np.hsv2rgb_u8(hsv)[..., ::-1].copy()
+
+
+def flow_to_color_speed(flow_hw2: np.ndarray, dt: float, pixel_to_meter: float, max_speed: float) -> np.ndarray:
+    """The sub node's dense view (``lfn3_sub_node.py:244-262``) on a float32 [H,W,2] field -> uint8 [H,W,3] BGR:
+    ``mag, ang = cartToPolar(u, v); mag_norm = clip(mag / dt * pixel_to_meter / max_speed, 0, 1)``,
+    ``hsv = (uint8(ang * 90 / pi), 255, uint8(mag_norm * 255))`` -> HSV2BGR; float32 operations in NumPy's order."""
+    u, v = flow_hw2[..., 0], flow_hw2[..., 1]
+    mag, ang = cart_to_polar(u, v)
+    t = (((mag / f32(dt)).astype(f32) * f32(pixel_to_meter)).astype(f32) / f32(max_speed)).astype(f32)
+    hsv = np.zeros(u.shape + (3,), np.uint8)
+    hsv[..., 0] = ((ang * f32(90.0)).astype(f32) / f32(np.pi)).astype(f32).astype(np.uint8)
+    hsv[..., 1] = 255
+    hsv[..., 2] = (np.clip(t, f32(0), f32(1)) * f32(255)).astype(f32).astype(np.uint8)
+    return prefilter_np.hsv2rgb_u8(hsv)[..., ::-1].copy()
+
+
+def flow_arrows(flow_hw2: np.ndarray, step: int = 20) -> np.ndarray:
+    """The sub node's arrow overlay (``lfn3_sub_node.py:225-238``): for every grid point (x, y) with stride ``step`` the
+    segment (x, y) -> (x + int(u), y + int(v)) that ``cv2.arrowedLine`` draws; int32 [n, 4] in the node's loop order."""
+    h, w = flow_hw2.shape[:2]
+    out = [(x, y, x + int(flow_hw2[y, x, 0]), y + int(flow_hw2[y, x, 1])) for y in range(0, h, step) for x in range(0, w, step)]
+    return np.asarray(out, np.int32).reshape(-1, 4)

@@ -416,3 +416,24 @@ def test_junction_detector_node_contract(built_lib):
         assert node.image_callback(np.full((120, 160, 3), 90, np.uint8), 13.0) is None
     finally:
         node.engine.close()
+
+
+def test_dense_view_and_arrow_grid(built_lib):
+    """The sub node's two debug views of the field (lfn3_sub_node.py:225-262) from the device: the speed-scaled HSV image
+    bit-exact against the recipe's restatement (pinned against cv2 + NumPy in tests/test_oracle_visual.py) and the arrow
+    segments against the node's loop on the downloaded field."""
+    import opticalflowcontainer_b200 as ofb
+    from opticalflowcontainer_b200 import node
+    from oracle import synth
+    from oracle import visual_np as V
+    h, w = 123, 208
+    a, b = synth.synth_pair(h, w, 21, (5.5, -3.25))
+    eng = ofb.FlowEngine(w, h, 1, 0)
+    try:
+        flow = eng.farneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+        for dt, p2m, vmax in ((0.033, 0.0011, 0.25), (0.1, 0.000566, 0.01)):
+            assert np.array_equal(eng.flow_to_color_speed(h, w, dt, p2m, vmax), V.flow_to_color_speed(flow, dt, p2m, vmax))
+        assert np.array_equal(eng.flow_to_color(h, w), V.flow_to_color(flow))          # (the other mode still holds)
+        assert np.array_equal(node.flow_arrows(eng, h, w, 20), V.flow_arrows(flow, 20))
+    finally:
+        eng.close()
