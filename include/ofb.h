@@ -90,6 +90,8 @@ typedef struct ofb_gftt_params {
   double quality_level;
   double min_distance;
   int block_size; /* 3 */
+  int use_harris_detector; /* 0: Shi-Tomasi (cornerMinEigenVal), 1: cv2.cornerHarris(image, blockSize, 3, harris_k) */
+  double harris_k;         /* 0.04 */
 } ofb_gftt_params;
 
 /* ---- lifetime ---------------------------------------------------------------- */

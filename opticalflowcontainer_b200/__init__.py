@@ -76,14 +76,11 @@ def find_junctions(img, grid_area=250, grid_area_threshold=2.0, eps=4, dampen=No
 
 def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None, blockSize=3,
                         useHarrisDetector=False, k=0.04):
-    """Drop-in for ``cv2.goodFeaturesToTrack`` (Shi-Tomasi, optional ``mask``).  ``useHarrisDetector=True`` is refused:
-    the wheel's Harris response is not reproduced bit for bit, and a corner list that merely resembles cv2's is not a
-    drop-in (out of scope)."""
-    if useHarrisDetector:
-        raise OfbError(1, "goodFeaturesToTrack: useHarrisDetector is not supported")
+    """Drop-in for ``cv2.goodFeaturesToTrack``: Shi-Tomasi or (``useHarrisDetector``) Harris response with parameter ``k``,
+    optional ``mask``; the corner list is cv2's bit for bit (the response maps reproduce the wheel's arithmetic)."""
     image = np.asarray(image)
     r = _engine_for(image.shape[0], image.shape[1]).good_features(image, maxCorners, qualityLevel, minDistance,
-                                                                  blockSize, mask)
+                                                                  blockSize, mask, useHarrisDetector, k)
     return r if len(r) else None
 
 

@@ -43,7 +43,7 @@ class LKParams(C.Structure):
 
 class GfttParams(C.Structure):
     _fields_ = [("max_corners", C.c_int), ("quality_level", C.c_double), ("min_distance", C.c_double),
-                ("block_size", C.c_int)]
+                ("block_size", C.c_int), ("use_harris_detector", C.c_int), ("harris_k", C.c_double)]
 
 
 # every symbol include/ofb.h declares: name -> (restype, argtypes)

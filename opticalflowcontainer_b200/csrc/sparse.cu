@@ -221,9 +221,12 @@ __global__ void __launch_bounds__(256) k_sobel_cov(const uint8_t* __restrict__ s
 
 // unnormalised blockSize^2 box sum in double (exact for these magnitudes), then
 // eig = (a + c) - sqrt((a - c)^2 + b^2), a = Sxx/2, c = Syy/2 — plain mul/add, no FMA.
+// harris != 0: cv2.cornerHarris instead, as the wheel computes it over the image as ONE continuous row of w * h pixels —
+// (a c - b b) - k ((a + c)(a + c)) in float in the 8-wide body, (a c - b b) - (k (a + c)) (a + c) in the 4-wide step
+// behind it, and the last (w * h) % 4 pixels in double with the caller's double k (oracle/features_np.py::corner_harris).
 __global__ void __launch_bounds__(256) k_min_eig(const float* __restrict__ cov, int w, int h, int block_size,
                                                  float* __restrict__ eig, unsigned int* __restrict__ max_bits,
-                                                 const uint8_t* __restrict__ mask) {
+                                                 const uint8_t* __restrict__ mask, int harris, float kf, double kd) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   float e = 0.f;
@@ -240,9 +243,18 @@ __global__ void __launch_bounds__(256) k_min_eig(const float* __restrict__ cov, 
         syy += (double)cov[2 * n + o];
       }
     }
-    const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
-    const float d = __fsub_rn(a, c);
-    e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+    if (!harris) {
+      const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
+      const float d = __fsub_rn(a, c);
+      e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+    } else {
+      const float a = (float)sxx, b = (float)sxy, c = (float)syy;
+      const float t1 = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b)), sm = __fadd_rn(a, c);
+      const size_t i = (size_t)y * w + x;
+      if (i < n - (n & 7)) e = __fsub_rn(t1, __fmul_rn(kf, __fmul_rn(sm, sm)));
+      else if (i < n - (n & 3)) e = __fsub_rn(t1, __fmul_rn(__fmul_rn(kf, sm), sm));
+      else e = (float)__dsub_rn((double)t1, __dmul_rn(__dmul_rn(kd, (double)sm), (double)sm));
+    }
     eig[(size_t)y * w + x] = e;
   }
   // max over the image — over the masked pixels with a mask — (minMaxLoc); the map is >= 0 up to rounding, a negative
@@ -808,7 +820,7 @@ static int build_pyr(ofb_handle* h, SparseState* s, int which, int width, int he
 }
 
 static int eigen_map(ofb_handle* h, SparseState* s, int which, int width, int height, int block_size,
-                     const uint8_t* d_mask) {
+                     const uint8_t* d_mask, int harris = 0, double harris_k = 0.04) {
   const double scale = 1.0 / (4.0 * block_size * 255.0);
   const float k0 = (float)(1.0 * scale), k1 = (float)(2.0 * scale), k2 = (float)(1.0 * scale);
   dim3 b(32, 8);
@@ -818,7 +830,8 @@ static int eigen_map(ofb_handle* h, SparseState* s, int which, int width, int he
   k_sobel_cov<<<g2(width, height, b), b, 0, h->stream>>>(s->img[which], width, height, (size_t)width, s->cov, k0, k1, k2,
                                                          (width / 32) * 32);
   OFB_LAUNCH_CHECK(h);
-  k_min_eig<<<g2(width, height, b), b, 0, h->stream>>>(s->cov, width, height, block_size, s->eig, s->counters + 1, d_mask);
+  k_min_eig<<<g2(width, height, b), b, 0, h->stream>>>(s->cov, width, height, block_size, s->eig, s->counters + 1, d_mask, harris,
+                                                       (float)harris_k, harris_k);
   OFB_LAUNCH_CHECK(h);
   return OFB_OK;
 }
@@ -837,7 +850,7 @@ static int validate_gftt(ofb_handle* h, const ofb_gftt_params* p, int width, int
 static int detect_corners(ofb_handle* h, SparseState* s, int which, int width, int height, const ofb_gftt_params* p,
                           const uint8_t* d_mask) {
   cudaStream_t sm = h->stream;
-  int st = eigen_map(h, s, which, width, height, p->block_size, d_mask);
+  int st = eigen_map(h, s, which, width, height, p->block_size, d_mask, p->use_harris_detector, p->harris_k);
   if (st) return st;
   SP_CUDA(h, cudaMemsetAsync(s->hist, 0, kBuckets * sizeof(unsigned int), sm));
   dim3 b(32, 8);

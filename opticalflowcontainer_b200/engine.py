@@ -553,13 +553,15 @@ class FlowEngine:
             _lib.check(st, self._h)
         return out
 
-    def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3, mask=None) -> np.ndarray:
+    def good_features(self, image, maxCorners, qualityLevel, minDistance, blockSize=3, mask=None, useHarrisDetector=False,
+                      k=0.04) -> np.ndarray:
         image = _u8_image(image, "image")
         hgt, wid = image.shape
         cap = int(maxCorners) if maxCorners > 0 else hgt * wid
         out = np.empty((max(cap, 1), 2), np.float32)
         n = C.c_int(0)
-        p = GfttParams(int(maxCorners), float(qualityLevel), float(minDistance), int(blockSize))
+        p = GfttParams(int(maxCorners), float(qualityLevel), float(minDistance), int(blockSize), 1 if useHarrisDetector else 0,
+                       float(k))
         mptr, mstride = None, 0
         if mask is not None:
             mask = _u8_image(mask, "mask")
@@ -603,7 +605,7 @@ class FlowEngine:
         cap = int(maxCorners)
         if cap <= 0:
             raise OfbError(1, "lk_stream: maxCorners must be > 0")
-        gp = GfttParams(cap, float(qualityLevel), float(minDistance), int(blockSize))
+        gp = GfttParams(cap, float(qualityLevel), float(minDistance), int(blockSize), 0, 0.04)
         ctype, max_count, eps = criteria
         if not (ctype & 1):
             max_count = 30

@@ -26,8 +26,9 @@ def _pad101(a, r):
     return np.pad(a, r, mode="reflect")
 
 
-def corner_min_eigenval(img_u8: np.ndarray, block_size: int = 3) -> np.ndarray:
-    """== cv2.cornerMinEigenVal(img, block_size, ksize=3) for uint8 input (block_size 3 verified)."""
+def _cov_box_sums(img_u8: np.ndarray, block_size: int = 3):
+    """Unnormalised block_size^2 box sums (REFLECT_101, accumulated in double, cast to float32) of dx*dx, dx*dy, dy*dy,
+    the Sobel derivatives scaled by 1 / (4 block_size 255) with the wheel's FMA placement and SIMD-tail rule."""
     h, w = img_u8.shape
     scale = 1.0 / (4.0 * block_size * 255.0)
     k = (np.array([1.0, 2.0, 1.0]) * scale).astype(f32)
@@ -62,12 +63,39 @@ def corner_min_eigenval(img_u8: np.ndarray, block_size: int = 3) -> np.ndarray:
                 s += cp[j:j + h, i:i + w]
         return s.astype(f32)
 
-    a = (box(cxx) * f32(0.5)).astype(f32)
-    b = box(cxy)
-    c = (box(cyy) * f32(0.5)).astype(f32)
+    return box(cxx), box(cxy), box(cyy)
+
+
+def corner_min_eigenval(img_u8: np.ndarray, block_size: int = 3) -> np.ndarray:
+    """== cv2.cornerMinEigenVal(img, block_size, ksize=3) for uint8 input (block_size 3 verified)."""
+    sxx, sxy, syy = _cov_box_sums(img_u8, block_size)
+    a = (sxx * f32(0.5)).astype(f32)
+    b = sxy
+    c = (syy * f32(0.5)).astype(f32)
     d = ((a - c).astype(f32) * (a - c).astype(f32)).astype(f32)
     d = (d + (b * b).astype(f32)).astype(f32)
     return ((a + c).astype(f32) - np.sqrt(d).astype(f32)).astype(f32)
+
+
+def corner_harris(img_u8: np.ndarray, block_size: int = 3, k: float = 0.04) -> np.ndarray:
+    """== cv2.cornerHarris(img, block_size, 3, k) for uint8 input.  Same derivative products and box sums as
+    ``corner_min_eigenval`` (a, b, c NOT halved); the response as the wheel computes it over the image as ONE continuous
+    row of n = w * h pixels (probe-verified): ``(a c - b b) - k ((a + c)(a + c))`` in float in the 8-wide body,
+    ``(a c - b b) - (k (a + c)) (a + c)`` in the 4-wide step for pixels n - n % 8 .. n - n % 4, and the last n % 4 pixels
+    in double with the double ``k``: ``float(double(float(a c - b b)) - (k (a + c)) (a + c))``."""
+    a, b, c = _cov_box_sums(img_u8, block_size)
+    h, w = a.shape
+    a, b, c = a.ravel(), b.ravel(), c.ravel()
+    kf = f32(k)
+    t1 = ((a * c).astype(f32) - (b * b).astype(f32)).astype(f32)
+    s = (a + c).astype(f32)
+    out = (t1 - (kf * (s * s).astype(f32)).astype(f32)).astype(f32)
+    n = h * w
+    n8, n4 = n - n % 8, n - n % 4
+    out[n8:n4] = (t1[n8:n4] - ((kf * s[n8:n4]).astype(f32) * s[n8:n4]).astype(f32)).astype(f32)
+    sd = s[n4:].astype(f64)
+    out[n4:] = (t1[n4:].astype(f64) - (float(k) * sd) * sd).astype(f32)
+    return out.reshape(h, w)
 
 
 def good_features(img_u8: np.ndarray, max_corners: int, quality_level: float, min_distance: float,

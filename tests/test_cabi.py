@@ -36,7 +36,7 @@ def test_struct_layouts():
     assert C.sizeof(FarnebackParams) == 40
     assert FarnebackParams.poly_sigma.offset == 24 and FarnebackParams.flags.offset == 32
     assert C.sizeof(LKParams) == 40
-    assert C.sizeof(GfttParams) == 32
+    assert C.sizeof(GfttParams) == 40 and GfttParams.use_harris_detector.offset == 28 and GfttParams.harris_k.offset == 32
 
 
 def test_no_cpu_fallback(built_lib):

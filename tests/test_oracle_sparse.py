@@ -56,6 +56,25 @@ def test_good_features_exact(shape, seed, maxc, q, md):
     assert ref.shape == mine.shape and np.array_equal(ref, mine)
 
 
+@pytest.mark.parametrize("shape,seed,k", [((120, 160), 0, 0.04), ((97, 131), 1, 0.04), ((77, 129), 2, 0.06), ((33, 36), 3, 0.04),
+                                          ((31, 1921), 4, 0.06), ((90, 125), 5, 0.1)])
+def test_corner_harris_bit_exact(shape, seed, k):
+    """cv2.cornerHarris incl. the wheel's treatment of the image as one continuous row: the last (w*h) % 8 pixels of the
+    image go through the 4-wide step ((k s) s instead of k (s s)) and the scalar double tail."""
+    a, _ = synth.synth_pair(shape[0], shape[1], seed)
+    ref = cv2.cornerHarris(a, 3, 3, k)
+    mine = FT.corner_harris(a, 3, k)
+    assert np.array_equal(ref, mine), int((ref != mine).sum())
+
+
+@pytest.mark.parametrize("shape,seed,maxc,q,md,k", [((240, 320), 0, 200, 0.01, 7, 0.04), ((135, 241), 1, 50, 0.05, 3.5, 0.06)])
+def test_good_features_harris_exact(shape, seed, maxc, q, md, k):
+    a, _ = synth.synth_pair(shape[0], shape[1], seed)
+    ref = cv2.goodFeaturesToTrack(a, maxc, q, md, blockSize=3, useHarrisDetector=True, k=k)
+    mine = FT.good_features(a, maxc, q, md, 3, eig=FT.corner_harris(a, 3, k))
+    assert ref.shape == mine.shape and np.array_equal(ref, mine)
+
+
 def test_good_features_tie_order():
     t = np.zeros((64, 64), np.uint8)
     for y in range(8, 64, 16):

@@ -73,6 +73,21 @@ def test_good_features_exact_list_widths_not_multiple_of_32(engine_factory, shap
     assert got.shape == ref.shape and np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("shape,seed,maxc,q,md,k", [((240, 320), 0, 200, 0.01, 7, 0.04), ((135, 241), 1, 50, 0.05, 3.5, 0.06),
+                                                      ((481, 637), 7, 2000, 0.01, 7, 0.04), ((1080, 1917), 9, 2000, 0.01, 7, 0.04),
+                                                      ((77, 129), 3, 0, 0.02, 2, 0.1)])
+def test_good_features_harris_exact_list(engine_factory, shape, seed, maxc, q, md, k):
+    """useHarrisDetector=True: cv2's corner list bit for bit (the Harris response reproduces the wheel's arithmetic,
+    including its 4-wide step and double tail at the END of the image — sizes with w*h % 8 != 0 are in the list)."""
+    import opticalflowcontainer_b200 as ofb
+    a, _ = synth.synth_pair(shape[0], shape[1], seed)
+    eng = engine_factory(shape[1], shape[0])
+    ref = cv2.goodFeaturesToTrack(a, maxc, q, md, blockSize=3, useHarrisDetector=True, k=k)
+    got = eng.good_features(a, maxc, q, md, 3, useHarrisDetector=True, k=k)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert np.array_equal(ofb.goodFeaturesToTrack(a, maxc, q, md, blockSize=3, useHarrisDetector=True, k=k), ref)
+
+
 def test_good_features_mask(engine_factory):
     """cv2's mask argument: candidates outside the mask are dropped AND the quality threshold is relative to the
     strongest response inside the mask."""
@@ -91,8 +106,9 @@ def test_good_features_mask(engine_factory):
     big = np.zeros((270, 512), np.uint8); big[:, :480] = mask
     assert np.array_equal(eng.good_features(a, 300, 0.01, 7, 3, mask=big[:, :480]),
                           cv2.goodFeaturesToTrack(a, 300, 0.01, 7, mask=mask, blockSize=3))
-    with pytest.raises(ofb.OfbError):
-        ofb.goodFeaturesToTrack(a, 10, 0.01, 7, useHarrisDetector=True)
+    # mask and Harris response together
+    assert np.array_equal(ofb.goodFeaturesToTrack(a, 100, 0.01, 7, mask=mask, useHarrisDetector=True),
+                          cv2.goodFeaturesToTrack(a, 100, 0.01, 7, mask=mask, useHarrisDetector=True))
 
 
 def test_good_features_many_equal_responses(engine_factory):
