@@ -48,6 +48,7 @@ struct SparseState {
   size_t cand_cap = 0, sort_cap = 0;
   unsigned int* hist = nullptr;                // kBuckets: candidates per value bucket, then the scatter cursors
   unsigned int* bstart = nullptr;              // kBuckets + 1: first position of every bucket, strongest bucket first
+  unsigned int* bpart = nullptr;               // kBuckets / 1024 partial sums of the bucket scan
   unsigned int* counters = nullptr;            // [0] candidate count, [1] max(eig) bits, [4 + slot] corner count of a slot
   unsigned int* grid_cnt = nullptr;            // per cell
   ushort2* grid_pts = nullptr;                 // per cell x kGridSlots
@@ -77,7 +78,7 @@ static void sparse_free(SparseState* s) {
   if (!s) return;
   for (int i = 0; i < 2; i++) { cudaFree(s->img[i]); cudaFree(s->pyr[i]); cudaFree(s->deriv[i]); cudaFree(s->corners[i]); }
   cudaFree(s->cov); cudaFree(s->eig); cudaFree(s->keys); cudaFree(s->sortbuf); cudaFree(s->hist); cudaFree(s->bstart);
-  cudaFree(s->counters); cudaFree(s->grid_cnt); cudaFree(s->grid_pts); cudaFree(s->mask);
+  cudaFree(s->counters); cudaFree(s->bpart); cudaFree(s->grid_cnt); cudaFree(s->grid_pts); cudaFree(s->mask);
   cudaFree(s->pts_prev); cudaFree(s->pts_next); cudaFree(s->lk_status); cudaFree(s->lk_err);
   if (s->h_stage) cudaFreeHost(s->h_stage);
   delete s;
@@ -118,6 +119,7 @@ static int sparse_get(ofb_handle* h, SparseState** out) {
   SP_CUDA(h, cudaMalloc(&s->hist, kBuckets * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->bstart, (kBuckets + 1) * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->counters, 16 * sizeof(unsigned int)));
+  SP_CUDA(h, cudaMalloc(&s->bpart, (kBuckets / 1024) * sizeof(unsigned int)));
   SP_CUDA(h, cudaMemset(s->counters, 0, 16 * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->grid_cnt, N * sizeof(unsigned int)));
   SP_CUDA(h, cudaMalloc(&s->grid_pts, N * kGridSlots * sizeof(ushort2)));
@@ -318,37 +320,55 @@ __global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ ei
 
 // bstart[r] = first position of the r-th strongest bucket (r = kBuckets - 1 - bucket), bstart[kBuckets] = total;
 // the counts are cleared: the scatter uses them as cursors.
-__global__ void __launch_bounds__(1024) k_bucket_scan(unsigned int* __restrict__ hist, unsigned int* __restrict__ bstart) {
-  constexpr int PER = kBuckets / 1024;
-  __shared__ unsigned int wsum[32];
+// Two launches of kBuckets / 1024 CTAs, every access coalesced (one CTA reading 64 buckets per thread was latency-bound:
+// 156 us per frame): k_bucket_sums adds up each CTA's 1024 buckets, k_bucket_scan places them behind the CTAs before it.
+// Position r of the order = bucket kBuckets - 1 - r (strongest bucket first).
+__device__ __forceinline__ unsigned int block_scan_1024(unsigned int v, unsigned int* wsum, unsigned int* total) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  unsigned int sum = 0;
-  for (int j = 0; j < PER; j++) sum += hist[kBuckets - 1 - (t * PER + j)];
-  unsigned int inc = sum;
+  unsigned int inc = v;
   for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
+    const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
   }
   if (lane == 31) wsum[wid] = inc;
   __syncthreads();
   if (wid == 0) {
-    unsigned int v = wsum[lane];
+    unsigned int w = wsum[lane];
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int u = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += u;
+      const unsigned int u = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += u;
     }
-    wsum[lane] = v;
+    wsum[lane] = w;
   }
   __syncthreads();
-  unsigned int run = inc - sum + (wid ? wsum[wid - 1] : 0u);
-  for (int j = 0; j < PER; j++) {
-    const int r = t * PER + j, b = kBuckets - 1 - r;
-    const unsigned int c = hist[b];
-    bstart[r] = run;
-    run += c;
-    hist[b] = 0;
+  *total = wsum[31];
+  return inc - v + (wid ? wsum[wid - 1] : 0u);          // exclusive
+}
+
+__global__ void __launch_bounds__(1024) k_bucket_sums(const unsigned int* __restrict__ hist, unsigned int* __restrict__ part) {
+  __shared__ unsigned int wsum[32];
+  unsigned int total;
+  block_scan_1024(hist[kBuckets - 1 - (blockIdx.x * 1024 + threadIdx.x)], wsum, &total);
+  if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_bucket_scan(unsigned int* __restrict__ hist, unsigned int* __restrict__ bstart,
+                                                      const unsigned int* __restrict__ part) {
+  __shared__ unsigned int wsum[32];
+  __shared__ unsigned int base;
+  if (threadIdx.x < 32) {                                // candidates in the CTAs before this one (<= 64 partial sums)
+    unsigned int v = 0;
+    for (int c = threadIdx.x; c < (int)blockIdx.x; c += 32) v += part[c];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) base = v;
   }
-  if (t == 1023) bstart[kBuckets] = run;
+  const int r = blockIdx.x * 1024 + threadIdx.x, b = kBuckets - 1 - r;
+  const unsigned int c = hist[b];
+  unsigned int total;
+  const unsigned int excl = block_scan_1024(c, wsum, &total);   // (its barriers also publish `base`)
+  bstart[r] = base + excl;
+  hist[b] = 0;
+  if (r == kBuckets - 1) bstart[kBuckets] = base + total;
 }
 
 __global__ void __launch_bounds__(256) k_bucket_scatter(const unsigned long long* __restrict__ keys,
@@ -857,7 +877,9 @@ static int detect_corners(ofb_handle* h, SparseState* s, int which, int width, i
   k_candidates<<<g2(width - 2, height - 2, b), b, 0, sm>>>(s->eig, width, height, p->quality_level, s->counters + 1,
                                                           s->keys, s->counters, (unsigned int)s->cand_cap, s->hist, d_mask);
   OFB_LAUNCH_CHECK(h);
-  k_bucket_scan<<<1, 1024, 0, sm>>>(s->hist, s->bstart);
+  k_bucket_sums<<<kBuckets / 1024, 1024, 0, sm>>>(s->hist, s->bpart);
+  OFB_LAUNCH_CHECK(h);
+  k_bucket_scan<<<kBuckets / 1024, 1024, 0, sm>>>(s->hist, s->bstart, s->bpart);
   OFB_LAUNCH_CHECK(h);
   k_bucket_scatter<<<2 * h->num_sms, 256, 0, sm>>>(s->keys, s->counters, (unsigned int)s->cand_cap, p->quality_level,
                                                    s->counters + 1, s->hist, s->bstart, s->keys + s->cand_cap);
