@@ -868,7 +868,9 @@ def run_ours(args, rank, local_rank, world):
                                 "sample": "cv2 %s calcOpticalFlowFarneback, %d processes x %d pairs of %dx%d "
                                           "(single-threaded algorithm; 1 pair = %.0f ms on one core)"
                                           % (cb["cv2_version"], cb["cores"], cb["pairs_per_worker"], W_, H_,
-                                             cb["single_pair_ms"])}
+                                             cb["single_pair_ms"]),
+                                "per_core_pairs_per_s": cb["per_core_pairs_per_s"],
+                                "single_process": cb["single_process"]}
     real_stdout.write(json.dumps(line) + "\n")
     real_stdout.flush()
     if world > 1:

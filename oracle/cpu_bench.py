@@ -45,6 +45,20 @@ def farneback_cpu_throughput(h, w, target_seconds=12.0, workers=None, params=PAR
     t0 = time.perf_counter()
     cv2.calcOpticalFlowFarneback(a, b, None, *params)
     t1 = time.perf_counter() - t0
+    # one process, cv2.setNumThreads(1) and the default thread count, 5 timed repetitions after the warm-up,
+    # best and median (Farneback is single-threaded in this wheel: the two agree)
+    single = {}
+    default_threads = cv2.getNumThreads()
+    for label, nt in (("threads_1", 1), ("threads_default", default_threads)):
+        cv2.setNumThreads(nt)
+        cv2.calcOpticalFlowFarneback(a, b, None, *params)
+        reps = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            cv2.calcOpticalFlowFarneback(a, b, None, *params)
+            reps.append((time.perf_counter() - t0) * 1e3)
+        single[label] = dict(threads=nt, best_ms=min(reps), median_ms=float(np.median(reps)), reps=5)
+    cv2.setNumThreads(default_threads)
     n_pairs = int(max(1, min(32, round(target_seconds / max(t1, 1e-3)))))
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
@@ -56,7 +70,8 @@ def farneback_cpu_throughput(h, w, target_seconds=12.0, workers=None, params=PAR
         times = pool.map(_worker, [(h, w, 2000 + i, n_pairs, params) for i in range(workers)])
     busy = max(times)
     return dict(value=workers * n_pairs / busy, cores=workers, pairs_per_worker=n_pairs, seconds=busy,
-                single_pair_ms=t1 * 1e3, cv2_version=cv2.__version__, cv2_threads=1, wall_first_pool=wall)
+                single_pair_ms=t1 * 1e3, cv2_version=cv2.__version__, cv2_threads=1, wall_first_pool=wall,
+                single_process=single, per_core_pairs_per_s=n_pairs / busy)
 
 
 def farneback_cpu_step(h, w, pairs_per_worker, workers, pool, params=PARAMS, seed=0):
