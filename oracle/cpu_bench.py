@@ -48,6 +48,7 @@ def farneback_cpu_throughput(h, w, target_seconds=12.0, workers=None, params=PAR
     # one process, cv2.setNumThreads(1) and the default thread count, 5 timed repetitions after the warm-up,
     # best and median (Farneback is single-threaded in this wheel: the two agree)
     single = {}
+    cv2.setNumThreads(-1)                       # back to the build's default, whatever the caller had set
     default_threads = cv2.getNumThreads()
     for label, nt in (("threads_1", 1), ("threads_default", default_threads)):
         cv2.setNumThreads(nt)
