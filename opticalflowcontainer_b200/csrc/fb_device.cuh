@@ -3,6 +3,17 @@
 #pragma once
 #include "common.cuh"
 
+// Debug builds (tools/build_variant.sh dbg "-DOFB_DBG=1"; never the shipped library): in-kernel bounds checks of the
+// ring / staging / output indexing.  A failing check aborts the kernel with the file and line (device-side assert);
+// tools/debug_asserts.sh runs the Farneback GPU tests against such a build.  No compute-sanitizer on the GPU pool, so this
+// is the memcheck stand-in for the hand-indexed shared-memory and tensor-memory structures.
+#if defined(OFB_DBG) && OFB_DBG
+#include <assert.h>
+#define OFB_DASSERT(cond) assert(cond)
+#else
+#define OFB_DASSERT(cond) do { } while (0)
+#endif
+
 namespace ofb {
 
 __device__ __forceinline__ int reflect101(int i, int n) {

@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
 
     // vertical van Herk step: P += M(t); V = (Bp - P_prev[k]) + P; ring[k] = P; block bookkeeping
     auto ring_step = [&](const M5& mm, float (&V)[5]) {
+      OFB_DASSERT(k >= 0 && k < R);                                   // ring slot inside the (2m+1)-row ring
+      OFB_DASSERT(!TMEM || (tk == (uint32_t)k * kTmemRingStride && tk + 5 <= (uint32_t)kTmemWgCols));
       float old[8];
       if constexpr (TMEM) {
         tmem_wait_st();                              // the slot read below was written R rows ago: long complete
@@ -332,7 +334,10 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
         return __ldg(fin + ((unsigned)yc * uw + (unsigned)x));
       }
     };
-    auto stage_row = [&](int buf, int rr) { return stage + ((buf * CH + rr) * 5) * COLS + tid; };
+    auto stage_row = [&](int buf, int rr) {
+      OFB_DASSERT(buf >= 0 && buf < NBUF && rr >= 0 && rr < CH && tid < COLS);   // inside the staging pipeline's buffers
+      return stage + ((buf * CH + rr) * 5) * COLS + tid;
+    };
 
     if constexpr (REUSE) {
       // Two rows in flight AND row-reuse gather.  Rows A = t, B = t + 1 of a chunk: all loads of both are issued before
@@ -635,6 +640,8 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
       mbar_wait(bar_full + 8u * buf, par);             // every producer warp has staged chunk c
       const int yo = y0 + c * CH + q_row;
       if (yo < y1 && vmask) {
+        OFB_DASSERT(buf >= 0 && buf < NBUF && q_row >= 0 && q_row < CH && q0 >= 0 && q0 + PXT <= COLS);
+        OFB_DASSERT(yo >= y_begin && yo < y_end && yo < h);              // an output row of this launch
         const float* srow = stage + (buf * CH + q_row) * 5 * COLS;
         // shared address of this thread's first quad in channel 0 of its staged row (PAD columns left of its pixels).
         // Where the strip halo equals PAD (radius 7 / 15) every thread with a valid output reads inside the row: one
@@ -704,6 +711,8 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
 #pragma unroll
         for (int j = 0; j < PXT; j++) f[j] = solve2x2_sums(sum[0][j], sum[1][j], sum[2][j], sum[3][j], sum[4][j], reg);
         const int oi = yo * w + ox;                    // (oi + j >= 0 for every valid column j)
+#pragma unroll
+        for (int j = 0; j < PXT; j++) OFB_DASSERT(!((vmask >> j) & 1u) || (ox + j >= 0 && ox + j < w && oi + j >= 0 && oi + j < w * h));
         float2* o = fout + (unsigned)max(oi, 0);
         if (PXT == 4 && vmask == ALL && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
           // 32-byte aligned (always, where strips start at multiples of 8 pixels and w % 4 == 0): the thread's four flow
