@@ -45,14 +45,27 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   const int slots = MINB * h->num_sms;
   const int per = strips * n_pairs;
   const int rows = y_end - y_begin;
-  int segs = per >= slots ? 1 : slots / per;
-  // Tiled mode (one pair, narrow bands): at least 6 rows per segment — a segment pays 2m warm-up rows, but these are
-  // latency-bound launches, where more, shorter CTAs on otherwise idle SMs finish sooner.  Whole frames: at least 16,
-  // which also keeps the segmentation of small frames (and with it the rounding of the vertical block sums) the same
-  // for every batch size.
-  int seg_rows = std::max(REUSE && TILED ? 6 : 16, (rows + segs - 1) / segs);
-  seg_rows += seg_rows & 1;       // even: the chunks of the fused upsample then start on odd rows (fb_iter_v.cuh)
-  segs = (rows + seg_rows - 1) / seg_rows;
+  // Row segments: a CTA marches its segment row by row (plus 2m warm-up rows), the CTAs run in waves of `slots`, so the
+  // launch takes about  waves(segs) * (seg_rows + 2m)  row steps.  The number of segments minimises that (fewest
+  // segments on a tie): whole frames at the benchmark batch keep one full wave (1080p x 18 pairs: 2 segments, as before),
+  // while small frames in large batches — VGA x 72: 216 strip columns, 0.73 of a wave — are cut so that the waves are
+  // full (4 segments: 2.9 waves of 134 rows instead of one of 494).
+  // Tiled mode (one pair, narrow bands): at least 6 rows per segment; whole frames: at least 16, which also keeps the
+  // segmentation of small frames (and with it the rounding of the vertical block sums) the same for every batch size.
+  const int min_rows = REUSE && TILED ? 6 : 16;
+  int segs = 1, seg_rows = rows + (rows & 1);
+  {
+    long best = -1;
+    const int max_segs = std::min(64, std::max(1, rows / min_rows));
+    for (int sgm = 1; sgm <= max_segs; sgm++) {
+      int sr = std::max(min_rows, (rows + sgm - 1) / sgm);
+      sr += sr & 1;       // even: the chunks of the fused upsample then start on odd rows (fb_iter_v.cuh)
+      const int ns = (rows + sr - 1) / sr;
+      const long waves = ((long)per * ns + slots - 1) / slots;
+      const long cost = waves * (sr + 2 * m);
+      if (best < 0 || cost < best) { best = cost; segs = ns; seg_rows = sr; }
+    }
+  }
   dim3 g(strips * segs, n_pairs);
   kern<<<g, COLS + CH * COLS / 4, smem, st>>>(rs, fin, fout, w, hh, m, reg, seg_rows, strips, y_begin, y_end, t, my_rank, u);
   return cudaGetLastError();
