@@ -41,7 +41,6 @@ struct SparseState {
   uint8_t* img[2] = {nullptr, nullptr};        // level-0 images of the two frame slots, packed pitch = width
   uint8_t* pyr[2] = {nullptr, nullptr};        // levels 1.. of both pyramids, packed one after another
   short2* deriv[2] = {nullptr, nullptr};       // Scharr (dx,dy) of every level of a slot
-  float* cov = nullptr;                        // 3 planes
   float* eig = nullptr;
   unsigned long long* keys = nullptr;          // 2 x cand_cap: candidates as found | bucket order
   unsigned long long* sortbuf = nullptr;       // power-of-two scratch of the oversized-bucket path
@@ -62,6 +61,9 @@ struct SparseState {
   // pinned host staging
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
+  // second stream of the camera-stream call: the corner detection of the new frame runs beside the tracker
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_aux = nullptr;
   // camera-stream state (ofb_lk_stream)
   struct Stream {
     bool primed = false;
@@ -77,10 +79,13 @@ struct SparseState {
 static void sparse_free(SparseState* s) {
   if (!s) return;
   for (int i = 0; i < 2; i++) { cudaFree(s->img[i]); cudaFree(s->pyr[i]); cudaFree(s->deriv[i]); cudaFree(s->corners[i]); }
-  cudaFree(s->cov); cudaFree(s->eig); cudaFree(s->keys); cudaFree(s->sortbuf); cudaFree(s->hist); cudaFree(s->bstart);
+  cudaFree(s->eig); cudaFree(s->keys); cudaFree(s->sortbuf); cudaFree(s->hist); cudaFree(s->bstart);
   cudaFree(s->counters); cudaFree(s->bpart); cudaFree(s->grid_cnt); cudaFree(s->grid_pts); cudaFree(s->mask);
   cudaFree(s->pts_prev); cudaFree(s->pts_next); cudaFree(s->lk_status); cudaFree(s->lk_err);
   if (s->h_stage) cudaFreeHost(s->h_stage);
+  if (s->aux) cudaStreamDestroy(s->aux);
+  if (s->ev_up) cudaEventDestroy(s->ev_up);
+  if (s->ev_aux) cudaEventDestroy(s->ev_aux);
   delete s;
 }
 
@@ -109,7 +114,6 @@ static int sparse_get(ofb_handle* h, SparseState** out) {
     SP_CUDA(h, cudaMalloc(&s->pyr[i], N));     // sum of levels >= 1 is < N/2 (+ rounding)
   }
   for (int i = 0; i < 2; i++) SP_CUDA(h, cudaMalloc(&s->deriv[i], 2 * N * sizeof(short2)));
-  SP_CUDA(h, cudaMalloc(&s->cov, 3 * N * sizeof(float)));
   SP_CUDA(h, cudaMalloc(&s->eig, N * sizeof(float)));
   s->cand_cap = N / 2 + 1024;
   SP_CUDA(h, cudaMalloc(&s->keys, 2 * s->cand_cap * sizeof(unsigned long long)));
@@ -127,6 +131,9 @@ static int sparse_get(ofb_handle* h, SparseState** out) {
   for (int i = 0; i < 2; i++) SP_CUDA(h, cudaMalloc(&s->corners[i], s->cand_cap * sizeof(float2)));
   s->h_stage_bytes = std::max<size_t>(2 * N, s->cand_cap * sizeof(float2) + 64);
   SP_CUDA(h, cudaHostAlloc(&s->h_stage, s->h_stage_bytes, cudaHostAllocDefault));
+  SP_CUDA(h, cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
+  SP_CUDA(h, cudaEventCreateWithFlags(&s->ev_up, cudaEventDisableTiming));
+  SP_CUDA(h, cudaEventCreateWithFlags(&s->ev_aux, cudaEventDisableTiming));
   *out = s;
   return OFB_OK;
 }
@@ -197,54 +204,69 @@ __global__ void __launch_bounds__(256) k_scharr(const uint8_t* __restrict__ src,
 //   dx = fma(r[y-1] + r[y+1], k0, r[y]*k1),  r = p[x+1] - p[x-1]
 //   dy = rw[y+1] - rw[y-1],  rw = fma(k2, p[x+1], fma(k1, p[x], k0*p[x-1]))   (vector body)
 //        rw = (p[x-1]*k0 + p[x]*k1) + p[x+1]*k2   for columns past the last full block of 32 (SIMD tail)
-__global__ void __launch_bounds__(256) k_sobel_cov(const uint8_t* __restrict__ src, int w, int h, size_t spitch,
-                                                   float* __restrict__ cov, float k0, float k1, float k2, int wb) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= w || y >= h) return;
-  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-  const uint8_t* rows[3] = {src + (size_t)reflect101(y - 1, h) * spitch, src + (size_t)y * spitch,
-                            src + (size_t)reflect101(y + 1, h) * spitch};
-  float r[3], rw[3];
-#pragma unroll
-  for (int j = 0; j < 3; j++) {
-    const float pm = (float)rows[j][xm], pc = (float)rows[j][x], pp = (float)rows[j][xp];
-    r[j] = pp - pm;
-    if (x < wb) rw[j] = fmaf(k2, pp, fmaf(k1, pc, __fmul_rn(k0, pm)));
-    else rw[j] = __fadd_rn(__fadd_rn(__fmul_rn(pm, k0), __fmul_rn(pc, k1)), __fmul_rn(pp, k2));
-  }
-  const float dx = fmaf(r[0] + r[2], k0, __fmul_rn(r[1], k1));
-  const float dy = rw[2] - rw[0];
-  const size_t n = (size_t)w * h, o = (size_t)y * w + x;
-  cov[o] = __fmul_rn(dx, dx);
-  cov[n + o] = __fmul_rn(dx, dy);
-  cov[2 * n + o] = __fmul_rn(dy, dy);
-}
-
+// Both stages in one kernel: a CTA computes the three derivative products for its 32 x 16 output tile plus the
+// box-filter apron into shared memory (the apron positions are the REFLECT_101 images of interior pixels, so each is the
+// product AT the reflected position, as a filter over a stored covariance image would read it), then sums the windows.
+// Nothing but the eigenvalue map is written: the 12 B/px covariance image of the two-kernel form (written once, read
+// blockSize^2 times through L1) is gone.
+//
 // unnormalised blockSize^2 box sum in double (exact for these magnitudes), then
 // eig = (a + c) - sqrt((a - c)^2 + b^2), a = Sxx/2, c = Syy/2 — plain mul/add, no FMA.
 // harris != 0: cv2.cornerHarris instead, as the wheel computes it over the image as ONE continuous row of w * h pixels —
 // (a c - b b) - k ((a + c)(a + c)) in float in the 8-wide body, (a c - b b) - (k (a + c)) (a + c) in the 4-wide step
 // behind it, and the last (w * h) % 4 pixels in double with the caller's double k (oracle/features_np.py::corner_harris).
-__global__ void __launch_bounds__(256) k_min_eig(const float* __restrict__ cov, int w, int h, int block_size,
-                                                 float* __restrict__ eig, unsigned int* __restrict__ max_bits,
-                                                 const uint8_t* __restrict__ mask, int harris, float kf, double kd) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  float e = 0.f;
-  if (x < w && y < h) {
-    const size_t n = (size_t)w * h;
-    const int rb = block_size / 2;
+constexpr int kEigTileH = 16;
+__global__ void __launch_bounds__(256) k_sobel_min_eig(const uint8_t* __restrict__ src, int w, int h, size_t spitch, float k0,
+                                                       float k1, float k2, int wb, int block_size,
+                                                       float* __restrict__ eig, unsigned int* __restrict__ max_bits,
+                                                       const uint8_t* __restrict__ mask, int harris, float kf, double kd) {
+  extern __shared__ float cov_tile[];                // [3][th][tw]
+  const int rb = block_size / 2, tw = 32 + 2 * rb, th = kEigTileH + 2 * rb, ta = tw * th;
+  float* cxx = cov_tile;
+  float* cxy = cov_tile + ta;
+  float* cyy = cov_tile + 2 * ta;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * kEigTileH;
+  for (int i = tid; i < ta; i += 256) {
+    const int ty = i / tw, tx = i - ty * tw;
+    // (tile positions beyond the apron of the image's last row / column are never read: keep them in range)
+    const int x = reflect101(min(bx - rb + tx, w - 1 + rb), w), y = reflect101(min(by - rb + ty, h - 1 + rb), h);
+    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    const uint8_t* rows[3] = {src + (size_t)reflect101(y - 1, h) * spitch, src + (size_t)y * spitch,
+                              src + (size_t)reflect101(y + 1, h) * spitch};
+    float r[3], rw[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float pm = (float)rows[j][xm], pc = (float)rows[j][x], pp = (float)rows[j][xp];
+      r[j] = pp - pm;
+      if (x < wb) rw[j] = fmaf(k2, pp, fmaf(k1, pc, __fmul_rn(k0, pm)));
+      else rw[j] = __fadd_rn(__fadd_rn(__fmul_rn(pm, k0), __fmul_rn(pc, k1)), __fmul_rn(pp, k2));
+    }
+    const float dx = fmaf(r[0] + r[2], k0, __fmul_rn(r[1], k1));
+    const float dy = rw[2] - rw[0];
+    cxx[i] = __fmul_rn(dx, dx);
+    cxy[i] = __fmul_rn(dx, dy);
+    cyy[i] = __fmul_rn(dy, dy);
+  }
+  __syncthreads();
+  const size_t n = (size_t)w * h;
+  float m = 0.f;
+#pragma unroll
+  for (int half = 0; half < kEigTileH / 8; half++) {
+    const int lx = threadIdx.x, ly = threadIdx.y + 8 * half;
+    const int x = bx + lx, y = by + ly;
+    if (x >= w || y >= h) continue;
     double sxx = 0, sxy = 0, syy = 0;
-    for (int j = -rb; j <= rb; j++) {
-      const size_t ro = (size_t)reflect101(y + j, h) * w;
-      for (int i = -rb; i <= rb; i++) {
-        const size_t o = ro + reflect101(x + i, w);
-        sxx += (double)cov[o];
-        sxy += (double)cov[n + o];
-        syy += (double)cov[2 * n + o];
+    for (int j = 0; j <= 2 * rb; j++) {
+      const int ro = (ly + j) * tw + lx;
+      for (int i = 0; i <= 2 * rb; i++) {
+        sxx += (double)cxx[ro + i];
+        sxy += (double)cxy[ro + i];
+        syy += (double)cyy[ro + i];
       }
     }
+    float e;
+    const size_t o = (size_t)y * w + x;
     if (!harris) {
       const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
       const float d = __fsub_rn(a, c);
@@ -252,19 +274,18 @@ __global__ void __launch_bounds__(256) k_min_eig(const float* __restrict__ cov, 
     } else {
       const float a = (float)sxx, b = (float)sxy, c = (float)syy;
       const float t1 = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b)), sm = __fadd_rn(a, c);
-      const size_t i = (size_t)y * w + x;
-      if (i < n - (n & 7)) e = __fsub_rn(t1, __fmul_rn(kf, __fmul_rn(sm, sm)));
-      else if (i < n - (n & 3)) e = __fsub_rn(t1, __fmul_rn(__fmul_rn(kf, sm), sm));
+      if (o < n - (n & 7)) e = __fsub_rn(t1, __fmul_rn(kf, __fmul_rn(sm, sm)));
+      else if (o < n - (n & 3)) e = __fsub_rn(t1, __fmul_rn(__fmul_rn(kf, sm), sm));
       else e = (float)__dsub_rn((double)t1, __dmul_rn(__dmul_rn(kd, (double)sm), (double)sm));
     }
-    eig[(size_t)y * w + x] = e;
+    eig[o] = e;
+    // max over the image — over the masked pixels with a mask — (minMaxLoc); the map is >= 0 up to rounding, a negative
+    // max means "no corners"
+    if (mask && mask[o] == 0) e = 0.f;
+    m = fmaxf(m, e);
   }
-  // max over the image — over the masked pixels with a mask — (minMaxLoc); the map is >= 0 up to rounding, a negative
-  // max means "no corners"
-  if (mask && x < w && y < h && mask[(size_t)y * w + x] == 0) e = 0.f;
-  float m = fmaxf(e, 0.f);
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && m > 0.f) atomicMax(max_bits, __float_as_uint(m));
+  if ((tid & 31) == 0 && m > 0.f) atomicMax(max_bits, __float_as_uint(m));
 }
 
 // Candidate ordering.  cv2 sorts all candidates (std::sort, value descending, ties by DESCENDING address) and walks the
@@ -299,19 +320,31 @@ __global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ ei
                                                     const uint8_t* __restrict__ mask) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  if (x >= w - 1 || y >= h - 1) return;
   float thr;
   const CandRange cr = cand_range(*max_bits, quality, &thr);
-  const float v = eig[(size_t)y * w + x];
-  if (!(v > thr)) return;
-  float mx = v;
+  float v = 0.f;
+  bool cand = false;
+  if (x < w - 1 && y < h - 1) {
+    v = eig[(size_t)y * w + x];
+    if (v > thr) {
+      float mx = v;
 #pragma unroll
-  for (int j = -1; j <= 1; j++)
+      for (int j = -1; j <= 1; j++)
 #pragma unroll
-    for (int i = -1; i <= 1; i++) mx = fmaxf(mx, eig[(size_t)(y + j) * w + x + i]);
-  if (v != mx) return;
-  if (mask && mask[(size_t)y * w + x] == 0) return;
-  const unsigned int slot = atomicAdd(count, 1u);
+        for (int i = -1; i <= 1; i++) mx = fmaxf(mx, eig[(size_t)(y + j) * w + x + i]);
+      cand = v == mx && !(mask && mask[(size_t)y * w + x] == 0);
+    }
+  }
+  // one counter update per warp (a warp is one 32-pixel row segment of the 32 x 8 block): every candidate adding to the
+  // one counter itself serialised ~1e5 same-address atomics per frame in L2
+  const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+  if (bal == 0u) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(count, (unsigned int)__popc(bal));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!cand) return;
+  const unsigned int slot = base + __popc(bal & ((1u << lane) - 1u));
   if (slot < cap) {
     keys[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * w + x);
     atomicAdd(&hist[min((__float_as_uint(v) - cr.thr_bits) >> cr.shift, (unsigned int)kBuckets - 1u)], 1u);
@@ -399,17 +432,25 @@ constexpr int GS_BUCKETS = 4096;
 __device__ __forceinline__ bool gs_far_from_accepted(int x, int y, int cell, int gw, int gh, float md2,
                                                      const unsigned int* grid_cnt, const ushort2* grid_pts) {
   const int xc = x / cell, yc = y / cell;
-  for (int yy = max(0, yc - 1); yy <= min(gh - 1, yc + 1); yy++)
-    for (int xx = max(0, xc - 1); xx <= min(gw - 1, xc + 1); xx++) {
-      const int c = yy * gw + xx;
-      const unsigned int cnt = min(grid_cnt[c], (unsigned int)kGridSlots);   // (one CTA: barrier/fence-ordered, L1-coherent)
-      for (unsigned int k = 0; k < cnt; k++) {
-        const ushort2 p = grid_pts[c * kGridSlots + k];
-        const float dx = (float)(x - (int)p.x), dy = (float)(y - (int)p.y);
-        if (dx * dx + dy * dy < md2) return false;
-      }
+  // the nine cell counts first (independent loads), then the cells' points: the walk is a chain of L2 round trips otherwise
+  unsigned int cnt[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+    const int yy = yc + q / 3 - 1, xx = xc + q % 3 - 1;
+    const bool in = (unsigned)yy < (unsigned)gh && (unsigned)xx < (unsigned)gw;
+    cnt[q] = in ? min(grid_cnt[yy * gw + xx], (unsigned int)kGridSlots) : 0u;   // (one CTA: barrier/fence-ordered, L1-coherent)
+  }
+  bool far = true;
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+    const int c = (yc + q / 3 - 1) * gw + xc + q % 3 - 1;
+    for (unsigned int k = 0; k < cnt[q]; k++) {
+      const ushort2 p = grid_pts[c * kGridSlots + k];
+      const float dx = (float)(x - (int)p.x), dy = (float)(y - (int)p.y);
+      if (dx * dx + dy * dy < md2) far = false;
     }
-  return true;
+  }
+  return far;
 }
 
 // descending bitonic sort of n = 2^k keys by the whole CTA; keys live in shared or global memory
@@ -427,6 +468,33 @@ __device__ __forceinline__ void gs_bitonic_desc(unsigned long long* a, unsigned 
     }
 }
 
+// The same order for exactly GS_THREADS keys, one per thread: exchanges at distances < 32 are warp shuffles on the key
+// in a register (40 of the 55 steps, no barrier), the 15 longer ones go through two alternating shared-memory buffers
+// (one barrier per step).  Leaves the sorted keys in `a`.
+__device__ __forceinline__ void gs_bitonic_desc_round(unsigned long long* a, unsigned long long* b) {
+  const unsigned int i = threadIdx.x;
+  unsigned long long u = a[i];
+  unsigned long long* wr = b;                        // (a is still being read by other warps: first exchange goes to b)
+  for (unsigned int k = 2; k <= (unsigned int)GS_THREADS; k <<= 1)
+    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long v;
+      if (j >= 32u) {
+        wr[i] = u;
+        __syncthreads();
+        v = wr[i ^ j];
+        wr = wr == a ? b : a;
+      } else {
+        v = __shfl_xor_sync(0xffffffffu, u, (int)j);
+      }
+      // descending block ((i & k) == 0): the lower index keeps the larger key
+      const bool keep_max = ((i & j) == 0u) == ((i & k) == 0u);
+      u = keep_max ? (u > v ? u : v) : (u < v ? u : v);
+    }
+  __syncthreads();                                   // every read of the last exchange is done
+  a[i] = u;
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned long long* __restrict__ bkeys,
                                                               const unsigned int* __restrict__ bstart,
                                                               unsigned long long* __restrict__ sortbuf,
@@ -435,6 +503,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
                                                               ushort2* grid_pts, float2* __restrict__ corners,
                                                               unsigned int* __restrict__ n_out) {
   __shared__ unsigned long long rk[GS_THREADS];      // the round's keys, descending
+  __shared__ unsigned long long rk2[GS_THREADS];     // exchange buffer of the round sort
   __shared__ unsigned int surv[GS_THREADS];          // x | y << 16, rank order
   __shared__ unsigned int warp_cnt[GS_THREADS / 32];
   __shared__ unsigned int s_nsurv, s_accepted;
@@ -491,7 +560,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
       pos += nr;
       rb = rb_end;
       __syncthreads();
-      if (nr > 1) gs_bitonic_desc(rk, GS_THREADS);
+      if (nr > 1) gs_bitonic_desc_round(rk, rk2);
     }
     if (nr == 0) continue;
     if (!use_dist) {
@@ -642,16 +711,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr int LK_WARPS = 4;
 
+// TW x TH: the window as a compile-time constant (0 = run time).  The window loops then have a constant trip count and
+// unroll completely: the 4 byte loads of all ceil(area / 32) window pixels of a lane are in flight together instead of
+// one dependent round trip per step, and e / ww is a multiply.  The arithmetic and its order are the same (same bits).
+template <int TW, int TH>
 __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const float2* __restrict__ prev_pts,
                                                             float2* __restrict__ next_pts, uint8_t* __restrict__ status,
                                                             float* __restrict__ err, int n_points,
-                                                            const unsigned int* __restrict__ n_dev, int ww, int wh,
+                                                            const unsigned int* __restrict__ n_dev, int ww_rt, int wh_rt,
                                                             int max_count, double eps2, int flags, double min_eig_thr) {
   extern __shared__ short lk_smem[];  // per warp: Iwin[area], dIx[area], dIy[area]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pid = blockIdx.x * LK_WARPS + warp;
   // n_dev: the point count is a device-side value (corner list of the previous frame); the grid covers n_points = its bound
   if (pid >= (n_dev ? (int)min(*n_dev, (unsigned int)n_points) : n_points)) return;
+  const int ww = TW ? TW : ww_rt, wh = TH ? TH : wh_rt;
   const int area = ww * wh;
   short* Iwin = lk_smem + (size_t)warp * 3 * area;
   short* dIx = Iwin + area;
@@ -690,6 +764,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
     const bool in_i = ipx >= 0 && ipy >= 0 && ipx + ww + 1 <= cols && ipy + wh + 1 <= rows;
     float a11 = 0.f, a12 = 0.f, a22 = 0.f;
     __syncwarp();
+#pragma unroll
     for (int e = lane; e < area; e += 32) {
       const int wy = e / ww, wx = e - wy * ww;
       const int x = ipx + wx, y = ipy + wy;
@@ -731,6 +806,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
       lk_weights(q.x - (float)jx, q.y - (float)jy, &iw00, &iw01, &iw10, &iw11);
       const bool in_j = jx >= 0 && jy >= 0 && jx + ww + 1 <= cols && jy + wh + 1 <= rows;
       float b1 = 0.f, b2 = 0.f;
+#pragma unroll
       for (int e = lane; e < area; e += 32) {
         const int wy = e / ww, wx = e - wy * ww;
         const int diff = lk_sample_u8(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11, in_j) - (int)Iwin[e];
@@ -761,6 +837,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
       lk_weights(r.x - (float)jx, r.y - (float)jy, &iw00, &iw01, &iw10, &iw11);
       const bool in_j = jx >= 0 && jy >= 0 && jx + ww + 1 <= cols && jy + wh + 1 <= rows;
       float ev = 0.f;
+#pragma unroll
       for (int e = lane; e < area; e += 32) {
         const int wy = e / ww, wx = e - wy * ww;
         const int diff = lk_sample_u8(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11, in_j) - (int)Iwin[e];
@@ -804,6 +881,19 @@ static int upload_image(ofb_handle* h, SparseState* s, int which, const uint8_t*
   return OFB_OK;
 }
 
+// Scharr derivatives of every level of the pyramid `fp` of slot `which`.
+static int build_derivs(ofb_handle* h, SparseState* s, int which, FramePyr* fp) {
+  dim3 b(32, 8);
+  short2* d = s->deriv[which];
+  for (int l = 0; l < fp->n_levels; l++) {
+    k_scharr<<<g2(fp->w[l], fp->h[l], b), b, 0, h->stream>>>(fp->lv[l], fp->w[l], fp->h[l], (size_t)fp->w[l], d);
+    OFB_LAUNCH_CHECK(h);
+    fp->D[l] = d;
+    d += (size_t)fp->w[l] * fp->h[l];
+  }
+  return OFB_OK;
+}
+
 // Builds levels 1.. of the pyramid of slot `which` (level 0 = s->img[which]) and, with `derivs`, the Scharr derivatives
 // of every level.
 static int build_pyr(ofb_handle* h, SparseState* s, int which, int width, int height, int win_w, int win_h,
@@ -827,31 +917,24 @@ static int build_pyr(ofb_handle* h, SparseState* s, int which, int width, int he
     n++;
   }
   fp->n_levels = n;
-  short2* d = s->deriv[which];
-  for (int l = 0; l < n; l++) {
-    fp->D[l] = nullptr;
-    if (!derivs) continue;
-    k_scharr<<<g2(fp->w[l], fp->h[l], b), b, 0, h->stream>>>(fp->lv[l], fp->w[l], fp->h[l], (size_t)fp->w[l], d);
-    OFB_LAUNCH_CHECK(h);
-    fp->D[l] = d;
-    d += (size_t)fp->w[l] * fp->h[l];
-  }
-  return OFB_OK;
+  for (int l = 0; l < n; l++) fp->D[l] = nullptr;
+  return derivs ? build_derivs(h, s, which, fp) : OFB_OK;
 }
 
 static int eigen_map(ofb_handle* h, SparseState* s, int which, int width, int height, int block_size,
-                     const uint8_t* d_mask, int harris = 0, double harris_k = 0.04) {
+                     const uint8_t* d_mask, int harris = 0, double harris_k = 0.04, cudaStream_t sm = nullptr) {
+  if (!sm) sm = h->stream;
   const double scale = 1.0 / (4.0 * block_size * 255.0);
   const float k0 = (float)(1.0 * scale), k1 = (float)(2.0 * scale), k2 = (float)(1.0 * scale);
   dim3 b(32, 8);
-  SP_CUDA(h, cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned int), h->stream));
+  SP_CUDA(h, cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned int), sm));
   // columns past the last full block of 32 take the row filter's scalar tail (no FMA): the same on the AVX2 and the
   // AVX-512 dispatch of the wheel (tests/test_oracle_sparse.py probes both with OPENCV_CPU_DISABLE)
-  k_sobel_cov<<<g2(width, height, b), b, 0, h->stream>>>(s->img[which], width, height, (size_t)width, s->cov, k0, k1, k2,
-                                                         (width / 32) * 32);
-  OFB_LAUNCH_CHECK(h);
-  k_min_eig<<<g2(width, height, b), b, 0, h->stream>>>(s->cov, width, height, block_size, s->eig, s->counters + 1, d_mask, harris,
-                                                       (float)harris_k, harris_k);
+  const int rb = block_size / 2;
+  const size_t smem = (size_t)3 * (32 + 2 * rb) * (kEigTileH + 2 * rb) * sizeof(float);   // <= 34 KB at blockSize 31
+  k_sobel_min_eig<<<dim3((width + 31) / 32, (height + kEigTileH - 1) / kEigTileH), b, smem, sm>>>(
+      s->img[which], width, height, (size_t)width, k0, k1, k2, (width / 32) * 32, block_size, s->eig, s->counters + 1,
+      d_mask, harris, (float)harris_k, harris_k);
   OFB_LAUNCH_CHECK(h);
   return OFB_OK;
 }
@@ -868,9 +951,9 @@ static int validate_gftt(ofb_handle* h, const ofb_gftt_params* p, int width, int
 // goodFeaturesToTrack of the image in slot `which`; the list lands in s->corners[which], its length in
 // s->counters[4 + which] — both on the device, nothing is synchronised.
 static int detect_corners(ofb_handle* h, SparseState* s, int which, int width, int height, const ofb_gftt_params* p,
-                          const uint8_t* d_mask) {
-  cudaStream_t sm = h->stream;
-  int st = eigen_map(h, s, which, width, height, p->block_size, d_mask, p->use_harris_detector, p->harris_k);
+                          const uint8_t* d_mask, cudaStream_t sm = nullptr) {
+  if (!sm) sm = h->stream;
+  int st = eigen_map(h, s, which, width, height, p->block_size, d_mask, p->use_harris_detector, p->harris_k, sm);
   if (st) return st;
   SP_CUDA(h, cudaMemsetAsync(s->hist, 0, kBuckets * sizeof(unsigned int), sm));
   dim3 b(32, 8);
@@ -918,11 +1001,22 @@ static int lk_launch(ofb_handle* h, SparseState* s, const FramePyr& I, const Fra
   double eps = std::min(std::max(p->epsilon, 0.0), 10.0);
   eps *= eps;
   const size_t smem = (size_t)p->win_w * p->win_h * 3 * sizeof(short) * LK_WARPS;
-  if (smem > 48 * 1024)
-    OFB_CUDA(h, cudaFuncSetAttribute(k_lk_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_lk_track<<<(n_bound + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, smem, h->stream>>>(
-      lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound, n_dev, p->win_w, p->win_h, max_count, eps, p->flags,
-      p->min_eig_threshold);
+  const dim3 grid((n_bound + LK_WARPS - 1) / LK_WARPS);
+  if (p->win_w == 21 && p->win_h == 21) {        // cv2's default window
+    k_lk_track<21, 21><<<grid, LK_WARPS * 32, smem, h->stream>>>(lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound,
+                                                                 n_dev, 21, 21, max_count, eps, p->flags,
+                                                                 p->min_eig_threshold);
+  } else if (p->win_w == 15 && p->win_h == 15) {
+    k_lk_track<15, 15><<<grid, LK_WARPS * 32, smem, h->stream>>>(lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound,
+                                                                 n_dev, 15, 15, max_count, eps, p->flags,
+                                                                 p->min_eig_threshold);
+  } else {
+    if (smem > 48 * 1024)
+      OFB_CUDA(h, cudaFuncSetAttribute(k_lk_track<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_lk_track<0, 0><<<grid, LK_WARPS * 32, smem, h->stream>>>(lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound,
+                                                               n_dev, p->win_w, p->win_h, max_count, eps, p->flags,
+                                                               p->min_eig_threshold);
+  }
   OFB_LAUNCH_CHECK(h);
   return OFB_OK;
 }
@@ -1089,8 +1183,18 @@ int ofb_lk_stream(ofb_handle* h, const uint8_t* frame, int width, int height, si
   const int cur = S.primed ? (S.cur ^ 1) : 0, prv = cur ^ 1;
   cudaStream_t sm = h->stream;
   if ((st = upload_image(h, s, cur, frame, width, height, stride_bytes))) { S.primed = false; return st; }
-  // pyramid of the new frame, and its Scharr derivatives for the call in which it is the previous frame
-  if ((st = build_pyr(h, s, cur, width, height, lp->win_w, lp->win_h, lp->max_level, true, &S.fp[cur]))) { S.primed = false; return st; }
+  // Two chains behind the upload: tracker (pyramid of the new frame -> LK from the previous frame's corners) on the
+  // handle's stream, corner detection of the new frame (needs level 0 only) on the second stream.  They share no buffer:
+  // the tracker reads slot prv's corners / derivatives and slot cur's levels, the detector writes slot cur's corners and
+  // the detection scratch.  The new frame's Scharr derivatives — needed by the NEXT call, in which it is the previous
+  // frame — go behind the tracker.
+  const bool track = S.primed;
+  cudaStream_t sdet = track ? s->aux : sm;
+  if (track) {
+    OFB_CUDA(h, cudaEventRecord(s->ev_up, sm));
+    OFB_CUDA(h, cudaStreamWaitEvent(s->aux, s->ev_up, 0));
+  }
+  if ((st = build_pyr(h, s, cur, width, height, lp->win_w, lp->win_h, lp->max_level, false, &S.fp[cur]))) { S.primed = false; return st; }
   // result block in pinned memory: [count prev, count cur | next pts | err | new corners | status]
   char* hb = reinterpret_cast<char*>(s->h_stage);
   const size_t need = 64 + (size_t)bound * (8 + 4 + 8 + 1);
@@ -1100,16 +1204,20 @@ int ofb_lk_stream(ofb_handle* h, const uint8_t* frame, int width, int height, si
   float* h_err = h_next + 2 * (size_t)bound;
   float* h_new = h_err + bound;
   uint8_t* h_status = reinterpret_cast<uint8_t*>(h_new + 2 * (size_t)bound);
-  const bool track = S.primed;
   if (track) {
     if ((st = lk_launch(h, s, S.fp[prv], S.fp[cur], width, s->corners[prv], bound, s->counters + 4 + prv, lp))) { S.primed = false; return st; }
     OFB_CUDA(h, cudaMemcpyAsync(h_next, s->pts_next, (size_t)bound * sizeof(float2), cudaMemcpyDeviceToHost, sm));
     OFB_CUDA(h, cudaMemcpyAsync(h_status, s->lk_status, (size_t)bound, cudaMemcpyDeviceToHost, sm));
     OFB_CUDA(h, cudaMemcpyAsync(h_err, s->lk_err, (size_t)bound * sizeof(float), cudaMemcpyDeviceToHost, sm));
   }
-  if ((st = detect_corners(h, s, cur, width, height, gp, nullptr))) { S.primed = false; return st; }
-  OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters + 4, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sm));
-  OFB_CUDA(h, cudaMemcpyAsync(h_new, s->corners[cur], (size_t)bound * sizeof(float2), cudaMemcpyDeviceToHost, sm));
+  if ((st = detect_corners(h, s, cur, width, height, gp, nullptr, sdet))) { S.primed = false; return st; }
+  OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters + 4, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sdet));
+  OFB_CUDA(h, cudaMemcpyAsync(h_new, s->corners[cur], (size_t)bound * sizeof(float2), cudaMemcpyDeviceToHost, sdet));
+  if ((st = build_derivs(h, s, cur, &S.fp[cur]))) { S.primed = false; return st; }
+  if (track) {
+    OFB_CUDA(h, cudaEventRecord(s->ev_aux, s->aux));
+    OFB_CUDA(h, cudaStreamWaitEvent(sm, s->ev_aux, 0));
+  }
   OFB_CUDA(h, cudaStreamSynchronize(sm));
   const int n_cur = (int)std::min<unsigned int>(hc[cur], (unsigned int)bound);
   if (track) {
