@@ -216,37 +216,55 @@ __global__ void __launch_bounds__(256) k_scharr(const uint8_t* __restrict__ src,
 // (a c - b b) - k ((a + c)(a + c)) in float in the 8-wide body, (a c - b b) - (k (a + c)) (a + c) in the 4-wide step
 // behind it, and the last (w * h) % 4 pixels in double with the caller's double k (oracle/features_np.py::corner_harris).
 constexpr int kEigTileH = 16;
+// derivative products at image position (x, y) [already inside the image]; BORDER: the 3x3 neighbourhood may leave it
+template <bool BORDER>
+__device__ __forceinline__ void sobel_products(const uint8_t* __restrict__ src, int w, int h, size_t spitch, int x, int y,
+                                               float k0, float k1, float k2, int wb, double* pxx, double* pxy, double* pyy) {
+  int xm = x - 1, xp = x + 1, ym = y - 1, yp = y + 1;
+  if (BORDER) { xm = reflect101(xm, w); xp = reflect101(xp, w); ym = reflect101(ym, h); yp = reflect101(yp, h); }
+  const uint8_t* rows[3] = {src + (size_t)ym * spitch, src + (size_t)y * spitch, src + (size_t)yp * spitch};
+  float r[3], rw[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const float pm = u8f(rows[j][xm]), pc = u8f(rows[j][x]), pp = u8f(rows[j][xp]);   // (exact, off the XU pipe)
+    r[j] = pp - pm;
+    if (x < wb) rw[j] = fmaf(k2, pp, fmaf(k1, pc, __fmul_rn(k0, pm)));
+    else rw[j] = __fadd_rn(__fadd_rn(__fmul_rn(pm, k0), __fmul_rn(pc, k1)), __fmul_rn(pp, k2));
+  }
+  const float dx = fmaf(r[0] + r[2], k0, __fmul_rn(r[1], k1));
+  const float dy = rw[2] - rw[0];
+  *pxx = (double)__fmul_rn(dx, dx);
+  *pxy = (double)__fmul_rn(dx, dy);
+  *pyy = (double)__fmul_rn(dy, dy);
+}
+
 __global__ void __launch_bounds__(256) k_sobel_min_eig(const uint8_t* __restrict__ src, int w, int h, size_t spitch, float k0,
                                                        float k1, float k2, int wb, int block_size,
                                                        float* __restrict__ eig, unsigned int* __restrict__ max_bits,
                                                        const uint8_t* __restrict__ mask, int harris, float kf, double kd) {
-  extern __shared__ float cov_tile[];                // [3][th][tw]
+  // the products as doubles: one conversion per product instead of one per window tap (ncu on the float tile: the XU
+  // pipe — I2F of the pixels and F2F of the taps — was the busiest unit at 57 %)
+  extern __shared__ double cov_tile[];               // [3][th][tw]
   const int rb = block_size / 2, tw = 32 + 2 * rb, th = kEigTileH + 2 * rb, ta = tw * th;
-  float* cxx = cov_tile;
-  float* cxy = cov_tile + ta;
-  float* cyy = cov_tile + 2 * ta;
+  double* cxx = cov_tile;
+  double* cxy = cov_tile + ta;
+  double* cyy = cov_tile + 2 * ta;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int bx = blockIdx.x * 32, by = blockIdx.y * kEigTileH;
-  for (int i = tid; i < ta; i += 256) {
-    const int ty = i / tw, tx = i - ty * tw;
-    // (tile positions beyond the apron of the image's last row / column are never read: keep them in range)
-    const int x = reflect101(min(bx - rb + tx, w - 1 + rb), w), y = reflect101(min(by - rb + ty, h - 1 + rb), h);
-    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-    const uint8_t* rows[3] = {src + (size_t)reflect101(y - 1, h) * spitch, src + (size_t)y * spitch,
-                              src + (size_t)reflect101(y + 1, h) * spitch};
-    float r[3], rw[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const float pm = (float)rows[j][xm], pc = (float)rows[j][x], pp = (float)rows[j][xp];
-      r[j] = pp - pm;
-      if (x < wb) rw[j] = fmaf(k2, pp, fmaf(k1, pc, __fmul_rn(k0, pm)));
-      else rw[j] = __fadd_rn(__fadd_rn(__fmul_rn(pm, k0), __fmul_rn(pc, k1)), __fmul_rn(pp, k2));
+  // tile + apron + the Sobel neighbourhood inside the image: no border arithmetic in the whole CTA
+  const bool interior = bx - rb - 1 >= 0 && by - rb - 1 >= 0 && bx + 32 + rb + 1 <= w && by + kEigTileH + rb + 1 <= h;
+  if (interior) {
+    for (int i = tid; i < ta; i += 256) {
+      const int ty = i / tw, tx = i - ty * tw;
+      sobel_products<false>(src, w, h, spitch, bx - rb + tx, by - rb + ty, k0, k1, k2, wb, cxx + i, cxy + i, cyy + i);
     }
-    const float dx = fmaf(r[0] + r[2], k0, __fmul_rn(r[1], k1));
-    const float dy = rw[2] - rw[0];
-    cxx[i] = __fmul_rn(dx, dx);
-    cxy[i] = __fmul_rn(dx, dy);
-    cyy[i] = __fmul_rn(dy, dy);
+  } else {
+    for (int i = tid; i < ta; i += 256) {
+      const int ty = i / tw, tx = i - ty * tw;
+      // (tile positions beyond the apron of the image's last row / column are never read: keep them in range)
+      const int x = reflect101(min(bx - rb + tx, w - 1 + rb), w), y = reflect101(min(by - rb + ty, h - 1 + rb), h);
+      sobel_products<true>(src, w, h, spitch, x, y, k0, k1, k2, wb, cxx + i, cxy + i, cyy + i);
+    }
   }
   __syncthreads();
   const size_t n = (size_t)w * h;
@@ -260,9 +278,9 @@ __global__ void __launch_bounds__(256) k_sobel_min_eig(const uint8_t* __restrict
     for (int j = 0; j <= 2 * rb; j++) {
       const int ro = (ly + j) * tw + lx;
       for (int i = 0; i <= 2 * rb; i++) {
-        sxx += (double)cxx[ro + i];
-        sxy += (double)cxy[ro + i];
-        syy += (double)cyy[ro + i];
+        sxx += cxx[ro + i];
+        sxy += cxy[ro + i];
+        syy += cyy[ro + i];
       }
     }
     float e;
@@ -313,41 +331,50 @@ __device__ __forceinline__ CandRange cand_range(unsigned int max_bits, double qu
 }
 
 // threshold (THRESH_TOZERO at max*quality, strict >) + 3x3 local maximum, 1-px frame skipped, optional mask.
+// One CTA per 32 x 32 tile: the tile's candidates are collected in shared memory and the global list is extended once per
+// CTA (every candidate — then every warp — adding to the one counter itself was ~5e4 same-address atomics per 1080p frame,
+// which L2 serialises: the kernel took 39 us for 8 MB of input).
+constexpr int kCandTile = 32;
 __global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ eig, int w, int h, double quality,
                                                     const unsigned int* __restrict__ max_bits,
                                                     unsigned long long* __restrict__ keys, unsigned int* __restrict__ count,
                                                     unsigned int cap, unsigned int* __restrict__ hist,
                                                     const uint8_t* __restrict__ mask) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  __shared__ unsigned long long s_keys[kCandTile * kCandTile];
+  __shared__ unsigned int s_n, s_base;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
   float thr;
   const CandRange cr = cand_range(*max_bits, quality, &thr);
-  float v = 0.f;
-  bool cand = false;
-  if (x < w - 1 && y < h - 1) {
-    v = eig[(size_t)y * w + x];
-    if (v > thr) {
-      float mx = v;
+  const int x = blockIdx.x * kCandTile + threadIdx.x + 1;
 #pragma unroll
-      for (int j = -1; j <= 1; j++)
+  for (int r = 0; r < kCandTile / 8; r++) {
+    const int y = blockIdx.y * kCandTile + threadIdx.y + 8 * r + 1;
+    if (x >= w - 1 || y >= h - 1) continue;
+    const float v = eig[(size_t)y * w + x];
+    if (!(v > thr)) continue;
+    float mx = v;
 #pragma unroll
-        for (int i = -1; i <= 1; i++) mx = fmaxf(mx, eig[(size_t)(y + j) * w + x + i]);
-      cand = v == mx && !(mask && mask[(size_t)y * w + x] == 0);
-    }
+    for (int j = -1; j <= 1; j++)
+#pragma unroll
+      for (int i = -1; i <= 1; i++) mx = fmaxf(mx, eig[(size_t)(y + j) * w + x + i]);
+    if (v != mx) continue;
+    if (mask && mask[(size_t)y * w + x] == 0) continue;
+    s_keys[atomicAdd(&s_n, 1u)] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * w + x);
   }
-  // one counter update per warp (a warp is one 32-pixel row segment of the 32 x 8 block): every candidate adding to the
-  // one counter itself serialised ~1e5 same-address atomics per frame in L2
-  const unsigned int bal = __ballot_sync(0xffffffffu, cand);
-  if (bal == 0u) return;
-  const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
-  unsigned int base = 0;
-  if (lane == leader) base = atomicAdd(count, (unsigned int)__popc(bal));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (!cand) return;
-  const unsigned int slot = base + __popc(bal & ((1u << lane) - 1u));
-  if (slot < cap) {
-    keys[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * w + x);
-    atomicAdd(&hist[min((__float_as_uint(v) - cr.thr_bits) >> cr.shift, (unsigned int)kBuckets - 1u)], 1u);
+  __syncthreads();
+  const unsigned int n = s_n;
+  if (n == 0u) return;
+  if (tid == 0) s_base = atomicAdd(count, n);
+  __syncthreads();
+  for (unsigned int i = tid; i < n; i += 256) {
+    const unsigned int slot = s_base + i;
+    if (slot < cap) {
+      const unsigned long long key = s_keys[i];
+      keys[slot] = key;
+      atomicAdd(&hist[min(((unsigned int)(key >> 32) - cr.thr_bits) >> cr.shift, (unsigned int)kBuckets - 1u)], 1u);
+    }
   }
 }
 
@@ -711,6 +738,105 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr int LK_WARPS = 4;
 
+// The window passes of the tracker, with the border decision as a template argument: whether the window (plus the
+// bilinear neighbour) lies inside the level is uniform over the warp and decided ONCE per pass — inside the loops it
+// was a branch (with reconvergence bookkeeping) per load: ncu counted 120-170 SASS instructions per window pixel,
+// a tenth of them branches.  Same arithmetic in the same order.
+template <bool INTERIOR, int TW, int TH>
+__device__ __forceinline__ void lk_window_build(const uint8_t* __restrict__ I, const short2* __restrict__ D, size_t pitch,
+                                                int cols, int rows, int ipx, int ipy, int iw00, int iw01, int iw10, int iw11,
+                                                int ww, int area, int lane, short* Iwin, short* dIx, short* dIy,
+                                                float* pa11, float* pa12, float* pa22) {
+  float a11 = 0.f, a12 = 0.f, a22 = 0.f;
+  auto step = [&](int e) {
+    const int wy = e / ww, wx = e - wy * ww;
+    const int x = ipx + wx, y = ipy + wy;
+    int ival;
+    short2 d00, d01, d10, d11;
+    if (INTERIOR) {
+      const uint8_t* r0 = I + (size_t)y * pitch + x;
+      const uint8_t* r1 = r0 + pitch;
+      ival = descale((int)r0[0] * iw00 + (int)r0[1] * iw01 + (int)r1[0] * iw10 + (int)r1[1] * iw11, 9);
+      const short2* q0 = D + (size_t)y * cols + x;
+      const short2* q1 = q0 + cols;
+      d00 = q0[0]; d01 = q0[1]; d10 = q1[0]; d11 = q1[1];
+    } else {
+      ival = lk_sample_u8(I, pitch, cols, rows, x, y, iw00, iw01, iw10, iw11, false);
+      d00 = lk_deriv_at(D, cols, rows, x, y); d01 = lk_deriv_at(D, cols, rows, x + 1, y);
+      d10 = lk_deriv_at(D, cols, rows, x, y + 1); d11 = lk_deriv_at(D, cols, rows, x + 1, y + 1);
+    }
+    const int ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
+    const int iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
+    Iwin[e] = (short)ival;
+    dIx[e] = (short)ix;
+    dIy[e] = (short)iy;
+    a11 += (float)(ix * ix);
+    a12 += (float)(ix * iy);
+    a22 += (float)(iy * iy);
+  };
+  if (INTERIOR) {
+#pragma unroll
+    for (int e = lane; e < area; e += 32) step(e);
+  } else {           // the border form is rare: keep it small
+#pragma unroll 1
+    for (int e = lane; e < area; e += 32) step(e);
+  }
+  *pa11 = a11; *pa12 = a12; *pa22 = a22;
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ int lk_sample_j(const uint8_t* __restrict__ J, size_t pitch, int cols, int rows, int x, int y,
+                                           int iw00, int iw01, int iw10, int iw11) {
+  if (INTERIOR) {
+    const uint8_t* r0 = J + (size_t)y * pitch + x;
+    const uint8_t* r1 = r0 + pitch;
+    return descale((int)r0[0] * iw00 + (int)r0[1] * iw01 + (int)r1[0] * iw10 + (int)r1[1] * iw11, 9);
+  }
+  return lk_sample_u8(J, pitch, cols, rows, x, y, iw00, iw01, iw10, iw11, false);
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ void lk_window_mismatch(const uint8_t* __restrict__ J, size_t pitch, int cols, int rows, int jx,
+                                                   int jy, int iw00, int iw01, int iw10, int iw11, int ww, int area, int lane,
+                                                   const short* Iwin, const short* dIx, const short* dIy, float* pb1,
+                                                   float* pb2) {
+  float b1 = 0.f, b2 = 0.f;
+  auto step = [&](int e) {
+    const int wy = e / ww, wx = e - wy * ww;
+    const int diff = lk_sample_j<INTERIOR>(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11) - (int)Iwin[e];
+    b1 += (float)(diff * (int)dIx[e]);
+    b2 += (float)(diff * (int)dIy[e]);
+  };
+  if (INTERIOR) {
+#pragma unroll
+    for (int e = lane; e < area; e += 32) step(e);
+  } else {           // the border form is rare: keep it small
+#pragma unroll 1
+    for (int e = lane; e < area; e += 32) step(e);
+  }
+  *pb1 = b1; *pb2 = b2;
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ float lk_window_abs_error(const uint8_t* __restrict__ J, size_t pitch, int cols, int rows, int jx,
+                                                     int jy, int iw00, int iw01, int iw10, int iw11, int ww, int area,
+                                                     int lane, const short* Iwin) {
+  float ev = 0.f;
+  auto step = [&](int e) {
+    const int wy = e / ww, wx = e - wy * ww;
+    const int diff = lk_sample_j<INTERIOR>(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11) - (int)Iwin[e];
+    ev += fabsf((float)diff);
+  };
+  if (INTERIOR) {
+#pragma unroll
+    for (int e = lane; e < area; e += 32) step(e);
+  } else {           // the border form is rare: keep it small
+#pragma unroll 1
+    for (int e = lane; e < area; e += 32) step(e);
+  }
+  return ev;
+}
+
 // TW x TH: the window as a compile-time constant (0 = run time).  The window loops then have a constant trip count and
 // unroll completely: the 4 byte loads of all ceil(area / 32) window pixels of a lane are in flight together instead of
 // one dependent round trip per step, and e / ww is a multiply.  The arithmetic and its order are the same (same bits).
@@ -762,24 +888,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
     int iw00, iw01, iw10, iw11;
     lk_weights(pp.x - (float)ipx, pp.y - (float)ipy, &iw00, &iw01, &iw10, &iw11);
     const bool in_i = ipx >= 0 && ipy >= 0 && ipx + ww + 1 <= cols && ipy + wh + 1 <= rows;
-    float a11 = 0.f, a12 = 0.f, a22 = 0.f;
+    float a11, a12, a22;
     __syncwarp();
-#pragma unroll
-    for (int e = lane; e < area; e += 32) {
-      const int wy = e / ww, wx = e - wy * ww;
-      const int x = ipx + wx, y = ipy + wy;
-      const int ival = lk_sample_u8(I, pitch, cols, rows, x, y, iw00, iw01, iw10, iw11, in_i);
-      const short2 d00 = lk_deriv_at(D, cols, rows, x, y), d01 = lk_deriv_at(D, cols, rows, x + 1, y);
-      const short2 d10 = lk_deriv_at(D, cols, rows, x, y + 1), d11 = lk_deriv_at(D, cols, rows, x + 1, y + 1);
-      const int ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
-      const int iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
-      Iwin[e] = (short)ival;
-      dIx[e] = (short)ix;
-      dIy[e] = (short)iy;
-      a11 += (float)(ix * ix);
-      a12 += (float)(ix * iy);
-      a22 += (float)(iy * iy);
-    }
+    if (in_i) lk_window_build<true, TW, TH>(I, D, pitch, cols, rows, ipx, ipy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &a11, &a12, &a22);
+    else lk_window_build<false, TW, TH>(I, D, pitch, cols, rows, ipx, ipy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &a11, &a12, &a22);
     __syncwarp();
     const float A11 = __fmul_rn(warp_sum(a11), FLT_SCALE), A12 = __fmul_rn(warp_sum(a12), FLT_SCALE),
                 A22 = __fmul_rn(warp_sum(a22), FLT_SCALE);
@@ -805,14 +917,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
       }
       lk_weights(q.x - (float)jx, q.y - (float)jy, &iw00, &iw01, &iw10, &iw11);
       const bool in_j = jx >= 0 && jy >= 0 && jx + ww + 1 <= cols && jy + wh + 1 <= rows;
-      float b1 = 0.f, b2 = 0.f;
-#pragma unroll
-      for (int e = lane; e < area; e += 32) {
-        const int wy = e / ww, wx = e - wy * ww;
-        const int diff = lk_sample_u8(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11, in_j) - (int)Iwin[e];
-        b1 += (float)(diff * (int)dIx[e]);
-        b2 += (float)(diff * (int)dIy[e]);
-      }
+      float b1, b2;
+      if (in_j) lk_window_mismatch<true>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &b1, &b2);
+      else lk_window_mismatch<false>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &b1, &b2);
       const float B1 = __fmul_rn(warp_sum(b1), FLT_SCALE), B2 = __fmul_rn(warp_sum(b2), FLT_SCALE);
       const float2 delta = make_float2(__fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), Dt),
                                        __fmul_rn(__fsub_rn(__fmul_rn(A12, B1), __fmul_rn(A11, B2)), Dt));
@@ -836,13 +943,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
       }
       lk_weights(r.x - (float)jx, r.y - (float)jy, &iw00, &iw01, &iw10, &iw11);
       const bool in_j = jx >= 0 && jy >= 0 && jx + ww + 1 <= cols && jy + wh + 1 <= rows;
-      float ev = 0.f;
-#pragma unroll
-      for (int e = lane; e < area; e += 32) {
-        const int wy = e / ww, wx = e - wy * ww;
-        const int diff = lk_sample_u8(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11, in_j) - (int)Iwin[e];
-        ev += fabsf((float)diff);
-      }
+      const float ev = in_j ? lk_window_abs_error<true>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin)
+                            : lk_window_abs_error<false>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin);
       er = __fdiv_rn(warp_sum(ev), (float)(32 * ww * wh));
     }
   }
@@ -931,7 +1033,9 @@ static int eigen_map(ofb_handle* h, SparseState* s, int which, int width, int he
   // columns past the last full block of 32 take the row filter's scalar tail (no FMA): the same on the AVX2 and the
   // AVX-512 dispatch of the wheel (tests/test_oracle_sparse.py probes both with OPENCV_CPU_DISABLE)
   const int rb = block_size / 2;
-  const size_t smem = (size_t)3 * (32 + 2 * rb) * (kEigTileH + 2 * rb) * sizeof(float);   // <= 34 KB at blockSize 31
+  const size_t smem = (size_t)3 * (32 + 2 * rb) * (kEigTileH + 2 * rb) * sizeof(double);   // 14.7 KB at blockSize 3, 68 KB at 31
+  if (smem > 48 * 1024)
+    SP_CUDA(h, cudaFuncSetAttribute(k_sobel_min_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_sobel_min_eig<<<dim3((width + 31) / 32, (height + kEigTileH - 1) / kEigTileH), b, smem, sm>>>(
       s->img[which], width, height, (size_t)width, k0, k1, k2, (width / 32) * 32, block_size, s->eig, s->counters + 1,
       d_mask, harris, (float)harris_k, harris_k);
@@ -957,7 +1061,7 @@ static int detect_corners(ofb_handle* h, SparseState* s, int which, int width, i
   if (st) return st;
   SP_CUDA(h, cudaMemsetAsync(s->hist, 0, kBuckets * sizeof(unsigned int), sm));
   dim3 b(32, 8);
-  k_candidates<<<g2(width - 2, height - 2, b), b, 0, sm>>>(s->eig, width, height, p->quality_level, s->counters + 1,
+  k_candidates<<<dim3((width - 2 + kCandTile - 1) / kCandTile, (height - 2 + kCandTile - 1) / kCandTile), b, 0, sm>>>(s->eig, width, height, p->quality_level, s->counters + 1,
                                                           s->keys, s->counters, (unsigned int)s->cand_cap, s->hist, d_mask);
   OFB_LAUNCH_CHECK(h);
   k_bucket_sums<<<kBuckets / 1024, 1024, 0, sm>>>(s->hist, s->bpart);
