@@ -17,6 +17,7 @@
 // ofb_lk_stream keeps a camera's temporal state (previous frame's pyramid, Scharr derivatives and corner
 // list) on the GPU: one upload per frame.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "fb_device.cuh"
@@ -54,6 +55,9 @@ struct SparseState {
   float2* corners[2] = {nullptr, nullptr};     // accepted corners of a slot (device)
   uint8_t* mask = nullptr;                     // goodFeaturesToTrack mask (device), allocated on first use
   float2* pts_prev = nullptr;                  // LK inputs / outputs (device)
+  // LK results of a call over n points, one block [next pts n x 8 | err n x 4 | status n] so that one copy brings
+  // them back (lk_out_layout sets the three pointers for the call's n)
+  char* lk_out = nullptr;
   float2* pts_next = nullptr;
   uint8_t* lk_status = nullptr;
   float* lk_err = nullptr;
@@ -71,17 +75,31 @@ struct SparseState {
     ofb_gftt_params gp = {};
     ofb_lk_params lp = {};
     FramePyr fp[2];
+    // the launch sequence of a tracking call with the new frame in slot 0 / 1, captured once (CUDA graph): ~30 launches,
+    // copies and event calls per frame become one launch — the driver's launch path is what 8 camera threads contend for
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    uint64_t graph_launches[2] = {0, 0};
+    const void* graph_out = nullptr;           // lk_out / bound the graphs were captured with
+    int graph_bound = 0;
     int n_host[2] = {0, 0};                    // corner count of a slot as last downloaded
     std::vector<float> host_corners[2];        // ... and the list itself (what the next call reports as prev_pts)
   } st;
 };
 
+static void stream_graphs_drop(SparseState* s) {
+  for (int i = 0; i < 2; i++) {
+    if (s->st.graph[i]) cudaGraphExecDestroy(s->st.graph[i]);
+    s->st.graph[i] = nullptr;
+  }
+}
+
 static void sparse_free(SparseState* s) {
   if (!s) return;
+  stream_graphs_drop(s);
   for (int i = 0; i < 2; i++) { cudaFree(s->img[i]); cudaFree(s->pyr[i]); cudaFree(s->deriv[i]); cudaFree(s->corners[i]); }
   cudaFree(s->eig); cudaFree(s->keys); cudaFree(s->sortbuf); cudaFree(s->hist); cudaFree(s->bstart);
   cudaFree(s->counters); cudaFree(s->bpart); cudaFree(s->grid_cnt); cudaFree(s->grid_pts); cudaFree(s->mask);
-  cudaFree(s->pts_prev); cudaFree(s->pts_next); cudaFree(s->lk_status); cudaFree(s->lk_err);
+  cudaFree(s->pts_prev); cudaFree(s->lk_out);
   if (s->h_stage) cudaFreeHost(s->h_stage);
   if (s->aux) cudaStreamDestroy(s->aux);
   if (s->ev_up) cudaEventDestroy(s->ev_up);
@@ -140,16 +158,20 @@ static int sparse_get(ofb_handle* h, SparseState** out) {
 
 static int sparse_points(ofb_handle* h, SparseState* s, int n) {
   if (n <= s->pts_cap) return OFB_OK;
-  cudaFree(s->pts_prev); cudaFree(s->pts_next); cudaFree(s->lk_status); cudaFree(s->lk_err);
-  s->pts_prev = s->pts_next = nullptr; s->lk_status = nullptr; s->lk_err = nullptr;
+  cudaFree(s->pts_prev); cudaFree(s->lk_out);
+  s->pts_prev = s->pts_next = nullptr; s->lk_out = nullptr; s->lk_status = nullptr; s->lk_err = nullptr;
   s->pts_cap = 0;
   const int cap = std::max(n, 4096);
   SP_CUDA(h, cudaMalloc(&s->pts_prev, cap * sizeof(float2)));
-  SP_CUDA(h, cudaMalloc(&s->pts_next, cap * sizeof(float2)));
-  SP_CUDA(h, cudaMalloc(&s->lk_status, cap));
-  SP_CUDA(h, cudaMalloc(&s->lk_err, cap * sizeof(float)));
+  SP_CUDA(h, cudaMalloc(&s->lk_out, (size_t)cap * 13));
   s->pts_cap = cap;
   return OFB_OK;
+}
+
+static void lk_out_layout(SparseState* s, int n) {
+  s->pts_next = reinterpret_cast<float2*>(s->lk_out);
+  s->lk_err = reinterpret_cast<float*>(s->lk_out + (size_t)n * 8);
+  s->lk_status = reinterpret_cast<uint8_t*>(s->lk_out + (size_t)n * 12);
 }
 
 // ======================================================================================
@@ -560,13 +582,18 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
       __syncthreads();
     } else {
       if (pos >= total) break;
-      unsigned int rb_end = rb;
-      for (;;) {                                     // how many whole buckets fit into one round
-        const unsigned int probe = rb_end + 1 + tid;
-        const bool ok = probe <= (unsigned int)kBuckets && bstart[probe] - pos <= (unsigned int)GS_THREADS;
-        const unsigned int adv = (unsigned int)__syncthreads_count(ok);
-        rb_end += adv;
-        if (adv < (unsigned int)GS_THREADS || rb_end >= (unsigned int)kBuckets) break;
+      // how many whole buckets fit into one round: bstart is non-decreasing, so "fits" is a prefix property and the CTA
+      // finds its end in two probes — every 64th bucket behind rb, then the 64 buckets behind the last fitting one
+      // (walking 1024 buckets per step took up to 64 dependent L2 round trips in the sparse strong end of the range)
+      static_assert(GS_THREADS * 64 >= kBuckets, "coarse probes cover every bucket");
+      unsigned int rb_end;
+      {
+        const unsigned int p1 = rb + ((unsigned int)tid + 1u) * 64u;
+        const bool ok1 = p1 <= (unsigned int)kBuckets && bstart[p1] - pos <= (unsigned int)GS_THREADS;
+        const unsigned int base = rb + 64u * (unsigned int)__syncthreads_count(ok1);
+        const unsigned int p2 = base + 1u + (unsigned int)tid;
+        const bool ok2 = tid < 64 && p2 <= (unsigned int)kBuckets && bstart[p2] - pos <= (unsigned int)GS_THREADS;
+        rb_end = base + (unsigned int)__syncthreads_count(ok2);
       }
       if (rb_end == rb) {
         // the strongest remaining bucket alone is larger than a round: order it in global memory first
@@ -737,12 +764,46 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 constexpr int LK_WARPS = 4;
+#ifndef OFB_LK_WPP
+#define OFB_LK_WPP 2          // warps per point of k_lk_track_cta at the 21 x 21 window
+#endif
+
+// Unroll factor of the interior window loops (experiment builds: -DOFB_LK_UNROLL=n; default: complete).
+#define OFB_PRAGMA_(x) _Pragma(#x)
+#define OFB_PRAGMA(x) OFB_PRAGMA_(x)
+#ifdef OFB_LK_UNROLL
+#define OFB_LK_PRAGMA_UNROLL OFB_PRAGMA(unroll OFB_LK_UNROLL)
+#else
+#define OFB_LK_PRAGMA_UNROLL OFB_PRAGMA(unroll)
+#endif
 
 // The window passes of the tracker, with the border decision as a template argument: whether the window (plus the
 // bilinear neighbour) lies inside the level is uniform over the warp and decided ONCE per pass — inside the loops it
 // was a branch (with reconvergence bookkeeping) per load: ncu counted 120-170 SASS instructions per window pixel,
 // a tenth of them branches.  Same arithmetic in the same order.
-template <bool INTERIOR, int TW, int TH>
+//   MODE 0: window inside the level.   MODE 1: window crosses the border of a level at least as large as the window (every
+//   pyramid level cv2 builds): REFLECT_101 is a single branch-free reflection, the derivative's constant border a
+//   predicated load.  The launch lasts as long as its slowest warp, and the slowest warps were the points within half a
+//   window of the border of the COARSEST level (88 px at level 0: a quarter of the corners of a 1080p frame) on the
+//   generic path.   MODE 2: generic (multiple reflections; level 0 smaller than the window).
+template <int MODE>
+__device__ __forceinline__ int lk_sample_j(const uint8_t* __restrict__ J, size_t pitch, int cols, int rows, int x, int y,
+                                           int iw00, int iw01, int iw10, int iw11) {
+  if (MODE == 0) {
+    const uint8_t* r0 = J + (size_t)y * pitch + x;
+    const uint8_t* r1 = r0 + pitch;
+    return descale((int)r0[0] * iw00 + (int)r0[1] * iw01 + (int)r1[0] * iw10 + (int)r1[1] * iw11, 9);
+  }
+  if (MODE == 1) {      // every coordinate overshoots by less than the level's size: one reflection, no branches
+    const int x0 = reflect101_once(x, cols), x1 = reflect101_once(x + 1, cols);
+    const uint8_t* r0 = J + (size_t)reflect101_once(y, rows) * pitch;
+    const uint8_t* r1 = J + (size_t)reflect101_once(y + 1, rows) * pitch;
+    return descale((int)r0[x0] * iw00 + (int)r0[x1] * iw01 + (int)r1[x0] * iw10 + (int)r1[x1] * iw11, 9);
+  }
+  return lk_sample_u8(J, pitch, cols, rows, x, y, iw00, iw01, iw10, iw11, false);
+}
+
+template <int MODE, int TW, int TH>
 __device__ __forceinline__ void lk_window_build(const uint8_t* __restrict__ I, const short2* __restrict__ D, size_t pitch,
                                                 int cols, int rows, int ipx, int ipy, int iw00, int iw01, int iw10, int iw11,
                                                 int ww, int area, int lane, short* Iwin, short* dIx, short* dIy,
@@ -753,13 +814,21 @@ __device__ __forceinline__ void lk_window_build(const uint8_t* __restrict__ I, c
     const int x = ipx + wx, y = ipy + wy;
     int ival;
     short2 d00, d01, d10, d11;
-    if (INTERIOR) {
+    if (MODE == 0) {
       const uint8_t* r0 = I + (size_t)y * pitch + x;
       const uint8_t* r1 = r0 + pitch;
       ival = descale((int)r0[0] * iw00 + (int)r0[1] * iw01 + (int)r1[0] * iw10 + (int)r1[1] * iw11, 9);
       const short2* q0 = D + (size_t)y * cols + x;
       const short2* q1 = q0 + cols;
       d00 = q0[0]; d01 = q0[1]; d10 = q1[0]; d11 = q1[1];
+    } else if (MODE == 1) {
+      ival = lk_sample_j<1>(I, pitch, cols, rows, x, y, iw00, iw01, iw10, iw11);
+      const bool xa = (unsigned)x < (unsigned)cols, xb = (unsigned)(x + 1) < (unsigned)cols;
+      const bool ya = (unsigned)y < (unsigned)rows, yb = (unsigned)(y + 1) < (unsigned)rows;
+      const short2* q0 = D + (ptrdiff_t)y * cols + x;    // (only dereferenced where inside)
+      const short2* q1 = q0 + cols;
+      const short2 z = make_short2(0, 0);                // constant-0 border of the derivative image
+      d00 = xa && ya ? q0[0] : z; d01 = xb && ya ? q0[1] : z; d10 = xa && yb ? q1[0] : z; d11 = xb && yb ? q1[1] : z;
     } else {
       ival = lk_sample_u8(I, pitch, cols, rows, x, y, iw00, iw01, iw10, iw11, false);
       d00 = lk_deriv_at(D, cols, rows, x, y); d01 = lk_deriv_at(D, cols, rows, x + 1, y);
@@ -774,28 +843,17 @@ __device__ __forceinline__ void lk_window_build(const uint8_t* __restrict__ I, c
     a12 += (float)(ix * iy);
     a22 += (float)(iy * iy);
   };
-  if (INTERIOR) {
-#pragma unroll
+  if (MODE != 2) {
+    OFB_LK_PRAGMA_UNROLL
     for (int e = lane; e < area; e += 32) step(e);
-  } else {           // the border form is rare: keep it small
+  } else {           // (windows larger than the level: rare, keep it small)
 #pragma unroll 1
     for (int e = lane; e < area; e += 32) step(e);
   }
   *pa11 = a11; *pa12 = a12; *pa22 = a22;
 }
 
-template <bool INTERIOR>
-__device__ __forceinline__ int lk_sample_j(const uint8_t* __restrict__ J, size_t pitch, int cols, int rows, int x, int y,
-                                           int iw00, int iw01, int iw10, int iw11) {
-  if (INTERIOR) {
-    const uint8_t* r0 = J + (size_t)y * pitch + x;
-    const uint8_t* r1 = r0 + pitch;
-    return descale((int)r0[0] * iw00 + (int)r0[1] * iw01 + (int)r1[0] * iw10 + (int)r1[1] * iw11, 9);
-  }
-  return lk_sample_u8(J, pitch, cols, rows, x, y, iw00, iw01, iw10, iw11, false);
-}
-
-template <bool INTERIOR>
+template <int MODE>
 __device__ __forceinline__ void lk_window_mismatch(const uint8_t* __restrict__ J, size_t pitch, int cols, int rows, int jx,
                                                    int jy, int iw00, int iw01, int iw10, int iw11, int ww, int area, int lane,
                                                    const short* Iwin, const short* dIx, const short* dIy, float* pb1,
@@ -803,34 +861,34 @@ __device__ __forceinline__ void lk_window_mismatch(const uint8_t* __restrict__ J
   float b1 = 0.f, b2 = 0.f;
   auto step = [&](int e) {
     const int wy = e / ww, wx = e - wy * ww;
-    const int diff = lk_sample_j<INTERIOR>(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11) - (int)Iwin[e];
+    const int diff = lk_sample_j<MODE>(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11) - (int)Iwin[e];
     b1 += (float)(diff * (int)dIx[e]);
     b2 += (float)(diff * (int)dIy[e]);
   };
-  if (INTERIOR) {
-#pragma unroll
+  if (MODE != 2) {
+    OFB_LK_PRAGMA_UNROLL
     for (int e = lane; e < area; e += 32) step(e);
-  } else {           // the border form is rare: keep it small
+  } else {           // (windows larger than the level: rare, keep it small)
 #pragma unroll 1
     for (int e = lane; e < area; e += 32) step(e);
   }
   *pb1 = b1; *pb2 = b2;
 }
 
-template <bool INTERIOR>
+template <int MODE>
 __device__ __forceinline__ float lk_window_abs_error(const uint8_t* __restrict__ J, size_t pitch, int cols, int rows, int jx,
                                                      int jy, int iw00, int iw01, int iw10, int iw11, int ww, int area,
                                                      int lane, const short* Iwin) {
   float ev = 0.f;
   auto step = [&](int e) {
     const int wy = e / ww, wx = e - wy * ww;
-    const int diff = lk_sample_j<INTERIOR>(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11) - (int)Iwin[e];
+    const int diff = lk_sample_j<MODE>(J, pitch, cols, rows, jx + wx, jy + wy, iw00, iw01, iw10, iw11) - (int)Iwin[e];
     ev += fabsf((float)diff);
   };
-  if (INTERIOR) {
-#pragma unroll
+  if (MODE != 2) {
+    OFB_LK_PRAGMA_UNROLL
     for (int e = lane; e < area; e += 32) step(e);
-  } else {           // the border form is rare: keep it small
+  } else {           // (windows larger than the level: rare, keep it small)
 #pragma unroll 1
     for (int e = lane; e < area; e += 32) step(e);
   }
@@ -890,8 +948,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
     const bool in_i = ipx >= 0 && ipy >= 0 && ipx + ww + 1 <= cols && ipy + wh + 1 <= rows;
     float a11, a12, a22;
     __syncwarp();
-    if (in_i) lk_window_build<true, TW, TH>(I, D, pitch, cols, rows, ipx, ipy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &a11, &a12, &a22);
-    else lk_window_build<false, TW, TH>(I, D, pitch, cols, rows, ipx, ipy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &a11, &a12, &a22);
+    const bool small = cols <= ww || rows <= wh;       // a coordinate may need more than one reflection
+    if (in_i) lk_window_build<0, TW, TH>(I, D, pitch, cols, rows, ipx, ipy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &a11, &a12, &a22);
+    else if (!small) lk_window_build<1, TW, TH>(I, D, pitch, cols, rows, ipx, ipy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &a11, &a12, &a22);
+    else lk_window_build<2, TW, TH>(I, D, pitch, cols, rows, ipx, ipy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &a11, &a12, &a22);
     __syncwarp();
     const float A11 = __fmul_rn(warp_sum(a11), FLT_SCALE), A12 = __fmul_rn(warp_sum(a12), FLT_SCALE),
                 A22 = __fmul_rn(warp_sum(a22), FLT_SCALE);
@@ -918,8 +978,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
       lk_weights(q.x - (float)jx, q.y - (float)jy, &iw00, &iw01, &iw10, &iw11);
       const bool in_j = jx >= 0 && jy >= 0 && jx + ww + 1 <= cols && jy + wh + 1 <= rows;
       float b1, b2;
-      if (in_j) lk_window_mismatch<true>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &b1, &b2);
-      else lk_window_mismatch<false>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &b1, &b2);
+      if (in_j) lk_window_mismatch<0>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &b1, &b2);
+      else if (!small) lk_window_mismatch<1>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &b1, &b2);
+      else lk_window_mismatch<2>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin, dIx, dIy, &b1, &b2);
       const float B1 = __fmul_rn(warp_sum(b1), FLT_SCALE), B2 = __fmul_rn(warp_sum(b2), FLT_SCALE);
       const float2 delta = make_float2(__fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), Dt),
                                        __fmul_rn(__fsub_rn(__fmul_rn(A12, B1), __fmul_rn(A11, B2)), Dt));
@@ -943,12 +1004,211 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(LkLevels lv, const f
       }
       lk_weights(r.x - (float)jx, r.y - (float)jy, &iw00, &iw01, &iw10, &iw11);
       const bool in_j = jx >= 0 && jy >= 0 && jx + ww + 1 <= cols && jy + wh + 1 <= rows;
-      const float ev = in_j ? lk_window_abs_error<true>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin)
-                            : lk_window_abs_error<false>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin);
+      const float ev = in_j ? lk_window_abs_error<0>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin)
+                       : !small ? lk_window_abs_error<1>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin)
+                                : lk_window_abs_error<2>(J, pitch, cols, rows, jx, jy, iw00, iw01, iw10, iw11, ww, area, lane, Iwin);
       er = __fdiv_rn(warp_sum(ev), (float)(32 * ww * wh));
     }
   }
   if (lane == 0) {
+    next_pts[pid] = np;
+    status[pid] = st ? 1 : 0;
+    err[pid] = er;
+  }
+}
+
+// ---- the tracker with ONE POINT PER CTA of WPP warps (fixed window TW x TH) -------------------------------------------------
+// k_lk_track above lasts as long as its slowest warp: all points are resident at once (2000 warps on 148 SMs), every warp
+// walks its 4 levels x (1 build + up to 30 mismatch passes) alone, and a pass over a 21 x 21 window is 14 pixels per lane
+// (ncu: 28 M warp-instructions, 14 k per warp, 6.6 cycles per instruction with 2.4 warps per scheduler: 103 us, the
+// average warp done after half of that).  Here the window of a point is spread over WPP warps: TW * TH / (32 WPP) pixels
+// per thread, whose patch values stay in REGISTERS (a thread only ever re-reads the pixels it built: no shared-memory
+// patch), partial sums meet through one double-buffered shared-memory slot and one barrier per pass, and every thread
+// carries the point's scalar state redundantly (uniform control flow, no broadcast).  The float sums are taken in a
+// different order than in the warp kernel (and than cv2's): positions agree within the contract tolerance, not bit for bit.
+template <int MODE>
+__device__ __forceinline__ void lk_build_px(const uint8_t* __restrict__ I, const short2* __restrict__ D, size_t pitch,
+                                            int cols, int rows, int x, int y, int iw00, int iw01, int iw10, int iw11,
+                                            int* ival, int* ix, int* iy) {
+  short2 d00, d01, d10, d11;
+  *ival = lk_sample_j<MODE>(I, pitch, cols, rows, x, y, iw00, iw01, iw10, iw11);
+  if (MODE == 0) {
+    const short2* q0 = D + (size_t)y * cols + x;
+    const short2* q1 = q0 + cols;
+    d00 = q0[0]; d01 = q0[1]; d10 = q1[0]; d11 = q1[1];
+  } else {
+    d00 = lk_deriv_at(D, cols, rows, x, y); d01 = lk_deriv_at(D, cols, rows, x + 1, y);
+    d10 = lk_deriv_at(D, cols, rows, x, y + 1); d11 = lk_deriv_at(D, cols, rows, x + 1, y + 1);
+  }
+  *ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
+  *iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
+}
+
+template <int TW, int TH, int WPP>
+__global__ void __launch_bounds__(WPP * 32) k_lk_track_cta(LkLevels lv, const float2* __restrict__ prev_pts,
+                                                           float2* __restrict__ next_pts, uint8_t* __restrict__ status,
+                                                           float* __restrict__ err, int n_points,
+                                                           const unsigned int* __restrict__ n_dev, int max_count, double eps2,
+                                                           int flags, double min_eig_thr) {
+  constexpr int NT = WPP * 32, AREA = TW * TH, STEPS = (AREA + NT - 1) / NT;
+  constexpr int ww = TW, wh = TH;
+  __shared__ float part[2][WPP][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pid = blockIdx.x;
+  if (pid >= (n_dev ? (int)min(*n_dev, (unsigned int)n_points) : n_points)) return;   // (uniform over the CTA)
+  int par = 0;
+  // sums over the CTA: butterfly inside the warps, the WPP partial sums through shared memory in a fixed order.  The slot
+  // alternates, so one barrier per reduction is enough: a thread reaches the next use of a slot only through the barrier
+  // of the reduction in between, which every thread passes after its reads of this one.
+  auto cta_sum3 = [&](float& a, float& b, float& c) {
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { part[par][warp][0] = a; part[par][warp][1] = b; part[par][warp][2] = c; }
+    __syncthreads();
+    a = part[par][0][0]; b = part[par][0][1]; c = part[par][0][2];
+#pragma unroll
+    for (int k = 1; k < WPP; k++) { a += part[par][k][0]; b += part[par][k][1]; c += part[par][k][2]; }
+    par ^= 1;
+  };
+  // window coordinates of this thread's pixels
+  int wxs[STEPS], wys[STEPS];
+#pragma unroll
+  for (int s2 = 0; s2 < STEPS; s2++) {
+    const int e = tid + s2 * NT;
+    wys[s2] = e / TW;
+    wxs[s2] = e - wys[s2] * TW;
+  }
+
+  const float2 p0 = prev_pts[pid];
+  const float halfx = (ww - 1) * 0.5f, halfy = (wh - 1) * 0.5f;
+  float2 np = make_float2(0.f, 0.f);
+  bool st = true;
+  float er = 0.f;
+  const bool use_init = (flags & OFB_OPTFLOW_USE_INITIAL_FLOW) != 0;
+  const bool get_min_eig = (flags & OFB_OPTFLOW_LK_GET_MIN_EIGENVALS) != 0;
+  const float2 init = use_init ? next_pts[pid] : p0;
+  const float FLT_SCALE = 1.f / (1 << 20);
+
+  for (int level = lv.n_levels - 1; level >= 0; level--) {
+    const float sc = (float)(1. / (1 << level));
+    const uint8_t* I = lv.I[level];
+    const uint8_t* J = lv.J[level];
+    const short2* D = lv.D[level];
+    const int cols = lv.w[level], rows = lv.h[level];
+    const size_t pitch = level == 0 ? lv.pitch0 : (size_t)cols;
+    float2 pp = make_float2(__fmul_rn(p0.x, sc), __fmul_rn(p0.y, sc));
+    if (level == lv.n_levels - 1) np = use_init ? make_float2(__fmul_rn(init.x, sc), __fmul_rn(init.y, sc)) : pp;
+    else np = make_float2(__fmul_rn(np.x, 2.f), __fmul_rn(np.y, 2.f));
+
+    pp.x -= halfx;
+    pp.y -= halfy;
+    const int ipx = (int)floorf(pp.x), ipy = (int)floorf(pp.y);
+    if (ipx < -ww || ipx >= cols || ipy < -wh || ipy >= rows) {
+      if (level == 0) { st = false; er = 0.f; }
+      continue;
+    }
+    int iw00, iw01, iw10, iw11;
+    lk_weights(pp.x - (float)ipx, pp.y - (float)ipy, &iw00, &iw01, &iw10, &iw11);
+    const bool in_i = ipx >= 0 && ipy >= 0 && ipx + ww + 1 <= cols && ipy + wh + 1 <= rows;
+    const bool small = cols <= ww || rows <= wh;       // a coordinate may need more than one reflection
+    int Iw[STEPS], dX[STEPS], dY[STEPS];               // this thread's part of the patch
+    float a11 = 0.f, a12 = 0.f, a22 = 0.f;
+    auto build = [&](auto mode) {
+      constexpr int MODE = decltype(mode)::value;
+#pragma unroll
+      for (int s2 = 0; s2 < STEPS; s2++) {
+        Iw[s2] = 0; dX[s2] = 0; dY[s2] = 0;
+        if (s2 < STEPS - 1 || tid + s2 * NT < AREA) {
+          lk_build_px<MODE>(I, D, pitch, cols, rows, ipx + wxs[s2], ipy + wys[s2], iw00, iw01, iw10, iw11, &Iw[s2], &dX[s2],
+                            &dY[s2]);
+          a11 += (float)(dX[s2] * dX[s2]);
+          a12 += (float)(dX[s2] * dY[s2]);
+          a22 += (float)(dY[s2] * dY[s2]);
+        }
+      }
+    };
+    if (in_i) build(std::integral_constant<int, 0>());
+    else if (!small) build(std::integral_constant<int, 1>());
+    else build(std::integral_constant<int, 2>());
+    cta_sum3(a11, a12, a22);
+    const float A11 = __fmul_rn(a11, FLT_SCALE), A12 = __fmul_rn(a12, FLT_SCALE), A22 = __fmul_rn(a22, FLT_SCALE);
+    float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dd = __fsub_rn(A11, A22);
+    const float min_eig =
+        __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11),
+                            __fsqrt_rn(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
+                  (float)(2 * ww * wh));
+    if (get_min_eig) er = min_eig;
+    if ((double)min_eig < min_eig_thr || Dt < 1.1920929e-07f) {
+      if (level == 0) st = false;
+      continue;
+    }
+    Dt = __fdiv_rn(1.f, Dt);
+    float2 q = make_float2(np.x - halfx, np.y - halfy);
+    float2 prev_delta = make_float2(0.f, 0.f);
+    for (int j = 0; j < max_count; j++) {
+      const int jx = (int)floorf(q.x), jy = (int)floorf(q.y);
+      if (jx < -ww || jx >= cols || jy < -wh || jy >= rows) {
+        if (level == 0) st = false;
+        break;
+      }
+      lk_weights(q.x - (float)jx, q.y - (float)jy, &iw00, &iw01, &iw10, &iw11);
+      const bool in_j = jx >= 0 && jy >= 0 && jx + ww + 1 <= cols && jy + wh + 1 <= rows;
+      float b1 = 0.f, b2 = 0.f, unused = 0.f;
+      auto mismatch = [&](auto mode) {
+        constexpr int MODE = decltype(mode)::value;
+#pragma unroll
+        for (int s2 = 0; s2 < STEPS; s2++)
+          if (s2 < STEPS - 1 || tid + s2 * NT < AREA) {
+            const int diff = lk_sample_j<MODE>(J, pitch, cols, rows, jx + wxs[s2], jy + wys[s2], iw00, iw01, iw10, iw11) - Iw[s2];
+            b1 += (float)(diff * dX[s2]);
+            b2 += (float)(diff * dY[s2]);
+          }
+      };
+      if (in_j) mismatch(std::integral_constant<int, 0>());
+      else if (!small) mismatch(std::integral_constant<int, 1>());
+      else mismatch(std::integral_constant<int, 2>());
+      cta_sum3(b1, b2, unused);
+      const float B1 = __fmul_rn(b1, FLT_SCALE), B2 = __fmul_rn(b2, FLT_SCALE);
+      const float2 delta = make_float2(__fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), Dt),
+                                       __fmul_rn(__fsub_rn(__fmul_rn(A12, B1), __fmul_rn(A11, B2)), Dt));
+      q.x += delta.x;
+      q.y += delta.y;
+      np = make_float2(q.x + halfx, q.y + halfy);
+      if ((double)delta.x * delta.x + (double)delta.y * delta.y <= eps2) break;
+      if (j > 0 && fabs((double)(delta.x + prev_delta.x)) < 0.01 && fabs((double)(delta.y + prev_delta.y)) < 0.01) {
+        np.x -= __fmul_rn(delta.x, 0.5f);
+        np.y -= __fmul_rn(delta.y, 0.5f);
+        break;
+      }
+      prev_delta = delta;
+    }
+    if (st && level == 0 && !get_min_eig) {
+      const float2 r = make_float2(np.x - halfx, np.y - halfy);
+      const int jx = (int)floorf(r.x), jy = (int)floorf(r.y);
+      if (jx < -ww || jx >= cols || jy < -wh || jy >= rows) {
+        st = false;
+        continue;
+      }
+      lk_weights(r.x - (float)jx, r.y - (float)jy, &iw00, &iw01, &iw10, &iw11);
+      const bool in_j = jx >= 0 && jy >= 0 && jx + ww + 1 <= cols && jy + wh + 1 <= rows;
+      float ev = 0.f, u1 = 0.f, u2 = 0.f;
+      auto abs_err = [&](auto mode) {
+        constexpr int MODE = decltype(mode)::value;
+#pragma unroll
+        for (int s2 = 0; s2 < STEPS; s2++)
+          if (s2 < STEPS - 1 || tid + s2 * NT < AREA) {
+            const int diff = lk_sample_j<MODE>(J, pitch, cols, rows, jx + wxs[s2], jy + wys[s2], iw00, iw01, iw10, iw11) - Iw[s2];
+            ev += fabsf((float)diff);
+          }
+      };
+      if (in_j) abs_err(std::integral_constant<int, 0>());
+      else if (!small) abs_err(std::integral_constant<int, 1>());
+      else abs_err(std::integral_constant<int, 2>());
+      cta_sum3(ev, u1, u2);
+      er = __fdiv_rn(ev, (float)(32 * ww * wh));
+    }
+  }
+  if (tid == 0) {
     next_pts[pid] = np;
     status[pid] = st ? 1 : 0;
     err[pid] = er;
@@ -975,9 +1235,16 @@ static int upload_image(ofb_handle* h, SparseState* s, int which, const uint8_t*
   if (!pinned) {
     SP_CUDA(h, cudaStreamSynchronize(h->stream));   // the staging half may still be read by the previous call's copy
     uint8_t* stg = reinterpret_cast<uint8_t*>(s->h_stage) + (size_t)which * width * height;
-    for (int y = 0; y < height; y++) memcpy(stg + (size_t)y * width, host + (size_t)y * stride, width);
-    from = stg;
-    from_stride = width;
+    // row bands: the DMA of a band runs while the host copies the next one into the staging buffer
+    const int bands = height >= 256 ? 4 : 1;
+    for (int b = 0; b < bands; b++) {
+      const int y0 = (int)((long long)height * b / bands), y1 = (int)((long long)height * (b + 1) / bands);
+      if (stride == (size_t)width) memcpy(stg + (size_t)y0 * width, host + (size_t)y0 * width, (size_t)(y1 - y0) * width);
+      else for (int y = y0; y < y1; y++) memcpy(stg + (size_t)y * width, host + (size_t)y * stride, width);
+      SP_CUDA(h, cudaMemcpyAsync(s->img[which] + (size_t)y0 * width, stg + (size_t)y0 * width, (size_t)(y1 - y0) * width,
+                                 cudaMemcpyHostToDevice, h->stream));
+    }
+    return OFB_OK;
   }
   SP_CUDA(h, cudaMemcpy2DAsync(s->img[which], width, from, from_stride, width, height, cudaMemcpyHostToDevice, h->stream));
   return OFB_OK;
@@ -1105,15 +1372,14 @@ static int lk_launch(ofb_handle* h, SparseState* s, const FramePyr& I, const Fra
   double eps = std::min(std::max(p->epsilon, 0.0), 10.0);
   eps *= eps;
   const size_t smem = (size_t)p->win_w * p->win_h * 3 * sizeof(short) * LK_WARPS;
+  if (n_bound <= 0) return OFB_OK;
   const dim3 grid((n_bound + LK_WARPS - 1) / LK_WARPS);
-  if (p->win_w == 21 && p->win_h == 21) {        // cv2's default window
-    k_lk_track<21, 21><<<grid, LK_WARPS * 32, smem, h->stream>>>(lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound,
-                                                                 n_dev, 21, 21, max_count, eps, p->flags,
-                                                                 p->min_eig_threshold);
+  if (p->win_w == 21 && p->win_h == 21) {        // cv2's default window: one point per CTA
+    k_lk_track_cta<21, 21, OFB_LK_WPP><<<n_bound, OFB_LK_WPP * 32, 0, h->stream>>>(
+        lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound, n_dev, max_count, eps, p->flags, p->min_eig_threshold);
   } else if (p->win_w == 15 && p->win_h == 15) {
-    k_lk_track<15, 15><<<grid, LK_WARPS * 32, smem, h->stream>>>(lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound,
-                                                                 n_dev, 15, 15, max_count, eps, p->flags,
-                                                                 p->min_eig_threshold);
+    k_lk_track_cta<15, 15, 2><<<n_bound, 64, 0, h->stream>>>(lv, d_prev, s->pts_next, s->lk_status, s->lk_err, n_bound, n_dev,
+                                                              max_count, eps, p->flags, p->min_eig_threshold);
   } else {
     if (smem > 48 * 1024)
       OFB_CUDA(h, cudaFuncSetAttribute(k_lk_track<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1239,6 +1505,7 @@ int ofb_pyrlk(ofb_handle* h, const uint8_t* prev, const uint8_t* next, int width
   if ((st = sparse_get(h, &s))) return st;
   s->st.primed = false;
   if ((st = sparse_points(h, s, n_points))) return st;
+  lk_out_layout(s, n_points);
   if ((st = upload_image(h, s, 0, prev, width, height, stride_bytes))) return st;
   if ((st = upload_image(h, s, 1, next, width, height, stride_bytes))) return st;
   cudaStream_t sm = h->stream;
@@ -1283,44 +1550,81 @@ int ofb_lk_stream(ofb_handle* h, const uint8_t* frame, int width, int height, si
   SparseState::Stream& S = s->st;
   const bool same = S.primed && S.w == width && S.h == height && memcmp(&S.gp, gp, sizeof(*gp)) == 0 &&
                     memcmp(&S.lp, lp, sizeof(*lp)) == 0;
-  if (!same) S.primed = false;
+  if (!same) { S.primed = false; stream_graphs_drop(s); }
   const int cur = S.primed ? (S.cur ^ 1) : 0, prv = cur ^ 1;
   cudaStream_t sm = h->stream;
   if ((st = upload_image(h, s, cur, frame, width, height, stride_bytes))) { S.primed = false; return st; }
+  // result block in pinned memory: [count prev, count cur | next pts | err | status | new corners]; the tracker's three
+  // arrays have the layout of the device block (lk_out_layout) and come back in one copy
+  char* hb = reinterpret_cast<char*>(s->h_stage);
+  const size_t lk_bytes = (size_t)bound * 13, new_off = 64 + ((lk_bytes + 15) & ~(size_t)15);
+  const size_t need = new_off + (size_t)bound * 8;
+  if (need > s->h_stage_bytes) { S.primed = false; return set_error(h, OFB_ERR_CAPACITY, "maxCorners exceeds the staging capacity"); }
+  unsigned int* hc = reinterpret_cast<unsigned int*>(hb);
+  float* h_next = reinterpret_cast<float*>(hb + 64);
+  float* h_err = h_next + 2 * (size_t)bound;
+  uint8_t* h_status = reinterpret_cast<uint8_t*>(h_err + bound);
+  float* h_new = reinterpret_cast<float*>(hb + new_off);
+  lk_out_layout(s, bound);
+  const bool track = S.primed;
   // Two chains behind the upload: tracker (pyramid of the new frame -> LK from the previous frame's corners) on the
   // handle's stream, corner detection of the new frame (needs level 0 only) on the second stream.  They share no buffer:
   // the tracker reads slot prv's corners / derivatives and slot cur's levels, the detector writes slot cur's corners and
   // the detection scratch.  The new frame's Scharr derivatives — needed by the NEXT call, in which it is the previous
   // frame — go behind the tracker.
-  const bool track = S.primed;
-  cudaStream_t sdet = track ? s->aux : sm;
-  if (track) {
-    OFB_CUDA(h, cudaEventRecord(s->ev_up, sm));
-    OFB_CUDA(h, cudaStreamWaitEvent(s->aux, s->ev_up, 0));
+  auto enqueue = [&]() -> int {
+    int st2;
+    cudaStream_t sdet = track ? s->aux : sm;
+    if (track) {
+      OFB_CUDA(h, cudaEventRecord(s->ev_up, sm));
+      OFB_CUDA(h, cudaStreamWaitEvent(s->aux, s->ev_up, 0));
+    }
+    if ((st2 = build_pyr(h, s, cur, width, height, lp->win_w, lp->win_h, lp->max_level, false, &S.fp[cur]))) return st2;
+    if (track) {
+      if ((st2 = lk_launch(h, s, S.fp[prv], S.fp[cur], width, s->corners[prv], bound, s->counters + 4 + prv, lp))) return st2;
+      OFB_CUDA(h, cudaMemcpyAsync(h_next, s->lk_out, lk_bytes, cudaMemcpyDeviceToHost, sm));
+    }
+    if ((st2 = detect_corners(h, s, cur, width, height, gp, nullptr, sdet))) return st2;
+    OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters + 4, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sdet));
+    OFB_CUDA(h, cudaMemcpyAsync(h_new, s->corners[cur], (size_t)bound * sizeof(float2), cudaMemcpyDeviceToHost, sdet));
+    if ((st2 = build_derivs(h, s, cur, &S.fp[cur]))) return st2;
+    if (track) {
+      OFB_CUDA(h, cudaEventRecord(s->ev_aux, s->aux));
+      OFB_CUDA(h, cudaStreamWaitEvent(sm, s->ev_aux, 0));
+    }
+    return OFB_OK;
+  };
+  if (S.graph_out != (const void*)s->lk_out || S.graph_bound != bound) {   // (the result buffers moved or changed layout)
+    stream_graphs_drop(s);
+    S.graph_out = s->lk_out;
+    S.graph_bound = bound;
   }
-  if ((st = build_pyr(h, s, cur, width, height, lp->win_w, lp->win_h, lp->max_level, false, &S.fp[cur]))) { S.primed = false; return st; }
-  // result block in pinned memory: [count prev, count cur | next pts | err | new corners | status]
-  char* hb = reinterpret_cast<char*>(s->h_stage);
-  const size_t need = 64 + (size_t)bound * (8 + 4 + 8 + 1);
-  if (need > s->h_stage_bytes) { S.primed = false; return set_error(h, OFB_ERR_CAPACITY, "maxCorners exceeds the staging capacity"); }
-  unsigned int* hc = reinterpret_cast<unsigned int*>(hb);
-  float* h_next = reinterpret_cast<float*>(hb + 64);
-  float* h_err = h_next + 2 * (size_t)bound;
-  float* h_new = h_err + bound;
-  uint8_t* h_status = reinterpret_cast<uint8_t*>(h_new + 2 * (size_t)bound);
-  if (track) {
-    if ((st = lk_launch(h, s, S.fp[prv], S.fp[cur], width, s->corners[prv], bound, s->counters + 4 + prv, lp))) { S.primed = false; return st; }
-    OFB_CUDA(h, cudaMemcpyAsync(h_next, s->pts_next, (size_t)bound * sizeof(float2), cudaMemcpyDeviceToHost, sm));
-    OFB_CUDA(h, cudaMemcpyAsync(h_status, s->lk_status, (size_t)bound, cudaMemcpyDeviceToHost, sm));
-    OFB_CUDA(h, cudaMemcpyAsync(h_err, s->lk_err, (size_t)bound * sizeof(float), cudaMemcpyDeviceToHost, sm));
-  }
-  if ((st = detect_corners(h, s, cur, width, height, gp, nullptr, sdet))) { S.primed = false; return st; }
-  OFB_CUDA(h, cudaMemcpyAsync(hc, s->counters + 4, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sdet));
-  OFB_CUDA(h, cudaMemcpyAsync(h_new, s->corners[cur], (size_t)bound * sizeof(float2), cudaMemcpyDeviceToHost, sdet));
-  if ((st = build_derivs(h, s, cur, &S.fp[cur]))) { S.primed = false; return st; }
-  if (track) {
-    OFB_CUDA(h, cudaEventRecord(s->ev_aux, s->aux));
-    OFB_CUDA(h, cudaStreamWaitEvent(sm, s->ev_aux, 0));
+  if (!track || h->no_graph || h->timing) {
+    if ((st = enqueue())) { S.primed = false; return st; }
+  } else if (S.graph[cur]) {
+    OFB_CUDA(h, cudaGraphLaunch(S.graph[cur], sm));
+    h->launches += S.graph_launches[cur];
+  } else {
+    const uint64_t l0 = h->launches;
+    OFB_CUDA(h, cudaStreamBeginCapture(sm, cudaStreamCaptureModeThreadLocal));
+    st = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(sm, &graph);
+    if (st != OFB_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      S.primed = false;
+      return st != OFB_OK ? st : set_error(h, OFB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    }
+    S.graph_launches[cur] = h->launches - l0;
+    const cudaError_t ie = cudaGraphInstantiate(&S.graph[cur], graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      S.graph[cur] = nullptr;
+      S.primed = false;
+      return set_error(h, OFB_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
+    }
+    OFB_CUDA(h, cudaGraphLaunch(S.graph[cur], sm));
   }
   OFB_CUDA(h, cudaStreamSynchronize(sm));
   const int n_cur = (int)std::min<unsigned int>(hc[cur], (unsigned int)bound);
