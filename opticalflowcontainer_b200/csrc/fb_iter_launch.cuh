@@ -6,6 +6,11 @@
 
 #include "fb_iter_v.cuh"
 
+// Fewest rows of a whole-frame row segment (experiment builds: -DOFB_EXP_MIN_SEG_ROWS=n; measured 8 / 12 / 16).
+#ifndef OFB_EXP_MIN_SEG_ROWS
+#define OFB_EXP_MIN_SEG_ROWS 8
+#endif
+
 namespace ofb {
 
 // k_iter_v launcher.  ups != nullptr: the launch is the first iteration of a level and upsamples its input flow from
@@ -50,9 +55,11 @@ static cudaError_t launch_iter_v(ofb_handle* h, const float2* fin, float2* fout,
   // segments on a tie): whole frames at the benchmark batch keep one full wave (1080p x 18 pairs: 2 segments, as before),
   // while small frames in large batches — VGA x 72: 216 strip columns, 0.73 of a wave — are cut so that the waves are
   // full (4 segments: 2.9 waves of 134 rows instead of one of 494).
-  // Tiled mode (one pair, narrow bands): at least 6 rows per segment; whole frames: at least 16, which also keeps the
-  // segmentation of small frames (and with it the rounding of the vertical block sums) the same for every batch size.
-  const int min_rows = REUSE && TILED ? 6 : 16;
+  // Tiled mode (one pair, narrow bands): at least 6 rows per segment; whole frames: at least 8 (a single VGA pair:
+  // 0.211 -> 0.180 ms against a minimum of 16; nothing changes at the benchmark batch).  The vertical block sums restart
+  // with a segment, so their float rounding — the last bits of the flow — follows the segmentation, and with it the
+  // batch size: calls over different batch sizes agree to ~1e-6 px, not bit for bit.
+  const int min_rows = REUSE && TILED ? 6 : OFB_EXP_MIN_SEG_ROWS;
   int segs = 1, seg_rows = rows + (rows & 1);
   {
     long best = -1;

@@ -194,7 +194,9 @@ def test_pinned_pipelined_batch_equals_single(engine_factory, n):
 
 def test_async_batch_pipelines_across_calls(built_lib):
     """ofb_farneback_batch_async + ofb_wait: three back-to-back calls on page-locked buffers, two result
-    buffers in flight, results identical to the synchronous call."""
+    buffers in flight, results equal to the synchronous call's.  The two paths split the batch into different chunks, and
+    the iteration kernel cuts a level into row segments by batch size (fb_iter_launch.cuh): its float window sums restart
+    with a segment, so the last bits of the flow follow the chunking — equal to 1e-4 px (measured 2e-6), not bit for bit."""
     import torch
     import opticalflowcontainer_b200 as ofb
     n, h, w = 8, 240, 320
@@ -212,12 +214,12 @@ def test_async_batch_pipelines_across_calls(built_lib):
             eng.farneback_batch_into(a.numpy(), b.numpy(), outs[s].numpy(), wait=False)
         eng.wait()
         for s in range(3):
-            assert np.array_equal(outs[s].numpy(), ref[s])
+            assert np.abs(outs[s].numpy() - ref[s]).max() <= 1e-4
         # reuse of a result buffer by a later call is ordered by the library
         eng.farneback_batch_into(sets[0][0].numpy(), sets[0][1].numpy(), outs[0].numpy(), wait=False)
         eng.farneback_batch_into(sets[1][0].numpy(), sets[1][1].numpy(), outs[0].numpy(), wait=False)
         eng.wait()
-        assert np.array_equal(outs[0].numpy(), ref[1])
+        assert np.abs(outs[0].numpy() - ref[1]).max() <= 1e-4
     finally:
         eng.close()
 
