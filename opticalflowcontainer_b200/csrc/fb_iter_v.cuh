@@ -59,6 +59,10 @@ constexpr int iter_v_smem_floats(int m, bool tmem, int nbuf) {
 
 constexpr int kTmemRingStride = 8;    // TMEM columns per ring slot (5 used; x4 + x1 accesses stay aligned)
 constexpr int kTmemWgCols = 128;      // TMEM columns per producer warpgroup
+// Rings of more than 16 slots (window radius 8..12) do not fit the warpgroup's 128 columns at 8 columns per slot; they are
+// PACKED: four channels of slot k at columns [4k, 4k + 4), the fifth at column 4R + k — 5 columns per slot, every access
+// aligned to its width, two tcgen05.ld / st per row instead of one.
+__host__ __device__ constexpr bool tmem_ring_packed(int mt) { return (2 * mt + 1) * kTmemRingStride > kTmemWgCols; }
 
 // Coarser level's flow for the fused upsample (prev == nullptr: the launch reads flow_in as it is).
 struct UpsSrc {
@@ -122,6 +126,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[5]) {
   asm volatile("{\n.reg .b32 u;\ntcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, u, u, u};\n}" ::"r"(taddr),
                "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]) : "memory");
 }
+// packed ring slot: x4 at `ta`, the fifth channel x1 at `tb`
+__device__ __forceinline__ void tmem_ld41(uint32_t ta, uint32_t tb, float (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(ta));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(v[4]) : "r"(tb));
+}
+__device__ __forceinline__ void tmem_st41(uint32_t ta, uint32_t tb, const float (&v)[5]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tb), "f"(v[4]) : "memory");
+}
 __device__ __forceinline__ void lds_f4(uint32_t addr, float& a, float& b, float& c, float& d) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
 }
@@ -180,8 +195,9 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
   constexpr int NCONS = CH * GROUPS;
   static_assert(NCONS % 32 == 0, "whole consumer warps");
   static_assert(!REUSE || CH == 2, "row-reuse schedule: chunks of two rows");
-  static_assert(!TMEM || (COLS == 256 && MT >= 1 && (2 * MT + 1) * kTmemRingStride <= kTmemWgCols),
+  static_assert(!TMEM || (COLS == 256 && MT >= 1 && (2 * MT + 1) * (tmem_ring_packed(MT) ? 5 : kTmemRingStride) <= kTmemWgCols),
                 "TMEM ring: two producer warpgroups, ring slots within the warpgroup's columns");
+  constexpr bool PACKED = TMEM && tmem_ring_packed(MT);
   static_assert(NBUF >= 2 && NBUF <= 8, "staging buffers");
   constexpr bool REGMOVE = REUSE && COLS == 256 && MINB == 2;   // setmaxnreg 96 / 48
   const int m = MT > 0 ? MT : m_rt;
@@ -245,7 +261,11 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     // The ring starts zero-filled, so the first block subtracts zeros: no "have a previous block" flag in the row step.
     if constexpr (TMEM) {
       const float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int i = 0; i < R; i++) tmem_st8(tring + (uint32_t)i * kTmemRingStride, z);
+      if constexpr (PACKED) {
+        for (int i = 0; i < R; i++) tmem_st41(tring + 4u * (uint32_t)i, tring + 4u * (uint32_t)R + (uint32_t)i, z);
+      } else {
+        for (int i = 0; i < R; i++) tmem_st8(tring + (uint32_t)i * kTmemRingStride, z);
+      }
     } else {
       for (int i = 0; i < R * 5; i++) rcol[i * COLS] = 0.f;
     }
@@ -253,11 +273,13 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     // vertical van Herk step: P += M(t); V = (Bp - P_prev[k]) + P; ring[k] = P; block bookkeeping
     auto ring_step = [&](const M5& mm, float (&V)[5]) {
       OFB_DASSERT(k >= 0 && k < R);                                   // ring slot inside the (2m+1)-row ring
-      OFB_DASSERT(!TMEM || (tk == (uint32_t)k * kTmemRingStride && tk + 5 <= (uint32_t)kTmemWgCols));
+      OFB_DASSERT(!TMEM || PACKED || (tk == (uint32_t)k * kTmemRingStride && tk + 5 <= (uint32_t)kTmemWgCols));
+      OFB_DASSERT(!PACKED || (tk == 4u * (uint32_t)k && 5 * R <= kTmemWgCols));
       float old[8];
       if constexpr (TMEM) {
         tmem_wait_st();                              // the slot read below was written R rows ago: long complete
-        tmem_ld8(tring + tk, old);
+        if constexpr (PACKED) tmem_ld41(tring + tk, tring + 4u * (uint32_t)R + (uint32_t)k, old);
+        else tmem_ld8(tring + tk, old);
       } else {
 #pragma unroll
         for (int ch = 0; ch < 5; ch++) old[ch] = rcol[(k * 5 + ch) * COLS];
@@ -266,8 +288,9 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
       P[3] = __fadd_rn(P[3], mm.h1); P[4] = __fadd_rn(P[4], mm.h2);
       if constexpr (TMEM) {
         tmem_wait_ld8(old);
-        tmem_st8(tring + tk, P);
-        tk += kTmemRingStride;
+        if constexpr (PACKED) tmem_st41(tring + tk, tring + 4u * (uint32_t)R + (uint32_t)k, P);
+        else tmem_st8(tring + tk, P);
+        tk += PACKED ? 4u : (uint32_t)kTmemRingStride;
       }
 #pragma unroll
       for (int ch = 0; ch < 5; ch++) {

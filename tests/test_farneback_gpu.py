@@ -40,6 +40,13 @@ CASES = [
     ("winsize16", (240, 320), 4, (3, 2), dict(winsize=16)),
     ("winsize5", (240, 320), 4, (2, 1), dict(winsize=5)),
     ("winsize31", (240, 320), 4, (2, 1), dict(winsize=31)),
+    # radii 8..12: the vertical ring packed into tensor memory (fb_iter_v.cuh, tmem_ring_packed); 1080p rows: two segments
+    ("winsize17", (240, 320), 4, (2, 1), dict(winsize=17)),
+    ("winsize19", (240, 320), 4, (2, 1), dict(winsize=19)),
+    ("winsize21_odd_size", (203, 331), 5, (-3, 2), dict(winsize=21)),
+    ("winsize23", (240, 320), 6, (2, -1), dict(winsize=23)),
+    ("winsize25_vga", (480, 640), 7, (4, 3), dict(winsize=25)),
+    ("winsize27", (240, 320), 4, (2, 1), dict(winsize=27)),
     ("poly7", (240, 320), 5, (3, 2), dict(poly_n=7, poly_sigma=1.5)),
     ("pyr08", (240, 320), 6, (3, 2), dict(pyr_scale=0.8, levels=5)),
     ("levels0", (200, 300), 7, (2, 1), dict(levels=0)),
