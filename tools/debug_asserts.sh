@@ -1,7 +1,7 @@
 #!/bin/bash
 # The Farneback GPU tests against a debug build of libofb.so with in-kernel bounds asserts (-DOFB_DBG=1: ring slots,
 # staging buffers, output rows / columns of k_iter_v).  Build first (no GPU needed):
-#   tools/build_variant.sh dbg "-DOFB_DBG=1"
+#   tools/build_variant.sh dbg "-DOFB_DBG=1"   (plus iter_fixed_a.cu / iter_fixed_b.cu with the same flag for the other window sizes)
 # then on the GPU box:  bash tools/debug_asserts.sh   -> gpurun_out/debug_asserts.log
 # A failing check aborts the kernel ("device-side assert triggered", with file and line on stderr).
 mkdir -p gpurun_out
