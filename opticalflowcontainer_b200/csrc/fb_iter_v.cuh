@@ -52,16 +52,21 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
 // 1920 / 960 / 480 / 240 / 3840 split into the same number of 240-column strips as of 242-column ones.
 __host__ __device__ constexpr int iter_v_halo(int mt, int m) { return (mt == 7 || mt == 15) ? mt + 1 : m; }
 
+// Ring slots a packed TMEM ring holds (5 columns each in a warpgroup's 128); the slots beyond (radii 13..15: 2..6 slots)
+// live in shared memory behind the staging buffers.
+constexpr int kTmemPackedSlots = 25;
 template <int COLS, int CH>
 constexpr int iter_v_smem_floats(int m, bool tmem, int nbuf) {
-  return (nbuf * CH + (tmem ? 0 : 2 * m + 1)) * 5 * COLS;
+  const int ring_slots = tmem ? (2 * m + 1 > kTmemPackedSlots ? 2 * m + 1 - kTmemPackedSlots : 0) : 2 * m + 1;
+  return (nbuf * CH + ring_slots) * 5 * COLS;
 }
 
 constexpr int kTmemRingStride = 8;    // TMEM columns per ring slot (5 used; x4 + x1 accesses stay aligned)
 constexpr int kTmemWgCols = 128;      // TMEM columns per producer warpgroup
 // Rings of more than 16 slots (window radius 8..12) do not fit the warpgroup's 128 columns at 8 columns per slot; they are
-// PACKED: four channels of slot k at columns [4k, 4k + 4), the fifth at column 4R + k — 5 columns per slot, every access
-// aligned to its width, two tcgen05.ld / st per row instead of one.
+// PACKED: four channels of slot k at columns [4k, 4k + 4), the fifth at column 4T + k (T = min(R, 25) slots) — 5 columns per
+// slot, every access aligned to its width, two tcgen05.ld / st per row instead of one.  Rings of more than 25 slots
+// (radius 13..15) keep their last R - 25 slots in shared memory.
 __host__ __device__ constexpr bool tmem_ring_packed(int mt) { return (2 * mt + 1) * kTmemRingStride > kTmemWgCols; }
 
 // Coarser level's flow for the fused upsample (prev == nullptr: the launch reads flow_in as it is).
@@ -195,9 +200,11 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
   constexpr int NCONS = CH * GROUPS;
   static_assert(NCONS % 32 == 0, "whole consumer warps");
   static_assert(!REUSE || CH == 2, "row-reuse schedule: chunks of two rows");
-  static_assert(!TMEM || (COLS == 256 && MT >= 1 && (2 * MT + 1) * (tmem_ring_packed(MT) ? 5 : kTmemRingStride) <= kTmemWgCols),
-                "TMEM ring: two producer warpgroups, ring slots within the warpgroup's columns");
+  static_assert(!TMEM || (COLS == 256 && MT >= 1), "TMEM ring: two producer warpgroups, radius known at compile time");
   constexpr bool PACKED = TMEM && tmem_ring_packed(MT);
+  constexpr int TSLOTS = !PACKED ? 2 * MT + 1 : (2 * MT + 1 < kTmemPackedSlots ? 2 * MT + 1 : kTmemPackedSlots);   // slots in TMEM
+  constexpr bool SPILL = PACKED && 2 * MT + 1 > kTmemPackedSlots;      // the slots beyond TSLOTS live in shared memory
+  static_assert(!TMEM || TSLOTS * (PACKED ? 5 : kTmemRingStride) <= kTmemWgCols, "ring slots within the warpgroup's columns");
   static_assert(NBUF >= 2 && NBUF <= 8, "staging buffers");
   constexpr bool REGMOVE = REUSE && COLS == 256 && MINB == 2;   // setmaxnreg 96 / 48
   const int m = MT > 0 ? MT : m_rt;
@@ -262,7 +269,9 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     if constexpr (TMEM) {
       const float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       if constexpr (PACKED) {
-        for (int i = 0; i < R; i++) tmem_st41(tring + 4u * (uint32_t)i, tring + 4u * (uint32_t)R + (uint32_t)i, z);
+        for (int i = 0; i < TSLOTS; i++) tmem_st41(tring + 4u * (uint32_t)i, tring + 4u * (uint32_t)TSLOTS + (uint32_t)i, z);
+        if constexpr (SPILL)
+          for (int i = 0; i < (R - TSLOTS) * 5; i++) rcol[i * COLS] = 0.f;
       } else {
         for (int i = 0; i < R; i++) tmem_st8(tring + (uint32_t)i * kTmemRingStride, z);
       }
@@ -274,12 +283,18 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
     auto ring_step = [&](const M5& mm, float (&V)[5]) {
       OFB_DASSERT(k >= 0 && k < R);                                   // ring slot inside the (2m+1)-row ring
       OFB_DASSERT(!TMEM || PACKED || (tk == (uint32_t)k * kTmemRingStride && tk + 5 <= (uint32_t)kTmemWgCols));
-      OFB_DASSERT(!PACKED || (tk == 4u * (uint32_t)k && 5 * R <= kTmemWgCols));
+      OFB_DASSERT(!PACKED || (tk == 4u * (uint32_t)k && 5 * TSLOTS <= kTmemWgCols));
       float old[8];
+      const bool in_tmem = !SPILL || k < TSLOTS;     // (uniform over the warp: k is the row's offset in its block)
       if constexpr (TMEM) {
-        tmem_wait_st();                              // the slot read below was written R rows ago: long complete
-        if constexpr (PACKED) tmem_ld41(tring + tk, tring + 4u * (uint32_t)R + (uint32_t)k, old);
-        else tmem_ld8(tring + tk, old);
+        if (in_tmem) {
+          tmem_wait_st();                            // the slot read below was written R rows ago: long complete
+          if constexpr (PACKED) tmem_ld41(tring + tk, tring + 4u * (uint32_t)TSLOTS + (uint32_t)k, old);
+          else tmem_ld8(tring + tk, old);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 5; ch++) old[ch] = rcol[((k - TSLOTS) * 5 + ch) * COLS];
+        }
       } else {
 #pragma unroll
         for (int ch = 0; ch < 5; ch++) old[ch] = rcol[(k * 5 + ch) * COLS];
@@ -287,15 +302,20 @@ __global__ void __launch_bounds__(COLS + CH * COLS / 4, MINB)
       P[0] = __fadd_rn(P[0], mm.g11); P[1] = __fadd_rn(P[1], mm.g12); P[2] = __fadd_rn(P[2], mm.g22);
       P[3] = __fadd_rn(P[3], mm.h1); P[4] = __fadd_rn(P[4], mm.h2);
       if constexpr (TMEM) {
-        tmem_wait_ld8(old);
-        if constexpr (PACKED) tmem_st41(tring + tk, tring + 4u * (uint32_t)R + (uint32_t)k, P);
-        else tmem_st8(tring + tk, P);
+        if (in_tmem) {
+          tmem_wait_ld8(old);
+          if constexpr (PACKED) tmem_st41(tring + tk, tring + 4u * (uint32_t)TSLOTS + (uint32_t)k, P);
+          else tmem_st8(tring + tk, P);
+        }
         tk += PACKED ? 4u : (uint32_t)kTmemRingStride;
       }
 #pragma unroll
       for (int ch = 0; ch < 5; ch++) {
         V[ch] = (Bp[ch] - old[ch]) + P[ch];
         if constexpr (!TMEM) rcol[(k * 5 + ch) * COLS] = P[ch];
+        if constexpr (SPILL) {
+          if (!in_tmem) rcol[((k - TSLOTS) * 5 + ch) * COLS] = P[ch];
+        }
       }
       if (++k == R) {
         k = 0;
