@@ -790,7 +790,7 @@ def run_ours(args, rank, local_rank, world):
                 extras["around_the_path"] = {"error": repr(e)}
         # (5) BASELINE.json config 5: one 8K pair tiled over the ranks (needs >= 2 GPUs)
         if world >= 2:
-            rec = tiled_record(args, rank, local_rank, world, "8k", steps=5, warmup=3, parity=True, whole=True)
+            rec = tiled_record(args, rank, local_rank, world, "8k", steps=20, warmup=3, parity=True, whole=True)
             if rank == 0:
                 extras["tiled_8k"] = rec
 
