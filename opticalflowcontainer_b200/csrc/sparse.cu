@@ -221,6 +221,79 @@ __global__ void __launch_bounds__(256) k_scharr(const uint8_t* __restrict__ src,
 
 // ======================================================================================
 // a13: cornerMinEigenVal(blockSize, ksize=3) — the wheel's optimized float recipe, bit for bit
+// ---- four pixels per thread: rows read as aligned 32-bit words, results stored as one vector ---------------------------
+// (the byte-per-thread forms above issue 9 / 25 byte loads per output pixel; these need w % 4 == 0, a pitch that is a
+// multiple of 4 and aligned bases — every level of a 1080p / VGA pyramid — and are the same integer arithmetic.)
+__device__ __forceinline__ unsigned int ldg_u32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
+__device__ __forceinline__ int byte_of(unsigned int w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
+
+__global__ void __launch_bounds__(256) k_scharr4(const uint8_t* __restrict__ src, int w, int h, size_t spitch,
+                                                 short2* __restrict__ dst) {
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= w || y >= h) return;
+  const uint8_t* rows[3] = {src + (size_t)reflect101(y - 1, h) * spitch, src + (size_t)y * spitch,
+                            src + (size_t)reflect101(y + 1, h) * spitch};
+  const int xl = x0 == 0 ? 1 : x0 - 1, xr = x0 + 4 >= w ? w - 2 : x0 + 4;     // REFLECT_101 of x0 - 1 and x0 + 4
+  int p[3][6];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const unsigned int wd = ldg_u32(rows[j] + x0);
+    p[j][0] = rows[j][xl];
+#pragma unroll
+    for (int i = 0; i < 4; i++) p[j][1 + i] = byte_of(wd, i);
+    p[j][5] = rows[j][xr];
+  }
+  // t0 = (above + below)*3 + centre*10 ; t1 = below - above   (per column), then the horizontal difference / smoothing
+  int t0[6], t1[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    t0[i] = (p[0][i] + p[2][i]) * 3 + p[1][i] * 10;
+    t1[i] = p[2][i] - p[0][i];
+  }
+  uint4 out;
+  unsigned int* o = &out.x;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int dx = t0[i + 2] - t0[i], dy = (t1[i + 2] + t1[i]) * 3 + t1[i + 1] * 10;
+    o[i] = ((unsigned int)dx & 0xffffu) | ((unsigned int)dy << 16);
+  }
+  *reinterpret_cast<uint4*>(dst + (size_t)y * w + x0) = out;
+}
+
+__global__ void __launch_bounds__(256) k_pyrdown_u8x4(const uint8_t* __restrict__ src, int w, int h, size_t spitch,
+                                                      uint8_t* __restrict__ dst, int ow, int oh) {
+  // needs w == 2 * ow, w % 4 == 0, ow % 4 == 0
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);       // first of the thread's four output columns
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= ow || y >= oh) return;
+  // source columns 2 x0 - 2 .. 2 x0 + 8.  2 x0 .. 2 x0 + 7 are two aligned words inside the row; the two columns to the
+  // left come from the word before — or, in the first group, are REFLECT_101 of -2 and -1: columns 2 and 1 of the first
+  // word; the column to the right is byte 0 of the word behind — or, in the last group, column w reflected to w - 2.
+  const bool first = x0 == 0, last = 2 * x0 + 8 >= w;
+  int acc[4] = {0, 0, 0, 0};
+  const int kk[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const uint8_t* row = src + (size_t)reflect101_once(2 * y + j - 2, h) * spitch + 2 * x0;
+    const unsigned int w1 = ldg_u32(row), w2 = ldg_u32(row + 4);
+    const unsigned int w0 = ldg_u32(first ? row : row - 4), w3 = ldg_u32(last ? row : row + 8);
+    int v[11];
+    v[0] = first ? byte_of(w1, 2) : byte_of(w0, 2);
+    v[1] = first ? byte_of(w1, 1) : byte_of(w0, 3);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { v[2 + i] = byte_of(w1, i); v[6 + i] = byte_of(w2, i); }
+    v[10] = last ? byte_of(w2, 2) : byte_of(w3, 0);
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+      acc[o] += kk[j] * (v[2 * o] + 4 * v[2 * o + 1] + 6 * v[2 * o + 2] + 4 * v[2 * o + 3] + v[2 * o + 4]);
+  }
+  unsigned int out = 0;
+#pragma unroll
+  for (int o = 0; o < 4; o++) out |= (unsigned int)((acc[o] + 128) >> 8) << (8 * o);
+  *reinterpret_cast<unsigned int*>(dst + (size_t)y * ow + x0) = out;
+}
+
 // ======================================================================================
 // Sobel with the scale folded into the smoothing kernel k = f32([1,2,1]/(4*blockSize*255)):
 //   dx = fma(r[y-1] + r[y+1], k0, r[y]*k1),  r = p[x+1] - p[x-1]
@@ -1255,7 +1328,11 @@ static int build_derivs(ofb_handle* h, SparseState* s, int which, FramePyr* fp) 
   dim3 b(32, 8);
   short2* d = s->deriv[which];
   for (int l = 0; l < fp->n_levels; l++) {
-    k_scharr<<<g2(fp->w[l], fp->h[l], b), b, 0, h->stream>>>(fp->lv[l], fp->w[l], fp->h[l], (size_t)fp->w[l], d);
+    const int lw = fp->w[l], lh = fp->h[l];
+    if (lw >= 8 && (lw & 3) == 0 && (reinterpret_cast<uintptr_t>(fp->lv[l]) & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0)
+      k_scharr4<<<g2(lw / 4, lh, b), b, 0, h->stream>>>(fp->lv[l], lw, lh, (size_t)lw, d);
+    else
+      k_scharr<<<g2(lw, lh, b), b, 0, h->stream>>>(fp->lv[l], lw, lh, (size_t)lw, d);
     OFB_LAUNCH_CHECK(h);
     fp->D[l] = d;
     d += (size_t)fp->w[l] * fp->h[l];
@@ -1276,8 +1353,12 @@ static int build_pyr(ofb_handle* h, SparseState* s, int which, int width, int he
   for (int l = 1; l <= max_level && l < kMaxLkLevels; l++) {
     const int ow = (fp->w[l - 1] + 1) / 2, oh = (fp->h[l - 1] + 1) / 2;
     if (ow <= win_w || oh <= win_h) break;
-    k_pyrdown_u8<<<g2(ow, oh, b), b, 0, h->stream>>>(fp->lv[l - 1], fp->w[l - 1], fp->h[l - 1], (size_t)fp->w[l - 1], next,
-                                                     ow, oh);
+    const int sw = fp->w[l - 1];
+    if (sw >= 16 && fp->h[l - 1] >= 4 && (sw & 3) == 0 && (ow & 3) == 0 && (reinterpret_cast<uintptr_t>(fp->lv[l - 1]) & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(next) & 3) == 0)
+      k_pyrdown_u8x4<<<g2(ow / 4, oh, b), b, 0, h->stream>>>(fp->lv[l - 1], sw, fp->h[l - 1], (size_t)sw, next, ow, oh);
+    else
+      k_pyrdown_u8<<<g2(ow, oh, b), b, 0, h->stream>>>(fp->lv[l - 1], sw, fp->h[l - 1], (size_t)sw, next, ow, oh);
     OFB_LAUNCH_CHECK(h);
     fp->lv[l] = next;
     fp->w[l] = ow;
