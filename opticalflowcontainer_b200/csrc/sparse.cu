@@ -310,6 +310,21 @@ __global__ void __launch_bounds__(256) k_pyrdown_u8x4(const uint8_t* __restrict_
 // harris != 0: cv2.cornerHarris instead, as the wheel computes it over the image as ONE continuous row of w * h pixels —
 // (a c - b b) - k ((a + c)(a + c)) in float in the 8-wide body, (a c - b b) - (k (a + c)) (a + c) in the 4-wide step
 // behind it, and the last (w * h) % 4 pixels in double with the caller's double k (oracle/features_np.py::corner_harris).
+// Maximum of a 256-thread CTA into a global word with at most ONE atomic per CTA, and none when the word already holds
+// a larger value (it only grows, so a stale read can only cost a redundant atomic): one atomicMax per warp was 32 000
+// same-address atomics per 1080p frame, which L2 serialises at ~1 ns each — the whole duration of the kernel.
+__device__ __forceinline__ void block_max_to_global(float m, int tid, unsigned int* max_bits) {
+  __shared__ float wmax[8];
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) wmax[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; k++) m = fmaxf(m, wmax[k]);
+    if (m > 0.f && __float_as_uint(m) > *reinterpret_cast<volatile unsigned int*>(max_bits)) atomicMax(max_bits, __float_as_uint(m));
+  }
+}
+
 constexpr int kEigTileH = 16;
 // derivative products at image position (x, y) [already inside the image]; BORDER: the 3x3 neighbourhood may leave it
 template <bool BORDER>
@@ -397,8 +412,116 @@ __global__ void __launch_bounds__(256) k_sobel_min_eig(const uint8_t* __restrict
     if (mask && mask[o] == 0) e = 0.f;
     m = fmaxf(m, e);
   }
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((tid & 31) == 0 && m > 0.f) atomicMax(max_bits, __float_as_uint(m));
+  block_max_to_global(m, tid, max_bits);
+}
+
+// blockSize 3 (the default): the same map with the tile pass in groups of four columns — aligned word loads, the border
+// decision per CTA — storing the HORIZONTAL 3-sums of the products (doubles, exact), so that the window pass of a thread
+// is a vertical 3-sum over one column, shared by its four vertically adjacent outputs.  ncu on the generic kernel at
+// blockSize 3: 388 instructions per pixel, issue slots 84 % busy; a first form of this kernel that stored the products
+// themselves: 225 instructions per pixel, the shared-memory pipe 72 % busy (36 LDS.64 per two outputs, strided stores
+// with 1.5 M bank conflicts).  Here: 4.5 LDS.64 per output, vector stores.
+constexpr int kE3T = 32;                            // outputs per CTA: 32 x 32
+constexpr int kE3H = kE3T + 2;                      // rows of row sums: by - 1 .. by + 32
+__device__ __forceinline__ void sts_d2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+__global__ void __launch_bounds__(256) k_sobel_min_eig3(const uint8_t* __restrict__ src, int w, int h, size_t spitch, float k0,
+                                                        float k1, float k2, int wb, float* __restrict__ eig,
+                                                        unsigned int* __restrict__ max_bits, const uint8_t* __restrict__ mask,
+                                                        int harris, float kf, double kd) {
+  __shared__ __align__(16) double hxx[kE3H][kE3T], hxy[kE3H][kE3T], hyy[kE3H][kE3T];   // 3-sums centred on column bx + c
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int bx = blockIdx.x * kE3T, by = blockIdx.y * kE3T;
+  // products are needed at columns bx - 1 .. bx + 32, rows by - 1 .. by + 32; their Sobel neighbourhood one further
+  const bool interior = bx - 4 >= 0 && by - 2 >= 0 && bx + kE3T + 4 <= w && by + kE3T + 2 <= h && (spitch & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+  if (interior) {
+    for (int t = tid; t < (kE3T / 4) * kE3H; t += 256) {
+      const int g = t % (kE3T / 4), r = t / (kE3T / 4);
+      const int x0 = bx + 4 * g, y = by - 1 + r;          // row sums at columns x0 .. x0 + 3: products at x0 - 1 .. x0 + 4
+      float p[3][8];                                      // pixels x0 - 2 .. x0 + 5 of rows y - 1 .. y + 1
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const uint8_t* row = src + (size_t)(y - 1 + j) * spitch + x0;
+        const unsigned int wl = ldg_u32(row - 4), wc = ldg_u32(row), wr = ldg_u32(row + 4);
+        p[j][0] = u8f((wl >> 16) & 0xffu); p[j][1] = u8f(wl >> 24);
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[j][2 + i] = u8f((wc >> (8 * i)) & 0xffu);
+        p[j][6] = u8f(wr & 0xffu); p[j][7] = u8f((wr >> 8) & 0xffu);
+      }
+      double pxx[6], pxy[6], pyy[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {                       // product at column x0 - 1 + i
+        float rr[3], rw[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float pm = p[j][i], pc = p[j][i + 1], pp = p[j][i + 2];
+          rr[j] = pp - pm;
+          if (x0 - 1 + i < wb) rw[j] = fmaf(k2, pp, fmaf(k1, pc, __fmul_rn(k0, pm)));
+          else rw[j] = __fadd_rn(__fadd_rn(__fmul_rn(pm, k0), __fmul_rn(pc, k1)), __fmul_rn(pp, k2));
+        }
+        const float dx = fmaf(rr[0] + rr[2], k0, __fmul_rn(rr[1], k1));
+        const float dy = rw[2] - rw[0];
+        pxx[i] = (double)__fmul_rn(dx, dx);
+        pxy[i] = (double)__fmul_rn(dx, dy);
+        pyy[i] = (double)__fmul_rn(dy, dy);
+      }
+      sts_d2(&hxx[r][4 * g], (pxx[0] + pxx[1]) + pxx[2], (pxx[1] + pxx[2]) + pxx[3]);
+      sts_d2(&hxx[r][4 * g + 2], (pxx[2] + pxx[3]) + pxx[4], (pxx[3] + pxx[4]) + pxx[5]);
+      sts_d2(&hxy[r][4 * g], (pxy[0] + pxy[1]) + pxy[2], (pxy[1] + pxy[2]) + pxy[3]);
+      sts_d2(&hxy[r][4 * g + 2], (pxy[2] + pxy[3]) + pxy[4], (pxy[3] + pxy[4]) + pxy[5]);
+      sts_d2(&hyy[r][4 * g], (pyy[0] + pyy[1]) + pyy[2], (pyy[1] + pyy[2]) + pyy[3]);
+      sts_d2(&hyy[r][4 * g + 2], (pyy[2] + pyy[3]) + pyy[4], (pyy[3] + pyy[4]) + pyy[5]);
+    }
+  } else {
+    for (int i = tid; i < kE3T * kE3H; i += 256) {
+      const int ty = i / kE3T, tx = i - ty * kE3T;
+      // (rows / columns beyond the image's last ones are never read: keep them in range)
+      const int xc = min(bx + tx, w - 1), y = reflect101(min(by - 1 + ty, h), h);
+      double sxx = 0, sxy = 0, syy = 0;
+#pragma unroll
+      for (int d = -1; d <= 1; d++) {
+        double a, b, c;
+        sobel_products<true>(src, w, h, spitch, reflect101(xc + d, w), y, k0, k1, k2, wb, &a, &b, &c);
+        sxx += a; sxy += b; syy += c;
+      }
+      hxx[ty][tx] = sxx; hxy[ty][tx] = sxy; hyy[ty][tx] = syy;
+    }
+  }
+  __syncthreads();
+  const size_t n = (size_t)w * h;
+  float m = 0.f;
+  const int lx = threadIdx.x, x = bx + lx;
+  double vxx[6], vxy[6], vyy[6];
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const int tr = 4 * threadIdx.y + r;
+    vxx[r] = hxx[tr][lx]; vxy[r] = hxy[tr][lx]; vyy[r] = hyy[tr][lx];
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int y = by + 4 * threadIdx.y + q;
+    if (x >= w || y >= h) continue;
+    const double sxx = (vxx[q] + vxx[q + 1]) + vxx[q + 2], sxy = (vxy[q] + vxy[q + 1]) + vxy[q + 2],
+                 syy = (vyy[q] + vyy[q + 1]) + vyy[q + 2];
+    float e;
+    const size_t o = (size_t)y * w + x;
+    if (!harris) {
+      const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
+      const float d = __fsub_rn(a, c);
+      e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+    } else {
+      const float a = (float)sxx, b = (float)sxy, c = (float)syy;
+      const float t1 = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b)), sm = __fadd_rn(a, c);
+      if (o < n - (n & 7)) e = __fsub_rn(t1, __fmul_rn(kf, __fmul_rn(sm, sm)));
+      else if (o < n - (n & 3)) e = __fsub_rn(t1, __fmul_rn(__fmul_rn(kf, sm), sm));
+      else e = (float)__dsub_rn((double)t1, __dmul_rn(__dmul_rn(kd, (double)sm), (double)sm));
+    }
+    eig[o] = e;
+    if (mask && mask[o] == 0) e = 0.f;
+    m = fmaxf(m, e);
+  }
+  block_max_to_global(m, tid, max_bits);
 }
 
 // Candidate ordering.  cv2 sorts all candidates (std::sort, value descending, ties by DESCENDING address) and walks the
@@ -1380,6 +1503,13 @@ static int eigen_map(ofb_handle* h, SparseState* s, int which, int width, int he
   SP_CUDA(h, cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned int), sm));
   // columns past the last full block of 32 take the row filter's scalar tail (no FMA): the same on the AVX2 and the
   // AVX-512 dispatch of the wheel (tests/test_oracle_sparse.py probes both with OPENCV_CPU_DISABLE)
+  if (block_size == 3) {
+    k_sobel_min_eig3<<<dim3((width + kE3T - 1) / kE3T, (height + kE3T - 1) / kE3T), b, 0, sm>>>(
+        s->img[which], width, height, (size_t)width, k0, k1, k2, (width / 32) * 32, s->eig, s->counters + 1, d_mask, harris,
+        (float)harris_k, harris_k);
+    OFB_LAUNCH_CHECK(h);
+    return OFB_OK;
+  }
   const int rb = block_size / 2;
   const size_t smem = (size_t)3 * (32 + 2 * rb) * (kEigTileH + 2 * rb) * sizeof(double);   // 14.7 KB at blockSize 3, 68 KB at 31
   if (smem > 48 * 1024)
