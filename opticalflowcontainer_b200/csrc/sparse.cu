@@ -864,27 +864,50 @@ __global__ void __launch_bounds__(GS_THREADS) k_greedy_select(const unsigned lon
         chain[tid] = (unsigned short)atomicExch(&bucket[bk], (unsigned int)tid);
       }
       __syncthreads();
+      // the earlier survivors within minDistance of this one, found ONCE (the decision loop below re-reads only their
+      // states; walking the nine cells' chains in every iteration was a third of the kernel's instructions, and chains
+      // of mutually close candidates take ten and more iterations).  Up to kNb of them in the sort's exchange buffer;
+      // a survivor with more walks the chains as before.
+      constexpr int kNb = 4;
+      unsigned short* nbl = reinterpret_cast<unsigned short*>(rk2);     // [GS_THREADS][kNb]
+      int ncnt = 0;
+      auto walk = [&](auto&& visit) {
+        const int xc = sx / cell, yc = sy / cell;
+        for (int yy = max(0, yc - 1); yy <= min(gh - 1, yc + 1); yy++)
+          for (int xx = max(0, xc - 1); xx <= min(gw - 1, xc + 1); xx++) {
+            unsigned int k = bucket[((unsigned int)yy * 73u + (unsigned int)xx) & (GS_BUCKETS - 1)];
+            while (k != 0xffffu) {
+              if (k < (unsigned int)tid) {
+                const unsigned int p = surv[k];
+                const float dx = (float)(sx - (int)(p & 0xffffu)), dy = (float)(sy - (int)(p >> 16));
+                if (dx * dx + dy * dy < md2 && visit(k)) return;
+              }
+              k = chain[k];
+            }
+          }
+      };
+      if ((unsigned int)tid < ns)
+        walk([&](unsigned int k) {
+          if (ncnt < kNb) nbl[tid * kNb + ncnt] = (unsigned short)k;
+          ncnt++;
+          return false;
+        });
       for (;;) {
         bool undecided = false;
         if ((unsigned int)tid < ns && state[tid] == 0) {
           bool blocked = false, rejected = false;
-          const int xc = sx / cell, yc = sy / cell;
-          for (int yy = max(0, yc - 1); yy <= min(gh - 1, yc + 1) && !rejected; yy++)
-            for (int xx = max(0, xc - 1); xx <= min(gw - 1, xc + 1) && !rejected; xx++) {
-              unsigned int k = bucket[((unsigned int)yy * 73u + (unsigned int)xx) & (GS_BUCKETS - 1)];
-              while (k != 0xffffu) {
-                if (k < (unsigned int)tid) {
-                  const unsigned int p = surv[k];
-                  const float dx = (float)(sx - (int)(p & 0xffffu)), dy = (float)(sy - (int)(p >> 16));
-                  if (dx * dx + dy * dy < md2) {
-                    const unsigned char sk = *(volatile unsigned char*)&state[k];
-                    if (sk == 1) { rejected = true; break; }
-                    if (sk == 0) blocked = true;
-                  }
-                }
-                k = chain[k];
-              }
-            }
+          auto look = [&](unsigned int k) {
+            const unsigned char sk = *(volatile unsigned char*)&state[k];
+            if (sk == 1) { rejected = true; return true; }
+            if (sk == 0) blocked = true;
+            return false;
+          };
+          if (ncnt <= kNb) {
+            for (int q = 0; q < ncnt; q++)
+              if (look(nbl[tid * kNb + q])) break;
+          } else {
+            walk(look);
+          }
           if (rejected) state[tid] = 2;
           else if (!blocked) state[tid] = 1;
           else undecided = true;
