@@ -517,6 +517,84 @@ def run_tiled(args, rank, local_rank, world):
 
 
 # ------------------------------------------------------------------------------------------ extras of the main line
+def batched_4k_record(rank, local_rank, world, B=18, steps=6, warmup=3):
+    """BASELINE.json config 3: Farneback on 3840x2160 frame pairs, B independent pairs per step per GPU, device-resident,
+    sharded over the ranks without a collective (weak scaling, like the headline).  One pair of the last step is checked
+    against cv2 on rank 0 (about 1.6 s of cv2).  Returns the record on rank 0."""
+    import torch
+    import torch.distributed as dist
+    import opticalflowcontainer_b200 as ofb
+    from oracle import synth
+    W, H = 3840, 2160
+    eng = ofb.FlowEngine(W, H, B, local_rank)
+    t = synth.cheap_texture(H, W, 700 + rank)
+    n_sets = 2                                   # 2 x 199 MB of frames > L2; the step's working set is several GB anyway
+    host = []
+    for s in range(n_sets):
+        fr = np.empty((2 * B, H, W), np.uint8)
+        for i in range(B):
+            fr[i] = np.roll(t, (5 * i + 3 * s, 9 * i + 7 * s), axis=(0, 1))
+        for i in range(B):
+            fr[B + i] = np.roll(fr[i], (1 + (i + s) % 5, -2 - (i % 3)), axis=(0, 1)) if i else synth.subpixel_shift(fr[0], 6.3 - s, -3.6)
+        host.append(fr)
+    dev = [torch.from_numpy(f).cuda() for f in host]
+    d_flow = torch.empty((B, H, W, 2), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.ExternalStream(eng.stream)
+
+    def step(i):
+        p0 = dev[i % n_sets].data_ptr()
+        eng.farneback_device(B, p0, p0 + B * W * H, W, H, W, W * H, d_flow.data_ptr(), **PARAMS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(steps):
+        step(warmup + i)
+    ev1.record(stream)
+    barrier()
+    tms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    rec = None
+    if rank == 0:
+        ms = float(tms.item()) / steps
+        value = B * world / ms * 1e3
+        peaks, _ = measured_peaks()
+        frac = None
+        if peaks.get("hbm_gbs"):
+            frac = algorithmic_bytes_per_pair(W, H) * value / world / 1e9 / peaks["hbm_gbs"]
+        rec = {"metric": "farneback_4k_frame_pairs_per_s", "value": value, "unit": "frame-pairs/s", "n_gpus": world,
+               "steps": steps, "warmup": warmup, "ms_per_step": ms, "pairs_per_step_per_gpu": B, "scaling": "weak",
+               "workload": "farneback_3840x2160_independent_frame_pairs, device-resident, default node params",
+               "pipeline_roofline_frac": frac}
+        try:
+            import cv2
+            last = (warmup + steps - 1) % n_sets
+            a, b = host[last][0], host[last][B]
+            t0 = time.perf_counter()
+            ref = cv2.calcOpticalFlowFarneback(a, b, None, PARAMS["pyr_scale"], PARAMS["levels"], PARAMS["winsize"],
+                                               PARAMS["iterations"], PARAMS["poly_n"], PARAMS["poly_sigma"], PARAMS["flags"])
+            cv_s = time.perf_counter() - t0
+            got = d_flow[0].cpu().numpy()
+            epe = np.sqrt(((got.astype(np.float64) - ref) ** 2).sum(-1))
+            rec["parity"] = {"mean_epe": float(epe.mean()), "max_epe": float(epe.max()), "vs": "cv2 %s, pair 0 of the last timed step" % cv2.__version__,
+                             "cv2_seconds": cv_s, "ok": bool(epe.mean() <= 0.01 and epe.max() <= 0.1)}
+        except ImportError:
+            pass
+    eng.close()
+    del dev, d_flow
+    torch.cuda.empty_cache()
+    return rec
+
+
 def e2e_copy_ceiling(torch, dist, world, h2d_bytes, d2h_bytes, steps=10):
     """Bare pinned-memory copies of one step's traffic (H2D of the frames, D2H of the fields, on two streams, all ranks
     at once): the pairs/s the host link allows with NO kernel at all — the ceiling of the full-field e2e number."""
@@ -795,6 +873,13 @@ def run_ours(args, rank, local_rank, world):
                 extras["around_the_path"] = around_record(local_rank, cpu=not args.no_cpu_baseline)
             except Exception as e:     # (never lose the headline line to a side record)
                 extras["around_the_path"] = {"error": repr(e)}
+        # (3) BASELINE.json config 3: 3840x2160 frame pairs, batched, sharded over the ranks like the 1080p pairs
+        try:
+            rec = batched_4k_record(rank, local_rank, world)
+        except Exception as e:         # (never lose the headline line to a side record)
+            rec = {"error": repr(e)}
+        if rank == 0:
+            extras["batched_4k"] = rec
         # (5) BASELINE.json config 5: one 8K pair tiled over the ranks (needs >= 2 GPUs)
         if world >= 2:
             rec = tiled_record(args, rank, local_rank, world, "8k", steps=20, warmup=3, parity=True, whole=True)
