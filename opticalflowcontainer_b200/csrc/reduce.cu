@@ -43,24 +43,51 @@ __global__ void __launch_bounds__(256) k_sel_hist(const float2* __restrict__ flo
   const uint32_t pa = st[SEL_PREFIX_A], pb = st[SEL_PREFIX_B];
   const int shift_hi = pass == 1 ? 21 : 10;  // bits above the current digit
   double s = 0.0;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < npix; i += gridDim.x * 256) {
-    if (mask && !mask[i]) continue;
-    const float u = f[i].x;
-    const uint32_t k = f2key(u);
-    if (pass == 0) {
-      atomicAdd(&ha[k >> 21], 1u);
-      s += (double)u;
-    } else {
-      const uint32_t hi = k >> shift_hi;
-      const uint32_t dig = pass == 1 ? (k >> 10) & 0x7ffu : k & 0x3ffu;
-      if (hi == pa) atomicAdd(&ha[dig], 1u);
-      if (hi == pb) atomicAdd(&hb[dig], 1u);
+  // A flow field is smooth: the 32 neighbouring pixels of a warp usually fall into the SAME bin of the leading digits
+  // (all of them under a uniform pan), and 32 shared-memory atomics on one address serialise.  One vote tells whether
+  // the warp agrees; then one lane adds 32.  (Otherwise: one atomic per lane, as before.)
+  const int lane = threadIdx.x & 31;
+  auto add = [&](uint32_t* hist, bool pred, uint32_t bin) {
+    int same;
+    __match_all_sync(0xffffffffu, pred ? bin : 0xffffffffu, &same);
+    if (same) {
+      if (pred && lane == 0) atomicAdd(&hist[bin], 32u);
+    } else if (pred) {
+      atomicAdd(&hist[bin], 1u);
+    }
+  };
+  // four 32-pixel groups per warp and step, their loads issued together: one load in flight per thread left the
+  // kernel at 3 TB/s (a pass is nothing but one read of the field)
+  constexpr int UNR = 8;
+  const int warp = threadIdx.x >> 5;
+  for (int base = (blockIdx.x * 8 + warp) * (32 * UNR); base < npix; base += gridDim.x * 8 * 32 * UNR) {   // (uniform over the warp)
+    float u[UNR];
+    bool valid[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      const int i = base + j * 32 + lane;
+      valid[j] = i < npix && !(mask && !mask[i]);
+      u[j] = valid[j] ? f[i].x : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      const uint32_t k = f2key(u[j]);
+      if (pass == 0) {
+        add(ha, valid[j], k >> 21);
+        if (valid[j]) s += (double)u[j];
+      } else {
+        const uint32_t hi = k >> shift_hi;
+        const uint32_t dig = pass == 1 ? (k >> 10) & 0x7ffu : k & 0x3ffu;
+        add(ha, valid[j] && hi == pa, dig);
+        if (pa != pb) add(hb, valid[j] && hi == pb, dig);     // (same prefix — the usual case: hb is ha, see below)
+      }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < SEL_BINS; i += 256) {
     if (ha[i]) atomicAdd(&st[i], ha[i]);
-    if (pass > 0 && hb[i]) atomicAdd(&st[SEL_BINS + i], hb[i]);
+    const uint32_t vb = pa == pb ? ha[i] : hb[i];
+    if (pass > 0 && vb) atomicAdd(&st[SEL_BINS + i], vb);
   }
   if (pass == 0) {
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
