@@ -136,16 +136,21 @@ def test_good_features_unbounded_and_tiny(engine_factory):
     assert len(eng.good_features(np.zeros((100, 2), np.uint8), 10, 0.01, 3, 3)) == 0
 
 
-def test_lk_stream_equals_pair_calls(built_lib):
-    """ofb_lk_stream keeps the previous frame's pyramid, derivatives and corner list on the GPU (one upload per frame):
+@pytest.mark.parametrize("shape,win", [((270, 480), (21, 21)), ((251, 333), (15, 15)), ((251, 333), (11, 13))],
+                         ids=["480x270_win21", "333x251_win15", "333x251_win11x13"])
+def test_lk_stream_equals_pair_calls(built_lib, shape, win):
+    """(The odd frame size takes the one-pixel-per-thread pyrDown / Scharr kernels, the 15x15 window the second
+    instantiation of the CTA-per-point tracker, 11x13 the warp-per-point tracker with a run-time window; the tracking
+    calls after the first two are CUDA-graph replays.)
+    ofb_lk_stream keeps the previous frame's pyramid, derivatives and corner list on the GPU (one upload per frame):
     what it returns for (frame t-1 -> frame t) equals good_features(t-1) + pyrlk(t-1, t) bit for bit, and cv2 within
     the LK gate; a change of parameters or another sparse call on the handle re-primes it."""
     import opticalflowcontainer_b200 as ofb
-    h, w = 270, 480
+    h, w = shape
     base = synth.synth_pair(h, w, 61, (0.0, 0.0))[0]
     fr = [synth.subpixel_shift(base, 1.7 * t, -0.8 * t) for t in range(5)]
     eng, ref = ofb.FlowEngine(w, h, 1, 0), ofb.FlowEngine(w, h, 1, 0)
-    kw = dict(maxCorners=400, qualityLevel=0.01, minDistance=7, blockSize=3, winSize=(21, 21), maxLevel=3,
+    kw = dict(maxCorners=400, qualityLevel=0.01, minDistance=7, blockSize=3, winSize=win, maxLevel=3,
               criteria=(3, 30, 0.01))
     try:
         assert eng.lk_stream(fr[0], **kw) is None
@@ -153,12 +158,12 @@ def test_lk_stream_equals_pair_calls(built_lib):
         for t in range(1, 5):
             prev, nxt, st, err = eng.lk_stream(fr[t], **kw)
             pts = ref.good_features(fr[t - 1], 400, 0.01, 7, 3)
-            want = ref.pyrlk(fr[t - 1], fr[t], pts, None, (21, 21), 3, (3, 30, 0.01))
+            want = ref.pyrlk(fr[t - 1], fr[t], pts, None, win, 3, (3, 30, 0.01))
             assert np.array_equal(prev, pts)
             assert np.array_equal(nxt, want[0]) and np.array_equal(st, want[1]) and np.array_equal(err, want[2])
             cpts = cv2.goodFeaturesToTrack(fr[t - 1], 400, 0.01, 7, blockSize=3)
             assert np.array_equal(prev, cpts)
-            _lk_check(cv2.calcOpticalFlowPyrLK(fr[t - 1], fr[t], cpts, None, winSize=(21, 21), maxLevel=3,
+            _lk_check(cv2.calcOpticalFlowPyrLK(fr[t - 1], fr[t], cpts, None, winSize=win, maxLevel=3,
                                                criteria=(3, 30, 0.01)), (nxt, st, err))
         # another sparse call on the handle re-primes the stream; so does a parameter change
         eng.good_features(fr[0], 10, 0.01, 7, 3)
