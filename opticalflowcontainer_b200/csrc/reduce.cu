@@ -118,30 +118,48 @@ __global__ void __launch_bounds__(256) k_sel_scan(uint32_t* __restrict__ sel, in
     csum[which][threadIdx.x] = c;
   }
   __syncthreads();
-  if (threadIdx.x < 2) {
-    const int which = threadIdx.x;
+  // the bin that holds rank r: prefix sums of the 256 chunk counts over the CTA (warp shuffles + the 8 warp totals), the
+  // one thread whose chunk [exclusive, inclusive) contains r walks its 8 bins (two threads walking 255 chunks one
+  // after the other took ~8 us per launch, three launches per reduction)
+  __shared__ uint32_t wtot[2][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc[2];
+  for (int which = 0; which < 2; which++) {
+    uint32_t v = csum[which][threadIdx.x];
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    inc[which] = v;
+    if (lane == 31) wtot[which][wid] = v;
+  }
+  __syncthreads();
+  for (int which = 0; which < 2; which++) {
+    uint32_t before = 0, cnt = 0;
+    for (int k = 0; k < 8; k++) {
+      if (k < wid) before += wtot[which][k];
+      cnt += wtot[which][k];
+    }
     uint32_t rank;
     if (pass == 0) {
-      uint32_t cnt = 0;
-      for (int i = 0; i < 256; i++) cnt += csum[0][i];
-      if (which == 0) st[SEL_COUNT] = cnt;
+      if (which == 0 && threadIdx.x == 0) st[SEL_COUNT] = cnt;
       rank = cnt ? (which == 0 ? (cnt - 1) / 2 : cnt / 2) : 0;
     } else {
       rank = st[which == 0 ? SEL_RANK_A : SEL_RANK_B];
     }
-    uint32_t acc = 0;
-    int c = 0;
-    for (; c < 255; c++) {
-      if (acc + csum[which][c] > rank) break;
-      acc += csum[which][c];
+    const uint32_t incl = before + inc[which], excl = incl - csum[which][threadIdx.x];
+    // the chunk that contains the rank — or, as the sequential walk did, the last chunk when no count exceeds it
+    const bool mine = cnt > rank ? (excl <= rank && rank < incl) : threadIdx.x == 255;
+    if (mine) {
+      uint32_t acc = excl;
+      int b = threadIdx.x * 8;
+      for (; b < threadIdx.x * 8 + 7; b++) {
+        if (acc + sh[which][b] > rank) break;
+        acc += sh[which][b];
+      }
+      res[which * 2] = (uint32_t)b;
+      res[which * 2 + 1] = rank - acc;
     }
-    int b = c * 8;
-    for (; b < c * 8 + 7; b++) {
-      if (acc + sh[which][b] > rank) break;
-      acc += sh[which][b];
-    }
-    res[which * 2] = (uint32_t)b;
-    res[which * 2 + 1] = rank - acc;
   }
   __syncthreads();
   const uint32_t pa = st[SEL_PREFIX_A], pb = st[SEL_PREFIX_B];
