@@ -923,8 +923,9 @@ def run_ours(args, rank, local_rank, world):
                 "parallelism": "frame-pair sharding x%d, no collective" % world,
                 "l2": "inputs rotate over %d frame sets (%.0f MB > 2x L2); per-step working set %.0f MB >> L2"
                       % (n_sets, n_sets * frames_per_set * istride / 1e6, B * 232.0 * W_ * H_ / 2073600.0),
-                "note": "a step = ONE launch sequence over %d independent pairs (the batch fills the 296 resident CTA "
-                        "slots of the iteration kernel); one pair per call is reported under batch1" % B},
+                "note": "a step = ONE launch sequence over %d independent pairs (36 pairs x 8 strips = 288 of the 296 "
+                        "resident CTA slots of the iteration kernel at level 0, one row segment each; 18 pairs per step "
+                        "run 2-3 %% slower, 54 no faster); one pair per call is reported under batch1" % B},
         "roofline": {"bound": "hbm", "kernel": "k_iter_v, level-0 launch (UpdateMatrices + box blur + 2x2 solve fused)",
                      "achieved": it_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": it_gbs / peaks["hbm_gbs"],
                      "traffic": traffic, "peak_source": peak_src,
@@ -977,7 +978,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # 18 pairs: the level-0 launch of the iteration kernel is 8 strips x 2 row segments x 18 pairs = 288 CTAs on
     # the 296 resident CTA slots of a B200 (16 pairs leave 40 slots, i.e. 40 SMs half empty)
-    ap.add_argument("--batch", type=int, default=18, help="frame pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=36, help="frame pairs per step per GPU")
     ap.add_argument("--frame", default="1080p", choices=["vga", "1080p", "4k"],
                     help="frame size of the pairs/sequence modes (1080p = the BASELINE.json metric; vga = config 0, 4k = config 3)")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "sequence", "stream", "tiled", "lk"],
