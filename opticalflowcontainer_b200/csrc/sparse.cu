@@ -15,7 +15,8 @@
 // (k_candidates / k_bucket_scan / k_bucket_scatter + an in-CTA bitonic sort per selection round) — the
 // greedy selection stops at maxCorners, so only the strongest few thousand candidates are ever sorted.
 // ofb_lk_stream keeps a camera's temporal state (previous frame's pyramid, Scharr derivatives and corner
-// list) on the GPU: one upload per frame.
+// list) on the GPU: one upload per frame; behind the upload the tracker and the new frame's corner detection run as two
+// chains on two streams, captured once per frame slot into a CUDA graph.
 #include <algorithm>
 #include <type_traits>
 
